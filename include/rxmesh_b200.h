@@ -1,0 +1,160 @@
+/*
+ * rxmesh_b200.h -- the C ABI of librxmesh_b200.so (B200 / sm_100a).
+ *
+ * The reference (owensgroup/RXMesh) has no FFI: its boundary is a C++ template
+ * API compiled into the user's .cu.  This header is the thin
+ * C-ABI layer that the drop-in C++ shim (include/rxmesh/ *.h, same class names
+ * as the reference) and the Python host mirror (rxmesh_b200/) call.  Every
+ * entry point names the reference interface it replaces; paths are relative to
+ * /root/reference/include/rxmesh unless stated otherwise.
+ *
+ * Conventions: plain pointers and sizes only; every function that can fail
+ * returns an int status (0 = RXM_OK) and records a thread-local message readable
+ * through rxm_last_error(); `stream` is a cudaStream_t passed as void* (NULL =
+ * default stream).  The reference's CUDA_ERROR macro logs and exit()s
+ * (util/macros.h:77-89); this ABI returns the error instead, the C++ shim
+ * restores the reference behaviour.
+ */
+#ifndef RXMESH_B200_H
+#define RXMESH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RXM_OK 0
+#define RXM_ERR_INVALID 1   /* bad argument */
+#define RXM_ERR_CUDA 2      /* CUDA runtime / driver error (no device, launch failure ...) */
+#define RXM_ERR_UNSUPPORTED 3
+
+/* element types and query ops: numeric values of the reference's Op enum (types.h:113-129) */
+enum { RXM_V = 0, RXM_E = 1, RXM_F = 2 };
+enum { RXM_OP_VV = 3, RXM_OP_VE = 4, RXM_OP_VF = 5, RXM_OP_FV = 6, RXM_OP_FE = 7, RXM_OP_FF = 8,
+       RXM_OP_EV = 9, RXM_OP_EF = 11 };
+/* locationT (types.h:51-58) and layoutT (types.h:84-90) */
+enum { RXM_HOST = 0x01, RXM_DEVICE = 0x02, RXM_LOCATION_ALL = 0x0F };
+enum { RXM_AOS = 0, RXM_AOSOA = 1, RXM_SOA = 2 };
+
+typedef struct rxm_mesh rxm_mesh; /* RXMeshStatic (rxmesh_static.h:37) */
+typedef struct rxm_attr rxm_attr; /* Attribute<T,HandleT> (attribute.h:56) */
+
+const char* rxm_last_error(void);
+const char* rxm_version(void);
+
+/* rx_init(device) (rxmesh.h:23-30): select the device, verify it is sm_100. */
+int rxm_init(int device);
+
+/* ---------------------------------------------------------------- mesh ---- */
+/* RXMeshStatic(fv, patcher_file, patch_size, ...) (rxmesh_static.h:61-100; rxmesh.cpp:89-225).
+ * fv: 3*num_faces zero-based vertex ids.  face_patch: NULL -> run the built-in Lloyd patcher
+ * (patcher/patcher.cu:828-987); otherwise a face -> patch assignment to honour, the analogue of
+ * constructing from a saved `patcher_file`.  Host-only work: succeeds without a GPU. */
+int rxm_mesh_create(const uint32_t* fv, uint32_t num_faces, const uint32_t* face_patch, uint32_t patch_size,
+                    int num_threads, rxm_mesh** out);
+/* RXMesh::build_device (rxmesh.cpp:1139-1615): upload the patch store to the current device. */
+int rxm_mesh_to_device(rxm_mesh* m);
+/* ~RXMesh (rxmesh.cpp:227-288) */
+void rxm_mesh_destroy(rxm_mesh* m);
+
+/* getters (rxmesh.h:44-399). `what` keys: */
+enum {
+    RXM_INFO_NUM_VERTICES = 0, RXM_INFO_NUM_EDGES = 1, RXM_INFO_NUM_FACES = 2, RXM_INFO_NUM_PATCHES = 3,
+    RXM_INFO_PATCH_SIZE = 4, RXM_INFO_MAX_VALENCE = 5, RXM_INFO_MAX_EDGE_INCIDENT_FACES = 6,
+    RXM_INFO_MAX_FACE_ADJACENT_FACES = 7, RXM_INFO_IS_CLOSED = 8, RXM_INFO_IS_EDGE_MANIFOLD = 9,
+    RXM_INFO_MAX_VERTICES_PER_PATCH = 10, RXM_INFO_MAX_EDGES_PER_PATCH = 11, RXM_INFO_MAX_FACES_PER_PATCH = 12,
+    RXM_INFO_NUM_SLOTS_V = 13, RXM_INFO_NUM_SLOTS_E = 14, RXM_INFO_NUM_SLOTS_F = 15,
+    RXM_INFO_TOPO_BYTES = 16, RXM_INFO_TOTAL_LOCAL_V = 17, RXM_INFO_TOTAL_LOCAL_E = 18,
+    RXM_INFO_TOTAL_LOCAL_F = 19, RXM_INFO_MAX_STASH = 20, RXM_INFO_ON_DEVICE = 21
+};
+uint64_t rxm_mesh_info(const rxm_mesh* m, int what);
+double   rxm_mesh_build_seconds(const rxm_mesh* m, int patcher_only);
+
+/* per-patch host view (PatchInfo, patch_info.h:24-92 + m_h_patches_ltog_*, rxmesh.h:598-640).
+ * Pointers stay valid until rxm_mesh_destroy. */
+typedef struct {
+    uint32_t        patch_id;
+    uint32_t        n[3];        /* #V,#E,#F incl. ribbon */
+    uint32_t        n_owned[3];
+    uint32_t        slot_base[3];
+    uint32_t        lin_base[3];
+    const uint16_t* ev;          /* 2*n[E]: local (larger-id vertex, smaller-id vertex) */
+    const uint16_t* fe;          /* 3*n[F]: (local edge << 1) | dir */
+    const uint16_t* fv;          /* 3*n[F] */
+    const uint32_t* owner[3];    /* n[t]-n_owned[t]: (stash slot << 16) | local id in owner */
+    const uint32_t* stash;       /* 4*n_stash u32: patch, slot base V, E, F */
+    uint32_t        n_stash;
+    const uint32_t* ltog[3];     /* n[t] global ids (owned first, each half ascending) */
+} rxm_patch_view;
+int rxm_mesh_patch(const rxm_mesh* m, uint32_t patch, rxm_patch_view* out);
+
+/* flat host id maps: slot -> global id (0xFFFFFFFF for padding), global -> slot, element -> owner patch
+ * (map_to_global / linear_id / get_owner_handle, rxmesh_static.cu:669-685, context.h:218-331) */
+const uint32_t* rxm_mesh_slot_to_global(const rxm_mesh* m, int elem);
+const uint32_t* rxm_mesh_global_to_slot(const rxm_mesh* m, int elem);
+const uint32_t* rxm_mesh_elem_patch(const rxm_mesh* m, int elem);
+const uint32_t* rxm_mesh_slot_base(const rxm_mesh* m, int elem); /* [num_patches+1] */
+const uint32_t* rxm_mesh_lin_base(const rxm_mesh* m, int elem);  /* [num_patches+1] */
+/* global edge list in the reference's numbering: 2*E (larger id, smaller id); 3*F edge ids */
+const uint32_t* rxm_mesh_edges(const rxm_mesh* m);
+const uint32_t* rxm_mesh_face_edges(const rxm_mesh* m);
+
+/* prepare_launch_box / calc_shared_memory (rxmesh_static.inl:443-841): dynamic shared memory bytes and
+ * grid size the query kernel for `op` uses on this mesh. */
+int rxm_mesh_launch_box(const rxm_mesh* m, int op, uint32_t* blocks, uint32_t* threads, uint32_t* smem_bytes);
+
+/* ----------------------------------------------------------- attributes ---- */
+/* add_{vertex,edge,face}_attribute<T>(name, n, location, layout) (rxmesh_static.h:608-806; attribute.cu:30-83,
+ * 531-590). elem_bytes in {1,2,4,8}. Storage holds owned elements only: num_slots(elem) * num_attr values. */
+int rxm_attr_create(rxm_mesh* m, int elem, uint32_t elem_bytes, uint32_t num_attr, int location, int layout,
+                    rxm_attr** out);
+void     rxm_attr_destroy(rxm_attr* a);                                /* remove_attribute / release */
+void*    rxm_attr_data(rxm_attr* a, int location);                     /* Attribute::data(location) */
+uint64_t rxm_attr_count(const rxm_attr* a);                            /* num_slots * num_attr */
+int      rxm_attr_reset(rxm_attr* a, const void* value, int location, void* stream); /* attribute.cu:306-357 */
+int      rxm_attr_move(rxm_attr* a, int source, int target, void* stream);           /* attribute.cu:359-364 */
+int      rxm_attr_copy_from(rxm_attr* dst, rxm_attr* src, int source, int target, void* stream);
+/* add_vertex_attribute(Verts, name): fill from / read back to an array in GLOBAL element order
+ * ([num_elems][num_attr], AoS), the role of rxmesh_static.inl:147-189 and of the
+ * for_each_vertex(HOST, map_to_global) read-back loops of the apps. Host buffers; copies + a device
+ * permutation kernel run on `stream`. */
+int rxm_attr_upload_global(rxm_attr* a, const void* host_global, void* stream);
+int rxm_attr_download_global(rxm_attr* a, void* host_global, void* stream);
+/* same with DEVICE buffers in global order (no host copy) */
+int rxm_attr_from_global_device(rxm_attr* a, const void* dev_global, void* stream);
+int rxm_attr_to_global_device(rxm_attr* a, void* dev_global, void* stream);
+
+/* ----------------------------------------------------- fixed-function hot path ---- */
+/* The reference's query test kernel (tests/RXMesh_test/query_kernel.cuh:13-46 through
+ * Query::dispatch, query.inl:107-156): in(h)=h, out(h,i)=iter[i] as 64-bit handles
+ * (patch_id << 32 | local id, handle.h:19-41). in: 1 x u64 on the source element type; out: W x u64. */
+int rxm_query_store(rxm_mesh* m, int op, rxm_attr* in, rxm_attr* out, void* stream);
+/* roofline "consume" variant: out(s) = sum_i in(iter[i]); in: 1 x fp32 on the op's output element type,
+ * out: 1 x fp32 on its source element type. */
+int rxm_query_consume(rxm_mesh* m, int op, rxm_attr* in, rxm_attr* out, void* stream);
+/* compute_vertex_normal (apps/VertexNormal/vertex_normal_kernel.cuh:10-43), coords/normals: 3 x fp32 AoS.
+ * unit_face_normals != 0 -> the Filtering variant (apps/Filtering/filtering_rxmesh_kernel.cuh:15-46). */
+int rxm_vertex_normals(rxm_mesh* m, rxm_attr* coords, rxm_attr* normals, int unit_face_normals, void* stream);
+/* manual smoothing (apps/Smoothing/manual.h:86-104): `iters` Jacobi steps x <- x - lr * sum_u 2(x - x_u);
+ * result in `out` (may not alias `in`). */
+int rxm_laplacian_smooth(rxm_mesh* m, rxm_attr* in, rxm_attr* out, double lr, uint32_t iters, void* stream);
+/* bilateral filtering (apps/Filtering/filtering_rxmesh.cuh:75-95): `iters` iterations of
+ * unit-face vertex normals + bilateral_filtering; result in `out`. */
+int rxm_bilateral_filter(rxm_mesh* m, rxm_attr* in, rxm_attr* out, uint32_t iters, void* stream);
+/* get_boundary_vertices (rxmesh_static.h; kernels/boundary.cuh:11-44): flag: 1 x u32 vertex attribute, 1 = boundary */
+int rxm_boundary_vertices(rxm_mesh* m, rxm_attr* flag, void* stream);
+
+/* host-buffer entry points (what bench.py times as `e2e`): H2D + kernel(s) + D2H inside the call,
+ * arrays in GLOBAL vertex order, [V][3] fp32. */
+int rxm_vertex_normals_host(rxm_mesh* m, const float* coords, float* normals, void* stream);
+int rxm_laplacian_smooth_host(rxm_mesh* m, const float* coords, float* out, double lr, uint32_t iters, void* stream);
+
+/* kernels launched by this library so far (bench.py "gpu_launches") */
+uint64_t rxm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RXMESH_B200_H */

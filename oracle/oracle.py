@@ -1,0 +1,218 @@
+"""ctypes/numpy front-end of oracle/rxmesh_oracle.c and oracle/_ref (TEST INFRASTRUCTURE ONLY).
+
+Each wrapper names the C function it calls; the C functions cite the reference
+file:line they restate.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_REF = None
+
+u32p = C.POINTER(C.c_uint32)
+f32p = C.POINTER(C.c_float)
+f64p = C.POINTER(C.c_double)
+u8p = C.POINTER(C.c_uint8)
+
+
+def build(force=False):
+    """Compile librxmesh_oracle.so (and _ref/ when /root/reference exists)."""
+    so = os.path.join(_HERE, "librxmesh_oracle.so")
+    src = os.path.join(_HERE, "rxmesh_oracle.c")
+    need = force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src)
+    ref_so = os.path.join(_HERE, "_ref", "libvn_ref.so")
+    if os.path.isdir("/root/reference/apps/VertexNormal") and not os.path.exists(ref_so):
+        need = True
+    if need:
+        subprocess.check_call(["make", "-s", "-C", _HERE, "all"], stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        build()
+        _LIB = C.CDLL(os.path.join(_HERE, "librxmesh_oracle.so"))
+        _LIB.rxo_build_edges.restype = C.c_uint32
+        _LIB.rxo_query_ff.restype = C.c_uint64
+        _LIB.rxo_boundary_vertices.restype = C.c_uint32
+        _LIB.rxo_bilateral_step.restype = C.c_uint32
+    return _LIB
+
+
+def ref_lib():
+    """The reference's own vertex_normal_ref.h compiled unmodified (None if absent)."""
+    global _REF
+    if _REF is None:
+        build()
+        p = os.path.join(_HERE, "_ref", "libvn_ref.so")
+        if not os.path.exists(p):
+            return None
+        _REF = C.CDLL(p)
+        _REF.ref_vertex_normal_f32_timed.restype = C.c_double
+    return _REF
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Topology:
+    """Global edge numbering + FE of a triangle soup (rxo_build_edges)."""
+
+    def __init__(self, fv):
+        self.fv = _u32(fv).reshape(-1, 3)
+        nf = self.fv.shape[0]
+        ev = np.empty((max(3 * nf, 1), 2), dtype=np.uint32)
+        self.fe = np.empty((nf, 3), dtype=np.uint32)
+        nv = C.c_uint32(0)
+        ne = lib().rxo_build_edges(_p(self.fv, u32p), nf, _p(ev, u32p), _p(self.fe, u32p),
+                                   C.byref(nv))
+        self.ev = np.ascontiguousarray(ev[:ne])
+        self.nf, self.ne, self.nv = nf, int(ne), int(nv.value)
+
+    # --- the eight queries, as CSR (offsets, values) over global ids ---
+    def _csr(self, fn, rows, nrows, ncols, nnz):
+        off = np.empty(ncols + 1, dtype=np.uint32)
+        val = np.empty(max(nnz, 1), dtype=np.uint32)
+        fn(_p(rows, u32p), nrows, ncols, _p(off, u32p), _p(val, u32p))
+        return off, val[:nnz]
+
+    def query(self, op):
+        op = op.upper()
+        L = lib()
+        if op == "VV":
+            return self._csr(L.rxo_query_vv, self.ev, self.ne, self.nv, 2 * self.ne)
+        if op == "VE":
+            return self._csr(L.rxo_query_ve, self.ev, self.ne, self.nv, 2 * self.ne)
+        if op == "VF":
+            return self._csr(L.rxo_query_vf, self.fv, self.nf, self.nv, 3 * self.nf)
+        if op == "EF":
+            return self._csr(L.rxo_query_ef, self.fe, self.nf, self.ne, 3 * self.nf)
+        if op == "EV":
+            return np.arange(0, 2 * self.ne + 1, 2, dtype=np.uint32), self.ev.reshape(-1).copy()
+        if op == "FV":
+            return np.arange(0, 3 * self.nf + 1, 3, dtype=np.uint32), self.fv.reshape(-1).copy()
+        if op == "FE":
+            return np.arange(0, 3 * self.nf + 1, 3, dtype=np.uint32), self.fe.reshape(-1).copy()
+        if op == "FF":
+            off = np.empty(self.nf + 1, dtype=np.uint32)
+            nnz = L.rxo_query_ff(_p(self.fe, u32p), self.nf, self.ne, _p(off, u32p), None)
+            val = np.empty(max(int(nnz), 1), dtype=np.uint32)
+            L.rxo_query_ff(_p(self.fe, u32p), self.nf, self.ne, _p(off, u32p), _p(val, u32p))
+            return off, val[:int(nnz)]
+        raise ValueError(op)
+
+    def boundary_vertices(self):
+        flags = np.zeros(max(self.nv, 1), dtype=np.uint8)
+        n = lib().rxo_boundary_vertices(_p(self.ev, u32p), _p(self.fe, u32p), self.nf, self.ne,
+                                        self.nv, _p(flags, u8p))
+        return int(n), flags[:self.nv].astype(bool)
+
+    def stats(self):
+        out = np.zeros(5, dtype=np.uint32)
+        lib().rxo_input_stats(_p(self.ev, u32p), _p(self.fe, u32p), self.nf, self.ne, self.nv,
+                              _p(out, u32p))
+        return dict(max_valence=int(out[0]), max_edge_incident_faces=int(out[1]),
+                    max_face_adjacent_faces=int(out[2]), is_closed=bool(out[3]),
+                    is_edge_manifold=bool(out[4]))
+
+
+def vertex_normals(fv, x, dtype=np.float32):
+    """rxo_vertex_normals_f32 / _f64 (apps/VertexNormal/vertex_normal_ref.h:5-85)."""
+    fv = _u32(fv).reshape(-1, 3)
+    x = _f32(x).reshape(-1, 3)
+    if dtype == np.float32:
+        n = np.empty_like(x)
+        lib().rxo_vertex_normals_f32(_p(fv, u32p), fv.shape[0], _p(x, f32p), x.shape[0], _p(n, f32p))
+    else:
+        n = np.empty(x.shape, dtype=np.float64)
+        lib().rxo_vertex_normals_f64(_p(fv, u32p), fv.shape[0], _p(x, f32p), x.shape[0], _p(n, f64p))
+    return n
+
+
+def ref_vertex_normals(fv, x, repeats=0):
+    """The reference's own loop from oracle/_ref. repeats>0 -> (normals, seconds per run)."""
+    R = ref_lib()
+    if R is None:
+        raise RuntimeError("oracle/_ref/libvn_ref.so not built (needs /root/reference)")
+    fv = _u32(fv).reshape(-1, 3)
+    x = _f32(x).reshape(-1, 3)
+    n = np.empty_like(x)
+    if repeats:
+        t = R.ref_vertex_normal_f32_timed(_p(fv, u32p), fv.shape[0], _p(x, f32p), x.shape[0],
+                                          _p(n, f32p), int(repeats))
+        return n, float(t)
+    R.ref_vertex_normal_f32(_p(fv, u32p), fv.shape[0], _p(x, f32p), x.shape[0], _p(n, f32p))
+    return n
+
+
+def vertex_normals_unit_faces(fv, x, dtype=np.float64):
+    """rxo_vertex_normals_unit_faces (apps/Filtering/filtering_rxmesh_kernel.cuh:15-46)."""
+    fv = _u32(fv).reshape(-1, 3)
+    x = _f32(x).reshape(-1, 3)
+    if dtype == np.float32:
+        n = np.empty_like(x)
+        lib().rxo_vertex_normals_unit_faces(_p(fv, u32p), fv.shape[0], _p(x, f32p), x.shape[0],
+                                            _p(n, f32p), None)
+    else:
+        n = np.empty(x.shape, dtype=np.float64)
+        lib().rxo_vertex_normals_unit_faces(_p(fv, u32p), fv.shape[0], _p(x, f32p), x.shape[0],
+                                            None, _p(n, f64p))
+    return n
+
+
+def laplacian_step(vv, x, lr, dtype=np.float32):
+    """rxo_laplacian_step_f32/_f64 (apps/Smoothing/manual.h:86-104)."""
+    off, val = vv
+    if dtype == np.float32:
+        x = _f32(x).reshape(-1, 3)
+        out = np.empty_like(x)
+        lib().rxo_laplacian_step_f32(_p(off, u32p), _p(val, u32p), x.shape[0], _p(x, f32p),
+                                     _p(out, f32p), C.c_double(lr))
+    else:
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 3)
+        out = np.empty_like(x)
+        lib().rxo_laplacian_step_f64(_p(off, u32p), _p(val, u32p), x.shape[0], _p(x, f64p),
+                                     _p(out, f64p), C.c_double(lr))
+    return out
+
+
+def bilateral_step(vv, fv, x, max_nbrs=80, use_f64=True):
+    """One bilateral iteration = unit-face normals + rxo_bilateral_step
+    (apps/Filtering/filtering_rxmesh.cuh:75-95). Returns (x_new, max neighbourhood)."""
+    off, val = vv
+    x = _f32(x).reshape(-1, 3)
+    n = vertex_normals_unit_faces(fv, x, np.float64)
+    out = np.empty_like(x)
+    worst = lib().rxo_bilateral_step(_p(off, u32p), _p(val, u32p), x.shape[0], _p(x, f32p),
+                                     _p(n, f64p), _p(out, f32p), int(max_nbrs), int(use_f64))
+    return out, int(worst)
+
+
+def consume_sum(csr, src):
+    """rxo_consume_sum: out[s] = sum_{t in list(s)} src[t] in float64."""
+    off, val = csr
+    src = _f32(src)
+    out = np.empty(off.shape[0] - 1, dtype=np.float64)
+    lib().rxo_consume_sum(_p(off, u32p), _p(val, u32p), off.shape[0] - 1, _p(src, f32p),
+                          _p(out, f64p))
+    return out
+
+
+def csr_to_sets(csr):
+    """list of sorted tuples (multiset per source element) for set-equality checks."""
+    off, val = csr
+    return [tuple(sorted(val[off[i]:off[i + 1]].tolist())) for i in range(off.shape[0] - 1)]

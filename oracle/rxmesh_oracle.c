@@ -1,0 +1,523 @@
+/*
+ * rxmesh_oracle.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * A plain-C, CPU restatement of the reference algorithms on the hot path named
+ * by BASELINE.json:north_star (static connectivity queries + vertex normals +
+ * Laplacian / bilateral smoothing).  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load this library; the
+ * product path (rxmesh_b200/) never links, imports or calls it.
+ *
+ * Every function cites the reference file:line (relative to /root/reference)
+ * whose behaviour it restates.  Nothing here is copied from the reference: the
+ * reference builds std::unordered_map / vector<vector<>> structures, this file
+ * works on flat arrays with an open-addressing table.
+ *
+ * Pinning (see oracle/README.md and tests/test_oracle.py):
+ *   - normals:   pinned bit-for-bit against the reference's own
+ *                apps/VertexNormal/vertex_normal_ref.h compiled UNMODIFIED into
+ *                oracle/_ref/ (fixtures tests/golden/*_vn_ref.npy) and against
+ *                the SURVEY.md 8(c) checksums.
+ *   - queries:   pinned by the reference's known-answer tests (cube.obj counts
+ *                test_for_each.cu:25-29, bunnyhead.obj 98 boundary vertices
+ *                test_boundary.cu:27) and the ground-truth construction of
+ *                tests/RXMesh_test/rxmesh_test.h:65-339 which this restates.
+ *   - laplacian: PARITY UNPINNED (the reference app has no check);
+ *                apps/Smoothing/manual.h:86-104 is the spec.
+ *   - bilateral: weakly pinned (the only reference check is abs 1e-2 against
+ *                OpenMesh, apps/Filtering/filtering_rxmesh.cuh:114-125; OpenMesh
+ *                8.1 is not in the tree).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define RXO_INVALID32 0xFFFFFFFFu
+
+/* ------------------------------------------------------------------------ */
+/* Edge numbering.                                                           */
+/* rxmesh.cpp:589-611: scan faces f = 0..F-1, corners (v, (v+1)%3); the key  */
+/* is (max, min) (util/util.h:410-416); an edge id is its order of first     */
+/* appearance.  ev_out[2e] = max id, ev_out[2e+1] = min id, which is the      */
+/* order the EV ground truth uses (rxmesh_test.h:207-211).                    */
+/* fe_out[3f+j] = id of edge (fv[3f+j], fv[3f+(j+1)%3]) (rxmesh_test.h:22-38). */
+/* ------------------------------------------------------------------------ */
+typedef struct
+{
+    uint64_t* keys;
+    uint32_t* vals;
+    uint64_t  mask;
+} rxo_table;
+
+static uint64_t rxo_mix(uint64_t x)
+{
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+
+/* returns number of edges; *num_vertices = max vertex id + 1 (rxmesh.cpp:602,640) */
+uint32_t rxo_build_edges(const uint32_t* fv,
+                         uint32_t        nf,
+                         uint32_t*       ev_out, /* capacity 2*3*nf */
+                         uint32_t*       fe_out, /* 3*nf */
+                         uint32_t*       num_vertices)
+{
+    uint64_t cap = 16;
+    while (cap < (uint64_t)nf * 6u + 8u)
+        cap <<= 1;
+    rxo_table t;
+    t.keys = (uint64_t*)malloc(cap * sizeof(uint64_t));
+    t.vals = (uint32_t*)malloc(cap * sizeof(uint32_t));
+    t.mask = cap - 1;
+    memset(t.keys, 0xFF, cap * sizeof(uint64_t));
+
+    uint32_t ne = 0, nv = 0;
+    for (uint32_t f = 0; f < nf; ++f) {
+        for (uint32_t j = 0; j < 3; ++j) {
+            uint32_t v0 = fv[3 * (uint64_t)f + j];
+            uint32_t v1 = fv[3 * (uint64_t)f + (j + 1) % 3];
+            if (v0 > nv) nv = v0;
+            if (v1 > nv) nv = v1;
+            uint32_t hi  = v0 > v1 ? v0 : v1;
+            uint32_t lo  = v0 > v1 ? v1 : v0;
+            uint64_t key = ((uint64_t)hi << 32) | lo;
+            uint64_t h   = rxo_mix(key) & t.mask;
+            while (t.keys[h] != key && t.keys[h] != ~0ULL)
+                h = (h + 1) & t.mask;
+            if (t.keys[h] == ~0ULL) {
+                t.keys[h]          = key;
+                t.vals[h]          = ne;
+                ev_out[2 * (uint64_t)ne]     = hi;
+                ev_out[2 * (uint64_t)ne + 1] = lo;
+                ++ne;
+            }
+            fe_out[3 * (uint64_t)f + j] = t.vals[h];
+        }
+    }
+    free(t.keys);
+    free(t.vals);
+    *num_vertices = nf ? nv + 1 : 0;
+    return ne;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Generic CSR transpose helper: rows of fixed degree `deg` with column ids    */
+/* in `rows`; pushes row id r onto column rows[r*deg+k] in (r, k) scan order,  */
+/* which is the push_back order of the reference ground truth.                */
+/* ------------------------------------------------------------------------ */
+static void rxo_transpose(const uint32_t* rows,
+                          uint32_t        nrows,
+                          uint32_t        deg,
+                          uint32_t        ncols,
+                          uint32_t*       off, /* ncols+1 */
+                          uint32_t*       val) /* nrows*deg */
+{
+    memset(off, 0, ((size_t)ncols + 1) * sizeof(uint32_t));
+    for (uint64_t i = 0; i < (uint64_t)nrows * deg; ++i)
+        off[rows[i] + 1]++;
+    for (uint32_t c = 0; c < ncols; ++c)
+        off[c + 1] += off[c];
+    uint32_t* cur = (uint32_t*)malloc(((size_t)ncols + 1) * sizeof(uint32_t));
+    memcpy(cur, off, ((size_t)ncols + 1) * sizeof(uint32_t));
+    for (uint32_t r = 0; r < nrows; ++r)
+        for (uint32_t k = 0; k < deg; ++k)
+            val[cur[rows[(uint64_t)r * deg + k]]++] = r;
+    free(cur);
+}
+
+/* VE ground truth: rxmesh_test.h:137-160 (v_e[first].push(e); v_e[second].push(e)). */
+void rxo_query_ve(const uint32_t* ev, uint32_t ne, uint32_t nv, uint32_t* off, uint32_t* val)
+{
+    rxo_transpose(ev, ne, 2, nv, off, val);
+}
+
+/* VV ground truth: rxmesh_test.h:65-83 (v_v[first].push(second) and vice versa). */
+void rxo_query_vv(const uint32_t* ev, uint32_t ne, uint32_t nv, uint32_t* off, uint32_t* val)
+{
+    rxo_transpose(ev, ne, 2, nv, off, val);
+    /* replace edge id by the other endpoint; entries of column v hold edges
+     * incident to v. */
+    for (uint32_t v = 0; v < nv; ++v)
+        for (uint32_t i = off[v]; i < off[v + 1]; ++i) {
+            uint32_t e = val[i];
+            val[i]     = (ev[2 * (uint64_t)e] == v) ? ev[2 * (uint64_t)e + 1] : ev[2 * (uint64_t)e];
+        }
+}
+
+/* VF ground truth: rxmesh_test.h:165-193. */
+void rxo_query_vf(const uint32_t* fv, uint32_t nf, uint32_t nv, uint32_t* off, uint32_t* val)
+{
+    rxo_transpose(fv, nf, 3, nv, off, val);
+}
+
+/* EF ground truth: rxmesh_test.h:228-252 (faces in order, edges of FE). */
+void rxo_query_ef(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t* off, uint32_t* val)
+{
+    rxo_transpose(fe, nf, 3, ne, off, val);
+}
+
+/* FF ground truth: rxmesh_test.h:292-339: for every edge, every unordered pair
+ * of incident faces (f0,f1) contributes f1 to f_f[f0] and f0 to f_f[f1]
+ * (multiplicity kept: two faces sharing two edges list each other twice).
+ * Returns nnz; val must have capacity for it (call with val==NULL to count). */
+uint64_t rxo_query_ff(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t* off, uint32_t* val)
+{
+    uint32_t* eoff = (uint32_t*)malloc(((size_t)ne + 1) * sizeof(uint32_t));
+    uint32_t* eval = (uint32_t*)malloc((size_t)nf * 3 * sizeof(uint32_t) + 4);
+    rxo_transpose(fe, nf, 3, ne, eoff, eval);
+    memset(off, 0, ((size_t)nf + 1) * sizeof(uint32_t));
+    for (uint32_t e = 0; e < ne; ++e) {
+        uint32_t k = eoff[e + 1] - eoff[e];
+        for (uint32_t i = eoff[e]; i < eoff[e + 1]; ++i)
+            off[eval[i] + 1] += k - 1;
+    }
+    for (uint32_t f = 0; f < nf; ++f)
+        off[f + 1] += off[f];
+    uint64_t nnz = off[nf];
+    if (val) {
+        uint32_t* cur = (uint32_t*)malloc(((size_t)nf + 1) * sizeof(uint32_t));
+        memcpy(cur, off, ((size_t)nf + 1) * sizeof(uint32_t));
+        for (uint32_t e = 0; e < ne; ++e)
+            for (uint32_t i = eoff[e]; i + 1 < eoff[e + 1]; ++i)
+                for (uint32_t j = i + 1; j < eoff[e + 1]; ++j) {
+                    uint32_t f0 = eval[i], f1 = eval[j];
+                    val[cur[f0]++] = f1;
+                    val[cur[f1]++] = f0;
+                }
+        free(cur);
+    }
+    free(eoff);
+    free(eval);
+    return nnz;
+}
+
+/* Boundary vertices: kernels/boundary.cuh:11-44 -- an edge with exactly one
+ * incident face marks both its vertices.  Returns the count, flags[v] in {0,1}. */
+uint32_t rxo_boundary_vertices(const uint32_t* ev, const uint32_t* fe, uint32_t nf, uint32_t ne,
+                               uint32_t nv, uint8_t* flags)
+{
+    uint32_t* cnt = (uint32_t*)calloc(ne ? ne : 1, sizeof(uint32_t));
+    for (uint64_t i = 0; i < (uint64_t)nf * 3; ++i)
+        cnt[fe[i]]++;
+    memset(flags, 0, nv);
+    for (uint32_t e = 0; e < ne; ++e)
+        if (cnt[e] == 1) {
+            flags[ev[2 * (uint64_t)e]]     = 1;
+            flags[ev[2 * (uint64_t)e + 1]] = 1;
+        }
+    uint32_t n = 0;
+    for (uint32_t v = 0; v < nv; ++v)
+        n += flags[v];
+    free(cnt);
+    return n;
+}
+
+/* Input statistics of rxmesh.cpp:560-650: max valence, max faces per edge,
+ * max adjacent faces per face, closed, edge-manifold. out[5]. */
+void rxo_input_stats(const uint32_t* ev, const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t nv,
+                     uint32_t* out)
+{
+    uint32_t* cnt = (uint32_t*)calloc(ne ? ne : 1, sizeof(uint32_t));
+    uint32_t* val = (uint32_t*)calloc(nv ? nv : 1, sizeof(uint32_t));
+    for (uint64_t i = 0; i < (uint64_t)nf * 3; ++i)
+        cnt[fe[i]]++;
+    uint32_t max_val = 0, max_ef = 0, closed = 1, manifold = 1, max_ff = 0;
+    for (uint32_t e = 0; e < ne; ++e) {
+        if (cnt[e] > max_ef) max_ef = cnt[e];
+        if (cnt[e] < 2) closed = 0;
+        if (cnt[e] > 2) manifold = 0;
+        if (++val[ev[2 * (uint64_t)e]] > max_val) max_val = val[ev[2 * (uint64_t)e]];
+        if (++val[ev[2 * (uint64_t)e + 1]] > max_val) max_val = val[ev[2 * (uint64_t)e + 1]];
+    }
+    for (uint32_t f = 0; f < nf; ++f) {
+        uint32_t k = 0;
+        for (uint32_t j = 0; j < 3; ++j)
+            k += cnt[fe[3 * (uint64_t)f + j]] - 1;
+        if (k > max_ff) max_ff = k;
+    }
+    out[0] = max_val;
+    out[1] = max_ef;
+    out[2] = max_ff;
+    out[3] = closed;
+    out[4] = manifold;
+    free(cnt);
+    free(val);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Vertex normals, Max 1999 weights.                                         */
+/* apps/VertexNormal/vertex_normal_ref.h:5-85: serial loop over faces in      */
+/* input order; n = (v1-v0) x (v2-v0); squared edge lengths l0=|v0v1|^2,      */
+/* l1=|v1v2|^2, l2=|v2v0|^2; corner i receives n / (l[i] + l[(i+2)%3]).       */
+/* fp32 arithmetic in exactly the reference's operation order so the result   */
+/* is bit-identical to oracle/_ref (compile without FMA contraction).         */
+/* ------------------------------------------------------------------------ */
+static float rxo_l2sq_f(const float* a, const float* b)
+{
+    float x0 = a[0] - b[0];
+    float x1 = a[1] - b[1];
+    float x2 = a[2] - b[2];
+    return x0 * x0 + x1 * x1 + x2 * x2;
+}
+
+void rxo_vertex_normals_f32(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, float* n)
+{
+    memset(n, 0, (size_t)nv * 3 * sizeof(float));
+    for (uint32_t f = 0; f < nf; ++f) {
+        const uint32_t* v  = fv + 3 * (uint64_t)f;
+        const float *   p0 = x + 3 * (uint64_t)v[0], *p1 = x + 3 * (uint64_t)v[1],
+                    *p2 = x + 3 * (uint64_t)v[2];
+        float a0 = p1[0] - p0[0], a1 = p1[1] - p0[1], a2 = p1[2] - p0[2];
+        float b0 = p2[0] - p0[0], b1 = p2[1] - p0[1], b2 = p2[2] - p0[2];
+        float fn[3];
+        fn[0] = a1 * b2 - a2 * b1;
+        fn[1] = a2 * b0 - a0 * b2;
+        fn[2] = a0 * b1 - a1 * b0;
+        float l[3];
+        l[0] = rxo_l2sq_f(p0, p1);
+        l[1] = rxo_l2sq_f(p1, p2);
+        l[2] = rxo_l2sq_f(p2, p0);
+        for (uint32_t i = 0; i < 3; ++i) {
+            uint32_t k = (i + 2) % 3;
+            float*   o = n + 3 * (uint64_t)v[i];
+            for (uint32_t c = 0; c < 3; ++c)
+                o[c] += fn[c] / (l[i] + l[k]);
+        }
+    }
+}
+
+/* same formula in float64 from the same fp32 inputs: the tolerance yardstick
+ * (SURVEY.md section 7 "hard parts": -use_fast_math in the reference build). */
+void rxo_vertex_normals_f64(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, double* n)
+{
+    memset(n, 0, (size_t)nv * 3 * sizeof(double));
+    for (uint32_t f = 0; f < nf; ++f) {
+        const uint32_t* v = fv + 3 * (uint64_t)f;
+        double          p[3][3];
+        for (int i = 0; i < 3; ++i)
+            for (int c = 0; c < 3; ++c)
+                p[i][c] = x[3 * (uint64_t)v[i] + c];
+        double a[3], b[3], fn[3], l[3];
+        for (int c = 0; c < 3; ++c) {
+            a[c] = p[1][c] - p[0][c];
+            b[c] = p[2][c] - p[0][c];
+        }
+        fn[0] = a[1] * b[2] - a[2] * b[1];
+        fn[1] = a[2] * b[0] - a[0] * b[2];
+        fn[2] = a[0] * b[1] - a[1] * b[0];
+        for (int i = 0; i < 3; ++i) {
+            int j = (i + 1) % 3;
+            l[i]  = 0;
+            for (int c = 0; c < 3; ++c)
+                l[i] += (p[i][c] - p[j][c]) * (p[i][c] - p[j][c]);
+        }
+        for (int i = 0; i < 3; ++i) {
+            int k = (i + 2) % 3;
+            for (int c = 0; c < 3; ++c)
+                n[3 * (uint64_t)v[i] + c] += fn[c] / (l[i] + l[k]);
+        }
+    }
+}
+
+/* Filtering's vertex normal: apps/Filtering/filtering_rxmesh_kernel.cuh:15-46
+ * -- sum over incident faces of the NORMALISED face normal (not normalised at
+ * the end; bilateral_filtering normalises when it reads it, :452). float64
+ * accumulate from fp32 inputs when out64 != NULL, fp32 otherwise. */
+void rxo_vertex_normals_unit_faces(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv,
+                                   float* out32, double* out64)
+{
+    if (out32) memset(out32, 0, (size_t)nv * 3 * sizeof(float));
+    if (out64) memset(out64, 0, (size_t)nv * 3 * sizeof(double));
+    for (uint32_t f = 0; f < nf; ++f) {
+        const uint32_t* v = fv + 3 * (uint64_t)f;
+        if (out64) {
+            double a[3], b[3], fn[3];
+            for (int c = 0; c < 3; ++c) {
+                a[c] = (double)x[3 * (uint64_t)v[1] + c] - x[3 * (uint64_t)v[0] + c];
+                b[c] = (double)x[3 * (uint64_t)v[2] + c] - x[3 * (uint64_t)v[0] + c];
+            }
+            fn[0]    = a[1] * b[2] - a[2] * b[1];
+            fn[1]    = a[2] * b[0] - a[0] * b[2];
+            fn[2]    = a[0] * b[1] - a[1] * b[0];
+            double s = 1.0 / sqrt(fn[0] * fn[0] + fn[1] * fn[1] + fn[2] * fn[2]);
+            for (int i = 0; i < 3; ++i)
+                for (int c = 0; c < 3; ++c)
+                    out64[3 * (uint64_t)v[i] + c] += fn[c] * s;
+        }
+        if (out32) {
+            float a[3], b[3], fn[3];
+            for (int c = 0; c < 3; ++c) {
+                a[c] = x[3 * (uint64_t)v[1] + c] - x[3 * (uint64_t)v[0] + c];
+                b[c] = x[3 * (uint64_t)v[2] + c] - x[3 * (uint64_t)v[0] + c];
+            }
+            fn[0]   = a[1] * b[2] - a[2] * b[1];
+            fn[1]   = a[2] * b[0] - a[0] * b[2];
+            fn[2]   = a[0] * b[1] - a[1] * b[0];
+            float s = 1.0f / sqrtf(fn[0] * fn[0] + fn[1] * fn[1] + fn[2] * fn[2]);
+            for (int i = 0; i < 3; ++i)
+                for (int c = 0; c < 3; ++c)
+                    out32[3 * (uint64_t)v[i] + c] += fn[c] * s;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* Laplacian smoothing ("manual" path).                                      */
+/* apps/Smoothing/manual.h:86-104: grad(v,i) = sum_u 2*(x(v,i) - x(u,i)) in   */
+/* fp32 (grad starts at 0, one += per neighbour); then x(v,i) -= lr*grad(v,i) */
+/* with lr a double (manual.h:37), i.e. the update is evaluated in double and */
+/* rounded to fp32.  All gradients are computed before any position moves     */
+/* (two kernels), i.e. a Jacobi step.  vv_off/vv_val = VV adjacency.          */
+/* ------------------------------------------------------------------------ */
+void rxo_laplacian_step_f32(const uint32_t* vv_off, const uint32_t* vv_val, uint32_t nv,
+                            const float* x_in, float* x_out, double lr)
+{
+    for (uint32_t v = 0; v < nv; ++v) {
+        float g[3] = {0.f, 0.f, 0.f};
+        for (uint32_t i = vv_off[v]; i < vv_off[v + 1]; ++i) {
+            uint32_t u = vv_val[i];
+            for (int c = 0; c < 3; ++c)
+                g[c] += 2 * (x_in[3 * (uint64_t)v + c] - x_in[3 * (uint64_t)u + c]);
+        }
+        for (int c = 0; c < 3; ++c)
+            x_out[3 * (uint64_t)v + c] = (float)((double)x_in[3 * (uint64_t)v + c] - lr * (double)g[c]);
+    }
+}
+
+void rxo_laplacian_step_f64(const uint32_t* vv_off, const uint32_t* vv_val, uint32_t nv,
+                            const double* x_in, double* x_out, double lr)
+{
+    for (uint32_t v = 0; v < nv; ++v) {
+        double g[3] = {0, 0, 0};
+        for (uint32_t i = vv_off[v]; i < vv_off[v + 1]; ++i) {
+            uint32_t u = vv_val[i];
+            for (int c = 0; c < 3; ++c)
+                g[c] += 2 * (x_in[3 * (uint64_t)v + c] - x_in[3 * (uint64_t)u + c]);
+        }
+        for (int c = 0; c < 3; ++c)
+            x_out[3 * (uint64_t)v + c] = x_in[3 * (uint64_t)v + c] - lr * g[c];
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* Bilateral mesh denoising, one iteration.                                  */
+/* Restates apps/Filtering/filtering_rxmesh_kernel.cuh:426-548 (+52-85 and    */
+/* filtering_util.h:8-59), which is the GPU side of the app; the OpenMesh side */
+/* (filtering_openmesh.h:73-207) computes the same quantities:                */
+/*   n      = normalise(sum of unit face normals)                             */
+/*   sc2    = min squared distance to a 1-ring neighbour                      */
+/*   radius = 4*sc2 on squared distances (== 2*sigma_c on distances, :53)     */
+/*   N      = {v} + breadth-first closure of neighbours with |q-v|^2<=radius, */
+/*            visited in discovery order, expanded only from members of N     */
+/*   ss2    = var(|<q-v,n>|) over N (population variance), +1e-20 if <1e-20   */
+/*   v'     = v + n * sum(wc*ws*h)/sum(wc*ws), wc=exp(-t^2/(2 sc2)),          */
+/*            ws=exp(-h^2/(2 ss2)), t=|q-v|, h=<q-v,n>                        */
+/* max_nbrs mirrors maxVVSize (filtering_rxmesh.cuh: 80): exceeding it is an  */
+/* assert in the reference; here the count is reported and the list clipped.  */
+/* `normals` = output of rxo_vertex_normals_unit_faces (unnormalised sum).    */
+/* Computed in float64 from fp32 inputs when use_f64 != 0, else in fp32.      */
+/* Returns the maximum neighbourhood size seen.                               */
+/* ------------------------------------------------------------------------ */
+uint32_t rxo_bilateral_step(const uint32_t* vv_off, const uint32_t* vv_val, uint32_t nv,
+                            const float* x, const double* normals, float* x_out,
+                            uint32_t max_nbrs, int use_f64)
+{
+    uint32_t* list = (uint32_t*)malloc((size_t)(max_nbrs + 1) * sizeof(uint32_t));
+    uint32_t  worst = 0;
+    for (uint32_t v = 0; v < nv; ++v) {
+        double p[3], n[3];
+        for (int c = 0; c < 3; ++c) {
+            p[c] = x[3 * (uint64_t)v + c];
+            n[c] = normals[3 * (uint64_t)v + c];
+        }
+        double nl = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        for (int c = 0; c < 3; ++c)
+            n[c] = use_f64 ? n[c] / nl : (double)((float)n[c] / (float)nl);
+        double sc2 = 1e10;
+        for (uint32_t i = vv_off[v]; i < vv_off[v + 1]; ++i) {
+            uint32_t u = vv_val[i];
+            double   d = 0;
+            for (int c = 0; c < 3; ++c) {
+                double t = (double)x[3 * (uint64_t)u + c] - p[c];
+                d += t * t;
+            }
+            if (!use_f64) d = (float)d;
+            if (d < sc2) sc2 = d;
+        }
+        double   radius = 4.0 * sc2;
+        uint32_t cnt    = 0;
+        list[cnt++]     = v;
+        for (uint32_t head = 0; head < cnt; ++head) {
+            uint32_t w = list[head];
+            for (uint32_t i = vv_off[w]; i < vv_off[w + 1]; ++i) {
+                uint32_t u = vv_val[i];
+                if (u == v) continue;
+                int dup = 0;
+                for (uint32_t k = 0; k < cnt; ++k)
+                    if (list[k] == u) {
+                        dup = 1;
+                        break;
+                    }
+                if (dup) continue;
+                double d = 0;
+                for (int c = 0; c < 3; ++c) {
+                    double t = (double)x[3 * (uint64_t)u + c] - p[c];
+                    d += t * t;
+                }
+                if (!use_f64) d = (float)d;
+                if (d <= radius) {
+                    if (cnt < max_nbrs) list[cnt] = u;
+                    cnt++;
+                    if (cnt > max_nbrs) cnt = max_nbrs, worst = max_nbrs + 1;
+                }
+            }
+        }
+        if (cnt > worst) worst = cnt;
+        double sum = 0, sum_sq = 0;
+        for (uint32_t k = 0; k < cnt; ++k) {
+            double h = 0;
+            for (int c = 0; c < 3; ++c)
+                h += ((double)x[3 * (uint64_t)list[k] + c] - p[c]) * n[c];
+            h = fabs(h);
+            sum += h;
+            sum_sq += h * h;
+        }
+        double cc  = (double)cnt;
+        double ss2 = sum_sq / cc - (sum * sum) / (cc * cc);
+        if (ss2 < 1.0e-20) ss2 += 1.0e-20;
+        double num = 0, den = 0;
+        for (uint32_t k = 0; k < cnt; ++k) {
+            double t2 = 0, h = 0;
+            for (int c = 0; c < 3; ++c) {
+                double q = (double)x[3 * (uint64_t)list[k] + c] - p[c];
+                t2 += q * q;
+                h += q * n[c];
+            }
+            double wc = exp(-0.5 * t2 / sc2);
+            double ws = exp(-0.5 * h * h / ss2);
+            num += wc * ws * h;
+            den += wc * ws;
+        }
+        for (int c = 0; c < 3; ++c)
+            x_out[3 * (uint64_t)v + c] = (float)(p[c] + n[c] * (num / den));
+    }
+    free(list);
+    return worst;
+}
+
+/* consume-variant checksums used by the roofline kernels: out[v] = sum of
+ * in[u] over the VV / VF lists, accumulated in float64 (order-free yardstick). */
+void rxo_consume_sum(const uint32_t* off, const uint32_t* val, uint32_t n_src, const float* in,
+                     double* out)
+{
+    for (uint32_t s = 0; s < n_src; ++s) {
+        double a = 0;
+        for (uint32_t i = off[s]; i < off[s + 1]; ++i)
+            a += in[val[i]];
+        out[s] = a;
+    }
+}

@@ -1,0 +1,91 @@
+"""ctypes binding of librxmesh_b200.so (the C ABI in include/rxmesh_b200.h).
+
+The product path has no fallback: if the CUDA library is missing this module raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librxmesh_b200.so")
+
+u32p = C.POINTER(C.c_uint32)
+u16p = C.POINTER(C.c_uint16)
+
+
+class PatchView(C.Structure):
+    _fields_ = [("patch_id", C.c_uint32), ("n", C.c_uint32 * 3), ("n_owned", C.c_uint32 * 3),
+                ("slot_base", C.c_uint32 * 3), ("lin_base", C.c_uint32 * 3),
+                ("ev", u16p), ("fe", u16p), ("fv", u16p), ("owner", u32p * 3), ("stash", u32p),
+                ("n_stash", C.c_uint32), ("ltog", u32p * 3)]
+
+
+# every symbol declared in include/rxmesh_b200.h: (restype, argtypes)
+SYMBOLS = {
+    "rxm_last_error": (C.c_char_p, []),
+    "rxm_version": (C.c_char_p, []),
+    "rxm_init": (C.c_int, [C.c_int]),
+    "rxm_mesh_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int,
+                                  C.POINTER(C.c_void_p)]),
+    "rxm_mesh_to_device": (C.c_int, [C.c_void_p]),
+    "rxm_mesh_destroy": (None, [C.c_void_p]),
+    "rxm_mesh_info": (C.c_uint64, [C.c_void_p, C.c_int]),
+    "rxm_mesh_build_seconds": (C.c_double, [C.c_void_p, C.c_int]),
+    "rxm_mesh_patch": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(PatchView)]),
+    "rxm_mesh_slot_to_global": (u32p, [C.c_void_p, C.c_int]),
+    "rxm_mesh_global_to_slot": (u32p, [C.c_void_p, C.c_int]),
+    "rxm_mesh_elem_patch": (u32p, [C.c_void_p, C.c_int]),
+    "rxm_mesh_slot_base": (u32p, [C.c_void_p, C.c_int]),
+    "rxm_mesh_lin_base": (u32p, [C.c_void_p, C.c_int]),
+    "rxm_mesh_edges": (u32p, [C.c_void_p]),
+    "rxm_mesh_face_edges": (u32p, [C.c_void_p]),
+    "rxm_mesh_launch_box": (C.c_int, [C.c_void_p, C.c_int, u32p, u32p, u32p]),
+    "rxm_attr_create": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                                  C.POINTER(C.c_void_p)]),
+    "rxm_attr_destroy": (None, [C.c_void_p]),
+    "rxm_attr_data": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "rxm_attr_count": (C.c_uint64, [C.c_void_p]),
+    "rxm_attr_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "rxm_attr_move": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "rxm_attr_copy_from": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "rxm_attr_upload_global": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rxm_attr_download_global": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rxm_attr_from_global_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rxm_attr_to_global_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rxm_query_store": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rxm_query_consume": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rxm_vertex_normals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "rxm_laplacian_smooth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_uint32,
+                                       C.c_void_p]),
+    "rxm_bilateral_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "rxm_boundary_vertices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rxm_vertex_normals_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rxm_laplacian_smooth_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                            C.c_uint32, C.c_void_p]),
+    "rxm_launch_count": (C.c_uint64, []),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (make -C rxmesh_b200/csrc). rxmesh_b200 has no CPU fallback.")
+        _lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(_lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    return _lib
+
+
+class RXMeshError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise RXMeshError(lib().rxm_last_error().decode())

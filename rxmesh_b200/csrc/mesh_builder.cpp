@@ -1,0 +1,589 @@
+// mesh_builder.cpp -- see mesh_builder.h.  Host C++17 + OpenMP, flat arrays only.
+#include "mesh_builder.h"
+
+#include <omp.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+namespace rxm {
+
+namespace {
+double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch())
+        .count();
+}
+
+// exclusive prefix sum in place over n+1 entries (entry n receives the total)
+template <typename T>
+void exclusive_scan(std::vector<T>& a)
+{
+    T run = 0;
+    for (size_t i = 0; i < a.size(); ++i) {
+        T c  = a[i];
+        a[i] = run;
+        run += c;
+    }
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// Edge numbering (reference semantics: rxmesh.cpp:589-611, util/util.h:410-416)
+// ---------------------------------------------------------------------------
+uint32_t build_edges(const uint32_t* fv, uint32_t nf, uint32_t nv, std::vector<uint32_t>& ev,
+                     std::vector<uint32_t>& fe)
+{
+    const uint64_t H = 3ull * nf;
+    fe.assign(H, 0);
+    if (nf == 0) {
+        ev.clear();
+        return 0;
+    }
+    // 1. bucket half-edges by their smaller endpoint
+    std::vector<uint32_t> off((size_t)nv + 1, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t h = 0; h < (int64_t)H; ++h) {
+        const uint32_t f = (uint32_t)(h / 3), j = (uint32_t)(h % 3);
+        const uint32_t a = fv[3ull * f + j], b = fv[3ull * f + (j + 1) % 3];
+        const uint32_t lo = a < b ? a : b;
+        __atomic_fetch_add(&off[lo], 1u, __ATOMIC_RELAXED);
+    }
+    exclusive_scan(off);
+    struct HE
+    {
+        uint32_t hi, h;
+    };
+    std::vector<HE>       bucket(H);
+    std::vector<uint32_t> cur(off.begin(), off.end() - 1);
+#pragma omp parallel for schedule(static)
+    for (int64_t h = 0; h < (int64_t)H; ++h) {
+        const uint32_t f = (uint32_t)(h / 3), j = (uint32_t)(h % 3);
+        const uint32_t a = fv[3ull * f + j], b = fv[3ull * f + (j + 1) % 3];
+        const uint32_t lo = a < b ? a : b, hi = a < b ? b : a;
+        const uint32_t p  = __atomic_fetch_add(&cur[lo], 1u, __ATOMIC_RELAXED);
+        bucket[p]         = {hi, (uint32_t)h};
+    }
+    // 2. inside a bucket, equal `hi` = same edge; its first half-edge (smallest h)
+    //    decides the edge id.
+    std::vector<uint32_t> rep(H);          // half-edge -> first half-edge of its edge
+    std::vector<uint32_t> first(H + 1, 0);  // 1 at the first half-edge of every edge
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (int64_t v = 0; v < (int64_t)nv; ++v) {
+        HE* b = bucket.data() + off[v];
+        HE* e = bucket.data() + off[v + 1];
+        std::sort(b, e, [](const HE& x, const HE& y) { return x.hi != y.hi ? x.hi < y.hi : x.h < y.h; });
+        for (HE* g = b; g < e;) {
+            HE* g2 = g;
+            while (g2 < e && g2->hi == g->hi) {
+                rep[g2->h] = g->h;
+                ++g2;
+            }
+            first[g->h] = 1;
+            g           = g2;
+        }
+    }
+    exclusive_scan(first);
+    const uint32_t ne = first[H];
+    ev.assign(2ull * ne, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t h = 0; h < (int64_t)H; ++h) {
+        const uint32_t e = first[rep[h]];
+        fe[h]            = e;
+        if (rep[h] == (uint32_t)h) {
+            const uint32_t f = (uint32_t)(h / 3), j = (uint32_t)(h % 3);
+            const uint32_t a = fv[3ull * f + j], b = fv[3ull * f + (j + 1) % 3];
+            ev[2ull * e]     = a < b ? b : a;
+            ev[2ull * e + 1] = a < b ? a : b;
+        }
+    }
+    return ne;
+}
+
+// ---------------------------------------------------------------------------
+// Lloyd patcher
+// ---------------------------------------------------------------------------
+void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_size,
+                   uint32_t lloyd_iters, std::vector<uint32_t>& face_patch, uint32_t& num_patches)
+{
+    face_patch.assign(nf, INVALID32_);
+    num_patches = 0;
+    if (nf == 0) return;
+    // edge -> faces CSR
+    std::vector<uint32_t> ef_off((size_t)ne + 1, 0), ef_val(3ull * nf);
+    for (uint64_t i = 0; i < 3ull * nf; ++i)
+        ef_off[fe[i]]++;
+    exclusive_scan(ef_off);
+    {
+        std::vector<uint32_t> cur(ef_off.begin(), ef_off.end() - 1);
+        for (uint32_t f = 0; f < nf; ++f)
+            for (int j = 0; j < 3; ++j)
+                ef_val[cur[fe[3ull * f + j]]++] = f;
+    }
+    auto for_each_nbr = [&](uint32_t f, auto&& fn) {
+        for (int j = 0; j < 3; ++j) {
+            const uint32_t e = fe[3ull * f + j];
+            for (uint32_t i = ef_off[e]; i < ef_off[e + 1]; ++i)
+                if (ef_val[i] != f) fn(ef_val[i]);
+        }
+    };
+
+    // start near the patch count the size bound ends up needing (the reference
+    // converges to ~F/370 for patch_size 512)
+    uint32_t K = std::max<uint32_t>(1, (uint32_t)((uint64_t)nf * 4 / (3ull * patch_size)) + 1);
+    K          = std::min(K, nf);
+    std::vector<uint32_t> seeds(K);
+    for (uint32_t i = 0; i < K; ++i)
+        seeds[i] = (uint32_t)(((2ull * i + 1) * nf) / (2ull * K));
+
+    std::vector<uint32_t> queue(nf), dist(nf), psize;
+
+    auto assign = [&]() {
+        std::fill(face_patch.begin(), face_patch.end(), INVALID32_);
+        uint32_t head = 0, tail = 0;
+        for (uint32_t i = 0; i < seeds.size(); ++i) {
+            if (face_patch[seeds[i]] != INVALID32_) continue;  // duplicate seed: dropped below
+            face_patch[seeds[i]] = i;
+            dist[seeds[i]]       = 0;
+            queue[tail++]        = seeds[i];
+        }
+        uint32_t scan = 0;
+        while (true) {
+            while (head < tail) {
+                const uint32_t f = queue[head++];
+                for_each_nbr(f, [&](uint32_t g) {
+                    if (face_patch[g] == INVALID32_) {
+                        face_patch[g] = face_patch[f];
+                        dist[g]       = dist[f] + 1;
+                        queue[tail++] = g;
+                    }
+                });
+            }
+            // components no seed reached get a seed of their own
+            while (scan < nf && face_patch[scan] != INVALID32_)
+                ++scan;
+            if (scan == nf) break;
+            seeds.push_back(scan);
+            face_patch[scan] = (uint32_t)seeds.size() - 1;
+            dist[scan]       = 0;
+            queue[tail++]    = scan;
+        }
+        // compact away patches that received no face (duplicate seeds)
+        psize.assign(seeds.size(), 0);
+        for (uint32_t f = 0; f < nf; ++f)
+            psize[face_patch[f]]++;
+        std::vector<uint32_t> remap(seeds.size());
+        uint32_t              k = 0;
+        for (uint32_t i = 0; i < seeds.size(); ++i) {
+            remap[i] = k;
+            if (psize[i]) {
+                seeds[k] = seeds[i];
+                psize[k] = psize[i];
+                ++k;
+            }
+        }
+        if (k != seeds.size()) {
+            seeds.resize(k);
+            psize.resize(k);
+            for (uint32_t f = 0; f < nf; ++f)
+                face_patch[f] = remap[face_patch[f]];
+        }
+    };
+
+    std::vector<uint32_t> depth(nf);
+    auto recenter = [&]() -> bool {
+        // distance of every face to its patch boundary; the deepest face becomes the seed
+        uint32_t head = 0, tail = 0;
+        std::fill(depth.begin(), depth.end(), INVALID32_);
+        for (uint32_t f = 0; f < nf; ++f) {
+            bool border = false;
+            for_each_nbr(f, [&](uint32_t g) { border |= (face_patch[g] != face_patch[f]); });
+            if (border) {
+                depth[f]      = 0;
+                queue[tail++] = f;
+            }
+        }
+        while (head < tail) {
+            const uint32_t f = queue[head++];
+            for_each_nbr(f, [&](uint32_t g) {
+                if (depth[g] == INVALID32_ && face_patch[g] == face_patch[f]) {
+                    depth[g]      = depth[f] + 1;
+                    queue[tail++] = g;
+                }
+            });
+        }
+        std::vector<uint32_t> best(seeds.size(), INVALID32_);
+        for (uint32_t f = 0; f < nf; ++f) {
+            if (depth[f] == INVALID32_) continue;  // patch without border: keep its seed
+            uint32_t& b = best[face_patch[f]];
+            if (b == INVALID32_ || depth[f] > depth[b]) b = f;
+        }
+        bool changed = false;
+        for (uint32_t p = 0; p < seeds.size(); ++p)
+            if (best[p] != INVALID32_ && best[p] != seeds[p]) {
+                seeds[p] = best[p];
+                changed  = true;
+            }
+        return changed;
+    };
+
+    for (int outer = 0; outer < 64; ++outer) {
+        assign();
+        for (uint32_t it = 0; it < lloyd_iters; ++it) {
+            if (!recenter()) break;
+            assign();
+        }
+        // split patches that are still too large: one more seed at the face
+        // farthest from the current seed
+        std::vector<uint32_t> far(seeds.size(), INVALID32_);
+        bool                  any = false;
+        for (uint32_t f = 0; f < nf; ++f) {
+            const uint32_t p = face_patch[f];
+            if (psize[p] <= patch_size) continue;
+            if (far[p] == INVALID32_ || dist[f] > dist[far[p]]) far[p] = f;
+        }
+        const uint32_t K0 = (uint32_t)seeds.size();
+        for (uint32_t p = 0; p < K0; ++p)
+            if (far[p] != INVALID32_ && far[p] != seeds[p]) {
+                seeds.push_back(far[p]);
+                any = true;
+            }
+        if (!any) break;
+    }
+    assign();
+    // last-resort guarantee of the size bound: chop oversized patches by BFS order
+    {
+        bool over = false;
+        for (uint32_t p = 0; p < psize.size(); ++p)
+            over |= psize[p] > patch_size;
+        if (over) {
+            std::vector<uint32_t> taken(psize.size(), 0), cur_id(psize.size());
+            std::iota(cur_id.begin(), cur_id.end(), 0u);
+            uint32_t next = (uint32_t)psize.size();
+            // queue still holds the BFS order of the last assign()
+            for (uint32_t i = 0; i < nf; ++i) {
+                const uint32_t f = queue[i], p = face_patch[f];
+                if (psize[p] <= patch_size) continue;
+                if (taken[p] == patch_size) {
+                    taken[p]  = 0;
+                    cur_id[p] = next++;
+                }
+                ++taken[p];
+                dist[f] = cur_id[p];  // reuse as new label
+            }
+            for (uint32_t f = 0; f < nf; ++f)
+                if (psize[face_patch[f]] > patch_size) face_patch[f] = dist[f];
+            seeds.resize(next);
+        }
+    }
+    num_patches = (uint32_t)seeds.size();
+}
+
+// ---------------------------------------------------------------------------
+// build_mesh
+// ---------------------------------------------------------------------------
+std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_patch_in,
+                       const BuildOptions& opt, HostMesh& M)
+{
+    const double t_start = now_s();
+    if (opt.num_threads > 0) omp_set_num_threads(opt.num_threads);
+    if (nf == 0) return "build_mesh: empty face list";
+    if (opt.patch_size == 0 || opt.patch_size > 16384) return "build_mesh: patch_size must be in [1, 16384]";
+    M            = HostMesh();
+    M.patch_size = opt.patch_size;
+
+    // ---- sizes, degenerate-face check (rxmesh.cpp:590-597 requires triangles) ----
+    uint32_t nv = 0;
+    bool     degenerate = false;
+#pragma omp parallel for reduction(max : nv) reduction(|| : degenerate) schedule(static)
+    for (int64_t f = 0; f < (int64_t)nf; ++f) {
+        const uint32_t a = fv[3 * f], b = fv[3 * f + 1], c = fv[3 * f + 2];
+        nv         = std::max(nv, std::max(a, std::max(b, c)));
+        degenerate = degenerate || (a == b || b == c || a == c);
+    }
+    if (degenerate) return "build_mesh: degenerate face (repeated vertex)";
+    if (nv == INVALID32_) return "build_mesh: vertex id 0xFFFFFFFF is reserved";
+    nv += 1;
+
+    // ---- global edges ----
+    const uint32_t ne = build_edges(fv, nf, nv, M.ev, M.fe);
+    M.num_elems[ELEM_V] = nv;
+    M.num_elems[ELEM_E] = ne;
+    M.num_elems[ELEM_F] = nf;
+    const uint32_t* fe = M.fe.data();
+
+    // ---- input statistics (rxmesh.cpp:560-650) ----
+    std::vector<uint32_t> ef_cnt(ne, 0);
+    for (uint64_t i = 0; i < 3ull * nf; ++i)
+        ef_cnt[fe[i]]++;
+    {
+        std::vector<uint32_t> val(nv, 0);
+        uint32_t max_ef = 0, max_val = 0;
+        bool     closed = true, manifold = true;
+        for (uint32_t e = 0; e < ne; ++e) {
+            max_ef = std::max(max_ef, ef_cnt[e]);
+            closed &= ef_cnt[e] >= 2;
+            manifold &= ef_cnt[e] <= 2;
+            max_val = std::max(max_val, ++val[M.ev[2ull * e]]);
+            max_val = std::max(max_val, ++val[M.ev[2ull * e + 1]]);
+        }
+        uint32_t max_ff = 0;
+#pragma omp parallel for reduction(max : max_ff) schedule(static)
+        for (int64_t f = 0; f < (int64_t)nf; ++f)
+            max_ff = std::max(max_ff, ef_cnt[fe[3 * f]] + ef_cnt[fe[3 * f + 1]] + ef_cnt[fe[3 * f + 2]] - 3);
+        M.max_valence             = max_val;
+        M.max_edge_incident_faces = max_ef;
+        M.max_face_adjacent_faces = max_ff;
+        M.is_closed               = closed;
+        M.is_edge_manifold        = manifold;
+    }
+    std::vector<uint32_t>().swap(ef_cnt);
+
+    // ---- face -> patch ----
+    std::vector<uint32_t>& fpatch = M.elem_patch[ELEM_F];
+    uint32_t               P      = 0;
+    const double           t_p0   = now_s();
+    if (face_patch_in) {
+        // compact user labels, keeping their order
+        uint32_t maxp = 0;
+        for (uint32_t f = 0; f < nf; ++f) {
+            if (face_patch_in[f] == INVALID32_) return "build_mesh: face_patch holds an invalid id";
+            maxp = std::max(maxp, face_patch_in[f]);
+        }
+        std::vector<uint32_t> used((size_t)maxp + 2, 0);
+        for (uint32_t f = 0; f < nf; ++f)
+            used[face_patch_in[f]] = 1;
+        exclusive_scan(used);
+        P = used[(size_t)maxp + 1];
+        fpatch.resize(nf);
+#pragma omp parallel for schedule(static)
+        for (int64_t f = 0; f < (int64_t)nf; ++f)
+            fpatch[f] = used[face_patch_in[f]];
+    } else {
+        patcher_lloyd(fe, nf, ne, opt.patch_size, opt.lloyd_iters, fpatch, P);
+    }
+    M.patcher_seconds = now_s() - t_p0;
+    M.num_patches     = P;
+
+    // ---- vertex / edge owner = lowest patch id among the incident faces'
+    //      patches (patcher/patcher.cu:730-756: first claim in patch order) ----
+    std::vector<uint32_t>& vpatch = M.elem_patch[ELEM_V];
+    std::vector<uint32_t>& epatch = M.elem_patch[ELEM_E];
+    vpatch.assign(nv, INVALID32_);
+    epatch.assign(ne, INVALID32_);
+    auto atomic_min = [](uint32_t* addr, uint32_t v) {
+        uint32_t old = __atomic_load_n(addr, __ATOMIC_RELAXED);
+        while (v < old && !__atomic_compare_exchange_n(addr, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+        }
+    };
+#pragma omp parallel for schedule(static)
+    for (int64_t f = 0; f < (int64_t)nf; ++f)
+        for (int j = 0; j < 3; ++j) {
+            atomic_min(&vpatch[fv[3 * f + j]], fpatch[f]);
+            atomic_min(&epatch[fe[3 * f + j]], fpatch[f]);
+        }
+    for (uint32_t v = 0; v < nv; ++v)
+        if (vpatch[v] == INVALID32_) return "build_mesh: isolated vertex id (not referenced by any face): " + std::to_string(v);
+
+    // ---- faces of every patch (ascending id) and vertex -> faces CSR ----
+    std::vector<uint32_t> pf_off((size_t)P + 1, 0), pf_val(nf);
+    for (uint32_t f = 0; f < nf; ++f)
+        pf_off[fpatch[f]]++;
+    exclusive_scan(pf_off);
+    {
+        std::vector<uint32_t> cur(pf_off.begin(), pf_off.end() - 1);
+        for (uint32_t f = 0; f < nf; ++f)
+            pf_val[cur[fpatch[f]]++] = f;
+    }
+    for (uint32_t p = 0; p < P; ++p)
+        if (pf_off[p + 1] - pf_off[p] > 16384)
+            return "build_mesh: patch " + std::to_string(p) + " owns more than 16384 faces";
+    std::vector<uint32_t> vf_off((size_t)nv + 1, 0), vf_val(3ull * nf);
+    for (uint64_t i = 0; i < 3ull * nf; ++i)
+        vf_off[fv[i]]++;
+    exclusive_scan(vf_off);
+    {
+        std::vector<uint32_t> cur(vf_off.begin(), vf_off.end() - 1);
+        for (uint32_t f = 0; f < nf; ++f)
+            for (int j = 0; j < 3; ++j)
+                vf_val[cur[fv[3ull * f + j]]++] = f;
+    }
+
+    // ---- phase A: per patch element lists (owned first, each half sorted by
+    //      global id: rxmesh.cpp:845-869) and the neighbour-patch stash ----
+    struct Tmp
+    {
+        std::vector<uint32_t> l[3];
+        std::vector<uint32_t> stash;
+        uint32_t              n_owned[3];
+    };
+    std::vector<Tmp> tmp(P);
+    std::string      err;
+#pragma omp parallel
+    {
+        std::vector<uint32_t> scratch;
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t p = 0; p < (int64_t)P; ++p) {
+            Tmp&            T  = tmp[p];
+            const uint32_t* of = pf_val.data() + pf_off[p];
+            const uint32_t  no = pf_off[p + 1] - pf_off[p];
+            // ribbon = foreign faces sharing >= 1 vertex with an owned face
+            // (patcher/patcher.cu:668-713)
+            scratch.clear();
+            for (uint32_t i = 0; i < no; ++i)
+                for (int j = 0; j < 3; ++j) {
+                    const uint32_t v = fv[3ull * of[i] + j];
+                    for (uint32_t k = vf_off[v]; k < vf_off[v + 1]; ++k)
+                        if (fpatch[vf_val[k]] != (uint32_t)p) scratch.push_back(vf_val[k]);
+                }
+            std::sort(scratch.begin(), scratch.end());
+            scratch.erase(std::unique(scratch.begin(), scratch.end()), scratch.end());
+            T.l[ELEM_F].assign(of, of + no);
+            T.l[ELEM_F].insert(T.l[ELEM_F].end(), scratch.begin(), scratch.end());
+            T.n_owned[ELEM_F] = no;
+            // vertices and edges touched by the patch's faces
+            for (int t = 0; t < 2; ++t) {
+                const uint32_t*              src   = t == ELEM_V ? fv : fe;
+                const std::vector<uint32_t>& owner = t == ELEM_V ? vpatch : epatch;
+                scratch.clear();
+                for (uint32_t f : T.l[ELEM_F])
+                    for (int j = 0; j < 3; ++j)
+                        scratch.push_back(src[3ull * f + j]);
+                std::sort(scratch.begin(), scratch.end());
+                scratch.erase(std::unique(scratch.begin(), scratch.end()), scratch.end());
+                auto mid = std::stable_partition(scratch.begin(), scratch.end(),
+                                                 [&](uint32_t g) { return owner[g] == (uint32_t)p; });
+                T.n_owned[t] = (uint32_t)(mid - scratch.begin());
+                T.l[t]       = scratch;
+            }
+            // neighbour patches referenced by not-owned elements
+            scratch.clear();
+            for (int t = 0; t < 3; ++t)
+                for (uint32_t i = T.n_owned[t]; i < T.l[t].size(); ++i)
+                    scratch.push_back(M.elem_patch[t][T.l[t][i]]);
+            std::sort(scratch.begin(), scratch.end());
+            scratch.erase(std::unique(scratch.begin(), scratch.end()), scratch.end());
+            T.stash = scratch;
+        }
+    }
+    for (uint32_t p = 0; p < P; ++p)
+        for (int t = 0; t < 3; ++t)
+            if (tmp[p].l[t].size() > 65535u || tmp[p].stash.size() > 65535u)
+                return "build_mesh: patch " + std::to_string(p) + " exceeds 65535 local elements; use a smaller patch_size";
+    std::vector<uint32_t>().swap(vf_off);
+    std::vector<uint32_t>().swap(vf_val);
+
+    // ---- prefixes: attribute slots (padded to 4), linear ids, ltog offsets, blob offsets ----
+    M.desc.assign(P, PatchDesc());
+    for (int t = 0; t < 3; ++t) {
+        M.slot_base[t].assign((size_t)P + 1, 0);
+        M.lin_base[t].assign((size_t)P + 1, 0);
+        M.ltog_off[t].assign((size_t)P + 1, 0);
+    }
+    uint64_t topo_total = 0;
+    for (uint32_t p = 0; p < P; ++p) {
+        PatchDesc& D = M.desc[p];
+        memset(&D, 0, sizeof(D));
+        D.patch_id = p;
+        for (int t = 0; t < 3; ++t) {
+            D.n[t]              = (uint16_t)tmp[p].l[t].size();
+            D.n_owned[t]        = (uint16_t)tmp[p].n_owned[t];
+            D.slot_base[t]      = M.slot_base[t][p];
+            D.lin_base[t]       = M.lin_base[t][p];
+            M.slot_base[t][p + 1] = M.slot_base[t][p] + round_up(D.n_owned[t], 4);
+            M.lin_base[t][p + 1]  = M.lin_base[t][p] + D.n_owned[t];
+            M.ltog_off[t][p + 1]  = M.ltog_off[t][p] + D.n[t];
+            M.max_per_patch[t]       = std::max<uint32_t>(M.max_per_patch[t], D.n[t]);
+            M.max_owned_per_patch[t] = std::max<uint32_t>(M.max_owned_per_patch[t], D.n_owned[t]);
+            M.max_not_owned[t]       = std::max<uint32_t>(M.max_not_owned[t], D.n[t] - D.n_owned[t]);
+            M.total_local[t] += D.n[t];
+        }
+        D.n_stash    = (uint16_t)tmp[p].stash.size();
+        M.max_stash  = std::max<uint32_t>(M.max_stash, D.n_stash);
+        D.topo_off   = topo_total;
+        D.topo_bytes = D.off_stash() + D.stash_bytes();
+        topo_total += D.topo_bytes;
+    }
+    for (int t = 0; t < 3; ++t) {
+        M.num_slots[t] = M.slot_base[t][P];
+        if (M.lin_base[t][P] != M.num_elems[t]) return "build_mesh: internal error, ownership does not partition the mesh";
+        M.slot_to_global[t].assign(M.num_slots[t], INVALID32_);
+        M.global_to_slot[t].assign(M.num_elems[t], INVALID32_);
+        M.ltog[t].resize(M.ltog_off[t][P]);
+    }
+    M.topo.assign(topo_total + 16, 0);
+
+    // ---- phase B: id maps ----
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t p = 0; p < (int64_t)P; ++p)
+        for (int t = 0; t < 3; ++t) {
+            const auto& L = tmp[p].l[t];
+            std::copy(L.begin(), L.end(), M.ltog[t].begin() + M.ltog_off[t][p]);
+            for (uint32_t i = 0; i < tmp[p].n_owned[t]; ++i) {
+                M.slot_to_global[t][M.slot_base[t][p] + i] = L[i];
+                M.global_to_slot[t][L[i]]                  = M.slot_base[t][p] + i;
+            }
+        }
+
+    // ---- phase C: local topology (rxmesh.cpp:872-996), owner tables, stash ----
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t p = 0; p < (int64_t)P; ++p) {
+        const Tmp&       T = tmp[p];
+        const PatchDesc& D = M.desc[p];
+        uint8_t*         B = M.topo.data() + D.topo_off;
+        auto local_of = [&](int t, uint32_t g) -> uint32_t {
+            if (M.elem_patch[t][g] == (uint32_t)p) return M.global_to_slot[t][g] - D.slot_base[t];
+            auto b  = T.l[t].begin() + T.n_owned[t];
+            auto it = std::lower_bound(b, T.l[t].end(), g);
+            return (uint32_t)(it - T.l[t].begin());
+        };
+        uint16_t* lev = reinterpret_cast<uint16_t*>(B + D.off_ev());
+        uint16_t* lfe = reinterpret_cast<uint16_t*>(B + D.off_fe());
+        uint16_t* lfv = reinterpret_cast<uint16_t*>(B + D.off_fv());
+        for (uint32_t e = 0; e < D.n[ELEM_E]; ++e) {
+            const uint32_t g = T.l[ELEM_E][e];
+            lev[2 * e]       = (uint16_t)local_of(ELEM_V, M.ev[2ull * g]);      // larger global id
+            lev[2 * e + 1]   = (uint16_t)local_of(ELEM_V, M.ev[2ull * g + 1]);  // smaller global id
+        }
+        for (uint32_t f = 0; f < D.n[ELEM_F]; ++f) {
+            const uint32_t g = T.l[ELEM_F][f];
+            for (int j = 0; j < 3; ++j) {
+                const uint32_t v0 = fv[3ull * g + j], v1 = fv[3ull * g + (j + 1) % 3];
+                const uint32_t le = local_of(ELEM_E, fe[3ull * g + j]);
+                const uint32_t dir = v0 > v1 ? 0u : 1u;  // 0 iff the corner vertex is the larger id
+                lfe[3 * f + j]     = (uint16_t)((le << 1) | dir);
+                lfv[3 * f + j]     = lev[2 * le + dir];  // == local id of v0
+            }
+        }
+        for (int t = 0; t < 3; ++t) {
+            uint32_t* own = reinterpret_cast<uint32_t*>(B + D.off_own(t));
+            for (uint32_t i = T.n_owned[t]; i < T.l[t].size(); ++i) {
+                const uint32_t g = T.l[t][i];
+                const uint32_t q = M.elem_patch[t][g];
+                const uint32_t s = (uint32_t)(std::lower_bound(T.stash.begin(), T.stash.end(), q) - T.stash.begin());
+                own[i - T.n_owned[t]] = pack_owner(s, M.global_to_slot[t][g] - M.slot_base[t][q]);
+            }
+        }
+        StashEntry* st = reinterpret_cast<StashEntry*>(B + D.off_stash());
+        for (uint32_t s = 0; s < T.stash.size(); ++s) {
+            st[s].patch = T.stash[s];
+            for (int t = 0; t < 3; ++t)
+                st[s].slot_base[t] = M.slot_base[t][T.stash[s]];
+        }
+    }
+    if (!opt.keep_ltog)
+        for (int t = 0; t < 3; ++t) {
+            std::vector<uint32_t>().swap(M.ltog[t]);
+        }
+    M.build_seconds = now_s() - t_start;
+    if (opt.verbose)
+        fprintf(stderr, "[rxmesh_b200] build: V=%u E=%u F=%u patches=%u (patcher %.2fs, total %.2fs)\n",
+                nv, ne, nf, P, M.patcher_seconds, M.build_seconds);
+    return "";
+}
+
+}  // namespace rxm

@@ -1,0 +1,83 @@
+// mesh_builder.h -- host-side mesh build for the static path.
+//
+// B200-first replacement of RXMesh::build / build_supporting_structures /
+// build_single_patch_ltog / build_single_patch_topology / populate_patch_stash
+// (/root/reference/include/rxmesh/rxmesh.cpp:290-448,518-681,754-996,1096-1137)
+// and of the patcher's host passes extract_ribbons / assign_patch
+// (patcher/patcher.cu:640-757), written over flat arrays so that it scales
+// linearly in the number of faces (the reference is O(P*(V+E))).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "patch_layout.h"
+
+namespace rxm {
+
+struct HostMesh
+{
+    // ---- global sizes / input statistics (rxmesh.h getters) ----
+    uint32_t num_elems[3]   = {0, 0, 0};  // V, E, F
+    uint32_t num_patches    = 0;
+    uint32_t patch_size     = 512;
+    uint32_t max_valence    = 0;
+    uint32_t max_edge_incident_faces = 0;
+    uint32_t max_face_adjacent_faces = 0;
+    bool     is_closed        = true;
+    bool     is_edge_manifold = true;
+    uint32_t max_per_patch[3]       = {0, 0, 0};  // ribbon included
+    uint32_t max_owned_per_patch[3] = {0, 0, 0};
+    uint32_t max_not_owned[3]       = {0, 0, 0};
+    uint32_t max_stash              = 0;
+    uint32_t num_slots[3]           = {0, 0, 0};
+    uint64_t total_local[3]         = {0, 0, 0};  // sum over patches of n[t] (ribbon stats)
+    double   build_seconds          = 0;
+    double   patcher_seconds        = 0;
+
+    // ---- the patch store ----
+    std::vector<PatchDesc> desc;
+    std::vector<uint8_t>   topo;
+    std::vector<uint32_t>  slot_base[3];  // [P+1]
+    std::vector<uint32_t>  lin_base[3];   // [P+1]
+
+    // ---- id maps ----
+    std::vector<uint32_t> ltog[3];      // concatenated local->global, per patch (owned first)
+    std::vector<uint64_t> ltog_off[3];  // [P+1]
+    std::vector<uint32_t> slot_to_global[3];  // [num_slots], INVALID32_ for padding slots
+    std::vector<uint32_t> global_to_slot[3];  // [num_elems]
+    std::vector<uint32_t> elem_patch[3];      // [num_elems] owner patch of every element
+
+    // global edges (kept for host-side queries such as get_edge_id)
+    std::vector<uint32_t> ev;  // 2*E: (larger id, smaller id)
+    std::vector<uint32_t> fe;  // 3*F: global edge ids
+};
+
+struct BuildOptions
+{
+    uint32_t patch_size   = 512;
+    int      num_threads  = 0;     // 0 = omp default
+    bool     keep_ltog    = true;  // false: drop ltog after the build (large meshes)
+    bool     verbose      = false;
+    uint32_t lloyd_iters  = 8;
+};
+
+// Global edge numbering identical to the reference (first appearance while
+// scanning faces, rxmesh.cpp:589-611) computed with counting sorts instead of a
+// hash map. ev: 2*E (max id, min id); fe: 3*F. Returns the number of edges.
+uint32_t build_edges(const uint32_t* fv, uint32_t nf, uint32_t nv, std::vector<uint32_t>& ev,
+                     std::vector<uint32_t>& fe);
+
+// Deterministic Lloyd clustering of faces over the face-adjacency graph; the
+// role of patcher::Patcher::run_lloyd (patcher/patcher.cu:828-987).
+void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_size,
+                   uint32_t lloyd_iters, std::vector<uint32_t>& face_patch, uint32_t& num_patches);
+
+// Builds everything. face_patch may be null (run the Lloyd patcher) or a
+// user-supplied face->patch assignment (the analogue of the reference's
+// patcher_file constructor argument, rxmesh_static.h:61-66). Returns "" on
+// success, an error message otherwise.
+std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_patch,
+                       const BuildOptions& opt, HostMesh& out);
+
+}  // namespace rxm

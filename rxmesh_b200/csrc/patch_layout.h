@@ -1,0 +1,165 @@
+// patch_layout.h -- the B200 patch record (host + device POD).
+//
+// Replaces the reference's PatchInfo / PatchStash / LPHashTable / Context bundle
+// (/root/reference/include/rxmesh/patch_info.h:24-92, patch_stash.h:12-67,
+// lp_hashtable.h:46-290, context.h:15-441) for the STATIC path.
+//
+// Design (see DESIGN.md "Data layout in HBM"):
+//  * one 64-byte PatchDesc per patch in a dense array (one 16-byte-aligned read
+//    gives a block everything it needs to issue its TMA bulk copies);
+//  * one contiguous, 16-byte-aligned "topology blob" per patch holding, in this
+//    order, EV (2 u16 / edge), FE (3 u16 / face, bit0 = direction, as the
+//    reference rxmesh.cpp:941-983), FV (3 u16 / face, derived = FE o EV, stored so
+//    that FV/VF consumers read 6 instead of 12 bytes per face), the three
+//    not-owned -> owner tables and the neighbour-patch stash.  Every section
+//    starts on a 16-byte boundary and is padded to a multiple of 16 bytes so a
+//    single cp.async.bulk moves it into shared memory;
+//  * local ids are owned-first, each half sorted by global id (the reference's
+//    numbering, rxmesh.cpp:845-869), so the owned / active bitmasks of the
+//    reference collapse to a prefix [0, n_owned) and the not-owned -> owner
+//    lookup is a DIRECT table indexed by (local id - n_owned) instead of a
+//    cuckoo hash probe;
+//  * attribute storage holds OWNED elements only.  Patch p owns the slot range
+//    [slot_base(p), slot_base(p) + round_up4(n_owned(p))); slot_base is a
+//    multiple of 4 so that a patch's owned slice of a 1/2/3/4-component fp32
+//    attribute is 16-byte aligned and TMA-loadable.  The stash carries the
+//    neighbour patches' slot bases, so resolving a ribbon element to the address
+//    of its value needs no dependent global load.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define RXM_HD __host__ __device__ __forceinline__
+#else
+#define RXM_HD inline
+#endif
+
+namespace rxm {
+
+enum : uint32_t
+{
+    ELEM_V = 0,
+    ELEM_E = 1,
+    ELEM_F = 2
+};
+
+// Same numeric values as the reference's Op enum (types.h:113-129).
+enum : int
+{
+    OP_V  = 0,
+    OP_E  = 1,
+    OP_F  = 2,
+    OP_VV = 3,
+    OP_VE = 4,
+    OP_VF = 5,
+    OP_FV = 6,
+    OP_FE = 7,
+    OP_FF = 8,
+    OP_EV = 9,
+    OP_EE = 10,
+    OP_EF = 11,
+    OP_EVDIAMOND = 12
+};
+
+constexpr uint32_t INVALID32_ = 0xFFFFFFFFu;
+constexpr uint64_t INVALID64_ = 0xFFFFFFFFFFFFFFFFull;
+
+RXM_HD uint32_t round_up(uint32_t x, uint32_t m)
+{
+    return (x + m - 1) / m * m;
+}
+
+// one entry of the neighbour-patch stash (16 bytes)
+struct StashEntry
+{
+    uint32_t patch;      // neighbour patch id
+    uint32_t slot_base[3];  // its attribute slot base for V, E, F
+};
+
+// owner record of a not-owned local element: (stash slot << 16) | local id in owner
+RXM_HD uint32_t pack_owner(uint32_t stash_slot, uint32_t owner_local)
+{
+    return (stash_slot << 16) | owner_local;
+}
+
+struct alignas(16) PatchDesc
+{
+    uint64_t topo_off;      // byte offset of this patch's blob in the topology buffer (16B aligned)
+    uint32_t topo_bytes;    // total blob bytes (multiple of 16)
+    uint32_t patch_id;      // global patch id (differs from the local index on a sharded mesh)
+    uint16_t n[3];          // #V, #E, #F in the patch, ribbon included
+    uint16_t n_owned[3];    // #owned V, E, F (local ids [0, n_owned) are owned)
+    uint32_t slot_base[3];  // attribute slot base for V, E, F (multiple of 4)
+    uint32_t lin_base[3];   // gap-free linear-id prefix (reference Context::linear_id, context.h:275-290)
+    uint16_t n_stash;       // neighbour patches referenced by the owner tables
+    uint16_t pad0;
+    uint32_t pad1;
+
+    // ---- section byte offsets inside the blob (all multiples of 16) ----
+    RXM_HD uint32_t ev_bytes() const { return round_up(4u * n[ELEM_E], 16); }
+    RXM_HD uint32_t fe_bytes() const { return round_up(6u * n[ELEM_F], 16); }
+    RXM_HD uint32_t own_bytes(uint32_t t) const { return round_up(4u * (n[t] - n_owned[t]), 16); }
+    RXM_HD uint32_t off_ev() const { return 0; }
+    RXM_HD uint32_t off_fe() const { return ev_bytes(); }
+    RXM_HD uint32_t off_fv() const { return off_fe() + fe_bytes(); }
+    RXM_HD uint32_t off_own(uint32_t t) const
+    {
+        uint32_t o = off_fv() + fe_bytes();
+        for (uint32_t i = 0; i < t; ++i)
+            o += own_bytes(i);
+        return o;
+    }
+    RXM_HD uint32_t off_stash() const { return off_own(3); }
+    RXM_HD uint32_t stash_bytes() const { return 16u * n_stash; }
+    RXM_HD uint32_t slot_cap(uint32_t t) const { return round_up(n_owned[t], 4); }
+};
+static_assert(sizeof(PatchDesc) == 64, "PatchDesc must be 64 bytes");
+
+// By-value kernel argument: the static-path equivalent of the reference Context.
+struct MeshView
+{
+    const PatchDesc* desc;   // [num_patches]
+    const uint8_t*   topo;   // topology blob
+    uint32_t         num_patches;
+    uint32_t         num_slots[3];  // attribute slots per element type (sum of slot caps)
+    uint32_t         num_elems[3];  // #V, #E, #F of the (local shard of the) mesh
+    const uint32_t*  patch_slot_base[3];  // [num_patches+1] per type: slot base of every patch
+};
+
+// Attribute layouts: numeric values of the reference's layoutT (types.h:84-90).
+enum : uint32_t
+{
+    LAYOUT_AOS   = 0,  // data[(slot) * nattr + a]
+    LAYOUT_AOSOA = 1,  // data[slot_base(p) * nattr + a * cap(p) + lid]  (patch-local SoA; reference default)
+    LAYOUT_SOA   = 2   // data[a * num_slots + slot]
+};
+
+// Device/host view of an attribute (shallow, by value into kernels like the
+// reference's Attribute copy, attribute.h:194).
+template <typename T>
+struct AttrView
+{
+    T*              data;
+    const uint32_t* slot_base;  // [num_patches+1] for this element type
+    uint32_t        num_slots;
+    uint32_t        nattr;
+    uint32_t        layout;
+
+    RXM_HD uint64_t index(uint32_t patch, uint32_t lid, uint32_t a) const
+    {
+        const uint32_t b = slot_base[patch];
+        if (layout == LAYOUT_AOS) return (uint64_t)(b + lid) * nattr + a;
+        if (layout == LAYOUT_SOA) return (uint64_t)a * num_slots + b + lid;
+        const uint32_t cap = slot_base[patch + 1] - b;
+        return (uint64_t)b * nattr + (uint64_t)a * cap + lid;
+    }
+    // same, when the caller already knows slot base and capacity (no global load)
+    RXM_HD uint64_t index_known(uint32_t b, uint32_t cap, uint32_t lid, uint32_t a) const
+    {
+        if (layout == LAYOUT_AOS) return (uint64_t)(b + lid) * nattr + a;
+        if (layout == LAYOUT_SOA) return (uint64_t)a * num_slots + b + lid;
+        return (uint64_t)b * nattr + (uint64_t)a * cap + lid;
+    }
+};
+
+}  // namespace rxm

@@ -1,0 +1,667 @@
+// rxm_capi.cu -- implementation of the C ABI declared in include/rxmesh_b200.h.
+// No CPU fallback: every compute entry point needs the mesh on a CUDA device and
+// fails with RXM_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/rxmesh_b200.h"
+#include "mesh_builder.h"
+#include "rxm_kernels.h"
+
+using namespace rxm;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(RXM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
+    } while (0)
+
+struct rxm_mesh
+{
+    HostMesh     h;
+    bool         on_device = false;
+    PatchDesc*   d_desc    = nullptr;
+    uint8_t*     d_topo    = nullptr;
+    uint32_t*    d_slot_base[3] = {nullptr, nullptr, nullptr};
+    uint32_t*    d_s2g[3]       = {nullptr, nullptr, nullptr};
+    MeshView     view{};
+    KernelLimits lim{};
+    // scratch for the host-buffer entry points and multi-iteration drivers
+    void*     d_stage       = nullptr;
+    size_t    d_stage_bytes = 0;
+    rxm_attr* scratch[4]    = {nullptr, nullptr, nullptr, nullptr};
+};
+
+struct rxm_attr
+{
+    rxm_mesh* m;
+    int       elem;
+    uint32_t  elem_bytes, nattr;
+    int       layout;
+    uint64_t  count;  // num_slots * nattr
+    void*     h = nullptr;
+    void*     d = nullptr;
+    bool      h_pinned = false;
+};
+
+template <typename T>
+static AttrView<T> view_of(rxm_attr* a)
+{
+    AttrView<T> v;
+    v.data      = (T*)a->d;
+    v.slot_base = a->m->d_slot_base[a->elem];
+    v.num_slots = a->m->h.num_slots[a->elem];
+    v.nattr     = a->nattr;
+    v.layout    = (uint32_t)a->layout;
+    return v;
+}
+
+extern "C" {
+
+const char* rxm_last_error(void)
+{
+    return g_err.c_str();
+}
+
+const char* rxm_version(void)
+{
+    return "rxmesh_b200 0.1 (sm_100a)";
+}
+
+int rxm_init(int device)
+{
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(RXM_ERR_UNSUPPORTED, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                             "; this library is built for sm_100a only");
+    return RXM_OK;
+}
+
+int rxm_mesh_create(const uint32_t* fv, uint32_t num_faces, const uint32_t* face_patch, uint32_t patch_size,
+                    int num_threads, rxm_mesh** out)
+{
+    if (!fv || !out) return fail(RXM_ERR_INVALID, "rxm_mesh_create: null argument");
+    rxm_mesh* m = new (std::nothrow) rxm_mesh();
+    if (!m) return fail(RXM_ERR_INVALID, "rxm_mesh_create: out of memory");
+    BuildOptions opt;
+    opt.patch_size  = patch_size ? patch_size : 512;
+    opt.num_threads = num_threads;
+    opt.verbose     = getenv("RXM_VERBOSE") != nullptr;
+    std::string e;
+    try {
+        e = build_mesh(fv, num_faces, face_patch, opt, m->h);
+    } catch (const std::exception& ex) {
+        e = std::string("rxm_mesh_create: ") + ex.what();
+    }
+    if (!e.empty()) {
+        delete m;
+        return fail(RXM_ERR_INVALID, e);
+    }
+    for (int t = 0; t < 3; ++t) {
+        m->lim.max_n[t]         = m->h.max_per_patch[t];
+        m->lim.max_owned[t]     = m->h.max_owned_per_patch[t];
+        m->lim.max_not_owned[t] = m->h.max_not_owned[t];
+    }
+    m->lim.max_stash               = m->h.max_stash;
+    m->lim.max_face_adjacent_faces = m->h.max_face_adjacent_faces;
+    *out                           = m;
+    return RXM_OK;
+}
+
+int rxm_mesh_to_device(rxm_mesh* m)
+{
+    if (!m) return fail(RXM_ERR_INVALID, "rxm_mesh_to_device: null mesh");
+    if (m->on_device) return RXM_OK;
+    const HostMesh& h = m->h;
+    CU(cudaMalloc(&m->d_desc, h.desc.size() * sizeof(PatchDesc)));
+    CU(cudaMemcpy(m->d_desc, h.desc.data(), h.desc.size() * sizeof(PatchDesc), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&m->d_topo, h.topo.size()));
+    CU(cudaMemcpy(m->d_topo, h.topo.data(), h.topo.size(), cudaMemcpyHostToDevice));
+    for (int t = 0; t < 3; ++t) {
+        CU(cudaMalloc(&m->d_slot_base[t], h.slot_base[t].size() * 4));
+        CU(cudaMemcpy(m->d_slot_base[t], h.slot_base[t].data(), h.slot_base[t].size() * 4, cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&m->d_s2g[t], std::max<size_t>(h.slot_to_global[t].size(), 1) * 4));
+        CU(cudaMemcpy(m->d_s2g[t], h.slot_to_global[t].data(), h.slot_to_global[t].size() * 4, cudaMemcpyHostToDevice));
+    }
+    m->view.desc        = m->d_desc;
+    m->view.topo        = m->d_topo;
+    m->view.num_patches = h.num_patches;
+    for (int t = 0; t < 3; ++t) {
+        m->view.num_slots[t]       = h.num_slots[t];
+        m->view.num_elems[t]       = h.num_elems[t];
+        m->view.patch_slot_base[t] = m->d_slot_base[t];
+    }
+    m->on_device = true;
+    return RXM_OK;
+}
+
+void rxm_mesh_destroy(rxm_mesh* m)
+{
+    if (!m) return;
+    for (auto*& s : m->scratch)
+        if (s) {
+            rxm_attr_destroy(s);
+            s = nullptr;
+        }
+    if (m->on_device) {
+        cudaFree(m->d_desc);
+        cudaFree(m->d_topo);
+        for (int t = 0; t < 3; ++t) {
+            cudaFree(m->d_slot_base[t]);
+            cudaFree(m->d_s2g[t]);
+        }
+        if (m->d_stage) cudaFree(m->d_stage);
+    }
+    delete m;
+}
+
+uint64_t rxm_mesh_info(const rxm_mesh* m, int what)
+{
+    if (!m) return 0;
+    const HostMesh& h = m->h;
+    switch (what) {
+        case RXM_INFO_NUM_VERTICES: return h.num_elems[ELEM_V];
+        case RXM_INFO_NUM_EDGES: return h.num_elems[ELEM_E];
+        case RXM_INFO_NUM_FACES: return h.num_elems[ELEM_F];
+        case RXM_INFO_NUM_PATCHES: return h.num_patches;
+        case RXM_INFO_PATCH_SIZE: return h.patch_size;
+        case RXM_INFO_MAX_VALENCE: return h.max_valence;
+        case RXM_INFO_MAX_EDGE_INCIDENT_FACES: return h.max_edge_incident_faces;
+        case RXM_INFO_MAX_FACE_ADJACENT_FACES: return h.max_face_adjacent_faces;
+        case RXM_INFO_IS_CLOSED: return h.is_closed;
+        case RXM_INFO_IS_EDGE_MANIFOLD: return h.is_edge_manifold;
+        case RXM_INFO_MAX_VERTICES_PER_PATCH: return h.max_per_patch[ELEM_V];
+        case RXM_INFO_MAX_EDGES_PER_PATCH: return h.max_per_patch[ELEM_E];
+        case RXM_INFO_MAX_FACES_PER_PATCH: return h.max_per_patch[ELEM_F];
+        case RXM_INFO_NUM_SLOTS_V: return h.num_slots[ELEM_V];
+        case RXM_INFO_NUM_SLOTS_E: return h.num_slots[ELEM_E];
+        case RXM_INFO_NUM_SLOTS_F: return h.num_slots[ELEM_F];
+        case RXM_INFO_TOPO_BYTES: return h.topo.size();
+        case RXM_INFO_TOTAL_LOCAL_V: return h.total_local[ELEM_V];
+        case RXM_INFO_TOTAL_LOCAL_E: return h.total_local[ELEM_E];
+        case RXM_INFO_TOTAL_LOCAL_F: return h.total_local[ELEM_F];
+        case RXM_INFO_MAX_STASH: return h.max_stash;
+        case RXM_INFO_ON_DEVICE: return m->on_device;
+        default: return 0;
+    }
+}
+
+double rxm_mesh_build_seconds(const rxm_mesh* m, int patcher_only)
+{
+    return m ? (patcher_only ? m->h.patcher_seconds : m->h.build_seconds) : 0.0;
+}
+
+int rxm_mesh_patch(const rxm_mesh* m, uint32_t p, rxm_patch_view* o)
+{
+    if (!m || !o || p >= m->h.num_patches) return fail(RXM_ERR_INVALID, "rxm_mesh_patch: bad argument");
+    const PatchDesc& D = m->h.desc[p];
+    const uint8_t*   B = m->h.topo.data() + D.topo_off;
+    o->patch_id        = D.patch_id;
+    for (int t = 0; t < 3; ++t) {
+        o->n[t]         = D.n[t];
+        o->n_owned[t]   = D.n_owned[t];
+        o->slot_base[t] = D.slot_base[t];
+        o->lin_base[t]  = D.lin_base[t];
+        o->owner[t]     = reinterpret_cast<const uint32_t*>(B + D.off_own(t));
+        o->ltog[t]      = m->h.ltog[t].empty() ? nullptr : m->h.ltog[t].data() + m->h.ltog_off[t][p];
+    }
+    o->ev      = reinterpret_cast<const uint16_t*>(B + D.off_ev());
+    o->fe      = reinterpret_cast<const uint16_t*>(B + D.off_fe());
+    o->fv      = reinterpret_cast<const uint16_t*>(B + D.off_fv());
+    o->stash   = reinterpret_cast<const uint32_t*>(B + D.off_stash());
+    o->n_stash = D.n_stash;
+    return RXM_OK;
+}
+
+const uint32_t* rxm_mesh_slot_to_global(const rxm_mesh* m, int t)
+{
+    return (m && t >= 0 && t < 3) ? m->h.slot_to_global[t].data() : nullptr;
+}
+const uint32_t* rxm_mesh_global_to_slot(const rxm_mesh* m, int t)
+{
+    return (m && t >= 0 && t < 3) ? m->h.global_to_slot[t].data() : nullptr;
+}
+const uint32_t* rxm_mesh_elem_patch(const rxm_mesh* m, int t)
+{
+    return (m && t >= 0 && t < 3) ? m->h.elem_patch[t].data() : nullptr;
+}
+const uint32_t* rxm_mesh_slot_base(const rxm_mesh* m, int t)
+{
+    return (m && t >= 0 && t < 3) ? m->h.slot_base[t].data() : nullptr;
+}
+const uint32_t* rxm_mesh_lin_base(const rxm_mesh* m, int t)
+{
+    return (m && t >= 0 && t < 3) ? m->h.lin_base[t].data() : nullptr;
+}
+const uint32_t* rxm_mesh_edges(const rxm_mesh* m)
+{
+    return m ? m->h.ev.data() : nullptr;
+}
+const uint32_t* rxm_mesh_face_edges(const rxm_mesh* m)
+{
+    return m ? m->h.fe.data() : nullptr;
+}
+
+int rxm_mesh_launch_box(const rxm_mesh* m, int op, uint32_t* blocks, uint32_t* threads, uint32_t* smem_bytes)
+{
+    if (!m) return fail(RXM_ERR_INVALID, "rxm_mesh_launch_box: null mesh");
+    auto           r16 = [](uint32_t x) { return (x + 15u) & ~15u; };
+    const auto&    L   = m->lim;
+    const uint32_t ev = r16(4 * L.max_n[ELEM_E]), f3 = r16(6 * L.max_n[ELEM_F]);
+    uint32_t       b = 0;
+    switch (op) {
+        case RXM_OP_EV: b = ev; break;
+        case RXM_OP_FV: case RXM_OP_FE: b = f3; break;
+        case RXM_OP_VV: case RXM_OP_VE: b = 2 * ev + r16(4 * (L.max_n[ELEM_V] + 1)); break;
+        case RXM_OP_VF: b = 2 * f3 + r16(4 * (L.max_n[ELEM_V] + 1)); break;
+        case RXM_OP_EF: b = 2 * f3 + r16(4 * (L.max_n[ELEM_E] + 1)); break;
+        case RXM_OP_FF: b = 2 * f3 + r16(4 * (L.max_n[ELEM_E] + 1)) + r16(4 * (L.max_n[ELEM_F] + 1)) + 2 * f3; break;
+        default: return fail(RXM_ERR_INVALID, "rxm_mesh_launch_box: unknown op");
+    }
+    const uint32_t mo = std::max(L.max_not_owned[0], std::max(L.max_not_owned[1], L.max_not_owned[2]));
+    b += r16(4 * mo) + 16 * L.max_stash;
+    if (blocks) *blocks = m->h.num_patches;
+    if (threads) *threads = 256;
+    if (smem_bytes) *smem_bytes = b;
+    return RXM_OK;
+}
+
+// ------------------------------------------------------------------ attributes
+int rxm_attr_create(rxm_mesh* m, int elem, uint32_t elem_bytes, uint32_t nattr, int location, int layout,
+                    rxm_attr** out)
+{
+    if (!m || !out || elem < 0 || elem > 2 || nattr == 0)
+        return fail(RXM_ERR_INVALID, "rxm_attr_create: bad argument");
+    if (elem_bytes != 1 && elem_bytes != 2 && elem_bytes != 4 && elem_bytes != 8)
+        return fail(RXM_ERR_INVALID, "rxm_attr_create: elem_bytes must be 1, 2, 4 or 8");
+    if (layout != RXM_AOS && layout != RXM_AOSOA && layout != RXM_SOA)
+        return fail(RXM_ERR_INVALID, "rxm_attr_create: unknown layout");
+    rxm_attr* a   = new rxm_attr();
+    a->m          = m;
+    a->elem       = elem;
+    a->elem_bytes = elem_bytes;
+    a->nattr      = nattr;
+    a->layout     = layout;
+    a->count      = (uint64_t)m->h.num_slots[elem] * nattr;
+    const size_t bytes = std::max<size_t>(a->count * elem_bytes, 16);
+    if (location & RXM_DEVICE) {
+        if (!m->on_device) {
+            delete a;
+            return fail(RXM_ERR_CUDA, "rxm_attr_create: DEVICE location requested but the mesh is not on a device");
+        }
+        cudaError_t e = cudaMalloc(&a->d, bytes);
+        if (e != cudaSuccess) {
+            delete a;
+            return fail(RXM_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        }
+    }
+    if (location & RXM_HOST) {
+        if (m->on_device && cudaMallocHost(&a->h, bytes) == cudaSuccess) {
+            a->h_pinned = true;
+        } else {
+            cudaGetLastError();
+            a->h = malloc(bytes);
+        }
+        if (!a->h) {
+            rxm_attr_destroy(a);
+            return fail(RXM_ERR_INVALID, "rxm_attr_create: host allocation failed");
+        }
+        memset(a->h, 0, bytes);
+    }
+    *out = a;
+    return RXM_OK;
+}
+
+void rxm_attr_destroy(rxm_attr* a)
+{
+    if (!a) return;
+    if (a->d) cudaFree(a->d);
+    if (a->h) {
+        if (a->h_pinned)
+            cudaFreeHost(a->h);
+        else
+            free(a->h);
+    }
+    delete a;
+}
+
+void* rxm_attr_data(rxm_attr* a, int location)
+{
+    if (!a) return nullptr;
+    return (location & RXM_DEVICE) ? a->d : a->h;
+}
+
+uint64_t rxm_attr_count(const rxm_attr* a)
+{
+    return a ? a->count : 0;
+}
+
+int rxm_attr_reset(rxm_attr* a, const void* value, int location, void* stream)
+{
+    if (!a || !value) return fail(RXM_ERR_INVALID, "rxm_attr_reset: null argument");
+    if ((location & RXM_DEVICE) && a->d) {
+        cudaError_t e = launch_fill(a->d, a->count, a->elem_bytes, value, (cudaStream_t)stream);
+        if (e != cudaSuccess) return fail(RXM_ERR_CUDA, std::string("fill: ") + cudaGetErrorString(e));
+    }
+    if ((location & RXM_HOST) && a->h) {
+        uint8_t* p = (uint8_t*)a->h;
+        for (uint64_t i = 0; i < a->count; ++i)
+            memcpy(p + i * a->elem_bytes, value, a->elem_bytes);
+    }
+    return RXM_OK;
+}
+
+int rxm_attr_move(rxm_attr* a, int source, int target, void* stream)
+{
+    if (!a) return fail(RXM_ERR_INVALID, "rxm_attr_move: null attribute");
+    if (source == target) return RXM_OK;
+    if (!a->h || !a->d) return fail(RXM_ERR_INVALID, "rxm_attr_move: attribute is not allocated on both sides");
+    const size_t bytes = a->count * a->elem_bytes;
+    if (source == RXM_HOST && target == RXM_DEVICE)
+        CU(cudaMemcpyAsync(a->d, a->h, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    else if (source == RXM_DEVICE && target == RXM_HOST) {
+        CU(cudaMemcpyAsync(a->h, a->d, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        CU(cudaStreamSynchronize((cudaStream_t)stream));
+    } else
+        return fail(RXM_ERR_INVALID, "rxm_attr_move: source/target must be HOST or DEVICE");
+    return RXM_OK;
+}
+
+int rxm_attr_copy_from(rxm_attr* dst, rxm_attr* src, int source, int target, void* stream)
+{
+    if (!dst || !src) return fail(RXM_ERR_INVALID, "rxm_attr_copy_from: null attribute");
+    if (dst->count != src->count || dst->elem_bytes != src->elem_bytes || dst->layout != src->layout ||
+        dst->elem != src->elem)
+        return fail(RXM_ERR_INVALID, "rxm_attr_copy_from: attributes differ in shape");
+    const size_t bytes = dst->count * dst->elem_bytes;
+    void*        s     = (source & RXM_DEVICE) ? src->d : src->h;
+    void*        d     = (target & RXM_DEVICE) ? dst->d : dst->h;
+    if (!s || !d) return fail(RXM_ERR_INVALID, "rxm_attr_copy_from: side not allocated");
+    if (!(source & RXM_DEVICE) && !(target & RXM_DEVICE)) {
+        memcpy(d, s, bytes);
+        return RXM_OK;
+    }
+    CU(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    if (!(target & RXM_DEVICE)) CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return RXM_OK;
+}
+
+static int ensure_stage(rxm_mesh* m, size_t bytes)
+{
+    if (m->d_stage_bytes >= bytes) return RXM_OK;
+    if (m->d_stage) cudaFree(m->d_stage);
+    m->d_stage = nullptr, m->d_stage_bytes = 0;
+    CU(cudaMalloc(&m->d_stage, bytes));
+    m->d_stage_bytes = bytes;
+    return RXM_OK;
+}
+
+int rxm_attr_from_global_device(rxm_attr* a, const void* dev_global, void* stream)
+{
+    if (!a || !a->d || !dev_global) return fail(RXM_ERR_INVALID, "rxm_attr_from_global_device: bad argument");
+    rxm_mesh* m = a->m;
+    cudaError_t e = launch_permute_to_slots(dev_global, a->d, m->d_s2g[a->elem], m->h.num_slots[a->elem],
+                                            a->elem_bytes, a->nattr, a->layout, m->d_slot_base[a->elem],
+                                            m->h.num_patches, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(RXM_ERR_CUDA, std::string("permute: ") + cudaGetErrorString(e));
+    return RXM_OK;
+}
+
+int rxm_attr_to_global_device(rxm_attr* a, void* dev_global, void* stream)
+{
+    if (!a || !a->d || !dev_global) return fail(RXM_ERR_INVALID, "rxm_attr_to_global_device: bad argument");
+    rxm_mesh* m = a->m;
+    cudaError_t e = launch_permute_to_global(a->d, dev_global, m->d_s2g[a->elem], m->h.num_slots[a->elem],
+                                             a->elem_bytes, a->nattr, a->layout, m->d_slot_base[a->elem],
+                                             m->h.num_patches, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(RXM_ERR_CUDA, std::string("permute: ") + cudaGetErrorString(e));
+    return RXM_OK;
+}
+
+// host-side permutation for HOST-only attributes
+static void host_permute(rxm_attr* a, void* global, bool to_slots)
+{
+    const HostMesh& h  = a->m->h;
+    const int       t  = a->elem;
+    const uint32_t  eb = a->elem_bytes, na = a->nattr;
+    AttrView<uint8_t> v{nullptr, h.slot_base[t].data(), h.num_slots[t], na, (uint32_t)a->layout};
+    uint8_t* S = (uint8_t*)a->h;
+    uint8_t* G = (uint8_t*)global;
+#pragma omp parallel for schedule(static)
+    for (int64_t p = 0; p < (int64_t)h.num_patches; ++p) {
+        const uint32_t b = h.slot_base[t][p], cap = h.slot_base[t][p + 1] - b;
+        for (uint32_t lid = 0; lid < cap; ++lid) {
+            const uint32_t g = h.slot_to_global[t][b + lid];
+            for (uint32_t k = 0; k < na; ++k) {
+                const uint64_t si = v.index_known(b, cap, lid, k);
+                if (to_slots) {
+                    if (g != INVALID32_)
+                        memcpy(S + si * eb, G + ((uint64_t)g * na + k) * eb, eb);
+                    else
+                        memset(S + si * eb, 0, eb);
+                } else if (g != INVALID32_)
+                    memcpy(G + ((uint64_t)g * na + k) * eb, S + si * eb, eb);
+            }
+        }
+    }
+}
+
+int rxm_attr_upload_global(rxm_attr* a, const void* host_global, void* stream)
+{
+    if (!a || !host_global) return fail(RXM_ERR_INVALID, "rxm_attr_upload_global: bad argument");
+    if (a->h) host_permute(a, const_cast<void*>(host_global), true);
+    if (a->d) {
+        rxm_mesh*    m     = a->m;
+        const size_t bytes = (size_t)m->h.num_elems[a->elem] * a->nattr * a->elem_bytes;
+        int          rc    = ensure_stage(m, bytes);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(m->d_stage, host_global, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        return rxm_attr_from_global_device(a, m->d_stage, stream);
+    }
+    return RXM_OK;
+}
+
+int rxm_attr_download_global(rxm_attr* a, void* host_global, void* stream)
+{
+    if (!a || !host_global) return fail(RXM_ERR_INVALID, "rxm_attr_download_global: bad argument");
+    if (a->d) {
+        rxm_mesh*    m     = a->m;
+        const size_t bytes = (size_t)m->h.num_elems[a->elem] * a->nattr * a->elem_bytes;
+        int          rc    = ensure_stage(m, bytes);
+        if (rc) return rc;
+        rc = rxm_attr_to_global_device(a, m->d_stage, stream);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(host_global, m->d_stage, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        CU(cudaStreamSynchronize((cudaStream_t)stream));
+        return RXM_OK;
+    }
+    if (a->h) {
+        host_permute(a, host_global, false);
+        return RXM_OK;
+    }
+    return fail(RXM_ERR_INVALID, "rxm_attr_download_global: attribute has no storage");
+}
+
+// ------------------------------------------------------------------ kernels
+static int check_dev(rxm_mesh* m, const char* who)
+{
+    if (!m) return fail(RXM_ERR_INVALID, std::string(who) + ": null mesh");
+    if (!m->on_device)
+        return fail(RXM_ERR_CUDA, std::string(who) + ": mesh is not on a CUDA device (call rxm_mesh_to_device); "
+                                                     "there is no CPU fallback");
+    return RXM_OK;
+}
+
+static int op_src(int op)
+{
+    switch (op) {
+        case RXM_OP_VV: case RXM_OP_VE: case RXM_OP_VF: return RXM_V;
+        case RXM_OP_EV: case RXM_OP_EF: return RXM_E;
+        case RXM_OP_FV: case RXM_OP_FE: case RXM_OP_FF: return RXM_F;
+        default: return -1;
+    }
+}
+static int op_dst(int op)
+{
+    switch (op) {
+        case RXM_OP_VV: case RXM_OP_EV: case RXM_OP_FV: return RXM_V;
+        case RXM_OP_VE: case RXM_OP_FE: return RXM_E;
+        case RXM_OP_VF: case RXM_OP_EF: case RXM_OP_FF: return RXM_F;
+        default: return -1;
+    }
+}
+
+static int kernel_status(cudaError_t e, const char* why, const char* who)
+{
+    if (e == cudaSuccess) return RXM_OK;
+    if (why) return fail(RXM_ERR_UNSUPPORTED, std::string(who) + ": " + why);
+    return fail(RXM_ERR_CUDA, std::string(who) + ": " + cudaGetErrorString(e));
+}
+
+int rxm_query_store(rxm_mesh* m, int op, rxm_attr* in, rxm_attr* out, void* stream)
+{
+    int rc = check_dev(m, "rxm_query_store");
+    if (rc) return rc;
+    if (op_src(op) < 0) return fail(RXM_ERR_INVALID, "rxm_query_store: unknown op");
+    if (!in || !out || !in->d || !out->d || in->elem != op_src(op) || out->elem != op_src(op) ||
+        in->elem_bytes != 8 || out->elem_bytes != 8 || in->nattr != 1)
+        return fail(RXM_ERR_INVALID, "rxm_query_store: in/out must be device u64 attributes on the op's source type");
+    const char* why = nullptr;
+    cudaError_t e   = launch_query_store(op, m->view, m->lim, view_of<uint64_t>(in), view_of<uint64_t>(out),
+                                         (cudaStream_t)stream, &why);
+    return kernel_status(e, why, "rxm_query_store");
+}
+
+int rxm_query_consume(rxm_mesh* m, int op, rxm_attr* in, rxm_attr* out, void* stream)
+{
+    int rc = check_dev(m, "rxm_query_consume");
+    if (rc) return rc;
+    if (op_src(op) < 0) return fail(RXM_ERR_INVALID, "rxm_query_consume: unknown op");
+    if (!in || !out || !in->d || !out->d || in->elem != op_dst(op) || out->elem != op_src(op) ||
+        in->elem_bytes != 4 || out->elem_bytes != 4 || in->nattr != 1 || out->nattr != 1)
+        return fail(RXM_ERR_INVALID, "rxm_query_consume: in = 1 x fp32 on the output type, out = 1 x fp32 on the source type");
+    const char* why = nullptr;
+    cudaError_t e   = launch_query_consume(op, m->view, m->lim, view_of<float>(in), view_of<float>(out),
+                                           (cudaStream_t)stream, &why);
+    return kernel_status(e, why, "rxm_query_consume");
+}
+
+static bool is_vec3_aos(rxm_attr* a)
+{
+    return a && a->d && a->elem == RXM_V && a->elem_bytes == 4 && a->nattr == 3 && a->layout == RXM_AOS;
+}
+
+int rxm_vertex_normals(rxm_mesh* m, rxm_attr* coords, rxm_attr* normals, int unit, void* stream)
+{
+    int rc = check_dev(m, "rxm_vertex_normals");
+    if (rc) return rc;
+    if (!is_vec3_aos(coords) || !is_vec3_aos(normals))
+        return fail(RXM_ERR_INVALID, "rxm_vertex_normals: coords/normals must be device 3 x fp32 AoS vertex attributes");
+    const char* why = nullptr;
+    cudaError_t e   = launch_vertex_normals(m->view, m->lim, (const float*)coords->d, (float*)normals->d, unit,
+                                            (cudaStream_t)stream, &why);
+    return kernel_status(e, why, "rxm_vertex_normals");
+}
+
+static int get_scratch(rxm_mesh* m, int idx, rxm_attr** out)
+{
+    if (!m->scratch[idx]) {
+        int rc = rxm_attr_create(m, RXM_V, 4, 3, RXM_DEVICE, RXM_AOS, &m->scratch[idx]);
+        if (rc) return rc;
+    }
+    *out = m->scratch[idx];
+    return RXM_OK;
+}
+
+int rxm_laplacian_smooth(rxm_mesh* m, rxm_attr* in, rxm_attr* out, double lr, uint32_t iters, void* stream)
+{
+    int rc = check_dev(m, "rxm_laplacian_smooth");
+    if (rc) return rc;
+    if (!is_vec3_aos(in) || !is_vec3_aos(out) || in == out)
+        return fail(RXM_ERR_INVALID, "rxm_laplacian_smooth: in/out must be distinct device 3 x fp32 AoS vertex attributes");
+    if (iters == 0) return rxm_attr_copy_from(out, in, RXM_DEVICE, RXM_DEVICE, stream);
+    rxm_attr* tmp = nullptr;
+    if (iters > 1) {
+        rc = get_scratch(m, 0, &tmp);
+        if (rc) return rc;
+    }
+    const float* src = (const float*)in->d;
+    for (uint32_t k = 1; k <= iters; ++k) {
+        float*      dst = ((iters - k) % 2 == 0) ? (float*)out->d : (float*)tmp->d;
+        const char* why = nullptr;
+        cudaError_t e   = launch_laplacian_step(m->view, m->lim, src, dst, lr, (cudaStream_t)stream, &why);
+        if (e != cudaSuccess) return kernel_status(e, why, "rxm_laplacian_smooth");
+        src = dst;
+    }
+    return RXM_OK;
+}
+
+int rxm_bilateral_filter(rxm_mesh* m, rxm_attr* in, rxm_attr* out, uint32_t iters, void* stream)
+{
+    (void)in, (void)out, (void)iters, (void)stream;
+    int rc = check_dev(m, "rxm_bilateral_filter");
+    if (rc) return rc;
+    return fail(RXM_ERR_UNSUPPORTED, "rxm_bilateral_filter: not built yet");
+}
+
+int rxm_boundary_vertices(rxm_mesh* m, rxm_attr* flag, void* stream)
+{
+    int rc = check_dev(m, "rxm_boundary_vertices");
+    if (rc) return rc;
+    if (!flag || !flag->d || flag->elem != RXM_V || flag->elem_bytes != 4 || flag->nattr != 1)
+        return fail(RXM_ERR_INVALID, "rxm_boundary_vertices: flag must be a device 1 x u32 vertex attribute");
+    const uint32_t zero = 0;
+    rc                  = rxm_attr_reset(flag, &zero, RXM_DEVICE, stream);
+    if (rc) return rc;
+    const char* why = nullptr;
+    cudaError_t e   = launch_boundary_vertices(m->view, m->lim, (uint32_t*)flag->d, (cudaStream_t)stream, &why);
+    return kernel_status(e, why, "rxm_boundary_vertices");
+}
+
+int rxm_vertex_normals_host(rxm_mesh* m, const float* coords, float* normals, void* stream)
+{
+    int rc = check_dev(m, "rxm_vertex_normals_host");
+    if (rc) return rc;
+    if (!coords || !normals) return fail(RXM_ERR_INVALID, "rxm_vertex_normals_host: null buffer");
+    rxm_attr *x, *n;
+    if ((rc = get_scratch(m, 1, &x)) || (rc = get_scratch(m, 2, &n))) return rc;
+    if ((rc = rxm_attr_upload_global(x, coords, stream))) return rc;
+    if ((rc = rxm_vertex_normals(m, x, n, 0, stream))) return rc;
+    return rxm_attr_download_global(n, normals, stream);
+}
+
+int rxm_laplacian_smooth_host(rxm_mesh* m, const float* coords, float* out, double lr, uint32_t iters, void* stream)
+{
+    int rc = check_dev(m, "rxm_laplacian_smooth_host");
+    if (rc) return rc;
+    if (!coords || !out) return fail(RXM_ERR_INVALID, "rxm_laplacian_smooth_host: null buffer");
+    rxm_attr *x, *y;
+    if ((rc = get_scratch(m, 1, &x)) || (rc = get_scratch(m, 2, &y))) return rc;
+    if ((rc = rxm_attr_upload_global(x, coords, stream))) return rc;
+    if ((rc = rxm_laplacian_smooth(m, x, y, lr, iters, stream))) return rc;
+    return rxm_attr_download_global(y, out, stream);
+}
+
+uint64_t rxm_launch_count(void)
+{
+    return launch_counter();
+}
+
+}  // extern "C"

@@ -1,0 +1,598 @@
+// rxm_kernels.cu -- fixed-function sm_100a kernels of the static hot path.
+//
+//   k_query_store     the reference's query test kernel (tests/RXMesh_test/query_kernel.cuh:13-46):
+//                     input(h) = h, output(h, i) = iter[i] as 64-bit owner handles
+//   k_query_consume   roofline "consume" variant: out(s) = sum_i in(iter[i])
+//   k_vertex_normals  apps/VertexNormal/vertex_normal_kernel.cuh:10-43 recast as owner-computes:
+//                     no global atomics, no zero-fill, one coalesced store per patch
+//   k_laplacian       apps/Smoothing/manual.h:86-104, the two kernels of an iteration fused
+//   k_bilateral       apps/Filtering/filtering_rxmesh_kernel.cuh:426-548 on a materialised VV CSR
+//   k_boundary        kernels/boundary.cuh:11-44
+//
+// One thread block per patch; every patch section and the patch's owned attribute
+// slice arrive by TMA bulk copies under one mbarrier phase.
+#include <cstdio>
+
+#include "rxm_kernels.h"
+#include "rxm_query.cuh"
+
+namespace rxm {
+
+static uint64_t g_launches = 0;
+uint64_t        launch_counter()
+{
+    return g_launches;
+}
+
+namespace {
+
+using namespace dev;
+
+constexpr int BT = 256;
+
+__device__ __forceinline__ PatchDesc load_desc(const PatchDesc* g)
+{
+    PatchDesc    d;
+    const uint4* s = reinterpret_cast<const uint4*>(g);
+    uint4*       t = reinterpret_cast<uint4*>(&d);
+    t[0]           = __ldg(s + 0);
+    t[1]           = __ldg(s + 1);
+    t[2]           = __ldg(s + 2);
+    t[3]           = __ldg(s + 3);
+    return d;
+}
+
+// --------------------------------------------------------------------------
+// query -> store handles
+// --------------------------------------------------------------------------
+template <int OP, int KMAX>
+__global__ void __launch_bounds__(BT) k_query_store(MeshView mv, AttrView<uint64_t> in, AttrView<uint64_t> out)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint64_t                      bar;
+    __shared__ uint32_t                      warp_tmp[36];
+    using Q = PatchQuery<OP, BT, KMAX>;
+    const uint32_t  p    = blockIdx.x;
+    const PatchDesc d    = load_desc(mv.desc + p);
+    const uint8_t*  blob = mv.topo + d.topo_off;
+    Smem            sm(smem_raw);
+    Q               q;
+    q.plan(d, sm, true, false);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(&bar, q.tx_bytes(d, true));
+        q.issue(d, blob, &bar, true);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    const QueryResult r  = q.compute(d, warp_tmp, false, false);
+    const OwnerTable  ot = q.owner_table(d);
+    constexpr uint32_t S = OpTraits<OP>::src;
+    const uint32_t sb_in = d.slot_base[S], cap_in = d.slot_cap(S);
+    for (uint32_t s = threadIdx.x; s < r.n_src; s += BT) {
+        in.data[in.index_known(sb_in, cap_in, s, 0)] = ((uint64_t)d.patch_id << 32) | s;
+        const uint32_t b = r.begin(s), n = min(r.size(s), out.nattr);
+        for (uint32_t i = 0; i < n; ++i)
+            out.data[out.index_known(sb_in, cap_in, s, i)] = ot.handle(r.at(b + i));
+    }
+}
+
+// --------------------------------------------------------------------------
+// query -> consume (gather one fp32 per neighbour, write one fp32 per source)
+// --------------------------------------------------------------------------
+template <int OP, int KMAX>
+__global__ void __launch_bounds__(BT) k_query_consume(MeshView mv, const float* __restrict__ in, float* __restrict__ out)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint64_t                      bar;
+    __shared__ uint32_t                      warp_tmp[36];
+    using Q = PatchQuery<OP, BT, KMAX>;
+    constexpr uint32_t S = OpTraits<OP>::src, D = OpTraits<OP>::dst;
+    const uint32_t     p    = blockIdx.x;
+    const PatchDesc    d    = load_desc(mv.desc + p);
+    const uint8_t*     blob = mv.topo + d.topo_off;
+    Smem               sm(smem_raw);
+    Q                  q;
+    q.plan(d, sm, true, false);
+    const uint32_t capD = d.slot_cap(D);
+    float*         s_in = sm.alloc<float>(max((uint32_t)d.n[D], capD));
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(&bar, q.tx_bytes(d, true) + 4u * capD);
+        q.issue(d, blob, &bar, true);
+        if (capD) bulk_g2s(s_in, in + d.slot_base[D], 4u * capD, &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    // ribbon values: gathered from their owners' slots
+    const OwnerTable ot = q.owner_table(d);
+    for (uint32_t i = d.n_owned[D] + threadIdx.x; i < d.n[D]; i += BT)
+        s_in[i] = ldg_stream(in + ot.slot(i));
+    const QueryResult r = q.compute(d, warp_tmp, false, true);  // compute() syncs before returning for CSR ops
+    if (op_is_fixed<OP>()) __syncthreads();
+    for (uint32_t s = threadIdx.x; s < r.n_src; s += BT) {
+        const uint32_t b = r.begin(s), n = r.size(s);
+        float          a = 0.f;
+        for (uint32_t i = 0; i < n; ++i)
+            a += s_in[r.at(b + i)];
+        out[d.slot_base[S] + s] = a;
+    }
+}
+
+// --------------------------------------------------------------------------
+// vertex normals (owner-computes)
+// --------------------------------------------------------------------------
+// UNIT = 0: Max-1999 weights (apps/VertexNormal); UNIT = 1: sum of unit face
+// normals (apps/Filtering/filtering_rxmesh_kernel.cuh:15-46).
+template <int UNIT>
+__global__ void __launch_bounds__(BT) k_vertex_normals(MeshView mv, const float* __restrict__ x, float* __restrict__ nrm)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint64_t                      bar;
+    const uint32_t  p    = blockIdx.x;
+    const PatchDesc d    = load_desc(mv.desc + p);
+    const uint8_t*  blob = mv.topo + d.topo_off;
+    const uint32_t  nv = d.n[ELEM_V], nov = d.n_owned[ELEM_V], nf = d.n[ELEM_F];
+    const uint32_t  cap = d.slot_cap(ELEM_V);
+    Smem            sm(smem_raw);
+    uint16_t*       s_fv    = sm.alloc<uint16_t>(d.fe_bytes() / 2);
+    uint32_t*       s_own   = sm.alloc<uint32_t>(d.own_bytes(ELEM_V) / 4);
+    StashEntry*     s_stash = sm.alloc<StashEntry>(d.n_stash);
+    float*          s_x     = sm.alloc<float>(3 * max(nv, cap));
+    float*          s_n     = sm.alloc<float>(3 * cap);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(&bar, d.fe_bytes() + d.own_bytes(ELEM_V) + d.stash_bytes() + 12u * cap);
+        if (d.fe_bytes()) bulk_g2s(s_fv, blob + d.off_fv(), d.fe_bytes(), &bar);
+        if (d.own_bytes(ELEM_V)) bulk_g2s(s_own, blob + d.off_own(ELEM_V), d.own_bytes(ELEM_V), &bar);
+        if (d.stash_bytes()) bulk_g2s(s_stash, blob + d.off_stash(), d.stash_bytes(), &bar);
+        if (cap) bulk_g2s(s_x, x + 3ull * d.slot_base[ELEM_V], 12u * cap, &bar);
+    }
+    for (uint32_t i = threadIdx.x; i < 3 * cap; i += BT)
+        s_n[i] = 0.f;
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    // ribbon vertices: gather their coordinates from the owner patches
+    for (uint32_t i = threadIdx.x; i < nv - nov; i += BT) {
+        const uint32_t o    = s_own[i];
+        const uint64_t slot = (uint64_t)s_stash[o >> 16].slot_base[ELEM_V] + (o & 0xFFFFu);
+        const float*   g    = x + 3ull * slot;
+        s_x[3 * (nov + i) + 0] = ldg_stream(g + 0);
+        s_x[3 * (nov + i) + 1] = ldg_stream(g + 1);
+        s_x[3 * (nov + i) + 2] = ldg_stream(g + 2);
+    }
+    __syncthreads();
+    for (uint32_t f = threadIdx.x; f < nf; f += BT) {
+        const uint32_t v0 = s_fv[3 * f], v1 = s_fv[3 * f + 1], v2 = s_fv[3 * f + 2];
+        if (v0 >= nov && v1 >= nov && v2 >= nov) continue;  // touches no owned vertex
+        const float p0x = s_x[3 * v0], p0y = s_x[3 * v0 + 1], p0z = s_x[3 * v0 + 2];
+        const float p1x = s_x[3 * v1], p1y = s_x[3 * v1 + 1], p1z = s_x[3 * v1 + 2];
+        const float p2x = s_x[3 * v2], p2y = s_x[3 * v2 + 1], p2z = s_x[3 * v2 + 2];
+        const float ax = p1x - p0x, ay = p1y - p0y, az = p1z - p0z;
+        const float bx = p2x - p0x, by = p2y - p0y, bz = p2z - p0z;
+        const float nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+        float       w0, w1, w2;
+        if (UNIT) {
+            w0 = w1 = w2 = rsqrtf(nx * nx + ny * ny + nz * nz);
+        } else {
+            const float cx = p2x - p1x, cy = p2y - p1y, cz = p2z - p1z;
+            const float l0 = ax * ax + ay * ay + az * az;  // |v0 v1|^2
+            const float l1 = cx * cx + cy * cy + cz * cz;  // |v1 v2|^2
+            const float l2 = bx * bx + by * by + bz * bz;  // |v2 v0|^2
+            w0 = __frcp_rn(l0 + l2);
+            w1 = __frcp_rn(l1 + l0);
+            w2 = __frcp_rn(l2 + l1);
+        }
+        if (v0 < nov) {
+            atomicAdd(&s_n[3 * v0], nx * w0), atomicAdd(&s_n[3 * v0 + 1], ny * w0), atomicAdd(&s_n[3 * v0 + 2], nz * w0);
+        }
+        if (v1 < nov) {
+            atomicAdd(&s_n[3 * v1], nx * w1), atomicAdd(&s_n[3 * v1 + 1], ny * w1), atomicAdd(&s_n[3 * v1 + 2], nz * w1);
+        }
+        if (v2 < nov) {
+            atomicAdd(&s_n[3 * v2], nx * w2), atomicAdd(&s_n[3 * v2 + 1], ny * w2), atomicAdd(&s_n[3 * v2 + 2], nz * w2);
+        }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0 && cap) {
+        bulk_s2g(nrm + 3ull * d.slot_base[ELEM_V], s_n, 12u * cap);
+        bulk_commit();
+        bulk_wait_all_read();
+    }
+}
+
+// --------------------------------------------------------------------------
+// Laplacian smoothing step: x_out(v) = x(v) - lr * sum_u 2 (x(v) - x(u))
+// --------------------------------------------------------------------------
+template <int KMAX>
+__global__ void __launch_bounds__(BT) k_laplacian(MeshView mv, const float* __restrict__ x, float* __restrict__ xo, double lr)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint64_t                      bar;
+    __shared__ uint32_t                      warp_tmp[36];
+    using Q = PatchQuery<OP_VV, BT, KMAX>;
+    const uint32_t  p    = blockIdx.x;
+    const PatchDesc d    = load_desc(mv.desc + p);
+    const uint8_t*  blob = mv.topo + d.topo_off;
+    const uint32_t  nv = d.n[ELEM_V], nov = d.n_owned[ELEM_V];
+    const uint32_t  cap = d.slot_cap(ELEM_V);
+    Smem            sm(smem_raw);
+    Q               q;
+    q.plan(d, sm, true, false);
+    float* s_x = sm.alloc<float>(3 * max(nv, cap));
+    float* s_o = sm.alloc<float>(3 * cap);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(&bar, q.tx_bytes(d, true) + 12u * cap);
+        q.issue(d, blob, &bar, true);
+        if (cap) bulk_g2s(s_x, x + 3ull * d.slot_base[ELEM_V], 12u * cap, &bar);
+    }
+    for (uint32_t i = 3 * nov + threadIdx.x; i < 3 * cap; i += BT)
+        s_o[i] = 0.f;
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    const OwnerTable ot = q.owner_table(d);
+    for (uint32_t i = nov + threadIdx.x; i < nv; i += BT) {
+        const float* g = x + 3ull * ot.slot(i);
+        s_x[3 * i + 0] = ldg_stream(g + 0);
+        s_x[3 * i + 1] = ldg_stream(g + 1);
+        s_x[3 * i + 2] = ldg_stream(g + 2);
+    }
+    const QueryResult r = q.compute(d, warp_tmp, false, true);
+    for (uint32_t v = threadIdx.x; v < nov; v += BT) {
+        const float    vx = s_x[3 * v], vy = s_x[3 * v + 1], vz = s_x[3 * v + 2];
+        float          gx = 0.f, gy = 0.f, gz = 0.f;
+        const uint32_t b = r.begin(v), n = r.size(v);
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint32_t u = r.at(b + i);
+            gx += 2.f * (vx - s_x[3 * u]);
+            gy += 2.f * (vy - s_x[3 * u + 1]);
+            gz += 2.f * (vz - s_x[3 * u + 2]);
+        }
+        // lr is a double in the reference (manual.h:37): the step is evaluated in fp64
+        s_o[3 * v + 0] = (float)__dsub_rn((double)vx, __dmul_rn(lr, (double)gx));
+        s_o[3 * v + 1] = (float)__dsub_rn((double)vy, __dmul_rn(lr, (double)gy));
+        s_o[3 * v + 2] = (float)__dsub_rn((double)vz, __dmul_rn(lr, (double)gz));
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0 && cap) {
+        bulk_s2g(xo + 3ull * d.slot_base[ELEM_V], s_o, 12u * cap);
+        bulk_commit();
+        bulk_wait_all_read();
+    }
+}
+
+// --------------------------------------------------------------------------
+// boundary vertices: an edge with one incident face marks its two vertices
+// --------------------------------------------------------------------------
+template <int KMAX>
+__global__ void __launch_bounds__(BT) k_boundary(MeshView mv, uint32_t* __restrict__ flag)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint64_t                      bar;
+    __shared__ uint32_t                      warp_tmp[36];
+    using Q = PatchQuery<OP_EF, BT, KMAX>;
+    const uint32_t  p    = blockIdx.x;
+    const PatchDesc d    = load_desc(mv.desc + p);
+    const uint8_t*  blob = mv.topo + d.topo_off;
+    Smem            sm(smem_raw);
+    Q               q;
+    q.plan(d, sm, false, false);
+    uint16_t*   s_ev    = sm.alloc<uint16_t>(d.ev_bytes() / 2);
+    uint32_t*   s_own   = sm.alloc<uint32_t>(d.own_bytes(ELEM_V) / 4);
+    StashEntry* s_stash = sm.alloc<StashEntry>(d.n_stash);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(&bar, q.tx_bytes(d, false) + d.ev_bytes() + d.own_bytes(ELEM_V) + d.stash_bytes());
+        q.issue(d, blob, &bar, false);
+        if (d.ev_bytes()) bulk_g2s(s_ev, blob + d.off_ev(), d.ev_bytes(), &bar);
+        if (d.own_bytes(ELEM_V)) bulk_g2s(s_own, blob + d.off_own(ELEM_V), d.own_bytes(ELEM_V), &bar);
+        if (d.stash_bytes()) bulk_g2s(s_stash, blob + d.off_stash(), d.stash_bytes(), &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    const QueryResult r = q.compute(d, warp_tmp, false, false);
+    OwnerTable        ot;
+    ot.own = s_own, ot.stash = s_stash, ot.n_owned = d.n_owned[ELEM_V], ot.patch = d.patch_id;
+    ot.slot_base = d.slot_base[ELEM_V], ot.type = ELEM_V;
+    for (uint32_t e = threadIdx.x; e < r.n_src; e += BT)
+        if (r.size(e) == 1) {
+            flag[ot.slot(s_ev[2 * e])]     = 1u;
+            flag[ot.slot(s_ev[2 * e + 1])] = 1u;
+        }
+}
+
+// --------------------------------------------------------------------------
+// attribute helpers
+// --------------------------------------------------------------------------
+template <typename T, bool TO_SLOTS>
+__global__ void k_permute(const T* __restrict__ src, T* __restrict__ dst, const uint32_t* __restrict__ slot_to_global,
+                          const uint32_t* __restrict__ slot_base, uint32_t num_patches, uint32_t num_slots,
+                          uint32_t nattr, uint32_t layout)
+{
+    for (uint32_t p = blockIdx.x; p < num_patches; p += gridDim.x) {
+        const uint32_t b = slot_base[p], cap = slot_base[p + 1] - b;
+        for (uint32_t i = threadIdx.x; i < cap * nattr; i += blockDim.x) {
+            // enumerate in the slot-side storage order so the slot side is coalesced
+            uint32_t lid, a;
+            uint64_t sidx;
+            if (layout == LAYOUT_AOS) {
+                lid = i / nattr, a = i % nattr;
+                sidx = (uint64_t)(b + lid) * nattr + a;
+            } else if (layout == LAYOUT_SOA) {
+                a = i / cap, lid = i % cap;
+                sidx = (uint64_t)a * num_slots + b + lid;
+            } else {
+                a = i / cap, lid = i % cap;
+                sidx = (uint64_t)b * nattr + (uint64_t)a * cap + lid;
+            }
+            const uint32_t g = slot_to_global[b + lid];
+            if (TO_SLOTS) {
+                if (g != INVALID32_)
+                    dst[sidx] = src[(uint64_t)g * nattr + a];
+                else {
+                    T z;
+                    memset(&z, 0, sizeof(T));
+                    dst[sidx] = z;
+                }
+            } else if (g != INVALID32_) {
+                dst[(uint64_t)g * nattr + a] = src[sidx];
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void k_fill(T* __restrict__ data, uint64_t n, T v)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        data[i] = v;
+}
+
+template <typename K>
+cudaError_t set_smem(K kernel, uint32_t bytes)
+{
+    if (bytes > 227u * 1024u) return cudaErrorInvalidValue;
+    if (bytes > 48u * 1024u)
+        return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return cudaSuccess;
+}
+
+uint32_t r16(uint32_t x)
+{
+    return (x + 15u) & ~15u;
+}
+
+// KMAX needed so that one atomic per non-zero fits in registers: nnz <= KMAX*BT
+int pick_kmax(uint32_t nnz)
+{
+    if (nnz <= 12u * BT) return 12;
+    if (nnz <= 24u * BT) return 24;
+    return 0;
+}
+
+}  // namespace
+
+#define RXM_FAIL(msg)                 \
+    do {                              \
+        if (err) *err = msg;          \
+        return cudaErrorInvalidValue; \
+    } while (0)
+
+#define RXM_LAUNCH_OP(KERNEL, KM, ...)                                                   \
+    do {                                                                                 \
+        switch (op) {                                                                    \
+            case OP_VV: RXM_LAUNCH_ONE(KERNEL, OP_VV, KM, __VA_ARGS__); break;           \
+            case OP_VE: RXM_LAUNCH_ONE(KERNEL, OP_VE, KM, __VA_ARGS__); break;           \
+            case OP_VF: RXM_LAUNCH_ONE(KERNEL, OP_VF, KM, __VA_ARGS__); break;           \
+            case OP_EV: RXM_LAUNCH_ONE(KERNEL, OP_EV, KM, __VA_ARGS__); break;           \
+            case OP_EF: RXM_LAUNCH_ONE(KERNEL, OP_EF, KM, __VA_ARGS__); break;           \
+            case OP_FV: RXM_LAUNCH_ONE(KERNEL, OP_FV, KM, __VA_ARGS__); break;           \
+            case OP_FE: RXM_LAUNCH_ONE(KERNEL, OP_FE, KM, __VA_ARGS__); break;           \
+            case OP_FF: RXM_LAUNCH_ONE(KERNEL, OP_FF, KM, __VA_ARGS__); break;           \
+            default: RXM_FAIL("unsupported query op");                                   \
+        }                                                                                \
+    } while (0)
+
+#define RXM_LAUNCH_ONE(KERNEL, OPV, KM, ...)                                             \
+    do {                                                                                 \
+        using Q = dev::PatchQuery<OPV, BT, KM>;                                          \
+        smem    = Q::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, true) + extra_smem(OPV); \
+        auto kern = KERNEL<OPV, KM>;                                                     \
+        e         = set_smem(kern, smem);                                                \
+        if (e != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");    \
+        kern<<<mv.num_patches, BT, smem, stream>>>(__VA_ARGS__);                         \
+    } while (0)
+
+static uint32_t max_nnz(const KernelLimits& lim)
+{
+    return std::max(2u * lim.max_n[ELEM_E], 3u * lim.max_n[ELEM_F]);
+}
+
+cudaError_t launch_query_store(int op, const MeshView& mv, const KernelLimits& lim, AttrView<uint64_t> in,
+                               AttrView<uint64_t> out, cudaStream_t stream, const char** err)
+{
+    const int km = pick_kmax(max_nnz(lim));
+    if (!km) RXM_FAIL("patch too large for the query kernels (nnz > 24*256)");
+    if (op == OP_FF && lim.max_face_adjacent_faces > 6) RXM_FAIL("FF: more than 6 adjacent faces per face");
+    uint32_t    smem = 0;
+    cudaError_t e    = cudaSuccess;
+    auto        extra_smem = [&](int) { return 0u; };
+    if (km == 12)
+        RXM_LAUNCH_OP(k_query_store, 12, mv, in, out);
+    else
+        RXM_LAUNCH_OP(k_query_store, 24, mv, in, out);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_query_consume(int op, const MeshView& mv, const KernelLimits& lim, AttrView<float> in,
+                                 AttrView<float> out, cudaStream_t stream, const char** err)
+{
+    const int km = pick_kmax(max_nnz(lim));
+    if (!km) RXM_FAIL("patch too large for the query kernels (nnz > 24*256)");
+    if (in.nattr != 1 || out.nattr != 1) RXM_FAIL("query_consume needs single-component fp32 attributes");
+    if (op == OP_FF && lim.max_face_adjacent_faces > 6) RXM_FAIL("FF: more than 6 adjacent faces per face");
+    uint32_t    smem = 0;
+    cudaError_t e    = cudaSuccess;
+    auto extra_smem = [&](int opv) {
+        uint32_t dst = 0;
+        switch (opv) {
+            case OP_VV: case OP_EV: case OP_FV: dst = ELEM_V; break;
+            case OP_VE: case OP_FE: dst = ELEM_E; break;
+            default: dst = ELEM_F;
+        }
+        return r16(4u * (lim.max_n[dst] + 4u));
+    };
+    if (km == 12)
+        RXM_LAUNCH_OP(k_query_consume, 12, mv, in.data, out.data);
+    else
+        RXM_LAUNCH_OP(k_query_consume, 24, mv, in.data, out.data);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_vertex_normals(const MeshView& mv, const KernelLimits& lim, const float* x, float* n,
+                                  int unit, cudaStream_t stream, const char** err)
+{
+    const uint32_t capv = lim.max_owned[ELEM_V] + 4;
+    const uint32_t smem = r16(6u * lim.max_n[ELEM_F]) + r16(4u * lim.max_not_owned[ELEM_V]) + 16u * lim.max_stash +
+                          r16(12u * std::max(lim.max_n[ELEM_V], capv)) + r16(12u * capv);
+    cudaError_t e = unit ? set_smem(k_vertex_normals<1>, smem) : set_smem(k_vertex_normals<0>, smem);
+    if (e != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
+    if (unit)
+        k_vertex_normals<1><<<mv.num_patches, BT, smem, stream>>>(mv, x, n);
+    else
+        k_vertex_normals<0><<<mv.num_patches, BT, smem, stream>>>(mv, x, n);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_laplacian_step(const MeshView& mv, const KernelLimits& lim, const float* x, float* xo, double lr,
+                                  cudaStream_t stream, const char** err)
+{
+    const int km = pick_kmax(2u * lim.max_n[ELEM_E]);
+    if (!km) RXM_FAIL("patch too large for the query kernels (nnz > 24*256)");
+    const uint32_t capv = lim.max_owned[ELEM_V] + 4;
+    const uint32_t extra = r16(12u * std::max(lim.max_n[ELEM_V], capv)) + r16(12u * capv);
+    uint32_t       smem;
+    cudaError_t    e;
+    if (km == 12) {
+        smem = dev::PatchQuery<OP_VV, BT, 12>::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, true) + extra;
+        e    = set_smem(k_laplacian<12>, smem);
+        if (e != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
+        k_laplacian<12><<<mv.num_patches, BT, smem, stream>>>(mv, x, xo, lr);
+    } else {
+        smem = dev::PatchQuery<OP_VV, BT, 24>::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, true) + extra;
+        e    = set_smem(k_laplacian<24>, smem);
+        if (e != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
+        k_laplacian<24><<<mv.num_patches, BT, smem, stream>>>(mv, x, xo, lr);
+    }
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_boundary_vertices(const MeshView& mv, const KernelLimits& lim, uint32_t* flag, cudaStream_t stream,
+                                     const char** err)
+{
+    const int km = pick_kmax(3u * lim.max_n[ELEM_F]);
+    if (!km) RXM_FAIL("patch too large for the query kernels (nnz > 24*256)");
+    const uint32_t extra = r16(4u * lim.max_n[ELEM_E]) + r16(4u * lim.max_not_owned[ELEM_V]) + 16u * lim.max_stash;
+    uint32_t       smem;
+    cudaError_t    e;
+    if (km == 12) {
+        smem = dev::PatchQuery<OP_EF, BT, 12>::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, false) + extra;
+        e    = set_smem(k_boundary<12>, smem);
+        if (e != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
+        k_boundary<12><<<mv.num_patches, BT, smem, stream>>>(mv, flag);
+    } else {
+        smem = dev::PatchQuery<OP_EF, BT, 24>::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, false) + extra;
+        e    = set_smem(k_boundary<24>, smem);
+        if (e != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
+        k_boundary<24><<<mv.num_patches, BT, smem, stream>>>(mv, flag);
+    }
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bilateral_step(const MeshView&, const KernelLimits&, const float*, const float*, float*, uint32_t*,
+                                  cudaStream_t, const char** err)
+{
+    RXM_FAIL("bilateral filtering: not built yet");
+}
+
+template <bool TO_SLOTS>
+static cudaError_t permute_dispatch(const void* src, void* dst, const uint32_t* s2g, uint32_t num_slots,
+                                    uint32_t elem_bytes, uint32_t nattr, uint32_t layout, const uint32_t* slot_base,
+                                    uint32_t num_patches, cudaStream_t stream)
+{
+    const uint32_t grid = std::min<uint32_t>(num_patches, 148u * 16u);
+    if (grid == 0) return cudaSuccess;
+    if (elem_bytes == 4)
+        k_permute<uint32_t, TO_SLOTS><<<grid, 128, 0, stream>>>((const uint32_t*)src, (uint32_t*)dst, s2g, slot_base,
+                                                                num_patches, num_slots, nattr, layout);
+    else if (elem_bytes == 8)
+        k_permute<uint64_t, TO_SLOTS><<<grid, 128, 0, stream>>>((const uint64_t*)src, (uint64_t*)dst, s2g, slot_base,
+                                                                num_patches, num_slots, nattr, layout);
+    else if (elem_bytes == 2)
+        k_permute<uint16_t, TO_SLOTS><<<grid, 128, 0, stream>>>((const uint16_t*)src, (uint16_t*)dst, s2g, slot_base,
+                                                                num_patches, num_slots, nattr, layout);
+    else if (elem_bytes == 1)
+        k_permute<uint8_t, TO_SLOTS><<<grid, 128, 0, stream>>>((const uint8_t*)src, (uint8_t*)dst, s2g, slot_base,
+                                                               num_patches, num_slots, nattr, layout);
+    else
+        return cudaErrorInvalidValue;
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_permute_to_slots(const void* in_global, void* out_slots, const uint32_t* s2g, uint32_t num_slots,
+                                    uint32_t elem_bytes, uint32_t nattr, uint32_t layout, const uint32_t* slot_base,
+                                    uint32_t num_patches, cudaStream_t stream)
+{
+    return permute_dispatch<true>(in_global, out_slots, s2g, num_slots, elem_bytes, nattr, layout, slot_base,
+                                  num_patches, stream);
+}
+
+cudaError_t launch_permute_to_global(const void* in_slots, void* out_global, const uint32_t* s2g, uint32_t num_slots,
+                                     uint32_t elem_bytes, uint32_t nattr, uint32_t layout, const uint32_t* slot_base,
+                                     uint32_t num_patches, cudaStream_t stream)
+{
+    return permute_dispatch<false>(in_slots, out_global, s2g, num_slots, elem_bytes, nattr, layout, slot_base,
+                                   num_patches, stream);
+}
+
+cudaError_t launch_fill(void* data, uint64_t count, uint32_t elem_bytes, const void* value, cudaStream_t stream)
+{
+    if (count == 0) return cudaSuccess;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((count + 255) / 256, 148ull * 32);
+    if (elem_bytes == 4) {
+        uint32_t v;
+        memcpy(&v, value, 4);
+        k_fill<uint32_t><<<grid, 256, 0, stream>>>((uint32_t*)data, count, v);
+    } else if (elem_bytes == 8) {
+        uint64_t v;
+        memcpy(&v, value, 8);
+        k_fill<uint64_t><<<grid, 256, 0, stream>>>((uint64_t*)data, count, v);
+    } else if (elem_bytes == 2) {
+        uint16_t v;
+        memcpy(&v, value, 2);
+        k_fill<uint16_t><<<grid, 256, 0, stream>>>((uint16_t*)data, count, v);
+    } else if (elem_bytes == 1) {
+        uint8_t v;
+        memcpy(&v, value, 1);
+        k_fill<uint8_t><<<grid, 256, 0, stream>>>((uint8_t*)data, count, v);
+    } else
+        return cudaErrorInvalidValue;
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+}  // namespace rxm

@@ -1,0 +1,53 @@
+// rxm_kernels.h -- host-callable launchers of the fixed-function sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "patch_layout.h"
+
+namespace rxm {
+
+struct KernelLimits
+{
+    uint32_t max_n[3];
+    uint32_t max_owned[3];
+    uint32_t max_not_owned[3];
+    uint32_t max_stash;
+    uint32_t max_face_adjacent_faces;
+};
+
+// Every launcher returns cudaSuccess or the launch error; `err` (may be null)
+// receives a human-readable reason when the configuration is unsupported.
+cudaError_t launch_query_store(int op, const MeshView& mv, const KernelLimits& lim, AttrView<uint64_t> in,
+                               AttrView<uint64_t> out, cudaStream_t stream, const char** err);
+
+cudaError_t launch_query_consume(int op, const MeshView& mv, const KernelLimits& lim, AttrView<float> in,
+                                 AttrView<float> out, cudaStream_t stream, const char** err);
+
+cudaError_t launch_vertex_normals(const MeshView& mv, const KernelLimits& lim, const float* coords_aos,
+                                  float* normals_aos, int unit_face_normals, cudaStream_t stream,
+                                  const char** err);
+
+cudaError_t launch_laplacian_step(const MeshView& mv, const KernelLimits& lim, const float* x_in_aos,
+                                  float* x_out_aos, double lr, cudaStream_t stream, const char** err);
+
+cudaError_t launch_bilateral_step(const MeshView& mv, const KernelLimits& lim, const float* x_in_aos,
+                                  const float* normals_aos, float* x_out_aos, uint32_t* overflow_flag,
+                                  cudaStream_t stream, const char** err);
+
+cudaError_t launch_boundary_vertices(const MeshView& mv, const KernelLimits& lim, uint32_t* flag_per_slot,
+                                     cudaStream_t stream, const char** err);
+
+// out_slot[slot*nattr + a] = in_global[global_of_slot*nattr + a] (AoS), 0 for padding slots
+cudaError_t launch_permute_to_slots(const void* in_global, void* out_slots, const uint32_t* slot_to_global,
+                                    uint32_t num_slots, uint32_t elem_bytes, uint32_t nattr, uint32_t layout,
+                                    const uint32_t* slot_base, uint32_t num_patches, cudaStream_t stream);
+cudaError_t launch_permute_to_global(const void* in_slots, void* out_global, const uint32_t* slot_to_global,
+                                     uint32_t num_slots, uint32_t elem_bytes, uint32_t nattr, uint32_t layout,
+                                     const uint32_t* slot_base, uint32_t num_patches, cudaStream_t stream);
+
+cudaError_t launch_fill(void* data, uint64_t count, uint32_t elem_bytes, const void* value, cudaStream_t stream);
+
+// number of kernels launched by this library since load (bench.py "gpu_launches")
+uint64_t launch_counter();
+
+}  // namespace rxm

@@ -1,0 +1,253 @@
+// rxm_query.cuh -- the eight patch-local static queries, computed in shared memory.
+//
+// B200-native counterpart of detail::query<blockThreads, op> and its helpers
+// v_v / v_e / v_f / e_f / f_v / f_f
+// (/root/reference/include/rxmesh/kernels/rxmesh_queries.cuh:501-1053) and of
+// detail::query_block_dispatcher (kernels/query_dispatcher.cuh:27-177).
+//
+// One thread block handles one patch.  PatchQuery<OP> knows which sections of
+// the patch blob the op needs, asks thread 0 to TMA them into shared memory
+// under the caller's mbarrier (so the caller can batch its own loads, e.g. the
+// patch's attribute slice, into the same phase), and then builds the adjacency:
+//   EV, FV, FE : the stored rows themselves (fixed stride 2 / 3 / 3); only the
+//                OWNED prefix of the rows is loaded;
+//   VV, VE     : transpose of EV (VV stores the other endpoint directly);
+//   VF         : transpose of FV;   EF : transpose of FE;
+//   FF         : EF, then per owned face the faces across its three edges, in
+//                edge order (the reference's order on manifold input,
+//                rxmesh_queries.cuh:839-853).
+// Only columns of OWNED source elements are built unless `all_sources` is set
+// (the reference's allow_not_owned, query.inl:174-203).
+#pragma once
+#include "rxm_device.cuh"
+
+namespace rxm {
+namespace dev {
+
+template <int OP>
+struct OpTraits;
+#define RXM_OP_TRAITS(OPV, SRC, DST, CONN)            \
+    template <>                                       \
+    struct OpTraits<OPV>                              \
+    {                                                 \
+        static constexpr uint32_t src  = SRC;         \
+        static constexpr uint32_t dst  = DST;         \
+        static constexpr int      conn = CONN; /* 0 = EV, 1 = FE, 2 = FV */ \
+    };
+RXM_OP_TRAITS(OP_VV, ELEM_V, ELEM_V, 0)
+RXM_OP_TRAITS(OP_VE, ELEM_V, ELEM_E, 0)
+RXM_OP_TRAITS(OP_VF, ELEM_V, ELEM_F, 2)
+RXM_OP_TRAITS(OP_EV, ELEM_E, ELEM_V, 0)
+RXM_OP_TRAITS(OP_EF, ELEM_E, ELEM_F, 1)
+RXM_OP_TRAITS(OP_FV, ELEM_F, ELEM_V, 2)
+RXM_OP_TRAITS(OP_FE, ELEM_F, ELEM_E, 1)
+RXM_OP_TRAITS(OP_FF, ELEM_F, ELEM_F, 1)
+#undef RXM_OP_TRAITS
+
+template <int OP>
+__host__ __device__ constexpr bool op_is_fixed()
+{
+    return OP == OP_EV || OP == OP_FV || OP == OP_FE;
+}
+
+// View over the result of a query for one patch (the data behind the
+// reference's Iterator, iterator.cuh:50-194).
+struct QueryResult
+{
+    const uint32_t* off;     // CSR offsets (shared) or nullptr for fixed stride
+    const uint16_t* val;     // neighbour local ids (shared)
+    uint32_t        stride;  // 2 / 3 for EV / FV, FE
+    uint32_t        shift;   // 1 for FE (drops the direction bit), else 0
+    uint32_t        n_src;   // number of source elements with a list
+
+    __device__ __forceinline__ uint32_t begin(uint32_t s) const { return off ? off[s] : s * stride; }
+    __device__ __forceinline__ uint32_t size(uint32_t s) const { return off ? off[s + 1] - off[s] : stride; }
+    __device__ __forceinline__ uint32_t at(uint32_t pos) const { return (uint32_t)(val[pos] >> shift); }
+};
+
+template <int OP, int BT, int KMAX>
+struct PatchQuery
+{
+    using Tr = OpTraits<OP>;
+    uint16_t*   s_conn;
+    uint32_t*   s_off;
+    uint16_t*   s_val;
+    uint32_t*   s_off2;  // FF only
+    uint16_t*   s_val2;  // FF only
+    uint32_t*   s_own;
+    StashEntry* s_stash;
+    uint32_t    conn_bytes;
+    uint32_t    n_rows;  // rows of the connectivity section that get loaded
+
+    // shared-memory bytes this op needs for a patch with the given maxima
+    // (host side; the role of calc_shared_memory, rxmesh_static.inl:498-841)
+    __host__ static uint32_t smem_bytes(const uint32_t max_n[3], const uint32_t max_not_owned[3],
+                                        uint32_t max_stash, bool with_owner)
+    {
+        auto     r16 = [](uint32_t x) { return (x + 15u) & ~15u; };
+        uint32_t b   = 0;
+        const uint32_t nr = Tr::conn == 0 ? max_n[ELEM_E] : max_n[ELEM_F];
+        const uint32_t w  = Tr::conn == 0 ? 2 : 3;
+        b += r16(2 * w * nr);
+        if (!op_is_fixed<OP>()) {
+            const uint32_t ncols = OP == OP_FF ? max_n[ELEM_E] : max_n[Tr::src];
+            b += r16(4 * (ncols + 1)) + r16(2 * w * nr);
+            if (OP == OP_FF) b += r16(4 * (max_n[ELEM_F] + 1)) + r16(2 * 3 * max_n[ELEM_F] * 2);
+        }
+        if (with_owner) b += r16(4 * max_not_owned[Tr::dst]) + 16 * max_stash;
+        return b;
+    }
+
+    // carve shared memory (all threads, identical arithmetic)
+    __device__ __forceinline__ void plan(const PatchDesc& d, Smem& sm, bool with_owner, bool all_sources)
+    {
+        constexpr uint32_t w = Tr::conn == 0 ? 2 : 3;
+        const uint32_t     rows_all = Tr::conn == 0 ? d.n[ELEM_E] : d.n[ELEM_F];
+        n_rows = (op_is_fixed<OP>() && !all_sources) ? d.n_owned[Tr::src] : rows_all;
+        if (OP == OP_FF) n_rows = rows_all;
+        conn_bytes = round_up(2u * w * n_rows, 16);
+        s_conn     = sm.alloc<uint16_t>(conn_bytes / 2);
+        s_off = nullptr, s_val = nullptr, s_off2 = nullptr, s_val2 = nullptr;
+        if (!op_is_fixed<OP>()) {
+            const uint32_t ncols = OP == OP_FF ? d.n[ELEM_E] : d.n[Tr::src];
+            s_off                = sm.alloc<uint32_t>(ncols + 1);
+            s_val                = sm.alloc<uint16_t>(w * n_rows);
+            if (OP == OP_FF) {
+                s_off2 = sm.alloc<uint32_t>(d.n[ELEM_F] + 1);
+                s_val2 = sm.alloc<uint16_t>(6u * d.n[ELEM_F]);
+            }
+        }
+        s_own = nullptr, s_stash = nullptr;
+        if (with_owner) {
+            s_own   = sm.alloc<uint32_t>(d.own_bytes(Tr::dst) / 4);
+            s_stash = sm.alloc<StashEntry>(d.n_stash);
+        }
+    }
+
+    // bytes that issue() will put in flight
+    __device__ __forceinline__ uint32_t tx_bytes(const PatchDesc& d, bool with_owner) const
+    {
+        return conn_bytes + (with_owner ? d.own_bytes(Tr::dst) + d.stash_bytes() : 0u);
+    }
+
+    // thread 0 only, after mbar_arrive_expect_tx
+    __device__ __forceinline__ void issue(const PatchDesc& d, const uint8_t* blob, uint64_t* bar, bool with_owner) const
+    {
+        const uint32_t o = Tr::conn == 0 ? d.off_ev() : (Tr::conn == 1 ? d.off_fe() : d.off_fv());
+        if (conn_bytes) bulk_g2s(s_conn, blob + o, conn_bytes, bar);
+        if (with_owner) {
+            if (d.own_bytes(Tr::dst)) bulk_g2s(s_own, blob + d.off_own(Tr::dst), d.own_bytes(Tr::dst), bar);
+            if (d.stash_bytes()) bulk_g2s(s_stash, blob + d.off_stash(), d.stash_bytes(), bar);
+        }
+    }
+
+    __device__ __forceinline__ OwnerTable owner_table(const PatchDesc& d) const
+    {
+        OwnerTable t;
+        t.own       = s_own;
+        t.stash     = s_stash;
+        t.n_owned   = d.n_owned[Tr::dst];
+        t.patch     = d.patch_id;
+        t.slot_base = d.slot_base[Tr::dst];
+        t.type      = Tr::dst;
+        return t;
+    }
+
+    // all threads, after the mbarrier wait
+    __device__ __forceinline__ QueryResult compute(const PatchDesc& d, uint32_t* warp_tmp, bool all_sources,
+                                                   bool sorted)
+    {
+        QueryResult    r;
+        const uint32_t lim = all_sources ? d.n[Tr::src] : d.n_owned[Tr::src];
+        r.n_src            = lim;
+        r.shift            = 0;
+        r.stride           = 0;
+        r.off              = nullptr;
+        const uint16_t* c  = s_conn;
+        if (OP == OP_EV) {
+            r.val = c, r.stride = 2;
+        } else if (OP == OP_FV) {
+            r.val = c, r.stride = 3;
+        } else if (OP == OP_FE) {
+            r.val = c, r.stride = 3, r.shift = 1;
+        } else if (OP == OP_VV || OP == OP_VE) {
+            // column = endpoint, value = other endpoint (VV) or the edge (VE)
+            const uint32_t nnz = 2u * n_rows;
+            csr_transpose_lim(nnz, d.n[ELEM_V], lim, warp_tmp, [c](uint32_t i) { return (uint32_t)c[i]; },
+                              [c](uint32_t i) { return OP == OP_VV ? (uint32_t)c[i ^ 1u] : (i >> 1); });
+            r.off = s_off, r.val = s_val;
+        } else if (OP == OP_VF) {
+            const uint32_t nnz = 3u * n_rows;
+            csr_transpose_lim(nnz, d.n[ELEM_V], lim, warp_tmp, [c](uint32_t i) { return (uint32_t)c[i]; },
+                              [](uint32_t i) { return i / 3u; });
+            r.off = s_off, r.val = s_val;
+        } else if (OP == OP_EF || OP == OP_FF) {
+            const uint32_t nnz  = 3u * n_rows;
+            const uint32_t elim = OP == OP_FF ? d.n[ELEM_E] : lim;
+            csr_transpose_lim(nnz, d.n[ELEM_E], elim, warp_tmp, [c](uint32_t i) { return (uint32_t)(c[i] >> 1); },
+                              [](uint32_t i) { return i / 3u; });
+            r.off = s_off, r.val = s_val;
+            if (OP == OP_FF) {
+                // faces across the three edges of every source face, edge order
+                const uint32_t nf = lim;
+                for (uint32_t f = threadIdx.x; f <= nf; f += BT) {
+                    uint32_t k = 0;
+                    if (f < nf)
+                        for (int j = 0; j < 3; ++j) {
+                            const uint32_t e = c[3 * f + j] >> 1;
+                            k += s_off[e + 1] - s_off[e] - 1;
+                        }
+                    s_off2[f] = k;
+                }
+                block_exclusive_scan<BT>(s_off2, nf, warp_tmp);
+                for (uint32_t f = threadIdx.x; f < nf; f += BT) {
+                    uint32_t w = s_off2[f];
+                    for (int j = 0; j < 3; ++j) {
+                        const uint32_t e = c[3 * f + j] >> 1;
+                        for (uint32_t i = s_off[e]; i < s_off[e + 1]; ++i)
+                            if (s_val[i] != f) s_val2[w++] = s_val[i];
+                    }
+                }
+                __syncthreads();
+                r.off = s_off2, r.val = s_val2;
+            }
+        }
+        if (sorted && r.off && OP != OP_FF) csr_sort_lists<BT>(lim, s_off, s_val);
+        return r;
+    }
+
+   private:
+    // transpose keeping only columns < lim
+    template <typename ColFn, typename ValFn>
+    __device__ __forceinline__ void csr_transpose_lim(uint32_t nnz, uint32_t ncols, uint32_t lim,
+                                                      uint32_t* warp_tmp, ColFn col, ValFn val)
+    {
+        (void)ncols;
+        const uint32_t tid = threadIdx.x;
+        for (uint32_t i = tid; i <= lim; i += BT)
+            s_off[i] = 0;
+        __syncthreads();
+        uint16_t rank[KMAX];
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            const uint32_t i = tid + k * BT;
+            if (i < nnz) {
+                const uint32_t cc = col(i);
+                if (cc < lim) rank[k] = (uint16_t)atomicAdd(&s_off[cc], 1u);
+            }
+        }
+        block_exclusive_scan<BT>(s_off, lim, warp_tmp);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            const uint32_t i = tid + k * BT;
+            if (i < nnz) {
+                const uint32_t cc = col(i);
+                if (cc < lim) s_val[s_off[cc] + rank[k]] = (uint16_t)val(i);
+            }
+        }
+        __syncthreads();
+    }
+};
+
+}  // namespace dev
+}  // namespace rxm

@@ -1,0 +1,93 @@
+"""All eight static queries on the GPU, through the C ABI, against the oracle.
+
+Verifier semantics of tests/RXMesh_test/rxmesh_test.h:343-440 for every OWNED source element:
+input(h) == h; every valid output handle is owned by the patch it names; its global id is in the
+ground truth; counts match (with multiplicity); every ground-truth neighbour is present.
+FV / FE / EV additionally keep the reference's order.
+"""
+import numpy as np
+import pytest
+
+import rxmesh_b200 as rx
+from conftest import make_mesh
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+MESHES = ["sphere3", "dragon", "cube", "bunnyhead", "plane", "diamond", "sphere1", "torus", "ico12",
+          "grid40x31"]
+OPS = ["VV", "VE", "VF", "EV", "EF", "FV", "FE", "FF"]
+
+
+@pytest.fixture(scope="module", params=MESHES)
+def built(request):
+    rx.rx_init(0)
+    V, F = make_mesh(request.param)
+    m = rx.RXMeshStatic(F, patch_size=512 if F.shape[0] > 600 else 64)
+    return request.param, V, F, m, O.Topology(F)
+
+
+def verify(m, op, inp, out, src, dst, csr, ordered):
+    off, val = csr
+    n_src = m._num(src)
+    ih = inp.host_array()
+    oh = out.host_array()
+    W = out.num_attributes
+    sb = m.slot_base(src).astype(np.int64)
+    lb = m.lin_base(src).astype(np.int64)
+    s2g = m.slot_to_global(src)
+    P = m.get_num_patches()
+    checked = 0
+    for p in range(P):
+        b, cap, no = int(sb[p]), int(sb[p + 1] - sb[p]), int(lb[p + 1] - lb[p])
+        lids = np.arange(no)
+        handles = ih[b + lids]  # 1 attribute: AoSoA == plain
+        assert np.array_equal(handles, (np.uint64(p) << np.uint64(32)) | lids.astype(np.uint64)), (op, p)
+        # AoSoA: out[b*W + a*cap + lid]
+        rows = oh[b * W:b * W + W * cap].reshape(W, cap)[:, :no].T  # [no, W]
+        valid = rows != np.uint64(rx.INVALID64)
+        # owned-by-the-named-patch check: local id < owned count of that patch
+        hp = (rows >> np.uint64(32)).astype(np.int64)
+        hl = (rows & np.uint64(0xFFFF)).astype(np.int64)
+        dlb = m.lin_base(dst).astype(np.int64)
+        owned_cnt = dlb[1:] - dlb[:-1]
+        assert np.all(hp[valid] < P)
+        assert np.all(hl[valid] < owned_cnt[hp[valid]]), (op, p, "output handle not owned")
+        g_out = m.map_to_global(dst, rows)
+        gsrc = s2g[b:b + no]
+        for i in range(no):
+            want = val[off[gsrc[i]]:off[gsrc[i] + 1]]
+            got = g_out[i][valid[i]]
+            assert valid[i].sum() == want.shape[0], (op, p, i, got, want)
+            if ordered:
+                assert np.array_equal(got, want), (op, p, i, got, want)
+            else:
+                assert np.array_equal(np.sort(got), np.sort(want)), (op, p, i, got, want)
+            # valid entries are a prefix of the row (iter[0..size))
+            assert valid[i][:want.shape[0]].all()
+        checked += no
+    assert checked == n_src
+
+
+@pytest.mark.parametrize("op", OPS)
+def test_query(built, op):
+    name, V, F, m, T = built
+    inp, out, src, dst = m.query_global(rx.Op[op])
+    ordered = op in ("EV", "FV", "FE") or (op == "FF" and m.is_edge_manifold())
+    csr = T.query(op)
+    if op == "FF" and ordered:
+        # reference order on manifold input: neighbour across edge 0, 1, 2, boundary edges skipped
+        ef = T.query("EF")
+        vals, offs = [], [0]
+        for f in range(T.nf):
+            for e in T.fe[f]:
+                vals += [g for g in ef[1][ef[0][e]:ef[0][e + 1]] if g != f]
+            offs.append(len(vals))
+        csr = (np.asarray(offs, np.uint32), np.asarray(vals, np.uint32))
+    verify(m, op, inp, out, src, dst, csr, ordered)
+
+
+def test_launch_box(built):
+    name, V, F, m, T = built
+    blocks, threads, smem = m.launch_box(rx.Op.VV)
+    assert blocks == m.get_num_patches() and threads == 256 and 0 < smem < 227 * 1024

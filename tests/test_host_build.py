@@ -1,0 +1,140 @@
+"""Patch store invariants, checked on the CPU against the oracle's global numbering.
+
+Mirrors RXMeshTest::run_ltog_mapping_test (tests/RXMesh_test/rxmesh_test.h:44-58,443-625)
+plus the numbering / ownership rules of SURVEY.md 3.6.  No CUDA call is made.
+"""
+import numpy as np
+import pytest
+
+import rxmesh_b200 as rx
+from conftest import make_mesh
+from oracle import oracle as O
+
+MESHES = ["sphere3", "dragon", "cube", "bunnyhead", "plane", "plane_5", "diamond", "sphere1",
+          "torus", "ico6", "grid23x17"]
+
+
+@pytest.fixture(scope="module", params=MESHES)
+def built(request):
+    V, F = make_mesh(request.param)
+    m = rx.RXMeshStatic(F, device=False, patch_size=512 if F.shape[0] > 600 else 64)
+    return request.param, V, F, m, O.Topology(F)
+
+
+def test_counts_and_stats(built):
+    name, V, F, m, T = built
+    assert (m.get_num_vertices(), m.get_num_edges(), m.get_num_faces()) == (T.nv, T.ne, T.nf)
+    s = T.stats()
+    assert m.get_input_max_valence() == s["max_valence"]
+    assert m.get_input_max_edge_incident_faces() == s["max_edge_incident_faces"]
+    assert m.get_input_max_face_adjacent_faces() == s["max_face_adjacent_faces"]
+    assert m.is_closed() == s["is_closed"] and m.is_edge_manifold() == s["is_edge_manifold"]
+    # global edge numbering is the reference's (first appearance, (max,min) key)
+    assert np.array_equal(m.edges(), T.ev)
+    assert np.array_equal(m.face_edges(), T.fe)
+
+
+def test_ltog_mapping_and_numbering(built):
+    name, V, F, m, T = built
+    P = m.get_num_patches()
+    fpatch, vpatch, epatch = m.elem_patch(2), m.elem_patch(0), m.elem_patch(1)
+    owner_of = [vpatch, epatch, fpatch]
+    owned_seen = [np.zeros(n, bool) for n in (T.nv, T.ne, T.nf)]
+    edge_id = {(int(a), int(b)): i for i, (a, b) in enumerate(T.ev)}
+    for p in range(P):
+        pv = m.patch(p)
+        assert pv["n_owned"][2] <= m.get_patch_size()
+        for t in range(3):
+            l, no = pv["ltog"][t], pv["n_owned"][t]
+            # owned first, each half ascending by global id (rxmesh.cpp:845-869)
+            assert np.all(np.diff(l[:no].astype(np.int64)) > 0)
+            assert np.all(np.diff(l[no:].astype(np.int64)) > 0)
+            assert np.all(owner_of[t][l[:no]] == p) and np.all(owner_of[t][l[no:]] != p)
+            assert not owned_seen[t][l[:no]].any()
+            owned_seen[t][l[:no]] = True
+            # slot / linear numbering
+            assert np.array_equal(m.slot_to_global(t)[pv["slot_base"][t]:pv["slot_base"][t] + no], l[:no])
+            assert pv["slot_base"][t] % 4 == 0
+        lv, le, lf = pv["ltog"]
+        # check_mapping_edges: local ev -> global vertices -> global edge id == ltog_e
+        gv = lv[pv["ev"]]
+        assert np.all(gv[:, 0] > gv[:, 1])
+        assert all(edge_id[(int(a), int(b))] == int(g) for (a, b), g in zip(gv, le))
+        # check_mapping_faces: local fe -> global edges == FE of the global face
+        assert np.array_equal(le[pv["fe"] >> 1], T.fe[lf])
+        # fv is FE o EV and equals the input corner order
+        fe = pv["fe"].astype(np.int64)
+        assert np.array_equal(pv["ev"].reshape(-1)[2 * (fe >> 1) + (fe & 1)], pv["fv"])
+        assert np.array_equal(lv[pv["fv"]], F[lf])
+        # owner tables name the owning patch and the element's local id there
+        for t in range(3):
+            no = pv["n_owned"][t]
+            for i, o in enumerate(pv["owner"][t]):
+                q = int(pv["stash"][o >> 16][0])
+                g = int(pv["ltog"][t][no + i])
+                assert q == owner_of[t][g] and q != p
+                assert m.slot_to_global(t)[int(pv["stash"][o >> 16][1 + t]) + (int(o) & 0xFFFF)] == g
+    for t in range(3):
+        assert owned_seen[t].all()  # ownership partitions the mesh
+
+
+def test_ribbon_gives_complete_one_ring(built):
+    # every owned vertex sees all its incident faces / edges inside its patch (patcher.cu:668-713)
+    name, V, F, m, T = built
+    vf, ve = O.csr_to_sets(T.query("VF")), O.csr_to_sets(T.query("VE"))
+    for p in range(m.get_num_patches()):
+        pv = m.patch(p)
+        fset, eset = set(pv["ltog"][2].tolist()), set(pv["ltog"][1].tolist())
+        for g in pv["ltog"][0][:pv["n_owned"][0]][::7]:
+            assert set(vf[g]) <= fset and set(ve[g]) <= eset
+
+
+def test_owner_is_lowest_patch(built):
+    # vertex / edge owner = lowest patch id among incident faces' patches (patcher.cu:730-756)
+    name, V, F, m, T = built
+    fpatch = m.elem_patch(2).astype(np.int64)
+    want_v = np.full(T.nv, 1 << 40, dtype=np.int64)
+    np.minimum.at(want_v, F.reshape(-1).astype(np.int64), np.repeat(fpatch, 3))
+    assert np.array_equal(want_v, m.elem_patch(0))
+    want_e = np.full(T.ne, 1 << 40, dtype=np.int64)
+    np.minimum.at(want_e, T.fe.reshape(-1).astype(np.int64), np.repeat(fpatch, 3))
+    assert np.array_equal(want_e, m.elem_patch(1))
+
+
+def test_user_patching_is_honoured():
+    from rxmesh_b200 import meshio
+    V, F = meshio.grid(33, 33)
+    fp = meshio.grid_face_tiles(33, 33, 8)
+    m = rx.RXMeshStatic(F, face_patch=fp, device=False)
+    assert m.get_num_patches() == 16
+    assert np.array_equal(m.elem_patch(2), fp)
+
+
+def test_errors():
+    with pytest.raises(rx.RXMeshError):
+        rx.RXMeshStatic(np.array([[0, 1, 1]], dtype=np.uint32), device=False)  # degenerate face
+    with pytest.raises(rx.RXMeshError):
+        rx.RXMeshStatic(np.array([[0, 1, 3]], dtype=np.uint32), device=False)  # isolated vertex id 2
+    m = rx.RXMeshStatic(np.array([[0, 1, 2]], dtype=np.uint32), device=False)
+    with pytest.raises(rx.RXMeshError, match="DEVICE"):
+        m.add_vertex_attribute("x", np.float32, 3, rx.DEVICE)  # no silent CPU fallback
+    a = m.add_vertex_attribute("h", np.float32, 3, rx.HOST, rx.AoS)
+    b = m.add_vertex_attribute("n", np.float32, 3, rx.HOST, rx.AoS)
+    with pytest.raises(rx.RXMeshError, match="no CPU fallback"):
+        m.vertex_normals(a, b)
+
+
+def test_host_attribute_roundtrip_all_layouts():
+    V, F = make_mesh("sphere3")
+    m = rx.RXMeshStatic(F, device=False, patch_size=128)
+    for layout in (rx.AoS, rx.AoSoA, rx.SoA):
+        a = rx.Attribute(m, 0, np.float32, 3, rx.HOST, layout)
+        a.from_global(V)
+        assert np.array_equal(a.to_global(), V)
+        # Attribute::operator()(handle, attr) addressing
+        h = a.host_array()
+        g2s, sb, ep = m.global_to_slot(0), m.slot_base(0), m.elem_patch(0)
+        for g in (0, 17, 385):
+            p = int(ep[g])
+            lid = int(g2s[g] - sb[p])
+            assert [h[a.index(p, lid, k)] for k in range(3)] == V[g].tolist()

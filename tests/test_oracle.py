@@ -1,0 +1,112 @@
+"""The oracle against the reference's golden vectors / known answers (CPU only)."""
+import json
+import os
+
+import numpy as np
+
+from conftest import GOLDEN, load_golden
+from oracle import oracle as O
+
+KNOWN = json.load(open(os.path.join(GOLDEN, "known_answers.json")))
+
+
+def test_normals_bit_exact_vs_reference_loop():
+    # vn_ref was produced by the reference's own vertex_normal_ref.h compiled unmodified
+    # (oracle/_ref, tests/golden/make_golden.py)
+    for name in ("sphere3", "dragon", "bunnyhead", "torus"):
+        g = load_golden(name)
+        n = O.vertex_normals(g["F"], g["V"], np.float32)
+        assert np.array_equal(n.view(np.uint32), g["vn_ref"].view(np.uint32)), name
+
+
+def test_normals_survey_checksums():
+    g = load_golden("dragon")
+    n = O.vertex_normals(g["F"], g["V"], np.float32)
+    assert abs(n.sum(dtype=np.float64) - KNOWN["dragon_sum"]) < 2e-3
+    assert abs(np.abs(n).sum(dtype=np.float64) - KNOWN["dragon_abs_sum"]) < 2e-2
+    assert np.allclose(n[0], KNOWN["dragon_n0"], rtol=0, atol=1e-6)
+    assert np.allclose(n[-1], KNOWN["dragon_nlast"], rtol=0, atol=1e-6)
+    g = load_golden("sphere3")
+    n = O.vertex_normals(g["F"], g["V"], np.float32)
+    assert abs(np.abs(n).sum(dtype=np.float64) - KNOWN["sphere3_abs_sum"]) < 1e-3
+    assert np.allclose(n[0], KNOWN["sphere3_n0"], rtol=0, atol=1e-6)
+    assert np.allclose(n[-1], KNOWN["sphere3_nlast"], rtol=0, atol=1e-6)
+    assert list(g["V"].shape[:1]) + list(g["F"].shape[:1]) == KNOWN["sphere3_VF"]
+
+
+def test_normals_f32_close_to_f64():
+    g = load_golden("dragon")
+    a = O.vertex_normals(g["F"], g["V"], np.float32).astype(np.float64)
+    b = O.vertex_normals(g["F"], g["V"], np.float64)
+    rel = np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)
+    assert rel.max() < 1e-5
+
+
+def test_cube_counts_and_euler():
+    g = load_golden("cube")
+    T = O.Topology(g["F"])
+    assert dict(V=T.nv, E=T.ne, F=T.nf) == KNOWN["cube_counts"]
+    for name in ("sphere3", "dragon", "torus"):
+        T = O.Topology(load_golden(name)["F"])
+        chi = T.nv - T.ne + T.nf
+        assert chi == {"sphere3": 2, "dragon": 0, "torus": 0}[name]  # the decimated dragon has genus 1
+        assert T.stats()["is_closed"] and T.stats()["is_edge_manifold"]
+
+
+def test_bunnyhead_boundary():
+    T = O.Topology(load_golden("bunnyhead")["F"])
+    n, flags = T.boundary_vertices()
+    assert n == KNOWN["bunnyhead_boundary_vertices"] == int(flags.sum())
+    assert not T.stats()["is_closed"]
+
+
+def test_edge_numbering_first_seen():
+    # rxmesh.cpp:589-611: ids in order of first appearance, (max, min) key
+    fv = np.array([[0, 1, 2], [2, 1, 3]], dtype=np.uint32)
+    T = O.Topology(fv)
+    assert T.ev.tolist() == [[1, 0], [2, 1], [2, 0], [3, 1], [3, 2]]
+    assert T.fe.tolist() == [[0, 1, 2], [1, 3, 4]]
+
+
+def test_queries_are_mutually_consistent():
+    g = load_golden("sphere3")
+    T = O.Topology(g["F"])
+    vv, ve, vf = T.query("VV"), T.query("VE"), T.query("VF")
+    ev, ef, fv, fe, ff = T.query("EV"), T.query("EF"), T.query("FV"), T.query("FE"), T.query("FF")
+    assert vv[1].shape[0] == ve[1].shape[0] == 2 * T.ne
+    assert vf[1].shape[0] == ef[1].shape[0] == fv[1].shape[0] == fe[1].shape[0] == 3 * T.nf
+    assert ff[1].shape[0] == 3 * T.nf  # closed manifold: 3 neighbours per face
+    # v in VV[u] <=> u in VV[v]
+    s = O.csr_to_sets(vv)
+    for u in range(0, T.nv, 17):
+        for v in s[u]:
+            assert u in s[v]
+    # every VE edge has the vertex as an endpoint
+    se = O.csr_to_sets(ve)
+    for v in range(0, T.nv, 13):
+        for e in se[v]:
+            assert v in T.ev[e]
+
+
+def test_laplacian_f32_vs_f64():
+    g = load_golden("sphere3")
+    T = O.Topology(g["F"])
+    vv = T.query("VV")
+    a = O.laplacian_step(vv, g["V"], 0.01, np.float32)
+    b = O.laplacian_step(vv, g["V"].astype(np.float64), 0.01, np.float64)
+    assert np.abs(a - b).max() < 1e-6
+    # a Jacobi step contracts a closed convex shape towards its centroid
+    assert np.linalg.norm(a, axis=1).mean() < np.linalg.norm(g["V"], axis=1).mean()
+
+
+def test_bilateral_denoises_noisy_sphere():
+    from rxmesh_b200 import meshio
+    V, F = meshio.icosphere(8)
+    rng = np.random.RandomState(0)
+    noisy = (V * (1 + 0.01 * rng.randn(V.shape[0], 1))).astype(np.float32)
+    T = O.Topology(F)
+    out, worst = O.bilateral_step(T.query("VV"), F, noisy)
+    assert worst <= 80
+    # the filter shrinks a convex shape slightly (all neighbours lie below the tangent plane) but
+    # must reduce the roughness: spread of the radius
+    assert np.linalg.norm(out, axis=1).std() < 0.75 * np.linalg.norm(noisy, axis=1).std()
