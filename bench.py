@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's headline workload on B200.
+
+Workload (BASELINE.json configs[3]): a 100 M-face procedurally generated
+grid (create_plane semantics, nx = ny = 7072, height field) on 1 GPU.  One "step" = one pass of the
+hot path over the mesh: VV query (consume), VF query (consume), vertex normals -- three of our
+sm_100a kernels.  `value` = faces/s through the whole pass (F / step time); the per-kernel rates
+(VV / VF neighbour entries/s, vertex-normal faces/s) and their HBM-roofline fractions are in
+`kernels`; `roofline` describes the dominant (longest) kernel.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--faces F]
+
+N > 1 (launched with torch.distributed.run): weak scaling, every rank owns a mesh of `--faces`
+faces (see DESIGN.md "Multi-GPU").
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ALG_BYTES_PER_FACE = {"VV": 16.0, "VF": 18.0, "VN": 24.0}  # SURVEY.md 8(d), BASELINE.md 2
+TILE = 16  # 16 x 16 quads = 512 owned faces per patch (the reference's default patch_size)
+
+
+def grid_side(faces):
+    return int(round(math.sqrt(faces / 2.0))) + 1
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t_begin=None, t_end=None):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = self.lines
+        if t_begin is not None:
+            win = [r for r in rows if t_begin - 0.02 <= r[0] <= t_end + 0.12]
+            if not win and rows:  # region shorter than the sampling period: nearest sample
+                win = [min(rows, key=lambda r: abs(r[0] - 0.5 * (t_begin + t_end)))]
+            rows = win
+        for _, ln in rows:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_sample_mesh(faces):
+    from rxmesh_b200 import meshio
+    n = grid_side(faces)
+    V, F = meshio.grid(n, n)
+    return V, F, n
+
+
+def cpu_pass_seconds(V, F, T, vv, vf, repeats):
+    """One CPU pass = VV consume + VF consume over cached CSR adjacency (oracle port) + the
+    reference's own serial vertex-normal loop (oracle/_ref when present, else the oracle port)."""
+    from oracle import oracle as O
+    rng = np.random.RandomState(1)
+    fvals = rng.rand(T.nv).astype(np.float32)
+    ffvals = rng.rand(T.nf).astype(np.float32)
+    have_ref = O.ref_lib() is not None
+    t_c = time.perf_counter()
+    for _ in range(repeats):
+        O.consume_sum(vv, fvals)
+        O.consume_sum(vf, ffvals)
+    t_c = (time.perf_counter() - t_c) / repeats
+    if have_ref:
+        _, t_n = O.ref_vertex_normals(F, V, repeats=repeats)
+    else:
+        t_n = time.perf_counter()
+        for _ in range(repeats):
+            O.vertex_normals(F, V, np.float32)
+        t_n = (time.perf_counter() - t_n) / repeats
+    return t_c + t_n, t_n, have_ref
+
+
+def cpu_baseline(sample_faces, repeats):
+    from oracle import oracle as O
+    V, F, n = cpu_sample_mesh(sample_faces)
+    T = O.Topology(F)
+    vv, vf = T.query("VV"), T.query("VF")
+    t, t_n, have_ref = cpu_pass_seconds(V, F, T, vv, vf, repeats)
+    return {
+        "value": F.shape[0] / t, "unit": "faces/s", "cores": 1,
+        "kind": "port",
+        "sample": ("%d x %d grid (%d faces) of the same generator, %d passes; VV+VF consume over cached CSR "
+                   "adjacency = oracle port; vertex-normal leg = %s, 1 thread as the reference runs it "
+                   "(%.3g faces/s for that leg alone)") %
+                  (n, n, F.shape[0], repeats,
+                   "the reference's own vertex_normal_ref.h compiled unmodified (oracle/_ref)" if have_ref
+                   else "oracle port of vertex_normal_ref.h", F.shape[0] / t_n),
+    }, (V, F, T, vv, vf)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from oracle import oracle as O  # noqa: F401
+    sample = min(args.faces, args.cpu_sample_faces)
+    V, F, n = cpu_sample_mesh(sample)
+    T = O.Topology(F)
+    vv, vf = T.query("VV"), T.query("VF")
+    for _ in range(args.warmup):
+        cpu_pass_seconds(V, F, T, vv, vf, 1)
+    dt = 0.0
+    for _ in range(args.steps):  # timed: the passes only (vector<vector<>> conversion is setup, as in the app)
+        t, _, have_ref = cpu_pass_seconds(V, F, T, vv, vf, 1)
+        dt += t
+    dt /= args.steps
+    val = F.shape[0] / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "faces/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(config_dict(args, grid_side(args.faces), 2 * (grid_side(args.faces) - 1) ** 2, None),
+                       sample="%d x %d grid, %d faces per step" % (n, n, F.shape[0])),
+        "cpu_baseline": {"value": val, "unit": "faces/s", "cores": 1, "kind": "port",
+                         "sample": ("each step = one pass over a %d x %d grid (%d faces), a bounded sample of the "
+                                    "workload; vertex-normal leg = %s; VV/VF consume legs = oracle port over cached "
+                                    "CSR (the reference has no CPU query engine)") %
+                                   (n, n, F.shape[0], "oracle/_ref (reference's vertex_normal_ref.h, unmodified)"
+                                    if have_ref else "oracle port")},
+        "e2e": {"value": val, "unit": "faces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+METRIC = "faces/s through one VV-query + VF-query + vertex-normal pass (100M-face grid); per-kernel entries/s, faces/s and HBM fraction in `kernels`"
+
+
+def config_dict(args, n, faces, mesh):
+    c = {"workload": "VV + VF query (consume) + vertex normals on a %d x %d procedurally generated grid "
+                     "(create_plane semantics + height field), %d faces per GPU" % (n, n, faces),
+         "faces_per_gpu": int(faces), "patch_size": 2 * TILE * TILE, "patcher": "analytic %dx%d-quad tiles" % (TILE, TILE),
+         "l2": "inputs larger than L2 (topology + attributes stream > 2 GB per step; no explicit flush)",
+         "parallelism": "patches sharded per GPU" if args.gpus > 1 else "1 GPU"}
+    if mesh is not None:
+        c.update(patches=mesh.get_num_patches(), ribbon_overhead=round(mesh.ribbon_overhead(), 4),
+                 topo_bytes_per_face=round(mesh.topo_bytes() / faces, 2))
+    return c
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+
+    import rxmesh_b200 as rx
+    from rxmesh_b200 import meshio
+
+    torch.cuda.set_device(local_rank)
+    rx.rx_init(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = grid_side(args.faces)
+    ncores = os.cpu_count() or 8
+    t0 = time.perf_counter()
+    V, F = meshio.grid(n, n)
+    fp = meshio.grid_face_tiles(n, n, TILE)
+    mesh = rx.RXMeshStatic(F, face_patch=fp, patch_size=2 * TILE * TILE, num_threads=max(1, ncores // world))
+    t_build = time.perf_counter() - t0
+    nF, nV = mesh.get_num_faces(), mesh.get_num_vertices()
+    del fp
+
+    stream = torch.cuda.current_stream()
+    x = rx.Attribute(mesh, 0, np.float32, 3, rx.DEVICE, rx.AoS)
+    nrm = rx.Attribute(mesh, 0, np.float32, 3, rx.DEVICE, rx.AoS)
+    sv_in = rx.Attribute(mesh, 0, np.float32, 1, rx.DEVICE, rx.AoS)
+    sv_out = rx.Attribute(mesh, 0, np.float32, 1, rx.DEVICE, rx.AoS)
+    sf_in = rx.Attribute(mesh, 2, np.float32, 1, rx.DEVICE, rx.AoS)
+    rng = np.random.RandomState(1 + rank)
+    h_x = torch.from_numpy(V).pin_memory()
+    h_sv = torch.from_numpy(rng.rand(nV).astype(np.float32)).pin_memory()
+    h_sf = torch.from_numpy(rng.rand(nF).astype(np.float32)).pin_memory()
+    x.from_global(h_x.numpy(), stream)
+    sv_in.from_global(h_sv.numpy(), stream)
+    sf_in.from_global(h_sf.numpy(), stream)
+    torch.cuda.synchronize()
+
+    def step(evs=None):
+        if evs:
+            evs[0].record(stream)
+        mesh.query_consume(rx.Op.VV, sv_in, sv_out, stream)
+        if evs:
+            evs[1].record(stream)
+        mesh.query_consume(rx.Op.VF, sf_in, sv_out, stream)
+        if evs:
+            evs[2].record(stream)
+        mesh.vertex_normals(x, nrm, False, stream)
+        if evs:
+            evs[3].record(stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_w = time.perf_counter()
+    n_warm = 0
+    while n_warm < args.warmup or time.perf_counter() - t_w < 0.6:  # >= W steps and long enough for the
+        step()                                                      # clocks to settle / sampler to start
+        n_warm += 1
+        if n_warm % 16 == 0:
+            torch.cuda.synchronize()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    barrier()
+    l0 = rx.launch_count()
+    t_begin = time.perf_counter()
+    for k in range(args.steps):
+        step(evs[k])
+    barrier()
+    t_end = time.perf_counter()
+    t_wall = t_end - t_begin
+    launches = rx.launch_count() - l0
+    clocks = sampler.stop(t_begin, t_end)
+    total_ms = evs[0][0].elapsed_time(evs[-1][3])
+    k_ms = [sum(e[i].elapsed_time(e[i + 1]) for e in evs) / args.steps for i in range(3)]
+
+    # ---- end to end through the C ABI with pinned HOST buffers (H2D + kernel + D2H per call) ----
+    h_n = torch.empty((nV, 3), dtype=torch.float32).pin_memory()
+    h_o1 = torch.empty(nV, dtype=torch.float32).pin_memory()
+    h_o2 = torch.empty(nV, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        mesh.query_consume_host_ptr(rx.Op.VV, h_sv.data_ptr(), h_o1.data_ptr(), stream)
+        mesh.query_consume_host_ptr(rx.Op.VF, h_sf.data_ptr(), h_o2.data_ptr(), stream)
+        mesh.vertex_normals_host_ptr(h_x.data_ptr(), h_n.data_ptr(), stream)
+
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    te = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    te = (time.perf_counter() - te) / e2e_steps
+    h2d = 12 * nV + 4 * nV + 4 * nF
+    d2h = 12 * nV + 4 * nV + 4 * nV
+
+    # ---- max over ranks ----
+    tm = torch.tensor([total_ms, te] + k_ms, dtype=torch.float64, device="cuda")
+    if world > 1:
+        torch.distributed.all_reduce(tm, op=torch.distributed.ReduceOp.MAX)
+    total_ms, te = float(tm[0]), float(tm[1])
+    k_ms = [float(v) for v in tm[2:5]]
+    if rank != 0:
+        return
+    ms_step = total_ms / args.steps
+    peak, peak_src = peaks()
+    kern = {}
+    for name, ms, unit, units in (("VV", k_ms[0], "neighbour entries/s", 2.0 * mesh.get_num_edges()),
+                                  ("VF", k_ms[1], "neighbour entries/s", 3.0 * nF),
+                                  ("VN", k_ms[2], "faces/s", float(nF))):
+        gbs = ALG_BYTES_PER_FACE[name] * nF / (ms * 1e-3) / 1e9
+        kern[name] = {"ms": ms, "rate": units / (ms * 1e-3) * world, "unit": unit,
+                      "alg_bytes": ALG_BYTES_PER_FACE[name] * nF, "achieved_gbs": gbs, "hbm_frac": gbs / peak}
+    dom = max(kern, key=lambda k: kern[k]["ms"])
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(dom)
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": nF * world / (ms_step * 1e-3), "unit": "faces/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "warmup_steps_run": n_warm, "ms_per_step": ms_step,
+        "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, n, nF, mesh),
+        "kernels": kern,
+        "roofline": {"bound": "hbm", "kernel": {"VV": "k_query_consume<VV>", "VF": "k_query_consume<VF>",
+                                                "VN": "k_vertex_normals"}[dom],
+                     "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                     "frac": kern[dom]["hbm_frac"], "traffic": traffic, "peak_source": peak_src,
+                     "alg_bytes_per_launch": kern[dom]["alg_bytes"]},
+        "e2e": {"value": nF * world / te, "unit": "faces/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": te * 1e3,
+                "api": "rxm_query_consume_host(VV), rxm_query_consume_host(VF), rxm_vertex_normals_host (pinned host buffers)"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "wall_ms_per_step": t_wall / args.steps * 1e3, "build_seconds": t_build,
+    }
+    if world == 1 and not args.no_cpu:
+        cb, _ = cpu_baseline(min(args.faces, args.cpu_sample_faces), 3)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--faces", type=int, default=100_000_000)
+    ap.add_argument("--cpu-sample-faces", type=int, default=4_000_000)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -150,6 +150,8 @@ int rxm_boundary_vertices(rxm_mesh* m, rxm_attr* flag, void* stream);
  * arrays in GLOBAL vertex order, [V][3] fp32. */
 int rxm_vertex_normals_host(rxm_mesh* m, const float* coords, float* normals, void* stream);
 int rxm_laplacian_smooth_host(rxm_mesh* m, const float* coords, float* out, double lr, uint32_t iters, void* stream);
+/* in: [num output-type elements] fp32, out: [num source-type elements] fp32, global order */
+int rxm_query_consume_host(rxm_mesh* m, int op, const float* in, float* out, void* stream);
 
 /* kernels launched by this library so far (bench.py "gpu_launches") */
 uint64_t rxm_launch_count(void);

@@ -61,6 +61,7 @@ SYMBOLS = {
     "rxm_vertex_normals_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rxm_laplacian_smooth_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                             C.c_uint32, C.c_void_p]),
+    "rxm_query_consume_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rxm_launch_count": (C.c_uint64, []),
 }
 

@@ -45,6 +45,7 @@ struct rxm_mesh
     void*     d_stage       = nullptr;
     size_t    d_stage_bytes = 0;
     rxm_attr* scratch[4]    = {nullptr, nullptr, nullptr, nullptr};
+    rxm_attr* scratch1[6]   = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 struct rxm_attr
@@ -156,6 +157,11 @@ void rxm_mesh_destroy(rxm_mesh* m)
 {
     if (!m) return;
     for (auto*& s : m->scratch)
+        if (s) {
+            rxm_attr_destroy(s);
+            s = nullptr;
+        }
+    for (auto*& s : m->scratch1)
         if (s) {
             rxm_attr_destroy(s);
             s = nullptr;
@@ -657,6 +663,21 @@ int rxm_laplacian_smooth_host(rxm_mesh* m, const float* coords, float* out, doub
     if ((rc = rxm_attr_upload_global(x, coords, stream))) return rc;
     if ((rc = rxm_laplacian_smooth(m, x, y, lr, iters, stream))) return rc;
     return rxm_attr_download_global(y, out, stream);
+}
+
+int rxm_query_consume_host(rxm_mesh* m, int op, const float* in, float* out, void* stream)
+{
+    int rc = check_dev(m, "rxm_query_consume_host");
+    if (rc) return rc;
+    if (!in || !out || op_src(op) < 0) return fail(RXM_ERR_INVALID, "rxm_query_consume_host: bad argument");
+    // cached 1 x fp32 attributes per element type: [0..2] inputs, [3..5] outputs
+    rxm_attr*& a = m->scratch1[op_dst(op)];
+    rxm_attr*& b = m->scratch1[3 + op_src(op)];
+    if (!a && (rc = rxm_attr_create(m, op_dst(op), 4, 1, RXM_DEVICE, RXM_AOS, &a))) return rc;
+    if (!b && (rc = rxm_attr_create(m, op_src(op), 4, 1, RXM_DEVICE, RXM_AOS, &b))) return rc;
+    if ((rc = rxm_attr_upload_global(a, in, stream))) return rc;
+    if ((rc = rxm_query_consume(m, op, a, b, stream))) return rc;
+    return rxm_attr_download_global(b, out, stream);
 }
 
 uint64_t rxm_launch_count(void)

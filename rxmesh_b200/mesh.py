@@ -380,6 +380,24 @@ class RXMeshStatic:
                                               _stream_ptr(stream)))
         return out
 
+    def query_consume_host(self, op, values, out=None, stream=None):
+        op = Op(op)
+        v = np.ascontiguousarray(values, dtype=np.float32).reshape(-1)
+        if out is None:
+            out = np.empty(self._num(_SRC[op]), dtype=np.float32)
+        check(lib().rxm_query_consume_host(self._h, int(op), v.ctypes.data_as(C.c_void_p),
+                                           out.ctypes.data_as(C.c_void_p), _stream_ptr(stream)))
+        return out
+
+    # raw-pointer variants (pinned torch tensors in bench.py): no numpy conversion
+    def vertex_normals_host_ptr(self, in_ptr, out_ptr, stream=None):
+        check(lib().rxm_vertex_normals_host(self._h, C.c_void_p(in_ptr), C.c_void_p(out_ptr),
+                                            _stream_ptr(stream)))
+
+    def query_consume_host_ptr(self, op, in_ptr, out_ptr, stream=None):
+        check(lib().rxm_query_consume_host(self._h, int(op), C.c_void_p(in_ptr), C.c_void_p(out_ptr),
+                                           _stream_ptr(stream)))
+
     # ---- helper used by the tests: run a query and return per-source global neighbour lists ----
     def query_global(self, op, width=None, stream=None):
         op = Op(op)
