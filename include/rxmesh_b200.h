@@ -67,7 +67,7 @@ enum {
     RXM_INFO_MAX_VERTICES_PER_PATCH = 10, RXM_INFO_MAX_EDGES_PER_PATCH = 11, RXM_INFO_MAX_FACES_PER_PATCH = 12,
     RXM_INFO_NUM_SLOTS_V = 13, RXM_INFO_NUM_SLOTS_E = 14, RXM_INFO_NUM_SLOTS_F = 15,
     RXM_INFO_TOPO_BYTES = 16, RXM_INFO_TOTAL_LOCAL_V = 17, RXM_INFO_TOTAL_LOCAL_E = 18,
-    RXM_INFO_TOTAL_LOCAL_F = 19, RXM_INFO_MAX_STASH = 20, RXM_INFO_ON_DEVICE = 21
+    RXM_INFO_TOTAL_LOCAL_F = 19, RXM_INFO_MAX_STASH = 20, RXM_INFO_ON_DEVICE = 21, RXM_INFO_PACKED = 22
 };
 uint64_t rxm_mesh_info(const rxm_mesh* m, int what);
 double   rxm_mesh_build_seconds(const rxm_mesh* m, int patcher_only);
@@ -80,9 +80,15 @@ typedef struct {
     uint32_t        n_owned[3];
     uint32_t        slot_base[3];
     uint32_t        lin_base[3];
+    /* packed != 0: entries are rank-annotated (rxmesh_b200/csrc/patch_layout.h): EV/FV entry = id | rank << 11,
+     * FE entry = dir | edge << 1 | rank << 12; otherwise plain 16-bit ids */
+    uint32_t        packed;
     const uint16_t* ev;          /* 2*n[E]: local (larger-id vertex, smaller-id vertex) */
     const uint16_t* fe;          /* 3*n[F]: (local edge << 1) | dir */
     const uint16_t* fv;          /* 3*n[F] */
+    const uint16_t* voff_e;      /* n[V]+1: start of every local vertex's edge list (VE / VV) */
+    const uint16_t* voff_f;      /* n[V]+1: start of every local vertex's face list (VF) */
+    const uint16_t* eoff_f;      /* n[E]+1: start of every local edge's face list (EF) */
     const uint32_t* owner[3];    /* n[t]-n_owned[t]: (stash slot << 16) | local id in owner */
     const uint32_t* stash;       /* 4*n_stash u32: patch, slot base V, E, F */
     uint32_t        n_stash;

@@ -503,11 +503,18 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
             M.total_local[t] += D.n[t];
         }
         D.n_stash    = (uint16_t)tmp[p].stash.size();
+        D.flags      = 0;
         M.max_stash  = std::max<uint32_t>(M.max_stash, D.n_stash);
         D.topo_off   = topo_total;
         D.topo_bytes = D.off_stash() + D.stash_bytes();
         topo_total += D.topo_bytes;
     }
+    M.packed = !opt.force_wide && M.max_valence < PK_MAX_VRANK && M.max_edge_incident_faces <= PK_MAX_ERANK &&
+               M.max_per_patch[0] <= PK_MAX_ELEMS && M.max_per_patch[1] <= PK_MAX_ELEMS &&
+               M.max_per_patch[2] <= PK_MAX_ELEMS;
+    if (M.packed)
+        for (uint32_t p = 0; p < P; ++p)
+            M.desc[p].flags |= FLAG_PACKED;
     for (int t = 0; t < 3; ++t) {
         M.num_slots[t] = M.slot_base[t][P];
         if (M.lin_base[t][P] != M.num_elems[t]) return "build_mesh: internal error, ownership does not partition the mesh";
@@ -558,6 +565,31 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
                 lfe[3 * f + j]     = (uint16_t)((le << 1) | dir);
                 lfv[3 * f + j]     = lev[2 * le + dir];  // == local id of v0
             }
+        }
+        // list offsets (always) and ranks (packed format only): rank = position of the
+        // incidence inside its column's list, rows visited in ascending local id
+        {
+            uint16_t* voe = reinterpret_cast<uint16_t*>(B + D.off_voff_e());
+            uint16_t* vof = reinterpret_cast<uint16_t*>(B + D.off_voff_f());
+            uint16_t* eof = reinterpret_cast<uint16_t*>(B + D.off_eoff_f());
+            const uint32_t nvp = D.n[ELEM_V], nep = D.n[ELEM_E], nfp = D.n[ELEM_F];
+            auto annotate = [&](uint16_t* conn, uint32_t nnz, uint16_t* off, uint32_t ncols, uint32_t id_shift,
+                                uint32_t rank_shift) {
+                std::vector<uint16_t> cnt(ncols + 1, 0);
+                for (uint32_t i = 0; i < nnz; ++i) {
+                    const uint32_t c = (uint32_t)conn[i] >> id_shift;
+                    const uint32_t r = cnt[c]++;
+                    if (M.packed) conn[i] = (uint16_t)(conn[i] | (r << rank_shift));
+                }
+                uint32_t run = 0;
+                for (uint32_t c = 0; c <= ncols; ++c) {
+                    off[c] = (uint16_t)run;
+                    run += c < ncols ? cnt[c] : 0;
+                }
+            };
+            annotate(lev, 2 * nep, voe, nvp, 0, PK_ID_BITS);
+            annotate(lfv, 3 * nfp, vof, nvp, 0, PK_ID_BITS);
+            annotate(lfe, 3 * nfp, eof, nep, 1, PK_ID_BITS + 1);
         }
         for (int t = 0; t < 3; ++t) {
             uint32_t* own = reinterpret_cast<uint32_t*>(B + D.off_own(t));

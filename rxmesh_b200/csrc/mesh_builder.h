@@ -32,6 +32,7 @@ struct HostMesh
     uint32_t max_stash              = 0;
     uint32_t num_slots[3]           = {0, 0, 0};
     uint64_t total_local[3]         = {0, 0, 0};  // sum over patches of n[t] (ribbon stats)
+    bool     packed                 = false;  // rank-annotated patch format (patch_layout.h)
     double   build_seconds          = 0;
     double   patcher_seconds        = 0;
 
@@ -60,6 +61,7 @@ struct BuildOptions
     bool     keep_ltog    = true;  // false: drop ltog after the build (large meshes)
     bool     verbose      = false;
     uint32_t lloyd_iters  = 8;
+    bool     force_wide   = false;  // never use the packed format (tests of the atomic path)
 };
 
 // Global edge numbering identical to the reference (first appearance while

@@ -14,6 +14,20 @@
 //    not-owned -> owner tables and the neighbour-patch stash.  Every section
 //    starts on a 16-byte boundary and is padded to a multiple of 16 bytes so a
 //    single cp.async.bulk moves it into shared memory;
+//  * RANK-ANNOTATED INCIDENCE (the "packed" format, used whenever every patch has
+//    <= 2048 elements per type, vertex valence < 32 and <= 16 faces per edge):
+//    the spare high bits of every 16-bit EV / FV / FE entry carry the RANK of
+//    that incidence inside the transposed list it belongs to (the k-th edge of
+//    its vertex, the k-th face of its vertex, the k-th face of its edge), and
+//    three small u16 offset arrays (VE/VV, VF, EF list starts) follow FV.  One
+//    array therefore answers a query in both directions: mask the rank bits to
+//    read EV/FV/FE, or scatter row ids to offset[col] + rank to obtain
+//    VE/VV/VF/EF in shared memory with no atomics, no scan and a deterministic
+//    (ascending row id) neighbour order -- the reference builds the transpose
+//    with two passes of CAS-emulated 16-bit shared atomics in racy order
+//    (kernels/rxmesh_queries.cuh:16-107), the same way the reference already
+//    hides the edge direction in bit 0 of FE (rxmesh.cpp:941-983).  Meshes that
+//    exceed the limits use the "wide" format (plain ids) and the atomic path;
 //  * local ids are owned-first, each half sorted by global id (the reference's
 //    numbering, rxmesh.cpp:845-869), so the owned / active bitmasks of the
 //    reference collapse to a prefix [0, n_owned) and the not-owned -> owner
@@ -62,6 +76,14 @@ enum : int
 };
 
 constexpr uint32_t INVALID32_ = 0xFFFFFFFFu;
+
+// packed (rank-annotated) entry formats
+constexpr uint32_t PK_ID_BITS   = 11;      // local id bits of EV / FV entries and of the edge id in FE
+constexpr uint32_t PK_ID_MASK   = 0x7FFu;
+constexpr uint32_t PK_MAX_ELEMS = 2048;    // per element type and patch
+constexpr uint32_t PK_MAX_VRANK = 32;      // ranks of vertex lists: 5 bits (entry >> 11)
+constexpr uint32_t PK_MAX_ERANK = 16;      // ranks of edge lists: 4 bits (FE entry >> 12)
+constexpr uint16_t FLAG_PACKED  = 1;
 constexpr uint64_t INVALID64_ = 0xFFFFFFFFFFFFFFFFull;
 
 RXM_HD uint32_t round_up(uint32_t x, uint32_t m)
@@ -92,7 +114,7 @@ struct alignas(16) PatchDesc
     uint32_t slot_base[3];  // attribute slot base for V, E, F (multiple of 4)
     uint32_t lin_base[3];   // gap-free linear-id prefix (reference Context::linear_id, context.h:275-290)
     uint16_t n_stash;       // neighbour patches referenced by the owner tables
-    uint16_t pad0;
+    uint16_t flags;         // bit 0: packed (rank-annotated) format
     uint32_t pad1;
 
     // ---- section byte offsets inside the blob (all multiples of 16) ----
@@ -102,9 +124,15 @@ struct alignas(16) PatchDesc
     RXM_HD uint32_t off_ev() const { return 0; }
     RXM_HD uint32_t off_fe() const { return ev_bytes(); }
     RXM_HD uint32_t off_fv() const { return off_fe() + fe_bytes(); }
+    // list-offset arrays (u16, one entry per local column + 1): VE/VV, VF, EF
+    RXM_HD uint32_t voff_bytes() const { return round_up(2u * (n[ELEM_V] + 1u), 16); }
+    RXM_HD uint32_t eoff_bytes() const { return round_up(2u * (n[ELEM_E] + 1u), 16); }
+    RXM_HD uint32_t off_voff_e() const { return off_fv() + fe_bytes(); }
+    RXM_HD uint32_t off_voff_f() const { return off_voff_e() + voff_bytes(); }
+    RXM_HD uint32_t off_eoff_f() const { return off_voff_f() + voff_bytes(); }
     RXM_HD uint32_t off_own(uint32_t t) const
     {
-        uint32_t o = off_fv() + fe_bytes();
+        uint32_t o = off_eoff_f() + eoff_bytes();
         for (uint32_t i = 0; i < t; ++i)
             o += own_bytes(i);
         return o;
@@ -124,6 +152,7 @@ struct MeshView
     uint32_t         num_slots[3];  // attribute slots per element type (sum of slot caps)
     uint32_t         num_elems[3];  // #V, #E, #F of the (local shard of the) mesh
     const uint32_t*  patch_slot_base[3];  // [num_patches+1] per type: slot base of every patch
+    uint32_t         packed;              // 1: every patch uses the rank-annotated format
 };
 
 // Attribute layouts: numeric values of the reference's layoutT (types.h:84-90).

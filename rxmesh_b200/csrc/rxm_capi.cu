@@ -105,6 +105,7 @@ int rxm_mesh_create(const uint32_t* fv, uint32_t num_faces, const uint32_t* face
     opt.patch_size  = patch_size ? patch_size : 512;
     opt.num_threads = num_threads;
     opt.verbose     = getenv("RXM_VERBOSE") != nullptr;
+    opt.force_wide  = getenv("RXM_FORCE_WIDE") != nullptr;  // tests: exercise the atomic (wide-format) kernels
     std::string e;
     try {
         e = build_mesh(fv, num_faces, face_patch, opt, m->h);
@@ -144,6 +145,7 @@ int rxm_mesh_to_device(rxm_mesh* m)
     m->view.desc        = m->d_desc;
     m->view.topo        = m->d_topo;
     m->view.num_patches = h.num_patches;
+    m->view.packed      = h.packed ? 1u : 0u;
     for (int t = 0; t < 3; ++t) {
         m->view.num_slots[t]       = h.num_slots[t];
         m->view.num_elems[t]       = h.num_elems[t];
@@ -205,6 +207,7 @@ uint64_t rxm_mesh_info(const rxm_mesh* m, int what)
         case RXM_INFO_TOTAL_LOCAL_F: return h.total_local[ELEM_F];
         case RXM_INFO_MAX_STASH: return h.max_stash;
         case RXM_INFO_ON_DEVICE: return m->on_device;
+        case RXM_INFO_PACKED: return h.packed;
         default: return 0;
     }
 }
@@ -231,6 +234,10 @@ int rxm_mesh_patch(const rxm_mesh* m, uint32_t p, rxm_patch_view* o)
     o->ev      = reinterpret_cast<const uint16_t*>(B + D.off_ev());
     o->fe      = reinterpret_cast<const uint16_t*>(B + D.off_fe());
     o->fv      = reinterpret_cast<const uint16_t*>(B + D.off_fv());
+    o->voff_e  = reinterpret_cast<const uint16_t*>(B + D.off_voff_e());
+    o->voff_f  = reinterpret_cast<const uint16_t*>(B + D.off_voff_f());
+    o->eoff_f  = reinterpret_cast<const uint16_t*>(B + D.off_eoff_f());
+    o->packed  = (D.flags & FLAG_PACKED) ? 1u : 0u;
     o->stash   = reinterpret_cast<const uint32_t*>(B + D.off_stash());
     o->n_stash = D.n_stash;
     return RXM_OK;

@@ -11,7 +11,9 @@
 //
 // One thread block per patch; every patch section and the patch's owned attribute
 // slice arrive by TMA bulk copies under one mbarrier phase.
+#include <algorithm>
 #include <cstdio>
+#include <cstring>
 
 #include "rxm_kernels.h"
 #include "rxm_query.cuh"
@@ -45,13 +47,13 @@ __device__ __forceinline__ PatchDesc load_desc(const PatchDesc* g)
 // --------------------------------------------------------------------------
 // query -> store handles
 // --------------------------------------------------------------------------
-template <int OP, int KMAX>
+template <int OP, int KMAX, bool PACKED>
 __global__ void __launch_bounds__(BT) k_query_store(MeshView mv, AttrView<uint64_t> in, AttrView<uint64_t> out)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t                      bar;
     __shared__ uint32_t                      warp_tmp[36];
-    using Q = PatchQuery<OP, BT, KMAX>;
+    using Q = PatchQuery<OP, BT, KMAX, PACKED>;
     const uint32_t  p    = blockIdx.x;
     const PatchDesc d    = load_desc(mv.desc + p);
     const uint8_t*  blob = mv.topo + d.topo_off;
@@ -81,13 +83,13 @@ __global__ void __launch_bounds__(BT) k_query_store(MeshView mv, AttrView<uint64
 // --------------------------------------------------------------------------
 // query -> consume (gather one fp32 per neighbour, write one fp32 per source)
 // --------------------------------------------------------------------------
-template <int OP, int KMAX>
+template <int OP, int KMAX, bool PACKED>
 __global__ void __launch_bounds__(BT) k_query_consume(MeshView mv, const float* __restrict__ in, float* __restrict__ out)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t                      bar;
     __shared__ uint32_t                      warp_tmp[36];
-    using Q = PatchQuery<OP, BT, KMAX>;
+    using Q = PatchQuery<OP, BT, KMAX, PACKED>;
     constexpr uint32_t S = OpTraits<OP>::src, D = OpTraits<OP>::dst;
     const uint32_t     p    = blockIdx.x;
     const PatchDesc    d    = load_desc(mv.desc + p);
@@ -113,10 +115,10 @@ __global__ void __launch_bounds__(BT) k_query_consume(MeshView mv, const float* 
     const QueryResult r = q.compute(d, warp_tmp, false, true);  // compute() syncs before returning for CSR ops
     if (op_is_fixed<OP>()) __syncthreads();
     for (uint32_t s = threadIdx.x; s < r.n_src; s += BT) {
-        const uint32_t b = r.begin(s), n = r.size(s);
+        const uint32_t b = r.begin(s), e = r.end(s);
         float          a = 0.f;
-        for (uint32_t i = 0; i < n; ++i)
-            a += s_in[r.at(b + i)];
+        for (uint32_t i = b; i < e; ++i)
+            a += s_in[r.at(i)];
         out[d.slot_base[S] + s] = a;
     }
 }
@@ -126,6 +128,102 @@ __global__ void __launch_bounds__(BT) k_query_consume(MeshView mv, const float* 
 // --------------------------------------------------------------------------
 // UNIT = 0: Max-1999 weights (apps/VertexNormal); UNIT = 1: sum of unit face
 // normals (apps/Filtering/filtering_rxmesh_kernel.cuh:15-46).
+// ---- packed format: atomic-free, deterministic ----
+// Phase 1, one thread per patch face: face normal n and the three corner weights;
+// corner j's contribution n*w_j is STORED at position voff_f[v_j] + rank_j of a
+// per-patch contribution list (the rank bits of the FV entry say where), so no
+// two threads ever write the same address.  Phase 2, one thread per owned vertex:
+// sum its contiguous segment in ascending face order.  Result: bit-reproducible.
+template <int UNIT>
+__global__ void __launch_bounds__(BT) k_vertex_normals_pk(MeshView mv, const float* __restrict__ x,
+                                                          float* __restrict__ nrm)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint64_t                      bar;
+    const uint32_t  p    = blockIdx.x;
+    const PatchDesc d    = load_desc(mv.desc + p);
+    const uint8_t*  blob = mv.topo + d.topo_off;
+    const uint32_t  nv = d.n[ELEM_V], nov = d.n_owned[ELEM_V], nf = d.n[ELEM_F];
+    const uint32_t  cap = d.slot_cap(ELEM_V);
+    const uint32_t  loff_bytes = round_up(2u * (nov + 1), 16);
+    Smem            sm(smem_raw);
+    uint16_t*       s_fv    = sm.alloc<uint16_t>(d.fe_bytes() / 2);
+    uint16_t*       s_loff  = sm.alloc<uint16_t>(loff_bytes / 2);
+    uint32_t*       s_own   = sm.alloc<uint32_t>(d.own_bytes(ELEM_V) / 4);
+    StashEntry*     s_stash = sm.alloc<StashEntry>(d.n_stash);
+    float*          s_xp    = sm.alloc<float>(3 * cap);  // owned coordinates as they arrive (packed xyz); reused for the result
+    float4*         s_x     = sm.alloc<float4>(nv);      // all local vertices, one LDS.128 each
+    float4*         s_c     = sm.alloc<float4>(3 * nf);  // contribution lists (only owned vertices' segments are used)
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(&bar, d.fe_bytes() + loff_bytes + d.own_bytes(ELEM_V) + d.stash_bytes() + 12u * cap);
+        if (d.fe_bytes()) bulk_g2s(s_fv, blob + d.off_fv(), d.fe_bytes(), &bar);
+        bulk_g2s(s_loff, blob + d.off_voff_f(), loff_bytes, &bar);
+        if (d.own_bytes(ELEM_V)) bulk_g2s(s_own, blob + d.off_own(ELEM_V), d.own_bytes(ELEM_V), &bar);
+        if (d.stash_bytes()) bulk_g2s(s_stash, blob + d.off_stash(), d.stash_bytes(), &bar);
+        if (cap) bulk_g2s(s_xp, x + 3ull * d.slot_base[ELEM_V], 12u * cap, &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    for (uint32_t i = threadIdx.x; i < nv; i += BT) {
+        float4 q;
+        if (i < nov) {
+            q = make_float4(s_xp[3 * i], s_xp[3 * i + 1], s_xp[3 * i + 2], 0.f);
+        } else {  // ribbon vertex: gather from the owner patch's slots
+            const uint32_t o = s_own[i - nov];
+            const float*   g = x + 3ull * ((uint64_t)s_stash[o >> 16].slot_base[ELEM_V] + (o & 0xFFFFu));
+            q = make_float4(ldg_stream(g), ldg_stream(g + 1), ldg_stream(g + 2), 0.f);
+        }
+        s_x[i] = q;
+    }
+    __syncthreads();
+    for (uint32_t f = threadIdx.x; f < nf; f += BT) {
+        const uint32_t e0 = s_fv[3 * f], e1 = s_fv[3 * f + 1], e2 = s_fv[3 * f + 2];
+        const uint32_t v0 = e0 & PK_ID_MASK, v1 = e1 & PK_ID_MASK, v2 = e2 & PK_ID_MASK;
+        if (v0 >= nov && v1 >= nov && v2 >= nov) continue;  // touches no owned vertex
+        const float4 p0 = s_x[v0], p1 = s_x[v1], p2 = s_x[v2];
+        const float  ax = p1.x - p0.x, ay = p1.y - p0.y, az = p1.z - p0.z;
+        const float  bx = p2.x - p0.x, by = p2.y - p0.y, bz = p2.z - p0.z;
+        const float  nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+        float        w0, w1, w2;
+        if (UNIT) {
+            w0 = w1 = w2 = rsqrtf(nx * nx + ny * ny + nz * nz);
+        } else {
+            const float cx = p2.x - p1.x, cy = p2.y - p1.y, cz = p2.z - p1.z;
+            const float l0 = ax * ax + ay * ay + az * az;  // |v0 v1|^2
+            const float l1 = cx * cx + cy * cy + cz * cz;  // |v1 v2|^2
+            const float l2 = bx * bx + by * by + bz * bz;  // |v2 v0|^2
+            w0 = __frcp_rn(l0 + l2);
+            w1 = __frcp_rn(l1 + l0);
+            w2 = __frcp_rn(l2 + l1);
+        }
+        if (v0 < nov) s_c[s_loff[v0] + (e0 >> PK_ID_BITS)] = make_float4(nx * w0, ny * w0, nz * w0, 0.f);
+        if (v1 < nov) s_c[s_loff[v1] + (e1 >> PK_ID_BITS)] = make_float4(nx * w1, ny * w1, nz * w1, 0.f);
+        if (v2 < nov) s_c[s_loff[v2] + (e2 >> PK_ID_BITS)] = make_float4(nx * w2, ny * w2, nz * w2, 0.f);
+    }
+    __syncthreads();
+    for (uint32_t v = threadIdx.x; v < cap; v += BT) {
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        if (v < nov) {
+            const uint32_t b = s_loff[v], e = s_loff[v + 1];
+            for (uint32_t i = b; i < e; ++i) {
+                const float4 c = s_c[i];
+                sx += c.x, sy += c.y, sz += c.z;
+            }
+        }
+        s_xp[3 * v] = sx, s_xp[3 * v + 1] = sy, s_xp[3 * v + 2] = sz;
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0 && cap) {
+        bulk_s2g(nrm + 3ull * d.slot_base[ELEM_V], s_xp, 12u * cap);
+        bulk_commit();
+        bulk_wait_all_read();
+    }
+}
+
+// ---- wide format: shared-memory float atomics (order not deterministic) ----
 template <int UNIT>
 __global__ void __launch_bounds__(BT) k_vertex_normals(MeshView mv, const float* __restrict__ x, float* __restrict__ nrm)
 {
@@ -208,13 +306,13 @@ __global__ void __launch_bounds__(BT) k_vertex_normals(MeshView mv, const float*
 // --------------------------------------------------------------------------
 // Laplacian smoothing step: x_out(v) = x(v) - lr * sum_u 2 (x(v) - x(u))
 // --------------------------------------------------------------------------
-template <int KMAX>
+template <int KMAX, bool PACKED>
 __global__ void __launch_bounds__(BT) k_laplacian(MeshView mv, const float* __restrict__ x, float* __restrict__ xo, double lr)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t                      bar;
     __shared__ uint32_t                      warp_tmp[36];
-    using Q = PatchQuery<OP_VV, BT, KMAX>;
+    using Q = PatchQuery<OP_VV, BT, KMAX, PACKED>;
     const uint32_t  p    = blockIdx.x;
     const PatchDesc d    = load_desc(mv.desc + p);
     const uint8_t*  blob = mv.topo + d.topo_off;
@@ -271,13 +369,13 @@ __global__ void __launch_bounds__(BT) k_laplacian(MeshView mv, const float* __re
 // --------------------------------------------------------------------------
 // boundary vertices: an edge with one incident face marks its two vertices
 // --------------------------------------------------------------------------
-template <int KMAX>
+template <int KMAX, bool PACKED>
 __global__ void __launch_bounds__(BT) k_boundary(MeshView mv, uint32_t* __restrict__ flag)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t                      bar;
     __shared__ uint32_t                      warp_tmp[36];
-    using Q = PatchQuery<OP_EF, BT, KMAX>;
+    using Q = PatchQuery<OP_EF, BT, KMAX, PACKED>;
     const uint32_t  p    = blockIdx.x;
     const PatchDesc d    = load_desc(mv.desc + p);
     const uint8_t*  blob = mv.topo + d.topo_off;
@@ -302,10 +400,11 @@ __global__ void __launch_bounds__(BT) k_boundary(MeshView mv, uint32_t* __restri
     OwnerTable        ot;
     ot.own = s_own, ot.stash = s_stash, ot.n_owned = d.n_owned[ELEM_V], ot.patch = d.patch_id;
     ot.slot_base = d.slot_base[ELEM_V], ot.type = ELEM_V;
+    constexpr uint32_t vm = PACKED ? PK_ID_MASK : 0xFFFFu;
     for (uint32_t e = threadIdx.x; e < r.n_src; e += BT)
         if (r.size(e) == 1) {
-            flag[ot.slot(s_ev[2 * e])]     = 1u;
-            flag[ot.slot(s_ev[2 * e + 1])] = 1u;
+            flag[ot.slot(s_ev[2 * e] & vm)]     = 1u;
+            flag[ot.slot(s_ev[2 * e + 1] & vm)] = 1u;
         }
 }
 
@@ -386,26 +485,26 @@ int pick_kmax(uint32_t nnz)
         return cudaErrorInvalidValue; \
     } while (0)
 
-#define RXM_LAUNCH_OP(KERNEL, KM, ...)                                                   \
+#define RXM_LAUNCH_OP(KERNEL, KM, PK, ...)                                               \
     do {                                                                                 \
         switch (op) {                                                                    \
-            case OP_VV: RXM_LAUNCH_ONE(KERNEL, OP_VV, KM, __VA_ARGS__); break;           \
-            case OP_VE: RXM_LAUNCH_ONE(KERNEL, OP_VE, KM, __VA_ARGS__); break;           \
-            case OP_VF: RXM_LAUNCH_ONE(KERNEL, OP_VF, KM, __VA_ARGS__); break;           \
-            case OP_EV: RXM_LAUNCH_ONE(KERNEL, OP_EV, KM, __VA_ARGS__); break;           \
-            case OP_EF: RXM_LAUNCH_ONE(KERNEL, OP_EF, KM, __VA_ARGS__); break;           \
-            case OP_FV: RXM_LAUNCH_ONE(KERNEL, OP_FV, KM, __VA_ARGS__); break;           \
-            case OP_FE: RXM_LAUNCH_ONE(KERNEL, OP_FE, KM, __VA_ARGS__); break;           \
-            case OP_FF: RXM_LAUNCH_ONE(KERNEL, OP_FF, KM, __VA_ARGS__); break;           \
+            case OP_VV: RXM_LAUNCH_ONE(KERNEL, OP_VV, KM, PK, __VA_ARGS__); break;       \
+            case OP_VE: RXM_LAUNCH_ONE(KERNEL, OP_VE, KM, PK, __VA_ARGS__); break;       \
+            case OP_VF: RXM_LAUNCH_ONE(KERNEL, OP_VF, KM, PK, __VA_ARGS__); break;       \
+            case OP_EV: RXM_LAUNCH_ONE(KERNEL, OP_EV, KM, PK, __VA_ARGS__); break;       \
+            case OP_EF: RXM_LAUNCH_ONE(KERNEL, OP_EF, KM, PK, __VA_ARGS__); break;       \
+            case OP_FV: RXM_LAUNCH_ONE(KERNEL, OP_FV, KM, PK, __VA_ARGS__); break;       \
+            case OP_FE: RXM_LAUNCH_ONE(KERNEL, OP_FE, KM, PK, __VA_ARGS__); break;       \
+            case OP_FF: RXM_LAUNCH_ONE(KERNEL, OP_FF, KM, PK, __VA_ARGS__); break;       \
             default: RXM_FAIL("unsupported query op");                                   \
         }                                                                                \
     } while (0)
 
-#define RXM_LAUNCH_ONE(KERNEL, OPV, KM, ...)                                             \
+#define RXM_LAUNCH_ONE(KERNEL, OPV, KM, PK, ...)                                         \
     do {                                                                                 \
-        using Q = dev::PatchQuery<OPV, BT, KM>;                                          \
+        using Q = dev::PatchQuery<OPV, BT, KM, PK>;                                      \
         smem    = Q::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, true) + extra_smem(OPV); \
-        auto kern = KERNEL<OPV, KM>;                                                     \
+        auto kern = KERNEL<OPV, KM, PK>;                                                 \
         e         = set_smem(kern, smem);                                                \
         if (e != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");    \
         kern<<<mv.num_patches, BT, smem, stream>>>(__VA_ARGS__);                         \
@@ -425,10 +524,12 @@ cudaError_t launch_query_store(int op, const MeshView& mv, const KernelLimits& l
     uint32_t    smem = 0;
     cudaError_t e    = cudaSuccess;
     auto        extra_smem = [&](int) { return 0u; };
-    if (km == 12)
-        RXM_LAUNCH_OP(k_query_store, 12, mv, in, out);
+    if (mv.packed)
+        RXM_LAUNCH_OP(k_query_store, 1, true, mv, in, out);
+    else if (km == 12)
+        RXM_LAUNCH_OP(k_query_store, 12, false, mv, in, out);
     else
-        RXM_LAUNCH_OP(k_query_store, 24, mv, in, out);
+        RXM_LAUNCH_OP(k_query_store, 24, false, mv, in, out);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -451,10 +552,12 @@ cudaError_t launch_query_consume(int op, const MeshView& mv, const KernelLimits&
         }
         return r16(4u * (lim.max_n[dst] + 4u));
     };
-    if (km == 12)
-        RXM_LAUNCH_OP(k_query_consume, 12, mv, in.data, out.data);
+    if (mv.packed)
+        RXM_LAUNCH_OP(k_query_consume, 1, true, mv, in.data, out.data);
+    else if (km == 12)
+        RXM_LAUNCH_OP(k_query_consume, 12, false, mv, in.data, out.data);
     else
-        RXM_LAUNCH_OP(k_query_consume, 24, mv, in.data, out.data);
+        RXM_LAUNCH_OP(k_query_consume, 24, false, mv, in.data, out.data);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -463,6 +566,19 @@ cudaError_t launch_vertex_normals(const MeshView& mv, const KernelLimits& lim, c
                                   int unit, cudaStream_t stream, const char** err)
 {
     const uint32_t capv = lim.max_owned[ELEM_V] + 4;
+    if (mv.packed) {
+        const uint32_t smem = r16(6u * lim.max_n[ELEM_F]) + r16(2u * (lim.max_owned[ELEM_V] + 1) + 16) +
+                              r16(4u * lim.max_not_owned[ELEM_V]) + 16u * lim.max_stash + r16(12u * capv) +
+                              16u * lim.max_n[ELEM_V] + 48u * lim.max_n[ELEM_F];
+        cudaError_t e = unit ? set_smem(k_vertex_normals_pk<1>, smem) : set_smem(k_vertex_normals_pk<0>, smem);
+        if (e != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
+        if (unit)
+            k_vertex_normals_pk<1><<<mv.num_patches, BT, smem, stream>>>(mv, x, n);
+        else
+            k_vertex_normals_pk<0><<<mv.num_patches, BT, smem, stream>>>(mv, x, n);
+        ++g_launches;
+        return cudaGetLastError();
+    }
     const uint32_t smem = r16(6u * lim.max_n[ELEM_F]) + r16(4u * lim.max_not_owned[ELEM_V]) + 16u * lim.max_stash +
                           r16(12u * std::max(lim.max_n[ELEM_V], capv)) + r16(12u * capv);
     cudaError_t e = unit ? set_smem(k_vertex_normals<1>, smem) : set_smem(k_vertex_normals<0>, smem);
@@ -484,16 +600,21 @@ cudaError_t launch_laplacian_step(const MeshView& mv, const KernelLimits& lim, c
     const uint32_t extra = r16(12u * std::max(lim.max_n[ELEM_V], capv)) + r16(12u * capv);
     uint32_t       smem;
     cudaError_t    e;
-    if (km == 12) {
-        smem = dev::PatchQuery<OP_VV, BT, 12>::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, true) + extra;
-        e    = set_smem(k_laplacian<12>, smem);
+    if (mv.packed) {
+        smem = dev::PatchQuery<OP_VV, BT, 1, true>::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, true) + extra;
+        e    = set_smem(k_laplacian<1, true>, smem);
         if (e != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
-        k_laplacian<12><<<mv.num_patches, BT, smem, stream>>>(mv, x, xo, lr);
+        k_laplacian<1, true><<<mv.num_patches, BT, smem, stream>>>(mv, x, xo, lr);
+    } else if (km == 12) {
+        smem = dev::PatchQuery<OP_VV, BT, 12, false>::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, true) + extra;
+        e    = set_smem(k_laplacian<12, false>, smem);
+        if (e != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
+        k_laplacian<12, false><<<mv.num_patches, BT, smem, stream>>>(mv, x, xo, lr);
     } else {
-        smem = dev::PatchQuery<OP_VV, BT, 24>::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, true) + extra;
-        e    = set_smem(k_laplacian<24>, smem);
+        smem = dev::PatchQuery<OP_VV, BT, 24, false>::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, true) + extra;
+        e    = set_smem(k_laplacian<24, false>, smem);
         if (e != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
-        k_laplacian<24><<<mv.num_patches, BT, smem, stream>>>(mv, x, xo, lr);
+        k_laplacian<24, false><<<mv.num_patches, BT, smem, stream>>>(mv, x, xo, lr);
     }
     ++g_launches;
     return cudaGetLastError();
@@ -507,16 +628,21 @@ cudaError_t launch_boundary_vertices(const MeshView& mv, const KernelLimits& lim
     const uint32_t extra = r16(4u * lim.max_n[ELEM_E]) + r16(4u * lim.max_not_owned[ELEM_V]) + 16u * lim.max_stash;
     uint32_t       smem;
     cudaError_t    e;
-    if (km == 12) {
-        smem = dev::PatchQuery<OP_EF, BT, 12>::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, false) + extra;
-        e    = set_smem(k_boundary<12>, smem);
+    if (mv.packed) {
+        smem = dev::PatchQuery<OP_EF, BT, 1, true>::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, false) + extra;
+        e    = set_smem(k_boundary<1, true>, smem);
         if (e != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
-        k_boundary<12><<<mv.num_patches, BT, smem, stream>>>(mv, flag);
+        k_boundary<1, true><<<mv.num_patches, BT, smem, stream>>>(mv, flag);
+    } else if (km == 12) {
+        smem = dev::PatchQuery<OP_EF, BT, 12, false>::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, false) + extra;
+        e    = set_smem(k_boundary<12, false>, smem);
+        if (e != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
+        k_boundary<12, false><<<mv.num_patches, BT, smem, stream>>>(mv, flag);
     } else {
-        smem = dev::PatchQuery<OP_EF, BT, 24>::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, false) + extra;
-        e    = set_smem(k_boundary<24>, smem);
+        smem = dev::PatchQuery<OP_EF, BT, 24, false>::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, false) + extra;
+        e    = set_smem(k_boundary<24, false>, smem);
         if (e != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
-        k_boundary<24><<<mv.num_patches, BT, smem, stream>>>(mv, flag);
+        k_boundary<24, false><<<mv.num_patches, BT, smem, stream>>>(mv, flag);
     }
     ++g_launches;
     return cudaGetLastError();

@@ -16,6 +16,14 @@
 //   FF         : EF, then per owned face the faces across its three edges, in
 //                edge order (the reference's order on manifold input,
 //                rxmesh_queries.cuh:839-853).
+// Two transposition paths:
+//   PACKED : every incidence entry carries its rank inside the transposed list
+//            and the list offsets are stored with the patch (patch_layout.h), so
+//            the transpose is ONE pass of plain shared-memory stores
+//            out[offset[col] + rank] = row -- no atomics, no scan, deterministic
+//            ascending order;
+//   wide   : one shared atomic per non-zero (rank kept in a register) + a
+//            hand-written shuffle scan (optionally followed by a per-list sort).
 // Only columns of OWNED source elements are built unless `all_sources` is set
 // (the reference's allow_not_owned, query.inl:174-203).
 #pragma once
@@ -54,44 +62,56 @@ __host__ __device__ constexpr bool op_is_fixed()
 // reference's Iterator, iterator.cuh:50-194).
 struct QueryResult
 {
-    const uint32_t* off;     // CSR offsets (shared) or nullptr for fixed stride
+    const uint16_t* off16;   // CSR offsets (shared, packed path / stored offsets)
+    const uint32_t* off32;   // CSR offsets (shared, atomic path and FF)
     const uint16_t* val;     // neighbour local ids (shared)
-    uint32_t        stride;  // 2 / 3 for EV / FV, FE
+    uint32_t        stride;  // 2 / 3 for EV / FV, FE when both off pointers are null
     uint32_t        shift;   // 1 for FE (drops the direction bit), else 0
+    uint32_t        mask;    // id mask applied after the shift
     uint32_t        n_src;   // number of source elements with a list
 
-    __device__ __forceinline__ uint32_t begin(uint32_t s) const { return off ? off[s] : s * stride; }
-    __device__ __forceinline__ uint32_t size(uint32_t s) const { return off ? off[s + 1] - off[s] : stride; }
-    __device__ __forceinline__ uint32_t at(uint32_t pos) const { return (uint32_t)(val[pos] >> shift); }
+    __device__ __forceinline__ uint32_t begin(uint32_t s) const
+    {
+        return off16 ? (uint32_t)off16[s] : (off32 ? off32[s] : s * stride);
+    }
+    __device__ __forceinline__ uint32_t end(uint32_t s) const
+    {
+        return off16 ? (uint32_t)off16[s + 1] : (off32 ? off32[s + 1] : (s + 1) * stride);
+    }
+    __device__ __forceinline__ uint32_t size(uint32_t s) const { return end(s) - begin(s); }
+    __device__ __forceinline__ uint32_t at(uint32_t pos) const { return ((uint32_t)val[pos] >> shift) & mask; }
 };
 
-template <int OP, int BT, int KMAX>
+template <int OP, int BT, int KMAX, bool PACKED>
 struct PatchQuery
 {
     using Tr = OpTraits<OP>;
+    static constexpr uint32_t W       = Tr::conn == 0 ? 2 : 3;
+    static constexpr uint32_t ID_MASK = PACKED ? PK_ID_MASK : 0xFFFFu;
     uint16_t*   s_conn;
-    uint32_t*   s_off;
+    uint16_t*   s_loff;  // packed: stored list offsets
+    uint32_t*   s_off;   // wide: counters / offsets
     uint16_t*   s_val;
     uint32_t*   s_off2;  // FF only
     uint16_t*   s_val2;  // FF only
     uint32_t*   s_own;
     StashEntry* s_stash;
-    uint32_t    conn_bytes;
+    uint32_t    conn_bytes, loff_bytes;
     uint32_t    n_rows;  // rows of the connectivity section that get loaded
+    uint32_t    n_cols;  // columns whose lists are built
 
     // shared-memory bytes this op needs for a patch with the given maxima
     // (host side; the role of calc_shared_memory, rxmesh_static.inl:498-841)
     __host__ static uint32_t smem_bytes(const uint32_t max_n[3], const uint32_t max_not_owned[3],
                                         uint32_t max_stash, bool with_owner)
     {
-        auto     r16 = [](uint32_t x) { return (x + 15u) & ~15u; };
-        uint32_t b   = 0;
-        const uint32_t nr = Tr::conn == 0 ? max_n[ELEM_E] : max_n[ELEM_F];
-        const uint32_t w  = Tr::conn == 0 ? 2 : 3;
-        b += r16(2 * w * nr);
+        auto           r16 = [](uint32_t x) { return (x + 15u) & ~15u; };
+        uint32_t       b   = 0;
+        const uint32_t nr  = Tr::conn == 0 ? max_n[ELEM_E] : max_n[ELEM_F];
+        b += r16(2 * W * nr);
         if (!op_is_fixed<OP>()) {
             const uint32_t ncols = OP == OP_FF ? max_n[ELEM_E] : max_n[Tr::src];
-            b += r16(4 * (ncols + 1)) + r16(2 * w * nr);
+            b += (PACKED ? r16(2 * (ncols + 1) + 16) : r16(4 * (ncols + 1))) + r16(2 * W * nr);
             if (OP == OP_FF) b += r16(4 * (max_n[ELEM_F] + 1)) + r16(2 * 3 * max_n[ELEM_F] * 2);
         }
         if (with_owner) b += r16(4 * max_not_owned[Tr::dst]) + 16 * max_stash;
@@ -101,17 +121,22 @@ struct PatchQuery
     // carve shared memory (all threads, identical arithmetic)
     __device__ __forceinline__ void plan(const PatchDesc& d, Smem& sm, bool with_owner, bool all_sources)
     {
-        constexpr uint32_t w = Tr::conn == 0 ? 2 : 3;
-        const uint32_t     rows_all = Tr::conn == 0 ? d.n[ELEM_E] : d.n[ELEM_F];
+        const uint32_t rows_all = Tr::conn == 0 ? d.n[ELEM_E] : d.n[ELEM_F];
         n_rows = (op_is_fixed<OP>() && !all_sources) ? d.n_owned[Tr::src] : rows_all;
         if (OP == OP_FF) n_rows = rows_all;
-        conn_bytes = round_up(2u * w * n_rows, 16);
+        conn_bytes = round_up(2u * W * n_rows, 16);
         s_conn     = sm.alloc<uint16_t>(conn_bytes / 2);
-        s_off = nullptr, s_val = nullptr, s_off2 = nullptr, s_val2 = nullptr;
+        s_loff = nullptr, s_off = nullptr, s_val = nullptr, s_off2 = nullptr, s_val2 = nullptr;
+        loff_bytes = 0, n_cols = 0;
         if (!op_is_fixed<OP>()) {
-            const uint32_t ncols = OP == OP_FF ? d.n[ELEM_E] : d.n[Tr::src];
-            s_off                = sm.alloc<uint32_t>(ncols + 1);
-            s_val                = sm.alloc<uint16_t>(w * n_rows);
+            n_cols = OP == OP_FF ? d.n[ELEM_E] : (all_sources ? d.n[Tr::src] : d.n_owned[Tr::src]);
+            if (PACKED) {
+                loff_bytes = round_up(2u * (n_cols + 1), 16);
+                s_loff     = sm.alloc<uint16_t>(loff_bytes / 2);
+            } else {
+                s_off = sm.alloc<uint32_t>(n_cols + 1);
+            }
+            s_val = sm.alloc<uint16_t>(W * n_rows);
             if (OP == OP_FF) {
                 s_off2 = sm.alloc<uint32_t>(d.n[ELEM_F] + 1);
                 s_val2 = sm.alloc<uint16_t>(6u * d.n[ELEM_F]);
@@ -127,7 +152,7 @@ struct PatchQuery
     // bytes that issue() will put in flight
     __device__ __forceinline__ uint32_t tx_bytes(const PatchDesc& d, bool with_owner) const
     {
-        return conn_bytes + (with_owner ? d.own_bytes(Tr::dst) + d.stash_bytes() : 0u);
+        return conn_bytes + loff_bytes + (with_owner ? d.own_bytes(Tr::dst) + d.stash_bytes() : 0u);
     }
 
     // thread 0 only, after mbar_arrive_expect_tx
@@ -135,6 +160,11 @@ struct PatchQuery
     {
         const uint32_t o = Tr::conn == 0 ? d.off_ev() : (Tr::conn == 1 ? d.off_fe() : d.off_fv());
         if (conn_bytes) bulk_g2s(s_conn, blob + o, conn_bytes, bar);
+        if (loff_bytes) {
+            const uint32_t lo = (OP == OP_VV || OP == OP_VE) ? d.off_voff_e()
+                                                              : (OP == OP_VF ? d.off_voff_f() : d.off_eoff_f());
+            bulk_g2s(s_loff, blob + lo, loff_bytes, bar);
+        }
         if (with_owner) {
             if (d.own_bytes(Tr::dst)) bulk_g2s(s_own, blob + d.off_own(Tr::dst), d.own_bytes(Tr::dst), bar);
             if (d.stash_bytes()) bulk_g2s(s_stash, blob + d.off_stash(), d.stash_bytes(), bar);
@@ -153,77 +183,93 @@ struct PatchQuery
         return t;
     }
 
-    // all threads, after the mbarrier wait
+    // all threads, after the mbarrier wait. Ends with a block barrier for CSR ops.
     __device__ __forceinline__ QueryResult compute(const PatchDesc& d, uint32_t* warp_tmp, bool all_sources,
                                                    bool sorted)
     {
         QueryResult    r;
         const uint32_t lim = all_sources ? d.n[Tr::src] : d.n_owned[Tr::src];
-        r.n_src            = lim;
-        r.shift            = 0;
-        r.stride           = 0;
-        r.off              = nullptr;
-        const uint16_t* c  = s_conn;
+        r.n_src = lim, r.shift = 0, r.stride = 0, r.mask = 0xFFFFu;
+        r.off16 = nullptr, r.off32 = nullptr;
+        const uint16_t* c = s_conn;
         if (OP == OP_EV) {
-            r.val = c, r.stride = 2;
+            r.val = c, r.stride = 2, r.mask = ID_MASK;
         } else if (OP == OP_FV) {
-            r.val = c, r.stride = 3;
+            r.val = c, r.stride = 3, r.mask = ID_MASK;
         } else if (OP == OP_FE) {
-            r.val = c, r.stride = 3, r.shift = 1;
+            r.val = c, r.stride = 3, r.shift = 1, r.mask = PACKED ? PK_ID_MASK : 0x7FFFu;
         } else if (OP == OP_VV || OP == OP_VE) {
-            // column = endpoint, value = other endpoint (VV) or the edge (VE)
-            const uint32_t nnz = 2u * n_rows;
-            csr_transpose_lim(nnz, d.n[ELEM_V], lim, warp_tmp, [c](uint32_t i) { return (uint32_t)c[i]; },
-                              [c](uint32_t i) { return OP == OP_VV ? (uint32_t)c[i ^ 1u] : (i >> 1); });
-            r.off = s_off, r.val = s_val;
-        } else if (OP == OP_VF) {
-            const uint32_t nnz = 3u * n_rows;
-            csr_transpose_lim(nnz, d.n[ELEM_V], lim, warp_tmp, [c](uint32_t i) { return (uint32_t)c[i]; },
-                              [](uint32_t i) { return i / 3u; });
-            r.off = s_off, r.val = s_val;
-        } else if (OP == OP_EF || OP == OP_FF) {
-            const uint32_t nnz  = 3u * n_rows;
-            const uint32_t elim = OP == OP_FF ? d.n[ELEM_E] : lim;
-            csr_transpose_lim(nnz, d.n[ELEM_E], elim, warp_tmp, [c](uint32_t i) { return (uint32_t)(c[i] >> 1); },
-                              [](uint32_t i) { return i / 3u; });
-            r.off = s_off, r.val = s_val;
+            if (PACKED) {
+                // one thread per edge: both endpoints in one 32-bit read
+                const uint32_t* c2 = reinterpret_cast<const uint32_t*>(c);
+                for (uint32_t e = threadIdx.x; e < n_rows; e += BT) {
+                    const uint32_t w  = c2[e];
+                    const uint32_t a = w & 0xFFFFu, b = w >> 16;
+                    const uint32_t va = a & PK_ID_MASK, vb = b & PK_ID_MASK;
+                    if (va < n_cols) s_val[s_loff[va] + (a >> PK_ID_BITS)] = (uint16_t)(OP == OP_VV ? vb : e);
+                    if (vb < n_cols) s_val[s_loff[vb] + (b >> PK_ID_BITS)] = (uint16_t)(OP == OP_VV ? va : e);
+                }
+                __syncthreads();
+            } else {
+                transpose_atomic(2u * n_rows, warp_tmp, [c](uint32_t i) { return (uint32_t)c[i]; },
+                                 [c](uint32_t i) { return OP == OP_VV ? (uint32_t)c[i ^ 1u] : (i >> 1); });
+                if (sorted) csr_sort_lists<BT>(n_cols, s_off, s_val);
+            }
+            r.off16 = PACKED ? s_loff : nullptr, r.off32 = PACKED ? nullptr : s_off, r.val = s_val;
+        } else {  // VF, EF, FF: transpose of a 3-wide face array
+            constexpr uint32_t sh = OP == OP_VF ? 0u : 1u;                          // FE: drop dir bit
+            constexpr uint32_t rk = OP == OP_VF ? PK_ID_BITS : PK_ID_BITS + 1;       // rank position
+            if (PACKED) {
+                for (uint32_t f = threadIdx.x; f < n_rows; f += BT) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const uint32_t a  = c[3 * f + j];
+                        const uint32_t cc = (a >> sh) & PK_ID_MASK;
+                        if (cc < n_cols) s_val[s_loff[cc] + (a >> rk)] = (uint16_t)f;
+                    }
+                }
+                __syncthreads();
+            } else {
+                transpose_atomic(3u * n_rows, warp_tmp, [c](uint32_t i) { return (uint32_t)c[i] >> sh; },
+                                 [](uint32_t i) { return i / 3u; });
+                if (sorted && OP != OP_FF) csr_sort_lists<BT>(n_cols, s_off, s_val);
+            }
+            r.off16 = PACKED ? s_loff : nullptr, r.off32 = PACKED ? nullptr : s_off, r.val = s_val;
             if (OP == OP_FF) {
-                // faces across the three edges of every source face, edge order
-                const uint32_t nf = lim;
+                // faces across the three edges of every source face, in edge order
+                const QueryResult ef = r;
+                const uint32_t    nf = lim;
+                const uint32_t    em = PACKED ? PK_ID_MASK : 0x7FFFu;
                 for (uint32_t f = threadIdx.x; f <= nf; f += BT) {
                     uint32_t k = 0;
                     if (f < nf)
-                        for (int j = 0; j < 3; ++j) {
-                            const uint32_t e = c[3 * f + j] >> 1;
-                            k += s_off[e + 1] - s_off[e] - 1;
-                        }
+                        for (int j = 0; j < 3; ++j)
+                            k += ef.size((c[3 * f + j] >> 1) & em) - 1;
                     s_off2[f] = k;
                 }
                 block_exclusive_scan<BT>(s_off2, nf, warp_tmp);
                 for (uint32_t f = threadIdx.x; f < nf; f += BT) {
                     uint32_t w = s_off2[f];
                     for (int j = 0; j < 3; ++j) {
-                        const uint32_t e = c[3 * f + j] >> 1;
-                        for (uint32_t i = s_off[e]; i < s_off[e + 1]; ++i)
+                        const uint32_t e = (c[3 * f + j] >> 1) & em;
+                        for (uint32_t i = ef.begin(e); i < ef.end(e); ++i)
                             if (s_val[i] != f) s_val2[w++] = s_val[i];
                     }
                 }
                 __syncthreads();
-                r.off = s_off2, r.val = s_val2;
+                r.off16 = nullptr, r.off32 = s_off2, r.val = s_val2;
             }
         }
-        if (sorted && r.off && OP != OP_FF) csr_sort_lists<BT>(lim, s_off, s_val);
         return r;
     }
 
    private:
-    // transpose keeping only columns < lim
+    // wide path: one shared atomic per non-zero, rank kept in a register
     template <typename ColFn, typename ValFn>
-    __device__ __forceinline__ void csr_transpose_lim(uint32_t nnz, uint32_t ncols, uint32_t lim,
-                                                      uint32_t* warp_tmp, ColFn col, ValFn val)
+    __device__ __forceinline__ void transpose_atomic(uint32_t nnz, uint32_t* warp_tmp, ColFn col, ValFn val)
     {
-        (void)ncols;
         const uint32_t tid = threadIdx.x;
+        const uint32_t lim = n_cols;
         for (uint32_t i = tid; i <= lim; i += BT)
             s_off[i] = 0;
         __syncthreads();

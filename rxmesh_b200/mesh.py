@@ -216,6 +216,10 @@ class RXMeshStatic:
     def total_local(self, elem):
         return self._info(17 + int(elem))
 
+    def is_packed(self):
+        """True when the patch store uses the rank-annotated (atomic-free) format."""
+        return bool(self._info(22))
+
     def ribbon_overhead(self):
         """ribbon faces / F (patcher/patcher.h:139-142)."""
         return self.total_local(2) / self.get_num_faces() - 1.0
@@ -257,9 +261,18 @@ class RXMeshStatic:
         def arr(ptr, cnt):
             return np.ctypeslib.as_array(ptr, shape=(cnt,)).copy() if cnt else np.zeros(0, np.uint32)
 
+        ev_raw, fe_raw, fv_raw = arr(v.ev, 2 * n[1]), arr(v.fe, 3 * n[2]), arr(v.fv, 3 * n[2])
+        pk = bool(v.packed)
+        idm, fem = (0x7FF, 0xFFF) if pk else (0xFFFF, 0xFFFF)
         return dict(patch_id=int(v.patch_id), n=n, n_owned=no, slot_base=list(v.slot_base),
-                    lin_base=list(v.lin_base), ev=arr(v.ev, 2 * n[1]).reshape(-1, 2),
-                    fe=arr(v.fe, 3 * n[2]).reshape(-1, 3), fv=arr(v.fv, 3 * n[2]).reshape(-1, 3),
+                    lin_base=list(v.lin_base), packed=pk,
+                    ev=(ev_raw & idm).reshape(-1, 2), fe=(fe_raw & fem).reshape(-1, 3),
+                    fv=(fv_raw & idm).reshape(-1, 3),
+                    ev_rank=(ev_raw >> 11).reshape(-1, 2) if pk else None,
+                    fv_rank=(fv_raw >> 11).reshape(-1, 3) if pk else None,
+                    fe_rank=(fe_raw >> 12).reshape(-1, 3) if pk else None,
+                    voff_e=arr(v.voff_e, n[0] + 1), voff_f=arr(v.voff_f, n[0] + 1),
+                    eoff_f=arr(v.eoff_f, n[1] + 1),
                     owner=[arr(v.owner[t], n[t] - no[t]) for t in range(3)],
                     stash=arr(v.stash, 4 * v.n_stash).reshape(-1, 4),
                     ltog=[arr(v.ltog[t], n[t]) for t in range(3)])

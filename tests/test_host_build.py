@@ -66,6 +66,24 @@ def test_ltog_mapping_and_numbering(built):
         fe = pv["fe"].astype(np.int64)
         assert np.array_equal(pv["ev"].reshape(-1)[2 * (fe >> 1) + (fe & 1)], pv["fv"])
         assert np.array_equal(lv[pv["fv"]], F[lf])
+        # rank-annotated incidence + stored list offsets (patch_layout.h): scattering row ids to
+        # offset[col] + rank must reproduce the transposed lists in ascending row order
+        assert pv["packed"] == m.is_packed()
+        for conn, off, ncol, rank in ((pv["ev"], pv["voff_e"], pv["n"][0], pv["ev_rank"]),
+                                      (pv["fv"], pv["voff_f"], pv["n"][0], pv["fv_rank"]),
+                                      (pv["fe"] >> 1, pv["eoff_f"], pv["n"][1], pv["fe_rank"])):
+            cols = conn.reshape(-1).astype(np.int64)
+            cnt = np.bincount(cols, minlength=ncol)
+            assert np.array_equal(np.concatenate([[0], np.cumsum(cnt)]), off)
+            if pv["packed"]:
+                pos = off[cols].astype(np.int64) + rank.reshape(-1)
+                assert np.array_equal(np.sort(pos), np.arange(cols.shape[0]))  # a permutation
+                rows = np.arange(cols.shape[0]) // conn.shape[1]
+                out = np.empty(cols.shape[0], np.int64)
+                out[pos] = rows
+                for c in range(0, ncol, 5):
+                    seg = out[off[c]:off[c + 1]]
+                    assert np.all(np.diff(seg) >= 0) and np.array_equal(np.sort(rows[cols == c]), seg)
         # owner tables name the owning patch and the element's local id there
         for t in range(3):
             no = pv["n_owned"][t]
@@ -99,6 +117,19 @@ def test_owner_is_lowest_patch(built):
     want_e = np.full(T.ne, 1 << 40, dtype=np.int64)
     np.minimum.at(want_e, T.fe.reshape(-1).astype(np.int64), np.repeat(fpatch, 3))
     assert np.array_equal(want_e, m.elem_patch(1))
+
+
+def test_wide_format_fallback(monkeypatch):
+    V, F = make_mesh("sphere3")
+    assert rx.RXMeshStatic(F, device=False).is_packed()
+    monkeypatch.setenv("RXM_FORCE_WIDE", "1")
+    m = rx.RXMeshStatic(F, device=False)
+    assert not m.is_packed() and m.patch(0)["ev_rank"] is None
+    monkeypatch.delenv("RXM_FORCE_WIDE")
+    # a vertex of valence >= 32 cannot carry its rank in 5 bits -> wide format
+    k = 40
+    fan = np.array([[0, 1 + i, 1 + (i + 1) % k] for i in range(k)], dtype=np.uint32)
+    assert not rx.RXMeshStatic(fan, device=False).is_packed()
 
 
 def test_user_patching_is_honoured():
