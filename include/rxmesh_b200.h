@@ -67,7 +67,8 @@ enum {
     RXM_INFO_MAX_VERTICES_PER_PATCH = 10, RXM_INFO_MAX_EDGES_PER_PATCH = 11, RXM_INFO_MAX_FACES_PER_PATCH = 12,
     RXM_INFO_NUM_SLOTS_V = 13, RXM_INFO_NUM_SLOTS_E = 14, RXM_INFO_NUM_SLOTS_F = 15,
     RXM_INFO_TOPO_BYTES = 16, RXM_INFO_TOTAL_LOCAL_V = 17, RXM_INFO_TOTAL_LOCAL_E = 18,
-    RXM_INFO_TOTAL_LOCAL_F = 19, RXM_INFO_MAX_STASH = 20, RXM_INFO_ON_DEVICE = 21, RXM_INFO_PACKED = 22
+    RXM_INFO_TOTAL_LOCAL_F = 19, RXM_INFO_MAX_STASH = 20, RXM_INFO_ON_DEVICE = 21, RXM_INFO_PACKED = 22,
+    RXM_INFO_FANS = 23
 };
 uint64_t rxm_mesh_info(const rxm_mesh* m, int what);
 double   rxm_mesh_build_seconds(const rxm_mesh* m, int patcher_only);
@@ -89,6 +90,11 @@ typedef struct {
     const uint16_t* voff_e;      /* n[V]+1: start of every local vertex's edge list (VE / VV) */
     const uint16_t* voff_f;      /* n[V]+1: start of every local vertex's face list (VF) */
     const uint16_t* eoff_f;      /* n[E]+1: start of every local edge's face list (EF) */
+    /* one-ring fans of the owned vertices (NULL when the mesh has none): fan_off[n_owned[V]+1], bit 15 =
+     * closed fan, low 15 bits = start in fan_v; fan_v = neighbour local vertex ids in oriented order */
+    const uint16_t* fan_off;
+    const uint16_t* fan_v;
+    uint32_t        fan_total;
     const uint32_t* owner[3];    /* n[t]-n_owned[t]: (stash slot << 16) | local id in owner */
     const uint32_t* stash;       /* 4*n_stash u32: patch, slot base V, E, F */
     uint32_t        n_stash;

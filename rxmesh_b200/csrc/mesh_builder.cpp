@@ -4,6 +4,7 @@
 #include <omp.h>
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -477,6 +478,86 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
     std::vector<uint32_t>().swap(vf_off);
     std::vector<uint32_t>().swap(vf_val);
 
+    // ---- phase A2: one-ring fans of the owned vertices (local ids), if the input allows ----
+    // For owned vertex v every incident face (v, a, b) (a cyclic rotation of its stored corner
+    // order) is a directed link a -> b; the links must chain into ONE open or closed sequence.
+    std::vector<std::vector<uint16_t>> fan_v(P), fan_off(P);
+    bool fans_ok = !opt.no_fans && M.is_edge_manifold && M.max_valence < 4096;
+    if (fans_ok) {
+        int bad = 0;
+#pragma omp parallel for schedule(dynamic, 16) reduction(| : bad)
+        for (int64_t p = 0; p < (int64_t)P; ++p) {
+            if (bad) continue;
+            const Tmp&     T   = tmp[p];
+            const uint32_t nov = T.n_owned[ELEM_V];
+            auto lv = [&](uint32_t g) -> uint32_t {  // global vertex -> local id in this patch
+                const auto& L = T.l[ELEM_V];
+                if (vpatch[g] == (uint32_t)p) return (uint32_t)(std::lower_bound(L.begin(), L.begin() + nov, g) - L.begin());
+                return (uint32_t)(std::lower_bound(L.begin() + nov, L.end(), g) - L.begin());
+            };
+            // links grouped by owned vertex
+            std::vector<uint32_t> cnt(nov + 1, 0);
+            std::vector<std::array<uint16_t, 3>> lf(T.l[ELEM_F].size());
+            for (size_t f = 0; f < T.l[ELEM_F].size(); ++f)
+                for (int j = 0; j < 3; ++j) {
+                    lf[f][j] = (uint16_t)lv(fv[3ull * T.l[ELEM_F][f] + j]);
+                    if (lf[f][j] < nov) cnt[lf[f][j]]++;
+                }
+            std::vector<uint32_t> off(nov + 1, 0);
+            for (uint32_t v = 0; v < nov; ++v)
+                off[v + 1] = off[v] + cnt[v];
+            std::vector<std::array<uint16_t, 2>> links(off[nov]);
+            std::vector<uint32_t>                cur(off.begin(), off.end() - 1);
+            for (size_t f = 0; f < lf.size(); ++f)
+                for (int j = 0; j < 3; ++j)
+                    if (lf[f][j] < nov) links[cur[lf[f][j]]++] = {lf[f][(j + 1) % 3], lf[f][(j + 2) % 3]};
+            auto& FO = fan_off[p];
+            auto& FV = fan_v[p];
+            FO.assign(nov + 1, 0);
+            for (uint32_t v = 0; v < nov && !bad; ++v) {
+                auto*          L = links.data() + off[v];
+                const uint32_t k = off[v + 1] - off[v];
+                // start: a link whose first vertex is nobody's second (open fan), else link 0
+                uint32_t start = k, n_start = 0;
+                for (uint32_t i = 0; i < k; ++i) {
+                    bool has_pred = false;
+                    for (uint32_t j = 0; j < k; ++j)
+                        has_pred |= (L[j][1] == L[i][0]);
+                    if (!has_pred) start = i, ++n_start;
+                }
+                const bool closed = (n_start == 0);
+                if (n_start > 1 || k == 0) { bad = 1; break; }
+                if (closed) {  // deterministic start: the link with the smallest first vertex
+                    start = 0;
+                    for (uint32_t i = 1; i < k; ++i)
+                        if (L[i][0] < L[start][0]) start = i;
+                }
+                if (FV.size() + k + 1 > FAN_OFF_MASK) { bad = 1; break; }
+                FO[v] = (uint16_t)(FV.size() | (closed ? FAN_CLOSED : 0));
+                uint32_t curl = start, used = 0;
+                FV.push_back(L[curl][0]);
+                while (used < k) {
+                    ++used;
+                    const uint16_t nxt = L[curl][1];
+                    if (used == k) {
+                        if (closed) { if (nxt != L[start][0]) bad = 1; }
+                        else FV.push_back(nxt);
+                        break;
+                    }
+                    FV.push_back(nxt);
+                    uint32_t found = k, nf_ = 0;
+                    for (uint32_t j = 0; j < k; ++j)
+                        if (L[j][0] == nxt) found = j, ++nf_;
+                    if (nf_ != 1) { bad = 1; break; }
+                    curl = found;
+                }
+            }
+            FO[nov] = (uint16_t)FV.size();
+        }
+        fans_ok = !bad;
+    }
+    M.fans = fans_ok;
+
     // ---- prefixes: attribute slots (padded to 4), linear ids, ltog offsets, blob offsets ----
     M.desc.assign(P, PatchDesc());
     for (int t = 0; t < 3; ++t) {
@@ -503,7 +584,9 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
             M.total_local[t] += D.n[t];
         }
         D.n_stash    = (uint16_t)tmp[p].stash.size();
-        D.flags      = 0;
+        D.flags      = M.fans ? FLAG_FANS : 0;
+        D.fan_total  = M.fans ? (uint16_t)fan_v[p].size() : 0;
+        M.max_fan_total = std::max<uint32_t>(M.max_fan_total, D.fan_total);
         M.max_stash  = std::max<uint32_t>(M.max_stash, D.n_stash);
         D.topo_off   = topo_total;
         D.topo_bytes = D.off_stash() + D.stash_bytes();
@@ -590,6 +673,10 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
             annotate(lev, 2 * nep, voe, nvp, 0, PK_ID_BITS);
             annotate(lfv, 3 * nfp, vof, nvp, 0, PK_ID_BITS);
             annotate(lfe, 3 * nfp, eof, nep, 1, PK_ID_BITS + 1);
+        }
+        if (M.fans) {
+            memcpy(B + D.off_fanoff(), fan_off[p].data(), fan_off[p].size() * 2);
+            memcpy(B + D.off_fanv(), fan_v[p].data(), fan_v[p].size() * 2);
         }
         for (int t = 0; t < 3; ++t) {
             uint32_t* own = reinterpret_cast<uint32_t*>(B + D.off_own(t));

@@ -33,6 +33,8 @@ struct HostMesh
     uint32_t num_slots[3]           = {0, 0, 0};
     uint64_t total_local[3]         = {0, 0, 0};  // sum over patches of n[t] (ribbon stats)
     bool     packed                 = false;  // rank-annotated patch format (patch_layout.h)
+    bool     fans                   = false;  // one-ring fans stored (manifold, consistently oriented input)
+    uint32_t max_fan_total          = 0;
     double   build_seconds          = 0;
     double   patcher_seconds        = 0;
 
@@ -62,6 +64,7 @@ struct BuildOptions
     bool     verbose      = false;
     uint32_t lloyd_iters  = 8;
     bool     force_wide   = false;  // never use the packed format (tests of the atomic path)
+    bool     no_fans      = false;  // never store one-ring fans (tests of the generic kernels)
 };
 
 // Global edge numbering identical to the reference (first appearance while

@@ -28,6 +28,14 @@
 //    (kernels/rxmesh_queries.cuh:16-107), the same way the reference already
 //    hides the edge direction in bit 0 of FE (rxmesh.cpp:941-983).  Meshes that
 //    exceed the limits use the "wide" format (plain ids) and the atomic path;
+//  * ONE-RING FANS (present when every owned vertex of every patch has a single,
+//    consistently oriented, edge-manifold fan): per owned vertex the cyclic
+//    (or, on a mesh boundary, open) sequence of its neighbour vertices, faces
+//    lying between consecutive entries.  2 bytes per half-edge -- the same HBM
+//    footprint as EV -- but it answers VV (and oriented VV, the reference's
+//    orient_edges_around_vertices, kernels/rxmesh_queries.cuh:375-499) by a plain
+//    read, and lets vertex normals / Laplacian run one thread per OWNED vertex
+//    with register accumulators: no transpose, no atomics, no ribbon-face work;
 //  * local ids are owned-first, each half sorted by global id (the reference's
 //    numbering, rxmesh.cpp:845-869), so the owned / active bitmasks of the
 //    reference collapse to a prefix [0, n_owned) and the not-owned -> owner
@@ -84,6 +92,9 @@ constexpr uint32_t PK_MAX_ELEMS = 2048;    // per element type and patch
 constexpr uint32_t PK_MAX_VRANK = 32;      // ranks of vertex lists: 5 bits (entry >> 11)
 constexpr uint32_t PK_MAX_ERANK = 16;      // ranks of edge lists: 4 bits (FE entry >> 12)
 constexpr uint16_t FLAG_PACKED  = 1;
+constexpr uint16_t FLAG_FANS    = 2;
+constexpr uint16_t FAN_CLOSED   = 0x8000;  // bit 15 of a fan_off entry: the fan of this vertex is closed
+constexpr uint16_t FAN_OFF_MASK = 0x7FFF;
 constexpr uint64_t INVALID64_ = 0xFFFFFFFFFFFFFFFFull;
 
 RXM_HD uint32_t round_up(uint32_t x, uint32_t m)
@@ -114,8 +125,9 @@ struct alignas(16) PatchDesc
     uint32_t slot_base[3];  // attribute slot base for V, E, F (multiple of 4)
     uint32_t lin_base[3];   // gap-free linear-id prefix (reference Context::linear_id, context.h:275-290)
     uint16_t n_stash;       // neighbour patches referenced by the owner tables
-    uint16_t flags;         // bit 0: packed (rank-annotated) format
-    uint32_t pad1;
+    uint16_t flags;         // bit 0: packed (rank-annotated) format, bit 1: one-ring fans present
+    uint16_t fan_total;     // entries of the fan neighbour array
+    uint16_t pad1;
 
     // ---- section byte offsets inside the blob (all multiples of 16) ----
     RXM_HD uint32_t ev_bytes() const { return round_up(4u * n[ELEM_E], 16); }
@@ -130,9 +142,14 @@ struct alignas(16) PatchDesc
     RXM_HD uint32_t off_voff_e() const { return off_fv() + fe_bytes(); }
     RXM_HD uint32_t off_voff_f() const { return off_voff_e() + voff_bytes(); }
     RXM_HD uint32_t off_eoff_f() const { return off_voff_f() + voff_bytes(); }
+    // one-ring fans of the owned vertices: fan_off[nov+1] (bit 15 = closed fan), fan_v[fan_total]
+    RXM_HD uint32_t fanoff_bytes() const { return (flags & 2) ? round_up(2u * (n_owned[ELEM_V] + 1u), 16) : 0u; }
+    RXM_HD uint32_t fanv_bytes() const { return (flags & 2) ? round_up(2u * fan_total, 16) : 0u; }
+    RXM_HD uint32_t off_fanoff() const { return off_eoff_f() + eoff_bytes(); }
+    RXM_HD uint32_t off_fanv() const { return off_fanoff() + fanoff_bytes(); }
     RXM_HD uint32_t off_own(uint32_t t) const
     {
-        uint32_t o = off_eoff_f() + eoff_bytes();
+        uint32_t o = off_fanv() + fanv_bytes();
         for (uint32_t i = 0; i < t; ++i)
             o += own_bytes(i);
         return o;
@@ -153,6 +170,7 @@ struct MeshView
     uint32_t         num_elems[3];  // #V, #E, #F of the (local shard of the) mesh
     const uint32_t*  patch_slot_base[3];  // [num_patches+1] per type: slot base of every patch
     uint32_t         packed;              // 1: every patch uses the rank-annotated format
+    uint32_t         fans;                // 1: every patch stores the one-ring fans of its owned vertices
 };
 
 // Attribute layouts: numeric values of the reference's layoutT (types.h:84-90).

@@ -106,6 +106,7 @@ int rxm_mesh_create(const uint32_t* fv, uint32_t num_faces, const uint32_t* face
     opt.num_threads = num_threads;
     opt.verbose     = getenv("RXM_VERBOSE") != nullptr;
     opt.force_wide  = getenv("RXM_FORCE_WIDE") != nullptr;  // tests: exercise the atomic (wide-format) kernels
+    opt.no_fans     = getenv("RXM_NO_FANS") != nullptr;     // tests: exercise the generic (transpose) kernels
     std::string e;
     try {
         e = build_mesh(fv, num_faces, face_patch, opt, m->h);
@@ -123,6 +124,7 @@ int rxm_mesh_create(const uint32_t* fv, uint32_t num_faces, const uint32_t* face
     }
     m->lim.max_stash               = m->h.max_stash;
     m->lim.max_face_adjacent_faces = m->h.max_face_adjacent_faces;
+    m->lim.max_fan_total           = m->h.max_fan_total;
     *out                           = m;
     return RXM_OK;
 }
@@ -146,6 +148,7 @@ int rxm_mesh_to_device(rxm_mesh* m)
     m->view.topo        = m->d_topo;
     m->view.num_patches = h.num_patches;
     m->view.packed      = h.packed ? 1u : 0u;
+    m->view.fans        = h.fans ? 1u : 0u;
     for (int t = 0; t < 3; ++t) {
         m->view.num_slots[t]       = h.num_slots[t];
         m->view.num_elems[t]       = h.num_elems[t];
@@ -208,6 +211,7 @@ uint64_t rxm_mesh_info(const rxm_mesh* m, int what)
         case RXM_INFO_MAX_STASH: return h.max_stash;
         case RXM_INFO_ON_DEVICE: return m->on_device;
         case RXM_INFO_PACKED: return h.packed;
+        case RXM_INFO_FANS: return h.fans;
         default: return 0;
     }
 }
@@ -238,6 +242,9 @@ int rxm_mesh_patch(const rxm_mesh* m, uint32_t p, rxm_patch_view* o)
     o->voff_f  = reinterpret_cast<const uint16_t*>(B + D.off_voff_f());
     o->eoff_f  = reinterpret_cast<const uint16_t*>(B + D.off_eoff_f());
     o->packed  = (D.flags & FLAG_PACKED) ? 1u : 0u;
+    o->fan_off = (D.flags & FLAG_FANS) ? reinterpret_cast<const uint16_t*>(B + D.off_fanoff()) : nullptr;
+    o->fan_v   = (D.flags & FLAG_FANS) ? reinterpret_cast<const uint16_t*>(B + D.off_fanv()) : nullptr;
+    o->fan_total = D.fan_total;
     o->stash   = reinterpret_cast<const uint32_t*>(B + D.off_stash());
     o->n_stash = D.n_stash;
     return RXM_OK;

@@ -366,6 +366,176 @@ __global__ void __launch_bounds__(BT) k_laplacian(MeshView mv, const float* __re
     }
 }
 
+
+// --------------------------------------------------------------------------
+// one-ring-fan kernels: one thread per OWNED vertex, register accumulators
+// --------------------------------------------------------------------------
+// Loads the fan sections + owner table + the patch's coordinate slice, gathers the
+// ribbon vertices' coordinates, and leaves every local vertex as one float4 in s_x.
+struct FanPatch
+{
+    const uint16_t* s_fo;
+    const uint16_t* s_fv;
+    float*          s_xp;  // 3*cap floats: owned slice as it arrived; reused for the result
+    float4*         s_x;
+    uint32_t        nv, nov, cap;
+};
+
+__device__ __forceinline__ FanPatch fan_load(const MeshView& mv, const PatchDesc& d, const float* __restrict__ x,
+                                             uint8_t* smem_raw, uint64_t* bar)
+{
+    const uint8_t* blob = mv.topo + d.topo_off;
+    FanPatch       F;
+    F.nv = d.n[ELEM_V], F.nov = d.n_owned[ELEM_V], F.cap = d.slot_cap(ELEM_V);
+    Smem        sm(smem_raw);
+    uint16_t*   s_fo    = sm.alloc<uint16_t>(d.fanoff_bytes() / 2);
+    uint16_t*   s_fv    = sm.alloc<uint16_t>(d.fanv_bytes() / 2);
+    uint32_t*   s_own   = sm.alloc<uint32_t>(d.own_bytes(ELEM_V) / 4);
+    StashEntry* s_stash = sm.alloc<StashEntry>(d.n_stash);
+    F.s_xp              = sm.alloc<float>(3 * F.cap);
+    F.s_x               = sm.alloc<float4>(F.nv);
+    F.s_fo = s_fo, F.s_fv = s_fv;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(bar, d.fanoff_bytes() + d.fanv_bytes() + d.own_bytes(ELEM_V) + d.stash_bytes() + 12u * F.cap);
+        bulk_g2s(s_fo, blob + d.off_fanoff(), d.fanoff_bytes(), bar);
+        if (d.fanv_bytes()) bulk_g2s(s_fv, blob + d.off_fanv(), d.fanv_bytes(), bar);
+        if (d.own_bytes(ELEM_V)) bulk_g2s(s_own, blob + d.off_own(ELEM_V), d.own_bytes(ELEM_V), bar);
+        if (d.stash_bytes()) bulk_g2s(s_stash, blob + d.off_stash(), d.stash_bytes(), bar);
+        if (F.cap) bulk_g2s(F.s_xp, x + 3ull * d.slot_base[ELEM_V], 12u * F.cap, bar);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+    for (uint32_t i = threadIdx.x; i < F.nv; i += BT) {
+        float4 q;
+        if (i < F.nov) {
+            q = make_float4(F.s_xp[3 * i], F.s_xp[3 * i + 1], F.s_xp[3 * i + 2], 0.f);
+        } else {
+            const uint32_t o = s_own[i - F.nov];
+            const float*   g = x + 3ull * ((uint64_t)s_stash[o >> 16].slot_base[ELEM_V] + (o & 0xFFFFu));
+            q = make_float4(ldg_stream(g), ldg_stream(g + 1), ldg_stream(g + 2), 0.f);
+        }
+        F.s_x[i] = q;
+    }
+    __syncthreads();
+    return F;
+}
+
+__device__ __forceinline__ void fan_store(const PatchDesc& d, const FanPatch& F, float* __restrict__ out)
+{
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0 && F.cap) {
+        bulk_s2g(out + 3ull * d.slot_base[ELEM_V], F.s_xp, 12u * F.cap);
+        bulk_commit();
+        bulk_wait_all_read();
+    }
+}
+
+template <int UNIT>
+__global__ void __launch_bounds__(BT) k_vertex_normals_fan(MeshView mv, const float* __restrict__ x,
+                                                           float* __restrict__ nrm)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint64_t                      bar;
+    const PatchDesc d = load_desc(mv.desc + blockIdx.x);
+    const FanPatch  F = fan_load(mv, d, x, smem_raw, &bar);
+    for (uint32_t v = threadIdx.x; v < F.cap; v += BT) {
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        if (v < F.nov) {
+            const uint32_t o = F.s_fo[v], b = o & FAN_OFF_MASK, e = F.s_fo[v + 1] & FAN_OFF_MASK;
+            const float4   p = F.s_x[v];
+            float4         q = F.s_x[F.s_fv[b]];
+            const float    d0x = q.x - p.x, d0y = q.y - p.y, d0z = q.z - p.z;
+            const float    l0 = d0x * d0x + d0y * d0y + d0z * d0z;
+            float          px = d0x, py = d0y, pz = d0z, pl = l0;
+            auto face = [&](float cx, float cy, float cz, float cl) {
+                // face (v, prev, cur): n = (prev - v) x (cur - v); corner weight 1 / (|prev-v|^2 + |cur-v|^2)
+                const float nx = py * cz - pz * cy, ny = pz * cx - px * cz, nz = px * cy - py * cx;
+                const float w  = UNIT ? rsqrtf(nx * nx + ny * ny + nz * nz) : __frcp_rn(pl + cl);
+                sx += nx * w, sy += ny * w, sz += nz * w;
+            };
+            for (uint32_t i = b + 1; i < e; ++i) {
+                q = F.s_x[F.s_fv[i]];
+                const float cx = q.x - p.x, cy = q.y - p.y, cz = q.z - p.z;
+                const float cl = cx * cx + cy * cy + cz * cz;
+                face(cx, cy, cz, cl);
+                px = cx, py = cy, pz = cz, pl = cl;
+            }
+            if (o & FAN_CLOSED) face(d0x, d0y, d0z, l0);
+        }
+        F.s_xp[3 * v] = sx, F.s_xp[3 * v + 1] = sy, F.s_xp[3 * v + 2] = sz;
+    }
+    fan_store(d, F, nrm);
+}
+
+__global__ void __launch_bounds__(BT) k_laplacian_fan(MeshView mv, const float* __restrict__ x, float* __restrict__ xo,
+                                                      double lr)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint64_t                      bar;
+    const PatchDesc d = load_desc(mv.desc + blockIdx.x);
+    const FanPatch  F = fan_load(mv, d, x, smem_raw, &bar);
+    for (uint32_t v = threadIdx.x; v < F.cap; v += BT) {
+        float ox = 0.f, oy = 0.f, oz = 0.f;
+        if (v < F.nov) {
+            const uint32_t b = F.s_fo[v] & FAN_OFF_MASK, e = F.s_fo[v + 1] & FAN_OFF_MASK;
+            const float4   p = F.s_x[v];
+            float          gx = 0.f, gy = 0.f, gz = 0.f;
+            for (uint32_t i = b; i < e; ++i) {
+                const float4 q = F.s_x[F.s_fv[i]];
+                gx += 2.f * (p.x - q.x), gy += 2.f * (p.y - q.y), gz += 2.f * (p.z - q.z);
+            }
+            ox = (float)__dsub_rn((double)p.x, __dmul_rn(lr, (double)gx));
+            oy = (float)__dsub_rn((double)p.y, __dmul_rn(lr, (double)gy));
+            oz = (float)__dsub_rn((double)p.z, __dmul_rn(lr, (double)gz));
+        }
+        F.s_xp[3 * v] = ox, F.s_xp[3 * v + 1] = oy, F.s_xp[3 * v + 2] = oz;
+    }
+    fan_store(d, F, xo);
+}
+
+// VV consume through the fans: out(v) = sum over the one-ring of in(u)
+__global__ void __launch_bounds__(BT) k_vv_consume_fan(MeshView mv, const float* __restrict__ in, float* __restrict__ out)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint64_t                      bar;
+    const PatchDesc d    = load_desc(mv.desc + blockIdx.x);
+    const uint8_t*  blob = mv.topo + d.topo_off;
+    const uint32_t  nv = d.n[ELEM_V], nov = d.n_owned[ELEM_V], cap = d.slot_cap(ELEM_V);
+    Smem            sm(smem_raw);
+    uint16_t*       s_fo    = sm.alloc<uint16_t>(d.fanoff_bytes() / 2);
+    uint16_t*       s_fv    = sm.alloc<uint16_t>(d.fanv_bytes() / 2);
+    uint32_t*       s_own   = sm.alloc<uint32_t>(d.own_bytes(ELEM_V) / 4);
+    StashEntry*     s_stash = sm.alloc<StashEntry>(d.n_stash);
+    float*          s_in    = sm.alloc<float>(max(nv, cap));
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(&bar, d.fanoff_bytes() + d.fanv_bytes() + d.own_bytes(ELEM_V) + d.stash_bytes() + 4u * cap);
+        bulk_g2s(s_fo, blob + d.off_fanoff(), d.fanoff_bytes(), &bar);
+        if (d.fanv_bytes()) bulk_g2s(s_fv, blob + d.off_fanv(), d.fanv_bytes(), &bar);
+        if (d.own_bytes(ELEM_V)) bulk_g2s(s_own, blob + d.off_own(ELEM_V), d.own_bytes(ELEM_V), &bar);
+        if (d.stash_bytes()) bulk_g2s(s_stash, blob + d.off_stash(), d.stash_bytes(), &bar);
+        if (cap) bulk_g2s(s_in, in + d.slot_base[ELEM_V], 4u * cap, &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    for (uint32_t i = nov + threadIdx.x; i < nv; i += BT) {
+        const uint32_t o = s_own[i - nov];
+        s_in[i]          = ldg_stream(in + s_stash[o >> 16].slot_base[ELEM_V] + (o & 0xFFFFu));
+    }
+    __syncthreads();
+    for (uint32_t v = threadIdx.x; v < nov; v += BT) {
+        const uint32_t b = s_fo[v] & FAN_OFF_MASK, e = s_fo[v + 1] & FAN_OFF_MASK;
+        float          a = 0.f;
+        for (uint32_t i = b; i < e; ++i)
+            a += s_in[s_fv[i]];
+        out[d.slot_base[ELEM_V] + v] = a;
+    }
+}
+
 // --------------------------------------------------------------------------
 // boundary vertices: an edge with one incident face marks its two vertices
 // --------------------------------------------------------------------------
@@ -510,6 +680,13 @@ int pick_kmax(uint32_t nnz)
         kern<<<mv.num_patches, BT, smem, stream>>>(__VA_ARGS__);                         \
     } while (0)
 
+// shared memory of the sections every fan kernel stages (offsets, neighbours, owner table, stash)
+static uint32_t fan_smem(const KernelLimits& lim)
+{
+    return r16(2u * (lim.max_owned[ELEM_V] + 1) + 16) + r16(2u * lim.max_fan_total + 16) +
+           r16(4u * lim.max_not_owned[ELEM_V]) + 16u * lim.max_stash;
+}
+
 static uint32_t max_nnz(const KernelLimits& lim)
 {
     return std::max(2u * lim.max_n[ELEM_E], 3u * lim.max_n[ELEM_F]);
@@ -540,6 +717,13 @@ cudaError_t launch_query_consume(int op, const MeshView& mv, const KernelLimits&
     const int km = pick_kmax(max_nnz(lim));
     if (!km) RXM_FAIL("patch too large for the query kernels (nnz > 24*256)");
     if (in.nattr != 1 || out.nattr != 1) RXM_FAIL("query_consume needs single-component fp32 attributes");
+    if (op == OP_VV && mv.fans) {
+        const uint32_t smem = fan_smem(lim) + r16(4u * (std::max(lim.max_n[ELEM_V], lim.max_owned[ELEM_V] + 4)));
+        if (set_smem(k_vv_consume_fan, smem) != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
+        k_vv_consume_fan<<<mv.num_patches, BT, smem, stream>>>(mv, in.data, out.data);
+        ++g_launches;
+        return cudaGetLastError();
+    }
     if (op == OP_FF && lim.max_face_adjacent_faces > 6) RXM_FAIL("FF: more than 6 adjacent faces per face");
     uint32_t    smem = 0;
     cudaError_t e    = cudaSuccess;
@@ -566,6 +750,17 @@ cudaError_t launch_vertex_normals(const MeshView& mv, const KernelLimits& lim, c
                                   int unit, cudaStream_t stream, const char** err)
 {
     const uint32_t capv = lim.max_owned[ELEM_V] + 4;
+    if (mv.fans) {
+        const uint32_t smem = fan_smem(lim) + r16(12u * capv) + 16u * lim.max_n[ELEM_V];
+        cudaError_t e = unit ? set_smem(k_vertex_normals_fan<1>, smem) : set_smem(k_vertex_normals_fan<0>, smem);
+        if (e != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
+        if (unit)
+            k_vertex_normals_fan<1><<<mv.num_patches, BT, smem, stream>>>(mv, x, n);
+        else
+            k_vertex_normals_fan<0><<<mv.num_patches, BT, smem, stream>>>(mv, x, n);
+        ++g_launches;
+        return cudaGetLastError();
+    }
     if (mv.packed) {
         const uint32_t smem = r16(6u * lim.max_n[ELEM_F]) + r16(2u * (lim.max_owned[ELEM_V] + 1) + 16) +
                               r16(4u * lim.max_not_owned[ELEM_V]) + 16u * lim.max_stash + r16(12u * capv) +
@@ -594,9 +789,16 @@ cudaError_t launch_vertex_normals(const MeshView& mv, const KernelLimits& lim, c
 cudaError_t launch_laplacian_step(const MeshView& mv, const KernelLimits& lim, const float* x, float* xo, double lr,
                                   cudaStream_t stream, const char** err)
 {
+    const uint32_t capv = lim.max_owned[ELEM_V] + 4;
+    if (mv.fans) {
+        const uint32_t smem = fan_smem(lim) + r16(12u * capv) + 16u * lim.max_n[ELEM_V];
+        if (set_smem(k_laplacian_fan, smem) != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
+        k_laplacian_fan<<<mv.num_patches, BT, smem, stream>>>(mv, x, xo, lr);
+        ++g_launches;
+        return cudaGetLastError();
+    }
     const int km = pick_kmax(2u * lim.max_n[ELEM_E]);
     if (!km) RXM_FAIL("patch too large for the query kernels (nnz > 24*256)");
-    const uint32_t capv = lim.max_owned[ELEM_V] + 4;
     const uint32_t extra = r16(12u * std::max(lim.max_n[ELEM_V], capv)) + r16(12u * capv);
     uint32_t       smem;
     cudaError_t    e;

@@ -13,6 +13,7 @@ struct KernelLimits
     uint32_t max_not_owned[3];
     uint32_t max_stash;
     uint32_t max_face_adjacent_faces;
+    uint32_t max_fan_total;
 };
 
 // Every launcher returns cudaSuccess or the launch error; `err` (may be null)

