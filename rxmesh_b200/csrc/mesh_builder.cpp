@@ -585,11 +585,11 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
         }
         D.n_stash    = (uint16_t)tmp[p].stash.size();
         D.flags      = M.fans ? FLAG_FANS : 0;
-        D.fan_total  = M.fans ? (uint16_t)fan_v[p].size() : 0;
+        D.fan_total  = M.fans ? (uint32_t)fan_v[p].size() : 0;
         M.max_fan_total = std::max<uint32_t>(M.max_fan_total, D.fan_total);
         M.max_stash  = std::max<uint32_t>(M.max_stash, D.n_stash);
         D.topo_off   = topo_total;
-        D.topo_bytes = D.off_stash() + D.stash_bytes();
+        D.compute_layout();
         topo_total += D.topo_bytes;
     }
     M.packed = !opt.force_wide && M.max_valence < PK_MAX_VRANK && M.max_edge_incident_faces <= PK_MAX_ERANK &&

@@ -5,8 +5,9 @@
 // lp_hashtable.h:46-290, context.h:15-441) for the STATIC path.
 //
 // Design (see DESIGN.md "Data layout in HBM"):
-//  * one 64-byte PatchDesc per patch in a dense array (one 16-byte-aligned read
-//    gives a block everything it needs to issue its TMA bulk copies);
+//  * one 128-byte PatchDesc per patch in a dense array: counts, slot bases and the
+//    PRECOMPUTED byte offset of every section, so a block issues its TMA bulk
+//    copies without any layout arithmetic;
 //  * one contiguous, 16-byte-aligned "topology blob" per patch holding, in this
 //    order, EV (2 u16 / edge), FE (3 u16 / face, bit0 = direction, as the
 //    reference rxmesh.cpp:941-983), FV (3 u16 / face, derived = FE o EV, stored so
@@ -122,43 +123,68 @@ struct alignas(16) PatchDesc
     uint32_t patch_id;      // global patch id (differs from the local index on a sharded mesh)
     uint16_t n[3];          // #V, #E, #F in the patch, ribbon included
     uint16_t n_owned[3];    // #owned V, E, F (local ids [0, n_owned) are owned)
-    uint32_t slot_base[3];  // attribute slot base for V, E, F (multiple of 4)
-    uint32_t lin_base[3];   // gap-free linear-id prefix (reference Context::linear_id, context.h:275-290)
     uint16_t n_stash;       // neighbour patches referenced by the owner tables
     uint16_t flags;         // bit 0: packed (rank-annotated) format, bit 1: one-ring fans present
-    uint16_t fan_total;     // entries of the fan neighbour array
-    uint16_t pad1;
+    uint32_t slot_base[3];  // attribute slot base for V, E, F (multiple of 4)
+    uint32_t fan_total;     // entries of the fan neighbour array
+    uint32_t lin_base[3];   // gap-free linear-id prefix (reference Context::linear_id, context.h:275-290)
+    uint32_t pad0;
+    // ---- section byte offsets inside the blob (all multiples of 16), precomputed by the builder so a
+    //      kernel spends no instructions on layout arithmetic. Order: EV, FE, FV, voff_e, voff_f, eoff_f,
+    //      fan_off, fan_v, owner V/E/F, stash ----
+    uint32_t o_fe, o_fv, o_voff_e, o_voff_f, o_eoff_f, o_fanoff, o_fanv, o_own[3], o_stash;
+    uint32_t pad1[5];
 
-    // ---- section byte offsets inside the blob (all multiples of 16) ----
-    RXM_HD uint32_t ev_bytes() const { return round_up(4u * n[ELEM_E], 16); }
-    RXM_HD uint32_t fe_bytes() const { return round_up(6u * n[ELEM_F], 16); }
-    RXM_HD uint32_t own_bytes(uint32_t t) const { return round_up(4u * (n[t] - n_owned[t]), 16); }
+    RXM_HD uint32_t ev_bytes() const { return o_fe; }
+    RXM_HD uint32_t fe_bytes() const { return o_fv - o_fe; }
+    RXM_HD uint32_t own_bytes(uint32_t t) const { return (t == 2 ? o_stash : o_own[t + 1]) - o_own[t]; }
     RXM_HD uint32_t off_ev() const { return 0; }
-    RXM_HD uint32_t off_fe() const { return ev_bytes(); }
-    RXM_HD uint32_t off_fv() const { return off_fe() + fe_bytes(); }
+    RXM_HD uint32_t off_fe() const { return o_fe; }
+    RXM_HD uint32_t off_fv() const { return o_fv; }
     // list-offset arrays (u16, one entry per local column + 1): VE/VV, VF, EF
-    RXM_HD uint32_t voff_bytes() const { return round_up(2u * (n[ELEM_V] + 1u), 16); }
-    RXM_HD uint32_t eoff_bytes() const { return round_up(2u * (n[ELEM_E] + 1u), 16); }
-    RXM_HD uint32_t off_voff_e() const { return off_fv() + fe_bytes(); }
-    RXM_HD uint32_t off_voff_f() const { return off_voff_e() + voff_bytes(); }
-    RXM_HD uint32_t off_eoff_f() const { return off_voff_f() + voff_bytes(); }
+    RXM_HD uint32_t voff_bytes() const { return o_voff_f - o_voff_e; }
+    RXM_HD uint32_t eoff_bytes() const { return o_fanoff - o_eoff_f; }
+    RXM_HD uint32_t off_voff_e() const { return o_voff_e; }
+    RXM_HD uint32_t off_voff_f() const { return o_voff_f; }
+    RXM_HD uint32_t off_eoff_f() const { return o_eoff_f; }
     // one-ring fans of the owned vertices: fan_off[nov+1] (bit 15 = closed fan), fan_v[fan_total]
-    RXM_HD uint32_t fanoff_bytes() const { return (flags & 2) ? round_up(2u * (n_owned[ELEM_V] + 1u), 16) : 0u; }
-    RXM_HD uint32_t fanv_bytes() const { return (flags & 2) ? round_up(2u * fan_total, 16) : 0u; }
-    RXM_HD uint32_t off_fanoff() const { return off_eoff_f() + eoff_bytes(); }
-    RXM_HD uint32_t off_fanv() const { return off_fanoff() + fanoff_bytes(); }
-    RXM_HD uint32_t off_own(uint32_t t) const
-    {
-        uint32_t o = off_fanv() + fanv_bytes();
-        for (uint32_t i = 0; i < t; ++i)
-            o += own_bytes(i);
-        return o;
-    }
-    RXM_HD uint32_t off_stash() const { return off_own(3); }
+    RXM_HD uint32_t fanoff_bytes() const { return o_fanv - o_fanoff; }
+    RXM_HD uint32_t fanv_bytes() const { return o_own[0] - o_fanv; }
+    RXM_HD uint32_t off_fanoff() const { return o_fanoff; }
+    RXM_HD uint32_t off_fanv() const { return o_fanv; }
+    RXM_HD uint32_t off_own(uint32_t t) const { return o_own[t]; }
+    RXM_HD uint32_t off_stash() const { return o_stash; }
     RXM_HD uint32_t stash_bytes() const { return 16u * n_stash; }
-    RXM_HD uint32_t slot_cap(uint32_t t) const { return round_up(n_owned[t], 4); }
+    RXM_HD uint32_t slot_cap(uint32_t t) const { return (n_owned[t] + 3u) & ~3u; }
+
+    // builder: lay the sections out from the counts / flags already stored in this record
+    inline void compute_layout()
+    {
+        uint32_t o = 0;
+        o += round_up(4u * n[ELEM_E], 16);
+        o_fe = o;
+        o += round_up(6u * n[ELEM_F], 16);
+        o_fv = o;
+        o += round_up(6u * n[ELEM_F], 16);
+        o_voff_e = o;
+        o += round_up(2u * (n[ELEM_V] + 1u), 16);
+        o_voff_f = o;
+        o += round_up(2u * (n[ELEM_V] + 1u), 16);
+        o_eoff_f = o;
+        o += round_up(2u * (n[ELEM_E] + 1u), 16);
+        o_fanoff = o;
+        o += (flags & 2) ? round_up(2u * (n_owned[ELEM_V] + 1u), 16) : 0u;
+        o_fanv = o;
+        o += (flags & 2) ? round_up(2u * fan_total, 16) : 0u;
+        for (int t = 0; t < 3; ++t) {
+            o_own[t] = o;
+            o += round_up(4u * (uint32_t)(n[t] - n_owned[t]), 16);
+        }
+        o_stash    = o;
+        topo_bytes = o + 16u * n_stash;
+    }
 };
-static_assert(sizeof(PatchDesc) == 64, "PatchDesc must be 64 bytes");
+static_assert(sizeof(PatchDesc) == 128, "PatchDesc must be 128 bytes");
 
 // By-value kernel argument: the static-path equivalent of the reference Context.
 struct MeshView
