@@ -28,7 +28,12 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 ALG_BYTES_PER_FACE = {"VV": 16.0, "VF": 18.0, "VN": 24.0}  # SURVEY.md 8(d), BASELINE.md 2
-TILE = 16  # 16 x 16 quads = 512 owned faces per patch (the reference's default patch_size)
+# 32 x 16 quads = 1024 owned faces per patch: the B200-tuned patch size (profiles/r01_tile_sweep.txt;
+# the reference's default of 512 = 16 x 16 runs the same kernels at 44-53 % instead of 62-85 % of roofline)
+TILE = 32
+TILE_I = 16
+if os.environ.get("RXM_TILE"):  # experiment knob: "<columns>x<rows>" quads per patch
+    TILE, TILE_I = (int(v) for v in os.environ["RXM_TILE"].split("x"))
 
 
 def grid_side(faces):
@@ -190,7 +195,7 @@ METRIC = "faces/s through one VV-query + VF-query + vertex-normal pass (100M-fac
 def config_dict(args, n, faces, mesh):
     c = {"workload": "VV + VF query (consume) + vertex normals on a %d x %d procedurally generated grid "
                      "(create_plane semantics + height field), %d faces per GPU" % (n, n, faces),
-         "faces_per_gpu": int(faces), "patch_size": 2 * TILE * TILE, "patcher": "analytic %dx%d-quad tiles" % (TILE, TILE),
+         "faces_per_gpu": int(faces), "patch_size": 2 * TILE * TILE_I, "patcher": "analytic %dx%d-quad tiles" % (TILE, TILE_I),
          "l2": "inputs larger than L2 (topology + attributes stream > 2 GB per step; no explicit flush)",
          "parallelism": "patches sharded per GPU" if args.gpus > 1 else "1 GPU"}
     if mesh is not None:
@@ -215,8 +220,8 @@ def run_ours(args, rank, world, local_rank):
     ncores = os.cpu_count() or 8
     t0 = time.perf_counter()
     V, F = meshio.grid(n, n)
-    fp = meshio.grid_face_tiles(n, n, TILE)
-    mesh = rx.RXMeshStatic(F, face_patch=fp, patch_size=2 * TILE * TILE, num_threads=max(1, ncores // world))
+    fp = meshio.grid_face_tiles(n, n, TILE, TILE_I)
+    mesh = rx.RXMeshStatic(F, face_patch=fp, patch_size=2 * TILE * TILE_I, num_threads=max(1, ncores // world))
     t_build = time.perf_counter() - t0
     nF, nV = mesh.get_num_faces(), mesh.get_num_vertices()
     del fp

@@ -13,9 +13,11 @@
 // slice arrive by TMA bulk copies under one mbarrier phase.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "rxm_kernels.h"
+#include "rxm_persistent.cuh"
 #include "rxm_query.cuh"
 
 namespace rxm {
@@ -546,6 +548,214 @@ __global__ void __launch_bounds__(BT) k_vv_consume_fan(MeshView mv, const float*
 }
 
 // --------------------------------------------------------------------------
+// persistent pipelined workers (rxm_persistent.cuh)
+// --------------------------------------------------------------------------
+struct FanLayout
+{
+    uint32_t stage_bytes, o_fo, o_fv, o_own, o_stash, o_xp, o_x4;
+};
+
+// MODE 0: Max-1999 vertex normals, 1: unit-face-normal sum, 2: Laplacian step
+template <int MODE>
+struct FanWorker
+{
+    struct Args
+    {
+        const float* x;
+        float*       out;
+        double       lr;
+    };
+    using Layout = FanLayout;
+
+    static __device__ __forceinline__ void issue(const PatchDesc& d, const uint8_t* blob, const Args& a, const Layout& L,
+                                                 uint8_t* st, uint64_t* bar)
+    {
+        const uint32_t cap = d.slot_cap(ELEM_V);
+        mbar_arrive_expect_tx(bar, d.fanoff_bytes() + d.fanv_bytes() + d.own_bytes(ELEM_V) + d.stash_bytes() + 12u * cap);
+        bulk_g2s(st + L.o_fo, blob + d.off_fanoff(), d.fanoff_bytes(), bar);
+        if (d.fanv_bytes()) bulk_g2s(st + L.o_fv, blob + d.off_fanv(), d.fanv_bytes(), bar);
+        if (d.own_bytes(ELEM_V)) bulk_g2s(st + L.o_own, blob + d.off_own(ELEM_V), d.own_bytes(ELEM_V), bar);
+        if (d.stash_bytes()) bulk_g2s(st + L.o_stash, blob + d.off_stash(), d.stash_bytes(), bar);
+        if (cap) bulk_g2s(st + L.o_xp, a.x + 3ull * d.slot_base[ELEM_V], 12u * cap, bar);
+    }
+
+    static __device__ __forceinline__ void pre(const PatchDesc& d, const Args& a, const Layout& L, uint8_t* st)
+    {
+        const uint32_t    nv = d.n[ELEM_V], nov = d.n_owned[ELEM_V];
+        const uint32_t*   own   = reinterpret_cast<const uint32_t*>(st + L.o_own);
+        const StashEntry* stash = reinterpret_cast<const StashEntry*>(st + L.o_stash);
+        const float*      xp    = reinterpret_cast<const float*>(st + L.o_xp);
+        float4*           x4    = reinterpret_cast<float4*>(st + L.o_x4);
+        for (uint32_t i = threadIdx.x; i < nv; i += BT) {
+            if (i < nov) {
+                x4[i] = make_float4(xp[3 * i], xp[3 * i + 1], xp[3 * i + 2], 0.f);
+            } else {  // ribbon vertex: asynchronous gather from the owner patch's slots
+                const uint32_t o = own[i - nov];
+                const float*   g = a.x + 3ull * ((uint64_t)stash[o >> 16].slot_base[ELEM_V] + (o & 0xFFFFu));
+                float*         t = reinterpret_cast<float*>(&x4[i]);
+                cp_async_4(t, g), cp_async_4(t + 1, g + 1), cp_async_4(t + 2, g + 2);
+            }
+        }
+    }
+
+    static __device__ __forceinline__ void compute(const PatchDesc& d, const Args& a, const Layout& L, uint8_t* st)
+    {
+        const uint32_t  nov = d.n_owned[ELEM_V];
+        const uint16_t* fo  = reinterpret_cast<const uint16_t*>(st + L.o_fo);
+        const uint16_t* fv  = reinterpret_cast<const uint16_t*>(st + L.o_fv);
+        const float4*   x4  = reinterpret_cast<const float4*>(st + L.o_x4);
+        float*          out = a.out + 3ull * d.slot_base[ELEM_V];
+        for (uint32_t v = threadIdx.x; v < nov; v += BT) {
+            const uint32_t o = fo[v], b = o & FAN_OFF_MASK, e = fo[v + 1] & FAN_OFF_MASK;
+            const float4   p = x4[v];
+            float          rx, ry, rz;
+            if (MODE == 2) {
+                float gx = 0.f, gy = 0.f, gz = 0.f;
+                for (uint32_t i = b; i < e; ++i) {
+                    const float4 q = x4[fv[i]];
+                    gx += 2.f * (p.x - q.x), gy += 2.f * (p.y - q.y), gz += 2.f * (p.z - q.z);
+                }
+                rx = (float)__dsub_rn((double)p.x, __dmul_rn(a.lr, (double)gx));
+                ry = (float)__dsub_rn((double)p.y, __dmul_rn(a.lr, (double)gy));
+                rz = (float)__dsub_rn((double)p.z, __dmul_rn(a.lr, (double)gz));
+            } else {
+                float       sx = 0.f, sy = 0.f, sz = 0.f;
+                float4      q  = x4[fv[b]];
+                const float d0x = q.x - p.x, d0y = q.y - p.y, d0z = q.z - p.z;
+                const float l0 = d0x * d0x + d0y * d0y + d0z * d0z;
+                float       px = d0x, py = d0y, pz = d0z, pl = l0;
+                auto face = [&](float cx, float cy, float cz, float cl) {
+                    const float nx = py * cz - pz * cy, ny = pz * cx - px * cz, nz = px * cy - py * cx;
+                    const float w  = MODE == 1 ? rsqrtf(nx * nx + ny * ny + nz * nz) : fast_rcp(pl + cl);
+                    sx += nx * w, sy += ny * w, sz += nz * w;
+                };
+#pragma unroll 2
+                for (uint32_t i = b + 1; i < e; ++i) {
+                    q = x4[fv[i]];
+                    const float cx = q.x - p.x, cy = q.y - p.y, cz = q.z - p.z;
+                    const float cl = cx * cx + cy * cy + cz * cz;
+                    face(cx, cy, cz, cl);
+                    px = cx, py = cy, pz = cz, pl = cl;
+                }
+                if (o & FAN_CLOSED) face(d0x, d0y, d0z, l0);
+                rx = sx, ry = sy, rz = sz;
+            }
+            out[3 * v] = rx, out[3 * v + 1] = ry, out[3 * v + 2] = rz;
+        }
+    }
+};
+
+struct ConsumeLayout
+{
+    uint32_t stage_bytes, o_a, o_b, o_own, o_stash, o_in, o_val;
+};
+
+// out(v) = sum of in(u) over the one-ring fan
+struct VVFanConsumeWorker
+{
+    struct Args
+    {
+        const float* in;
+        float*       out;
+    };
+    using Layout = ConsumeLayout;
+    static __device__ __forceinline__ void issue(const PatchDesc& d, const uint8_t* blob, const Args& a, const Layout& L,
+                                                 uint8_t* st, uint64_t* bar)
+    {
+        const uint32_t cap = d.slot_cap(ELEM_V);
+        mbar_arrive_expect_tx(bar, d.fanoff_bytes() + d.fanv_bytes() + d.own_bytes(ELEM_V) + d.stash_bytes() + 4u * cap);
+        bulk_g2s(st + L.o_a, blob + d.off_fanoff(), d.fanoff_bytes(), bar);
+        if (d.fanv_bytes()) bulk_g2s(st + L.o_b, blob + d.off_fanv(), d.fanv_bytes(), bar);
+        if (d.own_bytes(ELEM_V)) bulk_g2s(st + L.o_own, blob + d.off_own(ELEM_V), d.own_bytes(ELEM_V), bar);
+        if (d.stash_bytes()) bulk_g2s(st + L.o_stash, blob + d.off_stash(), d.stash_bytes(), bar);
+        if (cap) bulk_g2s(st + L.o_in, a.in + d.slot_base[ELEM_V], 4u * cap, bar);
+    }
+    static __device__ __forceinline__ void pre(const PatchDesc& d, const Args& a, const Layout& L, uint8_t* st)
+    {
+        const uint32_t    nv = d.n[ELEM_V], nov = d.n_owned[ELEM_V];
+        const uint32_t*   own   = reinterpret_cast<const uint32_t*>(st + L.o_own);
+        const StashEntry* stash = reinterpret_cast<const StashEntry*>(st + L.o_stash);
+        float*            sin   = reinterpret_cast<float*>(st + L.o_in);
+        for (uint32_t i = nov + threadIdx.x; i < nv; i += BT) {
+            const uint32_t o = own[i - nov];
+            cp_async_4(&sin[i], a.in + stash[o >> 16].slot_base[ELEM_V] + (o & 0xFFFFu));
+        }
+    }
+    static __device__ __forceinline__ void compute(const PatchDesc& d, const Args& a, const Layout& L, uint8_t* st)
+    {
+        const uint32_t  nov = d.n_owned[ELEM_V];
+        const uint16_t* fo  = reinterpret_cast<const uint16_t*>(st + L.o_a);
+        const uint16_t* fv  = reinterpret_cast<const uint16_t*>(st + L.o_b);
+        const float*    sin = reinterpret_cast<const float*>(st + L.o_in);
+        for (uint32_t v = threadIdx.x; v < nov; v += BT) {
+            const uint32_t b = fo[v] & FAN_OFF_MASK, e = fo[v + 1] & FAN_OFF_MASK;
+            float          acc = 0.f;
+            for (uint32_t i = b; i < e; ++i)
+                acc += sin[fv[i]];
+            a.out[d.slot_base[ELEM_V] + v] = acc;
+        }
+    }
+};
+
+// out(v) = sum of in(f) over VF(v); VF built in shared memory by the rank scatter (packed format)
+struct VFConsumeWorker
+{
+    struct Args
+    {
+        const float* in;
+        float*       out;
+    };
+    using Layout = ConsumeLayout;
+    static __device__ __forceinline__ uint32_t loff_bytes(const PatchDesc& d) { return round_up(2u * (d.n_owned[ELEM_V] + 1u), 16); }
+    static __device__ __forceinline__ void issue(const PatchDesc& d, const uint8_t* blob, const Args& a, const Layout& L,
+                                                 uint8_t* st, uint64_t* bar)
+    {
+        const uint32_t cap = d.slot_cap(ELEM_F);
+        mbar_arrive_expect_tx(bar, d.fe_bytes() + loff_bytes(d) + d.own_bytes(ELEM_F) + d.stash_bytes() + 4u * cap);
+        if (d.fe_bytes()) bulk_g2s(st + L.o_a, blob + d.off_fv(), d.fe_bytes(), bar);
+        bulk_g2s(st + L.o_b, blob + d.off_voff_f(), loff_bytes(d), bar);
+        if (d.own_bytes(ELEM_F)) bulk_g2s(st + L.o_own, blob + d.off_own(ELEM_F), d.own_bytes(ELEM_F), bar);
+        if (d.stash_bytes()) bulk_g2s(st + L.o_stash, blob + d.off_stash(), d.stash_bytes(), bar);
+        if (cap) bulk_g2s(st + L.o_in, a.in + d.slot_base[ELEM_F], 4u * cap, bar);
+    }
+    static __device__ __forceinline__ void pre(const PatchDesc& d, const Args& a, const Layout& L, uint8_t* st)
+    {
+        const uint32_t    nf = d.n[ELEM_F], nof = d.n_owned[ELEM_F], nov = d.n_owned[ELEM_V];
+        const uint16_t*   fv    = reinterpret_cast<const uint16_t*>(st + L.o_a);
+        const uint16_t*   loff  = reinterpret_cast<const uint16_t*>(st + L.o_b);
+        const uint32_t*   own   = reinterpret_cast<const uint32_t*>(st + L.o_own);
+        const StashEntry* stash = reinterpret_cast<const StashEntry*>(st + L.o_stash);
+        float*            sin   = reinterpret_cast<float*>(st + L.o_in);
+        uint16_t*         val   = reinterpret_cast<uint16_t*>(st + L.o_val);
+        for (uint32_t i = nof + threadIdx.x; i < nf; i += BT) {
+            const uint32_t o = own[i - nof];
+            cp_async_4(&sin[i], a.in + stash[o >> 16].slot_base[ELEM_F] + (o & 0xFFFFu));
+        }
+        for (uint32_t f = threadIdx.x; f < nf; f += BT) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const uint32_t e = fv[3 * f + j], c = e & PK_ID_MASK;
+                if (c < nov) val[loff[c] + (e >> PK_ID_BITS)] = (uint16_t)f;
+            }
+        }
+    }
+    static __device__ __forceinline__ void compute(const PatchDesc& d, const Args& a, const Layout& L, uint8_t* st)
+    {
+        const uint32_t  nov  = d.n_owned[ELEM_V];
+        const uint16_t* loff = reinterpret_cast<const uint16_t*>(st + L.o_b);
+        const uint16_t* val  = reinterpret_cast<const uint16_t*>(st + L.o_val);
+        const float*    sin  = reinterpret_cast<const float*>(st + L.o_in);
+        for (uint32_t v = threadIdx.x; v < nov; v += BT) {
+            const uint32_t b = loff[v], e = loff[v + 1];
+            float          acc = 0.f;
+            for (uint32_t i = b; i < e; ++i)
+                acc += sin[val[i]];
+            a.out[d.slot_base[ELEM_V] + v] = acc;
+        }
+    }
+};
+
+// --------------------------------------------------------------------------
 // boundary vertices: an edge with one incident face marks its two vertices
 // --------------------------------------------------------------------------
 template <int KMAX, bool PACKED>
@@ -689,6 +899,63 @@ int pick_kmax(uint32_t nnz)
         kern<<<mv.num_patches, BT, smem, stream>>>(__VA_ARGS__);                         \
     } while (0)
 
+
+// The persistent, software-pipelined variants (rxm_persistent.cuh) are opt-in: measured on the
+// 100 M-face grid they win only for the lightest kernel at 512-face patches (VV consume 0.46 ->
+// 0.38 ms) and lose once patches hold 1024 faces, where block-per-patch kernels already run at
+// 62-85 % of the HBM roofline (profiles/r01_tile_sweep.txt).
+static bool use_persistent()
+{
+    static const bool on = getenv("RXM_PERSIST") != nullptr;
+    return on;
+}
+
+static int num_sms()
+{
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// launch a persistent pipelined kernel: grid = #SMs x resident CTAs (<= #patches)
+template <class W>
+static cudaError_t launch_persistent(const MeshView& mv, const typename W::Args& a, const typename W::Layout& L,
+                                     cudaStream_t stream)
+{
+    auto           kern = dev::k_persistent<W, BT>;
+    const uint32_t smem = dev::PIPE_STAGES * L.stage_bytes;
+    cudaError_t    e    = set_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e          = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BT, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidValue;
+    const uint32_t grid = std::min<uint32_t>(mv.num_patches, (uint32_t)(num_sms() * per_sm));
+    kern<<<grid, BT, smem, stream>>>(mv, a, L);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+static FanLayout fan_layout(const KernelLimits& lim)
+{
+    FanLayout      L;
+    const uint32_t capv = lim.max_owned[ELEM_V] + 4;
+    uint32_t       o    = 0;
+    L.o_fo = o, o += r16(2u * (lim.max_owned[ELEM_V] + 1) + 16);
+    L.o_fv = o, o += r16(2u * lim.max_fan_total + 16);
+    L.o_own = o, o += r16(4u * lim.max_not_owned[ELEM_V] + 16);
+    L.o_stash = o, o += 16u * lim.max_stash + 16;
+    L.o_xp = o, o += r16(12u * capv);
+    L.o_x4 = o, o += 16u * lim.max_n[ELEM_V];
+    L.stage_bytes = (o + 127u) & ~127u;
+    return L;
+}
+
 // shared memory of the sections every fan kernel stages (offsets, neighbours, owner table, stash)
 static uint32_t fan_smem(const KernelLimits& lim)
 {
@@ -726,6 +993,34 @@ cudaError_t launch_query_consume(int op, const MeshView& mv, const KernelLimits&
     const int km = pick_kmax(max_nnz(lim));
     if (!km) RXM_FAIL("patch too large for the query kernels (nnz > 24*256)");
     if (in.nattr != 1 || out.nattr != 1) RXM_FAIL("query_consume needs single-component fp32 attributes");
+    if (op == OP_VV && mv.fans && use_persistent()) {
+        ConsumeLayout L;
+        uint32_t      o = 0;
+        L.o_a = o, o += r16(2u * (lim.max_owned[ELEM_V] + 1) + 16);
+        L.o_b = o, o += r16(2u * lim.max_fan_total + 16);
+        L.o_own = o, o += r16(4u * lim.max_not_owned[ELEM_V] + 16);
+        L.o_stash = o, o += 16u * lim.max_stash + 16;
+        L.o_in = o, o += r16(4u * (std::max(lim.max_n[ELEM_V], lim.max_owned[ELEM_V] + 4)));
+        L.o_val = o;
+        L.stage_bytes = (o + 127u) & ~127u;
+        cudaError_t e = launch_persistent<VVFanConsumeWorker>(mv, VVFanConsumeWorker::Args{in.data, out.data}, L, stream);
+        if (e == cudaErrorInvalidValue) RXM_FAIL("patch needs more shared memory than 227 KB");
+        return e;
+    }
+    if (op == OP_VF && mv.packed && use_persistent()) {
+        ConsumeLayout L;
+        uint32_t      o = 0;
+        L.o_a = o, o += r16(6u * lim.max_n[ELEM_F] + 16);
+        L.o_b = o, o += r16(2u * (lim.max_owned[ELEM_V] + 1) + 16);
+        L.o_own = o, o += r16(4u * lim.max_not_owned[ELEM_F] + 16);
+        L.o_stash = o, o += 16u * lim.max_stash + 16;
+        L.o_in = o, o += r16(4u * (std::max(lim.max_n[ELEM_F], lim.max_owned[ELEM_F] + 4)));
+        L.o_val = o, o += r16(6u * lim.max_n[ELEM_F] + 16);
+        L.stage_bytes = (o + 127u) & ~127u;
+        cudaError_t e = launch_persistent<VFConsumeWorker>(mv, VFConsumeWorker::Args{in.data, out.data}, L, stream);
+        if (e == cudaErrorInvalidValue) RXM_FAIL("patch needs more shared memory than 227 KB");
+        return e;
+    }
     if (op == OP_VV && mv.fans) {
         const uint32_t smem = fan_smem(lim) + r16(4u * (std::max(lim.max_n[ELEM_V], lim.max_owned[ELEM_V] + 4)));
         if (set_smem(k_vv_consume_fan, smem) != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
@@ -759,6 +1054,16 @@ cudaError_t launch_vertex_normals(const MeshView& mv, const KernelLimits& lim, c
                                   int unit, cudaStream_t stream, const char** err)
 {
     const uint32_t capv = lim.max_owned[ELEM_V] + 4;
+    if (mv.fans && use_persistent()) {
+        const FanLayout L = fan_layout(lim);
+        cudaError_t     e;
+        if (unit)
+            e = launch_persistent<FanWorker<1>>(mv, FanWorker<1>::Args{x, n, 0.0}, L, stream);
+        else
+            e = launch_persistent<FanWorker<0>>(mv, FanWorker<0>::Args{x, n, 0.0}, L, stream);
+        if (e == cudaErrorInvalidValue) RXM_FAIL("patch needs more shared memory than 227 KB");
+        return e;
+    }
     if (mv.fans) {
         const uint32_t smem = fan_smem(lim) + r16(12u * capv) + 16u * lim.max_n[ELEM_V];
         cudaError_t e = unit ? set_smem(k_vertex_normals_fan<1>, smem) : set_smem(k_vertex_normals_fan<0>, smem);
@@ -799,6 +1104,11 @@ cudaError_t launch_laplacian_step(const MeshView& mv, const KernelLimits& lim, c
                                   cudaStream_t stream, const char** err)
 {
     const uint32_t capv = lim.max_owned[ELEM_V] + 4;
+    if (mv.fans && use_persistent()) {
+        cudaError_t e = launch_persistent<FanWorker<2>>(mv, FanWorker<2>::Args{x, xo, lr}, fan_layout(lim), stream);
+        if (e == cudaErrorInvalidValue) RXM_FAIL("patch needs more shared memory than 227 KB");
+        return e;
+    }
     if (mv.fans) {
         const uint32_t smem = fan_smem(lim) + r16(12u * capv) + 16u * lim.max_n[ELEM_V];
         if (set_smem(k_laplacian_fan, smem) != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");

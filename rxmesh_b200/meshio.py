@@ -47,11 +47,12 @@ def grid(nx, ny, dx=1.0, height=True):
     return verts, faces.reshape(-1, 3)
 
 
-def grid_face_tiles(nx, ny, tile):
-    """Analytic patching of grid(): face -> patch id by tile x tile quad blocks
-    (2*tile*tile faces per full patch), the role of the reference's dead
+def grid_face_tiles(nx, ny, tile, tile_i=None):
+    """Analytic patching of grid(): face -> patch id by tile (columns) x tile_i (rows) quad blocks
+    (2*tile*tile_i faces per full patch), the role of the reference's dead
     Patcher::grid (patcher/patcher.cu:181-224)."""
-    qi = np.arange(ny - 1, dtype=np.uint32)[:, None] // np.uint32(tile)
+    tile_i = tile if tile_i is None else tile_i
+    qi = np.arange(ny - 1, dtype=np.uint32)[:, None] // np.uint32(tile_i)
     qj = np.arange(nx - 1, dtype=np.uint32)[None, :] // np.uint32(tile)
     ntj = (nx - 1 + tile - 1) // tile
     pid = (qi * np.uint32(ntj) + qj).reshape(-1)
