@@ -165,6 +165,25 @@ int rxm_laplacian_smooth_host(rxm_mesh* m, const float* coords, float* out, doub
 /* in: [num output-type elements] fp32, out: [num source-type elements] fp32, global order */
 int rxm_query_consume_host(rxm_mesh* m, int op, const float* in, float* out, void* stream);
 
+/* ------------------------------------------------------------- multi-GPU (new) ---- */
+/* A rank's mesh = its own ("real") patches plus the ghost patches that own its ribbon elements. Kernels run
+ * on the real range only; ghost patches' attribute slots are filled by the halo exchange. */
+int rxm_mesh_set_active_patches(rxm_mesh* m, uint32_t first, uint32_t count);
+/* sorted attribute slots, owned by patches OUTSIDE [first, first+count), that the patches inside reference
+ * through their owner tables (= what a halo exchange must fill). *out is malloc'd: release with rxm_free. */
+int  rxm_mesh_halo_slots(const rxm_mesh* m, int elem, uint32_t first, uint32_t count, uint32_t** out, uint64_t* n);
+void rxm_free(void* p);
+/* pack / unpack rows of an AoS attribute through a device index list (device buffers) */
+int rxm_attr_gather_slots(rxm_attr* a, const uint32_t* dev_idx, uint64_t n, void* dev_out, void* stream);
+int rxm_attr_scatter_slots(rxm_attr* a, const uint32_t* dev_idx, uint64_t n, const void* dev_in, void* stream);
+/* direct NVLink P2P halo push: remote_data[remote_idx[i]] = a[local_idx[i]] with remote_data a peer-mapped
+ * pointer (rxm_ipc_open) to the neighbour rank's attribute storage */
+int rxm_attr_push_slots(rxm_attr* a, const uint32_t* dev_local_idx, void* remote_data, const uint32_t* dev_remote_idx,
+                        uint64_t n, void* stream);
+int rxm_ipc_export(void* dev_ptr, void* handle64);        /* cudaIpcGetMemHandle */
+int rxm_ipc_open(const void* handle64, void** dev_ptr);   /* cudaIpcOpenMemHandle */
+int rxm_ipc_close(void* dev_ptr);
+
 /* kernels launched by this library so far (bench.py "gpu_launches") */
 uint64_t rxm_launch_count(void);
 

@@ -64,6 +64,16 @@ SYMBOLS = {
     "rxm_laplacian_smooth_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                             C.c_uint32, C.c_void_p]),
     "rxm_query_consume_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rxm_mesh_set_active_patches": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "rxm_mesh_halo_slots": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(u32p),
+                                      C.POINTER(C.c_uint64)]),
+    "rxm_free": (None, [C.c_void_p]),
+    "rxm_attr_gather_slots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "rxm_attr_scatter_slots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "rxm_attr_push_slots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "rxm_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rxm_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "rxm_ipc_close": (C.c_int, [C.c_void_p]),
     "rxm_launch_count": (C.c_uint64, []),
 }
 

@@ -39,6 +39,7 @@ struct rxm_mesh
     uint8_t*     d_topo    = nullptr;
     uint32_t*    d_slot_base[3] = {nullptr, nullptr, nullptr};
     uint32_t*    d_s2g[3]       = {nullptr, nullptr, nullptr};
+    uint32_t     active_first = 0, active_count = 0;  // patches the kernels run on (a shard's real patches)
     MeshView     view{};
     KernelLimits lim{};
     // scratch for the host-buffer entry points and multi-iteration drivers
@@ -147,6 +148,10 @@ int rxm_mesh_to_device(rxm_mesh* m)
     m->view.desc        = m->d_desc;
     m->view.topo        = m->d_topo;
     m->view.num_patches = h.num_patches;
+    if (m->active_count) {
+        m->view.desc        = m->d_desc + m->active_first;
+        m->view.num_patches = m->active_count;
+    }
     m->view.packed      = h.packed ? 1u : 0u;
     m->view.fans        = h.fans ? 1u : 0u;
     for (int t = 0; t < 3; ++t) {
@@ -692,6 +697,114 @@ int rxm_query_consume_host(rxm_mesh* m, int op, const float* in, float* out, voi
     if ((rc = rxm_attr_upload_global(a, in, stream))) return rc;
     if ((rc = rxm_query_consume(m, op, a, b, stream))) return rc;
     return rxm_attr_download_global(b, out, stream);
+}
+
+// ------------------------------------------------------------------ multi-GPU support
+int rxm_mesh_set_active_patches(rxm_mesh* m, uint32_t first, uint32_t count)
+{
+    if (!m || (uint64_t)first + count > m->h.num_patches)
+        return fail(RXM_ERR_INVALID, "rxm_mesh_set_active_patches: range outside the mesh");
+    m->active_first = first;
+    m->active_count = count;
+    if (m->on_device) {
+        m->view.desc        = m->d_desc + first;
+        m->view.num_patches = count;
+    }
+    return RXM_OK;
+}
+
+int rxm_mesh_halo_slots(const rxm_mesh* m, int elem, uint32_t first, uint32_t count, uint32_t** out, uint64_t* n)
+{
+    if (!m || !out || !n || elem < 0 || elem > 2 || (uint64_t)first + count > m->h.num_patches)
+        return fail(RXM_ERR_INVALID, "rxm_mesh_halo_slots: bad argument");
+    const HostMesh&      h = m->h;
+    std::vector<uint8_t> mark(h.num_slots[elem], 0);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t p = first; p < (int64_t)first + count; ++p) {
+        const PatchDesc&  D   = h.desc[p];
+        const uint8_t*    B   = h.topo.data() + D.topo_off;
+        const uint32_t*   own = reinterpret_cast<const uint32_t*>(B + D.off_own(elem));
+        const StashEntry* st  = reinterpret_cast<const StashEntry*>(B + D.off_stash());
+        for (uint32_t i = 0; i < (uint32_t)(D.n[elem] - D.n_owned[elem]); ++i) {
+            const uint32_t q = st[own[i] >> 16].patch;
+            if (q < first || q >= first + count) mark[st[own[i] >> 16].slot_base[elem] + (own[i] & 0xFFFFu)] = 1;
+        }
+    }
+    uint64_t k = 0;
+    for (uint8_t b : mark)
+        k += b;
+    uint32_t* r = (uint32_t*)malloc(std::max<uint64_t>(k, 1) * sizeof(uint32_t));
+    if (!r) return fail(RXM_ERR_INVALID, "rxm_mesh_halo_slots: out of memory");
+    uint64_t j = 0;
+    for (uint32_t s = 0; s < h.num_slots[elem]; ++s)
+        if (mark[s]) r[j++] = s;
+    *out = r;
+    *n   = k;
+    return RXM_OK;
+}
+
+void rxm_free(void* p)
+{
+    free(p);
+}
+
+static int rows_check(rxm_attr* a, const char* who)
+{
+    if (!a || !a->d) return fail(RXM_ERR_INVALID, std::string(who) + ": attribute has no device storage");
+    if (a->layout != RXM_AOS && a->nattr != 1) return fail(RXM_ERR_INVALID, std::string(who) + ": AoS attributes only");
+    if ((a->elem_bytes * a->nattr) % 4) return fail(RXM_ERR_INVALID, std::string(who) + ": row size must be a multiple of 4 bytes");
+    return RXM_OK;
+}
+
+int rxm_attr_gather_slots(rxm_attr* a, const uint32_t* dev_idx, uint64_t n, void* dev_out, void* stream)
+{
+    int rc = rows_check(a, "rxm_attr_gather_slots");
+    if (rc) return rc;
+    cudaError_t e = launch_slot_rows(true, a->d, dev_idx, n, a->elem_bytes * a->nattr / 4, dev_out, (cudaStream_t)stream);
+    return e == cudaSuccess ? RXM_OK : fail(RXM_ERR_CUDA, cudaGetErrorString(e));
+}
+
+int rxm_attr_scatter_slots(rxm_attr* a, const uint32_t* dev_idx, uint64_t n, const void* dev_in, void* stream)
+{
+    int rc = rows_check(a, "rxm_attr_scatter_slots");
+    if (rc) return rc;
+    cudaError_t e = launch_slot_rows(false, a->d, dev_idx, n, a->elem_bytes * a->nattr / 4, const_cast<void*>(dev_in),
+                                     (cudaStream_t)stream);
+    return e == cudaSuccess ? RXM_OK : fail(RXM_ERR_CUDA, cudaGetErrorString(e));
+}
+
+int rxm_attr_push_slots(rxm_attr* a, const uint32_t* dev_local_idx, void* remote_data, const uint32_t* dev_remote_idx,
+                        uint64_t n, void* stream)
+{
+    int rc = rows_check(a, "rxm_attr_push_slots");
+    if (rc) return rc;
+    if (!remote_data) return fail(RXM_ERR_INVALID, "rxm_attr_push_slots: null remote pointer");
+    cudaError_t e = launch_push_rows(a->d, dev_local_idx, remote_data, dev_remote_idx, n, a->elem_bytes * a->nattr / 4,
+                                     (cudaStream_t)stream);
+    return e == cudaSuccess ? RXM_OK : fail(RXM_ERR_CUDA, cudaGetErrorString(e));
+}
+
+int rxm_ipc_export(void* dev_ptr, void* handle64)
+{
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, dev_ptr));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    return RXM_OK;
+}
+
+int rxm_ipc_open(const void* handle64, void** dev_ptr)
+{
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CU(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RXM_OK;
+}
+
+int rxm_ipc_close(void* dev_ptr)
+{
+    CU(cudaIpcCloseMemHandle(dev_ptr));
+    return RXM_OK;
 }
 
 uint64_t rxm_launch_count(void)

@@ -837,6 +837,34 @@ __global__ void k_permute(const T* __restrict__ src, T* __restrict__ dst, const 
     }
 }
 
+// halo pack / unpack: rows of `row_words` 32-bit words, AoS attribute storage
+template <bool GATHER>
+__global__ void k_slot_rows(uint32_t* __restrict__ attr, const uint32_t* __restrict__ idx, uint64_t n, uint32_t row_words,
+                            uint32_t* __restrict__ buf)
+{
+    const uint64_t total = n * row_words;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / row_words, w = i % row_words;
+        const uint64_t a = (uint64_t)idx[r] * row_words + w;
+        if (GATHER)
+            buf[i] = attr[a];
+        else
+            attr[a] = buf[i];
+    }
+}
+
+// direct NVLink P2P halo push: remote[remote_idx[r]] = local[local_idx[r]] (remote = peer-mapped pointer)
+__global__ void k_push_rows(const uint32_t* __restrict__ local, const uint32_t* __restrict__ local_idx,
+                            uint32_t* __restrict__ remote, const uint32_t* __restrict__ remote_idx, uint64_t n,
+                            uint32_t row_words)
+{
+    const uint64_t total = n * row_words;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / row_words, w = i % row_words;
+        remote[(uint64_t)remote_idx[r] * row_words + w] = local[(uint64_t)local_idx[r] * row_words + w];
+    }
+}
+
 template <typename T>
 __global__ void k_fill(T* __restrict__ data, uint64_t n, T v)
 {
@@ -1214,6 +1242,29 @@ cudaError_t launch_permute_to_global(const void* in_slots, void* out_global, con
 {
     return permute_dispatch<false>(in_slots, out_global, s2g, num_slots, elem_bytes, nattr, layout, slot_base,
                                    num_patches, stream);
+}
+
+cudaError_t launch_slot_rows(bool gather, void* attr, const uint32_t* idx, uint64_t n, uint32_t row_words, void* buf,
+                             cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((n * row_words + 255) / 256, 148ull * 16);
+    if (gather)
+        k_slot_rows<true><<<grid, 256, 0, stream>>>((uint32_t*)attr, idx, n, row_words, (uint32_t*)buf);
+    else
+        k_slot_rows<false><<<grid, 256, 0, stream>>>((uint32_t*)attr, idx, n, row_words, (uint32_t*)buf);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_push_rows(const void* local, const uint32_t* local_idx, void* remote, const uint32_t* remote_idx,
+                             uint64_t n, uint32_t row_words, cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((n * row_words + 255) / 256, 148ull * 16);
+    k_push_rows<<<grid, 256, 0, stream>>>((const uint32_t*)local, local_idx, (uint32_t*)remote, remote_idx, n, row_words);
+    ++g_launches;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_fill(void* data, uint64_t count, uint32_t elem_bytes, const void* value, cudaStream_t stream)

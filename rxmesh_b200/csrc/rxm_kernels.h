@@ -46,6 +46,12 @@ cudaError_t launch_permute_to_global(const void* in_slots, void* out_global, con
                                      uint32_t num_slots, uint32_t elem_bytes, uint32_t nattr, uint32_t layout,
                                      const uint32_t* slot_base, uint32_t num_patches, cudaStream_t stream);
 
+// halo exchange helpers (AoS attributes, rows of row_words 32-bit words)
+cudaError_t launch_slot_rows(bool gather, void* attr, const uint32_t* idx, uint64_t n, uint32_t row_words, void* buf,
+                             cudaStream_t stream);
+cudaError_t launch_push_rows(const void* local, const uint32_t* local_idx, void* remote, const uint32_t* remote_idx,
+                             uint64_t n, uint32_t row_words, cudaStream_t stream);
+
 cudaError_t launch_fill(void* data, uint64_t count, uint32_t elem_bytes, const void* value, cudaStream_t stream);
 
 // number of kernels launched by this library since load (bench.py "gpu_launches")

@@ -1,0 +1,204 @@
+"""Multi-GPU mode: patch sharding + ribbon (halo) exchange.
+
+CPU: world_size-2 gloo run of the host logic (shard construction, ownership consistency with the
+global mesh, halo plan, exchange).  GPU (needs >= 2 devices): NCCL + P2P exchange and an iterated
+Laplacian on the sharded mesh against the single-GPU result.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _mesh(kind):
+    from rxmesh_b200 import meshio
+    if kind == "torus":
+        return meshio.torus(48, 40, noise=0.1)
+    if kind == "grid":
+        return meshio.grid(70, 53)
+    return meshio.icosphere(14)
+
+
+def _global_patching(F, patch_size):
+    import rxmesh_b200 as rx
+    g = rx.RXMeshStatic(F, device=False, patch_size=patch_size)
+    return g, g.elem_patch(2).copy()
+
+
+def _host_worker(rank, world, port, kind, q):
+    try:
+        import rxmesh_b200 as rx
+        from rxmesh_b200 import distributed as D
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+        V, F = _mesh(kind)
+        g, fp = _global_patching(F, 128)
+        sh = D.shard_faces(F, fp, rank, world)
+        sm = D.ShardedMesh(sh, rank, world, patch_size=128, device=False)
+        m = sm.mesh
+        assert sm.count > 0 and sm.first + sm.count <= m.get_num_patches()
+        # 1. every real patch is IDENTICAL to the same patch of the global mesh (ids mapped to global)
+        for q_ in range(sm.first, sm.first + sm.count):
+            pl, pg = m.patch(q_), g.patch(int(sm.patch_global[q_]))
+            assert pl["n"] == pg["n"] and pl["n_owned"] == pg["n_owned"]
+            assert np.array_equal(sm.l2g[0][pl["ltog"][0]], pg["ltog"][0])
+            assert np.array_equal(sm.l2g[2][pl["ltog"][2]], pg["ltog"][2])
+            assert np.array_equal(pl["fv"], pg["fv"]) and np.array_equal(pl["ev"], pg["ev"])
+        # 2. halo exchange by global id (vertices and faces)
+        for elem, width in ((0, 3), (2, 1)):
+            hx = D.HaloExchange(sm, elem)
+            a = rx.Attribute(m, elem, np.float32, width, rx.HOST, rx.AoS)
+            h = a.host_array().reshape(-1, width)
+            h[:] = np.nan
+            s2g = m.slot_to_global(elem)
+            valid = s2g != 0xFFFFFFFF
+            gid = np.zeros(s2g.shape[0], dtype=np.float64)
+            gid[valid] = sm.l2g[elem][s2g[valid]]
+            real = np.zeros(s2g.shape[0], bool)
+            real[valid] = sm.real_owned_mask(elem)[s2g[valid]]
+            f = lambda x: np.stack([np.sin(0.37 * x + k) for k in range(width)], -1).astype(np.float32)  # noqa: E731
+            h[real] = f(gid[real])
+            hx.exchange(a)
+            need = sm.halo_slots(elem)
+            assert need.shape[0] == hx.halo_elements() > 0
+            assert np.array_equal(h[need], f(gid[need])), "ghost slots must hold the owners' values"
+        # 3. every element referenced by a real patch now has a value (owned by real or filled halo)
+        dist.barrier()
+        q.put((rank, "ok", sm.count, int(hx.halo_elements())))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "fail: " + traceback.format_exc(), 0, 0))
+        raise e
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["torus", "grid", "ico"])
+def test_shards_and_halo_gloo(kind):
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_host_worker, args=(r, world, port, kind, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=240) for _ in range(world)]
+    [p.join(60) for p in procs]
+    assert all(r[1] == "ok" for r in res), res
+    assert all(p.exitcode == 0 for p in procs)
+
+
+def test_grid_slab_matches_global_grid():
+    import rxmesh_b200 as rx
+    from rxmesh_b200 import distributed as D, meshio
+    nx, ny, tile, tile_i, world = 41, 67, 8, 4, 3
+    Vg, Fg = meshio.grid(nx, ny)
+    fpg = meshio.grid_face_tiles(nx, ny, tile, tile_i)
+    g = rx.RXMeshStatic(Fg, face_patch=fpg, device=False)
+    for rank in range(world):
+        sh = D.grid_slab(nx, ny, tile, tile_i, rank, world)
+        assert np.allclose(sh["verts"], Vg[sh["l2g_v"].astype(np.int64)], atol=1e-6)
+        assert np.array_equal(sh["l2g_v"][sh["fv"]].astype(np.uint32), Fg[sh["l2g_f"].astype(np.int64)])
+        assert np.array_equal(sh["face_patch"], fpg[sh["l2g_f"].astype(np.int64)])
+        sm = D.ShardedMesh(sh, rank, world, device=False)
+        for q_ in range(sm.first, sm.first + sm.count):
+            pl, pg = sm.mesh.patch(q_), g.patch(int(sm.patch_global[q_]))
+            assert np.array_equal(sm.l2g[0][pl["ltog"][0]], pg["ltog"][0])
+            assert pl["n_owned"] == pg["n_owned"]
+    # the ranks' real patches partition the global patch set
+    b = sh["bounds"]
+    assert b[0] == 0 and b[-1] == g.get_num_patches()
+
+
+# ------------------------------------------------------------------------------------- GPU (>= 2)
+def _gpu_worker(rank, world, port, q):
+    try:
+        import rxmesh_b200 as rx
+        from oracle import oracle as O
+        from rxmesh_b200 import distributed as D, meshio
+        torch.cuda.set_device(rank)
+        rx.rx_init(rank)
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", rank))
+        nx, ny, tile, tile_i = 200, 331, 16, 16
+        Vg, Fg = meshio.grid(nx, ny)
+        sh = D.grid_slab(nx, ny, tile, tile_i, rank, world)
+        sm = D.ShardedMesh(sh, rank, world)
+        m = sm.mesh
+        hx = D.HaloExchange(sm, 0)
+        x = rx.Attribute(m, 0, np.float32, 3, rx.LOCATION_ALL, rx.AoS)
+        y = rx.Attribute(m, 0, np.float32, 3, rx.LOCATION_ALL, rx.AoS)
+        x.from_global(sh["verts"])
+        y.from_global(sh["verts"])
+        iters, lr = 6, 0.01
+        T = O.Topology(Fg)
+        ref = Vg.astype(np.float64)
+        vv = T.query("VV")
+        for _ in range(iters):
+            ref = O.laplacian_step(vv, ref, lr, np.float64)
+        real = sm.real_owned_mask(0)
+        gids = sm.l2g[0].astype(np.int64)
+        for mode in ("nccl", "p2p"):
+            x.from_global(sh["verts"])
+            y.from_global(sh["verts"])
+            a, b = x, y
+            peers = hx.bind_p2p(a) if mode == "p2p" else None
+            peers_b = hx.bind_p2p(b) if mode == "p2p" else None
+            for it in range(iters):
+                m.laplacian_smooth(a, b, lr, 1)       # real patches only
+                if mode == "nccl":
+                    hx.exchange(b)
+                else:
+                    hx.exchange_p2p(b, peers_b if b is y else peers)
+                a, b = b, a
+                if mode == "p2p":
+                    peers, peers_b = peers_b, peers
+            got = a.to_global()
+            err = np.abs(got[real] - ref[gids[real]]).max()
+            assert err < 1e-5 * np.abs(Vg).max() * iters, (mode, err)
+        # vertex normals after an exchange of the coordinates
+        x.from_global(sh["verts"])
+        hx.exchange(x)
+        m.vertex_normals(x, y)
+        n = y.to_global()
+        refn = O.vertex_normals(Fg, Vg, np.float64)
+        rel = np.linalg.norm(n[real] - refn[gids[real]], axis=1) / np.linalg.norm(refn[gids[real]], axis=1)
+        assert rel.max() < 1e-5
+        dist.barrier()
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, "fail: " + traceback.format_exc()))
+        raise
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_laplacian_and_normals_nccl():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gpu_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=600) for _ in range(world)]
+    [p.join(60) for p in procs]
+    assert all(r[1] == "ok" for r in res), res
