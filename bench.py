@@ -219,13 +219,29 @@ def run_ours(args, rank, world, local_rank):
     n = grid_side(args.faces)
     ncores = os.cpu_count() or 8
     t0 = time.perf_counter()
-    V, F = meshio.grid(n, n)
-    fp = meshio.grid_face_tiles(n, n, TILE, TILE_I)
-    mesh = rx.RXMeshStatic(F, face_patch=fp, patch_size=2 * TILE * TILE_I, num_threads=max(1, ncores // world))
+    hx_v = hx_f = None
+    if world == 1:
+        V, F = meshio.grid(n, n)
+        fp = meshio.grid_face_tiles(n, n, TILE, TILE_I)
+        mesh = rx.RXMeshStatic(F, face_patch=fp, patch_size=2 * TILE * TILE_I, num_threads=ncores)
+        del fp
+        nF, nV = mesh.get_num_faces(), mesh.get_num_vertices()
+        nE_real = mesh.get_num_edges()
+        halo_bytes = 0
+    else:
+        # weak scaling: a (world * (n-1) + 1)-row grid, every rank owns a slab of ~args.faces faces and
+        # mirrors one ghost tile row per neighbour (rxmesh_b200/distributed.py)
+        from rxmesh_b200 import distributed as D
+        sh = D.grid_slab(n, world * (n - 1) + 1, TILE, TILE_I, rank, world)
+        sm = D.ShardedMesh(sh, rank, world, patch_size=2 * TILE * TILE_I, num_threads=max(1, ncores // world))
+        mesh, V = sm.mesh, sh["verts"]
+        hx_v, hx_f = D.HaloExchange(sm, 0), D.HaloExchange(sm, 2)
+        lbf, lbv, lbe = mesh.lin_base(2), mesh.lin_base(0), mesh.lin_base(1)
+        a, b = sm.first, sm.first + sm.count
+        nF, nV = int(lbf[b] - lbf[a]), mesh.get_num_vertices()  # real faces; host arrays cover the whole slab
+        nE_real = int(lbe[b] - lbe[a])
+        halo_bytes = 12 * hx_v.halo_elements()
     t_build = time.perf_counter() - t0
-    nF, nV = mesh.get_num_faces(), mesh.get_num_vertices()
-    del fp
-
     stream = torch.cuda.current_stream()
     x = rx.Attribute(mesh, 0, np.float32, 3, rx.DEVICE, rx.AoS)
     nrm = rx.Attribute(mesh, 0, np.float32, 3, rx.DEVICE, rx.AoS)
@@ -235,15 +251,26 @@ def run_ours(args, rank, world, local_rank):
     rng = np.random.RandomState(1 + rank)
     h_x = torch.from_numpy(V).pin_memory()
     h_sv = torch.from_numpy(rng.rand(nV).astype(np.float32)).pin_memory()
-    h_sf = torch.from_numpy(rng.rand(nF).astype(np.float32)).pin_memory()
+    h_sf = torch.from_numpy(rng.rand(mesh.get_num_faces()).astype(np.float32)).pin_memory()
     x.from_global(h_x.numpy(), stream)
     sv_in.from_global(h_sv.numpy(), stream)
     sf_in.from_global(h_sf.numpy(), stream)
     torch.cuda.synchronize()
+    if hx_v is not None:  # static inputs: mirrored once; the coordinates are re-mirrored every step
+        hx_v.exchange(sv_in, stream)
+        hx_f.exchange(sf_in, stream)
+        hx_v.exchange(x, stream)
+        torch.cuda.synchronize()
+
+    if args.workload == "laplacian":
+        return run_laplacian(args, rank, world, local_rank, mesh, x, nrm, hx_v, nV if world == 1 else None,
+                             n, t_build, torch, rx, stream)
 
     def step(evs=None):
         if evs:
             evs[0].record(stream)
+        if hx_v is not None:
+            hx_v.exchange(x, stream)  # ribbon (halo) exchange, inside the timed step
         mesh.query_consume(rx.Op.VV, sv_in, sv_out, stream)
         if evs:
             evs[1].record(stream)
@@ -301,7 +328,7 @@ def run_ours(args, rank, world, local_rank):
         e2e_step()
     barrier()
     te = (time.perf_counter() - te) / e2e_steps
-    h2d = 12 * nV + 4 * nV + 4 * nF
+    h2d = 12 * nV + 4 * nV + 4 * mesh.get_num_faces()
     d2h = 12 * nV + 4 * nV + 4 * nV
 
     # ---- max over ranks ----
@@ -315,7 +342,7 @@ def run_ours(args, rank, world, local_rank):
     ms_step = total_ms / args.steps
     peak, peak_src = peaks()
     kern = {}
-    for name, ms, unit, units in (("VV", k_ms[0], "neighbour entries/s", 2.0 * mesh.get_num_edges()),
+    for name, ms, unit, units in (("VV", k_ms[0], "neighbour entries/s", 2.0 * nE_real),
                                   ("VF", k_ms[1], "neighbour entries/s", 3.0 * nF),
                                   ("VN", k_ms[2], "faces/s", float(nF))):
         gbs = ALG_BYTES_PER_FACE[name] * nF / (ms * 1e-3) / 1e9
@@ -344,13 +371,68 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": nF * world / te, "unit": "faces/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": te * 1e3,
                 "api": "rxm_query_consume_host(VV), rxm_query_consume_host(VF), rxm_vertex_normals_host (pinned host buffers)"},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches), "clocks": clocks, "halo_bytes_per_step_per_gpu": int(halo_bytes),
         "wall_ms_per_step": t_wall / args.steps * 1e3, "build_seconds": t_build,
     }
     if world == 1 and not args.no_cpu:
         cb, _ = cpu_baseline(min(args.faces, args.cpu_sample_faces), 3)
         line["cpu_baseline"] = cb
     print(json.dumps(line), flush=True)
+
+
+def run_laplacian(args, rank, world, local_rank, mesh, x, y, hx_v, nv_single, n, t_build, torch, rx, stream):
+    """BASELINE.json configs[4]: iterated Laplacian smoothing (apps/Smoothing/manual.h:86-104), patches
+    sharded across the ranks, ribbon exchange after every iteration inside the timed region."""
+    lbv = mesh.lin_base(0)
+    if hx_v is None:
+        n_upd = mesh.get_num_vertices()
+    else:
+        n_upd = None
+    def iterate(k):
+        a, b = x, y
+        for _ in range(k):
+            mesh.laplacian_smooth(a, b, 0.01, 1, stream)
+            if hx_v is not None:
+                hx_v.exchange(b, stream)
+            a, b = b, a
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+    iterate(max(3, args.warmup))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = rx.launch_count()
+    e0.record(stream)
+    for _ in range(args.steps):
+        iterate(args.iters)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    real_v = torch.tensor([float(n_upd) if n_upd is not None else float((mesh.elem_patch(0) >= 0).sum())],
+                          dtype=torch.float64, device="cuda")
+    if world > 1:
+        from rxmesh_b200 import distributed as D  # noqa: F401
+        torch.distributed.all_reduce(tm, op=torch.distributed.ReduceOp.MAX)
+    if rank != 0:
+        return
+    ms = float(tm[0])
+    its = args.steps * args.iters
+    nF = 2 * (n - 1) ** 2 * world
+    peak, peak_src = peaks()
+    per_it = ms / its
+    print(json.dumps({
+        "metric": "vertex-updates/s, iterated Laplacian smoothing, patches sharded across GPUs, ribbon exchange in the timing",
+        "value": (nF / 2.0) / (per_it * 1e-3), "unit": "vertex-updates/s", "n_gpus": world, "steps": args.steps,
+        "iters_per_step": args.iters, "ms_per_iteration": per_it, "higher_is_better": True, "scaling": "weak",
+        "dtype": "f32", "data": "synthetic", "faces_total": nF,
+        "roofline": {"bound": "hbm", "kernel": "k_laplacian_fan", "achieved": 24.0 * nF / world / (per_it * 1e-3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": 24.0 * nF / world / (per_it * 1e-3) / 1e9 / peak,
+                     "peak_source": peak_src, "note": "per GPU, includes the halo exchange time"},
+        "halo_bytes_per_iteration_per_gpu": 0 if hx_v is None else 12 * hx_v.halo_elements(),
+        "gpu_launches": int(rx.launch_count() - l0), "build_seconds": t_build}), flush=True)
 
 
 def main():
@@ -362,6 +444,9 @@ def main():
     ap.add_argument("--faces", type=int, default=100_000_000)
     ap.add_argument("--cpu-sample-faces", type=int, default=4_000_000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="queries", choices=["queries", "laplacian"],
+                    help="queries = the headline VV+VF+normals pass; laplacian = iterated smoothing (configs[4])")
+    ap.add_argument("--iters", type=int, default=100, help="Laplacian iterations per step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -369,7 +454,13 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
-    run_ours(args, rank, world, local_rank)
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
 
 
 if __name__ == "__main__":
