@@ -1,0 +1,119 @@
+// rxmesh/attribute.h -- Attribute<T, HandleT> (include/rxmesh/attribute.h:56-731, attribute.cu:30-590) over the
+// C ABI: storage for OWNED elements in slot order (rxmesh_b200/csrc/patch_layout.h), host + device copies,
+// the reference's three layouts and its operator()(handle, attr) on both sides.
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../rxmesh_b200.h"
+#include "rxmesh/handle.h"
+
+namespace rxmesh {
+namespace detail {
+inline void rxm_check(int rc)
+{
+    if (rc != RXM_OK) {  // CUDA_ERROR semantics of the reference: log and exit (util/macros.h:77-89)
+        fprintf(stderr, "rxmesh_b200: %s\n", rxm_last_error());
+        exit(EXIT_FAILURE);
+    }
+}
+}  // namespace detail
+
+class AttributeBase
+{
+   public:
+    virtual const char* get_name() const = 0;
+    virtual void        release(locationT location = LOCATION_ALL) = 0;
+    virtual ~AttributeBase()                                       = default;
+};
+
+template <class T, typename HandleT>
+class Attribute : public AttributeBase
+{
+   public:
+    using Type       = T;
+    using HandleType = HandleT;
+    Attribute()      = default;
+
+    // created by RXMeshStatic::add_*_attribute
+    Attribute(rxm_mesh* mesh, const char* name, uint32_t num_attributes, locationT location, layoutT layout)
+        : m_name(name), m_nattr(num_attributes), m_layout(layout), m_location(location)
+    {
+        static_assert(sizeof(T) == 1 || sizeof(T) == 2 || sizeof(T) == 4 || sizeof(T) == 8, "unsupported attribute type");
+        rxm_attr* a = nullptr;
+        detail::rxm_check(rxm_attr_create(mesh, HandleT::elem, sizeof(T), num_attributes, (int)location, (int)layout, &a));
+        m_owner        = std::shared_ptr<rxm_attr>(a, [](rxm_attr* p) { rxm_attr_destroy(p); });
+        m_attr         = a;
+        m_h            = (T*)rxm_attr_data(a, RXM_HOST);
+        m_d            = (T*)rxm_attr_data(a, RXM_DEVICE);
+        m_num_slots    = (uint32_t)rxm_mesh_info(mesh, RXM_INFO_NUM_SLOTS_V + HandleT::elem);
+        m_h_slot_base  = rxm_mesh_slot_base(mesh, HandleT::elem);
+        m_d_slot_base  = rxm_mesh_device_slot_base(mesh, HandleT::elem);
+    }
+    Attribute(const Attribute&) = default;  // shallow, like the reference (attribute.h:194)
+
+    const char* get_name() const override { return m_name.c_str(); }
+    __host__ __device__ uint32_t  get_num_attributes() const { return m_nattr; }
+    __host__ __device__ layoutT   get_layout() const { return m_layout; }
+    __host__ __device__ locationT get_allocated() const { return m_location; }
+    __host__ __device__ bool      is_device_allocated() const { return (m_location & DEVICE) == DEVICE; }
+    __host__ __device__ bool      is_host_allocated() const { return (m_location & HOST) == HOST; }
+    __host__ __device__ T*        data(locationT location = DEVICE) const { return (location & DEVICE) ? m_d : m_h; }
+    uint32_t size() const { return m_num_slots; }
+    rxm_attr* c_handle() const { return m_attr; }
+
+    void reset(const T value, locationT location, cudaStream_t stream = NULL) { detail::rxm_check(rxm_attr_reset(m_attr, &value, (int)location, stream)); }
+    void move(locationT source, locationT target, cudaStream_t stream = NULL) { detail::rxm_check(rxm_attr_move(m_attr, (int)source, (int)target, stream)); }
+    void copy_from(Attribute<T, HandleT>& source, locationT source_flag, locationT dst_flag, cudaStream_t stream = NULL)
+    {
+        detail::rxm_check(rxm_attr_copy_from(m_attr, source.m_attr, (int)source_flag, (int)dst_flag, stream));
+    }
+    void release(locationT = LOCATION_ALL) override { m_owner.reset(); m_attr = nullptr; m_h = nullptr; m_d = nullptr; }
+
+    // Attribute::operator()(handle, attr) (attribute.h:313-319,406-434)
+    __host__ __device__ __forceinline__ T& operator()(const HandleT handle, const uint32_t attr = 0) const
+    {
+#ifdef __CUDA_ARCH__
+        return m_d[index(m_d_slot_base, handle.patch_id(), handle.local_id(), attr)];
+#else
+        return m_h[index(m_h_slot_base, handle.patch_id(), handle.local_id(), attr)];
+#endif
+    }
+    template <int N>
+    __host__ __device__ __forceinline__ glm::vec<N, T> to_glm(const HandleT& handle) const
+    {
+        glm::vec<N, T> r;
+        for (int i = 0; i < N; ++i) r[i] = (*this)(handle, i);
+        return r;
+    }
+    template <int N>
+    __host__ __device__ __forceinline__ void from_glm(const HandleT& handle, const glm::vec<N, T>& in) const
+    {
+        for (int i = 0; i < N; ++i) (*this)(handle, i) = in[i];
+    }
+
+   private:
+    __host__ __device__ __forceinline__ uint64_t index(const uint32_t* sb, uint32_t p, uint32_t lid, uint32_t a) const
+    {
+        const uint32_t b = sb[p];
+        if (m_layout == AoS) return (uint64_t)(b + lid) * m_nattr + a;
+        if (m_layout == SoA) return (uint64_t)a * m_num_slots + b + lid;
+        return (uint64_t)b * m_nattr + (uint64_t)a * (sb[p + 1] - b) + lid;
+    }
+    std::string               m_name;
+    std::shared_ptr<rxm_attr> m_owner;
+    rxm_attr*                 m_attr = nullptr;
+    T *                       m_h = nullptr, *m_d = nullptr;
+    const uint32_t *          m_h_slot_base = nullptr, *m_d_slot_base = nullptr;
+    uint32_t                  m_num_slots = 0, m_nattr = 0;
+    layoutT                   m_layout   = AoSoA;
+    locationT                 m_location = LOCATION_NONE;
+};
+
+template <class T> using VertexAttribute = Attribute<T, VertexHandle>;
+template <class T> using EdgeAttribute   = Attribute<T, EdgeHandle>;
+template <class T> using FaceAttribute   = Attribute<T, FaceHandle>;
+}  // namespace rxmesh

@@ -1,0 +1,124 @@
+// rxmesh/query.h -- Query<blockThreads> (include/rxmesh/query.h:15-137, query.inl:107-260): dispatch<op>
+// loads the patch sections by TMA, builds the adjacency in shared memory and calls the user's device lambda
+// (InputHandle, OutputIterator&) once per OWNED source element that passes the active-set predicate.
+#pragma once
+#include <cooperative_groups.h>
+#include "rxmesh/context.h"
+#include "rxmesh/iterator.cuh"
+#include "rxmesh/kernels/shmem_allocator.cuh"
+
+namespace rxmesh {
+template <uint32_t blockThreads>
+struct Query
+{
+    __device__ Query(const Context& context, const uint32_t pid = blockIdx.x)
+        : m_ctx(context), m_pid(pid), m_desc(load(context.view.desc + pid)) {}
+    Query(const Query&)            = delete;
+    Query& operator=(const Query&) = delete;
+    __device__ int                  get_patch_id() const { return (int)m_desc.patch_id; }
+    __device__ const rxm::PatchDesc& get_patch_info() const { return m_desc; }
+
+    template <Op op, typename computeT>
+    __device__ void dispatch(cooperative_groups::thread_block& block, ShmemAllocator& shrd_alloc, computeT compute_op,
+                             const bool oriented = false)
+    {
+        using InH = typename InputHandle<op>::type;
+        dispatch<op>(block, shrd_alloc, compute_op, [](InH) { return true; }, oriented);
+    }
+
+    template <Op op, typename computeT, typename activeSetT>
+    __device__ void dispatch(cooperative_groups::thread_block& block, ShmemAllocator& shrd_alloc, computeT compute_op,
+                             activeSetT compute_active_set, const bool oriented = false, const bool allow_not_owned = false)
+    {
+        (void)block;
+        if (m_ctx.view.packed)
+            run<op, true>(shrd_alloc, compute_op, compute_active_set, oriented, allow_not_owned);
+        else
+            run<op, false>(shrd_alloc, compute_op, compute_active_set, oriented, allow_not_owned);
+    }
+
+   private:
+    static __device__ rxm::PatchDesc load(const rxm::PatchDesc* g)
+    {
+        rxm::PatchDesc d;
+        const uint4*   s = reinterpret_cast<const uint4*>(g);
+        uint4*         t = reinterpret_cast<uint4*>(&d);
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(rxm::PatchDesc) / 16); ++i)
+            t[i] = __ldg(s + i);
+        return d;
+    }
+
+    template <Op op, bool PACKED, typename computeT, typename activeSetT>
+    __device__ void run(ShmemAllocator& sa, computeT& compute_op, activeSetT& active, bool oriented, bool all_sources)
+    {
+        using namespace rxm::dev;
+        using InH  = typename InputHandle<op>::type;
+        using OutH = typename OutputHandle<op>::type;
+        constexpr int OPV = (int)op;
+        __shared__ uint64_t bar;
+        __shared__ uint32_t warp_tmp[36];
+        const rxm::PatchDesc& d    = m_desc;
+        const uint8_t*        blob = m_ctx.view.topo + d.topo_off;
+        const uint32_t        used0 = sa.m_sm.used;
+        // oriented VV (kernels/rxmesh_queries.cuh:375-499): served by the stored one-ring fans
+        const bool use_fans = (op == Op::VV) && oriented && m_ctx.view.fans && !all_sources;
+        PatchQuery<OPV, (int)blockThreads, 12, PACKED> q;
+        uint16_t *s_fo = nullptr, *s_fv = nullptr;
+        uint32_t* s_own = nullptr;
+        rxm::StashEntry* s_stash = nullptr;
+        if (use_fans) {
+            s_fo    = sa.template alloc<uint16_t>(d.fanoff_bytes() / 2);
+            s_fv    = sa.template alloc<uint16_t>(d.fanv_bytes() / 2);
+            s_own   = sa.template alloc<uint32_t>(d.own_bytes(rxm::ELEM_V) / 4);
+            s_stash = sa.template alloc<rxm::StashEntry>(d.n_stash);
+        } else {
+            q.plan(d, sa.m_sm, true, all_sources);
+        }
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+            if (use_fans) {
+                mbar_arrive_expect_tx(&bar, d.fanoff_bytes() + d.fanv_bytes() + d.own_bytes(rxm::ELEM_V) + d.stash_bytes());
+                bulk_g2s(s_fo, blob + d.off_fanoff(), d.fanoff_bytes(), &bar);
+                if (d.fanv_bytes()) bulk_g2s(s_fv, blob + d.off_fanv(), d.fanv_bytes(), &bar);
+                if (d.own_bytes(rxm::ELEM_V)) bulk_g2s(s_own, blob + d.off_own(rxm::ELEM_V), d.own_bytes(rxm::ELEM_V), &bar);
+                if (d.stash_bytes()) bulk_g2s(s_stash, blob + d.off_stash(), d.stash_bytes(), &bar);
+            } else {
+                mbar_arrive_expect_tx(&bar, q.tx_bytes(d, true));
+                q.issue(d, blob, &bar, true);
+            }
+        }
+        __syncthreads();
+        mbar_wait(&bar, 0);
+        QueryResult r;
+        OwnerTable  ot;
+        if (use_fans) {
+            // fan_off entries carry the closed flag in bit 15: strip it once so the list bounds are plain
+            for (uint32_t i = threadIdx.x; i <= d.n_owned[rxm::ELEM_V]; i += blockThreads)
+                s_fo[i] &= rxm::FAN_OFF_MASK;
+            __syncthreads();
+            r.off16 = s_fo, r.off32 = nullptr, r.val = s_fv, r.stride = 0, r.shift = 0, r.mask = 0xFFFFu;
+            r.n_src = d.n_owned[rxm::ELEM_V];
+            ot.own = s_own, ot.stash = s_stash, ot.n_owned = d.n_owned[rxm::ELEM_V], ot.patch = d.patch_id;
+            ot.slot_base = d.slot_base[rxm::ELEM_V], ot.type = rxm::ELEM_V;
+        } else {
+            r = q.compute(d, warp_tmp, all_sources, false);
+            if (op_is_fixed<OPV>()) __syncthreads();
+            ot = q.owner_table(d);
+        }
+        for (uint32_t s = threadIdx.x; s < r.n_src; s += blockThreads) {
+            InH h(d.patch_id, typename InH::LocalT((uint16_t)s));
+            if (!active(h)) continue;
+            Iterator<OutH> it(r, ot, s);
+            compute_op(h, it);
+        }
+        __syncthreads();
+        sa.m_sm.used = used0;  // epilogue: release the query's shared memory (query.inl:74-91)
+    }
+
+    const Context&       m_ctx;
+    uint32_t             m_pid;
+    const rxm::PatchDesc m_desc;
+};
+}  // namespace rxmesh

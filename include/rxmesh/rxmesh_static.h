@@ -1,0 +1,249 @@
+// rxmesh/rxmesh_static.h -- RXMeshStatic (include/rxmesh/rxmesh_static.h:37-1245) for the static hot path,
+// over librxmesh_b200 (C ABI in include/rxmesh_b200.h).  Same names / argument meaning; user kernels written
+// against the reference (Query::dispatch, for_each<Op>, Attribute::operator()) compile against this header.
+#pragma once
+#include <functional>
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "rxmesh/attribute.h"
+#include "rxmesh/context.h"
+#include "rxmesh/launch_box.h"
+#include "rxmesh/query.h"
+
+namespace rxmesh {
+
+inline void rx_init(int device_id = 0) { detail::rxm_check(rxm_init(device_id)); }  // rxmesh.h:23-30
+
+namespace detail {
+// detail::query_kernel (kernels/query_kernel.cuh:12-24)
+template <uint32_t blockThreads, Op op, typename LambdaT>
+__global__ static void query_kernel(const Context context, const bool oriented, LambdaT user_lambda)
+{
+    auto                block = cooperative_groups::this_thread_block();
+    Query<blockThreads> query(context);
+    ShmemAllocator      shrd_alloc;
+    query.template dispatch<op>(block, shrd_alloc, user_lambda, oriented);
+}
+// detail::for_each_vertex/edge/face (kernels/for_each.cuh:30-105): owned elements are the prefix [0, n_owned)
+template <typename HandleT, typename LambdaT>
+__global__ static void for_each_kernel(const Context context, LambdaT apply)
+{
+    const rxm::PatchDesc* d = context.view.desc + blockIdx.x;
+    const uint32_t        n = d->n_owned[HandleT::elem], pid = d->patch_id;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+        apply(HandleT(pid, typename HandleT::LocalT((uint16_t)i)));
+}
+}  // namespace detail
+
+class RXMeshStatic
+{
+   public:
+    RXMeshStatic(const RXMeshStatic&) = delete;
+
+    // RXMeshStatic(fv, patcher_file, patch_size, ...) (rxmesh_static.h:61-100). patcher_file's role (a saved
+    // patching) is played by an explicit face -> patch array.
+    explicit RXMeshStatic(const std::vector<std::vector<uint32_t>>& fv, const std::vector<uint32_t>& face_patch = {},
+                          const uint32_t patch_size = 512)
+    {
+        std::vector<uint32_t> flat;
+        flat.reserve(3 * fv.size());
+        for (const auto& f : fv) {
+            if (f.size() != 3) {  // rxmesh.cpp:590-597
+                fprintf(stderr, "rxmesh_b200: non-triangular faces are not supported\n");
+                exit(EXIT_FAILURE);
+            }
+            flat.insert(flat.end(), f.begin(), f.end());
+        }
+        init(flat.data(), (uint32_t)fv.size(), face_patch, patch_size);
+    }
+    RXMeshStatic(const uint32_t* fv, uint32_t num_faces, const std::vector<uint32_t>& face_patch = {},
+                 const uint32_t patch_size = 512)
+    {
+        init(fv, num_faces, face_patch, patch_size);
+    }
+    virtual ~RXMeshStatic()
+    {
+        m_attrs.clear();
+        rxm_mesh_destroy(m_mesh);
+    }
+
+    // ---- getters (rxmesh.h:44-399) ----
+    uint32_t get_num_vertices() const { return info(RXM_INFO_NUM_VERTICES); }
+    uint32_t get_num_edges() const { return info(RXM_INFO_NUM_EDGES); }
+    uint32_t get_num_faces() const { return info(RXM_INFO_NUM_FACES); }
+    uint32_t get_num_patches() const { return info(RXM_INFO_NUM_PATCHES); }
+    uint32_t get_patch_size() const { return info(RXM_INFO_PATCH_SIZE); }
+    uint32_t get_input_max_valence() const { return info(RXM_INFO_MAX_VALENCE); }
+    uint32_t get_input_max_edge_incident_faces() const { return info(RXM_INFO_MAX_EDGE_INCIDENT_FACES); }
+    uint32_t get_input_max_face_adjacent_faces() const { return info(RXM_INFO_MAX_FACE_ADJACENT_FACES); }
+    bool     is_closed() const { return info(RXM_INFO_IS_CLOSED) != 0; }
+    bool     is_edge_manifold() const { return info(RXM_INFO_IS_EDGE_MANIFOLD) != 0; }
+    uint32_t get_per_patch_max_vertices() const { return info(RXM_INFO_MAX_VERTICES_PER_PATCH); }
+    uint32_t get_per_patch_max_edges() const { return info(RXM_INFO_MAX_EDGES_PER_PATCH); }
+    uint32_t get_per_patch_max_faces() const { return info(RXM_INFO_MAX_FACES_PER_PATCH); }
+    const Context& get_context() const { return m_context; }
+    rxm_mesh*      c_handle() const { return m_mesh; }
+
+    // ---- attributes (rxmesh_static.h:608-806) ----
+    template <class T>
+    std::shared_ptr<VertexAttribute<T>> add_vertex_attribute(const std::string& name, uint32_t num_attributes,
+                                                             locationT location = LOCATION_ALL, layoutT layout = AoSoA)
+    {
+        return add<VertexAttribute<T>>(name, num_attributes, location, layout);
+    }
+    template <class T>
+    std::shared_ptr<EdgeAttribute<T>> add_edge_attribute(const std::string& name, uint32_t num_attributes,
+                                                         locationT location = LOCATION_ALL, layoutT layout = AoSoA)
+    {
+        return add<EdgeAttribute<T>>(name, num_attributes, location, layout);
+    }
+    template <class T>
+    std::shared_ptr<FaceAttribute<T>> add_face_attribute(const std::string& name, uint32_t num_attributes,
+                                                         locationT location = LOCATION_ALL, layoutT layout = AoSoA)
+    {
+        return add<FaceAttribute<T>>(name, num_attributes, location, layout);
+    }
+    // add_attribute<T, HandleT>: generic over the element type
+    template <class T, class HandleT>
+    std::shared_ptr<Attribute<T, HandleT>> add_attribute(const std::string& name, uint32_t num_attributes,
+                                                         locationT location = LOCATION_ALL, layoutT layout = AoSoA)
+    {
+        return add<Attribute<T, HandleT>>(name, num_attributes, location, layout);
+    }
+    // add_vertex_attribute(Verts, name): filled from per-vertex input in GLOBAL order (rxmesh_static.inl:147-189)
+    template <class T>
+    std::shared_ptr<VertexAttribute<T>> add_vertex_attribute(const std::vector<std::vector<T>>& values, const std::string& name,
+                                                             layoutT layout = AoSoA)
+    {
+        const uint32_t n = values.empty() ? 0 : (uint32_t)values[0].size();
+        auto           a = add<VertexAttribute<T>>(name, n, LOCATION_ALL, layout);
+        std::vector<T> flat;
+        flat.reserve(values.size() * n);
+        for (const auto& v : values)
+            flat.insert(flat.end(), v.begin(), v.end());
+        detail::rxm_check(rxm_attr_upload_global(a->c_handle(), flat.data(), nullptr));
+        detail::rxm_check(cudaDeviceSynchronize() == cudaSuccess ? RXM_OK : RXM_ERR_CUDA);
+        return a;
+    }
+    bool does_attribute_exist(const std::string& name) const { return m_attrs.count(name) != 0; }
+    void remove_attribute(const std::string& name) { m_attrs.erase(name); }
+
+    // ---- id maps ----
+    template <typename HandleT>
+    uint32_t map_to_global(const HandleT h) const  // rxmesh_static.cu:669-685
+    {
+        return rxm_mesh_slot_to_global(m_mesh, HandleT::elem)[rxm_mesh_slot_base(m_mesh, HandleT::elem)[h.patch_id()] + h.local_id()];
+    }
+    template <typename HandleT>
+    uint32_t linear_id(const HandleT h) const  // context.h:275-290
+    {
+        return rxm_mesh_lin_base(m_mesh, HandleT::elem)[h.patch_id()] + h.local_id();
+    }
+
+    // ---- for_each_vertex / edge / face (rxmesh_static.h:205-379) ----
+    template <typename LambdaT>
+    void for_each_vertex(locationT location, LambdaT apply, cudaStream_t stream = NULL, bool with_omp = true) const
+    {
+        for_each_elem<VertexHandle>(location, apply, stream, with_omp);
+    }
+    template <typename LambdaT>
+    void for_each_edge(locationT location, LambdaT apply, cudaStream_t stream = NULL, bool with_omp = true) const
+    {
+        for_each_elem<EdgeHandle>(location, apply, stream, with_omp);
+    }
+    template <typename LambdaT>
+    void for_each_face(locationT location, LambdaT apply, cudaStream_t stream = NULL, bool with_omp = true) const
+    {
+        for_each_elem<FaceHandle>(location, apply, stream, with_omp);
+    }
+
+    // ---- for_each<Op, blockThreads>(lambda) (rxmesh_static.h:524-566) ----
+    template <Op op, uint32_t blockThreads, typename LambdaT>
+    void for_each(const LambdaT user_lambda, const bool oriented = false, cudaStream_t stream = NULL) const
+    {
+        LaunchBox<blockThreads> lb;
+        prepare_launch_box({op}, lb, (void*)detail::query_kernel<blockThreads, op, LambdaT>, oriented);
+        detail::query_kernel<blockThreads, op><<<lb.blocks, lb.num_threads, lb.smem_bytes_dyn, stream>>>(m_context, oriented, user_lambda);
+    }
+
+    // ---- prepare_launch_box (rxmesh_static.inl:443-496) ----
+    template <uint32_t blockThreads>
+    void prepare_launch_box(const std::vector<Op> op, LaunchBox<blockThreads>& launch_box, const void* kernel,
+                            const bool oriented = false, const bool with_vertex_valence = false,
+                            const bool is_concurrent = false,
+                            std::function<size_t(uint32_t, uint32_t, uint32_t)> user_shmem =
+                                [](uint32_t, uint32_t, uint32_t) { return 0; }) const
+    {
+        (void)oriented, (void)with_vertex_valence;
+        size_t   dyn = 0;
+        uint32_t blocks = 0, threads = 0;
+        for (Op o : op) {
+            uint32_t b = 0;
+            detail::rxm_check(rxm_mesh_launch_box(m_mesh, (int)o, &blocks, &threads, &b));
+            dyn = is_concurrent ? dyn + b : std::max<size_t>(dyn, b);
+        }
+        dyn += user_shmem(get_per_patch_max_vertices(), get_per_patch_max_edges(), get_per_patch_max_faces());
+        launch_box.blocks         = blocks;
+        launch_box.smem_bytes_dyn = dyn;
+        cudaFuncAttributes fa{};
+        if (kernel && cudaFuncGetAttributes(&fa, kernel) == cudaSuccess) {
+            launch_box.smem_bytes_static        = fa.sharedSizeBytes;
+            launch_box.num_registers_per_thread = (uint32_t)fa.numRegs;
+            launch_box.local_mem_per_thread     = fa.localSizeBytes;
+            if (dyn > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        }
+    }
+
+   private:
+    void init(const uint32_t* fv, uint32_t nf, const std::vector<uint32_t>& face_patch, uint32_t patch_size)
+    {
+        detail::rxm_check(rxm_mesh_create(fv, nf, face_patch.empty() ? nullptr : face_patch.data(), patch_size, 0, &m_mesh));
+        detail::rxm_check(rxm_mesh_to_device(m_mesh));
+        detail::rxm_check(rxm_mesh_view(m_mesh, &m_context.view, (uint32_t)sizeof(rxm::MeshView)));
+    }
+    uint32_t info(int k) const { return (uint32_t)rxm_mesh_info(m_mesh, k); }
+
+    template <typename AttrT>
+    std::shared_ptr<AttrT> add(const std::string& name, uint32_t n, locationT location, layoutT layout)
+    {
+        if (m_attrs.count(name)) {
+            fprintf(stderr, "rxmesh_b200: attribute %s already exists\n", name.c_str());  // RXMESH_ERROR: log, continue
+            return std::dynamic_pointer_cast<AttrT>(m_attrs[name]);
+        }
+        auto a        = std::make_shared<AttrT>(m_mesh, name.c_str(), n, location, layout);
+        m_attrs[name] = a;
+        return a;
+    }
+
+    template <typename HandleT, typename LambdaT>
+    void for_each_elem(locationT location, LambdaT apply, cudaStream_t stream, bool with_omp) const
+    {
+        constexpr bool is_d  = __nv_is_extended_device_lambda_closure_type(LambdaT);
+        constexpr bool is_hd = __nv_is_extended_host_device_lambda_closure_type(LambdaT);
+        if ((location & HOST) == HOST) {
+            if constexpr (!is_d) {
+                const uint32_t* lb = rxm_mesh_lin_base(m_mesh, HandleT::elem);
+                const int       P  = (int)get_num_patches();
+#pragma omp parallel for if (with_omp)
+                for (int p = 0; p < P; ++p)
+                    for (uint32_t i = 0; i < lb[p + 1] - lb[p]; ++i)
+                        apply(HandleT((uint32_t)p, typename HandleT::LocalT((uint16_t)i)));
+            }
+        }
+        if ((location & DEVICE) == DEVICE) {
+            if constexpr (is_d || is_hd) {
+                detail::for_each_kernel<HandleT><<<get_num_patches(), 256, 0, stream>>>(m_context, apply);
+            } else {
+                fprintf(stderr, "RXMeshStatic::for_each_*() Input lambda function should be annotated with __device__ "
+                                "for execution on device\n");
+            }
+        }
+    }
+
+    rxm_mesh*                                             m_mesh = nullptr;
+    Context                                               m_context;
+    std::map<std::string, std::shared_ptr<AttributeBase>> m_attrs;
+};
+}  // namespace rxmesh

@@ -113,6 +113,13 @@ const uint32_t* rxm_mesh_lin_base(const rxm_mesh* m, int elem);  /* [num_patches
 const uint32_t* rxm_mesh_edges(const rxm_mesh* m);
 const uint32_t* rxm_mesh_face_edges(const rxm_mesh* m);
 
+/* device copy of rxm_mesh_slot_base (what Attribute::operator() indexes on the device) */
+const uint32_t* rxm_mesh_device_slot_base(const rxm_mesh* m, int elem);
+/* get_context() (rxmesh_static.h): copies the by-value kernel argument (rxm::MeshView of
+ * rxmesh_b200/csrc/patch_layout.h, the counterpart of Context, context.h:15-441) into out_view;
+ * out_bytes must equal sizeof(rxm::MeshView). Used by the C++ header shim (include/rxmesh/). */
+int rxm_mesh_view(const rxm_mesh* m, void* out_view, uint32_t out_bytes);
+
 /* prepare_launch_box / calc_shared_memory (rxmesh_static.inl:443-841): dynamic shared memory bytes and
  * grid size the query kernel for `op` uses on this mesh. */
 int rxm_mesh_launch_box(const rxm_mesh* m, int op, uint32_t* blocks, uint32_t* threads, uint32_t* smem_bytes);

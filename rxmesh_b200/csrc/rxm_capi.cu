@@ -284,6 +284,19 @@ const uint32_t* rxm_mesh_face_edges(const rxm_mesh* m)
     return m ? m->h.fe.data() : nullptr;
 }
 
+const uint32_t* rxm_mesh_device_slot_base(const rxm_mesh* m, int t)
+{
+    return (m && m->on_device && t >= 0 && t < 3) ? m->d_slot_base[t] : nullptr;
+}
+
+int rxm_mesh_view(const rxm_mesh* m, void* out_view, uint32_t out_bytes)
+{
+    if (!m || !out_view || out_bytes != sizeof(MeshView)) return fail(RXM_ERR_INVALID, "rxm_mesh_view: bad argument");
+    if (!m->on_device) return fail(RXM_ERR_CUDA, "rxm_mesh_view: mesh is not on a CUDA device");
+    memcpy(out_view, &m->view, sizeof(MeshView));
+    return RXM_OK;
+}
+
 int rxm_mesh_launch_box(const rxm_mesh* m, int op, uint32_t* blocks, uint32_t* threads, uint32_t* smem_bytes)
 {
     if (!m) return fail(RXM_ERR_INVALID, "rxm_mesh_launch_box: null mesh");

@@ -1,0 +1,184 @@
+// tests/cpp/shim_apps.cu -- "user code" written against the reference's C++ API surface
+// (RXMeshStatic / Query::dispatch / for_each<Op> / for_each_vertex / VertexAttribute), compiled against
+// the drop-in headers in include/rxmesh/ and linked to librxmesh_b200.so.  The kernels follow the shape
+// of the reference apps (apps/VertexNormal/vertex_normal_kernel.cuh:10-43, apps/Smoothing/manual.h:86-104,
+// tests/RXMesh_test/query_kernel.cuh:13-46) so that a reader can see the same call sites compile unchanged.
+// Exposed through extern "C" so tests/test_gpu_shim.py can drive it with ctypes.
+#include <vector>
+
+#include "rxmesh/attribute.h"
+#include "rxmesh/query.h"
+#include "rxmesh/rxmesh_static.h"
+
+using namespace rxmesh;
+
+template <typename T, uint32_t blockThreads>
+__global__ static void user_vertex_normal(const Context context, VertexAttribute<T> coords, VertexAttribute<T> normals)
+{
+    auto vn_lambda = [&](FaceHandle face_id, VertexIterator& fv) {
+        (void)face_id;
+        vec3<T> c0 = coords.template to_glm<3>(fv[0]);
+        vec3<T> c1 = coords.template to_glm<3>(fv[1]);
+        vec3<T> c2 = coords.template to_glm<3>(fv[2]);
+        vec3<T> n  = cross(c1 - c0, c2 - c0);
+        vec3<T> l(glm::distance2(c0, c1), glm::distance2(c1, c2), glm::distance2(c2, c0));
+        for (uint32_t v = 0; v < 3; ++v)
+            for (uint32_t i = 0; i < 3; ++i)
+                atomicAdd(&normals(fv[v], i), n[i] / (l[v] + l[(v + 2) % 3]));
+    };
+    auto                block = cooperative_groups::this_thread_block();
+    Query<blockThreads> query(context);
+    ShmemAllocator      shrd_alloc;
+    query.template dispatch<Op::FV>(block, shrd_alloc, vn_lambda);
+}
+
+template <uint32_t blockThreads, Op op, typename InH, typename OutH, typename InA, typename OutA>
+__global__ static void user_query_kernel(const Context context, InA input, OutA output, const bool oriented)
+{
+    auto store = [&](const InH& id, const Iterator<OutH>& iter) {
+        input(id) = id;
+        for (uint32_t i = 0; i < iter.size(); ++i)
+            output(id, i) = iter[i];
+    };
+    auto                block = cooperative_groups::this_thread_block();
+    Query<blockThreads> query(context);
+    ShmemAllocator      shrd_alloc;
+    query.template dispatch<op>(block, shrd_alloc, store, [](InH) { return true; }, oriented);
+}
+
+static std::vector<std::vector<uint32_t>> to_faces(const uint32_t* fv, uint32_t nf)
+{
+    std::vector<std::vector<uint32_t>> F(nf, std::vector<uint32_t>(3));
+    for (uint32_t f = 0; f < nf; ++f)
+        for (int i = 0; i < 3; ++i)
+            F[f][i] = fv[3 * f + i];
+    return F;
+}
+static std::vector<std::vector<float>> to_verts(const float* x, uint32_t nv)
+{
+    std::vector<std::vector<float>> V(nv, std::vector<float>(3));
+    for (uint32_t v = 0; v < nv; ++v)
+        for (int i = 0; i < 3; ++i)
+            V[v][i] = x[3 * v + i];
+    return V;
+}
+
+template <typename H, typename L>
+static void host_for_each(RXMeshStatic& rx, L f)
+{
+    if constexpr (std::is_same_v<H, VertexHandle>) rx.for_each_vertex(HOST, f, NULL, false);
+    if constexpr (std::is_same_v<H, EdgeHandle>) rx.for_each_edge(HOST, f, NULL, false);
+    if constexpr (std::is_same_v<H, FaceHandle>) rx.for_each_face(HOST, f, NULL, false);
+}
+
+// the query test (tests/RXMesh_test/test_queries.h:98-219) for one op; out_global: [num_src][width] global ids of
+// the output handles (0xFFFFFFFF = invalid), rows in GLOBAL source order; returns -1 on a failed invariant
+template <Op op, typename InH, typename OutH>
+static int run_query(RXMeshStatic& rx, uint32_t width, bool oriented, uint32_t* out_global)
+{
+    constexpr uint32_t blockThreads = 256;
+    auto input  = rx.add_attribute<InH, InH>("input", 1);
+    auto output = rx.add_attribute<OutH, InH>("output", width);
+    input->reset(InH(), DEVICE);
+    output->reset(OutH(), DEVICE);
+    LaunchBox<blockThreads> lb;
+    auto kern = user_query_kernel<blockThreads, op, InH, OutH, Attribute<InH, InH>, Attribute<OutH, InH>>;
+    rx.prepare_launch_box({op}, lb, (void*)kern, oriented);
+    kern<<<lb.blocks, blockThreads, lb.smem_bytes_dyn>>>(rx.get_context(), *input, *output, oriented);
+    if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+    input->move(DEVICE, HOST);
+    output->move(DEVICE, HOST);
+    int bad = 0;
+    host_for_each<InH>(rx, [&](const InH& h) {
+        if ((*input)(h) != h) bad = 1;
+        const uint32_t g = rx.map_to_global(h);
+        for (uint32_t i = 0; i < width; ++i) {
+            OutH o = (*output)(h, i);
+            out_global[(size_t)g * width + i] = o.is_valid() ? rx.map_to_global(o) : 0xFFFFFFFFu;
+        }
+    });
+    rx.remove_attribute("input");
+    rx.remove_attribute("output");
+    return bad ? -1 : 0;
+}
+
+extern "C" {
+
+// the VertexNormal app (apps/VertexNormal/vertex_normal.cu:28-110), RXMesh path
+int shim_vertex_normals(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, float* out)
+{
+    rx_init(0);
+    RXMeshStatic rx(to_faces(fv, nf), {}, patch_size);
+    constexpr uint32_t blockThreads = 256;
+    auto coords    = rx.add_vertex_attribute<float>(to_verts(x, nv), "coordinates");
+    auto v_normals = rx.add_vertex_attribute<float>("v_normals", 3, LOCATION_ALL);
+    LaunchBox<blockThreads> launch_box;
+    rx.prepare_launch_box({Op::FV}, launch_box, (void*)user_vertex_normal<float, blockThreads>);
+    v_normals->reset(0, DEVICE);
+    user_vertex_normal<float, blockThreads><<<launch_box.blocks, launch_box.num_threads, launch_box.smem_bytes_dyn>>>(
+        rx.get_context(), *coords, *v_normals);
+    if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+    v_normals->move(DEVICE, HOST);
+    rx.for_each_vertex(HOST, [&](const VertexHandle& vh) {
+        const uint32_t v_id = rx.map_to_global(vh);
+        for (uint32_t i = 0; i < 3; ++i)
+            out[v_id * 3 + i] = (*v_normals)(vh, i);
+    });
+    return 0;
+}
+
+// manual smoothing (apps/Smoothing/manual.h:86-104): for_each<Op::VV> gradient + for_each_vertex(DEVICE) step
+int shim_smoothing(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, double lr,
+                   int num_iter, int oriented, float* out)
+{
+    rx_init(0);
+    RXMeshStatic rx(to_faces(fv, nf), {}, patch_size);
+    constexpr int blockThreads = 256;
+    auto pos  = *rx.add_vertex_attribute<float>(to_verts(x, nv), "pos");
+    auto grad = *rx.add_vertex_attribute<float>("grad", 3, LOCATION_ALL);
+    const int cols = pos.get_num_attributes();
+    for (int iter = 0; iter < num_iter; ++iter) {
+        grad.reset(0, DEVICE);
+        rx.for_each<Op::VV, blockThreads>(
+            [=] __device__(const VertexHandle& vh, const VertexIterator& iter) mutable {
+                for (int v = 0; v < iter.size(); ++v) {
+                    const VertexHandle uh = iter[v];
+                    for (int i = 0; i < cols; ++i)
+                        grad(vh, i) += 2 * (pos(vh, i) - pos(uh, i));
+                }
+            },
+            oriented != 0);
+        rx.for_each_vertex(DEVICE, [grad, pos, lr, cols] __device__(const VertexHandle& vh) {
+            for (int i = 0; i < cols; ++i)
+                pos(vh, i) -= lr * grad(vh, i);
+        });
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+    pos.move(DEVICE, HOST);
+    rx.for_each_vertex(HOST, [&](const VertexHandle& vh) {
+        const uint32_t v_id = rx.map_to_global(vh);
+        for (uint32_t i = 0; i < 3; ++i)
+            out[v_id * 3 + i] = pos(vh, i);
+    });
+    return 0;
+}
+
+int shim_query(int op, const uint32_t* fv, uint32_t nf, uint32_t patch_size, uint32_t width, int oriented,
+               uint32_t* out_global)
+{
+    rx_init(0);
+    RXMeshStatic rx(to_faces(fv, nf), {}, patch_size);
+    switch ((Op)op) {
+        case Op::VV: return run_query<Op::VV, VertexHandle, VertexHandle>(rx, width, oriented, out_global);
+        case Op::VE: return run_query<Op::VE, VertexHandle, EdgeHandle>(rx, width, oriented, out_global);
+        case Op::VF: return run_query<Op::VF, VertexHandle, FaceHandle>(rx, width, oriented, out_global);
+        case Op::EV: return run_query<Op::EV, EdgeHandle, VertexHandle>(rx, width, oriented, out_global);
+        case Op::EF: return run_query<Op::EF, EdgeHandle, FaceHandle>(rx, width, oriented, out_global);
+        case Op::FV: return run_query<Op::FV, FaceHandle, VertexHandle>(rx, width, oriented, out_global);
+        case Op::FE: return run_query<Op::FE, FaceHandle, EdgeHandle>(rx, width, oriented, out_global);
+        case Op::FF: return run_query<Op::FF, FaceHandle, FaceHandle>(rx, width, oriented, out_global);
+        default: return 2;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+"""Drop-in check: "user code" written against the reference's C++ API (tests/cpp/shim_apps.cu --
+RXMeshStatic, Query::dispatch with device lambdas, for_each<Op::VV>, for_each_vertex(DEVICE),
+VertexAttribute::operator()) compiled against include/rxmesh/ and run on the GPU, vs the oracle."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import rxmesh_b200 as rx
+from conftest import ROOT, make_mesh
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+SO = os.path.join(ROOT, "tests", "cpp", "libshim_apps.so")
+
+
+@pytest.fixture(scope="module")
+def shim():
+    if not os.path.exists(SO):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")])
+    rx.lib()  # librxmesh_b200.so first (rpath also finds it)
+    return C.CDLL(SO)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.mark.parametrize("name", ["sphere3", "dragon", "bunnyhead"])
+def test_user_vertex_normal_kernel(shim, name):
+    V, F = make_mesh(name)
+    out = np.zeros_like(V)
+    assert shim.shim_vertex_normals(_p(F), F.shape[0], _p(V), V.shape[0], 512, _p(out)) == 0
+    ref = O.vertex_normals(F, V, np.float64)
+    rel = np.linalg.norm(out - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert rel.max() < 1e-5
+    # the app's own check (apps/VertexNormal/vertex_normal.cu:93-104)
+    assert np.abs(np.abs(out) - np.abs(O.vertex_normals(F, V, np.float32))).max() < 1e-4
+
+
+@pytest.mark.parametrize("name,oriented", [("sphere3", 0), ("torus", 0), ("torus", 1), ("grid40x31", 1)])
+def test_user_smoothing_lambdas(shim, name, oriented):
+    V, F = make_mesh(name)
+    out = np.zeros_like(V)
+    iters, lr = 4, 0.01
+    assert shim.shim_smoothing(_p(F), F.shape[0], _p(V), V.shape[0], 256, C.c_double(lr), iters, oriented, _p(out)) == 0
+    T = O.Topology(F)
+    ref = V.astype(np.float64)
+    for _ in range(iters):
+        ref = O.laplacian_step(T.query("VV"), ref, lr, np.float64)
+    assert np.abs(out - ref).max() < 1e-5 * np.abs(V).max() * iters
+
+
+@pytest.mark.parametrize("op", ["VV", "VE", "VF", "EV", "EF", "FV", "FE", "FF"])
+def test_user_query_kernel(shim, op):
+    V, F = make_mesh("dragon")
+    T = O.Topology(F)
+    s = T.stats()
+    width = {"EV": 2, "FV": 3, "FE": 3, "EF": s["max_edge_incident_faces"],
+             "FF": s["max_face_adjacent_faces"] + 2}.get(op, s["max_valence"])
+    n_src = {"V": T.nv, "E": T.ne, "F": T.nf}[op[0]]
+    out = np.zeros((n_src, width), dtype=np.uint32)
+    assert shim.shim_query(int(rx.Op[op]), _p(F), F.shape[0], 512, width, 0, _p(out)) == 0
+    off, val = T.query(op)
+    for g in range(n_src):
+        got = out[g][out[g] != 0xFFFFFFFF]
+        want = val[off[g]:off[g + 1]]
+        if op in ("EV", "FV", "FE"):
+            assert np.array_equal(got, want), (op, g)
+        else:
+            assert np.array_equal(np.sort(got), np.sort(want)), (op, g)
+
+
+def test_oriented_vv(shim):
+    # oriented VV (tests/RXMesh_test/test_queries_oriented.cu): consecutive neighbours span a face with v
+    V, F = make_mesh("torus")
+    T = O.Topology(F)
+    width = T.stats()["max_valence"]
+    out = np.zeros((T.nv, width), dtype=np.uint32)
+    assert shim.shim_query(int(rx.Op.VV), _p(F), F.shape[0], 512, width, 1, _p(out)) == 0
+    faces = {tuple(int(x) for x in np.roll(f, -k)) for f in F for k in range(3)}
+    vv = O.csr_to_sets(T.query("VV"))
+    for v in range(T.nv):
+        ring = [int(u) for u in out[v] if u != 0xFFFFFFFF]
+        assert tuple(sorted(ring)) == vv[v]
+        assert all((v, a, b) in faces for a, b in zip(ring, ring[1:] + ring[:1]))  # closed mesh: cyclic
