@@ -4,6 +4,7 @@
 #pragma once
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <string>
 #include <vector>
@@ -39,13 +40,16 @@ class Attribute : public AttributeBase
     Attribute()      = default;
 
     // created by RXMeshStatic::add_*_attribute
+    // Like the reference's Attribute (attribute.h:194) this object is a SHALLOW, trivially copyable view:
+    // raw pointers only, so that copies captured by device lambdas / passed to kernels are plain memcpy.
+    // The storage is owned by RXMeshStatic's container and freed by release().
     Attribute(rxm_mesh* mesh, const char* name, uint32_t num_attributes, locationT location, layoutT layout)
-        : m_name(name), m_nattr(num_attributes), m_layout(layout), m_location(location)
+        : m_nattr(num_attributes), m_layout(layout), m_location(location)
     {
         static_assert(sizeof(T) == 1 || sizeof(T) == 2 || sizeof(T) == 4 || sizeof(T) == 8, "unsupported attribute type");
+        m_name = strdup(name);
         rxm_attr* a = nullptr;
         detail::rxm_check(rxm_attr_create(mesh, HandleT::elem, sizeof(T), num_attributes, (int)location, (int)layout, &a));
-        m_owner        = std::shared_ptr<rxm_attr>(a, [](rxm_attr* p) { rxm_attr_destroy(p); });
         m_attr         = a;
         m_h            = (T*)rxm_attr_data(a, RXM_HOST);
         m_d            = (T*)rxm_attr_data(a, RXM_DEVICE);
@@ -55,7 +59,7 @@ class Attribute : public AttributeBase
     }
     Attribute(const Attribute&) = default;  // shallow, like the reference (attribute.h:194)
 
-    const char* get_name() const override { return m_name.c_str(); }
+    const char* get_name() const override { return m_name; }
     __host__ __device__ uint32_t  get_num_attributes() const { return m_nattr; }
     __host__ __device__ layoutT   get_layout() const { return m_layout; }
     __host__ __device__ locationT get_allocated() const { return m_location; }
@@ -71,7 +75,12 @@ class Attribute : public AttributeBase
     {
         detail::rxm_check(rxm_attr_copy_from(m_attr, source.m_attr, (int)source_flag, (int)dst_flag, stream));
     }
-    void release(locationT = LOCATION_ALL) override { m_owner.reset(); m_attr = nullptr; m_h = nullptr; m_d = nullptr; }
+    void release(locationT = LOCATION_ALL) override
+    {
+        if (m_attr) rxm_attr_destroy(m_attr);
+        free(m_name);
+        m_attr = nullptr, m_h = nullptr, m_d = nullptr, m_name = nullptr;
+    }
 
     // Attribute::operator()(handle, attr) (attribute.h:313-319,406-434)
     __host__ __device__ __forceinline__ T& operator()(const HandleT handle, const uint32_t attr = 0) const
@@ -103,8 +112,7 @@ class Attribute : public AttributeBase
         if (m_layout == SoA) return (uint64_t)a * m_num_slots + b + lid;
         return (uint64_t)b * m_nattr + (uint64_t)a * (sb[p + 1] - b) + lid;
     }
-    std::string               m_name;
-    std::shared_ptr<rxm_attr> m_owner;
+    char*                     m_name = nullptr;
     rxm_attr*                 m_attr = nullptr;
     T *                       m_h = nullptr, *m_d = nullptr;
     const uint32_t *          m_h_slot_base = nullptr, *m_d_slot_base = nullptr;

@@ -17,6 +17,14 @@ namespace rxmesh {
 inline void rx_init(int device_id = 0) { detail::rxm_check(rxm_init(device_id)); }  // rxmesh.h:23-30
 
 namespace detail {
+inline void check_launch(const char* what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {  // CUDA_ERROR semantics (util/macros.h:77-89)
+        fprintf(stderr, "rxmesh_b200: %s launch failed: %s\n", what, cudaGetErrorString(e));
+        exit(EXIT_FAILURE);
+    }
+}
 // detail::query_kernel (kernels/query_kernel.cuh:12-24)
 template <uint32_t blockThreads, Op op, typename LambdaT>
 __global__ static void query_kernel(const Context context, const bool oriented, LambdaT user_lambda)
@@ -166,6 +174,7 @@ class RXMeshStatic
         LaunchBox<blockThreads> lb;
         prepare_launch_box({op}, lb, (void*)detail::query_kernel<blockThreads, op, LambdaT>, oriented);
         detail::query_kernel<blockThreads, op><<<lb.blocks, lb.num_threads, lb.smem_bytes_dyn, stream>>>(m_context, oriented, user_lambda);
+        detail::check_launch("for_each<Op>");
     }
 
     // ---- prepare_launch_box (rxmesh_static.inl:443-496) ----
@@ -212,7 +221,12 @@ class RXMeshStatic
             fprintf(stderr, "rxmesh_b200: attribute %s already exists\n", name.c_str());  // RXMESH_ERROR: log, continue
             return std::dynamic_pointer_cast<AttrT>(m_attrs[name]);
         }
-        auto a        = std::make_shared<AttrT>(m_mesh, name.c_str(), n, location, layout);
+        // the container owns the storage (AttributeContainer, attribute.h:676-731): released when the last
+        // shared_ptr goes, i.e. at remove_attribute / ~RXMeshStatic unless the user still holds one
+        std::shared_ptr<AttrT> a(new AttrT(m_mesh, name.c_str(), n, location, layout), [](AttrT* p) {
+            p->release();
+            delete p;
+        });
         m_attrs[name] = a;
         return a;
     }
@@ -235,6 +249,7 @@ class RXMeshStatic
         if ((location & DEVICE) == DEVICE) {
             if constexpr (is_d || is_hd) {
                 detail::for_each_kernel<HandleT><<<get_num_patches(), 256, 0, stream>>>(m_context, apply);
+                detail::check_launch("for_each_vertex/edge/face");
             } else {
                 fprintf(stderr, "RXMeshStatic::for_each_*() Input lambda function should be annotated with __device__ "
                                 "for execution on device\n");

@@ -71,6 +71,29 @@ static void host_for_each(RXMeshStatic& rx, L f)
     if constexpr (std::is_same_v<H, FaceHandle>) rx.for_each_face(HOST, f, NULL, false);
 }
 
+// vertex valence through for_each<Op::VV> + a step through for_each_vertex(DEVICE) (both lambda paths)
+// (nvcc: extended __device__ lambdas must not be defined inside extern "C" functions, so the apps are
+// plain C++ functions and the extern "C" entry points at the bottom only forward)
+static int app_valence(const uint32_t* fv, uint32_t nf, uint32_t patch_size, float* out_valence, float* out_plus1)
+{
+    rx_init(0);
+    RXMeshStatic rx(to_faces(fv, nf), {}, patch_size);
+    auto val = *rx.add_vertex_attribute<float>("val", 1, LOCATION_ALL);
+    auto one = *rx.add_vertex_attribute<float>("one", 1, LOCATION_ALL);
+    val.reset(-1.f, DEVICE);
+    one.reset(0.f, DEVICE);
+    rx.for_each<Op::VV, 256>([=] __device__(const VertexHandle& vh, const VertexIterator& iter) mutable { val(vh) = iter.size(); });
+    rx.for_each_vertex(DEVICE, [val, one] __device__(const VertexHandle& vh) { one(vh) = val(vh) + 1.f; });
+    if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+    val.move(DEVICE, HOST);
+    one.move(DEVICE, HOST);
+    rx.for_each_vertex(HOST, [&](const VertexHandle& vh) {
+        out_valence[rx.map_to_global(vh)] = val(vh);
+        out_plus1[rx.map_to_global(vh)]   = one(vh);
+    });
+    return 0;
+}
+
 // the query test (tests/RXMesh_test/test_queries.h:98-219) for one op; out_global: [num_src][width] global ids of
 // the output handles (0xFFFFFFFF = invalid), rows in GLOBAL source order; returns -1 on a failed invariant
 template <Op op, typename InH, typename OutH>
@@ -102,10 +125,8 @@ static int run_query(RXMeshStatic& rx, uint32_t width, bool oriented, uint32_t* 
     return bad ? -1 : 0;
 }
 
-extern "C" {
-
 // the VertexNormal app (apps/VertexNormal/vertex_normal.cu:28-110), RXMesh path
-int shim_vertex_normals(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, float* out)
+static int app_vertex_normals(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, float* out)
 {
     rx_init(0);
     RXMeshStatic rx(to_faces(fv, nf), {}, patch_size);
@@ -128,8 +149,8 @@ int shim_vertex_normals(const uint32_t* fv, uint32_t nf, const float* x, uint32_
 }
 
 // manual smoothing (apps/Smoothing/manual.h:86-104): for_each<Op::VV> gradient + for_each_vertex(DEVICE) step
-int shim_smoothing(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, double lr,
-                   int num_iter, int oriented, float* out)
+static int app_smoothing(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, double lr,
+                         int num_iter, int oriented, float* out)
 {
     rx_init(0);
     RXMeshStatic rx(to_faces(fv, nf), {}, patch_size);
@@ -163,8 +184,8 @@ int shim_smoothing(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv,
     return 0;
 }
 
-int shim_query(int op, const uint32_t* fv, uint32_t nf, uint32_t patch_size, uint32_t width, int oriented,
-               uint32_t* out_global)
+static int app_query(int op, const uint32_t* fv, uint32_t nf, uint32_t patch_size, uint32_t width, int oriented,
+                     uint32_t* out_global)
 {
     rx_init(0);
     RXMeshStatic rx(to_faces(fv, nf), {}, patch_size);
@@ -181,4 +202,22 @@ int shim_query(int op, const uint32_t* fv, uint32_t nf, uint32_t patch_size, uin
     }
 }
 
+extern "C" {
+int shim_vertex_normals(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, float* out)
+{
+    return app_vertex_normals(fv, nf, x, nv, patch_size, out);
+}
+int shim_smoothing(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, double lr, int num_iter,
+                   int oriented, float* out)
+{
+    return app_smoothing(fv, nf, x, nv, patch_size, lr, num_iter, oriented, out);
+}
+int shim_valence(const uint32_t* fv, uint32_t nf, uint32_t patch_size, float* out_valence, float* out_plus1)
+{
+    return app_valence(fv, nf, patch_size, out_valence, out_plus1);
+}
+int shim_query(int op, const uint32_t* fv, uint32_t nf, uint32_t patch_size, uint32_t width, int oriented, uint32_t* out_global)
+{
+    return app_query(op, fv, nf, patch_size, width, oriented, out_global);
+}
 }  // extern "C"

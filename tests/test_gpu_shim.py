@@ -40,6 +40,16 @@ def test_user_vertex_normal_kernel(shim, name):
     assert np.abs(np.abs(out) - np.abs(O.vertex_normals(F, V, np.float32))).max() < 1e-4
 
 
+def test_user_for_each_lambdas(shim):
+    V, F = make_mesh("sphere3")
+    T = O.Topology(F)
+    a, b = np.zeros(T.nv, np.float32), np.zeros(T.nv, np.float32)
+    assert shim.shim_valence(_p(F), F.shape[0], 256, _p(a), _p(b)) == 0
+    off, _ = T.query("VV")
+    assert np.array_equal(a, np.diff(off.astype(np.int64)).astype(np.float32))
+    assert np.array_equal(b, a + 1)
+
+
 @pytest.mark.parametrize("name,oriented", [("sphere3", 0), ("torus", 0), ("torus", 1), ("grid40x31", 1)])
 def test_user_smoothing_lambdas(shim, name, oriented):
     V, F = make_mesh(name)
