@@ -162,6 +162,11 @@ int rxm_laplacian_smooth(rxm_mesh* m, rxm_attr* in, rxm_attr* out, double lr, ui
 /* bilateral filtering (apps/Filtering/filtering_rxmesh.cuh:75-95): `iters` iterations of
  * unit-face vertex normals + bilateral_filtering; result in `out`. */
 int rxm_bilateral_filter(rxm_mesh* m, rxm_attr* in, rxm_attr* out, uint32_t iters, void* stream);
+/* Materialise a query as a CSR over attribute SLOTS on the device (cached in the mesh): off[num_slots(src)+1],
+ * val[nnz] = owner slots of the neighbours, lists grouped by patch. The k-ring consumer (bilateral filtering)
+ * traverses this instead of re-running whole-patch queries per foreign patch like the reference's
+ * higher_query_block_dispatcher (kernels/query_dispatcher.cuh:445-565). Pointers are device pointers owned by m. */
+int rxm_query_csr(rxm_mesh* m, int op, uint32_t** dev_off, uint32_t** dev_val, uint64_t* nnz, void* stream);
 /* get_boundary_vertices (rxmesh_static.h; kernels/boundary.cuh:11-44): flag: 1 x u32 vertex attribute, 1 = boundary */
 int rxm_boundary_vertices(rxm_mesh* m, rxm_attr* flag, void* stream);
 
@@ -180,6 +185,7 @@ int rxm_mesh_set_active_patches(rxm_mesh* m, uint32_t first, uint32_t count);
  * through their owner tables (= what a halo exchange must fill). *out is malloc'd: release with rxm_free. */
 int  rxm_mesh_halo_slots(const rxm_mesh* m, int elem, uint32_t first, uint32_t count, uint32_t** out, uint64_t* n);
 void rxm_free(void* p);
+int  rxm_memcpy_d2h(void* host, const void* dev, uint64_t bytes); /* read back a device array the library owns */
 /* pack / unpack rows of an AoS attribute through a device index list (device buffers) */
 int rxm_attr_gather_slots(rxm_attr* a, const uint32_t* dev_idx, uint64_t n, void* dev_out, void* stream);
 int rxm_attr_scatter_slots(rxm_attr* a, const uint32_t* dev_idx, uint64_t n, const void* dev_in, void* stream);

@@ -61,6 +61,8 @@ SYMBOLS = {
     "rxm_laplacian_smooth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_uint32,
                                        C.c_void_p]),
     "rxm_bilateral_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "rxm_query_csr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                C.POINTER(C.c_uint64), C.c_void_p]),
     "rxm_boundary_vertices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "rxm_vertex_normals_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rxm_laplacian_smooth_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
@@ -70,6 +72,7 @@ SYMBOLS = {
     "rxm_mesh_halo_slots": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(u32p),
                                       C.POINTER(C.c_uint64)]),
     "rxm_free": (None, [C.c_void_p]),
+    "rxm_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "rxm_attr_gather_slots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "rxm_attr_scatter_slots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "rxm_attr_push_slots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),

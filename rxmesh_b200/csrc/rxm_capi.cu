@@ -46,6 +46,13 @@ struct rxm_mesh
     void*     d_stage       = nullptr;
     size_t    d_stage_bytes = 0;
     rxm_attr* scratch[4]    = {nullptr, nullptr, nullptr, nullptr};
+    struct Csr
+    {
+        uint32_t *off = nullptr, *val = nullptr;
+        uint64_t  nnz = 0;
+    };
+    Csr       csr[16];      // materialised queries (rxm_query_csr), indexed by op
+    uint32_t* d_flag = nullptr;
     rxm_attr* scratch1[6]   = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -184,6 +191,11 @@ void rxm_mesh_destroy(rxm_mesh* m)
             cudaFree(m->d_s2g[t]);
         }
         if (m->d_stage) cudaFree(m->d_stage);
+        if (m->d_flag) cudaFree(m->d_flag);
+        for (auto& c : m->csr) {
+            if (c.off) cudaFree(c.off);
+            if (c.val) cudaFree(c.val);
+        }
     }
     delete m;
 }
@@ -651,12 +663,99 @@ int rxm_laplacian_smooth(rxm_mesh* m, rxm_attr* in, rxm_attr* out, double lr, ui
     return RXM_OK;
 }
 
+// number of list entries a patch contributes to the CSR of `op` (owned sources only), from the stored offsets
+static uint32_t patch_nnz(const HostMesh& h, uint32_t p, int op)
+{
+    const PatchDesc& D = h.desc[p];
+    const uint8_t*   B = h.topo.data() + D.topo_off;
+    auto u16 = [&](uint32_t off, uint32_t i) { return (uint32_t) reinterpret_cast<const uint16_t*>(B + off)[i]; };
+    switch (op) {
+        case RXM_OP_VV: case RXM_OP_VE: return u16(D.off_voff_e(), D.n_owned[ELEM_V]);
+        case RXM_OP_VF: return u16(D.off_voff_f(), D.n_owned[ELEM_V]);
+        case RXM_OP_EF: return u16(D.off_eoff_f(), D.n_owned[ELEM_E]);
+        case RXM_OP_EV: return 2u * D.n_owned[ELEM_E];
+        case RXM_OP_FV: case RXM_OP_FE: return 3u * D.n_owned[ELEM_F];
+        case RXM_OP_FF: {
+            const uint16_t* fe = reinterpret_cast<const uint16_t*>(B + D.off_fe());
+            const uint32_t  em = (D.flags & FLAG_PACKED) ? PK_ID_MASK : 0x7FFFu;
+            uint32_t        k  = 0;
+            for (uint32_t i = 0; i < 3u * D.n_owned[ELEM_F]; ++i) {
+                const uint32_t e = (fe[i] >> 1) & em;
+                k += u16(D.off_eoff_f(), e + 1) - u16(D.off_eoff_f(), e) - 1;
+            }
+            return k;
+        }
+        default: return 0;
+    }
+}
+
+int rxm_query_csr(rxm_mesh* m, int op, uint32_t** dev_off, uint32_t** dev_val, uint64_t* nnz, void* stream)
+{
+    int rc = check_dev(m, "rxm_query_csr");
+    if (rc) return rc;
+    if (op_src(op) < 0 || !dev_off || !dev_val || !nnz) return fail(RXM_ERR_INVALID, "rxm_query_csr: bad argument");
+    if (m->active_count && m->active_count != m->h.num_patches)
+        return fail(RXM_ERR_UNSUPPORTED, "rxm_query_csr: not available on a shard (active patch range set)");
+    auto& C = m->csr[op];
+    if (!C.off) {
+        const HostMesh&       h = m->h;
+        std::vector<uint32_t> pno(h.num_patches + 1, 0);
+        uint64_t              run = 0;
+        for (uint32_t p = 0; p < h.num_patches; ++p) {
+            pno[p] = (uint32_t)run;
+            run += patch_nnz(h, p, op);
+        }
+        if (run > 0xFFFFFFFFull) return fail(RXM_ERR_UNSUPPORTED, "rxm_query_csr: more than 2^32 entries");
+        pno[h.num_patches] = (uint32_t)run;
+        const uint32_t ns  = h.num_slots[op_src(op)];
+        uint32_t*      d_pno = nullptr;
+        CU(cudaMalloc(&d_pno, pno.size() * 4));
+        CU(cudaMemcpyAsync(d_pno, pno.data(), pno.size() * 4, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        CU(cudaMalloc(&C.off, ((size_t)ns + 1) * 4));
+        CU(cudaMalloc(&C.val, std::max<size_t>(run, 1) * 4));
+        const char* why = nullptr;
+        cudaError_t e   = launch_query_csr(op, m->view, m->lim, d_pno, C.off, C.val, (cudaStream_t)stream, &why);
+        if (e != cudaSuccess) return kernel_status(e, why, "rxm_query_csr");
+        const uint32_t total = (uint32_t)run;
+        CU(cudaMemcpyAsync(C.off + ns, &total, 4, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        CU(cudaStreamSynchronize((cudaStream_t)stream));
+        CU(cudaFree(d_pno));
+        C.nnz = run;
+    }
+    *dev_off = C.off, *dev_val = C.val, *nnz = C.nnz;
+    return RXM_OK;
+}
+
 int rxm_bilateral_filter(rxm_mesh* m, rxm_attr* in, rxm_attr* out, uint32_t iters, void* stream)
 {
-    (void)in, (void)out, (void)iters, (void)stream;
     int rc = check_dev(m, "rxm_bilateral_filter");
     if (rc) return rc;
-    return fail(RXM_ERR_UNSUPPORTED, "rxm_bilateral_filter: not built yet");
+    if (!is_vec3_aos(in) || !is_vec3_aos(out) || in == out)
+        return fail(RXM_ERR_INVALID, "rxm_bilateral_filter: in/out must be distinct device 3 x fp32 AoS vertex attributes");
+    if (iters == 0) return rxm_attr_copy_from(out, in, RXM_DEVICE, RXM_DEVICE, stream);
+    uint32_t *off = nullptr, *val = nullptr;
+    uint64_t  nnz = 0;
+    if ((rc = rxm_query_csr(m, RXM_OP_VV, &off, &val, &nnz, stream))) return rc;
+    rxm_attr *nrm = nullptr, *tmp = nullptr;
+    if ((rc = get_scratch(m, 3, &nrm))) return rc;
+    if (iters > 1 && (rc = get_scratch(m, 0, &tmp))) return rc;
+    if (!m->d_flag) CU(cudaMalloc(&m->d_flag, 4));
+    CU(cudaMemsetAsync(m->d_flag, 0, 4, (cudaStream_t)stream));
+    rxm_attr* src = in;
+    for (uint32_t k = 1; k <= iters; ++k) {
+        rxm_attr* dst = ((iters - k) % 2 == 0) ? out : tmp;
+        // filtering_rxmesh.cuh:75-95: vertex normals of the current positions, then the filter
+        if ((rc = rxm_vertex_normals(m, src, nrm, 1, stream))) return rc;
+        cudaError_t e = launch_bilateral_step(off, val, m->h.num_slots[ELEM_V], (const float*)src->d, (const float*)nrm->d,
+                                              (float*)dst->d, m->d_flag, (cudaStream_t)stream);
+        if (e != cudaSuccess) return fail(RXM_ERR_CUDA, std::string("bilateral: ") + cudaGetErrorString(e));
+        src = dst;
+    }
+    uint32_t flag = 0;
+    CU(cudaMemcpyAsync(&flag, m->d_flag, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    if (flag) return fail(RXM_ERR_UNSUPPORTED, "rxm_bilateral_filter: a neighbourhood exceeded 80 vertices (maxVVSize of the reference)");
+    return RXM_OK;
 }
 
 int rxm_boundary_vertices(rxm_mesh* m, rxm_attr* flag, void* stream)
@@ -753,6 +852,12 @@ int rxm_mesh_halo_slots(const rxm_mesh* m, int elem, uint32_t first, uint32_t co
         if (mark[s]) r[j++] = s;
     *out = r;
     *n   = k;
+    return RXM_OK;
+}
+
+int rxm_memcpy_d2h(void* host, const void* dev, uint64_t bytes)
+{
+    CU(cudaMemcpy(host, dev, bytes, cudaMemcpyDeviceToHost));
     return RXM_OK;
 }
 

@@ -756,6 +756,120 @@ struct VFConsumeWorker
 };
 
 // --------------------------------------------------------------------------
+// query -> materialised CSR in slot space (patch-grouped): off[slot], val = owner slots
+// --------------------------------------------------------------------------
+template <int OP, int KMAX, bool PACKED>
+__global__ void __launch_bounds__(BT) k_query_csr(MeshView mv, const uint32_t* __restrict__ patch_nnz_off,
+                                                  uint32_t* __restrict__ csr_off, uint32_t* __restrict__ csr_val)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint64_t                      bar;
+    __shared__ uint32_t                      warp_tmp[36];
+    using Q = PatchQuery<OP, BT, KMAX, PACKED>;
+    constexpr uint32_t S = OpTraits<OP>::src;
+    const uint32_t  p    = blockIdx.x;
+    const PatchDesc d    = load_desc(mv.desc + p);
+    const uint8_t*  blob = mv.topo + d.topo_off;
+    Smem            sm(smem_raw);
+    Q               q;
+    q.plan(d, sm, true, false);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(&bar, q.tx_bytes(d, true));
+        q.issue(d, blob, &bar, true);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    const QueryResult r    = q.compute(d, warp_tmp, false, true);
+    const OwnerTable  ot   = q.owner_table(d);
+    const uint32_t    base = patch_nnz_off[d.patch_id];
+    const uint32_t    cap  = d.slot_cap(S), sb = d.slot_base[S];
+    const uint32_t    tot  = r.n_src ? r.end(r.n_src - 1) : 0u;
+    for (uint32_t s = threadIdx.x; s < cap; s += BT)
+        csr_off[sb + s] = base + (s < r.n_src ? r.begin(s) : tot);  // padding slots: empty lists
+    for (uint32_t s = threadIdx.x; s < r.n_src; s += BT) {
+        const uint32_t b = r.begin(s), e = r.end(s);
+        for (uint32_t i = b; i < e; ++i)
+            csr_val[base + i] = ot.slot(r.at(i));
+    }
+}
+
+// --------------------------------------------------------------------------
+// bilateral mesh denoising on the materialised VV CSR (one thread per owned vertex slot)
+// apps/Filtering/filtering_rxmesh_kernel.cuh:426-548 (+ 52-85, filtering_util.h:8-59)
+// --------------------------------------------------------------------------
+constexpr int BILATERAL_MAX_VV = 80;  // maxVVSize of the reference (filtering_rxmesh.cuh)
+
+__global__ void __launch_bounds__(128) k_bilateral(const uint32_t* __restrict__ off, const uint32_t* __restrict__ val,
+                                                   const float* __restrict__ x, const float* __restrict__ nrm,
+                                                   float* __restrict__ xo, uint32_t num_slots, uint32_t* __restrict__ overflow)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= num_slots) return;
+    const uint32_t b = off[s], e = off[s + 1];
+    const float    px = x[3ull * s], py = x[3ull * s + 1], pz = x[3ull * s + 2];
+    if (b == e) {  // padding slot
+        xo[3ull * s] = px, xo[3ull * s + 1] = py, xo[3ull * s + 2] = pz;
+        return;
+    }
+    float nx = nrm[3ull * s], ny = nrm[3ull * s + 1], nz = nrm[3ull * s + 2];
+    {
+        const float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
+        nx *= inv, ny *= inv, nz *= inv;
+    }
+    auto dist2 = [&](uint32_t u) {
+        const float dx = x[3ull * u] - px, dy = x[3ull * u + 1] - py, dz = x[3ull * u + 2] - pz;
+        return dx * dx + dy * dy + dz * dz;
+    };
+    float sc2 = 1e10f;
+    for (uint32_t i = b; i < e; ++i)
+        sc2 = fminf(sc2, dist2(val[i]));
+    const float radius = 4.0f * sc2;
+    uint32_t    vv[BILATERAL_MAX_VV];
+    uint32_t    cnt = 1;
+    vv[0]           = s;
+    for (uint32_t head = 0; head < cnt; ++head) {
+        const uint32_t w = vv[head];
+        for (uint32_t i = off[w]; i < off[w + 1]; ++i) {
+            const uint32_t u = val[i];
+            if (u == s) continue;
+            bool dup = false;
+            for (uint32_t k = 0; k < cnt; ++k)
+                dup |= (vv[k] == u);
+            if (dup) continue;
+            if (dist2(u) <= radius) {
+                if (cnt < BILATERAL_MAX_VV)
+                    vv[cnt++] = u;
+                else
+                    *overflow = 1u;  // the reference asserts here
+            }
+        }
+    }
+    float sum = 0.f, sum_sq = 0.f;
+    for (uint32_t k = 0; k < cnt; ++k) {
+        const uint32_t u = vv[k];
+        float h = (x[3ull * u] - px) * nx + (x[3ull * u + 1] - py) * ny + (x[3ull * u + 2] - pz) * nz;
+        h = fabsf(h);
+        sum += h, sum_sq += h * h;
+    }
+    const float c   = (float)cnt;
+    float       ss2 = sum_sq / c - (sum * sum) / (c * c);
+    if (ss2 < 1.0e-20f) ss2 += 1.0e-20f;
+    float num = 0.f, den = 0.f;
+    for (uint32_t k = 0; k < cnt; ++k) {
+        const uint32_t u  = vv[k];
+        const float    qx = x[3ull * u] - px, qy = x[3ull * u + 1] - py, qz = x[3ull * u + 2] - pz;
+        const float    t2 = qx * qx + qy * qy + qz * qz;
+        const float    h  = qx * nx + qy * ny + qz * nz;
+        const float    wc = expf(-0.5f * t2 / sc2), ws = expf(-0.5f * h * h / ss2);
+        num += wc * ws * h, den += wc * ws;
+    }
+    const float k = num / den;
+    xo[3ull * s] = px + nx * k, xo[3ull * s + 1] = py + ny * k, xo[3ull * s + 2] = pz + nz * k;
+}
+
+// --------------------------------------------------------------------------
 // boundary vertices: an edge with one incident face marks its two vertices
 // --------------------------------------------------------------------------
 template <int KMAX, bool PACKED>
@@ -1197,10 +1311,32 @@ cudaError_t launch_boundary_vertices(const MeshView& mv, const KernelLimits& lim
     return cudaGetLastError();
 }
 
-cudaError_t launch_bilateral_step(const MeshView&, const KernelLimits&, const float*, const float*, float*, uint32_t*,
-                                  cudaStream_t, const char** err)
+cudaError_t launch_query_csr(int op, const MeshView& mv, const KernelLimits& lim, const uint32_t* patch_nnz_off,
+                             uint32_t* csr_off, uint32_t* csr_val, cudaStream_t stream, const char** err)
 {
-    RXM_FAIL("bilateral filtering: not built yet");
+    const int km = pick_kmax(max_nnz(lim));
+    if (!km) RXM_FAIL("patch too large for the query kernels (nnz > 24*256)");
+    if (op == OP_FF && lim.max_face_adjacent_faces > 6) RXM_FAIL("FF: more than 6 adjacent faces per face");
+    uint32_t    smem = 0;
+    cudaError_t e    = cudaSuccess;
+    auto        extra_smem = [&](int) { return 0u; };
+    if (mv.packed)
+        RXM_LAUNCH_OP(k_query_csr, 1, true, mv, patch_nnz_off, csr_off, csr_val);
+    else if (km == 12)
+        RXM_LAUNCH_OP(k_query_csr, 12, false, mv, patch_nnz_off, csr_off, csr_val);
+    else
+        RXM_LAUNCH_OP(k_query_csr, 24, false, mv, patch_nnz_off, csr_off, csr_val);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bilateral_step(const uint32_t* csr_off, const uint32_t* csr_val, uint32_t num_slots, const float* x,
+                                  const float* normals, float* xo, uint32_t* overflow_flag, cudaStream_t stream)
+{
+    if (num_slots == 0) return cudaSuccess;
+    k_bilateral<<<(num_slots + 127) / 128, 128, 0, stream>>>(csr_off, csr_val, x, normals, xo, num_slots, overflow_flag);
+    ++g_launches;
+    return cudaGetLastError();
 }
 
 template <bool TO_SLOTS>

@@ -31,9 +31,13 @@ cudaError_t launch_vertex_normals(const MeshView& mv, const KernelLimits& lim, c
 cudaError_t launch_laplacian_step(const MeshView& mv, const KernelLimits& lim, const float* x_in_aos,
                                   float* x_out_aos, double lr, cudaStream_t stream, const char** err);
 
-cudaError_t launch_bilateral_step(const MeshView& mv, const KernelLimits& lim, const float* x_in_aos,
-                                  const float* normals_aos, float* x_out_aos, uint32_t* overflow_flag,
-                                  cudaStream_t stream, const char** err);
+// materialise a query as a CSR over attribute slots (patch-grouped): csr_off[num_slots(src)+1] (the last
+// entry is written by the caller), csr_val[nnz] = owner slots; patch_nnz_off[P] = first entry of every patch
+cudaError_t launch_query_csr(int op, const MeshView& mv, const KernelLimits& lim, const uint32_t* patch_nnz_off,
+                             uint32_t* csr_off, uint32_t* csr_val, cudaStream_t stream, const char** err);
+
+cudaError_t launch_bilateral_step(const uint32_t* csr_off, const uint32_t* csr_val, uint32_t num_slots, const float* x_aos,
+                                  const float* normals_aos, float* x_out_aos, uint32_t* overflow_flag, cudaStream_t stream);
 
 cudaError_t launch_boundary_vertices(const MeshView& mv, const KernelLimits& lim, uint32_t* flag_per_slot,
                                      cudaStream_t stream, const char** err);

@@ -379,6 +379,17 @@ class RXMeshStatic:
     def bilateral_filter(self, inp, out, iters=1, stream=None):
         check(lib().rxm_bilateral_filter(self._h, inp._h, out._h, int(iters), _stream_ptr(stream)))
 
+    def query_csr(self, op, stream=None):
+        """Materialised query in slot space, downloaded: (off[num_slots+1], val[nnz]) numpy arrays."""
+        off, val, nnz = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        check(lib().rxm_query_csr(self._h, int(op), C.byref(off), C.byref(val), C.byref(nnz), _stream_ptr(stream)))
+        ns = self.num_slots(_SRC[Op(op)])
+        h_off = np.empty(ns + 1, dtype=np.uint32)
+        h_val = np.empty(max(nnz.value, 1), dtype=np.uint32)
+        check(lib().rxm_memcpy_d2h(h_off.ctypes.data_as(C.c_void_p), off, 4 * (ns + 1)))
+        check(lib().rxm_memcpy_d2h(h_val.ctypes.data_as(C.c_void_p), val, 4 * nnz.value))
+        return h_off, h_val[:nnz.value]
+
     def boundary_vertices(self, flag, stream=None):
         check(lib().rxm_boundary_vertices(self._h, flag._h, _stream_ptr(stream)))
 
