@@ -8,6 +8,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -125,12 +126,34 @@ void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_
             for (int j = 0; j < 3; ++j)
                 ef_val[cur[fe[3ull * f + j]]++] = f;
     }
-    auto for_each_nbr = [&](uint32_t f, auto&& fn) {
+    // face -> adjacent faces CSR (one indirection per visit instead of face -> edge -> faces)
+    std::vector<uint32_t> ff_off((size_t)nf + 1, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t f = 0; f < (int64_t)nf; ++f) {
+        uint32_t k = 0;
+        for (int j = 0; j < 3; ++j) {
+            const uint32_t e = fe[3ull * f + j];
+            k += ef_off[e + 1] - ef_off[e] - 1;
+        }
+        ff_off[f + 1] = k;
+    }
+    for (uint32_t f = 0; f < nf; ++f)
+        ff_off[f + 1] += ff_off[f];
+    std::vector<uint32_t> ff_val(ff_off[nf]);
+#pragma omp parallel for schedule(static)
+    for (int64_t f = 0; f < (int64_t)nf; ++f) {
+        uint32_t w = ff_off[f];
         for (int j = 0; j < 3; ++j) {
             const uint32_t e = fe[3ull * f + j];
             for (uint32_t i = ef_off[e]; i < ef_off[e + 1]; ++i)
-                if (ef_val[i] != f) fn(ef_val[i]);
+                if (ef_val[i] != (uint32_t)f) ff_val[w++] = ef_val[i];
         }
+    }
+    std::vector<uint32_t>().swap(ef_off);
+    std::vector<uint32_t>().swap(ef_val);
+    auto for_each_nbr = [&](uint32_t f, auto&& fn) {
+        for (uint32_t i = ff_off[f]; i < ff_off[f + 1]; ++i)
+            fn(ff_val[i]);
     };
 
     // start near the patch count the size bound ends up needing (the reference
@@ -232,11 +255,14 @@ void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_
         return changed;
     };
 
+    int n_assign = 0, n_outer = 0;
     for (int outer = 0; outer < 64; ++outer) {
+        ++n_outer;
         assign();
         for (uint32_t it = 0; it < lloyd_iters; ++it) {
             if (!recenter()) break;
             assign();
+            ++n_assign;
         }
         // split patches that are still too large: one more seed at the face
         // farthest from the current seed
@@ -282,6 +308,9 @@ void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_
         }
     }
     num_patches = (uint32_t)seeds.size();
+    if (getenv("RXM_VERBOSE"))
+        fprintf(stderr, "[rxmesh_b200] lloyd: %d outer rounds, %d recentre+assign passes, %u patches\n", n_outer, n_assign,
+                num_patches);
 }
 
 // ---------------------------------------------------------------------------

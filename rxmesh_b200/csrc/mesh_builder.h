@@ -62,7 +62,7 @@ struct BuildOptions
     int      num_threads  = 0;     // 0 = omp default
     bool     keep_ltog    = true;  // false: drop ltog after the build (large meshes)
     bool     verbose      = false;
-    uint32_t lloyd_iters  = 8;
+    uint32_t lloyd_iters  = 5;
     bool     force_wide   = false;  // never use the packed format (tests of the atomic path)
     bool     no_fans      = false;  // never store one-ring fans (tests of the generic kernels)
 };
