@@ -197,6 +197,13 @@ int rxm_ipc_export(void* dev_ptr, void* handle64);        /* cudaIpcGetMemHandle
 int rxm_ipc_open(const void* handle64, void** dev_ptr);   /* cudaIpcOpenMemHandle */
 int rxm_ipc_close(void* dev_ptr);
 
+/* Asynchronous host calls: with rxm_set_async(1) the *_host entry points return once their H2D copy, kernels
+ * and D2H copy are ENQUEUED on `stream` (the host buffers must be pinned and stay valid); results are ready
+ * after rxm_stream_sync(stream). Calls issued on different streams overlap their copies and kernels (every
+ * entry point owns its device staging buffers). Default: synchronous. */
+void rxm_set_async(int on);
+int  rxm_stream_sync(void* stream);
+
 /* kernels launched by this library so far (bench.py "gpu_launches") */
 uint64_t rxm_launch_count(void);
 

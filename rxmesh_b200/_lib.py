@@ -79,6 +79,8 @@ SYMBOLS = {
     "rxm_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rxm_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "rxm_ipc_close": (C.c_int, [C.c_void_p]),
+    "rxm_set_async": (None, [C.c_int]),
+    "rxm_stream_sync": (C.c_int, [C.c_void_p]),
     "rxm_launch_count": (C.c_uint64, []),
 }
 

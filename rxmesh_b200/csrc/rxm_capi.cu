@@ -43,8 +43,8 @@ struct rxm_mesh
     MeshView     view{};
     KernelLimits lim{};
     // scratch for the host-buffer entry points and multi-iteration drivers
-    void*     d_stage       = nullptr;
-    size_t    d_stage_bytes = 0;
+    void*     d_stage[32]       = {};  // [0] generic; host entry points own dedicated in/out buffers
+    size_t    d_stage_bytes[32] = {};
     rxm_attr* scratch[4]    = {nullptr, nullptr, nullptr, nullptr};
     struct Csr
     {
@@ -53,7 +53,7 @@ struct rxm_mesh
     };
     Csr       csr[16];      // materialised queries (rxm_query_csr), indexed by op
     uint32_t* d_flag = nullptr;
-    rxm_attr* scratch1[6]   = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    rxm_attr* scratch1[32]  = {};  // per query op: [2*op] input, [2*op+1] output of rxm_query_consume_host
 };
 
 struct rxm_attr
@@ -190,7 +190,8 @@ void rxm_mesh_destroy(rxm_mesh* m)
             cudaFree(m->d_slot_base[t]);
             cudaFree(m->d_s2g[t]);
         }
-        if (m->d_stage) cudaFree(m->d_stage);
+        for (void* b : m->d_stage)
+            if (b) cudaFree(b);
         if (m->d_flag) cudaFree(m->d_flag);
         for (auto& c : m->csr) {
             if (c.off) cudaFree(c.off);
@@ -453,13 +454,38 @@ int rxm_attr_copy_from(rxm_attr* dst, rxm_attr* src, int source, int target, voi
     return RXM_OK;
 }
 
-static int ensure_stage(rxm_mesh* m, size_t bytes)
+static int  g_async_host_calls = 0;  // rxm_set_async
+
+static int ensure_stage(rxm_mesh* m, size_t bytes, int k = 0)
 {
-    if (m->d_stage_bytes >= bytes) return RXM_OK;
-    if (m->d_stage) cudaFree(m->d_stage);
-    m->d_stage = nullptr, m->d_stage_bytes = 0;
-    CU(cudaMalloc(&m->d_stage, bytes));
-    m->d_stage_bytes = bytes;
+    if (m->d_stage_bytes[k] >= bytes) return RXM_OK;
+    if (m->d_stage[k]) cudaFree(m->d_stage[k]);
+    m->d_stage[k] = nullptr, m->d_stage_bytes[k] = 0;
+    CU(cudaMalloc(&m->d_stage[k], bytes));
+    m->d_stage_bytes[k] = bytes;
+    return RXM_OK;
+}
+
+// upload / download through a dedicated staging buffer `k` (concurrent host calls on different streams
+// must not share one); `sync` = wait for the result before returning
+static int upload_via(rxm_attr* a, const void* host_global, void* stream, int k)
+{
+    rxm_mesh*    m     = a->m;
+    const size_t bytes = (size_t)m->h.num_elems[a->elem] * a->nattr * a->elem_bytes;
+    int          rc    = ensure_stage(m, bytes, k);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(m->d_stage[k], host_global, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return rxm_attr_from_global_device(a, m->d_stage[k], stream);
+}
+static int download_via(rxm_attr* a, void* host_global, void* stream, int k, bool sync)
+{
+    rxm_mesh*    m     = a->m;
+    const size_t bytes = (size_t)m->h.num_elems[a->elem] * a->nattr * a->elem_bytes;
+    int          rc    = ensure_stage(m, bytes, k);
+    if (rc) return rc;
+    if ((rc = rxm_attr_to_global_device(a, m->d_stage[k], stream))) return rc;
+    CU(cudaMemcpyAsync(host_global, m->d_stage[k], bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    if (sync) CU(cudaStreamSynchronize((cudaStream_t)stream));
     return RXM_OK;
 }
 
@@ -520,10 +546,8 @@ int rxm_attr_upload_global(rxm_attr* a, const void* host_global, void* stream)
     if (a->d) {
         rxm_mesh*    m     = a->m;
         const size_t bytes = (size_t)m->h.num_elems[a->elem] * a->nattr * a->elem_bytes;
-        int          rc    = ensure_stage(m, bytes);
-        if (rc) return rc;
-        CU(cudaMemcpyAsync(m->d_stage, host_global, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
-        return rxm_attr_from_global_device(a, m->d_stage, stream);
+        (void)bytes;
+        return upload_via(a, host_global, stream, 0);
     }
     return RXM_OK;
 }
@@ -534,13 +558,8 @@ int rxm_attr_download_global(rxm_attr* a, void* host_global, void* stream)
     if (a->d) {
         rxm_mesh*    m     = a->m;
         const size_t bytes = (size_t)m->h.num_elems[a->elem] * a->nattr * a->elem_bytes;
-        int          rc    = ensure_stage(m, bytes);
-        if (rc) return rc;
-        rc = rxm_attr_to_global_device(a, m->d_stage, stream);
-        if (rc) return rc;
-        CU(cudaMemcpyAsync(host_global, m->d_stage, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-        CU(cudaStreamSynchronize((cudaStream_t)stream));
-        return RXM_OK;
+        (void)bytes, (void)m;
+        return download_via(a, host_global, stream, 0, true);
     }
     if (a->h) {
         host_permute(a, host_global, false);
@@ -779,9 +798,9 @@ int rxm_vertex_normals_host(rxm_mesh* m, const float* coords, float* normals, vo
     if (!coords || !normals) return fail(RXM_ERR_INVALID, "rxm_vertex_normals_host: null buffer");
     rxm_attr *x, *n;
     if ((rc = get_scratch(m, 1, &x)) || (rc = get_scratch(m, 2, &n))) return rc;
-    if ((rc = rxm_attr_upload_global(x, coords, stream))) return rc;
+    if ((rc = upload_via(x, coords, stream, 2))) return rc;
     if ((rc = rxm_vertex_normals(m, x, n, 0, stream))) return rc;
-    return rxm_attr_download_global(n, normals, stream);
+    return download_via(n, normals, stream, 3, !g_async_host_calls);
 }
 
 int rxm_laplacian_smooth_host(rxm_mesh* m, const float* coords, float* out, double lr, uint32_t iters, void* stream)
@@ -801,14 +820,14 @@ int rxm_query_consume_host(rxm_mesh* m, int op, const float* in, float* out, voi
     int rc = check_dev(m, "rxm_query_consume_host");
     if (rc) return rc;
     if (!in || !out || op_src(op) < 0) return fail(RXM_ERR_INVALID, "rxm_query_consume_host: bad argument");
-    // cached 1 x fp32 attributes per element type: [0..2] inputs, [3..5] outputs
-    rxm_attr*& a = m->scratch1[op_dst(op)];
-    rxm_attr*& b = m->scratch1[3 + op_src(op)];
+    // cached 1 x fp32 attributes per op (calls for different ops may be in flight on different streams)
+    rxm_attr*& a = m->scratch1[2 * (op & 15)];
+    rxm_attr*& b = m->scratch1[2 * (op & 15) + 1];
     if (!a && (rc = rxm_attr_create(m, op_dst(op), 4, 1, RXM_DEVICE, RXM_AOS, &a))) return rc;
     if (!b && (rc = rxm_attr_create(m, op_src(op), 4, 1, RXM_DEVICE, RXM_AOS, &b))) return rc;
-    if ((rc = rxm_attr_upload_global(a, in, stream))) return rc;
+    if ((rc = upload_via(a, in, stream, 4 + 2 * (op & 15) % 28))) return rc;
     if ((rc = rxm_query_consume(m, op, a, b, stream))) return rc;
-    return rxm_attr_download_global(b, out, stream);
+    return download_via(b, out, stream, 5 + 2 * (op & 15) % 28, !g_async_host_calls);
 }
 
 // ------------------------------------------------------------------ multi-GPU support
@@ -922,6 +941,17 @@ int rxm_ipc_open(const void* handle64, void** dev_ptr)
 int rxm_ipc_close(void* dev_ptr)
 {
     CU(cudaIpcCloseMemHandle(dev_ptr));
+    return RXM_OK;
+}
+
+void rxm_set_async(int on)
+{
+    g_async_host_calls = on;
+}
+
+int rxm_stream_sync(void* stream)
+{
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
     return RXM_OK;
 }
 

@@ -446,5 +446,10 @@ class RXMeshStatic:
         return inp, out, src, dst
 
 
+def set_async(on):
+    """rxm_set_async: *_host entry points return after enqueueing; sync the stream before reading results."""
+    lib().rxm_set_async(int(bool(on)))
+
+
 def launch_count():
     return int(lib().rxm_launch_count())
