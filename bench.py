@@ -236,12 +236,14 @@ def run_ours(args, rank, world, local_rank):
         sm = D.ShardedMesh(sh, rank, world, patch_size=2 * TILE * TILE_I, num_threads=max(1, ncores // world))
         mesh, V = sm.mesh, sh["verts"]
         hx_v, hx_f = D.HaloExchange(sm, 0), D.HaloExchange(sm, 2)
+        _ = mesh.ribbon_overhead()
         lbf, lbv, lbe = mesh.lin_base(2), mesh.lin_base(0), mesh.lin_base(1)
         a, b = sm.first, sm.first + sm.count
         nF, nV = int(lbf[b] - lbf[a]), mesh.get_num_vertices()  # real faces; host arrays cover the whole slab
         nE_real = int(lbe[b] - lbe[a])
         halo_bytes = 12 * hx_v.halo_elements()
     t_build = time.perf_counter() - t0
+    mesh.compact()  # the 100 M-face mesh lives on the device; drop host helper arrays (halo plans are built)
     stream = torch.cuda.current_stream()
     x = rx.Attribute(mesh, 0, np.float32, 3, rx.DEVICE, rx.AoS)
     nrm = rx.Attribute(mesh, 0, np.float32, 3, rx.DEVICE, rx.AoS)

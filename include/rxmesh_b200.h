@@ -56,6 +56,10 @@ int rxm_mesh_create(const uint32_t* fv, uint32_t num_faces, const uint32_t* face
                     int num_threads, rxm_mesh** out);
 /* RXMesh::build_device (rxmesh.cpp:1139-1615): upload the patch store to the current device. */
 int rxm_mesh_to_device(rxm_mesh* m);
+/* Release host-side helper arrays of a large mesh once it is on the device (local->global lists, global edge
+ * arrays, the host copy of the patch store): rxm_mesh_patch / rxm_mesh_edges / rxm_query_csr / halo planning
+ * are no longer available afterwards; attributes, kernels and the slot<->global maps keep working. */
+int rxm_mesh_compact(rxm_mesh* m);
 /* ~RXMesh (rxmesh.cpp:227-288) */
 void rxm_mesh_destroy(rxm_mesh* m);
 

@@ -29,6 +29,7 @@ SYMBOLS = {
     "rxm_mesh_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int,
                                   C.POINTER(C.c_void_p)]),
     "rxm_mesh_to_device": (C.c_int, [C.c_void_p]),
+    "rxm_mesh_compact": (C.c_int, [C.c_void_p]),
     "rxm_mesh_destroy": (None, [C.c_void_p]),
     "rxm_mesh_info": (C.c_uint64, [C.c_void_p, C.c_int]),
     "rxm_mesh_build_seconds": (C.c_double, [C.c_void_p, C.c_int]),

@@ -39,6 +39,7 @@ struct rxm_mesh
     uint8_t*     d_topo    = nullptr;
     uint32_t*    d_slot_base[3] = {nullptr, nullptr, nullptr};
     uint32_t*    d_s2g[3]       = {nullptr, nullptr, nullptr};
+    uint64_t     topo_bytes   = 0;
     uint32_t     active_first = 0, active_count = 0;  // patches the kernels run on (a shard's real patches)
     MeshView     view{};
     KernelLimits lim{};
@@ -130,6 +131,7 @@ int rxm_mesh_create(const uint32_t* fv, uint32_t num_faces, const uint32_t* face
         m->lim.max_owned[t]     = m->h.max_owned_per_patch[t];
         m->lim.max_not_owned[t] = m->h.max_not_owned[t];
     }
+    m->topo_bytes                  = m->h.topo.size();
     m->lim.max_stash               = m->h.max_stash;
     m->lim.max_face_adjacent_faces = m->h.max_face_adjacent_faces;
     m->lim.max_fan_total           = m->h.max_fan_total;
@@ -167,6 +169,20 @@ int rxm_mesh_to_device(rxm_mesh* m)
         m->view.patch_slot_base[t] = m->d_slot_base[t];
     }
     m->on_device = true;
+    return RXM_OK;
+}
+
+int rxm_mesh_compact(rxm_mesh* m)
+{
+    if (!m) return fail(RXM_ERR_INVALID, "rxm_mesh_compact: null mesh");
+    HostMesh& h = m->h;
+    for (int t = 0; t < 3; ++t) {
+        std::vector<uint32_t>().swap(h.ltog[t]);
+        std::vector<uint64_t>().swap(h.ltog_off[t]);
+    }
+    std::vector<uint32_t>().swap(h.ev);
+    std::vector<uint32_t>().swap(h.fe);
+    if (m->on_device) std::vector<uint8_t>().swap(h.topo);  // the device holds the patch store
     return RXM_OK;
 }
 
@@ -222,7 +238,7 @@ uint64_t rxm_mesh_info(const rxm_mesh* m, int what)
         case RXM_INFO_NUM_SLOTS_V: return h.num_slots[ELEM_V];
         case RXM_INFO_NUM_SLOTS_E: return h.num_slots[ELEM_E];
         case RXM_INFO_NUM_SLOTS_F: return h.num_slots[ELEM_F];
-        case RXM_INFO_TOPO_BYTES: return h.topo.size();
+        case RXM_INFO_TOPO_BYTES: return m->topo_bytes;
         case RXM_INFO_TOTAL_LOCAL_V: return h.total_local[ELEM_V];
         case RXM_INFO_TOTAL_LOCAL_E: return h.total_local[ELEM_E];
         case RXM_INFO_TOTAL_LOCAL_F: return h.total_local[ELEM_F];
@@ -242,6 +258,7 @@ double rxm_mesh_build_seconds(const rxm_mesh* m, int patcher_only)
 int rxm_mesh_patch(const rxm_mesh* m, uint32_t p, rxm_patch_view* o)
 {
     if (!m || !o || p >= m->h.num_patches) return fail(RXM_ERR_INVALID, "rxm_mesh_patch: bad argument");
+    if (m->h.topo.empty()) return fail(RXM_ERR_INVALID, "rxm_mesh_patch: host patch store was released (rxm_mesh_compact)");
     const PatchDesc& D = m->h.desc[p];
     const uint8_t*   B = m->h.topo.data() + D.topo_off;
     o->patch_id        = D.patch_id;
@@ -716,6 +733,8 @@ int rxm_query_csr(rxm_mesh* m, int op, uint32_t** dev_off, uint32_t** dev_val, u
     if (m->active_count && m->active_count != m->h.num_patches)
         return fail(RXM_ERR_UNSUPPORTED, "rxm_query_csr: not available on a shard (active patch range set)");
     auto& C = m->csr[op];
+    if (!C.off && m->h.topo.empty())
+        return fail(RXM_ERR_INVALID, "rxm_query_csr: host patch store was released (rxm_mesh_compact)");
     if (!C.off) {
         const HostMesh&       h = m->h;
         std::vector<uint32_t> pno(h.num_patches + 1, 0);
@@ -849,6 +868,7 @@ int rxm_mesh_halo_slots(const rxm_mesh* m, int elem, uint32_t first, uint32_t co
     if (!m || !out || !n || elem < 0 || elem > 2 || (uint64_t)first + count > m->h.num_patches)
         return fail(RXM_ERR_INVALID, "rxm_mesh_halo_slots: bad argument");
     const HostMesh&      h = m->h;
+    if (h.topo.empty()) return fail(RXM_ERR_INVALID, "rxm_mesh_halo_slots: host patch store was released (rxm_mesh_compact)");
     std::vector<uint8_t> mark(h.num_slots[elem], 0);
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t p = first; p < (int64_t)first + count; ++p) {

@@ -216,6 +216,10 @@ class RXMeshStatic:
     def total_local(self, elem):
         return self._info(17 + int(elem))
 
+    def compact(self):
+        """rxm_mesh_compact: free host-side helper arrays of a large mesh that already lives on the device."""
+        check(lib().rxm_mesh_compact(self._h))
+
     def is_packed(self):
         """True when the patch store uses the rank-annotated (atomic-free) format."""
         return bool(self._info(22))
