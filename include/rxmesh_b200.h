@@ -98,6 +98,7 @@ typedef struct {
      * closed fan, low 15 bits = start in fan_v; fan_v = neighbour local vertex ids in oriented order */
     const uint16_t* fan_off;
     const uint16_t* fan_v;
+    const uint16_t* fan_f;       /* fan_f[i] = local face between fan_v[i] and fan_v[i+1] (0xFFFF at the end of an open fan) */
     uint32_t        fan_total;
     const uint32_t* owner[3];    /* n[t]-n_owned[t]: (stash slot << 16) | local id in owner */
     const uint32_t* stash;       /* 4*n_stash u32: patch, slot base V, E, F */

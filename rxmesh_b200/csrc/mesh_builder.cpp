@@ -510,7 +510,7 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
     // ---- phase A2: one-ring fans of the owned vertices (local ids), if the input allows ----
     // For owned vertex v every incident face (v, a, b) (a cyclic rotation of its stored corner
     // order) is a directed link a -> b; the links must chain into ONE open or closed sequence.
-    std::vector<std::vector<uint16_t>> fan_v(P), fan_off(P);
+    std::vector<std::vector<uint16_t>> fan_v(P), fan_off(P), fan_f(P);
     bool fans_ok = !opt.no_fans && M.is_edge_manifold && M.max_valence < 4096;
     if (fans_ok) {
         int bad = 0;
@@ -535,13 +535,14 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
             std::vector<uint32_t> off(nov + 1, 0);
             for (uint32_t v = 0; v < nov; ++v)
                 off[v + 1] = off[v] + cnt[v];
-            std::vector<std::array<uint16_t, 2>> links(off[nov]);
+            std::vector<std::array<uint16_t, 3>> links(off[nov]);  // (first, second, face)
             std::vector<uint32_t>                cur(off.begin(), off.end() - 1);
             for (size_t f = 0; f < lf.size(); ++f)
                 for (int j = 0; j < 3; ++j)
-                    if (lf[f][j] < nov) links[cur[lf[f][j]]++] = {lf[f][(j + 1) % 3], lf[f][(j + 2) % 3]};
+                    if (lf[f][j] < nov) links[cur[lf[f][j]]++] = {lf[f][(j + 1) % 3], lf[f][(j + 2) % 3], (uint16_t)f};
             auto& FO = fan_off[p];
             auto& FV = fan_v[p];
+            auto& FF = fan_f[p];
             FO.assign(nov + 1, 0);
             for (uint32_t v = 0; v < nov && !bad; ++v) {
                 auto*          L = links.data() + off[v];
@@ -565,12 +566,13 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
                 FO[v] = (uint16_t)(FV.size() | (closed ? FAN_CLOSED : 0));
                 uint32_t curl = start, used = 0;
                 FV.push_back(L[curl][0]);
+                FF.push_back(L[curl][2]);
                 while (used < k) {
                     ++used;
                     const uint16_t nxt = L[curl][1];
                     if (used == k) {
                         if (closed) { if (nxt != L[start][0]) bad = 1; }
-                        else FV.push_back(nxt);
+                        else { FV.push_back(nxt); FF.push_back(0xFFFFu); }
                         break;
                     }
                     FV.push_back(nxt);
@@ -579,6 +581,7 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
                         if (L[j][0] == nxt) found = j, ++nf_;
                     if (nf_ != 1) { bad = 1; break; }
                     curl = found;
+                    FF.push_back(L[curl][2]);
                 }
             }
             FO[nov] = (uint16_t)FV.size();
@@ -706,6 +709,7 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
         if (M.fans) {
             memcpy(B + D.off_fanoff(), fan_off[p].data(), fan_off[p].size() * 2);
             memcpy(B + D.off_fanv(), fan_v[p].data(), fan_v[p].size() * 2);
+            memcpy(B + D.off_fanf(), fan_f[p].data(), fan_f[p].size() * 2);
         }
         for (int t = 0; t < 3; ++t) {
             uint32_t* own = reinterpret_cast<uint32_t*>(B + D.off_own(t));

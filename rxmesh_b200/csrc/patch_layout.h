@@ -36,7 +36,9 @@
 //    footprint as EV -- but it answers VV (and oriented VV, the reference's
 //    orient_edges_around_vertices, kernels/rxmesh_queries.cuh:375-499) by a plain
 //    read, and lets vertex normals / Laplacian run one thread per OWNED vertex
-//    with register accumulators: no transpose, no atomics, no ribbon-face work;
+//    with register accumulators: no transpose, no atomics, no ribbon-face work.
+//    A parallel array fan_f names the face between consecutive fan vertices, so
+//    VF is a plain read as well;
 //  * local ids are owned-first, each half sorted by global id (the reference's
 //    numbering, rxmesh.cpp:845-869), so the owned / active bitmasks of the
 //    reference collapse to a prefix [0, n_owned) and the not-owned -> owner
@@ -133,7 +135,8 @@ struct alignas(16) PatchDesc
     //      kernel spends no instructions on layout arithmetic. Order: EV, FE, FV, voff_e, voff_f, eoff_f,
     //      fan_off, fan_v, owner V/E/F, stash ----
     uint32_t o_fe, o_fv, o_voff_e, o_voff_f, o_eoff_f, o_fanoff, o_fanv, o_own[3], o_stash;
-    uint32_t pad1[5];
+    uint32_t o_fanf;        // fan faces: fan_f[i] = local face between fan_v[i] and fan_v[i+1] (0xFFFF: none)
+    uint32_t pad1[4];
 
     RXM_HD uint32_t ev_bytes() const { return o_fe; }
     RXM_HD uint32_t fe_bytes() const { return o_fv - o_fe; }
@@ -149,7 +152,9 @@ struct alignas(16) PatchDesc
     RXM_HD uint32_t off_eoff_f() const { return o_eoff_f; }
     // one-ring fans of the owned vertices: fan_off[nov+1] (bit 15 = closed fan), fan_v[fan_total]
     RXM_HD uint32_t fanoff_bytes() const { return o_fanv - o_fanoff; }
-    RXM_HD uint32_t fanv_bytes() const { return o_own[0] - o_fanv; }
+    RXM_HD uint32_t fanv_bytes() const { return o_fanf - o_fanv; }
+    RXM_HD uint32_t fanf_bytes() const { return o_own[0] - o_fanf; }
+    RXM_HD uint32_t off_fanf() const { return o_fanf; }
     RXM_HD uint32_t off_fanoff() const { return o_fanoff; }
     RXM_HD uint32_t off_fanv() const { return o_fanv; }
     RXM_HD uint32_t off_own(uint32_t t) const { return o_own[t]; }
@@ -175,6 +180,8 @@ struct alignas(16) PatchDesc
         o_fanoff = o;
         o += (flags & 2) ? round_up(2u * (n_owned[ELEM_V] + 1u), 16) : 0u;
         o_fanv = o;
+        o += (flags & 2) ? round_up(2u * fan_total, 16) : 0u;
+        o_fanf = o;
         o += (flags & 2) ? round_up(2u * fan_total, 16) : 0u;
         for (int t = 0; t < 3; ++t) {
             o_own[t] = o;

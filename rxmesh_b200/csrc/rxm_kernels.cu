@@ -507,6 +507,47 @@ __global__ void __launch_bounds__(BT) k_laplacian_fan(MeshView mv, const float* 
     fan_store(d, F, xo);
 }
 
+// VF consume through the fan faces: out(v) = sum over the incident faces of in(f)
+__global__ void __launch_bounds__(BT) k_vf_consume_fan(MeshView mv, const float* __restrict__ in, float* __restrict__ out)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint64_t                      bar;
+    const PatchDesc d    = load_desc(mv.desc + blockIdx.x);
+    const uint8_t*  blob = mv.topo + d.topo_off;
+    const uint32_t  nf = d.n[ELEM_F], nof = d.n_owned[ELEM_F], nov = d.n_owned[ELEM_V], cap = d.slot_cap(ELEM_F);
+    Smem            sm(smem_raw);
+    uint16_t*       s_fo    = sm.alloc<uint16_t>(d.fanoff_bytes() / 2);
+    uint16_t*       s_ff    = sm.alloc<uint16_t>(d.fanf_bytes() / 2);
+    uint32_t*       s_own   = sm.alloc<uint32_t>(d.own_bytes(ELEM_F) / 4);
+    StashEntry*     s_stash = sm.alloc<StashEntry>(d.n_stash);
+    float*          s_in    = sm.alloc<float>(max(nf, cap));
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(&bar, d.fanoff_bytes() + d.fanf_bytes() + d.own_bytes(ELEM_F) + d.stash_bytes() + 4u * cap);
+        bulk_g2s(s_fo, blob + d.off_fanoff(), d.fanoff_bytes(), &bar);
+        if (d.fanf_bytes()) bulk_g2s(s_ff, blob + d.off_fanf(), d.fanf_bytes(), &bar);
+        if (d.own_bytes(ELEM_F)) bulk_g2s(s_own, blob + d.off_own(ELEM_F), d.own_bytes(ELEM_F), &bar);
+        if (d.stash_bytes()) bulk_g2s(s_stash, blob + d.off_stash(), d.stash_bytes(), &bar);
+        if (cap) bulk_g2s(s_in, in + d.slot_base[ELEM_F], 4u * cap, &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    for (uint32_t i = nof + threadIdx.x; i < nf; i += BT) {
+        const uint32_t o = s_own[i - nof];
+        s_in[i]          = ldg_stream(in + s_stash[o >> 16].slot_base[ELEM_F] + (o & 0xFFFFu));
+    }
+    __syncthreads();
+    for (uint32_t v = threadIdx.x; v < nov; v += BT) {
+        const uint32_t o = s_fo[v], b = o & FAN_OFF_MASK;
+        const uint32_t e = (s_fo[v + 1] & FAN_OFF_MASK) - ((o & FAN_CLOSED) ? 0u : 1u);  // open fan: last slot has no face
+        float          a = 0.f;
+        for (uint32_t i = b; i < e; ++i)
+            a += s_in[s_ff[i]];
+        out[d.slot_base[ELEM_V] + v] = a;
+    }
+}
+
 // VV consume through the fans: out(v) = sum over the one-ring of in(u)
 __global__ void __launch_bounds__(BT) k_vv_consume_fan(MeshView mv, const float* __restrict__ in, float* __restrict__ out)
 {
@@ -1162,6 +1203,15 @@ cudaError_t launch_query_consume(int op, const MeshView& mv, const KernelLimits&
         cudaError_t e = launch_persistent<VFConsumeWorker>(mv, VFConsumeWorker::Args{in.data, out.data}, L, stream);
         if (e == cudaErrorInvalidValue) RXM_FAIL("patch needs more shared memory than 227 KB");
         return e;
+    }
+    if (op == OP_VF && mv.fans && !use_persistent()) {
+        const uint32_t smem = r16(2u * (lim.max_owned[ELEM_V] + 1) + 16) + r16(2u * lim.max_fan_total + 16) +
+                              r16(4u * lim.max_not_owned[ELEM_F]) + 16u * lim.max_stash +
+                              r16(4u * (std::max(lim.max_n[ELEM_F], lim.max_owned[ELEM_F] + 4)));
+        if (set_smem(k_vf_consume_fan, smem) != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
+        k_vf_consume_fan<<<mv.num_patches, BT, smem, stream>>>(mv, in.data, out.data);
+        ++g_launches;
+        return cudaGetLastError();
     }
     if (op == OP_VV && mv.fans) {
         const uint32_t smem = fan_smem(lim) + r16(4u * (std::max(lim.max_n[ELEM_V], lim.max_owned[ELEM_V] + 4)));

@@ -141,6 +141,13 @@ def test_one_ring_fans(built):
             assert closed == (not bflags[g])
             pairs = list(zip(ring, ring[1:])) + ([(ring[-1], ring[0])] if closed else [])
             assert all((g, a, c) in faces for a, c in pairs), (name, p, v)
+            # fan_f names the face spanned by consecutive fan vertices
+            ff = pv["fan_f"][b:e]
+            lf = pv["ltog"][2]
+            for (a, c), f in zip(pairs, ff):
+                assert set(F[lf[f]].tolist()) == {g, a, c}
+            if not closed:
+                assert ff[-1] == 0xFFFF
 
 
 def test_fans_absent_on_inconsistent_orientation():
