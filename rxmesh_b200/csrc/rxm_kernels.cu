@@ -444,7 +444,7 @@ __device__ __forceinline__ void fan_store(const PatchDesc& d, const FanPatch& F,
 }
 
 template <int UNIT>
-__global__ void __launch_bounds__(BT) k_vertex_normals_fan(MeshView mv, const float* __restrict__ x,
+__global__ void __launch_bounds__(BT, 8) k_vertex_normals_fan(MeshView mv, const float* __restrict__ x,
                                                            float* __restrict__ nrm)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -456,25 +456,41 @@ __global__ void __launch_bounds__(BT) k_vertex_normals_fan(MeshView mv, const fl
         if (v < F.nov) {
             const uint32_t o = F.s_fo[v], b = o & FAN_OFF_MASK, e = F.s_fo[v + 1] & FAN_OFF_MASK;
             const float4   p = F.s_x[v];
-            float4         q = F.s_x[F.s_fv[b]];
-            const float    d0x = q.x - p.x, d0y = q.y - p.y, d0z = q.z - p.z;
-            const float    l0 = d0x * d0x + d0y * d0y + d0z * d0z;
-            float          px = d0x, py = d0y, pz = d0z, pl = l0;
-            auto face = [&](float cx, float cy, float cz, float cl) {
-                // face (v, prev, cur): n = (prev - v) x (cur - v); corner weight 1 / (|prev-v|^2 + |cur-v|^2)
+            // face (v, prev, cur): n = (prev - v) x (cur - v); corner weight 1 / (|prev-v|^2 + |cur-v|^2)
+            auto face = [&](float px, float py, float pz, float pl, float cx, float cy, float cz, float cl) {
                 const float nx = py * cz - pz * cy, ny = pz * cx - px * cz, nz = px * cy - py * cx;
                 const float w  = UNIT ? rsqrtf(nx * nx + ny * ny + nz * nz) : fast_rcp(pl + cl);
                 sx += nx * w, sy += ny * w, sz += nz * w;
             };
-#pragma unroll 2
-            for (uint32_t i = b + 1; i < e; ++i) {
-                q = F.s_x[F.s_fv[i]];
-                const float cx = q.x - p.x, cy = q.y - p.y, cz = q.z - p.z;
-                const float cl = cx * cx + cy * cy + cz * cz;
-                face(cx, cy, cz, cl);
-                px = cx, py = cy, pz = cz, pl = cl;
+            if (o == (b | FAN_CLOSED) && e - b == 6) {
+                // the regular case (closed fan of valence 6): straight-line code, all six neighbour loads in
+                // flight together, no loop counter / branches
+                float dx[6], dy[6], dz[6], dl[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const float4 q = F.s_x[F.s_fv[b + k]];
+                    dx[k] = q.x - p.x, dy[k] = q.y - p.y, dz[k] = q.z - p.z;
+                    dl[k] = dx[k] * dx[k] + dy[k] * dy[k] + dz[k] * dz[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const int j = (k + 1) % 6;
+                    face(dx[k], dy[k], dz[k], dl[k], dx[j], dy[j], dz[j], dl[j]);
+                }
+            } else {
+                float4      q  = F.s_x[F.s_fv[b]];
+                const float d0x = q.x - p.x, d0y = q.y - p.y, d0z = q.z - p.z;
+                const float l0 = d0x * d0x + d0y * d0y + d0z * d0z;
+                float       px = d0x, py = d0y, pz = d0z, pl = l0;
+                for (uint32_t i = b + 1; i < e; ++i) {
+                    q = F.s_x[F.s_fv[i]];
+                    const float cx = q.x - p.x, cy = q.y - p.y, cz = q.z - p.z;
+                    const float cl = cx * cx + cy * cy + cz * cz;
+                    face(px, py, pz, pl, cx, cy, cz, cl);
+                    px = cx, py = cy, pz = cz, pl = cl;
+                }
+                if (o & FAN_CLOSED) face(px, py, pz, pl, d0x, d0y, d0z, l0);
             }
-            if (o & FAN_CLOSED) face(d0x, d0y, d0z, l0);
         }
         F.s_xp[3 * v] = sx, F.s_xp[3 * v + 1] = sy, F.s_xp[3 * v + 2] = sz;
     }
