@@ -71,6 +71,31 @@ class RXMeshStatic
     {
         init(fv, num_faces, face_patch, patch_size);
     }
+    // RXMeshStatic(fv, patcher_file, patch_size): replay a patching saved by Patcher::save / RXMesh::save
+    // (rxmesh_static.h:61-66, patcher/patcher.h:154-182)
+    RXMeshStatic(const std::vector<std::vector<uint32_t>>& fv, const std::string& patcher_file, const uint32_t patch_size = 512)
+    {
+        std::vector<uint32_t> flat;
+        flat.reserve(3 * fv.size());
+        for (const auto& f : fv)
+            flat.insert(flat.end(), f.begin(), f.end());
+        std::vector<uint32_t> face_patch;
+        uint32_t              ps = patch_size;
+        if (!patcher_file.empty()) {
+            rxm_patcher_file pf;
+            if (rxm_patcher_file_read(patcher_file.c_str(), &pf) == RXM_OK && pf.len[0] == fv.size()) {
+                face_patch.assign(pf.vec[0], pf.vec[0] + pf.len[0]);
+                ps = pf.header[0];
+                rxm_patcher_file_free(&pf);
+            } else {  // rxmesh.cpp:303-317: log and build fresh patches
+                fprintf(stderr, "RXMesh::build patch file %s does not exist or does not match. Building unique patches.\n",
+                        patcher_file.c_str());
+            }
+        }
+        init(flat.data(), (uint32_t)fv.size(), face_patch, ps);
+    }
+    // RXMesh::save (rxmesh.h:326-329)
+    void save(const std::string& filename) const { detail::rxm_check(rxm_mesh_save_patcher_file(m_mesh, filename.c_str())); }
     virtual ~RXMeshStatic()
     {
         m_attrs.clear();

@@ -202,6 +202,20 @@ int rxm_ipc_export(void* dev_ptr, void* handle64);        /* cudaIpcGetMemHandle
 int rxm_ipc_open(const void* handle64, void** dev_ptr);   /* cudaIpcOpenMemHandle */
 int rxm_ipc_close(void* dev_ptr);
 
+/* Saved patchings: the reference's Patcher::save / Patcher(filename) (patcher/patcher.h:154-182; the
+ * `patcher_file` constructor argument, rxmesh_static.h:61-66), cereal PortableBinary layout. header = patch_size,
+ * num_patches, num_vertices, num_edges, num_faces, num_seeds, max_num_patches, num_components, num_lloyd_run;
+ * vec = face_patch, vertex_patch, edge_patch, patches_val, patches_offset, ribbon_ext_val, ribbon_ext_offset. */
+typedef struct {
+    uint32_t  header[9];
+    uint32_t* vec[7];
+    uint64_t  len[7];
+    float     patching_time_ms;
+} rxm_patcher_file;
+int  rxm_patcher_file_read(const char* path, rxm_patcher_file* out); /* vec[0] is the face_patch for rxm_mesh_create */
+void rxm_patcher_file_free(rxm_patcher_file* pf);
+int  rxm_mesh_save_patcher_file(const rxm_mesh* m, const char* path);
+
 /* Asynchronous host calls: with rxm_set_async(1) the *_host entry points return once their H2D copy, kernels
  * and D2H copy are ENQUEUED on `stream` (the host buffers must be pinned and stay valid); results are ready
  * after rxm_stream_sync(stream). Calls issued on different streams overlap their copies and kernels (every

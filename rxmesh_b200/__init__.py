@@ -6,4 +6,4 @@ library must be built (rxmesh_b200/librxmesh_b200.so) -- there is no CPU fallbac
 from . import meshio  # noqa: F401
 from ._lib import RXMeshError, lib, LIB_PATH  # noqa: F401
 from .mesh import (AoS, AoSoA, Attribute, DEVICE, HOST, INVALID64, LOCATION_ALL, Op, RXMeshStatic,  # noqa: F401
-                   SoA, launch_count, rx_init, set_async)
+                   SoA, launch_count, load_patcher_file, rx_init, set_async)

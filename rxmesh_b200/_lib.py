@@ -21,6 +21,11 @@ class PatchView(C.Structure):
                 ("n_stash", C.c_uint32), ("ltog", u32p * 3)]
 
 
+class PatcherFile(C.Structure):
+    _fields_ = [("header", C.c_uint32 * 9), ("vec", u32p * 7), ("len", C.c_uint64 * 7),
+                ("patching_time_ms", C.c_float)]
+
+
 # every symbol declared in include/rxmesh_b200.h: (restype, argtypes)
 SYMBOLS = {
     "rxm_last_error": (C.c_char_p, []),
@@ -80,6 +85,9 @@ SYMBOLS = {
     "rxm_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rxm_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "rxm_ipc_close": (C.c_int, [C.c_void_p]),
+    "rxm_patcher_file_read": (C.c_int, [C.c_char_p, C.POINTER(PatcherFile)]),
+    "rxm_patcher_file_free": (None, [C.POINTER(PatcherFile)]),
+    "rxm_mesh_save_patcher_file": (C.c_int, [C.c_void_p, C.c_char_p]),
     "rxm_set_async": (None, [C.c_int]),
     "rxm_stream_sync": (C.c_int, [C.c_void_p]),
     "rxm_launch_count": (C.c_uint64, []),

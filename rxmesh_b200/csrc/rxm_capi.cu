@@ -965,6 +965,77 @@ int rxm_ipc_close(void* dev_ptr)
     return RXM_OK;
 }
 
+// ------------------------------------------------------------------ saved patchings
+// The reference's Patcher::serialize layout (patcher/patcher.h:162-182) in cereal's PortableBinary archive:
+// 1 byte (1 = little endian), 9 x u32 scalars, 7 x (u64 length + u32[length]), 1 x f32.
+int rxm_patcher_file_read(const char* path, rxm_patcher_file* out)
+{
+    if (!path || !out) return fail(RXM_ERR_INVALID, "rxm_patcher_file_read: null argument");
+    memset(out, 0, sizeof(*out));
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(RXM_ERR_INVALID, std::string("rxm_patcher_file_read: cannot open ") + path);
+    uint8_t endian = 0;
+    bool    ok     = fread(&endian, 1, 1, f) == 1 && endian == 1;
+    ok             = ok && fread(out->header, 4, 9, f) == 9;
+    for (int i = 0; ok && i < 7; ++i) {
+        uint64_t n = 0;
+        ok         = fread(&n, 8, 1, f) == 1 && n < (1ull << 32);
+        if (!ok) break;
+        out->len[i] = n;
+        out->vec[i] = (uint32_t*)malloc(std::max<uint64_t>(n, 1) * 4);
+        ok          = out->vec[i] && fread(out->vec[i], 4, n, f) == n;
+    }
+    ok = ok && fread(&out->patching_time_ms, 4, 1, f) == 1;
+    fclose(f);
+    if (!ok) {
+        rxm_patcher_file_free(out);
+        return fail(RXM_ERR_INVALID, std::string("rxm_patcher_file_read: not a little-endian Patcher archive: ") + path);
+    }
+    return RXM_OK;
+}
+
+void rxm_patcher_file_free(rxm_patcher_file* pf)
+{
+    if (!pf) return;
+    for (int i = 0; i < 7; ++i) {
+        free(pf->vec[i]);
+        pf->vec[i] = nullptr;
+    }
+}
+
+int rxm_mesh_save_patcher_file(const rxm_mesh* m, const char* path)
+{
+    if (!m || !path) return fail(RXM_ERR_INVALID, "rxm_mesh_save_patcher_file: null argument");
+    const HostMesh& h = m->h;
+    if (h.ltog[ELEM_F].empty()) return fail(RXM_ERR_INVALID, "rxm_mesh_save_patcher_file: local->global lists were released");
+    const uint32_t        P = h.num_patches;
+    std::vector<uint32_t> pval, poff(P), rval, roff(P);
+    for (uint32_t p = 0; p < P; ++p) {
+        const uint32_t* l  = h.ltog[ELEM_F].data() + h.ltog_off[ELEM_F][p];
+        const uint32_t  no = h.desc[p].n_owned[ELEM_F], n = h.desc[p].n[ELEM_F];
+        pval.insert(pval.end(), l, l + no);
+        rval.insert(rval.end(), l + no, l + n);
+        poff[p] = (uint32_t)pval.size();  // the reference stores inclusive END offsets (rxmesh.cpp:760-768)
+        roff[p] = (uint32_t)rval.size();
+    }
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(RXM_ERR_INVALID, std::string("rxm_mesh_save_patcher_file: cannot open ") + path);
+    const uint8_t  endian = 1;
+    const uint32_t hdr[9] = {h.patch_size, P, h.num_elems[ELEM_V], h.num_elems[ELEM_E], h.num_elems[ELEM_F], P, P, 1, 1};
+    fwrite(&endian, 1, 1, f);
+    fwrite(hdr, 4, 9, f);
+    const std::vector<uint32_t>* vecs[7] = {&h.elem_patch[ELEM_F], &h.elem_patch[ELEM_V], &h.elem_patch[ELEM_E], &pval, &poff, &rval, &roff};
+    for (auto* v : vecs) {
+        const uint64_t n = v->size();
+        fwrite(&n, 8, 1, f);
+        fwrite(v->data(), 4, n, f);
+    }
+    const float t = (float)(h.patcher_seconds * 1e3);
+    fwrite(&t, 4, 1, f);
+    fclose(f);
+    return RXM_OK;
+}
+
 void rxm_set_async(int on)
 {
     g_async_host_calls = on;

@@ -11,7 +11,7 @@ import enum
 import numpy as np
 
 from . import meshio
-from ._lib import PatchView, RXMeshError, check, lib
+from ._lib import PatcherFile, PatchView, RXMeshError, check, lib
 
 HOST, DEVICE, LOCATION_ALL = 0x01, 0x02, 0x0F  # types.h:51-58
 AoS, AoSoA, SoA = 0, 1, 2  # types.h:84-90
@@ -49,6 +49,26 @@ def _stream_ptr(stream):
 def rx_init(device=0):
     """rx_init (rxmesh.h:23-30)."""
     check(lib().rxm_init(int(device)))
+
+
+_PF_FIELDS = ["face_patch", "vertex_patch", "edge_patch", "patches_val", "patches_offset", "ribbon_ext_val",
+              "ribbon_ext_offset"]
+_PF_HEADER = ["patch_size", "num_patches", "num_vertices", "num_edges", "num_faces", "num_seeds",
+              "max_num_patches", "num_components", "num_lloyd_run"]
+
+
+def load_patcher_file(path):
+    """Read a patching saved by the reference (Patcher::save, patcher/patcher.h:154-182) or by
+    RXMeshStatic.save_patcher_file: dict of header scalars + uint32 arrays."""
+    pf = PatcherFile()
+    check(lib().rxm_patcher_file_read(str(path).encode(), C.byref(pf)))
+    out = {k: int(pf.header[i]) for i, k in enumerate(_PF_HEADER)}
+    for i, k in enumerate(_PF_FIELDS):
+        n = int(pf.len[i])
+        out[k] = np.ctypeslib.as_array(pf.vec[i], shape=(max(n, 1),))[:n].copy()
+    out["patching_time_ms"] = float(pf.patching_time_ms)
+    lib().rxm_patcher_file_free(C.byref(pf))
+    return out
 
 
 class Attribute:
@@ -133,13 +153,18 @@ class RXMeshStatic:
     """
 
     def __init__(self, faces_or_path, face_patch=None, patch_size=512, num_threads=0, device=True,
-                 verts=None):
+                 verts=None, patcher_file=None):
         if isinstance(faces_or_path, str):
             verts, faces = meshio.import_obj(faces_or_path)
         else:
             faces = faces_or_path
         self._fv = np.ascontiguousarray(faces, dtype=np.uint32).reshape(-1, 3)
         self._verts = None if verts is None else np.ascontiguousarray(verts, dtype=np.float32)
+        if patcher_file is not None:  # RXMeshStatic(fv, patcher_file) (rxmesh_static.h:61-66)
+            pf = load_patcher_file(patcher_file)
+            if pf["num_faces"] != self._fv.shape[0]:
+                raise RXMeshError("patcher_file was saved for a mesh with a different number of faces")
+            face_patch, patch_size = pf["face_patch"], pf["patch_size"]
         fp = None
         if face_patch is not None:
             fp = np.ascontiguousarray(face_patch, dtype=np.uint32)
@@ -215,6 +240,10 @@ class RXMeshStatic:
 
     def total_local(self, elem):
         return self._info(17 + int(elem))
+
+    def save_patcher_file(self, path):
+        """RXMesh::save (rxmesh.h:326-329): write the patching in the reference's Patcher archive format."""
+        check(lib().rxm_mesh_save_patcher_file(self._h, str(path).encode()))
 
     def compact(self):
         """rxm_mesh_compact: free host-side helper arrays of a large mesh that already lives on the device."""

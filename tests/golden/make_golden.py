@@ -54,6 +54,11 @@ def main():
             out["vn_ref"] = O.ref_vertex_normals(F, V)  # the reference's own loop
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
         print(name, V.shape, F.shape, sorted(out))
+    # patchings saved by the reference itself (cereal archives shipped in input/): golden vectors for the
+    # ownership / ribbon rules of the patch builder (tests/test_host_build.py)
+    import shutil
+    for name in ("sphere3_patches", "torus_patches"):
+        shutil.copyfile(os.path.join(REF_INPUT, name), os.path.join(OUT, name))
     with open(os.path.join(OUT, "known_answers.json"), "w") as fh:
         json.dump(KNOWN, fh, indent=1)
 

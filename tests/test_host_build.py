@@ -208,3 +208,40 @@ def test_host_attribute_roundtrip_all_layouts():
             p = int(ep[g])
             lid = int(g2s[g] - sb[p])
             assert [h[a.index(p, lid, k)] for k in range(3)] == V[g].tolist()
+
+
+@pytest.mark.parametrize("name", ["sphere3", "torus"])
+def test_reference_saved_patching_golden(name, tmp_path):
+    """tests/golden/<name>_patches are the patchings SAVED BY THE REFERENCE (input/sphere3_patches,
+    input/torus_patches; Patcher::serialize, patcher/patcher.h:162-182). Replaying the reference's face->patch
+    assignment, our builder must reproduce the reference's OWN outputs for ownership (Patcher::assign_patch,
+    patcher.cu:719-757: m_vertex_patch / m_edge_patch, edge ids in the reference's numbering), owned face
+    lists (m_patches_val/offset) and ribbons (Patcher::extract_ribbons, patcher.cu:640-717)."""
+    import os
+    from conftest import GOLDEN
+    V, F = make_mesh(name)
+    path = os.path.join(GOLDEN, name + "_patches")
+    pf = rx.load_patcher_file(path)
+    assert (pf["num_vertices"], pf["num_faces"]) == (V.shape[0], F.shape[0]) and pf["patch_size"] == 512
+    m = rx.RXMeshStatic(F, patcher_file=path, device=False)
+    P = pf["num_patches"]
+    assert m.get_num_patches() == P and m.get_num_edges() == pf["num_edges"]
+    assert np.array_equal(m.elem_patch(2), pf["face_patch"])
+    assert np.array_equal(m.elem_patch(0), pf["vertex_patch"])   # reference's vertex ownership
+    assert np.array_equal(m.elem_patch(1), pf["edge_patch"])     # reference's edge ownership AND edge numbering
+    pend, rend = pf["patches_offset"][:P], pf["ribbon_ext_offset"][:P]
+    for p in range(P):
+        pv = m.patch(p)
+        no = pv["n_owned"][2]
+        owned_ref = pf["patches_val"][(pend[p - 1] if p else 0):pend[p]]
+        ribbon_ref = pf["ribbon_ext_val"][(rend[p - 1] if p else 0):rend[p]]
+        assert np.array_equal(np.sort(owned_ref), pv["ltog"][2][:no])
+        assert np.array_equal(np.sort(ribbon_ref), pv["ltog"][2][no:])
+    # write -> read round trip in the same format
+    out = str(tmp_path / "saved_patches")
+    m.save_patcher_file(out)
+    back = rx.load_patcher_file(out)
+    for k in ("face_patch", "vertex_patch", "edge_patch"):
+        assert np.array_equal(back[k], pf[k])
+    assert np.array_equal(back["patches_offset"], pend) and np.array_equal(back["ribbon_ext_offset"], rend)
+    assert np.array_equal(np.sort(back["patches_val"][:pend[0]]), np.sort(pf["patches_val"][:pend[0]]))
