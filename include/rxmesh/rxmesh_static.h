@@ -52,8 +52,9 @@ class RXMeshStatic
 
     // RXMeshStatic(fv, patcher_file, patch_size, ...) (rxmesh_static.h:61-100). patcher_file's role (a saved
     // patching) is played by an explicit face -> patch array.
-    explicit RXMeshStatic(const std::vector<std::vector<uint32_t>>& fv, const std::vector<uint32_t>& face_patch = {},
-                          const uint32_t patch_size = 512)
+    // extension: an explicit face -> patch array instead of a saved file
+    RXMeshStatic(const std::vector<std::vector<uint32_t>>& fv, const std::vector<uint32_t>& face_patch,
+                 const uint32_t patch_size)
     {
         std::vector<uint32_t> flat;
         flat.reserve(3 * fv.size());
@@ -73,12 +74,18 @@ class RXMeshStatic
     }
     // RXMeshStatic(fv, patcher_file, patch_size): replay a patching saved by Patcher::save / RXMesh::save
     // (rxmesh_static.h:61-66, patcher/patcher.h:154-182)
-    RXMeshStatic(const std::vector<std::vector<uint32_t>>& fv, const std::string& patcher_file, const uint32_t patch_size = 512)
+    explicit RXMeshStatic(const std::vector<std::vector<uint32_t>>& fv, const std::string patcher_file = "",
+                          const uint32_t patch_size = 512)
     {
         std::vector<uint32_t> flat;
         flat.reserve(3 * fv.size());
-        for (const auto& f : fv)
+        for (const auto& f : fv) {
+            if (f.size() != 3) {  // rxmesh.cpp:590-597
+                fprintf(stderr, "rxmesh_b200: non-triangular faces are not supported\n");
+                exit(EXIT_FAILURE);
+            }
             flat.insert(flat.end(), f.begin(), f.end());
+        }
         std::vector<uint32_t> face_patch;
         uint32_t              ps = patch_size;
         if (!patcher_file.empty()) {

@@ -77,7 +77,7 @@ static void host_for_each(RXMeshStatic& rx, L f)
 static int app_valence(const uint32_t* fv, uint32_t nf, uint32_t patch_size, float* out_valence, float* out_plus1)
 {
     rx_init(0);
-    RXMeshStatic rx(to_faces(fv, nf), {}, patch_size);
+    RXMeshStatic rx(to_faces(fv, nf), "", patch_size);
     auto val = *rx.add_vertex_attribute<float>("val", 1, LOCATION_ALL);
     auto one = *rx.add_vertex_attribute<float>("one", 1, LOCATION_ALL);
     val.reset(-1.f, DEVICE);
@@ -129,7 +129,7 @@ static int run_query(RXMeshStatic& rx, uint32_t width, bool oriented, uint32_t* 
 static int app_vertex_normals(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, float* out)
 {
     rx_init(0);
-    RXMeshStatic rx(to_faces(fv, nf), {}, patch_size);
+    RXMeshStatic rx(to_faces(fv, nf), "", patch_size);
     constexpr uint32_t blockThreads = 256;
     auto coords    = rx.add_vertex_attribute<float>(to_verts(x, nv), "coordinates");
     auto v_normals = rx.add_vertex_attribute<float>("v_normals", 3, LOCATION_ALL);
@@ -153,7 +153,7 @@ static int app_smoothing(const uint32_t* fv, uint32_t nf, const float* x, uint32
                          int num_iter, int oriented, float* out)
 {
     rx_init(0);
-    RXMeshStatic rx(to_faces(fv, nf), {}, patch_size);
+    RXMeshStatic rx(to_faces(fv, nf), "", patch_size);
     constexpr int blockThreads = 256;
     auto pos  = *rx.add_vertex_attribute<float>(to_verts(x, nv), "pos");
     auto grad = *rx.add_vertex_attribute<float>("grad", 3, LOCATION_ALL);
@@ -188,7 +188,7 @@ static int app_query(int op, const uint32_t* fv, uint32_t nf, uint32_t patch_siz
                      uint32_t* out_global)
 {
     rx_init(0);
-    RXMeshStatic rx(to_faces(fv, nf), {}, patch_size);
+    RXMeshStatic rx(to_faces(fv, nf), "", patch_size);
     switch ((Op)op) {
         case Op::VV: return run_query<Op::VV, VertexHandle, VertexHandle>(rx, width, oriented, out_global);
         case Op::VE: return run_query<Op::VE, VertexHandle, EdgeHandle>(rx, width, oriented, out_global);
