@@ -1105,8 +1105,7 @@ int pick_kmax(uint32_t nnz)
 // 62-85 % of the HBM roofline (profiles/r01_tile_sweep.txt).
 static bool use_persistent()
 {
-    static const bool on = getenv("RXM_PERSIST") != nullptr;
-    return on;
+    return getenv("RXM_PERSIST") != nullptr;  // read per launch so tests can switch it
 }
 
 static int num_sms()
