@@ -202,6 +202,12 @@ int rxm_ipc_export(void* dev_ptr, void* handle64);        /* cudaIpcGetMemHandle
 int rxm_ipc_open(const void* handle64, void** dev_ptr);   /* cudaIpcOpenMemHandle */
 int rxm_ipc_close(void* dev_ptr);
 
+/* ReduceHandle (reduce_handle.h:64-166, reduce_handle.cu:53-156) over the OWNED elements of fp32 attributes.
+ * kind: 0 dot(a,b), 1 sum of squares (norm2 = sqrt), 2 sum, 3 min, 4 max, 5 arg-min, 6 arg-max.
+ * attribute_id = 0xFFFFFFFF -> all attributes. out_handle (arg ops): 64-bit owner handle. */
+int rxm_attr_reduce(rxm_attr* a, rxm_attr* b, int kind, uint32_t attribute_id, double* out_value, uint64_t* out_handle,
+                    void* stream);
+
 /* Saved patchings: the reference's Patcher::save / Patcher(filename) (patcher/patcher.h:154-182; the
  * `patcher_file` constructor argument, rxmesh_static.h:61-66), cereal PortableBinary layout. header = patch_size,
  * num_patches, num_vertices, num_edges, num_faces, num_seeds, max_num_patches, num_components, num_lloyd_run;

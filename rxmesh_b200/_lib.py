@@ -85,6 +85,8 @@ SYMBOLS = {
     "rxm_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rxm_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "rxm_ipc_close": (C.c_int, [C.c_void_p]),
+    "rxm_attr_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.POINTER(C.c_double),
+                                  C.POINTER(C.c_uint64), C.c_void_p]),
     "rxm_patcher_file_read": (C.c_int, [C.c_char_p, C.POINTER(PatcherFile)]),
     "rxm_patcher_file_free": (None, [C.POINTER(PatcherFile)]),
     "rxm_mesh_save_patcher_file": (C.c_int, [C.c_void_p, C.c_char_p]),

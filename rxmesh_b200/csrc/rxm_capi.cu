@@ -965,6 +965,32 @@ int rxm_ipc_close(void* dev_ptr)
     return RXM_OK;
 }
 
+// ------------------------------------------------------------------ reductions (ReduceHandle)
+int rxm_attr_reduce(rxm_attr* a, rxm_attr* b, int kind, uint32_t attribute_id, double* out_value, uint64_t* out_handle,
+                    void* stream)
+{
+    if (!a || !a->d || a->elem_bytes != 4) return fail(RXM_ERR_INVALID, "rxm_attr_reduce: needs a device fp32 attribute");
+    if (kind < 0 || kind > 6) return fail(RXM_ERR_INVALID, "rxm_attr_reduce: unknown kind");
+    if (kind == 0 && (!b || !b->d || b->elem != a->elem || b->nattr != a->nattr || b->layout != a->layout || b->elem_bytes != 4))
+        return fail(RXM_ERR_INVALID, "rxm_attr_reduce: dot needs two attributes of the same shape");
+    if (attribute_id != INVALID32_ && attribute_id >= a->nattr) return fail(RXM_ERR_INVALID, "rxm_attr_reduce: attribute_id out of range");
+    rxm_mesh* m = a->m;
+    int       rc = check_dev(m, "rxm_attr_reduce");
+    if (rc) return rc;
+    const uint32_t grid = std::min<uint32_t>(m->view.num_patches, 148u * 8u);
+    if ((rc = ensure_stage(m, ((size_t)grid + 1) * 16, 1))) return rc;
+    MeshView full = m->view;  // reductions cover every owned element of the (local) mesh
+    cudaError_t e = launch_reduce(full, view_of<float>(a), kind == 0 ? view_of<float>(b) : view_of<float>(a), a->elem, kind,
+                                  attribute_id, m->d_stage[1], grid, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(RXM_ERR_CUDA, std::string("reduce: ") + cudaGetErrorString(e));
+    struct { double v; uint64_t h; } r;
+    CU(cudaMemcpyAsync(&r, (char*)m->d_stage[1] + (size_t)grid * 16, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    if (out_value) *out_value = r.v;
+    if (out_handle) *out_handle = r.h;
+    return RXM_OK;
+}
+
 // ------------------------------------------------------------------ saved patchings
 // The reference's Patcher::serialize layout (patcher/patcher.h:162-182) in cereal's PortableBinary archive:
 // 1 byte (1 = little endian), 9 x u32 scalars, 7 x (u64 length + u32[length]), 1 x f32.

@@ -927,6 +927,72 @@ __global__ void __launch_bounds__(128) k_bilateral(const uint32_t* __restrict__ 
 }
 
 // --------------------------------------------------------------------------
+// reductions over OWNED elements (ReduceHandle: reduce_handle.cu:53-156, kernels/reduce.cuh:43-191)
+// kind: 0 dot, 1 sum of squares, 2 sum, 3 min, 4 max, 5 arg-min, 6 arg-max.  fp32 values, fp64 partials.
+// --------------------------------------------------------------------------
+struct RedPair
+{
+    double   v;
+    uint64_t h;
+};
+
+__device__ __forceinline__ RedPair red_combine(int kind, RedPair a, RedPair b)
+{
+    if (kind <= 2) return RedPair{a.v + b.v, 0};
+    const bool take_min = (kind == 3 || kind == 5);
+    const bool b_better = take_min ? (b.v < a.v) : (b.v > a.v);
+    if (b_better || (b.v == a.v && b.h < a.h)) return b;  // ties: smallest handle, deterministic
+    return a;
+}
+
+__global__ void __launch_bounds__(256) k_reduce_stage1(MeshView mv, AttrView<float> a, AttrView<float> b, int elem, int kind,
+                                                       uint32_t attr_id, RedPair* __restrict__ partial)
+{
+    __shared__ RedPair s_w[8];
+    const double init = kind <= 2 ? 0.0 : ((kind == 3 || kind == 5) ? 1e300 : -1e300);
+    RedPair      acc{init, INVALID64_};
+    for (uint32_t p = blockIdx.x; p < mv.num_patches; p += gridDim.x) {
+        const PatchDesc* d   = mv.desc + p;
+        const uint32_t   no  = d->n_owned[elem], sb = d->slot_base[elem], cap = (no + 3u) & ~3u, pid = d->patch_id;
+        const uint32_t   na  = attr_id == INVALID32_ ? a.nattr : 1u;
+        for (uint32_t i = threadIdx.x; i < no * na; i += blockDim.x) {
+            const uint32_t lid = i % no, k = attr_id == INVALID32_ ? i / no : attr_id;
+            const float    x = a.data[a.index_known(sb, cap, lid, k)];
+            RedPair        c;
+            if (kind == 0)
+                c = RedPair{(double)x * (double)b.data[b.index_known(sb, cap, lid, k)], 0};
+            else if (kind == 1)
+                c = RedPair{(double)x * (double)x, 0};
+            else
+                c = RedPair{(double)x, ((uint64_t)pid << 32) | lid};
+            acc = red_combine(kind, acc, c);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        RedPair t;
+        t.v = __shfl_xor_sync(0xffffffffu, acc.v, o);
+        t.h = __shfl_xor_sync(0xffffffffu, acc.h, o);
+        acc = red_combine(kind, acc, t);
+    }
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (uint32_t w = 1; w < blockDim.x / 32; ++w)
+            acc = red_combine(kind, acc, s_w[w]);
+        partial[blockIdx.x] = acc;
+    }
+}
+
+__global__ void k_reduce_stage2(const RedPair* __restrict__ partial, uint32_t n, int kind, RedPair* __restrict__ out)
+{
+    RedPair acc = partial[0];
+    for (uint32_t i = 1; i < n; ++i)  // n <= a few thousand: one thread, deterministic order
+        acc = red_combine(kind, acc, partial[i]);
+    *out = acc;
+}
+
+// --------------------------------------------------------------------------
 // boundary vertices: an edge with one incident face marks its two vertices
 // --------------------------------------------------------------------------
 template <int KMAX, bool PACKED>
@@ -1465,6 +1531,16 @@ cudaError_t launch_push_rows(const void* local, const uint32_t* local_idx, void*
     const uint32_t grid = (uint32_t)std::min<uint64_t>((n * row_words + 255) / 256, 148ull * 16);
     k_push_rows<<<grid, 256, 0, stream>>>((const uint32_t*)local, local_idx, (uint32_t*)remote, remote_idx, n, row_words);
     ++g_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reduce(const MeshView& mv, AttrView<float> a, AttrView<float> b, int elem, int kind, uint32_t attr_id,
+                          void* scratch /* (grid+1) * 16 bytes */, uint32_t grid, cudaStream_t stream)
+{
+    RedPair* part = reinterpret_cast<RedPair*>(scratch);
+    k_reduce_stage1<<<grid, 256, 0, stream>>>(mv, a, b, elem, kind, attr_id, part);
+    k_reduce_stage2<<<1, 1, 0, stream>>>(part, grid, kind, part + grid);
+    g_launches += 2;
     return cudaGetLastError();
 }
 

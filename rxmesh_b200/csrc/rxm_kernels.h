@@ -56,6 +56,10 @@ cudaError_t launch_slot_rows(bool gather, void* attr, const uint32_t* idx, uint6
 cudaError_t launch_push_rows(const void* local, const uint32_t* local_idx, void* remote, const uint32_t* remote_idx,
                              uint64_t n, uint32_t row_words, cudaStream_t stream);
 
+// reductions over owned elements; scratch: (grid + 1) x 16 bytes, result (double value, u64 handle) at scratch[grid]
+cudaError_t launch_reduce(const MeshView& mv, AttrView<float> a, AttrView<float> b, int elem, int kind, uint32_t attr_id,
+                          void* scratch, uint32_t grid, cudaStream_t stream);
+
 cudaError_t launch_fill(void* data, uint64_t count, uint32_t elem_bytes, const void* value, cudaStream_t stream);
 
 // number of kernels launched by this library since load (bench.py "gpu_launches")

@@ -135,6 +135,31 @@ class Attribute:
                                              _stream_ptr(stream)))
         return out
 
+    # ---- ReduceHandle (reduce_handle.h:64-166) ----
+    def _reduce(self, kind, other=None, attribute_id=None, stream=None):
+        v, h = C.c_double(), C.c_uint64()
+        check(lib().rxm_attr_reduce(self._h, other._h if other is not None else None, kind,
+                                    0xFFFFFFFF if attribute_id is None else int(attribute_id), C.byref(v), C.byref(h),
+                                    _stream_ptr(stream)))
+        return v.value, h.value
+
+    def dot(self, other, attribute_id=None, stream=None):
+        return self._reduce(0, other, attribute_id, stream)[0]
+
+    def norm2(self, attribute_id=None, stream=None):
+        return self._reduce(1, None, attribute_id, stream)[0] ** 0.5
+
+    def reduce(self, op="sum", attribute_id=None, stream=None):
+        return self._reduce({"sum": 2, "min": 3, "max": 4}[op], None, attribute_id, stream)[0]
+
+    def arg_max(self, attribute_id=0, stream=None):
+        v, h = self._reduce(6, None, attribute_id, stream)
+        return h, v
+
+    def arg_min(self, attribute_id=0, stream=None):
+        v, h = self._reduce(5, None, attribute_id, stream)
+        return h, v
+
     def index(self, patch, lid, attr=0):
         """flat storage index of (handle, attr): Attribute::operator() (attribute.h:406-434)."""
         sb = self.mesh.slot_base(self.elem)

@@ -183,3 +183,26 @@ def test_bilateral_filter(built):
         assert np.mean(err < 2e-5 * scale * iters) > 0.995, (name, iters, np.mean(err < 2e-5 * scale * iters))
         # the reference app's own criterion (abs 1e-2, apps/Filtering/filtering_rxmesh.cuh:114-125), scaled
         assert err.max() < 1e-2 * max(1.0, scale)
+
+
+def test_reduce_handle(built):
+    """ReduceHandle: dot / norm2 / reduce / arg-min / arg-max over owned elements (tests/RXMesh_test/test_attribute.cu)"""
+    name, V, F, m, T = built
+    rng = np.random.RandomState(5)
+    for layout in (rx.AoS, rx.AoSoA, rx.SoA):
+        A, B = rng.randn(T.nv, 3).astype(np.float32), rng.randn(T.nv, 3).astype(np.float32)
+        a = rx.Attribute(m, 0, np.float32, 3, rx.LOCATION_ALL, layout)
+        b = rx.Attribute(m, 0, np.float32, 3, rx.LOCATION_ALL, layout)
+        a.from_global(A), b.from_global(B)
+        assert abs(a.dot(b) - np.sum(A.astype(np.float64) * B)) < 1e-6 * T.nv
+        assert abs(a.norm2() - np.sqrt(np.sum(A.astype(np.float64) ** 2))) < 1e-6 * np.sqrt(T.nv)
+        assert abs(a.norm2(1) - np.sqrt(np.sum(A[:, 1].astype(np.float64) ** 2))) < 1e-6 * np.sqrt(T.nv)
+        assert abs(a.reduce("sum") - A.astype(np.float64).sum()) < 1e-6 * T.nv
+        assert a.reduce("max") == A.max() and a.reduce("min", 2) == A[:, 2].min()
+        h, v = a.arg_max(0)
+        assert v == A[:, 0].max() and m.map_to_global(0, np.array([h], np.uint64))[0] == np.argmax(A[:, 0])
+        h, v = a.arg_min(2)
+        assert v == A[:, 2].min() and m.map_to_global(0, np.array([h], np.uint64))[0] == np.argmin(A[:, 2])
+    f = rx.Attribute(m, 2, np.float32, 1, rx.LOCATION_ALL, rx.AoS)
+    f.from_global(np.ones(T.nf, np.float32))
+    assert f.reduce("sum") == T.nf  # padding slots are not counted
