@@ -216,3 +216,32 @@ def csr_to_sets(csr):
     """list of sorted tuples (multiset per source element) for set-equality checks."""
     off, val = csr
     return [tuple(sorted(val[off[i]:off[i + 1]].tolist())) for i in range(off.shape[0] - 1)]
+
+
+def oriented_rings(fv, nv):
+    """rxo_oriented_rings: cyclic one-rings of a closed, consistently oriented manifold mesh (CSR)."""
+    fv = _u32(fv).reshape(-1, 3)
+    off = np.empty(nv + 1, dtype=np.uint32)
+    val = np.empty(3 * fv.shape[0], dtype=np.uint32)
+    bad = lib().rxo_oriented_rings(_p(fv, u32p), fv.shape[0], nv, _p(off, u32p), _p(val, u32p))
+    if bad:
+        raise ValueError("mesh is not closed / consistently oriented")
+    return off, val
+
+
+def mcf_matvec(rings, X, vec_in, time_step):
+    """rxo_mcf_matvec (apps/MCF/mcf_kernels.cuh:117-205), float64."""
+    off, val = rings
+    X, vin = _f32(X).reshape(-1, 3), _f32(vec_in).reshape(-1, 3)
+    out = np.empty(X.shape, dtype=np.float64)
+    lib().rxo_mcf_matvec(_p(off, u32p), _p(val, u32p), X.shape[0], _p(X, f32p), _p(vin, f32p), C.c_double(time_step),
+                         _p(out, f64p))
+    return out
+
+
+def gaussian_curvature(fv, X):
+    """rxo_gaussian_curvature (apps/GaussianCurvature/gaussian_curvature_kernel.cuh:10-69): (gcs, amix), float64."""
+    fv, X = _u32(fv).reshape(-1, 3), _f32(X).reshape(-1, 3)
+    g, a = np.empty(X.shape[0]), np.empty(X.shape[0])
+    lib().rxo_gaussian_curvature(_p(fv, u32p), fv.shape[0], _p(X, f32p), X.shape[0], _p(g, f64p), _p(a, f64p))
+    return g, a

@@ -15,7 +15,7 @@
  * Pinning (see oracle/README.md and tests/test_oracle.py):
  *   - normals:   pinned bit-for-bit against the reference's own
  *                apps/VertexNormal/vertex_normal_ref.h compiled UNMODIFIED into
- *                oracle/_ref/ (fixtures tests/golden/*_vn_ref.npy) and against
+ *                oracle/_ref/ (fixtures tests/golden/<mesh>.npz: vn_ref) and against
  *                the SURVEY.md 8(c) checksums.
  *   - queries:   pinned by the reference's known-answer tests (cube.obj counts
  *                test_for_each.cu:25-29, bunnyhead.obj 98 boundary vertices
@@ -519,5 +519,162 @@ void rxo_consume_sum(const uint32_t* off, const uint32_t* val, uint32_t n_src, c
         for (uint32_t i = off[s]; i < off[s + 1]; ++i)
             a += in[val[i]];
         out[s] = a;
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* Oriented one-rings of a CLOSED, consistently oriented manifold mesh: for    */
+/* vertex v the cyclic sequence of neighbours such that consecutive entries    */
+/* (a, b) span a face (v, a, b); the contract of the reference's oriented VV    */
+/* (kernels/rxmesh_queries.cuh:375-499; start and winding unspecified).         */
+/* off[nv+1], val[3*nf]. Returns 0 on success, 1 if some ring is not a cycle.   */
+/* ------------------------------------------------------------------------ */
+int rxo_oriented_rings(const uint32_t* fv, uint32_t nf, uint32_t nv, uint32_t* off, uint32_t* val)
+{
+    /* next[(v, a)] = b for every face rotation (v, a, b): store per vertex as pairs */
+    uint32_t* cnt = (uint32_t*)calloc((size_t)nv + 1, sizeof(uint32_t));
+    for (uint64_t i = 0; i < (uint64_t)nf * 3; ++i)
+        cnt[fv[i] + 1]++;
+    off[0] = 0;
+    for (uint32_t v = 0; v < nv; ++v)
+        off[v + 1] = off[v] + cnt[v + 1];
+    uint32_t* a = (uint32_t*)malloc((size_t)nf * 3 * sizeof(uint32_t));
+    uint32_t* b = (uint32_t*)malloc((size_t)nf * 3 * sizeof(uint32_t));
+    uint32_t* cur = (uint32_t*)malloc(((size_t)nv + 1) * sizeof(uint32_t));
+    memcpy(cur, off, ((size_t)nv + 1) * sizeof(uint32_t));
+    for (uint32_t f = 0; f < nf; ++f)
+        for (int j = 0; j < 3; ++j) {
+            uint32_t v = fv[3 * (uint64_t)f + j];
+            a[cur[v]]   = fv[3 * (uint64_t)f + (j + 1) % 3];
+            b[cur[v]++] = fv[3 * (uint64_t)f + (j + 2) % 3];
+        }
+    int bad = 0;
+    for (uint32_t v = 0; v < nv && !bad; ++v) {
+        uint32_t k = off[v + 1] - off[v], base = off[v];
+        uint32_t curl = 0;
+        for (uint32_t i = 0; i < k; ++i) {
+            val[base + i] = a[base + curl];
+            uint32_t nxt = b[base + curl], found = k;
+            for (uint32_t j = 0; j < k; ++j)
+                if (a[base + j] == nxt) found = j;
+            if (found == k) { bad = 1; break; }
+            curl = found;
+        }
+        if (!bad && curl != 0) bad = 1; /* must close the cycle */
+    }
+    free(cnt); free(a); free(b); free(cur);
+    return bad;
+}
+
+static double rxo_tri_area(const double* p, const double* q, const double* r)
+{
+    double u[3] = {q[0] - p[0], q[1] - p[1], q[2] - p[2]}, w[3] = {r[0] - p[0], r[1] - p[1], r[2] - p[2]};
+    double c[3] = {u[1] * w[2] - u[2] * w[1], u[2] * w[0] - u[0] * w[2], u[0] * w[1] - u[1] * w[0]};
+    return 0.5 * sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+}
+static double rxo_clamp_cot(double v)
+{
+    return v < -19.1 ? -19.1 : (v > 19.1 ? 19.1 : v);
+}
+/* geometry_util.cuh:120-172 */
+static double rxo_partial_voronoi(const double* p, const double* q, const double* r)
+{
+    double pq[3], qr[3], pr[3];
+    for (int c = 0; c < 3; ++c) pq[c] = q[c] - p[c], qr[c] = r[c] - q[c], pr[c] = r[c] - p[c];
+    double area = rxo_tri_area(p, q, r);
+    if (area <= 1.17549435e-38) return -1;
+    double dotp = pq[0] * pr[0] + pq[1] * pr[1] + pq[2] * pr[2];
+    double dotq = -(qr[0] * pq[0] + qr[1] * pq[1] + qr[2] * pq[2]);
+    double dotr = qr[0] * pr[0] + qr[1] * pr[1] + qr[2] * pr[2];
+    if (dotp < 0) return 0.25 * area;
+    if (dotq < 0 || dotr < 0) return 0.125 * area;
+    double cotq = rxo_clamp_cot(dotq / area), cotr = rxo_clamp_cot(dotr / area);
+    double lpr = pr[0] * pr[0] + pr[1] * pr[1] + pr[2] * pr[2], lpq = pq[0] * pq[0] + pq[1] * pq[1] + pq[2] * pq[2];
+    return 0.125 * (lpr * cotq + lpq * cotr);
+}
+/* geometry_util.cuh:178-206 */
+static double rxo_cot_part(const double* p, const double* r, const double* v)
+{
+    double area = rxo_tri_area(p, r, v);
+    if (area > 1.17549435e-38) {
+        double d = (p[0] - v[0]) * (r[0] - v[0]) + (p[1] - v[1]) * (r[1] - v[1]) + (p[2] - v[2]) * (r[2] - v[2]);
+        return rxo_clamp_cot(d / area);
+    }
+    return 0;
+}
+
+/* MCF matrix-free mat-vec, cotan weights (apps/MCF/mcf_kernels.cuh:117-205):
+ * out(p) = (1/vw + sum_w) in(p) - sum_r w(p,r) in(r), w = max(0, cot_q + cot_s) * time_step,
+ * vw = 0.5 / sum of positive partial Voronoi areas. rings = rxo_oriented_rings. float64 from fp32 inputs. */
+void rxo_mcf_matvec(const uint32_t* off, const uint32_t* val, uint32_t nv, const float* X, const float* in,
+                    double time_step, double* out)
+{
+    for (uint32_t p = 0; p < nv; ++p) {
+        double P[3] = {X[3 * (uint64_t)p], X[3 * (uint64_t)p + 1], X[3 * (uint64_t)p + 2]};
+        uint32_t k = off[p + 1] - off[p];
+        const uint32_t* ring = val + off[p];
+        double sum_w = 0, vw = 0, x[3] = {0, 0, 0};
+        for (uint32_t v = 0; v < k; ++v) {
+            uint32_t qi = ring[(v + k - 1) % k], ri = ring[v], si = ring[(v + 1) % k];
+            double Q[3], R[3], S[3];
+            for (int c = 0; c < 3; ++c)
+                Q[c] = X[3 * (uint64_t)qi + c], R[c] = X[3 * (uint64_t)ri + c], S[c] = X[3 * (uint64_t)si + c];
+            double w = rxo_cot_part(P, R, Q) + rxo_cot_part(P, R, S);
+            if (w < 0) w = 0;
+            w *= time_step;
+            sum_w += w;
+            for (int c = 0; c < 3; ++c)
+                x[c] -= w * in[3 * (uint64_t)ri + c];
+            double ta = rxo_partial_voronoi(P, Q, R);
+            vw += ta > 0 ? ta : 0;
+        }
+        vw = 0.5 / vw;
+        double diag = 1.0 / vw + sum_w;
+        for (int c = 0; c < 3; ++c)
+            out[3 * (uint64_t)p + c] = x[c] + diag * in[3 * (uint64_t)p + c];
+    }
+}
+
+/* Gaussian curvature accumulators (apps/GaussianCurvature/gaussian_curvature_kernel.cuh:10-69):
+ * per face corner v: gcs(v) -= angle_v; amix(v) += mixed Voronoi area share. float64 from fp32 inputs. */
+void rxo_gaussian_curvature(const uint32_t* fv, uint32_t nf, const float* X, uint32_t nv, double* gcs, double* amix)
+{
+    const double PI = 3.14159265358979323846;
+    memset(gcs, 0, (size_t)nv * sizeof(double));
+    memset(amix, 0, (size_t)nv * sizeof(double));
+    for (uint32_t f = 0; f < nf; ++f) {
+        const uint32_t* t = fv + 3 * (uint64_t)f;
+        double c[3][3];
+        for (int i = 0; i < 3; ++i)
+            for (int k = 0; k < 3; ++k)
+                c[i][k] = X[3 * (uint64_t)t[i] + k];
+        double l[3], dt[3], u[3], w[3];
+        for (int i = 0; i < 3; ++i) {
+            int j = (i + 1) % 3;
+            l[i] = 0;
+            for (int k = 0; k < 3; ++k) l[i] += (c[i][k] - c[j][k]) * (c[i][k] - c[j][k]);
+        }
+        for (int k = 0; k < 3; ++k) u[k] = c[1][k] - c[0][k], w[k] = c[2][k] - c[0][k];
+        double cr[3] = {u[1] * w[2] - u[2] * w[1], u[2] * w[0] - u[0] * w[2], u[0] * w[1] - u[1] * w[0]};
+        double s = sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
+        for (int i = 0; i < 3; ++i) {
+            int j = (i + 1) % 3, m = (i + 2) % 3;
+            dt[i] = 0;
+            for (int k = 0; k < 3; ++k) dt[i] += (c[j][k] - c[i][k]) * (c[m][k] - c[i][k]);
+        }
+        double rads[3];
+        int    ob = 0;
+        for (int i = 0; i < 3; ++i) {
+            rads[i] = atan2(s, dt[i]);
+            if (rads[i] > PI * 0.5) ob = 1;
+        }
+        for (int v = 0; v < 3; ++v) {
+            int v1 = (v + 1) % 3, v2 = (v + 2) % 3;
+            if (ob)
+                amix[t[v]] += (rads[v] > PI * 0.5) ? 0.25 * s : 0.125 * s;
+            else
+                amix[t[v]] += 0.125 * (l[v2] * (dt[v1] / s) + l[v] * (dt[v2] / s));
+            gcs[t[v]] -= rads[v];
+        }
     }
 }

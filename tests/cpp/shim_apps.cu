@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "rxmesh/attribute.h"
+#include "rxmesh/geometry_util.cuh"
 #include "rxmesh/query.h"
 #include "rxmesh/rxmesh_static.h"
 
@@ -30,6 +31,75 @@ __global__ static void user_vertex_normal(const Context context, VertexAttribute
     Query<blockThreads> query(context);
     ShmemAllocator      shrd_alloc;
     query.template dispatch<Op::FV>(block, shrd_alloc, vn_lambda);
+}
+
+// the MCF matrix-free mat-vec with cotan weights (apps/MCF/mcf_kernels.cuh:117-205): oriented VV
+template <typename T, uint32_t blockThreads>
+__global__ static void user_mcf_matvec(const Context context, const VertexAttribute<T> coords, const VertexAttribute<T> in,
+                                       VertexAttribute<T> out, const T time_step)
+{
+    auto matvec_lambda = [&](VertexHandle& p_id, const VertexIterator& iter) {
+        T            sum_e_weight(0), v_weight(0);
+        vec3<T>      x(T(0));
+        const vec3<T> p = coords.template to_glm<3>(p_id);
+        VertexHandle q_id = iter.back();
+        for (uint32_t v = 0; v < iter.size(); ++v) {
+            VertexHandle r_id = iter[v];
+            VertexHandle s_id = (v == iter.size() - 1) ? iter[0] : iter[v + 1];
+            const vec3<T> r = coords.template to_glm<3>(r_id), q = coords.template to_glm<3>(q_id),
+                          s = coords.template to_glm<3>(s_id);
+            T e_weight = edge_cotan_weight(p, r, q, s);
+            e_weight   = (static_cast<T>(e_weight >= 0.0)) * e_weight;
+            e_weight *= time_step;
+            sum_e_weight += e_weight;
+            x[0] -= e_weight * in(r_id, 0);
+            x[1] -= e_weight * in(r_id, 1);
+            x[2] -= e_weight * in(r_id, 2);
+            T tri = partial_voronoi_area(p, q, r);
+            v_weight += (tri > 0) ? tri : 0;
+            q_id = r_id;
+        }
+        v_weight     = 0.5 / v_weight;
+        T diag       = ((1.0 / v_weight) + sum_e_weight);
+        out(p_id, 0) = x[0] + diag * in(p_id, 0);
+        out(p_id, 1) = x[1] + diag * in(p_id, 1);
+        out(p_id, 2) = x[2] + diag * in(p_id, 2);
+    };
+    auto                block = cooperative_groups::this_thread_block();
+    Query<blockThreads> query(context);
+    ShmemAllocator      shrd_alloc;
+    query.template dispatch<Op::VV>(block, shrd_alloc, matvec_lambda, [](VertexHandle) { return true; }, true);
+}
+
+// Gaussian curvature accumulators (apps/GaussianCurvature/gaussian_curvature_kernel.cuh:10-69): FV + atomics
+template <typename T, uint32_t blockThreads>
+__global__ static void user_gaussian_curvature(const Context context, VertexAttribute<T> coords, VertexAttribute<T> gcs,
+                                               VertexAttribute<T> amix)
+{
+    auto gc_lambda = [&](FaceHandle, VertexIterator& fv) {
+        const vec3<T> c0 = coords.template to_glm<3>(fv[0]), c1 = coords.template to_glm<3>(fv[1]),
+                      c2 = coords.template to_glm<3>(fv[2]);
+        vec3<T> l(glm::distance2(c0, c1), glm::distance2(c1, c2), glm::distance2(c2, c0));
+        T       s = glm::length(glm::cross(c1 - c0, c2 - c0));
+        vec3<T> c(glm::dot(c1 - c0, c2 - c0), glm::dot(c2 - c1, c0 - c1), glm::dot(c0 - c2, c1 - c2));
+        vec3<T> rads(atan2(s, c[0]), atan2(s, c[1]), atan2(s, c[2]));
+        const T half_pi = T(1.57079632679489661923);
+        bool    is_ob   = false;
+        for (int i = 0; i < 3; ++i)
+            if (rads[i] > half_pi) is_ob = true;
+        for (uint32_t v = 0; v < 3; ++v) {
+            uint32_t v1 = (v + 1) % 3, v2 = (v + 2) % 3;
+            if (is_ob)
+                atomicAdd(&amix(fv[v]), rads[v] > half_pi ? T(0.25) * s : T(0.125) * s);
+            else
+                atomicAdd(&amix(fv[v]), T(0.125) * ((l[v2]) * (c[v1] / s) + (l[v]) * (c[v2] / s)));
+            atomicAdd(&gcs(fv[v]), -rads[v]);
+        }
+    };
+    auto                block = cooperative_groups::this_thread_block();
+    Query<blockThreads> query(context);
+    ShmemAllocator      shrd_alloc;
+    query.template dispatch<Op::FV>(block, shrd_alloc, gc_lambda);
 }
 
 template <uint32_t blockThreads, Op op, typename InH, typename OutH, typename InA, typename OutA>
@@ -91,6 +161,51 @@ static int app_valence(const uint32_t* fv, uint32_t nf, uint32_t patch_size, flo
         out_valence[rx.map_to_global(vh)] = val(vh);
         out_plus1[rx.map_to_global(vh)]   = one(vh);
     });
+    return 0;
+}
+
+static int app_mcf_matvec(const uint32_t* fv, uint32_t nf, const float* x, const float* vin, uint32_t nv, uint32_t patch_size,
+                          float time_step, float* out)
+{
+    rx_init(0);
+    RXMeshStatic rx(to_faces(fv, nf), "", patch_size);
+    constexpr uint32_t blockThreads = 256;
+    auto coords = rx.add_vertex_attribute<float>(to_verts(x, nv), "coords");
+    auto in     = rx.add_vertex_attribute<float>(to_verts(vin, nv), "in");
+    auto res    = rx.add_vertex_attribute<float>("out", 3, LOCATION_ALL);
+    LaunchBox<blockThreads> lb;
+    rx.prepare_launch_box({Op::VV}, lb, (void*)user_mcf_matvec<float, blockThreads>, true);
+    user_mcf_matvec<float, blockThreads><<<lb.blocks, lb.num_threads, lb.smem_bytes_dyn>>>(rx.get_context(), *coords, *in, *res, time_step);
+    if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+    res->move(DEVICE, HOST);
+    rx.for_each_vertex(HOST, [&](const VertexHandle& vh) {
+        for (uint32_t i = 0; i < 3; ++i)
+            out[rx.map_to_global(vh) * 3 + i] = (*res)(vh, i);
+    }, NULL, false);
+    return 0;
+}
+
+static int app_gaussian_curvature(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size,
+                                  float* out_gcs, float* out_amix)
+{
+    rx_init(0);
+    RXMeshStatic rx(to_faces(fv, nf), "", patch_size);
+    constexpr uint32_t blockThreads = 256;
+    auto coords = rx.add_vertex_attribute<float>(to_verts(x, nv), "coords");
+    auto gcs    = rx.add_vertex_attribute<float>("gcs", 1, LOCATION_ALL);
+    auto amix   = rx.add_vertex_attribute<float>("amix", 1, LOCATION_ALL);
+    gcs->reset(0, DEVICE);
+    amix->reset(0, DEVICE);
+    LaunchBox<blockThreads> lb;
+    rx.prepare_launch_box({Op::FV}, lb, (void*)user_gaussian_curvature<float, blockThreads>);
+    user_gaussian_curvature<float, blockThreads><<<lb.blocks, lb.num_threads, lb.smem_bytes_dyn>>>(rx.get_context(), *coords, *gcs, *amix);
+    if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+    gcs->move(DEVICE, HOST);
+    amix->move(DEVICE, HOST);
+    rx.for_each_vertex(HOST, [&](const VertexHandle& vh) {
+        out_gcs[rx.map_to_global(vh)]  = (*gcs)(vh);
+        out_amix[rx.map_to_global(vh)] = (*amix)(vh);
+    }, NULL, false);
     return 0;
 }
 
@@ -215,6 +330,16 @@ int shim_smoothing(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv,
 int shim_valence(const uint32_t* fv, uint32_t nf, uint32_t patch_size, float* out_valence, float* out_plus1)
 {
     return app_valence(fv, nf, patch_size, out_valence, out_plus1);
+}
+int shim_mcf_matvec(const uint32_t* fv, uint32_t nf, const float* x, const float* vin, uint32_t nv, uint32_t patch_size,
+                    float time_step, float* out)
+{
+    return app_mcf_matvec(fv, nf, x, vin, nv, patch_size, time_step, out);
+}
+int shim_gaussian_curvature(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, float* out_gcs,
+                            float* out_amix)
+{
+    return app_gaussian_curvature(fv, nf, x, nv, patch_size, out_gcs, out_amix);
 }
 int shim_query(int op, const uint32_t* fv, uint32_t nf, uint32_t patch_size, uint32_t width, int oriented, uint32_t* out_global)
 {

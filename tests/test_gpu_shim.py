@@ -96,3 +96,29 @@ def test_oriented_vv(shim):
         ring = [int(u) for u in out[v] if u != 0xFFFFFFFF]
         assert tuple(sorted(ring)) == vv[v]
         assert all((v, a, b) in faces for a, b in zip(ring, ring[1:] + ring[:1]))  # closed mesh: cyclic
+
+
+@pytest.mark.parametrize("name", ["sphere3", "torus", "dragon"])
+def test_user_mcf_matvec(shim, name):
+    """MCF cotan-Laplacian mat-vec (apps/MCF/mcf_kernels.cuh:117-205) as a user kernel on ORIENTED VV."""
+    V, F = make_mesh(name)
+    rng = np.random.RandomState(2)
+    vin = (V + 0.01 * rng.randn(*V.shape)).astype(np.float32)
+    out = np.zeros_like(V)
+    dt = 10.0
+    assert shim.shim_mcf_matvec(_p(F), F.shape[0], _p(V), _p(vin), V.shape[0], 512, C.c_float(dt), _p(out)) == 0
+    ref = O.mcf_matvec(O.oriented_rings(F, V.shape[0]), V, vin, dt)
+    rel = np.linalg.norm(out - ref, axis=1) / np.maximum(np.linalg.norm(ref, axis=1), 1e-30)
+    assert np.quantile(rel, 0.999) < 2e-4 and rel.max() < 2e-2, (np.quantile(rel, 0.999), rel.max())
+
+
+@pytest.mark.parametrize("name", ["sphere3", "dragon", "bunnyhead"])
+def test_user_gaussian_curvature(shim, name):
+    V, F = make_mesh(name)
+    g, a = np.zeros(V.shape[0], np.float32), np.zeros(V.shape[0], np.float32)
+    assert shim.shim_gaussian_curvature(_p(F), F.shape[0], _p(V), V.shape[0], 512, _p(g), _p(a)) == 0
+    rg, ra = O.gaussian_curvature(F, V)
+    assert np.abs(g - rg).max() < 1e-4 * np.abs(rg).max()
+    assert np.abs(a - ra).max() < 1e-4 * np.abs(ra).max()
+    if name == "sphere3":  # Gauss-Bonnet on a closed genus-0 mesh: sum(2 pi - angles) = 4 pi
+        assert abs((2 * np.pi + rg).sum() - 4 * np.pi) < 1e-6
