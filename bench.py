@@ -156,6 +156,40 @@ def cpu_baseline(sample_faces, repeats):
     }, (V, F, T, vv, vf)
 
 
+def reference_gpu_sample(sample_faces, nrun=20, timeout=240):
+    """The reference's OWN GPU kernels (oracle/_ref/ref_gpu_queries: rxmesh.cpp + patcher + Query<256>::dispatch
+    compiled unmodified for sm_100a, see oracle/ref_gpu_queries.cu) on a bounded sample of the workload, this GPU.
+    Reported next to our numbers; never on the product path."""
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_gpu_queries")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/ref_gpu_queries not built (needs /root/reference at build time)"}
+    V, F, n = cpu_sample_mesh(sample_faces)
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            mesh = os.path.join(td, "mesh.bin")
+            with open(mesh, "wb") as fh:
+                np.asarray([V.shape[0], F.shape[0]], np.uint32).tofile(fh)
+                np.ascontiguousarray(F, np.uint32).tofile(fh)
+                np.ascontiguousarray(V, np.float32).tofile(fh)
+            r = subprocess.run([exe, mesh, td, "512", "0", str(nrun)], capture_output=True, text=True, timeout=timeout)
+            if r.returncode != 0:
+                return {"unavailable": "reference binary failed: " + (r.stderr or r.stdout)[-200:]}
+            meta = json.load(open(os.path.join(td, "meta.json")))
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": str(e)[:200]}
+    ms = {"VV": meta["consume"]["VV"], "VF": meta["consume"]["VF"], "VN": meta["vertex_normals"]["ms"]}
+    step = sum(ms.values())
+    return {"value": F.shape[0] / (step * 1e-3), "unit": "faces/s", "ms": ms, "ms_per_step": step,
+            "patches": meta["patches"], "patch_size": 512, "build_seconds": meta["build_ms"] / 1e3,
+            "blocks_per_sm": meta["ops"]["VV"]["blocks_per_sm"], "regs": meta["ops"]["VV"]["regs"],
+            "sample": ("%d x %d grid (%d faces) of the same generator; the reference's unmodified Query<256>::dispatch "
+                       "VV / VF consume lambdas + its FV vertex-normal lambda (global atomics) over raw per-patch arrays, "
+                       "its own Lloyd patching at its default patch size; its host build is O(patches x elements), so "
+                       "the full 100M-face mesh is out of its reach (111 s at 20M faces); kernel time scales linearly "
+                       "with faces (profiles/r01_reference_gpu_vs_ours.jsonl)") % (n, n, F.shape[0])}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -393,6 +427,7 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and not args.no_cpu:
         cb, _ = cpu_baseline(min(args.faces, args.cpu_sample_faces), 3)
         line["cpu_baseline"] = cb
+        line["reference_gpu"] = reference_gpu_sample(min(args.faces, args.cpu_sample_faces))
     print(json.dumps(line), flush=True)
 
 

@@ -19,6 +19,7 @@
 //
 // usage: ref_gpu_queries <mesh.bin> <outdir> [patch_size=512] [dump=1] [nrun=100]
 //   mesh.bin = u32 nv, u32 nf, u32 fv[3 nf], f32 x[3 nv]
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -129,6 +130,27 @@ __global__ static void ref_vertex_normal_kernel(const Context context, RawAttr3 
     Query<blockThreads> query(context);
     ShmemAllocator      shrd_alloc;
     query.template dispatch<Op::FV>(block, shrd_alloc, vn_lambda);
+}
+
+// "consume" variant (the roofline kernels of bench.py): out(s) = sum_i in(iter[i]) over raw
+// per-patch arrays, one fp32 per element (row = patch * cap + local id, the reference's slab addressing)
+template <uint32_t blockThreads, Op op, typename InH, typename OutH>
+__global__ static void ref_consume_kernel(const Context context, const float* in, uint32_t cap_in, float* out,
+                                          uint32_t cap_out)
+{
+    auto sum_lambda = [&](const InH& id, const Iterator<OutH>& iter) {
+        float a = 0.f;
+        for (uint32_t i = 0; i < iter.size(); ++i) {
+            const auto pl = iter[i].unpack();
+            a += in[(size_t)pl.first * cap_in + pl.second];
+        }
+        const auto pl                            = id.unpack();
+        out[(size_t)pl.first * cap_out + pl.second] = a;
+    };
+    auto                block = cooperative_groups::this_thread_block();
+    Query<blockThreads> query(context);
+    ShmemAllocator      shrd_alloc;
+    query.template dispatch<op>(block, shrd_alloc, sum_lambda);
 }
 
 static void write_file(const std::string& path, const void* p, size_t bytes)
@@ -331,6 +353,59 @@ int main(int argc, char** argv)
         CK(cudaFree(normals.data));
     }
 
+    // consume variants of VV and VF (inputs = 1.0 everywhere, so out = neighbour count: checked on the host)
+    double cons_ms[2] = {0, 0};
+    {
+        const uint32_t capv = rx.max_per_patch(0), capf = rx.max_per_patch(2);
+        float *        d_inv, *d_inf, *d_out;
+        CK(cudaMalloc(&d_inv, (size_t)P * capv * 4));
+        CK(cudaMalloc(&d_inf, (size_t)P * capf * 4));
+        CK(cudaMalloc(&d_out, (size_t)P * capv * 4));
+        std::vector<float> ones((size_t)P * std::max(capv, capf), 1.0f);
+        CK(cudaMemcpy(d_inv, ones.data(), (size_t)P * capv * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_inf, ones.data(), (size_t)P * capf * 4, cudaMemcpyHostToDevice));
+        auto kvv = ref_consume_kernel<BT, Op::VV, VertexHandle, VertexHandle>;
+        auto kvf = ref_consume_kernel<BT, Op::VF, VertexHandle, FaceHandle>;
+        CK(cudaFuncSetAttribute(kvv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_smem));
+        CK(cudaFuncSetAttribute(kvf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_smem));
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a));
+        CK(cudaEventCreate(&b));
+        for (int which = 0; which < 2; ++which) {
+            auto launch = [&]() {
+                if (which == 0)
+                    kvv<<<P, BT, g_smem>>>(rx.get_context(), d_inv, capv, d_out, capv);
+                else
+                    kvf<<<P, BT, g_smem>>>(rx.get_context(), d_inf, capf, d_out, capv);
+            };
+            CK(cudaMemset(d_out, 0, (size_t)P * capv * 4));
+            launch();
+            CK(cudaDeviceSynchronize());
+            CK(cudaEventRecord(a));
+            for (int i = 0; i < nrun; ++i)
+                launch();
+            CK(cudaEventRecord(b));
+            CK(cudaEventSynchronize(b));
+            float ms;
+            CK(cudaEventElapsedTime(&ms, a, b));
+            cons_ms[which] = ms / nrun;
+            std::vector<float> ho((size_t)P * capv);
+            CK(cudaMemcpy(ho.data(), d_out, ho.size() * 4, cudaMemcpyDeviceToHost));
+            double total = 0;
+            for (uint32_t p = 0; p < P; ++p)
+                for (uint32_t l = 0; l < rx.ltog(0)[p].size(); ++l)
+                    if (detail::is_owned((uint16_t)l, rx.owned_mask(p, 0))) total += ho[(size_t)p * capv + l];
+            const double want = which == 0 ? 2.0 * rx.get_num_edges() : 3.0 * rx.get_num_faces();
+            if (total != want) {
+                fprintf(stderr, "consume %d: sum %.0f != %.0f\n", which, total, want);
+                exit(4);
+            }
+        }
+        CK(cudaFree(d_inv));
+        CK(cudaFree(d_inf));
+        CK(cudaFree(d_out));
+    }
+
     if (dump) {
         write_file(outdir + "/face_patch.u32", rx.face_patch().data(), (size_t)nf * 4);
         const char* tn[3] = {"v", "e", "f"};
@@ -362,7 +437,9 @@ int main(int argc, char** argv)
                  i ? ", " : "", runs[i].name, runs[i].ms, runs[i].width, runs[i].occupancy, runs[i].regs, runs[i].smem_static);
         js += buf;
     }
-    snprintf(buf, sizeof buf, "}, \"vertex_normals\": {\"ms\": %.6f, \"blocks_per_sm\": %d}}", vn_ms, vn_occ);
+    snprintf(buf, sizeof buf,
+             "}, \"vertex_normals\": {\"ms\": %.6f, \"blocks_per_sm\": %d}, \"consume\": {\"VV\": %.6f, \"VF\": %.6f}}", vn_ms,
+             vn_occ, cons_ms[0], cons_ms[1]);
     js += buf;
     write_file(outdir + "/meta.json", js.data(), js.size());
     printf("%s\n", js.c_str());

@@ -102,6 +102,58 @@ __device__ __forceinline__ float ldg_stream(const float* p)
     return v;
 }
 
+// ------------------------------------------------------------------ packed fp32x2 arithmetic
+// sm_100a executes two fp32 operations per issued instruction (SASS FFMA2 / FADD2 / FMUL2, PTX *.f32x2).
+// The FP32 pipe time is that of two scalar instructions, but only ONE issue slot is spent, and integer / LSU
+// instructions issue in the shadow (scripts/microbench/ffma2.cu: 8 FFMA2 + 8 IADD take the cycles of 8 FFMA2
+// alone, 16 FFMA + 8 IADD take the sum).  The fan kernels are issue-bound, so they process TWO vertices per
+// thread with every arithmetic instruction packed across the pair.  Each lane is an ordinary IEEE fp32
+// operation: results are bit-identical to the scalar code.
+struct f2
+{
+    unsigned long long v;
+};
+__device__ __forceinline__ f2 pk(float lo, float hi)
+{
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk(f2 a, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+}
+__device__ __forceinline__ f2 neg2(f2 a)  // folded by ptxas into the consumer's operand modifier
+{
+    float lo, hi;
+    upk(a, lo, hi);
+    return pk(-lo, -hi);
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b)
+{
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b)
+{
+    f2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b)
+{
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c)
+{
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+
 // ------------------------------------------------------------------ shared memory carve-up
 // Bump allocator over dynamic shared memory; every allocation is 16-byte aligned
 // (TMA destinations need it; the reference aligns to 8, shmem_allocator.cuh:17).

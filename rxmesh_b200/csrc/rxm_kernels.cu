@@ -497,6 +497,165 @@ __global__ void __launch_bounds__(BT, 8) k_vertex_normals_fan(MeshView mv, const
     fan_store(d, F, nrm);
 }
 
+// ---- two vertices per thread, packed fp32x2 arithmetic ----
+// Evidence for the redesign (profiles/r01_ncu_full_tile32x16.csv, k_vertex_normals_fan; profiles/r01_vn_fan2_ncu.txt):
+// the one-vertex-per-thread kernel sits at 74 % issue-active AND 78 % of the L1 data-pipe wavefront peak, DRAM at
+// 57 %.  (1) Thread t owns vertices (t, t + BT2) and every subtraction / product / FMA of the pair is ONE FADD2 /
+// FMUL2 / FFMA2 (dev::f2): 40 % fewer issued instructions.  (2) Shared-memory wavefronts are the remaining limiter,
+// so nothing is staged twice: neighbours are read straight from the AoS slice the TMA delivered (3 LDS.32 at a
+// 12-byte stride = 3 conflict-free wavefronts; the old float4 copy cost 4 per gather plus the conversion pass),
+// ribbon vertices are gathered into the tail of the same array, fan ids are fetched two per LDS.32, and the result
+// goes to its own buffer so no barrier separates compute from store.
+constexpr int BT2 = 128;
+
+struct FanPatch2
+{
+    const uint16_t* s_fo;
+    const uint16_t* s_fv;
+    const float*    s_x;    // AoS xyz of every local vertex: [0, 3 nov) by TMA, [3 nov, 3 nv) gathered from the owners
+    float*          s_out;  // 3*cap floats, bulk-stored to the patch's owned slice
+    uint32_t        nv, nov, cap;
+};
+
+__device__ __forceinline__ FanPatch2 fan_load2(const MeshView& mv, const PatchDesc& d, const float* __restrict__ x,
+                                               uint8_t* smem_raw, uint64_t* bar)
+{
+    const uint8_t* blob = mv.topo + d.topo_off;
+    FanPatch2      F;
+    F.nv = d.n[ELEM_V], F.nov = d.n_owned[ELEM_V], F.cap = d.slot_cap(ELEM_V);
+    Smem        sm(smem_raw);
+    uint16_t*   s_fo    = sm.alloc<uint16_t>(d.fanoff_bytes() / 2);
+    uint16_t*   s_fv    = sm.alloc<uint16_t>(d.fanv_bytes() / 2);
+    uint32_t*   s_own   = sm.alloc<uint32_t>(d.own_bytes(ELEM_V) / 4);
+    StashEntry* s_stash = sm.alloc<StashEntry>(d.n_stash);
+    float*      s_x     = sm.alloc<float>(3 * max(F.nv, F.cap));
+    F.s_out             = sm.alloc<float>(3 * F.cap);
+    F.s_fo = s_fo, F.s_fv = s_fv, F.s_x = s_x;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(bar, d.fanoff_bytes() + d.fanv_bytes() + d.own_bytes(ELEM_V) + d.stash_bytes() + 12u * F.cap);
+        bulk_g2s(s_fo, blob + d.off_fanoff(), d.fanoff_bytes(), bar);
+        if (d.fanv_bytes()) bulk_g2s(s_fv, blob + d.off_fanv(), d.fanv_bytes(), bar);
+        if (d.own_bytes(ELEM_V)) bulk_g2s(s_own, blob + d.off_own(ELEM_V), d.own_bytes(ELEM_V), bar);
+        if (d.stash_bytes()) bulk_g2s(s_stash, blob + d.off_stash(), d.stash_bytes(), bar);
+        if (F.cap) bulk_g2s(s_x, x + 3ull * d.slot_base[ELEM_V], 12u * F.cap, bar);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+    for (uint32_t i = F.nov + threadIdx.x; i < F.nv; i += BT2) {  // ribbon vertices: from their owners' slots
+        const uint32_t o = s_own[i - F.nov];
+        const float*   g = x + 3ull * ((uint64_t)s_stash[o >> 16].slot_base[ELEM_V] + (o & 0xFFFFu));
+        const float    a = ldg_stream(g), b = ldg_stream(g + 1), c = ldg_stream(g + 2);
+        s_x[3 * i] = a, s_x[3 * i + 1] = b, s_x[3 * i + 2] = c;
+    }
+    __syncthreads();
+    return F;
+}
+
+// one vertex, any valence, open or closed fan (scalar arithmetic)
+template <int UNIT>
+__device__ __forceinline__ void vn_one(const FanPatch2& F, uint32_t v, float& sx, float& sy, float& sz)
+{
+    const uint32_t o = F.s_fo[v], b = o & FAN_OFF_MASK, e = F.s_fo[v + 1] & FAN_OFF_MASK;
+    const float    X = F.s_x[3 * v], Y = F.s_x[3 * v + 1], Z = F.s_x[3 * v + 2];
+    sx = sy = sz = 0.f;
+    if (b == e) return;
+    auto face = [&](float px, float py, float pz, float pl, float cx, float cy, float cz, float cl) {
+        const float nx = py * cz - pz * cy, ny = pz * cx - px * cz, nz = px * cy - py * cx;
+        const float w  = UNIT ? rsqrtf(nx * nx + ny * ny + nz * nz) : fast_rcp(pl + cl);
+        sx += nx * w, sy += ny * w, sz += nz * w;
+    };
+    const float* q   = F.s_x + 3u * F.s_fv[b];
+    const float  d0x = q[0] - X, d0y = q[1] - Y, d0z = q[2] - Z;
+    const float  l0  = d0x * d0x + d0y * d0y + d0z * d0z;
+    float        px = d0x, py = d0y, pz = d0z, pl = l0;
+    for (uint32_t i = b + 1; i < e; ++i) {
+        q              = F.s_x + 3u * F.s_fv[i];
+        const float cx = q[0] - X, cy = q[1] - Y, cz = q[2] - Z;
+        const float cl = cx * cx + cy * cy + cz * cz;
+        face(px, py, pz, pl, cx, cy, cz, cl);
+        px = cx, py = cy, pz = cz, pl = cl;
+    }
+    if (o & FAN_CLOSED) face(px, py, pz, pl, d0x, d0y, d0z, l0);
+}
+
+template <int UNIT>
+__global__ void __launch_bounds__(BT2, 8) k_vertex_normals_fan2(MeshView mv, const float* __restrict__ x,
+                                                              float* __restrict__ nrm)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint64_t                      bar;
+    const PatchDesc d = load_desc(mv.desc + blockIdx.x);
+    const FanPatch2 F = fan_load2(mv, d, x, smem_raw, &bar);
+    for (uint32_t vA = threadIdx.x; vA < F.cap; vA += 2 * BT2) {
+        const uint32_t vB = vA + BT2;
+        float          ax = 0.f, ay = 0.f, az = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+        bool           fast = false;
+        uint32_t       bA = 0, bB = 0;
+        if (vB < F.nov) {
+            const uint32_t oA = F.s_fo[vA], eA = F.s_fo[vA + 1] & FAN_OFF_MASK;
+            const uint32_t oB = F.s_fo[vB], eB = F.s_fo[vB + 1] & FAN_OFF_MASK;
+            bA = oA & FAN_OFF_MASK, bB = oB & FAN_OFF_MASK;
+            // both fans closed with valence 6 (the regular case), ids readable as aligned 32-bit pairs
+            fast = (oA & oB & FAN_CLOSED) && eA - bA == 6 && eB - bB == 6 && ((bA | bB) & 1u) == 0;
+        }
+        if (fast) {
+            // straight-line packed code: lane 0 of every f2 belongs to vertex A, lane 1 to vertex B
+            const float *pa = F.s_x + 3u * vA, *pb = F.s_x + 3u * vB;
+            const f2     PX = pk(pa[0], pb[0]), PY = pk(pa[1], pb[1]), PZ = pk(pa[2], pb[2]);
+            const uint32_t* ia = reinterpret_cast<const uint32_t*>(F.s_fv + bA);
+            const uint32_t* ib = reinterpret_cast<const uint32_t*>(F.s_fv + bB);
+            f2              dx[6], dy[6], dz[6], dl[6];
+#pragma unroll
+            for (int k2 = 0; k2 < 3; ++k2) {
+                const uint32_t wa = ia[k2], wb = ib[k2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int    k  = 2 * k2 + h;
+                    const float* qa = F.s_x + 3u * (h ? wa >> 16 : wa & 0xFFFFu);
+                    const float* qb = F.s_x + 3u * (h ? wb >> 16 : wb & 0xFFFFu);
+                    dx[k] = sub2(pk(qa[0], qb[0]), PX);
+                    dy[k] = sub2(pk(qa[1], qb[1]), PY);
+                    dz[k] = sub2(pk(qa[2], qb[2]), PZ);
+                    dl[k] = fma2(dz[k], dz[k], fma2(dy[k], dy[k], mul2(dx[k], dx[k])));
+                }
+            }
+            f2 SX = pk(0.f, 0.f), SY = SX, SZ = SX;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const int j  = (k + 1) % 6;
+                const f2  nx = fma2(dy[k], dz[j], neg2(mul2(dz[k], dy[j])));
+                const f2  ny = fma2(dz[k], dx[j], neg2(mul2(dx[k], dz[j])));
+                const f2  nz = fma2(dx[k], dy[j], neg2(mul2(dy[k], dx[j])));
+                float     w0, w1;
+                if (UNIT) {
+                    upk(fma2(nz, nz, fma2(ny, ny, mul2(nx, nx))), w0, w1);
+                    w0 = rsqrtf(w0), w1 = rsqrtf(w1);
+                } else {
+                    upk(add2(dl[k], dl[j]), w0, w1);
+                    w0 = fast_rcp(w0), w1 = fast_rcp(w1);
+                }
+                const f2 W = pk(w0, w1);
+                SX = fma2(nx, W, SX), SY = fma2(ny, W, SY), SZ = fma2(nz, W, SZ);
+            }
+            upk(SX, ax, bx), upk(SY, ay, by), upk(SZ, az, bz);
+        } else {
+            if (vA < F.nov) vn_one<UNIT>(F, vA, ax, ay, az);
+            if (vB < F.nov) vn_one<UNIT>(F, vB, bx, by, bz);
+        }
+        F.s_out[3 * vA] = ax, F.s_out[3 * vA + 1] = ay, F.s_out[3 * vA + 2] = az;
+        if (vB < F.cap) F.s_out[3 * vB] = bx, F.s_out[3 * vB + 1] = by, F.s_out[3 * vB + 2] = bz;
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0 && F.cap) {
+        bulk_s2g(nrm + 3ull * d.slot_base[ELEM_V], F.s_out, 12u * F.cap);
+        bulk_commit();
+        bulk_wait_all_read();
+    }
+}
+
 __global__ void __launch_bounds__(BT) k_laplacian_fan(MeshView mv, const float* __restrict__ x, float* __restrict__ xo,
                                                       double lr)
 {
@@ -1336,6 +1495,17 @@ cudaError_t launch_vertex_normals(const MeshView& mv, const KernelLimits& lim, c
             e = launch_persistent<FanWorker<0>>(mv, FanWorker<0>::Args{x, n, 0.0}, L, stream);
         if (e == cudaErrorInvalidValue) RXM_FAIL("patch needs more shared memory than 227 KB");
         return e;
+    }
+    if (mv.fans && !getenv("RXM_VN_SCALAR")) {  // two vertices per thread, packed fp32x2 (the default)
+        const uint32_t smem = fan_smem(lim) + r16(12u * std::max(lim.max_n[ELEM_V], capv)) + r16(12u * capv) + 64u;
+        cudaError_t e = unit ? set_smem(k_vertex_normals_fan2<1>, smem) : set_smem(k_vertex_normals_fan2<0>, smem);
+        if (e != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
+        if (unit)
+            k_vertex_normals_fan2<1><<<mv.num_patches, BT2, smem, stream>>>(mv, x, n);
+        else
+            k_vertex_normals_fan2<0><<<mv.num_patches, BT2, smem, stream>>>(mv, x, n);
+        ++g_launches;
+        return cudaGetLastError();
     }
     if (mv.fans) {
         const uint32_t smem = fan_smem(lim) + r16(12u * capv) + 16u * lim.max_n[ELEM_V];
