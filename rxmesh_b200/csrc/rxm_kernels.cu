@@ -656,6 +656,84 @@ __global__ void __launch_bounds__(BT2, 8) k_vertex_normals_fan2(MeshView mv, con
     }
 }
 
+// Laplacian step (apps/Smoothing/manual.h:86-104) in the same two-vertices-per-thread form.  grad = sum 2 (x_v - x_u)
+// is accumulated as 2 * sum (x_v - x_u): doubling is exact in binary floating point, so both give the same bits.
+__device__ __forceinline__ void lap_finish(float px, float py, float pz, float gx, float gy, float gz, double lr, float* o)
+{
+    o[0] = (float)__dsub_rn((double)px, __dmul_rn(lr, (double)(2.f * gx)));
+    o[1] = (float)__dsub_rn((double)py, __dmul_rn(lr, (double)(2.f * gy)));
+    o[2] = (float)__dsub_rn((double)pz, __dmul_rn(lr, (double)(2.f * gz)));
+}
+__device__ __forceinline__ void lap_one(const FanPatch2& F, uint32_t v, double lr)
+{
+    const uint32_t b = F.s_fo[v] & FAN_OFF_MASK, e = F.s_fo[v + 1] & FAN_OFF_MASK;
+    const float    X = F.s_x[3 * v], Y = F.s_x[3 * v + 1], Z = F.s_x[3 * v + 2];
+    float          gx = 0.f, gy = 0.f, gz = 0.f;
+    for (uint32_t i = b; i < e; ++i) {
+        const float* q = F.s_x + 3u * F.s_fv[i];
+        gx += X - q[0], gy += Y - q[1], gz += Z - q[2];
+    }
+    lap_finish(X, Y, Z, gx, gy, gz, lr, F.s_out + 3 * v);
+}
+
+__global__ void __launch_bounds__(BT2, 8) k_laplacian_fan2(MeshView mv, const float* __restrict__ x, float* __restrict__ xo,
+                                                         double lr)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint64_t                      bar;
+    const PatchDesc d = load_desc(mv.desc + blockIdx.x);
+    const FanPatch2 F = fan_load2(mv, d, x, smem_raw, &bar);
+    for (uint32_t vA = threadIdx.x; vA < F.cap; vA += 2 * BT2) {
+        const uint32_t vB = vA + BT2;
+        bool           fast = false;
+        uint32_t       bA = 0, bB = 0;
+        if (vB < F.nov) {
+            const uint32_t eA = F.s_fo[vA + 1] & FAN_OFF_MASK, eB = F.s_fo[vB + 1] & FAN_OFF_MASK;
+            bA = F.s_fo[vA] & FAN_OFF_MASK, bB = F.s_fo[vB] & FAN_OFF_MASK;
+            fast = eA - bA == 6 && eB - bB == 6 && ((bA | bB) & 1u) == 0;
+        }
+        if (fast) {
+            const float *   pa = F.s_x + 3u * vA, *pb = F.s_x + 3u * vB;
+            const f2        PX = pk(pa[0], pb[0]), PY = pk(pa[1], pb[1]), PZ = pk(pa[2], pb[2]);
+            const uint32_t* ia = reinterpret_cast<const uint32_t*>(F.s_fv + bA);
+            const uint32_t* ib = reinterpret_cast<const uint32_t*>(F.s_fv + bB);
+            f2              GX = pk(0.f, 0.f), GY = GX, GZ = GX;
+#pragma unroll
+            for (int k2 = 0; k2 < 3; ++k2) {
+                const uint32_t wa = ia[k2], wb = ib[k2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float* qa = F.s_x + 3u * (h ? wa >> 16 : wa & 0xFFFFu);
+                    const float* qb = F.s_x + 3u * (h ? wb >> 16 : wb & 0xFFFFu);
+                    GX = add2(GX, sub2(PX, pk(qa[0], qb[0])));
+                    GY = add2(GY, sub2(PY, pk(qa[1], qb[1])));
+                    GZ = add2(GZ, sub2(PZ, pk(qa[2], qb[2])));
+                }
+            }
+            float gax, gbx, gay, gby, gaz, gbz;
+            upk(GX, gax, gbx), upk(GY, gay, gby), upk(GZ, gaz, gbz);
+            lap_finish(pa[0], pa[1], pa[2], gax, gay, gaz, lr, F.s_out + 3 * vA);
+            lap_finish(pb[0], pb[1], pb[2], gbx, gby, gbz, lr, F.s_out + 3 * vB);
+        } else {
+            if (vA < F.nov)
+                lap_one(F, vA, lr);
+            else
+                F.s_out[3 * vA] = F.s_out[3 * vA + 1] = F.s_out[3 * vA + 2] = 0.f;
+            if (vB < F.nov)
+                lap_one(F, vB, lr);
+            else if (vB < F.cap)
+                F.s_out[3 * vB] = F.s_out[3 * vB + 1] = F.s_out[3 * vB + 2] = 0.f;
+        }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0 && F.cap) {
+        bulk_s2g(xo + 3ull * d.slot_base[ELEM_V], F.s_out, 12u * F.cap);
+        bulk_commit();
+        bulk_wait_all_read();
+    }
+}
+
 __global__ void __launch_bounds__(BT) k_laplacian_fan(MeshView mv, const float* __restrict__ x, float* __restrict__ xo,
                                                       double lr)
 {
@@ -1551,6 +1629,13 @@ cudaError_t launch_laplacian_step(const MeshView& mv, const KernelLimits& lim, c
         cudaError_t e = launch_persistent<FanWorker<2>>(mv, FanWorker<2>::Args{x, xo, lr}, fan_layout(lim), stream);
         if (e == cudaErrorInvalidValue) RXM_FAIL("patch needs more shared memory than 227 KB");
         return e;
+    }
+    if (mv.fans && !getenv("RXM_VN_SCALAR")) {
+        const uint32_t smem = fan_smem(lim) + r16(12u * std::max(lim.max_n[ELEM_V], capv)) + r16(12u * capv) + 64u;
+        if (set_smem(k_laplacian_fan2, smem) != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
+        k_laplacian_fan2<<<mv.num_patches, BT2, smem, stream>>>(mv, x, xo, lr);
+        ++g_launches;
+        return cudaGetLastError();
     }
     if (mv.fans) {
         const uint32_t smem = fan_smem(lim) + r16(12u * capv) + 16u * lim.max_n[ELEM_V];
