@@ -63,5 +63,7 @@ RXM_OP_HANDLES(Op::EF, EdgeHandle, FaceHandle)
 RXM_OP_HANDLES(Op::FV, FaceHandle, VertexHandle)
 RXM_OP_HANDLES(Op::FE, FaceHandle, EdgeHandle)
 RXM_OP_HANDLES(Op::FF, FaceHandle, FaceHandle)
+RXM_OP_HANDLES(Op::EE, EdgeHandle, EdgeHandle)
+RXM_OP_HANDLES(Op::EVDiamond, EdgeHandle, VertexHandle)
 #undef RXM_OP_HANDLES
 }  // namespace rxmesh

@@ -33,7 +33,7 @@ extern "C" {
 /* element types and query ops: numeric values of the reference's Op enum (types.h:113-129) */
 enum { RXM_V = 0, RXM_E = 1, RXM_F = 2 };
 enum { RXM_OP_VV = 3, RXM_OP_VE = 4, RXM_OP_VF = 5, RXM_OP_FV = 6, RXM_OP_FE = 7, RXM_OP_FF = 8,
-       RXM_OP_EV = 9, RXM_OP_EF = 11 };
+       RXM_OP_EV = 9, RXM_OP_EE = 10, RXM_OP_EF = 11, RXM_OP_EVDIAMOND = 12 };
 /* locationT (types.h:51-58) and layoutT (types.h:84-90) */
 enum { RXM_HOST = 0x01, RXM_DEVICE = 0x02, RXM_LOCATION_ALL = 0x0F };
 enum { RXM_AOS = 0, RXM_AOSOA = 1, RXM_SOA = 2 };

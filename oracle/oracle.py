@@ -115,6 +115,30 @@ class Topology:
             return off, val[:int(nnz)]
         raise ValueError(op)
 
+    def edge_dirs(self):
+        """dir[f, j] = 0 if face f traverses its j-th edge from ev[e, 0] to ev[e, 1], else 1 (rxmesh.cpp:941-944)."""
+        return (self.ev[self.fe, 0] != self.fv).astype(np.uint32)
+
+    def ev_diamond(self):
+        """e_v_diamond (kernels/rxmesh_queries.cuh:198-264): [ne, 4] = [v0, w0, v1, w1]; w_d = the vertex opposite to
+        the edge in the face that traverses it with direction d; 0xFFFFFFFF where that face is missing."""
+        out = np.full((self.ne, 4), 0xFFFFFFFF, dtype=np.uint32)
+        out[:, 0], out[:, 2] = self.ev[:, 0], self.ev[:, 1]
+        d = self.edge_dirs()
+        for j in range(3):
+            out[self.fe[:, j], 1 + 2 * d[:, j]] = self.fv[:, (j + 2) % 3]
+        return out
+
+    def ee(self):
+        """e_e_manifold (kernels/rxmesh_queries.cuh:267-342) for consistently oriented edge-manifold input:
+        [ne, 4] = for the face on side dir = 0 and 1: [next edge, previous edge] in that face's winding."""
+        out = np.full((self.ne, 4), 0xFFFFFFFF, dtype=np.uint32)
+        d = self.edge_dirs()
+        for j in range(3):
+            out[self.fe[:, j], 2 * d[:, j]] = self.fe[:, (j + 1) % 3]
+            out[self.fe[:, j], 2 * d[:, j] + 1] = self.fe[:, (j + 2) % 3]
+        return out
+
     def boundary_vertices(self):
         flags = np.zeros(max(self.nv, 1), dtype=np.uint8)
         n = lib().rxo_boundary_vertices(_p(self.ev, u32p), _p(self.fe, u32p), self.nf, self.ne,

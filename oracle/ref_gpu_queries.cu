@@ -289,9 +289,10 @@ int main(int argc, char** argv)
     build_timer.stop();
     const uint32_t P = rx.get_num_patches();
 
-    OpRun runs[8] = {{"VV", 0, 0, rx.max_valence()}, {"VE", 0, 1, rx.max_valence()}, {"VF", 0, 2, rx.max_valence()},
+    OpRun runs[10] = {{"VV", 0, 0, rx.max_valence()}, {"VE", 0, 1, rx.max_valence()}, {"VF", 0, 2, rx.max_valence()},
                      {"EV", 1, 0, 2},          {"EF", 1, 2, rx.max_ef()}, {"FV", 2, 0, 3},
-                     {"FE", 2, 1, 3},          {"FF", 2, 2, rx.max_ff()}};
+                     {"FE", 2, 1, 3},          {"FF", 2, 2, rx.max_ff()},
+                     {"EVDiamond", 1, 0, 4},   {"EE", 1, 1, 4}};
     run_op<Op::VV, VertexHandle, VertexHandle>(rx, runs[0], outdir, dump, nrun);
     run_op<Op::VE, VertexHandle, EdgeHandle>(rx, runs[1], outdir, dump, nrun);
     run_op<Op::VF, VertexHandle, FaceHandle>(rx, runs[2], outdir, dump, nrun);
@@ -300,6 +301,11 @@ int main(int argc, char** argv)
     run_op<Op::FV, FaceHandle, VertexHandle>(rx, runs[5], outdir, dump, nrun);
     run_op<Op::FE, FaceHandle, EdgeHandle>(rx, runs[6], outdir, dump, nrun);
     run_op<Op::FF, FaceHandle, FaceHandle>(rx, runs[7], outdir, dump, nrun);
+    const bool edge4 = rx.max_ef() <= 2 && !getenv("REF_NO_EDGE4");  // EVDiamond / EE need an edge-manifold mesh
+    if (edge4) {
+        run_op<Op::EVDiamond, EdgeHandle, VertexHandle>(rx, runs[8], outdir, dump, nrun);
+        run_op<Op::EE, EdgeHandle, EdgeHandle>(rx, runs[9], outdir, dump, nrun);
+    }
 
     // vertex normals: raw AoSoA coords scattered from the global array through ltog (every local copy filled,
     // like the reference's attribute upload), normals zeroed outside the timed region (vertex_normal.cu:70-72)
@@ -431,7 +437,7 @@ int main(int argc, char** argv)
              rx.get_num_vertices(), rx.get_num_edges(), rx.get_num_faces(), P, patch_size, build_timer.elapsed_millis(),
              rx.max_per_patch(0), rx.max_per_patch(1), rx.max_per_patch(2), g_smem, BT, nrun);
     js += buf;
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < (edge4 ? 10 : 8); ++i) {
         snprintf(buf, sizeof buf,
                  "%s\"%s\": {\"ms\": %.6f, \"width\": %u, \"blocks_per_sm\": %d, \"regs\": %d, \"smem_static\": %d}",
                  i ? ", " : "", runs[i].name, runs[i].ms, runs[i].width, runs[i].occupancy, runs[i].regs, runs[i].smem_static);

@@ -204,6 +204,7 @@ struct MeshView
     const uint32_t*  patch_slot_base[3];  // [num_patches+1] per type: slot base of every patch
     uint32_t         packed;              // 1: every patch uses the rank-annotated format
     uint32_t         fans;                // 1: every patch stores the one-ring fans of its owned vertices
+    uint32_t         edge_manifold;       // 1: no edge of the input has more than two incident faces
 };
 
 // Attribute layouts: numeric values of the reference's layoutT (types.h:84-90).

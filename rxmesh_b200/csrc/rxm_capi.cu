@@ -163,6 +163,7 @@ int rxm_mesh_to_device(rxm_mesh* m)
     }
     m->view.packed      = h.packed ? 1u : 0u;
     m->view.fans        = h.fans ? 1u : 0u;
+    m->view.edge_manifold = h.max_edge_incident_faces <= 2 ? 1u : 0u;
     for (int t = 0; t < 3; ++t) {
         m->view.num_slots[t]       = h.num_slots[t];
         m->view.num_elems[t]       = h.num_elems[t];
@@ -600,7 +601,7 @@ static int op_src(int op)
 {
     switch (op) {
         case RXM_OP_VV: case RXM_OP_VE: case RXM_OP_VF: return RXM_V;
-        case RXM_OP_EV: case RXM_OP_EF: return RXM_E;
+        case RXM_OP_EV: case RXM_OP_EF: case RXM_OP_EE: case RXM_OP_EVDIAMOND: return RXM_E;
         case RXM_OP_FV: case RXM_OP_FE: case RXM_OP_FF: return RXM_F;
         default: return -1;
     }
@@ -608,8 +609,8 @@ static int op_src(int op)
 static int op_dst(int op)
 {
     switch (op) {
-        case RXM_OP_VV: case RXM_OP_EV: case RXM_OP_FV: return RXM_V;
-        case RXM_OP_VE: case RXM_OP_FE: return RXM_E;
+        case RXM_OP_VV: case RXM_OP_EV: case RXM_OP_FV: case RXM_OP_EVDIAMOND: return RXM_V;
+        case RXM_OP_VE: case RXM_OP_FE: case RXM_OP_EE: return RXM_E;
         case RXM_OP_VF: case RXM_OP_EF: case RXM_OP_FF: return RXM_F;
         default: return -1;
     }

@@ -283,6 +283,7 @@ struct OwnerTable
     __device__ __forceinline__ uint64_t handle(uint32_t lid) const
     {
         if (lid < n_owned) return ((uint64_t)patch << 32) | lid;
+        if (lid == 0xFFFFu) return INVALID64_;  // empty slot of a fixed-width result (EVDiamond / EE on a boundary)
         const uint32_t o = own[lid - n_owned];
         return ((uint64_t)stash[o >> 16].patch << 32) | (o & 0xFFFFu);
     }

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(BT) k_query_store(MeshView mv, AttrView<uint64
     const uint8_t*  blob = mv.topo + d.topo_off;
     Smem            sm(smem_raw);
     Q               q;
-    q.plan(d, sm, true, false);
+    q.plan(d, sm, true, false, mv.edge_manifold != 0);
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(BT) k_query_consume(MeshView mv, const float* 
     const uint8_t*     blob = mv.topo + d.topo_off;
     Smem               sm(smem_raw);
     Q                  q;
-    q.plan(d, sm, true, false);
+    q.plan(d, sm, true, false, mv.edge_manifold != 0);
     const uint32_t capD = d.slot_cap(D);
     float*         s_in = sm.alloc<float>(max((uint32_t)d.n[D], capD));
     if (threadIdx.x == 0) {
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(BT) k_laplacian(MeshView mv, const float* __re
     const uint32_t  cap = d.slot_cap(ELEM_V);
     Smem            sm(smem_raw);
     Q               q;
-    q.plan(d, sm, true, false);
+    q.plan(d, sm, true, false, mv.edge_manifold != 0);
     float* s_x = sm.alloc<float>(3 * max(nv, cap));
     float* s_o = sm.alloc<float>(3 * cap);
     if (threadIdx.x == 0) {
@@ -1066,7 +1066,7 @@ __global__ void __launch_bounds__(BT) k_query_csr(MeshView mv, const uint32_t* _
     const uint8_t*  blob = mv.topo + d.topo_off;
     Smem            sm(smem_raw);
     Q               q;
-    q.plan(d, sm, true, false);
+    q.plan(d, sm, true, false);  // the CSR layout needs gap-free lists: FF stays on the generic (scan) path
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
@@ -1387,6 +1387,7 @@ int pick_kmax(uint32_t nnz)
             case OP_FV: RXM_LAUNCH_ONE(KERNEL, OP_FV, KM, PK, __VA_ARGS__); break;       \
             case OP_FE: RXM_LAUNCH_ONE(KERNEL, OP_FE, KM, PK, __VA_ARGS__); break;       \
             case OP_FF: RXM_LAUNCH_ONE(KERNEL, OP_FF, KM, PK, __VA_ARGS__); break;       \
+            RXM_EDGE4_CASES(KERNEL, KM, PK, __VA_ARGS__)                                 \
             default: RXM_FAIL("unsupported query op");                                   \
         }                                                                                \
     } while (0)
@@ -1469,9 +1470,15 @@ static uint32_t max_nnz(const KernelLimits& lim)
     return std::max(2u * lim.max_n[ELEM_E], 3u * lim.max_n[ELEM_F]);
 }
 
+// EE / EVDiamond exist for the store kernel (and user lambdas through the headers) only
+#define RXM_EDGE4_CASES(KERNEL, KM, PK, ...)                                              \
+    case OP_EE: RXM_LAUNCH_ONE(KERNEL, OP_EE, KM, PK, __VA_ARGS__); break;               \
+    case OP_EVDIAMOND: RXM_LAUNCH_ONE(KERNEL, OP_EVDIAMOND, KM, PK, __VA_ARGS__); break;
 cudaError_t launch_query_store(int op, const MeshView& mv, const KernelLimits& lim, AttrView<uint64_t> in,
                                AttrView<uint64_t> out, cudaStream_t stream, const char** err)
 {
+    if ((op == OP_EE || op == OP_EVDIAMOND) && !mv.edge_manifold)
+        RXM_FAIL("Op::EE / Op::EVDiamond only work on edge-manifold meshes (rxmesh_static.inl:519-525)");
     const int km = pick_kmax(max_nnz(lim));
     if (!km) RXM_FAIL("patch too large for the query kernels (nnz > 24*256)");
     if (op == OP_FF && lim.max_face_adjacent_faces > 6) RXM_FAIL("FF: more than 6 adjacent faces per face");
@@ -1487,6 +1494,8 @@ cudaError_t launch_query_store(int op, const MeshView& mv, const KernelLimits& l
     ++g_launches;
     return cudaGetLastError();
 }
+#undef RXM_EDGE4_CASES
+#define RXM_EDGE4_CASES(KERNEL, KM, PK, ...)
 
 cudaError_t launch_query_consume(int op, const MeshView& mv, const KernelLimits& lim, AttrView<float> in,
                                  AttrView<float> out, cudaStream_t stream, const char** err)

@@ -15,7 +15,17 @@
 //   VF         : transpose of FV;   EF : transpose of FE;
 //   FF         : EF, then per owned face the faces across its three edges, in
 //                edge order (the reference's order on manifold input,
-//                rxmesh_queries.cuh:839-853).
+//                rxmesh_queries.cuh:839-853).  Edge-manifold packed meshes take a pair
+//                table instead (no CSR, no scan);
+//   EVDiamond  : per edge [v0, w0, v1, w1]: its end vertices and the vertices opposite
+//                to it in the face that traverses it v0->v1 (w0) / v1->v0 (w1);
+//                fixed stride 4, 0xFFFF where a face is missing
+//                (e_v_diamond, rxmesh_queries.cuh:198-264);
+//   EE         : per edge, for the face on side dir = 0 / 1: [next edge, previous
+//                edge] in that face's winding; fixed stride 4, 0xFFFF on a mesh
+//                boundary (e_e_manifold, rxmesh_queries.cuh:267-342; the reference
+//                indexes the previous edge with (cur - 1) % 3, which is -1 for
+//                cur = 0 in C++ -- the intended (cur + 2) % 3 is used here).
 // Two transposition paths:
 //   PACKED : every incidence entry carries its rank inside the transposed list
 //            and the list offsets are stored with the patch (patch_layout.h), so
@@ -50,7 +60,15 @@ RXM_OP_TRAITS(OP_EF, ELEM_E, ELEM_F, 1)
 RXM_OP_TRAITS(OP_FV, ELEM_F, ELEM_V, 2)
 RXM_OP_TRAITS(OP_FE, ELEM_F, ELEM_E, 1)
 RXM_OP_TRAITS(OP_FF, ELEM_F, ELEM_F, 1)
+RXM_OP_TRAITS(OP_EE, ELEM_E, ELEM_E, 1)         // the four edges of the two faces at an edge (edge-manifold input)
+RXM_OP_TRAITS(OP_EVDIAMOND, ELEM_E, ELEM_V, 1)  // the two end vertices + the two opposite vertices
 #undef RXM_OP_TRAITS
+
+template <int OP>
+__host__ __device__ constexpr bool op_is_edge4()
+{
+    return OP == OP_EE || OP == OP_EVDIAMOND;
+}
 
 template <int OP>
 __host__ __device__ constexpr bool op_is_fixed()
@@ -69,6 +87,7 @@ struct QueryResult
     uint32_t        shift;   // 1 for FE (drops the direction bit), else 0
     uint32_t        mask;    // id mask applied after the shift
     uint32_t        n_src;   // number of source elements with a list
+    const uint16_t* cnt;     // fixed stride with per-row fill count (FF on edge-manifold input), else null
 
     __device__ __forceinline__ uint32_t begin(uint32_t s) const
     {
@@ -76,7 +95,8 @@ struct QueryResult
     }
     __device__ __forceinline__ uint32_t end(uint32_t s) const
     {
-        return off16 ? (uint32_t)off16[s + 1] : (off32 ? off32[s + 1] : (s + 1) * stride);
+        return off16 ? (uint32_t)off16[s + 1]
+                     : (off32 ? off32[s + 1] : (cnt ? s * stride + (uint32_t)cnt[s] : (s + 1) * stride));
     }
     __device__ __forceinline__ uint32_t size(uint32_t s) const { return end(s) - begin(s); }
     __device__ __forceinline__ uint32_t at(uint32_t pos) const { return ((uint32_t)val[pos] >> shift) & mask; }
@@ -99,6 +119,7 @@ struct PatchQuery
     uint32_t    conn_bytes, loff_bytes;
     uint32_t    n_rows;  // rows of the connectivity section that get loaded
     uint32_t    n_cols;  // columns whose lists are built
+    bool        ff2;     // FF on edge-manifold input, packed format: pair table instead of the EF CSR
 
     // shared-memory bytes this op needs for a patch with the given maxima
     // (host side; the role of calc_shared_memory, rxmesh_static.inl:498-841)
@@ -109,7 +130,9 @@ struct PatchQuery
         uint32_t       b   = 0;
         const uint32_t nr  = Tr::conn == 0 ? max_n[ELEM_E] : max_n[ELEM_F];
         b += r16(2 * W * nr);
-        if (!op_is_fixed<OP>()) {
+        if (op_is_edge4<OP>()) {
+            b += r16(8 * max_n[ELEM_E]) + (OP == OP_EVDIAMOND ? r16(4 * max_n[ELEM_E]) : 0u);
+        } else if (!op_is_fixed<OP>()) {
             const uint32_t ncols = OP == OP_FF ? max_n[ELEM_E] : max_n[Tr::src];
             b += (PACKED ? r16(2 * (ncols + 1) + 16) : r16(4 * (ncols + 1))) + r16(2 * W * nr);
             if (OP == OP_FF) b += r16(4 * (max_n[ELEM_F] + 1)) + r16(2 * 3 * max_n[ELEM_F] * 2);
@@ -119,25 +142,37 @@ struct PatchQuery
     }
 
     // carve shared memory (all threads, identical arithmetic)
-    __device__ __forceinline__ void plan(const PatchDesc& d, Smem& sm, bool with_owner, bool all_sources)
+    __device__ __forceinline__ void plan(const PatchDesc& d, Smem& sm, bool with_owner, bool all_sources,
+                                         bool edge_manifold = false)
     {
+        ff2 = OP == OP_FF && PACKED && edge_manifold;
         const uint32_t rows_all = Tr::conn == 0 ? d.n[ELEM_E] : d.n[ELEM_F];
         n_rows = (op_is_fixed<OP>() && !all_sources) ? d.n_owned[Tr::src] : rows_all;
-        if (OP == OP_FF) n_rows = rows_all;
+        if (OP == OP_FF || op_is_edge4<OP>()) n_rows = rows_all;
         conn_bytes = round_up(2u * W * n_rows, 16);
         s_conn     = sm.alloc<uint16_t>(conn_bytes / 2);
         s_loff = nullptr, s_off = nullptr, s_val = nullptr, s_off2 = nullptr, s_val2 = nullptr;
         loff_bytes = 0, n_cols = 0;
-        if (!op_is_fixed<OP>()) {
+        if (op_is_edge4<OP>()) {
+            n_cols = d.n[ELEM_E];
+            s_val  = sm.alloc<uint16_t>(4u * n_cols);
+            if (OP == OP_EVDIAMOND) s_val2 = sm.alloc<uint16_t>(d.ev_bytes() / 2);  // EV section
+        } else if (!op_is_fixed<OP>()) {
             n_cols = OP == OP_FF ? d.n[ELEM_E] : (all_sources ? d.n[Tr::src] : d.n_owned[Tr::src]);
-            if (PACKED) {
+            if (ff2) {
+                // (face, face) pair per edge + compacted 3-wide rows + per-row counts; no offsets, no scan
+                s_off  = sm.alloc<uint32_t>(n_cols);
+                const uint32_t nsrc = all_sources ? d.n[ELEM_F] : d.n_owned[ELEM_F];
+                s_val2              = sm.alloc<uint16_t>(3u * nsrc);
+                s_val               = sm.alloc<uint16_t>(nsrc);
+            } else if (PACKED) {
                 loff_bytes = round_up(2u * (n_cols + 1), 16);
                 s_loff     = sm.alloc<uint16_t>(loff_bytes / 2);
             } else {
                 s_off = sm.alloc<uint32_t>(n_cols + 1);
             }
-            s_val = sm.alloc<uint16_t>(W * n_rows);
-            if (OP == OP_FF) {
+            if (!ff2) s_val = sm.alloc<uint16_t>(W * n_rows);
+            if (OP == OP_FF && !ff2) {
                 s_off2 = sm.alloc<uint32_t>(d.n[ELEM_F] + 1);
                 s_val2 = sm.alloc<uint16_t>(6u * d.n[ELEM_F]);
             }
@@ -152,7 +187,8 @@ struct PatchQuery
     // bytes that issue() will put in flight
     __device__ __forceinline__ uint32_t tx_bytes(const PatchDesc& d, bool with_owner) const
     {
-        return conn_bytes + loff_bytes + (with_owner ? d.own_bytes(Tr::dst) + d.stash_bytes() : 0u);
+        return conn_bytes + loff_bytes + (OP == OP_EVDIAMOND ? d.ev_bytes() : 0u) +
+               (with_owner ? d.own_bytes(Tr::dst) + d.stash_bytes() : 0u);
     }
 
     // thread 0 only, after mbar_arrive_expect_tx
@@ -160,6 +196,7 @@ struct PatchQuery
     {
         const uint32_t o = Tr::conn == 0 ? d.off_ev() : (Tr::conn == 1 ? d.off_fe() : d.off_fv());
         if (conn_bytes) bulk_g2s(s_conn, blob + o, conn_bytes, bar);
+        if (OP == OP_EVDIAMOND && d.ev_bytes()) bulk_g2s(s_val2, blob + d.off_ev(), d.ev_bytes(), bar);
         if (loff_bytes) {
             const uint32_t lo = (OP == OP_VV || OP == OP_VE) ? d.off_voff_e()
                                                               : (OP == OP_VF ? d.off_voff_f() : d.off_eoff_f());
@@ -190,8 +227,92 @@ struct PatchQuery
         QueryResult    r;
         const uint32_t lim = all_sources ? d.n[Tr::src] : d.n_owned[Tr::src];
         r.n_src = lim, r.shift = 0, r.stride = 0, r.mask = 0xFFFFu;
-        r.off16 = nullptr, r.off32 = nullptr;
+        r.off16 = nullptr, r.off32 = nullptr, r.cnt = nullptr;
         const uint16_t* c = s_conn;
+        if (op_is_edge4<OP>()) {
+            const uint32_t em = PACKED ? PK_ID_MASK : 0x7FFFu;
+            const uint32_t ne = n_cols;
+            if (OP == OP_EVDIAMOND) {
+                const uint32_t* ev2 = reinterpret_cast<const uint32_t*>(s_val2);
+                uint32_t*       o2  = reinterpret_cast<uint32_t*>(s_val);
+                for (uint32_t e = threadIdx.x; e < ne; e += BT) {
+                    const uint32_t w = ev2[e];
+                    o2[2 * e]     = (w & ID_MASK) | 0xFFFF0000u;
+                    o2[2 * e + 1] = ((w >> 16) & ID_MASK) | 0xFFFF0000u;
+                }
+                __syncthreads();
+                for (uint32_t f = threadIdx.x; f < n_rows; f += BT) {
+                    uint32_t e[3], dir[3];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const uint32_t a = c[3 * f + j];
+                        e[j] = (a >> 1) & em, dir[j] = a & 1u;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const int      j1 = (j + 1) % 3;
+                        const uint16_t v  = s_val[4 * e[j] + 2 * dir[j]];  // first vertex of edge j in the face's winding
+                        s_val[4 * e[j1] + 1 + 2 * dir[j1]] = v;           // = the vertex opposite to edge j + 1
+                    }
+                }
+            } else {
+                for (uint32_t i = threadIdx.x; i < 4u * ne; i += BT)
+                    s_val[i] = 0xFFFFu;
+                __syncthreads();
+                for (uint32_t f = threadIdx.x; f < n_rows; f += BT) {
+                    uint32_t e[3], dir[3];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const uint32_t a = c[3 * f + j];
+                        e[j] = (a >> 1) & em, dir[j] = a & 1u;
+                    }
+#pragma unroll
+                    for (int cur = 0; cur < 3; ++cur) {
+                        const unsigned short nxt = (unsigned short)e[(cur + 1) % 3], prv = (unsigned short)e[(cur + 2) % 3];
+                        unsigned short*      side = reinterpret_cast<unsigned short*>(s_val) + 4 * e[cur] + 2 * dir[cur];
+                        if (atomicCAS(side, (unsigned short)0xFFFFu, nxt) != 0xFFFFu) {
+                            // both faces traverse the edge the same way (inconsistent orientation): take the other side
+                            side = reinterpret_cast<unsigned short*>(s_val) + 4 * e[cur] + 2 * (dir[cur] ^ 1u);
+                            atomicCAS(side, (unsigned short)0xFFFFu, nxt);
+                        }
+                        side[1] = prv;
+                    }
+                }
+            }
+            __syncthreads();
+            r.val = s_val, r.stride = 4;
+            return r;
+        }
+        if (OP == OP_FF && ff2) {
+            // every edge has at most two faces: slot (2 e + rank) of the pair table names them; the face across
+            // edge j of f is the other entry of the pair (reference order: edge 0, 1, 2, boundary edges skipped)
+            constexpr uint32_t rk = PK_ID_BITS + 1;
+            for (uint32_t e = threadIdx.x; e < n_cols; e += BT)
+                s_off[e] = 0xFFFFFFFFu;
+            __syncthreads();
+            uint16_t* pair = reinterpret_cast<uint16_t*>(s_off);
+            for (uint32_t f = threadIdx.x; f < n_rows; f += BT) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const uint32_t a = c[3 * f + j];
+                    pair[2u * ((a >> 1) & PK_ID_MASK) + ((a >> rk) & 1u)] = (uint16_t)f;
+                }
+            }
+            __syncthreads();
+            for (uint32_t f = threadIdx.x; f < lim; f += BT) {
+                uint32_t k = 0;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const uint32_t w = s_off[(c[3 * f + j] >> 1) & PK_ID_MASK];
+                    const uint32_t o = (w & 0xFFFFu) == f ? (w >> 16) : (w & 0xFFFFu);
+                    if (o != 0xFFFFu) s_val2[3 * f + k++] = (uint16_t)o;
+                }
+                s_val[f] = (uint16_t)k;
+            }
+            __syncthreads();
+            r.val = s_val2, r.stride = 3, r.cnt = s_val;
+            return r;
+        }
         if (OP == OP_EV) {
             r.val = c, r.stride = 2, r.mask = ID_MASK;
         } else if (OP == OP_FV) {

@@ -34,8 +34,8 @@ class Op(enum.IntEnum):  # types.h:113-129
     EVDiamond = 12
 
 
-_SRC = {Op.VV: 0, Op.VE: 0, Op.VF: 0, Op.EV: 1, Op.EF: 1, Op.FV: 2, Op.FE: 2, Op.FF: 2}
-_DST = {Op.VV: 0, Op.VE: 1, Op.VF: 2, Op.EV: 0, Op.EF: 2, Op.FV: 0, Op.FE: 1, Op.FF: 2}
+_SRC = {Op.VV: 0, Op.VE: 0, Op.VF: 0, Op.EV: 1, Op.EF: 1, Op.FV: 2, Op.FE: 2, Op.FF: 2, Op.EE: 1, Op.EVDiamond: 1}
+_DST = {Op.VV: 0, Op.VE: 1, Op.VF: 2, Op.EV: 0, Op.EF: 2, Op.FV: 0, Op.FE: 1, Op.FF: 2, Op.EE: 1, Op.EVDiamond: 0}
 
 
 def _stream_ptr(stream):
@@ -492,7 +492,8 @@ class RXMeshStatic:
         op = Op(op)
         src, dst = _SRC[op], _DST[op]
         if width is None:
-            width = {Op.EV: 2, Op.FV: 3, Op.FE: 3, Op.EF: self.get_input_max_edge_incident_faces(),
+            width = {Op.EV: 2, Op.FV: 3, Op.FE: 3, Op.EE: 4, Op.EVDiamond: 4,
+                     Op.EF: self.get_input_max_edge_incident_faces(),
                      Op.FF: self.get_input_max_face_adjacent_faces() + 2}.get(
                          op, self.get_input_max_valence())
         inp = Attribute(self, src, np.uint64, 1, LOCATION_ALL, AoSoA)

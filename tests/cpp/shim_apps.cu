@@ -263,6 +263,45 @@ static int app_vertex_normals(const uint32_t* fv, uint32_t nf, const float* x, u
     return 0;
 }
 
+// timing of the SAME user kernel (reference call sites, our headers): cudaEvent pair around nrun launches after one
+// warm-up, output zeroed outside the timed region as the app does (apps/VertexNormal/vertex_normal.cu:69-85).
+// face_patch (optional) replays a given patching, e.g. the reference's own.
+static int app_time_vertex_normals(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, const uint32_t* face_patch,
+                                   uint32_t patch_size, int nrun, float* ms_out)
+{
+    rx_init(0);
+    std::vector<uint32_t> fp;
+    if (face_patch) fp.assign(face_patch, face_patch + nf);
+    RXMeshStatic rx(fv, nf, fp, patch_size);
+    constexpr uint32_t blockThreads = 256;
+    auto coords    = rx.add_vertex_attribute<float>("coordinates", 3, LOCATION_ALL);
+    auto v_normals = rx.add_vertex_attribute<float>("v_normals", 3, LOCATION_ALL);
+    rx.for_each_vertex(HOST, [&](const VertexHandle& vh) {
+        const uint32_t v_id = rx.map_to_global(vh);
+        for (uint32_t i = 0; i < 3; ++i)
+            (*coords)(vh, i) = x[v_id * 3 + i];
+    }, NULL, false);
+    coords->move(HOST, DEVICE);
+    LaunchBox<blockThreads> launch_box;
+    rx.prepare_launch_box({Op::FV}, launch_box, (void*)user_vertex_normal<float, blockThreads>);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a), cudaEventCreate(&b);
+    float total = 0;
+    for (int i = 0; i <= nrun; ++i) {
+        v_normals->reset(0, DEVICE);
+        cudaEventRecord(a);
+        user_vertex_normal<float, blockThreads><<<launch_box.blocks, launch_box.num_threads, launch_box.smem_bytes_dyn>>>(
+            rx.get_context(), *coords, *v_normals);
+        cudaEventRecord(b);
+        if (cudaEventSynchronize(b) != cudaSuccess) return 1;
+        float ms;
+        cudaEventElapsedTime(&ms, a, b);
+        if (i) total += ms;
+    }
+    *ms_out = total / nrun;
+    return 0;
+}
+
 // manual smoothing (apps/Smoothing/manual.h:86-104): for_each<Op::VV> gradient + for_each_vertex(DEVICE) step
 static int app_smoothing(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, double lr,
                          int num_iter, int oriented, float* out)
@@ -321,6 +360,11 @@ extern "C" {
 int shim_vertex_normals(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, float* out)
 {
     return app_vertex_normals(fv, nf, x, nv, patch_size, out);
+}
+int shim_time_vertex_normals(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, const uint32_t* face_patch,
+                             uint32_t patch_size, int nrun, float* ms_out)
+{
+    return app_time_vertex_normals(fv, nf, x, nv, face_patch, patch_size, nrun, ms_out);
 }
 int shim_smoothing(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, double lr, int num_iter,
                    int oriented, float* out)

@@ -55,8 +55,9 @@ def run_ref(V, F, patch_size, dump, nrun, timeout=1500):
                     arrs[fn[:-4]] = np.fromfile(os.path.join(td, fn), dtype=np.uint32)
                 elif fn.endswith(".f32"):
                     arrs[fn[:-4]] = np.fromfile(os.path.join(td, fn), dtype=np.float32)
-            for op in OPS:
-                arrs["q_" + op] = arrs["q_" + op].reshape(-1, meta["ops"][op]["width"])
+            for op in OPS + ["EVDiamond", "EE"]:
+                if "q_" + op in arrs:
+                    arrs["q_" + op] = arrs["q_" + op].reshape(-1, meta["ops"][op]["width"])
             arrs["vn"] = arrs["vn"].reshape(-1, 3)
         return meta, arrs
 
@@ -125,6 +126,17 @@ def main():
                 ours[tag] = {"patches": m.get_num_patches(), "build_s": tb, "ms": res, "vertex_normals_ms": vn}
                 del m, x, nrm
             line["ours"] = ours
+            # the reference app's own kernel source (Query::dispatch<Op::FV> lambda with global atomics,
+            # tests/cpp/shim_apps.cu:user_vertex_normal) compiled against OUR drop-in headers: what a user gets
+            # without touching their code
+            import ctypes as C
+            shim = C.CDLL(os.path.join(ROOT, "tests", "cpp", "libshim_apps.so"))
+            msf = C.c_float()
+            fpr = np.ascontiguousarray(arrs["face_patch"], np.uint32)
+            if shim.shim_time_vertex_normals(F.ctypes.data_as(C.c_void_p), F.shape[0], V.ctypes.data_as(C.c_void_p), V.shape[0],
+                                             fpr.ctypes.data_as(C.c_void_p), args.patch_size, 100, C.byref(msf)) == 0:
+                line["user_kernel_on_our_headers_vertex_normals_ms"] = msf.value
+                line["speedup_user_kernel_unchanged"] = meta["vertex_normals"]["ms"] / msf.value
             line["speedup_same_patching"] = {o: meta["ops"][o]["ms"] / ours["same_patching"]["ms"][o] for o in OPS}
             line["speedup_same_patching"]["vertex_normals"] = meta["vertex_normals"]["ms"] / ours["same_patching"]["vertex_normals_ms"]
             line["speedup_lloyd_1024"] = {o: meta["ops"][o]["ms"] / ours["lloyd_1024"]["ms"][o] for o in OPS}

@@ -91,3 +91,44 @@ def test_launch_box(built):
     name, V, F, m, T = built
     blocks, threads, smem = m.launch_box(rx.Op.VV)
     assert blocks == m.get_num_patches() and threads == 256 and 0 < smem < 227 * 1024
+
+
+EDGE4_MESHES = ["sphere3", "torus", "dragon", "bunnyhead", "plane_5", "ico12", "grid40x31"]
+
+
+@pytest.mark.parametrize("name", EDGE4_MESHES)
+@pytest.mark.parametrize("op", ["EVDiamond", "EE"])
+def test_edge4_queries(name, op):
+    """Op::EVDiamond / Op::EE (kernels/rxmesh_queries.cuh:198-342; test_ev_diamond.cu): fixed width 4, invalid
+    handles on mesh boundaries, exact slot order."""
+    rx.rx_init(0)
+    V, F = make_mesh(name)
+    m = rx.RXMeshStatic(F, patch_size=512 if F.shape[0] > 600 else 64)
+    T = O.Topology(F)
+    want = T.ev_diamond() if op == "EVDiamond" else T.ee()
+    inp, out, src, dst = m.query_global(rx.Op[op])
+    assert out.num_attributes == 4
+    oh = out.host_array()
+    sb, lb = m.slot_base(1).astype(np.int64), m.lin_base(1).astype(np.int64)
+    s2g = m.slot_to_global(1)
+    seen = 0
+    for p in range(m.get_num_patches()):
+        b, cap, no = int(sb[p]), int(sb[p + 1] - sb[p]), int(lb[p + 1] - lb[p])
+        rows = m.map_to_global(dst, oh[b * 4:b * 4 + 4 * cap].reshape(4, cap)[:, :no].T)
+        assert np.array_equal(rows, want[s2g[b:b + no]]), (op, p)
+        seen += no
+    assert seen == T.ne
+    if op == "EVDiamond" and name == "plane_5":
+        # the reference's own check (test_ev_diamond.cu:62-76): the two triangles of an interior diamond tile a unit quad
+        full = want[(want != 0xFFFFFFFF).all(axis=1)]
+        x = V.astype(np.float64)
+        area = lambda a, b, c: 0.5 * np.linalg.norm(np.cross(x[b] - x[a], x[c] - x[a]), axis=1)
+        assert np.allclose(area(full[:, 0], full[:, 1], full[:, 2]) + area(full[:, 0], full[:, 2], full[:, 3]), 1.0, atol=1e-5)
+
+
+def test_edge4_rejects_non_manifold():
+    rx.rx_init(0)
+    F = np.array([[0, 1, 2], [0, 1, 3], [0, 1, 4]], np.uint32)  # three faces on edge (0, 1)
+    m = rx.RXMeshStatic(F, patch_size=64)
+    with pytest.raises(rx.RXMeshError):
+        m.query_global(rx.Op.EVDiamond)

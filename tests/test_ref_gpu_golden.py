@@ -25,7 +25,7 @@ from oracle import oracle as O
 
 MESHES = ["sphere3", "dragon", "bunnyhead", "torus", "cube", "plane_5"]
 OPS = ["VV", "VE", "VF", "EV", "EF", "FV", "FE", "FF"]
-ORDERED = ("EV", "FV", "FE")
+ORDERED = ("EV", "FV", "FE", "EVDiamond")
 NONE = 0xFFFFFFFF
 
 
@@ -55,6 +55,18 @@ def test_oracle_matches_reference_gpu_queries(name):
                 assert np.array_equal(q[s][q[s] != NONE], val[off[s]:off[s + 1]]), (op, s)
         else:
             assert rows_as_sets(q) == O.csr_to_sets((off, val)), op
+
+
+@pytest.mark.parametrize("name", MESHES)
+def test_oracle_ev_diamond_matches_reference_gpu(name):
+    """Op::EVDiamond: exact slot order [v0, w0, v1, w1], invalid on boundaries.  (Op::EE is recorded in the fixture
+    too, but the reference returns only invalid handles for it: Query::get_iterator gives EE a zero fixed offset and
+    a null offset array, query.inl:238-242 -- there is nothing to pin against; tests/test_gpu_queries.py checks our
+    EE against the restated e_e_manifold.)"""
+    V, F = make_mesh(name)
+    g = load(name)
+    assert np.array_equal(O.Topology(F).ev_diamond(), g["q_EVDiamond"])
+    assert np.all(g["q_EE"] == NONE)
 
 
 @pytest.mark.parametrize("name", ["sphere3", "dragon", "bunnyhead", "torus"])
@@ -89,7 +101,7 @@ def test_gpu_queries_match_reference_gpu(name):
     V, F = make_mesh(name)
     g = load(name)
     m = rx.RXMeshStatic(F, face_patch=g["face_patch"], patch_size=g["meta"]["patch_size"])
-    for op in OPS:
+    for op in OPS + ["EVDiamond"]:
         inp, out, src, dst = m.query_global(rx.Op[op])
         W = out.num_attributes
         oh = out.host_array()
@@ -102,6 +114,9 @@ def test_gpu_queries_match_reference_gpu(name):
             rows = m.map_to_global(dst, oh[b * W:b * W + W * cap].reshape(W, cap)[:, :no].T)
             for i in range(no):
                 want = q[s2g[b + i]]
+                if op == "EVDiamond":  # fixed width 4, invalid slots are part of the answer
+                    assert np.array_equal(rows[i], want), (op, p, i, rows[i], want)
+                    continue
                 want = want[want != NONE]
                 got = rows[i][rows[i] != NONE]
                 if ordered:
