@@ -343,6 +343,11 @@ int rxm_mesh_launch_box(const rxm_mesh* m, int op, uint32_t* blocks, uint32_t* t
         case RXM_OP_VF: b = 2 * f3 + r16(4 * (L.max_n[ELEM_V] + 1)); break;
         case RXM_OP_EF: b = 2 * f3 + r16(4 * (L.max_n[ELEM_E] + 1)); break;
         case RXM_OP_FF: b = 2 * f3 + r16(4 * (L.max_n[ELEM_E] + 1)) + r16(4 * (L.max_n[ELEM_F] + 1)) + 2 * f3; break;
+        case RXM_OP_EE: case RXM_OP_EVDIAMOND:  // rxmesh_static.inl:519-525: edge-manifold input only
+            if (m->h.max_edge_incident_faces > 2)
+                return fail(RXM_ERR_UNSUPPORTED, "Op::EVDiamond and Op::EE only work on edge-manifold meshes");
+            b = f3 + r16(8 * L.max_n[ELEM_E]) + ev;
+            break;
         default: return fail(RXM_ERR_INVALID, "rxm_mesh_launch_box: unknown op");
     }
     const uint32_t mo = std::max(L.max_not_owned[0], std::max(L.max_not_owned[1], L.max_not_owned[2]));

@@ -761,8 +761,10 @@ __global__ void __launch_bounds__(BT) k_laplacian_fan(MeshView mv, const float* 
 }
 
 // VF consume through the fan faces: out(v) = sum over the incident faces of in(f)
-__global__ void __launch_bounds__(BT) k_vf_consume_fan(MeshView mv, const float* __restrict__ in, float* __restrict__ out)
+template <int BTC>
+__global__ void __launch_bounds__(BTC, 2048 / BTC) k_vf_consume_fan(MeshView mv, const float* __restrict__ in, float* __restrict__ out)
 {
+    constexpr int BT = BTC;  // block size of the consume kernels (shadows the file-wide 256)
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t                      bar;
     const PatchDesc d    = load_desc(mv.desc + blockIdx.x);
@@ -802,8 +804,10 @@ __global__ void __launch_bounds__(BT) k_vf_consume_fan(MeshView mv, const float*
 }
 
 // VV consume through the fans: out(v) = sum over the one-ring of in(u)
-__global__ void __launch_bounds__(BT) k_vv_consume_fan(MeshView mv, const float* __restrict__ in, float* __restrict__ out)
+template <int BTC>
+__global__ void __launch_bounds__(BTC, 2048 / BTC) k_vv_consume_fan(MeshView mv, const float* __restrict__ in, float* __restrict__ out)
 {
+    constexpr int BT = BTC;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t                      bar;
     const PatchDesc d    = load_desc(mv.desc + blockIdx.x);
@@ -1535,15 +1539,25 @@ cudaError_t launch_query_consume(int op, const MeshView& mv, const KernelLimits&
         const uint32_t smem = r16(2u * (lim.max_owned[ELEM_V] + 1) + 16) + r16(2u * lim.max_fan_total + 16) +
                               r16(4u * lim.max_not_owned[ELEM_F]) + 16u * lim.max_stash +
                               r16(4u * (std::max(lim.max_n[ELEM_F], lim.max_owned[ELEM_F] + 4)));
-        if (set_smem(k_vf_consume_fan, smem) != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
-        k_vf_consume_fan<<<mv.num_patches, BT, smem, stream>>>(mv, in.data, out.data);
+        const bool small = smem <= 14000u && !getenv("RXM_CONSUME_BT256");  // 16 blocks of 128 threads fit one SM
+        if (set_smem(k_vf_consume_fan<128>, smem) != cudaSuccess || set_smem(k_vf_consume_fan<256>, smem) != cudaSuccess)
+            RXM_FAIL("patch needs more shared memory than 227 KB");
+        if (small)
+            k_vf_consume_fan<128><<<mv.num_patches, 128, smem, stream>>>(mv, in.data, out.data);
+        else
+            k_vf_consume_fan<256><<<mv.num_patches, 256, smem, stream>>>(mv, in.data, out.data);
         ++g_launches;
         return cudaGetLastError();
     }
     if (op == OP_VV && mv.fans) {
         const uint32_t smem = fan_smem(lim) + r16(4u * (std::max(lim.max_n[ELEM_V], lim.max_owned[ELEM_V] + 4)));
-        if (set_smem(k_vv_consume_fan, smem) != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
-        k_vv_consume_fan<<<mv.num_patches, BT, smem, stream>>>(mv, in.data, out.data);
+        const bool small = smem <= 14000u && !getenv("RXM_CONSUME_BT256");
+        if (set_smem(k_vv_consume_fan<128>, smem) != cudaSuccess || set_smem(k_vv_consume_fan<256>, smem) != cudaSuccess)
+            RXM_FAIL("patch needs more shared memory than 227 KB");
+        if (small)
+            k_vv_consume_fan<128><<<mv.num_patches, 128, smem, stream>>>(mv, in.data, out.data);
+        else
+            k_vv_consume_fan<256><<<mv.num_patches, 256, smem, stream>>>(mv, in.data, out.data);
         ++g_launches;
         return cudaGetLastError();
     }

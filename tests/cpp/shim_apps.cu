@@ -352,6 +352,8 @@ static int app_query(int op, const uint32_t* fv, uint32_t nf, uint32_t patch_siz
         case Op::FV: return run_query<Op::FV, FaceHandle, VertexHandle>(rx, width, oriented, out_global);
         case Op::FE: return run_query<Op::FE, FaceHandle, EdgeHandle>(rx, width, oriented, out_global);
         case Op::FF: return run_query<Op::FF, FaceHandle, FaceHandle>(rx, width, oriented, out_global);
+        case Op::EVDiamond: return run_query<Op::EVDiamond, EdgeHandle, VertexHandle>(rx, width, oriented, out_global);
+        case Op::EE: return run_query<Op::EE, EdgeHandle, EdgeHandle>(rx, width, oriented, out_global);
         default: return 2;
     }
 }

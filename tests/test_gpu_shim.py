@@ -83,6 +83,16 @@ def test_user_query_kernel(shim, op):
             assert np.array_equal(np.sort(got), np.sort(want)), (op, g)
 
 
+@pytest.mark.parametrize("op", ["EVDiamond", "EE"])
+def test_user_edge4_query_kernel(shim, op):
+    """the reference's EVDiamond test kernel (tests/RXMesh_test/test_ev_diamond.cu:16-37) through the drop-in headers"""
+    V, F = make_mesh("bunnyhead")
+    T = O.Topology(F)
+    out = np.zeros((T.ne, 4), dtype=np.uint32)
+    assert shim.shim_query(int(rx.Op[op]), _p(F), F.shape[0], 512, 4, 0, _p(out)) == 0
+    assert np.array_equal(out, T.ev_diamond() if op == "EVDiamond" else T.ee())
+
+
 def test_oriented_vv(shim):
     # oriented VV (tests/RXMesh_test/test_queries_oriented.cu): consecutive neighbours span a face with v
     V, F = make_mesh("torus")
