@@ -236,6 +236,34 @@ def consume_sum(csr, src):
     return out
 
 
+def max_threads():
+    return int(lib().rxo_max_threads())
+
+
+def vertex_normals_mt(fv, x, threads, repeats=1):
+    """rxo_vertex_normals_f32_mt: all-cores port (per-thread accumulators). -> (normals, seconds per run)."""
+    import time
+    fv = _u32(fv).reshape(-1, 3)
+    x = _f32(x).reshape(-1, 3)
+    n = np.empty_like(x)
+    scratch = np.empty((threads, x.shape[0], 3), dtype=np.float32)
+    t0 = time.perf_counter()
+    for _ in range(max(1, repeats)):
+        lib().rxo_vertex_normals_f32_mt(_p(fv, u32p), fv.shape[0], _p(x, f32p), x.shape[0], _p(n, f32p),
+                                        _p(scratch, f32p), int(threads))
+    return n, (time.perf_counter() - t0) / max(1, repeats)
+
+
+def consume_sum_mt(csr, src, threads):
+    """rxo_consume_sum_f32_mt: out[s] = sum_{t in list(s)} src[t], fp32, rows split over `threads`."""
+    off, val = csr
+    src = _f32(src)
+    out = np.empty(off.shape[0] - 1, dtype=np.float32)
+    lib().rxo_consume_sum_f32_mt(_p(off, u32p), _p(val, u32p), off.shape[0] - 1, _p(src, f32p), _p(out, f32p),
+                                 int(threads))
+    return out
+
+
 def csr_to_sets(csr):
     """list of sorted tuples (multiset per source element) for set-equality checks."""
     off, val = csr

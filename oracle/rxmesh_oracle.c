@@ -509,6 +509,84 @@ uint32_t rxo_bilateral_step(const uint32_t* vv_off, const uint32_t* vv_val, uint
     return worst;
 }
 
+/* ------------------------------------------------------------------------ */
+/* All-cores variants for the CPU baseline ("an OpenMP-over-faces  */
+/* variant with per-thread accumulation"; the reference's own vertex_normal_ref  */
+/* is serial, its Filtering CPU path uses `omp parallel for schedule(static)`     */
+/* with omp_get_max_threads() threads, filtering.cu:45-46).  Deterministic: every */
+/* thread accumulates a contiguous face range into its own array, the arrays are  */
+/* summed in thread order.  scratch: threads * nv * 3 floats, caller-owned.        */
+/* ------------------------------------------------------------------------ */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+int rxo_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+void rxo_vertex_normals_f32_mt(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, float* n, float* scratch,
+                               int threads)
+{
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    uint32_t lo[256], hi[256]; /* vertex span [lo, hi) touched by each thread's face range */
+#pragma omp parallel num_threads(threads)
+    {
+#ifdef _OPENMP
+        const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+#else
+        const int t = 0, nt = 1;
+#endif
+        float*         acc = scratch + (size_t)t * nv * 3;
+        const uint32_t f0 = (uint32_t)((uint64_t)nf * t / nt), f1 = (uint32_t)((uint64_t)nf * (t + 1) / nt);
+        uint32_t       vmin = nv, vmax = 0;
+        for (uint64_t i = 3 * (uint64_t)f0; i < 3 * (uint64_t)f1; ++i) {
+            if (fv[i] < vmin) vmin = fv[i];
+            if (fv[i] + 1 > vmax) vmax = fv[i] + 1;
+        }
+        if (vmin > vmax) vmin = vmax = 0;
+        lo[t] = vmin, hi[t] = vmax;
+        memset(acc + 3 * (size_t)vmin, 0, (size_t)(vmax - vmin) * 3 * sizeof(float));
+        for (uint32_t f = f0; f < f1; ++f) {
+            const uint32_t* v  = fv + 3 * (uint64_t)f;
+            const float *   p0 = x + 3 * (uint64_t)v[0], *p1 = x + 3 * (uint64_t)v[1], *p2 = x + 3 * (uint64_t)v[2];
+            float a0 = p1[0] - p0[0], a1 = p1[1] - p0[1], a2 = p1[2] - p0[2];
+            float b0 = p2[0] - p0[0], b1 = p2[1] - p0[1], b2 = p2[2] - p0[2];
+            float fn[3] = {a1 * b2 - a2 * b1, a2 * b0 - a0 * b2, a0 * b1 - a1 * b0};
+            float l[3]  = {rxo_l2sq_f(p0, p1), rxo_l2sq_f(p1, p2), rxo_l2sq_f(p2, p0)};
+            for (uint32_t i = 0; i < 3; ++i) {
+                float* o = acc + 3 * (uint64_t)v[i];
+                for (uint32_t c = 0; c < 3; ++c)
+                    o[c] += fn[c] / (l[i] + l[(i + 2) % 3]);
+            }
+        }
+#pragma omp barrier
+        const uint32_t v0 = (uint32_t)((uint64_t)nv * t / nt), v1 = (uint32_t)((uint64_t)nv * (t + 1) / nt);
+        memset(n + 3 * (size_t)v0, 0, (size_t)(v1 - v0) * 3 * sizeof(float));
+        for (int k = 0; k < nt; ++k) { /* thread order: deterministic */
+            const uint32_t a = lo[k] > v0 ? lo[k] : v0, e = hi[k] < v1 ? hi[k] : v1;
+            const float*   src = scratch + (size_t)k * nv * 3;
+            for (uint64_t i = 3 * (uint64_t)a; i < 3 * (uint64_t)e && a < e; ++i)
+                n[i] += src[i];
+        }
+    }
+}
+void rxo_consume_sum_f32_mt(const uint32_t* off, const uint32_t* val, uint32_t n_src, const float* in, float* out, int threads)
+{
+    if (threads < 1) threads = 1;
+#pragma omp parallel for schedule(static) num_threads(threads)
+    for (int64_t s = 0; s < (int64_t)n_src; ++s) {
+        float a = 0.f;
+        for (uint32_t i = off[s]; i < off[s + 1]; ++i)
+            a += in[val[i]];
+        out[s] = a;
+    }
+}
+
 /* consume-variant checksums used by the roofline kernels: out[v] = sum of
  * in[u] over the VV / VF lists, accumulated in float64 (order-free yardstick). */
 void rxo_consume_sum(const uint32_t* off, const uint32_t* val, uint32_t n_src, const float* in,

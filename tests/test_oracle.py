@@ -110,3 +110,18 @@ def test_bilateral_denoises_noisy_sphere():
     # the filter shrinks a convex shape slightly (all neighbours lie below the tangent plane) but
     # must reduce the roughness: spread of the radius
     assert np.linalg.norm(out, axis=1).std() < 0.75 * np.linalg.norm(noisy, axis=1).std()
+
+
+def test_all_cores_ports_match_serial():
+    """rxo_vertex_normals_f32_mt / rxo_consume_sum_f32_mt (the all-cores CPU baseline of bench.py) == the serial forms:
+    per-thread accumulators summed in thread order differ from the serial sum only by fp32 reassociation."""
+    g = load_golden("dragon")
+    ref = O.vertex_normals(g["F"], g["V"], np.float32)
+    for t in (1, 3, 8):
+        n, _ = O.vertex_normals_mt(g["F"], g["V"], t)
+        assert np.abs(n - ref).max() < 2e-6 * np.abs(ref).max()
+    assert np.array_equal(O.vertex_normals_mt(g["F"], g["V"], 1)[0].view(np.uint32), ref.view(np.uint32))
+    T = O.Topology(g["F"])
+    x = np.random.RandomState(0).rand(T.nv).astype(np.float32)
+    a = O.consume_sum_mt(T.query("VV"), x, 4)
+    assert np.allclose(a, O.consume_sum(T.query("VV"), x), rtol=1e-6)
