@@ -55,6 +55,21 @@ struct rxm_mesh
     Csr       csr[16];      // materialised queries (rxm_query_csr), indexed by op
     uint32_t* d_flag = nullptr;
     rxm_attr* scratch1[32]  = {};  // per query op: [2*op] input, [2*op+1] output of rxm_query_consume_host
+    // ---- chunked upload / compute / download pipeline of the host-buffer entry points (see pipelined_host_call) ----
+    struct PipePlan
+    {
+        uint32_t              K = 0;       // chunks (contiguous patch ranges); 0 = pipeline unavailable
+        std::vector<uint32_t> pb;          // [K+1] patch boundaries
+        std::vector<uint64_t> up_hi[3];    // [K] per element type: ids < up_hi[c] cover every element OWNED by patches < pb[c+1]
+        std::vector<uint64_t> down_lo[3];  // [K+1] ids < down_lo[c] are owned by patches < pb[c] only; [K] = #elements
+        std::vector<uint32_t> need;        // [K] chunk q reads ribbon values owned by patches of chunks <= need[q]
+    } plan;
+    struct Pipe
+    {
+        cudaStream_t             h2d = nullptr, d2h = nullptr;
+        cudaEvent_t              start = nullptr, done = nullptr;
+        std::vector<cudaEvent_t> up, comp;
+    } pipe[32];
 };
 
 struct rxm_attr
@@ -139,6 +154,66 @@ int rxm_mesh_create(const uint32_t* fv, uint32_t num_faces, const uint32_t* face
     return RXM_OK;
 }
 
+// Frontiers that let a host-buffer call overlap its H2D copy, its kernels and its D2H copy: patches are cut into K
+// contiguous chunks; chunk c's owned slots can be filled once the global-order input prefix [0, up_hi[c]) is on the
+// device, its kernel can run once the chunks holding its ribbon owners (<= need[c]) are filled, and the output prefix
+// [0, down_lo[c+1]) is final once chunks <= c are done.  Always correct; how much overlaps depends on how well patch
+// order follows global element order (row-major tiles of a grid: almost perfectly; Lloyd patches of a scrambled mesh:
+// the first piece is most of the array and the call degenerates to upload -> compute -> download).
+static void build_pipe_plan(rxm_mesh* m)
+{
+    const HostMesh& h = m->h;
+    auto&           P = m->plan;
+    P.K               = 0;
+    const char* env   = getenv("RXM_PIPE_CHUNKS");
+    uint32_t    K     = env ? (uint32_t)atoi(env) : 8u;
+    if (K < 2 || h.num_patches < 2 * K || h.topo.empty()) return;
+    if (m->active_count && m->active_count != h.num_patches) return;  // shards with ghost patches: plain path
+    P.pb.resize(K + 1);
+    for (uint32_t c = 0; c <= K; ++c)
+        P.pb[c] = (uint32_t)((uint64_t)h.num_patches * c / K);
+    for (int t = 0; t < 3; ++t) {
+        std::vector<uint64_t> omin(h.num_patches, UINT64_MAX), omax(h.num_patches, 0);
+#pragma omp parallel for schedule(static)
+        for (int64_t p = 0; p < (int64_t)h.num_patches; ++p) {
+            const uint32_t b = h.slot_base[t][p], no = h.desc[p].n_owned[t];
+            for (uint32_t i = 0; i < no; ++i) {
+                const uint64_t g = h.slot_to_global[t][b + i];
+                omin[p] = std::min(omin[p], g), omax[p] = std::max(omax[p], g + 1);
+            }
+        }
+        P.up_hi[t].assign(K, 0), P.down_lo[t].assign(K + 1, h.num_elems[t]);
+        uint64_t run = 0;
+        for (uint32_t c = 0; c < K; ++c) {
+            for (uint32_t p = P.pb[c]; p < P.pb[c + 1]; ++p)
+                run = std::max(run, omax[p]);
+            P.up_hi[t][c] = run;
+        }
+        P.up_hi[t][K - 1] = h.num_elems[t];
+        uint64_t lo = h.num_elems[t];
+        for (uint32_t c = K; c-- > 0;) {
+            for (uint32_t p = P.pb[c]; p < P.pb[c + 1]; ++p)
+                lo = std::min(lo, omin[p]);
+            P.down_lo[t][c] = lo;
+        }
+        P.down_lo[t][0] = 0;
+    }
+    P.need.assign(K, 0);
+    for (uint32_t c = 0; c < K; ++c) {
+        uint32_t mx = P.pb[c + 1] - 1;
+        for (uint32_t p = P.pb[c]; p < P.pb[c + 1]; ++p) {
+            const PatchDesc&  D  = h.desc[p];
+            const StashEntry* st = reinterpret_cast<const StashEntry*>(h.topo.data() + D.topo_off + D.off_stash());
+            for (uint32_t i = 0; i < D.n_stash; ++i)
+                mx = std::max(mx, st[i].patch);
+        }
+        uint32_t q = c;
+        while (q + 1 < K && mx >= P.pb[q + 1]) ++q;
+        P.need[c] = q;
+    }
+    P.K = K;
+}
+
 int rxm_mesh_to_device(rxm_mesh* m)
 {
     if (!m) return fail(RXM_ERR_INVALID, "rxm_mesh_to_device: null mesh");
@@ -170,6 +245,7 @@ int rxm_mesh_to_device(rxm_mesh* m)
         m->view.patch_slot_base[t] = m->d_slot_base[t];
     }
     m->on_device = true;
+    build_pipe_plan(m);
     return RXM_OK;
 }
 
@@ -190,6 +266,14 @@ int rxm_mesh_compact(rxm_mesh* m)
 void rxm_mesh_destroy(rxm_mesh* m)
 {
     if (!m) return;
+    for (auto& pp : m->pipe) {
+        for (auto e : pp.up) cudaEventDestroy(e);
+        for (auto e : pp.comp) cudaEventDestroy(e);
+        if (pp.start) cudaEventDestroy(pp.start);
+        if (pp.done) cudaEventDestroy(pp.done);
+        if (pp.h2d) cudaStreamDestroy(pp.h2d);
+        if (pp.d2h) cudaStreamDestroy(pp.d2h);
+    }
     for (auto*& s : m->scratch)
         if (s) {
             rxm_attr_destroy(s);
@@ -817,6 +901,76 @@ int rxm_boundary_vertices(rxm_mesh* m, rxm_attr* flag, void* stream)
     return kernel_status(e, why, "rxm_boundary_vertices");
 }
 
+// One host-buffer call as a K-stage pipeline (plan: build_pipe_plan): the input travels H2D in K global-order pieces on
+// its own stream; as soon as a chunk of patches has its owned slots filled and its ribbon owners present, `launch`
+// runs on that patch range (a MeshView whose descriptor pointer is offset) on the caller's stream; its results are
+// scattered back to global order and leave D2H on a third stream while later pieces are still arriving.
+extern "C++" {
+template <class Launch>
+static int pipelined_host_call(rxm_mesh* m, rxm_attr* ain, rxm_attr* aout, const void* host_in, void* host_out, int k,
+                               void* stream, bool sync, Launch launch)
+{
+    const auto&    P  = m->plan;
+    const uint32_t K  = P.K;
+    const int      ti = ain->elem, to = aout->elem;
+    const size_t   row_i = (size_t)ain->nattr * ain->elem_bytes, row_o = (size_t)aout->nattr * aout->elem_bytes;
+    int            rc;
+    if ((rc = ensure_stage(m, (size_t)m->h.num_elems[ti] * row_i, k))) return rc;
+    if ((rc = ensure_stage(m, (size_t)m->h.num_elems[to] * row_o, k + 1))) return rc;
+    auto& pp = m->pipe[k];
+    if (!pp.h2d) {
+        CU(cudaStreamCreateWithFlags(&pp.h2d, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&pp.d2h, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&pp.start, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&pp.done, cudaEventDisableTiming));
+        pp.up.resize(K), pp.comp.resize(K);
+        for (uint32_t c = 0; c < K; ++c) {
+            CU(cudaEventCreateWithFlags(&pp.up[c], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&pp.comp[c], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t S = (cudaStream_t)stream;
+    uint8_t *    din = (uint8_t*)m->d_stage[k], *dout = (uint8_t*)m->d_stage[k + 1];
+    CU(cudaEventRecord(pp.start, S));  // the pipeline starts after the work already queued on the caller's stream
+    CU(cudaStreamWaitEvent(pp.h2d, pp.start, 0));
+    CU(cudaStreamWaitEvent(pp.d2h, pp.start, 0));
+    for (uint32_t c = 0; c < K; ++c) {
+        const uint64_t g0 = c ? P.up_hi[ti][c - 1] : 0, g1 = P.up_hi[ti][c];
+        if (g1 > g0)
+            CU(cudaMemcpyAsync(din + g0 * row_i, (const uint8_t*)host_in + g0 * row_i, (g1 - g0) * row_i,
+                               cudaMemcpyHostToDevice, pp.h2d));
+        CU(cudaEventRecord(pp.up[c], pp.h2d));
+    }
+    uint32_t q = 0;
+    for (uint32_t c = 0; c < K; ++c) {
+        CU(cudaStreamWaitEvent(S, pp.up[c], 0));
+        cudaError_t e = launch_permute_to_slots(din, ain->d, m->d_s2g[ti], m->h.num_slots[ti], ain->elem_bytes, ain->nattr,
+                                                ain->layout, m->d_slot_base[ti] + P.pb[c], P.pb[c + 1] - P.pb[c], S);
+        if (e != cudaSuccess) return fail(RXM_ERR_CUDA, std::string("permute: ") + cudaGetErrorString(e));
+        while (q < K && P.need[q] <= c) {
+            MeshView v    = m->view;
+            v.desc        = m->d_desc + P.pb[q];
+            v.num_patches = P.pb[q + 1] - P.pb[q];
+            if ((rc = launch(v, S))) return rc;
+            e = launch_permute_to_global(aout->d, dout, m->d_s2g[to], m->h.num_slots[to], aout->elem_bytes, aout->nattr,
+                                         aout->layout, m->d_slot_base[to] + P.pb[q], P.pb[q + 1] - P.pb[q], S);
+            if (e != cudaSuccess) return fail(RXM_ERR_CUDA, std::string("permute: ") + cudaGetErrorString(e));
+            CU(cudaEventRecord(pp.comp[q], S));
+            CU(cudaStreamWaitEvent(pp.d2h, pp.comp[q], 0));
+            const uint64_t g0 = P.down_lo[to][q], g1 = P.down_lo[to][q + 1];
+            if (g1 > g0)
+                CU(cudaMemcpyAsync((uint8_t*)host_out + g0 * row_o, dout + g0 * row_o, (g1 - g0) * row_o,
+                                   cudaMemcpyDeviceToHost, pp.d2h));
+            ++q;
+        }
+    }
+    CU(cudaEventRecord(pp.done, pp.d2h));
+    CU(cudaStreamWaitEvent(S, pp.done, 0));  // a sync on the caller's stream covers the whole call
+    if (sync) CU(cudaStreamSynchronize(S));
+    return RXM_OK;
+}
+}  // extern "C++"
+
 int rxm_vertex_normals_host(rxm_mesh* m, const float* coords, float* normals, void* stream)
 {
     int rc = check_dev(m, "rxm_vertex_normals_host");
@@ -824,6 +978,13 @@ int rxm_vertex_normals_host(rxm_mesh* m, const float* coords, float* normals, vo
     if (!coords || !normals) return fail(RXM_ERR_INVALID, "rxm_vertex_normals_host: null buffer");
     rxm_attr *x, *n;
     if ((rc = get_scratch(m, 1, &x)) || (rc = get_scratch(m, 2, &n))) return rc;
+    if (m->plan.K)
+        return pipelined_host_call(m, x, n, coords, normals, 2, stream, !g_async_host_calls,
+                                   [&](const MeshView& v, cudaStream_t s) {
+                                       const char* why = nullptr;
+                                       cudaError_t e = launch_vertex_normals(v, m->lim, (const float*)x->d, (float*)n->d, 0, s, &why);
+                                       return kernel_status(e, why, "rxm_vertex_normals_host");
+                                   });
     if ((rc = upload_via(x, coords, stream, 2))) return rc;
     if ((rc = rxm_vertex_normals(m, x, n, 0, stream))) return rc;
     return download_via(n, normals, stream, 3, !g_async_host_calls);
@@ -851,6 +1012,13 @@ int rxm_query_consume_host(rxm_mesh* m, int op, const float* in, float* out, voi
     rxm_attr*& b = m->scratch1[2 * (op & 15) + 1];
     if (!a && (rc = rxm_attr_create(m, op_dst(op), 4, 1, RXM_DEVICE, RXM_AOS, &a))) return rc;
     if (!b && (rc = rxm_attr_create(m, op_src(op), 4, 1, RXM_DEVICE, RXM_AOS, &b))) return rc;
+    if (m->plan.K)
+        return pipelined_host_call(m, a, b, in, out, 4 + 2 * (op & 15) % 28, stream, !g_async_host_calls,
+                                   [&](const MeshView& v, cudaStream_t s) {
+                                       const char* why = nullptr;
+                                       cudaError_t e = launch_query_consume(op, v, m->lim, view_of<float>(a), view_of<float>(b), s, &why);
+                                       return kernel_status(e, why, "rxm_query_consume_host");
+                                   });
     if ((rc = upload_via(a, in, stream, 4 + 2 * (op & 15) % 28))) return rc;
     if ((rc = rxm_query_consume(m, op, a, b, stream))) return rc;
     return download_via(b, out, stream, 5 + 2 * (op & 15) % 28, !g_async_host_calls);

@@ -60,3 +60,36 @@ def test_apps(built):
     flag = rx.Attribute(m, 0, np.uint32, 1, rx.LOCATION_ALL, rx.AoS)
     m.boundary_vertices(flag)
     assert np.array_equal(flag.to_global().reshape(-1).astype(bool), T.boundary_vertices()[1])
+
+
+@pytest.mark.parametrize("mesh,tiles", [("grid200x150", True), ("grid200x150", False), ("dragon", False), ("torus64x48", False)])
+def test_pipelined_host_calls_match_plain(monkeypatch, mesh, tiles):
+    """The host-buffer entry points run as a chunked H2D / kernel / D2H pipeline (rxm_capi.cu: pipelined_host_call)
+    whenever the mesh has enough patches.  They must return exactly what the plain upload -> kernel -> download path
+    (RXM_PIPE_CHUNKS=0) returns, for tile-ordered patches (real overlap) and for Lloyd patches (degenerate frontiers)."""
+    from rxmesh_b200 import meshio
+    rx.rx_init(0)
+    V, F = make_mesh(mesh)
+    fp = meshio.grid_face_tiles(200, 150, 8) if tiles else None
+    rng = np.random.RandomState(3)
+    res = {}
+    for chunks in ("0", "8", "5"):
+        monkeypatch.setenv("RXM_PIPE_CHUNKS", chunks)
+        m = rx.RXMeshStatic(F, face_patch=fp, patch_size=128)
+        assert m.get_num_patches() >= 16
+        sv = rng.rand(m.get_num_vertices()).astype(np.float32) if "sv" not in res else res["sv"]
+        sf = rng.rand(m.get_num_faces()).astype(np.float32) if "sf" not in res else res["sf"]
+        res.setdefault("sv", sv), res.setdefault("sf", sf)
+        got = (m.vertex_normals_host(V), m.query_consume_host(rx.Op.VV, sv), m.query_consume_host(rx.Op.VF, sf),
+               m.query_consume_host(rx.Op.FV, sv), m.query_consume_host(rx.Op.EF, sf))
+        # twice on the same mesh: staging buffers and events are reused
+        again = m.vertex_normals_host(V)
+        assert np.array_equal(got[0], again)
+        if "plain" not in res:
+            res["plain"] = got
+        else:
+            for a, b in zip(res["plain"], got):
+                assert np.array_equal(a, b), chunks
+    ref = O.vertex_normals(F, V, np.float64)
+    err = np.linalg.norm(res["plain"][0] - ref, axis=1) / np.maximum(np.linalg.norm(ref, axis=1), 1e-30)
+    assert err.max() < 1e-5
