@@ -330,17 +330,25 @@ def run_ours(args, rank, world, local_rank):
         return run_laplacian(args, rank, world, local_rank, mesh, x, nrm, hx_v, nV if world == 1 else None,
                              n, t_build, torch, rx, stream)
 
+    comm = torch.cuda.Stream() if hx_v is not None else None
+
     def step(evs=None):
         if evs:
             evs[0].record(stream)
         if hx_v is not None:
-            hx_v.exchange(x, stream)  # ribbon (halo) exchange, inside the timed step
+            # ribbon (halo) exchange of the coordinates, inside the timed step, on its own stream: only the vertex
+            # normals read the mirrored coordinates, so the NVLink transfer overlaps the two query kernels
+            comm.wait_stream(stream)
+            with torch.cuda.stream(comm):
+                hx_v.exchange(x, comm)
         mesh.query_consume(rx.Op.VV, sv_in, sv_out, stream)
         if evs:
             evs[1].record(stream)
         mesh.query_consume(rx.Op.VF, sf_in, sv_out, stream)
         if evs:
             evs[2].record(stream)
+        if hx_v is not None:
+            stream.wait_stream(comm)
         mesh.vertex_normals(x, nrm, False, stream)
         if evs:
             evs[3].record(stream)
@@ -431,7 +439,14 @@ def run_ours(args, rank, world, local_rank):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(dom)
+            tj = json.load(open(tp))
+            traffic = tj.get(dom)
+            # fraction by ACTUAL DRAM bytes (ncu, per launch, 100M-face mesh): the algorithmic-byte fraction can exceed 1
+            # because 16-bit local ids and owned-only attributes move fewer bytes than the canonical count
+            for k in kern:
+                if k in tj and world == 1 and abs(nF - 99998082) < 1000:
+                    kern[k]["dram_bytes_ncu"] = tj[k]
+                    kern[k]["dram_frac"] = tj[k] / (kern[k]["ms"] * 1e-3) / 1e9 / peak
         except Exception:
             traffic = None
     line = {
@@ -441,8 +456,8 @@ def run_ours(args, rank, world, local_rank):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(args, n, nF, mesh),
         "kernels": kern,
-        "roofline": {"bound": "hbm", "kernel": {"VV": "k_query_consume<VV>", "VF": "k_query_consume<VF>",
-                                                "VN": "k_vertex_normals"}[dom],
+        "roofline": {"bound": "hbm", "kernel": {"VV": "k_vv_consume_fan<128>", "VF": "k_vf_consume_fan<128>",
+                                                "VN": "k_vertex_normals_fan2<0>"}[dom],
                      "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                      "frac": kern[dom]["hbm_frac"], "traffic": traffic, "peak_source": peak_src,
                      "alg_bytes_per_launch": kern[dom]["alg_bytes"]},
@@ -468,6 +483,9 @@ def run_laplacian(args, rank, world, local_rank, mesh, x, y, hx_v, nv_single, n,
         n_upd = mesh.get_num_vertices()
     else:
         n_upd = None
+    # Exchange after every iteration on the compute stream.  Splitting the step into boundary patches -> exchange on a
+    # second stream -> interior patches was measured at N = 2 (0.266 vs 0.262 ms per iteration): the 60 KB transfer is
+    # already cheap, the extra launches cost more than the overlap returns, so the simple order stays.
     def iterate(k):
         a, b = x, y
         for _ in range(k):
@@ -475,6 +493,7 @@ def run_laplacian(args, rank, world, local_rank, mesh, x, y, hx_v, nv_single, n,
             if hx_v is not None:
                 hx_v.exchange(b, stream)
             a, b = b, a
+
     def barrier():
         torch.cuda.synchronize()
         if world > 1:

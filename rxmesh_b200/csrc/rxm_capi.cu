@@ -905,6 +905,13 @@ int rxm_boundary_vertices(rxm_mesh* m, rxm_attr* flag, void* stream)
 // its own stream; as soon as a chunk of patches has its owned slots filled and its ribbon owners present, `launch`
 // runs on that patch range (a MeshView whose descriptor pointer is offset) on the caller's stream; its results are
 // scattered back to global order and leave D2H on a third stream while later pieces are still arriving.
+// the pipeline covers the whole mesh: a shard that computes on a sub-range of its patches (ghost patches excluded,
+// rxm_mesh_set_active_patches) keeps the plain upload -> kernel -> download path
+static bool use_pipeline(const rxm_mesh* m)
+{
+    return m->plan.K && (!m->active_count || m->active_count == m->h.num_patches);
+}
+
 extern "C++" {
 template <class Launch>
 static int pipelined_host_call(rxm_mesh* m, rxm_attr* ain, rxm_attr* aout, const void* host_in, void* host_out, int k,
@@ -978,7 +985,7 @@ int rxm_vertex_normals_host(rxm_mesh* m, const float* coords, float* normals, vo
     if (!coords || !normals) return fail(RXM_ERR_INVALID, "rxm_vertex_normals_host: null buffer");
     rxm_attr *x, *n;
     if ((rc = get_scratch(m, 1, &x)) || (rc = get_scratch(m, 2, &n))) return rc;
-    if (m->plan.K)
+    if (use_pipeline(m))
         return pipelined_host_call(m, x, n, coords, normals, 2, stream, !g_async_host_calls,
                                    [&](const MeshView& v, cudaStream_t s) {
                                        const char* why = nullptr;
@@ -1012,7 +1019,7 @@ int rxm_query_consume_host(rxm_mesh* m, int op, const float* in, float* out, voi
     rxm_attr*& b = m->scratch1[2 * (op & 15) + 1];
     if (!a && (rc = rxm_attr_create(m, op_dst(op), 4, 1, RXM_DEVICE, RXM_AOS, &a))) return rc;
     if (!b && (rc = rxm_attr_create(m, op_src(op), 4, 1, RXM_DEVICE, RXM_AOS, &b))) return rc;
-    if (m->plan.K)
+    if (use_pipeline(m))
         return pipelined_host_call(m, a, b, in, out, 4 + 2 * (op & 15) % 28, stream, !g_async_host_calls,
                                    [&](const MeshView& v, cudaStream_t s) {
                                        const char* why = nullptr;
