@@ -49,14 +49,15 @@ struct Query
         return d;
     }
 
-    template <Op op, bool PACKED, typename computeT, typename activeSetT>
-    __device__ void run(ShmemAllocator& sa, computeT& compute_op, activeSetT& active, bool oriented, bool all_sources)
+    // builds the adjacency of this patch in shared memory (TMA loads + transpose / fans); leaves the result view
+    // and the owner table; all threads of the block call it; returns the allocator mark to restore in release()
+    template <Op op, bool PACKED>
+    __device__ uint32_t build(ShmemAllocator& sa, bool oriented, bool all_sources, rxm::dev::QueryResult& r,
+                              rxm::dev::OwnerTable& ot)
     {
         using namespace rxm::dev;
-        using InH  = typename InputHandle<op>::type;
-        using OutH = typename OutputHandle<op>::type;
         constexpr int OPV = (int)op;
-        __shared__ uint64_t bar;
+        __shared__ uint64_t bar;  // one phase per call; invalidated below once every thread has passed the wait
         __shared__ uint32_t warp_tmp[36];
         const rxm::PatchDesc& d    = m_desc;
         const uint8_t*        blob = m_ctx.view.topo + d.topo_off;
@@ -91,8 +92,9 @@ struct Query
         }
         __syncthreads();
         mbar_wait(&bar, 0);
-        QueryResult r;
-        OwnerTable  ot;
+        __syncthreads();
+        if (threadIdx.x == 0) mbar_inval(&bar);  // a kernel may run several queries (a second dispatch, every round of
+                                                 // higher_query_block_dispatcher): the next call initialises it again
         if (use_fans) {
             // fan_off entries carry the closed flag in bit 15: strip it once so the list bounds are plain
             for (uint32_t i = threadIdx.x; i <= d.n_owned[rxm::ELEM_V]; i += blockThreads)
@@ -107,16 +109,53 @@ struct Query
             if (op_is_fixed<OPV>()) __syncthreads();
             ot = q.owner_table(d);
         }
+        return used0;
+    }
+    // epilogue: every thread is done with the result; release the query's shared memory (query.inl:74-91)
+    __device__ void release(ShmemAllocator& sa, uint32_t used0)
+    {
+        __syncthreads();
+        sa.m_sm.used = used0;
+    }
+
+    template <Op op, bool PACKED, typename computeT, typename activeSetT>
+    __device__ void run(ShmemAllocator& sa, computeT& compute_op, activeSetT& active, bool oriented, bool all_sources)
+    {
+        using InH  = typename InputHandle<op>::type;
+        using OutH = typename OutputHandle<op>::type;
+        rxm::dev::QueryResult r;
+        rxm::dev::OwnerTable  ot;
+        const uint32_t        used0 = build<op, PACKED>(sa, oriented, all_sources, r, ot);
         for (uint32_t s = threadIdx.x; s < r.n_src; s += blockThreads) {
-            InH h(d.patch_id, typename InH::LocalT((uint16_t)s));
+            InH h(m_desc.patch_id, typename InH::LocalT((uint16_t)s));
             if (!active(h)) continue;
             Iterator<OutH> it(r, ot, s);
             compute_op(h, it);
         }
-        __syncthreads();
-        sa.m_sm.used = used0;  // epilogue: release the query's shared memory (query.inl:74-91)
+        release(sa, used0);
     }
 
+   public:
+    // The query of THIS patch answered for one source element per thread (the element may differ per thread, threads
+    // without one pass has_src = false): the building block of higher_query_block_dispatcher
+    // (kernels/query_dispatcher.cuh:445-565), called by the whole block.
+    template <Op op, typename computeT>
+    __device__ void dispatch_src(ShmemAllocator& sa, bool has_src, typename InputHandle<op>::type src, computeT& compute_op,
+                                 bool oriented)
+    {
+        using OutH = typename OutputHandle<op>::type;
+        rxm::dev::QueryResult r;
+        rxm::dev::OwnerTable  ot;
+        const uint32_t used0 = m_ctx.view.packed ? build<op, true>(sa, oriented, false, r, ot)
+                                                 : build<op, false>(sa, oriented, false, r, ot);
+        if (has_src && src.local_id() < r.n_src) {
+            Iterator<OutH> it(r, ot, src.local_id());
+            compute_op(src, it);
+        }
+        release(sa, used0);
+    }
+
+   private:
     const Context&       m_ctx;
     uint32_t             m_pid;
     const rxm::PatchDesc m_desc;

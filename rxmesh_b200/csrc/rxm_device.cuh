@@ -34,6 +34,13 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 
+// an mbarrier object must be invalidated before its storage is initialised again (PTX: mbarrier.init on a live
+// object is undefined); used by code that runs several load phases per kernel through one static barrier
+__device__ __forceinline__ void mbar_inval(uint64_t* bar)
+{
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // make the barrier initialisation visible to the async (TMA) proxy
 __device__ __forceinline__ void fence_mbar_init()
 {

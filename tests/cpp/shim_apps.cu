@@ -8,6 +8,7 @@
 
 #include "rxmesh/attribute.h"
 #include "rxmesh/geometry_util.cuh"
+#include "rxmesh/kernels/query_dispatcher.cuh"
 #include "rxmesh/query.h"
 #include "rxmesh/rxmesh_static.h"
 
@@ -100,6 +101,105 @@ __global__ static void user_gaussian_curvature(const Context context, VertexAttr
     Query<blockThreads> query(context);
     ShmemAllocator      shrd_alloc;
     query.template dispatch<Op::FV>(block, shrd_alloc, gc_lambda);
+}
+
+// ---- the Filtering app (apps/Filtering/filtering_rxmesh_kernel.cuh:15-85,426-548, filtering_util.h:31-76):
+// unit-face-normal vertex normals, then per vertex a breadth-first k-ring gathered with the free-function
+// query_block_dispatcher (first ring) and higher_query_block_dispatcher (every further ring), then the bilateral update
+template <typename T, uint32_t blockThreads>
+__global__ static void user_filter_vertex_normal(const Context context, VertexAttribute<T> coords, VertexAttribute<T> normals)
+{
+    auto vn_lambda = [&](FaceHandle, VertexIterator& fv) {
+        const vec3<T> c0 = coords.template to_glm<3>(fv[0]), c1 = coords.template to_glm<3>(fv[1]),
+                      c2 = coords.template to_glm<3>(fv[2]);
+        const vec3<T> n = glm::normalize(glm::cross(c1 - c0, c2 - c0));
+        for (uint32_t v = 0; v < 3; ++v)
+            for (uint32_t i = 0; i < 3; ++i)
+                atomicAdd(&normals(fv[v], i), n[i]);
+    };
+    auto                block = cooperative_groups::this_thread_block();
+    Query<blockThreads> query(context);
+    ShmemAllocator      shrd_alloc;
+    query.template dispatch<Op::FV>(block, shrd_alloc, vn_lambda);
+}
+
+template <typename T, typename S>
+__device__ __forceinline__ bool user_linear_search(const T list[], const T item, const S end)
+{
+    for (S i = 0; i < end; ++i)
+        if (list[i] == item) return true;
+    return false;
+}
+
+template <typename T, uint32_t blockThreads, uint32_t maxVVSize>
+__global__ static void user_bilateral_filtering(const Context context, VertexAttribute<T> input_coords,
+                                                VertexAttribute<T> filtered_coords, VertexAttribute<T> vertex_normals)
+{
+    VertexHandle vv[maxVVSize];
+    uint32_t     num_vv     = 0;
+    T            sigma_c_sq = 0, radius = 0;
+    vec3<T>      vertex, normal;
+    VertexHandle v_id;
+
+    auto first_ring = [&](VertexHandle& p_id, VertexIterator& iter) {
+        v_id   = p_id;
+        vertex = input_coords.template to_glm<3>(v_id);
+        normal = glm::normalize(vertex_normals.template to_glm<3>(v_id));
+        vv[0]  = v_id;
+        ++num_vv;
+        sigma_c_sq = 1e10;
+        for (uint32_t v = 0; v < iter.size(); ++v) {
+            const T len = glm::distance2(vertex, input_coords.template to_glm<3>(iter[v]));
+            if (len < sigma_c_sq) sigma_c_sq = len;
+        }
+        radius = 4.0 * sigma_c_sq;
+        for (uint32_t v = 0; v < iter.size(); ++v) {
+            const VertexHandle vv_id = iter[v];
+            if (glm::distance2(vertex, input_coords.template to_glm<3>(vv_id)) <= radius) vv[num_vv++] = vv_id;
+        }
+    };
+    query_block_dispatcher<Op::VV, blockThreads>(context, first_ring);
+    __syncthreads();
+
+    uint32_t next_id = 1;
+    while (true) {
+        VertexHandle next_vertex;
+        if (v_id.is_valid() && next_id < num_vv) next_vertex = vv[next_id];
+        auto n_rings = [&](const VertexHandle& id, const VertexIterator& iter) {
+            for (uint32_t i = 0; i < iter.size(); ++i) {
+                const VertexHandle vvv_id = iter[i];
+                if (vvv_id != v_id && !user_linear_search(vv, vvv_id, num_vv)) {
+                    if (glm::distance2(input_coords.template to_glm<3>(vvv_id), vertex) <= radius && num_vv < maxVVSize)
+                        vv[num_vv++] = vvv_id;
+                }
+            }
+        };
+        higher_query_block_dispatcher<Op::VV, blockThreads>(context, next_vertex, n_rings);
+        const bool is_done = (next_id >= num_vv) || !v_id.is_valid();
+        if (__syncthreads_and(is_done)) break;
+        next_id++;
+    }
+
+    if (v_id.is_valid()) {
+        // compute_sigma_s_sq (filtering_util.h:31-59) + compute_new_coordinates (filtering_rxmesh_kernel.cuh:52-85)
+        T sum = 0, sum_sq = 0;
+        for (uint32_t i = 0; i < num_vv; ++i) {
+            T t = fabs(glm::dot(input_coords.template to_glm<3>(vv[i]) - vertex, normal));
+            sum += t, sum_sq += t * t;
+        }
+        const T c          = static_cast<T>(num_vv);
+        T       sigma_s_sq = (sum_sq / c) - ((sum * sum) / (c * c));
+        sigma_s_sq         = (sigma_s_sq < 1.0e-20) ? (sigma_s_sq + 1.0e-20) : sigma_s_sq;
+        T acc = 0, normalizer = 0;
+        for (uint32_t i = 0; i < num_vv; ++i) {
+            const vec3<T> q  = input_coords.template to_glm<3>(vv[i]) - vertex;
+            const T       t  = glm::length(q), h = glm::dot(q, normal);
+            const T       wc = exp(-0.5 * t * t / sigma_c_sq), ws = exp(-0.5 * h * h / sigma_s_sq);
+            acc += wc * ws * h, normalizer += wc * ws;
+        }
+        vertex += normal * (acc / normalizer);
+        filtered_coords(v_id, 0) = vertex[0], filtered_coords(v_id, 1) = vertex[1], filtered_coords(v_id, 2) = vertex[2];
+    }
 }
 
 template <uint32_t blockThreads, Op op, typename InH, typename OutH, typename InA, typename OutA>
@@ -302,6 +402,40 @@ static int app_time_vertex_normals(const uint32_t* fv, uint32_t nf, const float*
     return 0;
 }
 
+// the Filtering driver loop (apps/Filtering/filtering_rxmesh.cuh:60-100)
+static int app_filtering(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, int num_iter,
+                         float* out)
+{
+    rx_init(0);
+    RXMeshStatic rx(to_faces(fv, nf), "", patch_size);
+    // the kernel keeps ONE vertex's state per thread (as the reference's does), so a block must cover every owned vertex
+    // of its patch: 512-face patches own up to ~300 vertices -> 512 threads (the reference app launches 256)
+    constexpr uint32_t blockThreads = 512, maxVVSize = 80;
+    auto coords   = rx.add_vertex_attribute<float>(to_verts(x, nv), "coords");
+    auto filtered = rx.add_vertex_attribute<float>("filtered", 3, LOCATION_ALL);
+    auto normals  = rx.add_vertex_attribute<float>("vn", 3, LOCATION_ALL);
+    LaunchBox<blockThreads> lb_vn, lb_f;
+    rx.prepare_launch_box({Op::FV}, lb_vn, (void*)user_filter_vertex_normal<float, blockThreads>);
+    rx.prepare_launch_box({Op::VV}, lb_f, (void*)user_bilateral_filtering<float, blockThreads, maxVVSize>);
+    VertexAttribute<float>* a = coords.get();
+    VertexAttribute<float>* b = filtered.get();
+    for (int it = 0; it < num_iter; ++it) {
+        normals->reset(0, DEVICE);
+        user_filter_vertex_normal<float, blockThreads><<<lb_vn.blocks, blockThreads, lb_vn.smem_bytes_dyn>>>(rx.get_context(), *a, *normals);
+        user_bilateral_filtering<float, blockThreads, maxVVSize><<<lb_f.blocks, blockThreads, lb_f.smem_bytes_dyn>>>(
+            rx.get_context(), *a, *b, *normals);
+        std::swap(a, b);
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+    a->move(DEVICE, HOST);
+    rx.for_each_vertex(HOST, [&](const VertexHandle& vh) {
+        const uint32_t v_id = rx.map_to_global(vh);
+        for (uint32_t i = 0; i < 3; ++i)
+            out[v_id * 3 + i] = (*a)(vh, i);
+    }, NULL, false);
+    return 0;
+}
+
 // manual smoothing (apps/Smoothing/manual.h:86-104): for_each<Op::VV> gradient + for_each_vertex(DEVICE) step
 static int app_smoothing(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, double lr,
                          int num_iter, int oriented, float* out)
@@ -367,6 +501,10 @@ int shim_time_vertex_normals(const uint32_t* fv, uint32_t nf, const float* x, ui
                              uint32_t patch_size, int nrun, float* ms_out)
 {
     return app_time_vertex_normals(fv, nf, x, nv, face_patch, patch_size, nrun, ms_out);
+}
+int shim_filtering(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, int num_iter, float* out)
+{
+    return app_filtering(fv, nf, x, nv, patch_size, num_iter, out);
 }
 int shim_smoothing(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, double lr, int num_iter,
                    int oriented, float* out)

@@ -132,3 +132,34 @@ def test_user_gaussian_curvature(shim, name):
     assert np.abs(a - ra).max() < 1e-4 * np.abs(ra).max()
     if name == "sphere3":  # Gauss-Bonnet on a closed genus-0 mesh: sum(2 pi - angles) = 4 pi
         assert abs((2 * np.pi + rg).sum() - 4 * np.pi) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["sphere3", "torus", "dragon"])
+def test_user_filtering_app(shim, name):
+    """The Filtering app in the reference's own form (apps/Filtering/filtering_rxmesh_kernel.cuh:426-548): free-function
+    query_block_dispatcher for the first ring, higher_query_block_dispatcher for every further ring, through the
+    drop-in headers; against the oracle's bilateral step and our fixed-function rxm_bilateral_filter."""
+    V, F = make_mesh(name)
+    T = O.Topology(F)
+    rng = np.random.RandomState(3)
+    scale = np.abs(V).max()
+    ref_n = O.vertex_normals(F, V, np.float64)
+    ref_n /= np.linalg.norm(ref_n, axis=1, keepdims=True)
+    mean_edge = np.linalg.norm(V[T.ev[:, 0]] - V[T.ev[:, 1]], axis=1).mean()
+    noisy = (V + ref_n * (0.2 * mean_edge * (2 * rng.rand(V.shape[0], 1) - 1))).astype(np.float32)
+    iters = 2
+    out = np.zeros_like(noisy)
+    assert shim.shim_filtering(_p(F), F.shape[0], _p(noisy), V.shape[0], 512, iters, _p(out)) == 0
+    ref, vv = noisy, T.query("VV")
+    for _ in range(iters):
+        ref, worst = O.bilateral_step(vv, F, ref, 80, True)
+    err = np.abs(out - ref).max(axis=1)
+    assert np.mean(err < 2e-5 * scale * iters) > 0.995, np.mean(err < 2e-5 * scale * iters)
+    assert err.max() < 1e-2 * max(1.0, scale)  # the app's own criterion (filtering_rxmesh.cuh:114-125)
+    m = rx.RXMeshStatic(F, patch_size=512)
+    x = rx.Attribute(m, 0, np.float32, 3, rx.LOCATION_ALL, rx.AoS)
+    y = rx.Attribute(m, 0, np.float32, 3, rx.LOCATION_ALL, rx.AoS)
+    x.from_global(noisy)
+    m.bilateral_filter(x, y, iters)
+    fixed = y.to_global()
+    assert np.mean(np.abs(out - fixed).max(axis=1) < 2e-5 * scale * iters) > 0.995
