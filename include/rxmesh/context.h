@@ -11,6 +11,19 @@ class Context
     __host__ __device__ uint32_t get_num_vertices() const { return view.num_elems[rxm::ELEM_V]; }
     __host__ __device__ uint32_t get_num_edges() const { return view.num_elems[rxm::ELEM_E]; }
     __host__ __device__ uint32_t get_num_faces() const { return view.num_elems[rxm::ELEM_F]; }
+    // get_owner_handle (context.h:219-270): a (patch, local id) naming a not-owned copy -> the owner's handle, through
+    // the patch's direct owner table in the topology blob (two dependent global loads, no hash probe)
+    template <typename HandleT>
+    __device__ HandleT get_owner_handle(const HandleT handle) const
+    {
+        const rxm::PatchDesc& d   = view.desc[handle.patch_id()];
+        const uint32_t        lid = handle.local_id(), t = HandleT::elem;
+        if (lid < d.n_owned[t]) return handle;
+        const uint8_t*  blob = view.topo + d.topo_off;
+        const uint32_t  o    = reinterpret_cast<const uint32_t*>(blob + d.off_own(t))[lid - d.n_owned[t]];
+        const uint32_t  pid  = reinterpret_cast<const rxm::StashEntry*>(blob + d.off_stash())[o >> 16].patch;
+        return HandleT(pid, typename HandleT::LocalT((uint16_t)(o & 0xFFFFu)));
+    }
     // linear_id (context.h:275-290) of an OWNER handle: prefix[patch] + local
     template <typename HandleT>
     __device__ uint32_t linear_id(HandleT h) const

@@ -3,11 +3,29 @@
 // (InputHandle, OutputIterator&) once per OWNED source element that passes the active-set predicate.
 #pragma once
 #include <cooperative_groups.h>
+#include <type_traits>
 #include "rxmesh/context.h"
 #include "rxmesh/iterator.cuh"
 #include "rxmesh/kernels/shmem_allocator.cuh"
 
 namespace rxmesh {
+namespace detail {
+// first / second parameter types of a compute lambda (the reference's FunctionTraits, util/meta.h)
+template <typename T>
+struct LambdaArgs : LambdaArgs<decltype(&T::operator())> {};
+template <typename C, typename R, typename A0, typename A1>
+struct LambdaArgs<R (C::*)(A0, A1) const>
+{
+    using Arg0 = std::remove_cv_t<std::remove_reference_t<A0>>;
+    using Arg1 = std::remove_cv_t<std::remove_reference_t<A1>>;
+};
+template <typename C, typename R, typename A0, typename A1>
+struct LambdaArgs<R (C::*)(A0, A1)>
+{
+    using Arg0 = std::remove_cv_t<std::remove_reference_t<A0>>;
+    using Arg1 = std::remove_cv_t<std::remove_reference_t<A1>>;
+};
+}  // namespace detail
 template <uint32_t blockThreads>
 struct Query
 {
@@ -36,6 +54,87 @@ struct Query
         else
             run<op, false>(shrd_alloc, compute_op, compute_active_set, oriented, allow_not_owned);
     }
+
+    // ---- the split form of dispatch (query.h:83-127, query.inl:178-260): prologue builds the adjacency and keeps it in
+    // shared memory, run_compute / get_iterator read it, epilogue frees it.  prologue's allow_not_owned defaults to
+    // true as in the reference: lists exist for not-owned (ribbon) sources too.
+    template <Op op>
+    __device__ void prologue(cooperative_groups::thread_block& block, ShmemAllocator& shrd_alloc, const bool oriented = false,
+                             const bool allow_not_owned = true)
+    {
+        using InH = typename InputHandle<op>::type;
+        prologue<op>(block, shrd_alloc, [](InH) { return true; }, oriented, allow_not_owned);
+    }
+    template <Op op, typename activeSetT>
+    __device__ void prologue(cooperative_groups::thread_block& block, ShmemAllocator& shrd_alloc, activeSetT compute_active_set,
+                             const bool oriented = false, const bool allow_not_owned = true)
+    {
+        (void)block;
+        using InH  = typename InputHandle<op>::type;
+        m_op       = op;
+        m_used0    = m_ctx.view.packed ? build<op, true>(shrd_alloc, oriented, allow_not_owned, m_r, m_ot)
+                                       : build<op, false>(shrd_alloc, oriented, allow_not_owned, m_r, m_ot);
+        // participant bitmask (query_dispatcher.cuh:27-177): owned sources that pass the predicate, plus every
+        // not-owned source when allow_not_owned
+        const uint32_t words = (m_r.n_src + 31u) / 32u;
+        m_participant        = shrd_alloc.template alloc<uint32_t>(words ? words : 1u);
+        for (uint32_t w = threadIdx.x; w < words; w += blockThreads) {
+            uint32_t bits = 0;
+            for (uint32_t b = 0; b < 32u && 32u * w + b < m_r.n_src; ++b) {
+                const uint32_t s = 32u * w + b;
+                if (s >= m_desc.n_owned[InH::elem] || compute_active_set(InH(m_desc.patch_id, typename InH::LocalT((uint16_t)s))))
+                    bits |= 1u << b;
+            }
+            m_participant[w] = bits;
+        }
+        __syncthreads();
+    }
+    template <typename computeT>
+    __device__ void run_compute(cooperative_groups::thread_block& block, computeT compute_op)
+    {
+        (void)block;
+        using Traits = detail::LambdaArgs<computeT>;
+        using InH    = typename Traits::Arg0;
+        using ItT    = typename Traits::Arg1;
+        for (uint32_t s = threadIdx.x; s < m_r.n_src; s += blockThreads) {
+            if (!((m_participant[s >> 5] >> (s & 31u)) & 1u)) continue;
+            InH h(m_desc.patch_id, typename InH::LocalT((uint16_t)s));
+            ItT it(m_r, m_ot, s);
+            compute_op(h, it);
+        }
+    }
+    template <typename IteratorT>
+    __device__ IteratorT get_iterator(uint16_t local_id) const
+    {
+        return IteratorT(m_r, m_ot, local_id);
+    }
+    __device__ void epilogue(cooperative_groups::thread_block& block, ShmemAllocator& shrd_alloc)
+    {
+        (void)block;
+        release(shrd_alloc, m_used0);
+        m_participant = nullptr;
+    }
+    // compute_vertex_valence / vertex_valence (query.inl:25-74): edges incident to every local vertex of the patch,
+    // counted from EV in shared memory (stays allocated; the reference keeps it for the life of the kernel too)
+    __device__ void compute_vertex_valence(cooperative_groups::thread_block& block, ShmemAllocator& shrd_alloc)
+    {
+        (void)block;
+        const uint32_t nv = m_desc.n[rxm::ELEM_V], ne = m_desc.n[rxm::ELEM_E];
+        m_valence         = shrd_alloc.template alloc<uint32_t>(nv ? nv : 1u);
+        for (uint32_t v = threadIdx.x; v < nv; v += blockThreads)
+            m_valence[v] = 0;
+        __syncthreads();
+        const uint32_t* ev   = reinterpret_cast<const uint32_t*>(m_ctx.view.topo + m_desc.topo_off + m_desc.off_ev());
+        const uint32_t  mask = m_ctx.view.packed ? rxm::PK_ID_MASK : 0xFFFFu;
+        for (uint32_t e = threadIdx.x; e < ne; e += blockThreads) {
+            const uint32_t w = __ldg(ev + e);
+            atomicAdd(&m_valence[w & mask], 1u);
+            atomicAdd(&m_valence[(w >> 16) & mask], 1u);
+        }
+        __syncthreads();
+    }
+    __device__ uint16_t vertex_valence(uint16_t v) const { return (uint16_t)m_valence[v]; }
+    __device__ uint16_t vertex_valence(VertexHandle vh) const { return (uint16_t)m_valence[vh.local_id()]; }
 
    private:
     static __device__ rxm::PatchDesc load(const rxm::PatchDesc* g)
@@ -159,5 +258,12 @@ struct Query
     const Context&       m_ctx;
     uint32_t             m_pid;
     const rxm::PatchDesc m_desc;
+    // state between prologue and epilogue
+    rxm::dev::QueryResult m_r{};
+    rxm::dev::OwnerTable  m_ot{};
+    uint32_t              m_used0       = 0;
+    uint32_t*             m_participant = nullptr;
+    uint32_t*             m_valence     = nullptr;
+    Op                    m_op          = Op::INVALID;
 };
 }  // namespace rxmesh

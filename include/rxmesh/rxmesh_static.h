@@ -2,13 +2,17 @@
 // over librxmesh_b200 (C ABI in include/rxmesh_b200.h).  Same names / argument meaning; user kernels written
 // against the reference (Query::dispatch, for_each<Op>, Attribute::operator()) compile against this header.
 #pragma once
+#include <array>
+#include <fstream>
 #include <functional>
 #include <map>
 #include <memory>
+#include <sstream>
 #include <vector>
 
 #include "rxmesh/attribute.h"
 #include "rxmesh/context.h"
+#include "rxmesh/kernels/for_each.cuh"
 #include "rxmesh/launch_box.h"
 #include "rxmesh/query.h"
 
@@ -24,6 +28,12 @@ inline void check_launch(const char* what)
         fprintf(stderr, "rxmesh_b200: %s launch failed: %s\n", what, cudaGetErrorString(e));
         exit(EXIT_FAILURE);
     }
+}
+template <typename T>
+__global__ static void flags_to_value(T* data, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) data[i] = reinterpret_cast<const uint32_t*>(data)[i] ? T(1) : T(0);
 }
 // detail::query_kernel (kernels/query_kernel.cuh:12-24)
 template <uint32_t blockThreads, Op op, typename LambdaT>
@@ -101,6 +111,33 @@ class RXMeshStatic
         }
         init(flat.data(), (uint32_t)fv.size(), face_patch, ps);
     }
+    // RXMeshStatic(file_path, patcher_file, patch_size) (rxmesh_static.h:61-66): OBJ input, positions kept as the
+    // input vertex coordinates (import_obj semantics of util/import_obj.h: "v x y z" and "f a b c" / "f a/b/c ..." lines,
+    // 1-based or negative indices, triangles only)
+    explicit RXMeshStatic(const std::string file_path, const std::string patcher_file = "", const uint32_t patch_size = 512)
+        : RXMeshStatic(read_obj_faces(file_path), patcher_file, patch_size)
+    {
+        std::vector<std::vector<float>> verts;
+        std::vector<std::vector<uint32_t>> faces;
+        read_obj(file_path, verts, faces);
+        add_vertex_coordinates(verts);
+    }
+    // add_vertex_coordinates (rxmesh_static.h:110-112): attach positions to a mesh built from faces only
+    void add_vertex_coordinates(std::vector<std::vector<float>>& vertices, std::string = "")
+    {
+        if (m_attrs.count("rx:vertices")) return;
+        m_input_coords = add_vertex_attribute<float>(vertices, "rx:vertices");
+    }
+    // get_input_vertex_coordinates (rxmesh_static.h:823)
+    std::shared_ptr<VertexAttribute<float>> get_input_vertex_coordinates()
+    {
+        if (!m_input_coords) {
+            fprintf(stderr, "RXMeshStatic::get_input_vertex_coordinates input vertex was not initialized. Call RXMeshStatic "
+                            "with a constructor to the obj file path\n");
+            exit(EXIT_FAILURE);
+        }
+        return m_input_coords;
+    }
     // RXMesh::save (rxmesh.h:326-329)
     void save(const std::string& filename) const { detail::rxm_check(rxm_mesh_save_patcher_file(m_mesh, filename.c_str())); }
     virtual ~RXMeshStatic()
@@ -167,6 +204,57 @@ class RXMeshStatic
         detail::rxm_check(cudaDeviceSynchronize() == cudaSuccess ? RXM_OK : RXM_ERR_CUDA);
         return a;
     }
+    // add_*_attribute(values, name): one value per element in the order given to the constructor (rxmesh_static.h:608-806)
+    template <class T>
+    std::shared_ptr<VertexAttribute<T>> add_vertex_attribute(const std::vector<T>& values, const std::string& name,
+                                                             layoutT layout = AoSoA)
+    {
+        return add_filled<VertexAttribute<T>>(values.data(), 1, name, layout);
+    }
+    template <class T>
+    std::shared_ptr<FaceAttribute<T>> add_face_attribute(const std::vector<T>& values, const std::string& name, layoutT layout = AoSoA)
+    {
+        return add_filled<FaceAttribute<T>>(values.data(), 1, name, layout);
+    }
+    template <class T>
+    std::shared_ptr<FaceAttribute<T>> add_face_attribute(const std::vector<std::vector<T>>& values, const std::string& name,
+                                                         layoutT layout = AoSoA)
+    {
+        const uint32_t n = values.empty() ? 0 : (uint32_t)values[0].size();
+        std::vector<T> flat;
+        flat.reserve(values.size() * n);
+        for (const auto& v : values)
+            flat.insert(flat.end(), v.begin(), v.end());
+        return add_filled<FaceAttribute<T>>(flat.data(), n, name, layout);
+    }
+    // add_*_attribute_like (rxmesh_static.h:643-806): same allocation, number of attributes and layout as `other`
+    template <class T>
+    std::shared_ptr<VertexAttribute<T>> add_vertex_attribute_like(const std::string& name, const VertexAttribute<T>& other)
+    {
+        return add<VertexAttribute<T>>(name, other.get_num_attributes(), other.get_allocated(), other.get_layout());
+    }
+    template <class T>
+    std::shared_ptr<EdgeAttribute<T>> add_edge_attribute_like(const std::string& name, const EdgeAttribute<T>& other)
+    {
+        return add<EdgeAttribute<T>>(name, other.get_num_attributes(), other.get_allocated(), other.get_layout());
+    }
+    template <class T>
+    std::shared_ptr<FaceAttribute<T>> add_face_attribute_like(const std::string& name, const FaceAttribute<T>& other)
+    {
+        return add<FaceAttribute<T>>(name, other.get_num_attributes(), other.get_allocated(), other.get_layout());
+    }
+    template <class T, class HandleT>
+    std::shared_ptr<Attribute<T, HandleT>> add_attribute_like(const std::string& name, const Attribute<T, HandleT>& other)
+    {
+        return add<Attribute<T, HandleT>>(name, other.get_num_attributes(), other.get_allocated(), other.get_layout());
+    }
+    std::vector<std::string> get_attribute_names() const
+    {
+        std::vector<std::string> names;
+        for (const auto& kv : m_attrs)
+            names.push_back(kv.first);
+        return names;
+    }
     bool does_attribute_exist(const std::string& name) const { return m_attrs.count(name) != 0; }
     void remove_attribute(const std::string& name) { m_attrs.erase(name); }
 
@@ -180,6 +268,86 @@ class RXMeshStatic
     uint32_t linear_id(const HandleT h) const  // context.h:275-290
     {
         return rxm_mesh_lin_base(m_mesh, HandleT::elem)[h.patch_id()] + h.local_id();
+    }
+
+    // get_owner_handle (rxmesh_static.h:905, context.h:219-270) on the host: a local (possibly not-owned) element of a
+    // patch -> the handle of its owner
+    template <typename HandleT>
+    HandleT get_owner_handle(const HandleT input) const
+    {
+        rxm_patch_view v;
+        detail::rxm_check(rxm_mesh_patch(m_mesh, input.patch_id(), &v));
+        const uint32_t t = HandleT::elem, lid = input.local_id();
+        if (lid < v.n_owned[t]) return input;
+        const uint32_t o = v.owner[t][lid - v.n_owned[t]];
+        return HandleT(v.stash[4 * (o >> 16)], typename HandleT::LocalT((uint16_t)(o & 0xFFFFu)));
+    }
+    // get_boundary_vertices (rxmesh_static.h:816-819, kernels/boundary.cuh:11-44): boundary_v(vh) = 1 on the boundary
+    template <typename T>
+    void get_boundary_vertices(VertexAttribute<T>& boundary_v, bool move_to_host = true, cudaStream_t stream = NULL) const
+    {
+        static_assert(sizeof(T) == 4, "get_boundary_vertices needs a 32-bit attribute");
+        detail::rxm_check(rxm_boundary_vertices(m_mesh, boundary_v.c_handle(), stream));
+        if (!std::is_integral_v<T>)  // the kernel writes integer flags; convert in place for floating-point attributes
+            detail::flags_to_value<T><<<(boundary_v.size() + 255) / 256, 256, 0, stream>>>(boundary_v.data(DEVICE), boundary_v.size());
+        if (move_to_host) boundary_v.move(DEVICE, HOST, stream);
+    }
+    // export_obj (rxmesh_static.inl:365-397): vertices in linear-id order, faces in linear-id order with 1-based
+    // linear vertex ids
+    template <typename T>
+    void export_obj(const std::string& filename, const VertexAttribute<T>& coords) const
+    {
+        std::fstream file(filename, std::ios::out);
+        file.precision(30);
+        const uint32_t                  nv = get_num_vertices(), nf = get_num_faces();
+        std::vector<std::array<T, 3>>   vl(nv);
+        for_each_vertex(HOST, [&](const VertexHandle vh) {
+            for (int i = 0; i < 3; ++i) vl[linear_id(vh)][i] = coords(vh, i);
+        }, NULL, false);
+        for (uint32_t v = 0; v < nv; ++v)
+            file << "v " << vl[v][0] << " " << vl[v][1] << " " << vl[v][2] << " \n";
+        // global vertex id -> linear id
+        const uint32_t* g2s = rxm_mesh_global_to_slot(m_mesh, RXM_V);
+        const uint32_t* ep  = rxm_mesh_elem_patch(m_mesh, RXM_V);
+        const uint32_t* sb  = rxm_mesh_slot_base(m_mesh, RXM_V);
+        const uint32_t* lb  = rxm_mesh_lin_base(m_mesh, RXM_V);
+        std::vector<std::array<uint32_t, 3>> fl(nf);
+        for_each_face(HOST, [&](const FaceHandle fh) {
+            const uint32_t g = map_to_global(fh);
+            for (int i = 0; i < 3; ++i) {
+                const uint32_t gv = m_fv[3 * (size_t)g + i];
+                fl[linear_id(fh)][i] = lb[ep[gv]] + (g2s[gv] - sb[ep[gv]]);
+            }
+        }, NULL, false);
+        for (uint32_t f = 0; f < nf; ++f)
+            file << "f " << fl[f][0] + 1 << " " << fl[f][1] + 1 << " " << fl[f][2] + 1 << " \n";
+    }
+
+    // ---- run_kernel (rxmesh_static.h:415-505) ----
+    template <uint32_t blockThreads, typename KernelT, typename... ArgsT>
+    void run_kernel(const LaunchBox<blockThreads>& lb, const KernelT kernel, cudaStream_t stream, ArgsT... args) const
+    {
+        kernel<<<lb.blocks, lb.num_threads, lb.smem_bytes_dyn, stream>>>(get_context(), args...);
+    }
+    template <uint32_t blockThreads, typename KernelT, typename... ArgsT>
+    void run_kernel(const LaunchBox<blockThreads>& lb, const KernelT kernel, ArgsT... args) const
+    {
+        kernel<<<lb.blocks, lb.num_threads, lb.smem_bytes_dyn>>>(get_context(), args...);
+    }
+    template <uint32_t blockThreads, typename KernelT, typename... ArgsT>
+    void run_kernel(const std::vector<Op> op, KernelT kernel, ArgsT... args) const
+    {
+        run_kernel<blockThreads>(kernel, op, false, false, false,
+                                 [](uint32_t, uint32_t, uint32_t) -> size_t { return 0; }, NULL, args...);
+    }
+    template <uint32_t blockThreads, typename KernelT, typename... ArgsT>
+    void run_kernel(KernelT kernel, const std::vector<Op> op, const bool oriented, const bool with_vertex_valence,
+                    const bool is_concurrent, std::function<size_t(uint32_t, uint32_t, uint32_t)> user_shmem,
+                    cudaStream_t stream, ArgsT... args) const
+    {
+        LaunchBox<blockThreads> lb;
+        prepare_launch_box(op, lb, (void*)kernel, oriented, with_vertex_valence, is_concurrent, user_shmem);
+        run_kernel(lb, kernel, stream, args...);
     }
 
     // ---- for_each_vertex / edge / face (rxmesh_static.h:205-379) ----
@@ -217,8 +385,9 @@ class RXMeshStatic
                             std::function<size_t(uint32_t, uint32_t, uint32_t)> user_shmem =
                                 [](uint32_t, uint32_t, uint32_t) { return 0; }) const
     {
-        (void)oriented, (void)with_vertex_valence;
-        size_t   dyn = 0;
+        (void)oriented;
+        size_t   dyn = with_vertex_valence ? 4 * (size_t)get_per_patch_max_vertices() + 16 : 0;  // compute_vertex_valence
+        dyn += 4 * ((size_t)std::max(get_per_patch_max_edges(), get_per_patch_max_faces()) / 32 + 8);  // prologue mask
         uint32_t blocks = 0, threads = 0;
         for (Op o : op) {
             uint32_t b = 0;
@@ -240,11 +409,55 @@ class RXMeshStatic
    private:
     void init(const uint32_t* fv, uint32_t nf, const std::vector<uint32_t>& face_patch, uint32_t patch_size)
     {
+        m_fv.assign(fv, fv + 3 * (size_t)nf);  // kept for export_obj
         detail::rxm_check(rxm_mesh_create(fv, nf, face_patch.empty() ? nullptr : face_patch.data(), patch_size, 0, &m_mesh));
         detail::rxm_check(rxm_mesh_to_device(m_mesh));
         detail::rxm_check(rxm_mesh_view(m_mesh, &m_context.view, (uint32_t)sizeof(rxm::MeshView)));
     }
     uint32_t info(int k) const { return (uint32_t)rxm_mesh_info(m_mesh, k); }
+
+    template <typename AttrT, typename T>
+    std::shared_ptr<AttrT> add_filled(const T* flat_global, uint32_t n, const std::string& name, layoutT layout)
+    {
+        auto a = add<AttrT>(name, n, LOCATION_ALL, layout);
+        detail::rxm_check(rxm_attr_upload_global(a->c_handle(), flat_global, nullptr));
+        detail::rxm_check(cudaDeviceSynchronize() == cudaSuccess ? RXM_OK : RXM_ERR_CUDA);
+        return a;
+    }
+    static void read_obj(const std::string& path, std::vector<std::vector<float>>& verts, std::vector<std::vector<uint32_t>>& faces)
+    {
+        std::ifstream in(path);
+        if (!in) {
+            fprintf(stderr, "RXMeshStatic::RXMeshStatic could not read the input file %s\n", path.c_str());
+            exit(EXIT_FAILURE);
+        }
+        std::string line;
+        while (std::getline(in, line)) {
+            std::istringstream ss(line);
+            std::string        tag;
+            ss >> tag;
+            if (tag == "v") {
+                std::vector<float> p(3);
+                ss >> p[0] >> p[1] >> p[2];
+                verts.push_back(p);
+            } else if (tag == "f") {
+                std::vector<uint32_t> f;
+                std::string           tok;
+                while (ss >> tok) {
+                    const long i = std::stol(tok.substr(0, tok.find('/')));
+                    f.push_back(i > 0 ? (uint32_t)(i - 1) : (uint32_t)((long)verts.size() + i));
+                }
+                faces.push_back(f);
+            }
+        }
+    }
+    static std::vector<std::vector<uint32_t>> read_obj_faces(const std::string& path)
+    {
+        std::vector<std::vector<float>>    v;
+        std::vector<std::vector<uint32_t>> f;
+        read_obj(path, v, f);
+        return f;
+    }
 
     template <typename AttrT>
     std::shared_ptr<AttrT> add(const std::string& name, uint32_t n, locationT location, layoutT layout)
@@ -290,6 +503,8 @@ class RXMeshStatic
     }
 
     rxm_mesh*                                             m_mesh = nullptr;
+    std::vector<uint32_t>                                 m_fv;
+    std::shared_ptr<VertexAttribute<float>>               m_input_coords;
     Context                                               m_context;
     std::map<std::string, std::shared_ptr<AttributeBase>> m_attrs;
 };

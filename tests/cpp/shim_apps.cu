@@ -202,6 +202,47 @@ __global__ static void user_bilateral_filtering(const Context context, VertexAtt
     }
 }
 
+// ---- the split query API + valence + device for_each, in one user kernel:
+//   deg_split(v) = iterator size from prologue / get_iterator;  deg_val(v) = vertex_valence;  face_cnt(v) = #incident faces
+//   via run_compute on a second query;  touched(f) = 1 through for_each<Op::F>;  owner(v) = patch of get_owner_handle
+template <uint32_t blockThreads>
+__global__ static void user_split_api(const Context context, VertexAttribute<int> deg_split, VertexAttribute<int> deg_val,
+                                      VertexAttribute<int> face_cnt, FaceAttribute<int> touched, VertexAttribute<int> owner_ok)
+{
+    auto                block = cooperative_groups::this_thread_block();
+    Query<blockThreads> query(context);
+    ShmemAllocator      shrd_alloc;
+    query.compute_vertex_valence(block, shrd_alloc);
+    query.template prologue<Op::VV>(block, shrd_alloc);
+    const uint32_t nv_owned = query.get_patch_info().n_owned[0], nv = query.get_patch_info().n[0];
+    for (uint32_t v = threadIdx.x; v < nv; v += blockThreads) {
+        VertexHandle vh(query.get_patch_id(), LocalVertexT((uint16_t)v));
+        if (v < nv_owned) {
+            VertexIterator it = query.template get_iterator<VertexIterator>((uint16_t)v);
+            deg_split(vh)     = it.size();
+            deg_val(vh)       = query.vertex_valence(vh);
+        } else {
+            // a ribbon copy resolves to an owner handle that lives in another patch and is owned there
+            const VertexHandle oh = context.get_owner_handle(vh);
+            if (oh.patch_id() == vh.patch_id() || oh.local_id() >= context.view.desc[oh.patch_id()].n_owned[0])
+                owner_ok(VertexHandle(query.get_patch_id(), LocalVertexT(0))) = 0;
+        }
+    }
+    query.epilogue(block, shrd_alloc);
+    query.template prologue<Op::VF>(block, shrd_alloc, [](VertexHandle) { return true; }, false, false);
+    query.run_compute(block, [&](const VertexHandle& vh, const FaceIterator& it) { face_cnt(vh) = it.size(); });
+    query.epilogue(block, shrd_alloc);
+    for_each<Op::F, blockThreads>(context, [&](const FaceHandle fh) { touched(fh) = 1; });
+}
+
+// a kernel launched through run_kernel: out(v) = scale * valence(v)
+template <uint32_t blockThreads>
+__global__ static void user_scaled_valence(const Context context, VertexAttribute<float> out, float scale)
+{
+    auto lambda = [&](VertexHandle& vh, const VertexIterator& it) { out(vh) = scale * it.size(); };
+    query_block_dispatcher<Op::VV, blockThreads>(context, lambda);
+}
+
 template <uint32_t blockThreads, Op op, typename InH, typename OutH, typename InA, typename OutA>
 __global__ static void user_query_kernel(const Context context, InA input, OutA output, const bool oriented)
 {
@@ -402,6 +443,50 @@ static int app_time_vertex_normals(const uint32_t* fv, uint32_t nf, const float*
     return 0;
 }
 
+// host + device API surface that the apps above do not touch: OBJ constructor +
+// get_input_vertex_coordinates, add_*_attribute_like, vector<T> attribute constructors, run_kernel (two overloads),
+// Query::prologue / get_iterator / run_compute / epilogue, compute_vertex_valence, device for_each<Op::F>,
+// Context::get_owner_handle (device) and RXMeshStatic::get_owner_handle (host), get_boundary_vertices, export_obj.
+// out[0..nv) = valence from the split API, [nv..2nv) = vertex_valence, [2nv..3nv) = #incident faces,
+// [3nv..4nv) = 3 * valence through run_kernel, [4nv..5nv) = boundary flag; returns a bit mask of failed host checks
+static int app_api_surface(const char* obj_path, const char* export_path, uint32_t patch_size, float* out)
+{
+    rx_init(0);
+    RXMeshStatic rx(std::string(obj_path), "", patch_size);
+    constexpr uint32_t blockThreads = 256;
+    const uint32_t nv = rx.get_num_vertices(), nf = rx.get_num_faces();
+    int bad = 0;
+    auto coords = rx.get_input_vertex_coordinates();
+    auto a      = rx.add_vertex_attribute<int>("deg_split", 1, LOCATION_ALL);
+    auto b      = rx.add_vertex_attribute_like<int>("deg_val", *a);
+    auto c      = rx.add_vertex_attribute_like<int>("face_cnt", *a);
+    auto ok     = rx.add_vertex_attribute_like<int>("owner_ok", *a);
+    auto t      = rx.add_face_attribute<int>(std::vector<int>(nf, 0), "touched");
+    auto sv     = rx.add_vertex_attribute<float>("scaled", 1, LOCATION_ALL);
+    auto bd     = rx.add_vertex_attribute<int>("boundary", 1, LOCATION_ALL);
+    if (b->get_num_attributes() != 1 || b->get_layout() != a->get_layout() || !rx.does_attribute_exist("face_cnt")) bad |= 1;
+    a->reset(-1, DEVICE), b->reset(-1, DEVICE), c->reset(-1, DEVICE), ok->reset(1, DEVICE), sv->reset(0.f, DEVICE);
+    LaunchBox<blockThreads> lb;
+    rx.prepare_launch_box({Op::VV, Op::VF}, lb, (void*)user_split_api<blockThreads>, false, true);
+    rx.run_kernel(lb, user_split_api<blockThreads>, *a, *b, *c, *t, *ok);
+    rx.run_kernel<blockThreads>({Op::VV}, user_scaled_valence<blockThreads>, *sv, 3.0f);
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    rx.get_boundary_vertices(*bd);
+    a->move(DEVICE, HOST), b->move(DEVICE, HOST), c->move(DEVICE, HOST), t->move(DEVICE, HOST), ok->move(DEVICE, HOST);
+    sv->move(DEVICE, HOST);
+    rx.for_each_vertex(HOST, [&](const VertexHandle& vh) {
+        const uint32_t g = rx.map_to_global(vh);
+        out[g] = (float)(*a)(vh), out[nv + g] = (float)(*b)(vh), out[2 * nv + g] = (float)(*c)(vh);
+        out[3 * nv + g] = (*sv)(vh), out[4 * nv + g] = (float)(*bd)(vh);
+        if ((*ok)(vh) != 1) bad |= 2;
+        if (!(rx.get_owner_handle(vh) == vh)) bad |= 4;  // an owned handle is its own owner
+    }, NULL, false);
+    rx.for_each_face(HOST, [&](const FaceHandle& fh) { if ((*t)(fh) != 1) bad |= 8; }, NULL, false);
+    rx.export_obj(export_path, *coords);
+    if (rx.get_attribute_names().size() < 8) bad |= 16;
+    return bad;
+}
+
 // the Filtering driver loop (apps/Filtering/filtering_rxmesh.cuh:60-100)
 static int app_filtering(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, int num_iter,
                          float* out)
@@ -501,6 +586,10 @@ int shim_time_vertex_normals(const uint32_t* fv, uint32_t nf, const float* x, ui
                              uint32_t patch_size, int nrun, float* ms_out)
 {
     return app_time_vertex_normals(fv, nf, x, nv, face_patch, patch_size, nrun, ms_out);
+}
+int shim_api_surface(const char* obj_path, const char* export_path, uint32_t patch_size, float* out)
+{
+    return app_api_surface(obj_path, export_path, patch_size, out);
 }
 int shim_filtering(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, int num_iter, float* out)
 {

@@ -163,3 +163,34 @@ def test_user_filtering_app(shim, name):
     m.bilateral_filter(x, y, iters)
     fixed = y.to_global()
     assert np.mean(np.abs(out - fixed).max(axis=1) < 2e-5 * scale * iters) > 0.995
+
+
+@pytest.mark.parametrize("name", ["bunnyhead", "dragon"])
+def test_user_api_surface(shim, name, tmp_path):
+    """OBJ constructor / get_input_vertex_coordinates, add_*_attribute_like, vector<T> attribute constructors, run_kernel,
+    Query::prologue / get_iterator / run_compute / epilogue, compute_vertex_valence, device for_each<Op::F>, device and
+    host get_owner_handle, get_boundary_vertices, export_obj -- the rest of the reference's API on this path
+    (SURVEY.md 8b), in one user program."""
+    from rxmesh_b200 import meshio
+    V, F = make_mesh(name)
+    src, dst = str(tmp_path / "in.obj"), str(tmp_path / "out.obj")
+    with open(src, "w") as fh:
+        for v in V:
+            fh.write("v %.9g %.9g %.9g\n" % tuple(v))
+        for f in F:
+            fh.write("f %d %d %d\n" % tuple(f + 1))
+    T = O.Topology(F)
+    out = np.zeros(5 * T.nv, np.float32)
+    rc = shim.shim_api_surface(src.encode(), dst.encode(), 512, _p(out))
+    assert rc == 0, "failed host checks, bit mask %d" % rc
+    out = out.reshape(5, T.nv)
+    val = np.diff(T.query("VV")[0].astype(np.int64))
+    assert np.array_equal(out[0], val) and np.array_equal(out[1], val)      # split API, vertex_valence
+    assert np.array_equal(out[2], np.diff(T.query("VF")[0].astype(np.int64)))  # run_compute on VF
+    assert np.array_equal(out[3], 3.0 * val)                                 # run_kernel
+    assert np.array_equal(out[4].astype(bool), T.boundary_vertices()[1])      # get_boundary_vertices
+    V2, F2 = meshio.import_obj(dst)                                          # export_obj: same surface, patch-ordered ids
+    assert V2.shape == V.shape and F2.shape == F.shape
+    area = lambda X, G: np.linalg.norm(np.cross(X[G[:, 1]] - X[G[:, 0]], X[G[:, 2]] - X[G[:, 0]]), axis=1)
+    assert np.allclose(np.sort(area(V2.astype(np.float64), F2)), np.sort(area(V.astype(np.float64), F)), rtol=1e-5, atol=1e-12)
+    assert np.allclose(np.sort(V2, axis=0), np.sort(V, axis=0))
