@@ -305,10 +305,14 @@ def run_ours(args, rank, world, local_rank):
         nE_real = int(lbe[b] - lbe[a])
         halo_bytes = 12 * hx_v.halo_elements()
     t_build = time.perf_counter() - t0
-    mesh.compact()  # the 100 M-face mesh lives on the device; drop host helper arrays (halo plans are built)
     stream = torch.cuda.current_stream()
     x = rx.Attribute(mesh, 0, np.float32, 3, rx.DEVICE, rx.AoS)
     nrm = rx.Attribute(mesh, 0, np.float32, 3, rx.DEVICE, rx.AoS)
+    fused = None
+    if hx_v is not None and args.workload == "laplacian" and not os.environ.get("RXM_NO_FUSED"):
+        from rxmesh_b200 import distributed as D
+        fused = D.FusedHalo(hx_v, x, nrm)  # needs the host patch store: before compact()
+    mesh.compact()  # the 100 M-face mesh lives on the device; drop host helper arrays (halo plans are built)
     sv_in = rx.Attribute(mesh, 0, np.float32, 1, rx.DEVICE, rx.AoS)
     sv_out = rx.Attribute(mesh, 0, np.float32, 1, rx.DEVICE, rx.AoS)
     sf_in = rx.Attribute(mesh, 2, np.float32, 1, rx.DEVICE, rx.AoS)
@@ -328,7 +332,7 @@ def run_ours(args, rank, world, local_rank):
 
     if args.workload == "laplacian":
         return run_laplacian(args, rank, world, local_rank, mesh, x, nrm, hx_v, nV if world == 1 else None,
-                             n, t_build, torch, rx, stream)
+                             n, t_build, torch, rx, stream, fused)
 
     comm = torch.cuda.Stream() if hx_v is not None else None
 
@@ -475,7 +479,7 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
-def run_laplacian(args, rank, world, local_rank, mesh, x, y, hx_v, nv_single, n, t_build, torch, rx, stream):
+def run_laplacian(args, rank, world, local_rank, mesh, x, y, hx_v, nv_single, n, t_build, torch, rx, stream, fused=None):
     """BASELINE.json configs[4]: iterated Laplacian smoothing (apps/Smoothing/manual.h:86-104), patches
     sharded across the ranks, ribbon exchange after every iteration inside the timed region."""
     lbv = mesh.lin_base(0)
@@ -486,7 +490,13 @@ def run_laplacian(args, rank, world, local_rank, mesh, x, y, hx_v, nv_single, n,
     # Exchange after every iteration on the compute stream.  Splitting the step into boundary patches -> exchange on a
     # second stream -> interior patches was measured at N = 2 (0.266 vs 0.262 ms per iteration): the 60 KB transfer is
     # already cheap, the extra launches cost more than the overlap returns, so the simple order stays.
+    # Default at N > 1: ONE kernel per iteration that also pushes the mirrored rows into the neighbours' ghost slots over
+    # NVLink and synchronises with them through flag words (rxmesh_b200/distributed.py: FusedHalo).  RXM_NO_FUSED=1:
+    # kernel, then packed NCCL send/recv.
     def iterate(k):
+        if fused is not None:
+            fused.smooth(0.01, k, stream)
+            return
         a, b = x, y
         for _ in range(k):
             mesh.laplacian_smooth(a, b, 0.01, 1, stream)
@@ -531,6 +541,8 @@ def run_laplacian(args, rank, world, local_rank, mesh, x, y, hx_v, nv_single, n,
                      "peak": peak, "unit": "GB/s", "frac": 24.0 * nF / world / (per_it * 1e-3) / 1e9 / peak,
                      "peak_source": peak_src, "note": "per GPU, includes the halo exchange time"},
         "halo_bytes_per_iteration_per_gpu": 0 if hx_v is None else 12 * hx_v.halo_elements(),
+        "halo_transport": None if hx_v is None else ("fused into the compute kernel: NVLink P2P stores + flag words" if fused is not None
+                                                      else "packed NCCL send/recv after the kernel"),
         "gpu_launches": int(rx.launch_count() - l0), "build_seconds": t_build}), flush=True)
 
 

@@ -198,6 +198,18 @@ int rxm_attr_scatter_slots(rxm_attr* a, const uint32_t* dev_idx, uint64_t n, con
  * pointer (rxm_ipc_open) to the neighbour rank's attribute storage */
 int rxm_attr_push_slots(rxm_attr* a, const uint32_t* dev_local_idx, void* remote_data, const uint32_t* dev_remote_idx,
                         uint64_t n, void* stream);
+/* Laplacian step fused with the halo exchange (new: the reference is single-GPU): the kernel stores the rows mirrored
+ * on neighbouring ranks into their ghost slots over NVLink P2P and raises a flag there; patches that read ghost slots
+ * wait for the neighbours' flags.  Setup: create (allocates the flag words), export / exchange rxm_fused_halo_flags and
+ * both attributes over cudaIpc, then set.  See rxmesh_b200/distributed.py: FusedHalo. */
+typedef struct rxm_fused_halo rxm_fused_halo;
+int   rxm_fused_halo_create(rxm_mesh* m, uint32_t npeers, rxm_fused_halo** out);
+void* rxm_fused_halo_flags(rxm_fused_halo* h);
+int   rxm_fused_halo_set(rxm_fused_halo* h, const uint32_t* push_off, const uint32_t* push_lid_peer, const uint32_t* push_slot,
+                         uint64_t n_push, void* const* peer_attr_a, void* const* peer_attr_b, void* const* peer_flag);
+void  rxm_fused_halo_destroy(rxm_fused_halo* h);
+int   rxm_laplacian_smooth_fused(rxm_mesh* m, rxm_attr* in, rxm_attr* out, double lr, rxm_fused_halo* h, int out_is_b,
+                                 uint32_t step, void* stream);
 int rxm_ipc_export(void* dev_ptr, void* handle64);        /* cudaIpcGetMemHandle */
 int rxm_ipc_open(const void* handle64, void** dev_ptr);   /* cudaIpcOpenMemHandle */
 int rxm_ipc_close(void* dev_ptr);

@@ -82,6 +82,13 @@ SYMBOLS = {
     "rxm_attr_gather_slots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "rxm_attr_scatter_slots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "rxm_attr_push_slots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "rxm_fused_halo_create": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "rxm_fused_halo_flags": (C.c_void_p, [C.c_void_p]),
+    "rxm_fused_halo_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
+    "rxm_fused_halo_destroy": (None, [C.c_void_p]),
+    "rxm_laplacian_smooth_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int,
+                                             C.c_uint32, C.c_void_p]),
     "rxm_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rxm_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "rxm_ipc_close": (C.c_int, [C.c_void_p]),

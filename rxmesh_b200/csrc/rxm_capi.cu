@@ -1123,6 +1123,118 @@ int rxm_attr_push_slots(rxm_attr* a, const uint32_t* dev_local_idx, void* remote
     return e == cudaSuccess ? RXM_OK : fail(RXM_ERR_CUDA, cudaGetErrorString(e));
 }
 
+// ---- compute + halo exchange in one kernel (FusedHaloView, rxm_kernels.h) ----
+struct rxm_fused_halo
+{
+    rxm_mesh* m        = nullptr;
+    uint32_t  npeers   = 0, n_push_blocks = 0, shift = 0;
+    uint32_t *d_flags = nullptr, *d_ctr = nullptr, *d_push_off = nullptr;
+    uint2*    d_push  = nullptr;
+    uint8_t*  d_reads = nullptr;
+    float**   d_peer_attr[2] = {nullptr, nullptr};  // neighbour-side base of attribute A / attribute B
+    uint32_t** d_peer_flag   = nullptr;
+};
+
+int rxm_fused_halo_create(rxm_mesh* m, uint32_t npeers, rxm_fused_halo** out)
+{
+    int rc = check_dev(m, "rxm_fused_halo_create");
+    if (rc) return rc;
+    if (!out || npeers == 0 || npeers > 64) return fail(RXM_ERR_INVALID, "rxm_fused_halo_create: bad argument");
+    if (m->h.topo.empty()) return fail(RXM_ERR_INVALID, "rxm_fused_halo_create: host patch store was released (rxm_mesh_compact)");
+    rxm_fused_halo* h = new rxm_fused_halo();
+    h->m = m, h->npeers = npeers;
+    CU(cudaMalloc(&h->d_flags, 4 * npeers));
+    CU(cudaMemset(h->d_flags, 0, 4 * npeers));
+    CU(cudaMalloc(&h->d_ctr, 4));
+    CU(cudaMemset(h->d_ctr, 0, 4));
+    // patches that read ghost slots: a stash entry names a patch outside the active (real) range
+    const HostMesh&      H = m->h;
+    const uint32_t       a0 = m->active_count ? m->active_first : 0, a1 = m->active_count ? a0 + m->active_count : H.num_patches;
+    std::vector<uint8_t> reads(H.num_patches, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t p = 0; p < (int64_t)H.num_patches; ++p) {
+        const PatchDesc&  D  = H.desc[p];
+        const StashEntry* st = reinterpret_cast<const StashEntry*>(H.topo.data() + D.topo_off + D.off_stash());
+        for (uint32_t i = 0; i < D.n_stash; ++i)
+            if (st[i].patch < a0 || st[i].patch >= a1) reads[p] = 1;
+    }
+    CU(cudaMalloc(&h->d_reads, std::max<size_t>(reads.size(), 1)));
+    CU(cudaMemcpy(h->d_reads, reads.data(), reads.size(), cudaMemcpyHostToDevice));
+    *out = h;
+    return RXM_OK;
+}
+
+void* rxm_fused_halo_flags(rxm_fused_halo* h)
+{
+    return h ? h->d_flags : nullptr;
+}
+
+// push lists: for patch index p the entries [push_off[p], push_off[p+1]) of (local vertex id | neighbour << 16) and the
+// slot on that neighbour; peer_attr_a / _b: neighbour-side base pointers (rxm_ipc_open) of the two attributes the
+// iteration ping-pongs between; peer_flag: neighbour-side address of the flag word this rank raises
+int rxm_fused_halo_set(rxm_fused_halo* h, const uint32_t* push_off, const uint32_t* push_lid_peer, const uint32_t* push_slot,
+                       uint64_t n_push, void* const* peer_attr_a, void* const* peer_attr_b, void* const* peer_flag)
+{
+    if (!h || !push_off || !peer_attr_a || !peer_attr_b || !peer_flag) return fail(RXM_ERR_INVALID, "rxm_fused_halo_set: null argument");
+    const uint32_t P = h->m->h.num_patches;
+    if (push_off[P] != n_push) return fail(RXM_ERR_INVALID, "rxm_fused_halo_set: push_off does not end at n_push");
+    h->n_push_blocks = 0;
+    for (uint32_t p = 0; p < P; ++p)
+        h->n_push_blocks += push_off[p + 1] > push_off[p] ? 1u : 0u;
+    {   // rotation: start the launch at the first pushing patch of the upper half of the active range
+        const uint32_t a0 = h->m->active_count ? h->m->active_first : 0, cnt = h->m->active_count ? h->m->active_count : P;
+        h->shift = 0;
+        for (uint32_t r = cnt / 2; r < cnt; ++r)
+            if (push_off[a0 + r + 1] > push_off[a0 + r]) {
+                h->shift = r;
+                break;
+            }
+    }
+    if (h->n_push_blocks == 0) return fail(RXM_ERR_INVALID, "rxm_fused_halo_set: nothing to push (no neighbour shares an element)");
+    std::vector<uint2> e(std::max<uint64_t>(n_push, 1));
+    for (uint64_t i = 0; i < n_push; ++i)
+        e[i] = make_uint2(push_lid_peer[i], push_slot[i]);
+    CU(cudaMalloc(&h->d_push_off, 4 * (size_t)(P + 1)));
+    CU(cudaMemcpy(h->d_push_off, push_off, 4 * (size_t)(P + 1), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&h->d_push, sizeof(uint2) * e.size()));
+    CU(cudaMemcpy(h->d_push, e.data(), sizeof(uint2) * e.size(), cudaMemcpyHostToDevice));
+    const void* const* src[3] = {peer_attr_a, peer_attr_b, peer_flag};
+    void**             dst[3] = {(void**)&h->d_peer_attr[0], (void**)&h->d_peer_attr[1], (void**)&h->d_peer_flag};
+    for (int k = 0; k < 3; ++k) {
+        CU(cudaMalloc(dst[k], sizeof(void*) * h->npeers));
+        CU(cudaMemcpy(*dst[k], src[k], sizeof(void*) * h->npeers, cudaMemcpyHostToDevice));
+    }
+    return RXM_OK;
+}
+
+void rxm_fused_halo_destroy(rxm_fused_halo* h)
+{
+    if (!h) return;
+    cudaFree(h->d_flags), cudaFree(h->d_ctr), cudaFree(h->d_push_off), cudaFree(h->d_push), cudaFree(h->d_reads);
+    cudaFree(h->d_peer_attr[0]), cudaFree(h->d_peer_attr[1]), cudaFree(h->d_peer_flag);
+    delete h;
+}
+
+// one Laplacian step in -> out with the halo push fused in; out_is_b selects which neighbour-side attribute `out` is;
+// step = number of fused steps every rank has issued before this one (monotonic)
+int rxm_laplacian_smooth_fused(rxm_mesh* m, rxm_attr* in, rxm_attr* out, double lr, rxm_fused_halo* h, int out_is_b,
+                               uint32_t step, void* stream)
+{
+    int rc = check_dev(m, "rxm_laplacian_smooth_fused");
+    if (rc) return rc;
+    if (!h || !h->d_push_off || !is_vec3_aos(in) || !is_vec3_aos(out) || in == out)
+        return fail(RXM_ERR_INVALID, "rxm_laplacian_smooth_fused: bad argument");
+    FusedHaloView v;
+    v.push_off = h->d_push_off, v.push = h->d_push, v.peer_out = h->d_peer_attr[out_is_b ? 1 : 0];
+    v.peer_flag = h->d_peer_flag, v.reads_ghost = h->d_reads, v.flags = h->d_flags, v.done_ctr = h->d_ctr;
+    v.npeers = h->npeers, v.first = m->active_count ? m->active_first : 0, v.step = step;
+    v.n_push_blocks = h->n_push_blocks, v.shift = h->shift;
+    const char* why = nullptr;
+    cudaError_t e   = launch_laplacian_step_fused(m->view, m->lim, (const float*)in->d, (float*)out->d, lr, v,
+                                                  (cudaStream_t)stream, &why);
+    return kernel_status(e, why, "rxm_laplacian_smooth_fused");
+}
+
 int rxm_ipc_export(void* dev_ptr, void* handle64)
 {
     cudaIpcMemHandle_t h;

@@ -676,12 +676,36 @@ __device__ __forceinline__ void lap_one(const FanPatch2& F, uint32_t v, double l
     lap_finish(X, Y, Z, gx, gy, gz, lr, F.s_out + 3 * v);
 }
 
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <bool FUSED>
 __global__ void __launch_bounds__(BT2, 8) k_laplacian_fan2(MeshView mv, const float* __restrict__ x, float* __restrict__ xo,
-                                                         double lr)
+                                                         double lr, FusedHaloView fh)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t                      bar;
-    const PatchDesc d = load_desc(mv.desc + blockIdx.x);
+    // fused: blocks are rotated so that the patches with rows to push (the two ends of the rank's patch range) run
+    // first and the neighbours' flags are raised early in the launch, not at its end
+    const uint32_t  bidx = FUSED ? (blockIdx.x + fh.shift) % gridDim.x : blockIdx.x;
+    const PatchDesc d    = load_desc(mv.desc + bidx);
+    if (FUSED) {
+        // ghost slots hold what the neighbours pushed at the end of THEIR previous step: wait for their flags
+        const uint32_t lp0 = fh.first + bidx;
+        if (fh.reads_ghost[lp0] || fh.push_off[lp0 + 1] > fh.push_off[lp0]) {
+            if (threadIdx.x < fh.npeers)
+                while (ld_acquire_sys(fh.flags + threadIdx.x) < fh.step) {}
+            __syncthreads();
+        }
+    }
     const FanPatch2 F = fan_load2(mv, d, x, smem_raw, &bar);
     for (uint32_t vA = threadIdx.x; vA < F.cap; vA += 2 * BT2) {
         const uint32_t vB = vA + BT2;
@@ -731,6 +755,29 @@ __global__ void __launch_bounds__(BT2, 8) k_laplacian_fan2(MeshView mv, const fl
         bulk_s2g(xo + 3ull * d.slot_base[ELEM_V], F.s_out, 12u * F.cap);
         bulk_commit();
         bulk_wait_all_read();
+    }
+    if (FUSED) {
+        // rows mirrored on other GPUs go straight into the neighbours' ghost slots (NVLink P2P stores); only the few
+        // blocks that have such rows pay for the system-scope fence, and the last of THEM tells every neighbour that
+        // this step's rows are all there
+        const uint32_t lp = fh.first + bidx;
+        const uint32_t pb = fh.push_off[lp], pe = fh.push_off[lp + 1];
+        if (pe > pb) {
+            for (uint32_t i = pb + threadIdx.x; i < pe; i += BT2) {
+                const uint2  e   = fh.push[i];
+                const float* src = F.s_out + 3u * (e.x & 0xFFFFu);
+                float*       dst = fh.peer_out[e.x >> 16] + 3ull * e.y;
+                dst[0] = src[0], dst[1] = src[1], dst[2] = src[2];
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0 && atomicAdd(fh.done_ctr, 1u) == fh.n_push_blocks - 1) {
+                *fh.done_ctr = 0;
+                __threadfence_system();
+                for (uint32_t q = 0; q < fh.npeers; ++q)
+                    st_release_sys(fh.peer_flag[q], fh.step + 1);
+            }
+        }
     }
 }
 
@@ -1655,8 +1702,8 @@ cudaError_t launch_laplacian_step(const MeshView& mv, const KernelLimits& lim, c
     }
     if (mv.fans && !getenv("RXM_VN_SCALAR")) {
         const uint32_t smem = fan_smem(lim) + r16(12u * std::max(lim.max_n[ELEM_V], capv)) + r16(12u * capv) + 64u;
-        if (set_smem(k_laplacian_fan2, smem) != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
-        k_laplacian_fan2<<<mv.num_patches, BT2, smem, stream>>>(mv, x, xo, lr);
+        if (set_smem(k_laplacian_fan2<false>, smem) != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
+        k_laplacian_fan2<false><<<mv.num_patches, BT2, smem, stream>>>(mv, x, xo, lr, FusedHaloView{});
         ++g_launches;
         return cudaGetLastError();
     }
@@ -1688,6 +1735,19 @@ cudaError_t launch_laplacian_step(const MeshView& mv, const KernelLimits& lim, c
         if (e != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
         k_laplacian<24, false><<<mv.num_patches, BT, smem, stream>>>(mv, x, xo, lr);
     }
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_laplacian_step_fused(const MeshView& mv, const KernelLimits& lim, const float* x, float* xo, double lr,
+                                        const FusedHaloView& fh, cudaStream_t stream, const char** err)
+{
+    if (!mv.fans) RXM_FAIL("the fused Laplacian + halo kernel needs the one-ring fans (manifold, consistently oriented input)");
+    if (fh.npeers > BT2) RXM_FAIL("too many neighbour ranks");
+    const uint32_t capv = lim.max_owned[ELEM_V] + 4;
+    const uint32_t smem = fan_smem(lim) + r16(12u * std::max(lim.max_n[ELEM_V], capv)) + r16(12u * capv) + 64u;
+    if (set_smem(k_laplacian_fan2<true>, smem) != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
+    k_laplacian_fan2<true><<<mv.num_patches, BT2, smem, stream>>>(mv, x, xo, lr, fh);
     ++g_launches;
     return cudaGetLastError();
 }

@@ -28,6 +28,26 @@ cudaError_t launch_vertex_normals(const MeshView& mv, const KernelLimits& lim, c
                                   float* normals_aos, int unit_face_normals, cudaStream_t stream,
                                   const char** err);
 
+// Laplacian step fused with the ribbon (halo) exchange of a patch-sharded mesh: the kernel that produces the new
+// positions also stores the rows mirrored on neighbouring GPUs straight into their ghost slots (NVLink P2P stores
+// through cudaIpc-mapped pointers) and, when its last block is done, raises a flag on every neighbour; blocks whose
+// patch reads ghost slots wait for the neighbours' flags of the previous step.  No NCCL call, no host synchronisation.
+struct FusedHaloView
+{
+    const uint32_t*  push_off;     // [P + 1] over the mesh's patch slots (index = patch index in the descriptor array)
+    const uint2*     push;         // {local vertex id | neighbour index << 16, slot on the neighbour}
+    float* const*    peer_out;     // [npeers] base of the OUT attribute in each neighbour's memory
+    uint32_t* const* peer_flag;    // [npeers] address, in the neighbour's memory, of its flags[me]
+    const uint8_t*   reads_ghost;  // [P] the patch has ribbon elements owned by a ghost patch
+    uint32_t*        flags;        // [npeers] raised by the neighbours (step count they have finished)
+    uint32_t*        done_ctr;     // blocks of this launch that have pushed their rows
+    uint32_t         npeers, first, step;
+    uint32_t         shift;          // block b works on patch (b + shift) % #patches
+    uint32_t         n_push_blocks;  // patches of the active range with at least one row to push
+};
+cudaError_t launch_laplacian_step_fused(const MeshView& mv, const KernelLimits& lim, const float* x_in_aos, float* x_out_aos,
+                                        double lr, const FusedHaloView& fh, cudaStream_t stream, const char** err);
+
 cudaError_t launch_laplacian_step(const MeshView& mv, const KernelLimits& lim, const float* x_in_aos,
                                   float* x_out_aos, double lr, cudaStream_t stream, const char** err);
 

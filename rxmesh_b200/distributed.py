@@ -241,3 +241,92 @@ class HaloExchange:
         if barrier:
             torch.cuda.current_stream().synchronize()
             self.dist.barrier(group=self.group)
+
+
+class FusedHalo:
+    """Laplacian smoothing with the ribbon exchange fused into the compute kernel (rxm_laplacian_smooth_fused).
+
+    Every step is ONE kernel per rank: it computes the new positions, stores the rows that are mirrored on neighbouring
+    ranks straight into their ghost slots over NVLink (P2P stores through cudaIpc-mapped pointers), and its last block
+    raises a flag word on every neighbour; blocks whose patch reads ghost slots wait on the flags the neighbours raised
+    at the end of their previous step.  No NCCL call and no host synchronisation inside the iteration.  The two vertex
+    attributes the iteration ping-pongs between must have been created in the same order on every rank.
+    `plan(hx)` (host only, no GPU needed) is what the gloo tests check."""
+
+    @staticmethod
+    def plan(hx):
+        """push lists from a vertex HaloExchange: per local patch the (local vertex id, neighbour index) pairs this rank
+        sends, in the neighbours' request order; -> (peers, push_off[P+1], patch, lid, peer_index, position in request)"""
+        m = hx.sm.mesh
+        sb = m.slot_base(0).astype(np.int64)
+        peers = sorted(hx.send)
+        pat, lid, pidx, pos = [], [], [], []
+        for k, p in enumerate(peers):
+            slots = hx.send[p].astype(np.int64)
+            pp = np.searchsorted(sb, slots, side="right") - 1
+            pat.append(pp), lid.append(slots - sb[pp]), pidx.append(np.full(len(slots), k)), pos.append(np.arange(len(slots)))
+        pat, lid, pidx, pos = (np.concatenate(a) if a else np.zeros(0, np.int64) for a in (pat, lid, pidx, pos))
+        order = np.argsort(pat, kind="stable")
+        pat, lid, pidx, pos = pat[order], lid[order], pidx[order], pos[order]
+        off = np.zeros(m.get_num_patches() + 1, dtype=np.uint32)
+        np.add.at(off, pat + 1, 1)
+        return peers, np.cumsum(off, dtype=np.uint32), pat, lid, pidx, pos
+
+    def __init__(self, hx, attr_a, attr_b):
+        import torch  # noqa: F401
+        assert hx.elem == 0
+        self.hx, self.mesh, self.a, self.b, self.step = hx, hx.sm.mesh, attr_a, attr_b, 0
+        dist, sm = hx.dist, hx.sm
+        peers, off, pat, lid, pidx, pos = self.plan(hx)
+        assert set(peers) == set(hx.recv), "halo neighbourhoods must be symmetric"
+        self.peers = peers
+        h = C.c_void_p()
+        check(lib().rxm_fused_halo_create(self.mesh._h, len(peers), C.byref(h)))
+        self._h = h
+
+        def export(ptr):
+            buf = (C.c_uint8 * 64)()
+            check(lib().rxm_ipc_export(C.c_void_p(ptr), buf))
+            return bytes(buf)
+
+        infos = [None] * sm.world
+        dist.all_gather_object(infos, dict(a=export(attr_a.data_ptr(DEVICE)), b=export(attr_b.data_ptr(DEVICE)),
+                                           flags=export(lib().rxm_fused_halo_flags(h)), peers=peers,
+                                           recv={p: v for p, v in hx.recv.items()}), group=hx.group)
+
+        def open_(raw):
+            ptr = C.c_void_p()
+            check(lib().rxm_ipc_open((C.c_uint8 * 64).from_buffer_copy(raw), C.byref(ptr)))
+            return ptr.value
+
+        pa = (C.c_void_p * len(peers))(*[open_(infos[p]["a"]) for p in peers])
+        pb = (C.c_void_p * len(peers))(*[open_(infos[p]["b"]) for p in peers])
+        # my flag word on neighbour p = its flags[index of me among ITS neighbours]
+        pf = (C.c_void_p * len(peers))(*[open_(infos[p]["flags"]) + 4 * infos[p]["peers"].index(sm.rank) for p in peers])
+        # slot on the neighbour of every row I push = its ghost slots in the order it requested them
+        slot = np.empty(len(pat), dtype=np.uint32)
+        for k, p in enumerate(peers):
+            sel = pidx == k
+            slot[sel] = np.asarray(infos[p]["recv"][sm.rank], dtype=np.uint32)[pos[sel]]
+        lp = (lid.astype(np.uint32) | (pidx.astype(np.uint32) << np.uint32(16))).astype(np.uint32)
+        check(lib().rxm_fused_halo_set(h, off.ctypes.data_as(C.c_void_p), lp.ctypes.data_as(C.c_void_p),
+                                       slot.ctypes.data_as(C.c_void_p), len(lp), pa, pb, pf))
+        self._keep = (pa, pb, pf)
+        dist.barrier(group=hx.group)
+
+    def smooth(self, lr, iters, stream=None):
+        """iters fused steps starting from attribute A if an even number of steps has been run, else B; returns the
+        attribute that holds the result.  Ghost slots of the starting attribute must be current (HaloExchange.exchange
+        before the first call)."""
+        src, dst = (self.a, self.b) if self.step % 2 == 0 else (self.b, self.a)
+        for _ in range(iters):
+            check(lib().rxm_laplacian_smooth_fused(self.mesh._h, src._h, dst._h, float(lr), self._h,
+                                                   int(dst is self.b), self.step, _stream_ptr(stream)))
+            self.step += 1
+            src, dst = dst, src
+        return src
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().rxm_fused_halo_destroy(self._h)
+            self._h = None

@@ -78,6 +78,18 @@ def _host_worker(rank, world, port, kind, q):
             need = sm.halo_slots(elem)
             assert need.shape[0] == hx.halo_elements() > 0
             assert np.array_equal(h[need], f(gid[need])), "ghost slots must hold the owners' values"
+            if elem == 0:
+                # push lists of the fused compute + exchange kernel (FusedHalo.plan): every row this rank sends appears
+                # once, under the patch that owns it, and (patch, local id) names exactly the slot in the send list
+                peers, off, pat, lid, pidx, pos = D.FusedHalo.plan(hx)
+                assert off[-1] == sum(len(v) for v in hx.send.values()) == len(pat)
+                sbv = m.slot_base(0).astype(np.int64)
+                for k, p in enumerate(peers):
+                    sel = pidx == k
+                    assert np.array_equal(np.sort(sbv[pat[sel]] + lid[sel]), np.sort(hx.send[p].astype(np.int64)))
+                    assert np.array_equal((sbv[pat[sel]] + lid[sel]), hx.send[p].astype(np.int64)[pos[sel]])
+                assert np.all(pat >= sm.first) and np.all(pat < sm.first + sm.count)
+                assert np.all(np.diff(pat) >= 0) and np.array_equal(np.bincount(pat, minlength=m.get_num_patches()), np.diff(off))
         # 3. every element referenced by a real patch now has a value (owned by real or filled halo)
         dist.barrier()
         q.put((rank, "ok", sm.count, int(hx.halo_elements())))
@@ -171,6 +183,20 @@ def _gpu_worker(rank, world, port, q):
             got = a.to_global()
             err = np.abs(got[real] - ref[gids[real]]).max()
             assert err < 1e-5 * np.abs(Vg).max() * iters, (mode, err)
+            if mode == "nccl":
+                got_nccl = got.copy()
+        # compute + exchange in ONE kernel (P2P stores + flag words): bit-identical to kernel -> NCCL exchange, also
+        # across two calls (the step counter and the ping-pong parity carry over)
+        x.from_global(sh["verts"])
+        y.from_global(sh["verts"])
+        hx.exchange(x)
+        fh = D.FusedHalo(hx, x, y)
+        res = fh.smooth(lr, 2)
+        res = fh.smooth(lr, iters - 2)
+        torch.cuda.synchronize()
+        dist.barrier()
+        got = res.to_global()
+        assert np.array_equal(got[real], got_nccl[real]), np.abs(got[real] - got_nccl[real]).max()
         # vertex normals after an exchange of the coordinates
         x.from_global(sh["verts"])
         hx.exchange(x)
