@@ -55,6 +55,7 @@ __device__ __inline__ void higher_query_block_dispatcher(const Context& context,
     const uint32_t      mine  = valid ? src_id.patch_id() : INVALID32;
     bool                served = !valid;
     ShmemAllocator      shrd_alloc;
+    int                 round = 0;
     while (true) {
         if (threadIdx.x == 0) s_next_patch = INVALID32;
         __syncthreads();
@@ -64,8 +65,9 @@ __device__ __inline__ void higher_query_block_dispatcher(const Context& context,
         __syncthreads();  // everyone has read s_next_patch before the next round resets it
         if (p == INVALID32) break;
         Query<blockThreads> query(context, p);
-        query.template dispatch_src<op>(shrd_alloc, !served && mine == p, src_id, compute_op, oriented);
+        query.template dispatch_src<op>(shrd_alloc, !served && mine == p, src_id, compute_op, oriented, round++);
         if (mine == p) served = true;
     }
+    if (round) Query<blockThreads>::end_rounds();
 }
 }  // namespace rxmesh

@@ -10,6 +10,12 @@
 
 namespace rxmesh {
 namespace detail {
+// the one mbarrier every query of a kernel loads through (a function-scope __shared__ object: one per kernel)
+__device__ __forceinline__ uint64_t* query_barrier()
+{
+    __shared__ uint64_t bar;
+    return &bar;
+}
 // first / second parameter types of a compute lambda (the reference's FunctionTraits, util/meta.h)
 template <typename T>
 struct LambdaArgs : LambdaArgs<decltype(&T::operator())> {};
@@ -150,13 +156,18 @@ struct Query
 
     // builds the adjacency of this patch in shared memory (TMA loads + transpose / fans); leaves the result view
     // and the owner table; all threads of the block call it; returns the allocator mark to restore in release()
+    // round < 0: a stand-alone query -- the barrier is initialised, used for one phase and invalidated (an mbarrier must
+    // be invalidated before its storage is initialised again).  round >= 0: one of a series of queries of the same kernel
+    // call site (higher_query_block_dispatcher): initialised in round 0, later rounds wait on the next phase parity, the
+    // caller invalidates it after the last round (end_rounds).
     template <Op op, bool PACKED>
     __device__ uint32_t build(ShmemAllocator& sa, bool oriented, bool all_sources, rxm::dev::QueryResult& r,
-                              rxm::dev::OwnerTable& ot)
+                              rxm::dev::OwnerTable& ot, int round = -1)
     {
         using namespace rxm::dev;
         constexpr int OPV = (int)op;
-        __shared__ uint64_t bar;  // one phase per call; invalidated below once every thread has passed the wait
+        uint64_t*     barp = detail::query_barrier();
+        uint64_t&     bar  = *barp;
         __shared__ uint32_t warp_tmp[36];
         const rxm::PatchDesc& d    = m_desc;
         const uint8_t*        blob = m_ctx.view.topo + d.topo_off;
@@ -176,8 +187,10 @@ struct Query
             q.plan(d, sa.m_sm, true, all_sources, m_ctx.view.edge_manifold != 0);
         }
         if (threadIdx.x == 0) {
-            mbar_init(&bar, 1);
-            fence_mbar_init();
+            if (round <= 0) {
+                mbar_init(&bar, 1);
+                fence_mbar_init();
+            }
             if (use_fans) {
                 mbar_arrive_expect_tx(&bar, d.fanoff_bytes() + d.fanv_bytes() + d.own_bytes(rxm::ELEM_V) + d.stash_bytes());
                 bulk_g2s(s_fo, blob + d.off_fanoff(), d.fanoff_bytes(), &bar);
@@ -190,10 +203,11 @@ struct Query
             }
         }
         __syncthreads();
-        mbar_wait(&bar, 0);
-        __syncthreads();
-        if (threadIdx.x == 0) mbar_inval(&bar);  // a kernel may run several queries (a second dispatch, every round of
-                                                 // higher_query_block_dispatcher): the next call initialises it again
+        mbar_wait(&bar, round > 0 ? (uint32_t)(round & 1) : 0u);
+        if (round < 0) {
+            __syncthreads();
+            if (threadIdx.x == 0) mbar_inval(&bar);  // a kernel may run several queries: the next one initialises it again
+        }
         if (use_fans) {
             // fan_off entries carry the closed flag in bit 15: strip it once so the list bounds are plain
             for (uint32_t i = threadIdx.x; i <= d.n_owned[rxm::ELEM_V]; i += blockThreads)
@@ -213,6 +227,7 @@ struct Query
     // epilogue: every thread is done with the result; release the query's shared memory (query.inl:74-91)
     __device__ void release(ShmemAllocator& sa, uint32_t used0)
     {
+        rxm::dev::fence_proxy_async();  // generic-proxy accesses to this shared memory before the next query's TMA writes
         __syncthreads();
         sa.m_sm.used = used0;
     }
@@ -238,15 +253,21 @@ struct Query
     // The query of THIS patch answered for one source element per thread (the element may differ per thread, threads
     // without one pass has_src = false): the building block of higher_query_block_dispatcher
     // (kernels/query_dispatcher.cuh:445-565), called by the whole block.
+    // after the last round of a series (build with round >= 0): every thread has passed its waits
+    static __device__ void end_rounds()
+    {
+        __syncthreads();
+        if (threadIdx.x == 0) rxm::dev::mbar_inval(detail::query_barrier());
+    }
     template <Op op, typename computeT>
     __device__ void dispatch_src(ShmemAllocator& sa, bool has_src, typename InputHandle<op>::type src, computeT& compute_op,
-                                 bool oriented)
+                                 bool oriented, int round)
     {
         using OutH = typename OutputHandle<op>::type;
         rxm::dev::QueryResult r;
         rxm::dev::OwnerTable  ot;
-        const uint32_t used0 = m_ctx.view.packed ? build<op, true>(sa, oriented, false, r, ot)
-                                                 : build<op, false>(sa, oriented, false, r, ot);
+        const uint32_t used0 = m_ctx.view.packed ? build<op, true>(sa, oriented, false, r, ot, round)
+                                                 : build<op, false>(sa, oriented, false, r, ot, round);
         if (has_src && src.local_id() < r.n_src) {
             Iterator<OutH> it(r, ot, src.local_id());
             compute_op(src, it);

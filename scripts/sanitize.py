@@ -17,8 +17,9 @@ from conftest import make_mesh  # noqa: E402
 
 rx.rx_init(0)
 DST = {"V": 0, "E": 1, "F": 2}
-for mode in ({}, {"RXM_NO_FANS": "1"}, {"RXM_NO_FANS": "1", "RXM_FORCE_WIDE": "1"}, {"RXM_PERSIST": "1"}):
-    for k in ("RXM_NO_FANS", "RXM_FORCE_WIDE", "RXM_PERSIST"):
+for mode in ({}, {"RXM_NO_FANS": "1"}, {"RXM_NO_FANS": "1", "RXM_FORCE_WIDE": "1"}, {"RXM_PERSIST": "1"},
+             {"RXM_VN_SCALAR": "1", "RXM_CONSUME_BT256": "1", "RXM_PIPE_CHUNKS": "0"}):
+    for k in ("RXM_NO_FANS", "RXM_FORCE_WIDE", "RXM_PERSIST", "RXM_VN_SCALAR", "RXM_CONSUME_BT256", "RXM_PIPE_CHUNKS"):
         os.environ.pop(k, None)
     os.environ.update(mode)
     V, F = make_mesh("bunnyhead")
@@ -28,6 +29,8 @@ for mode in ({}, {"RXM_NO_FANS": "1"}, {"RXM_NO_FANS": "1", "RXM_FORCE_WIDE": "1
     for op in ("VV", "VE", "VF", "EV", "EF", "FV", "FE", "FF"):
         m.query_global(rx.Op[op])
         m.query_consume_host(rx.Op[op], np.ones(m._num(DST[op[1]]), np.float32))
+    for op in ("EVDiamond", "EE"):  # fixed-width-4 results (bunnyhead is edge-manifold with a boundary)
+        m.query_global(rx.Op[op])
     x = rx.Attribute(m, 0, np.float32, 3, rx.LOCATION_ALL, rx.AoS)
     y = rx.Attribute(m, 0, np.float32, 3, rx.LOCATION_ALL, rx.AoS)
     x.from_global(V)
@@ -36,3 +39,12 @@ for mode in ({}, {"RXM_NO_FANS": "1"}, {"RXM_NO_FANS": "1", "RXM_FORCE_WIDE": "1
         flag = rx.Attribute(m, 0, np.uint32, 1, rx.LOCATION_ALL, rx.AoS)
         m.boundary_vertices(flag)
     print("mode", mode, "ok", flush=True)
+# the user-kernel path through the drop-in headers (Query::dispatch, higher_query_block_dispatcher, split API)
+import ctypes as C  # noqa: E402
+shim = C.CDLL(os.path.join(ROOT, "tests", "cpp", "libshim_apps.so"))
+V, F = make_mesh("bunnyhead")
+p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+out = np.zeros_like(V)
+assert shim.shim_vertex_normals(p(F), F.shape[0], p(V), V.shape[0], 256, p(out)) == 0
+assert shim.shim_filtering(p(F), F.shape[0], p(V), V.shape[0], 512, 1, p(out)) == 0
+print("shim ok", flush=True)
