@@ -46,7 +46,7 @@ struct rxm_mesh
     // scratch for the host-buffer entry points and multi-iteration drivers
     void*     d_stage[32]       = {};  // [0] generic; host entry points own dedicated in/out buffers
     size_t    d_stage_bytes[32] = {};
-    rxm_attr* scratch[4]    = {nullptr, nullptr, nullptr, nullptr};
+    rxm_attr* scratch[8]    = {};  // [0..3] drivers / host entry points, [4..7] AoS stand-ins for other layouts
     struct Csr
     {
         uint32_t *off = nullptr, *val = nullptr;
@@ -740,23 +740,6 @@ int rxm_query_consume(rxm_mesh* m, int op, rxm_attr* in, rxm_attr* out, void* st
     return kernel_status(e, why, "rxm_query_consume");
 }
 
-static bool is_vec3_aos(rxm_attr* a)
-{
-    return a && a->d && a->elem == RXM_V && a->elem_bytes == 4 && a->nattr == 3 && a->layout == RXM_AOS;
-}
-
-int rxm_vertex_normals(rxm_mesh* m, rxm_attr* coords, rxm_attr* normals, int unit, void* stream)
-{
-    int rc = check_dev(m, "rxm_vertex_normals");
-    if (rc) return rc;
-    if (!is_vec3_aos(coords) || !is_vec3_aos(normals))
-        return fail(RXM_ERR_INVALID, "rxm_vertex_normals: coords/normals must be device 3 x fp32 AoS vertex attributes");
-    const char* why = nullptr;
-    cudaError_t e   = launch_vertex_normals(m->view, m->lim, (const float*)coords->d, (float*)normals->d, unit,
-                                            (cudaStream_t)stream, &why);
-    return kernel_status(e, why, "rxm_vertex_normals");
-}
-
 static int get_scratch(rxm_mesh* m, int idx, rxm_attr** out)
 {
     if (!m->scratch[idx]) {
@@ -767,12 +750,66 @@ static int get_scratch(rxm_mesh* m, int idx, rxm_attr** out)
     return RXM_OK;
 }
 
+// The fixed-function kernels read and write AoS xyz.  An attribute in another layout (the reference's default is
+// AoSoA) is served through an AoS stand-in: relayout in, run, relayout out -- two extra streaming passes, same results.
+static bool is_vec3(rxm_attr* a)
+{
+    return a && a->d && a->elem == RXM_V && a->elem_bytes == 4 && a->nattr == 3;
+}
+static int aos_standin(rxm_mesh* m, rxm_attr* a, int idx, bool load, void* stream, rxm_attr** out)
+{
+    if (a->layout == RXM_AOS) {
+        *out = a;
+        return RXM_OK;
+    }
+    int rc = get_scratch(m, idx, out);
+    if (rc) return rc;
+    if (load) {
+        cudaError_t e = launch_relayout(a->d, (*out)->d, m->d_slot_base[RXM_V], m->h.num_patches, m->h.num_slots[RXM_V], 3,
+                                        (uint32_t)a->layout, RXM_AOS, (cudaStream_t)stream);
+        if (e != cudaSuccess) return fail(RXM_ERR_CUDA, std::string("relayout: ") + cudaGetErrorString(e));
+    }
+    return RXM_OK;
+}
+static int aos_writeback(rxm_mesh* m, rxm_attr* a, rxm_attr* standin, void* stream)
+{
+    if (a == standin) return RXM_OK;
+    cudaError_t e = launch_relayout(standin->d, a->d, m->d_slot_base[RXM_V], m->h.num_patches, m->h.num_slots[RXM_V], 3, RXM_AOS,
+                                    (uint32_t)a->layout, (cudaStream_t)stream);
+    return e == cudaSuccess ? RXM_OK : fail(RXM_ERR_CUDA, std::string("relayout: ") + cudaGetErrorString(e));
+}
+
+static bool is_vec3_aos(rxm_attr* a)
+{
+    return a && a->d && a->elem == RXM_V && a->elem_bytes == 4 && a->nattr == 3 && a->layout == RXM_AOS;
+}
+
+int rxm_vertex_normals(rxm_mesh* m, rxm_attr* coords, rxm_attr* normals, int unit, void* stream)
+{
+    int rc = check_dev(m, "rxm_vertex_normals");
+    if (rc) return rc;
+    if (!is_vec3(coords) || !is_vec3(normals))
+        return fail(RXM_ERR_INVALID, "rxm_vertex_normals: coords/normals must be device 3 x fp32 vertex attributes");
+    rxm_attr *x, *n;
+    if ((rc = aos_standin(m, coords, 4, true, stream, &x)) || (rc = aos_standin(m, normals, 5, false, stream, &n))) return rc;
+    const char* why = nullptr;
+    cudaError_t e   = launch_vertex_normals(m->view, m->lim, (const float*)x->d, (float*)n->d, unit, (cudaStream_t)stream, &why);
+    if ((rc = kernel_status(e, why, "rxm_vertex_normals"))) return rc;
+    return aos_writeback(m, normals, n, stream);
+}
+
 int rxm_laplacian_smooth(rxm_mesh* m, rxm_attr* in, rxm_attr* out, double lr, uint32_t iters, void* stream)
 {
     int rc = check_dev(m, "rxm_laplacian_smooth");
     if (rc) return rc;
-    if (!is_vec3_aos(in) || !is_vec3_aos(out) || in == out)
-        return fail(RXM_ERR_INVALID, "rxm_laplacian_smooth: in/out must be distinct device 3 x fp32 AoS vertex attributes");
+    if (!is_vec3(in) || !is_vec3(out) || in == out)
+        return fail(RXM_ERR_INVALID, "rxm_laplacian_smooth: in/out must be distinct device 3 x fp32 vertex attributes");
+    if (in->layout != RXM_AOS || out->layout != RXM_AOS) {
+        rxm_attr *x, *y;
+        if ((rc = aos_standin(m, in, 4, true, stream, &x)) || (rc = aos_standin(m, out, 5, false, stream, &y))) return rc;
+        if ((rc = rxm_laplacian_smooth(m, x, y, lr, iters, stream))) return rc;
+        return aos_writeback(m, out, y, stream);
+    }
     if (iters == 0) return rxm_attr_copy_from(out, in, RXM_DEVICE, RXM_DEVICE, stream);
     rxm_attr* tmp = nullptr;
     if (iters > 1) {
@@ -859,8 +896,14 @@ int rxm_bilateral_filter(rxm_mesh* m, rxm_attr* in, rxm_attr* out, uint32_t iter
 {
     int rc = check_dev(m, "rxm_bilateral_filter");
     if (rc) return rc;
-    if (!is_vec3_aos(in) || !is_vec3_aos(out) || in == out)
-        return fail(RXM_ERR_INVALID, "rxm_bilateral_filter: in/out must be distinct device 3 x fp32 AoS vertex attributes");
+    if (!is_vec3(in) || !is_vec3(out) || in == out)
+        return fail(RXM_ERR_INVALID, "rxm_bilateral_filter: in/out must be distinct device 3 x fp32 vertex attributes");
+    if (in->layout != RXM_AOS || out->layout != RXM_AOS) {
+        rxm_attr *x, *y;
+        if ((rc = aos_standin(m, in, 4, true, stream, &x)) || (rc = aos_standin(m, out, 5, false, stream, &y))) return rc;
+        if ((rc = rxm_bilateral_filter(m, x, y, iters, stream))) return rc;
+        return aos_writeback(m, out, y, stream);
+    }
     if (iters == 0) return rxm_attr_copy_from(out, in, RXM_DEVICE, RXM_DEVICE, stream);
     uint32_t *off = nullptr, *val = nullptr;
     uint64_t  nnz = 0;

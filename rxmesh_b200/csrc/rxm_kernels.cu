@@ -1325,6 +1325,21 @@ __global__ void __launch_bounds__(BT) k_boundary(MeshView mv, uint32_t* __restri
 // --------------------------------------------------------------------------
 // attribute helpers
 // --------------------------------------------------------------------------
+// same slots, another layout (AoS <-> AoSoA <-> SoA): lets the fixed-function kernels, which read AoS, serve attributes
+// created with the reference's default layout
+__global__ void k_relayout(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const uint32_t* __restrict__ slot_base,
+                           uint32_t num_patches, uint32_t num_slots, uint32_t nattr, uint32_t layout_src, uint32_t layout_dst)
+{
+    AttrView<uint32_t> vs{nullptr, slot_base, num_slots, nattr, layout_src}, vd{nullptr, slot_base, num_slots, nattr, layout_dst};
+    for (uint32_t p = blockIdx.x; p < num_patches; p += gridDim.x) {
+        const uint32_t b = slot_base[p], cap = slot_base[p + 1] - b;
+        for (uint32_t i = threadIdx.x; i < cap * nattr; i += blockDim.x) {
+            const uint32_t lid = i / nattr, a = i % nattr;
+            dst[vd.index_known(b, cap, lid, a)] = src[vs.index_known(b, cap, lid, a)];
+        }
+    }
+}
+
 template <typename T, bool TO_SLOTS>
 __global__ void k_permute(const T* __restrict__ src, T* __restrict__ dst, const uint32_t* __restrict__ slot_to_global,
                           const uint32_t* __restrict__ slot_base, uint32_t num_patches, uint32_t num_slots,
@@ -1829,6 +1844,17 @@ static cudaError_t permute_dispatch(const void* src, void* dst, const uint32_t* 
                                                                num_patches, num_slots, nattr, layout);
     else
         return cudaErrorInvalidValue;
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_relayout(const void* src, void* dst, const uint32_t* slot_base, uint32_t num_patches, uint32_t num_slots,
+                            uint32_t nattr, uint32_t layout_src, uint32_t layout_dst, cudaStream_t stream)
+{
+    const uint32_t grid = std::min<uint32_t>(num_patches, 148u * 16u);
+    if (grid == 0) return cudaSuccess;
+    k_relayout<<<grid, 128, 0, stream>>>((const uint32_t*)src, (uint32_t*)dst, slot_base, num_patches, num_slots, nattr,
+                                         layout_src, layout_dst);
     ++g_launches;
     return cudaGetLastError();
 }

@@ -63,6 +63,9 @@ cudaError_t launch_boundary_vertices(const MeshView& mv, const KernelLimits& lim
                                      cudaStream_t stream, const char** err);
 
 // out_slot[slot*nattr + a] = in_global[global_of_slot*nattr + a] (AoS), 0 for padding slots
+// 32-bit attributes: copy between layouts over the same slots
+cudaError_t launch_relayout(const void* src, void* dst, const uint32_t* slot_base, uint32_t num_patches, uint32_t num_slots,
+                            uint32_t nattr, uint32_t layout_src, uint32_t layout_dst, cudaStream_t stream);
 cudaError_t launch_permute_to_slots(const void* in_global, void* out_slots, const uint32_t* slot_to_global,
                                     uint32_t num_slots, uint32_t elem_bytes, uint32_t nattr, uint32_t layout,
                                     const uint32_t* slot_base, uint32_t num_patches, cudaStream_t stream);
