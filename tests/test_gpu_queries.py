@@ -132,3 +132,29 @@ def test_edge4_rejects_non_manifold():
     m = rx.RXMeshStatic(F, patch_size=64)
     with pytest.raises(rx.RXMeshError):
         m.query_global(rx.Op.EVDiamond)
+
+
+def test_ee_inconsistent_orientation():
+    """Op::EE when neighbouring faces disagree on the winding (both traverse a shared edge the same way): the second face
+    takes the other side (the reference's atomicCAS fallback, rxmesh_queries.cuh:318-337), so every edge still reports
+    the {next, previous} pair of each of its faces -- which side holds which face is not defined."""
+    rx.rx_init(0)
+    V, F = make_mesh("sphere3")
+    F = F.copy()
+    F[::3] = F[::3][:, [0, 2, 1]]  # flip every third face
+    m = rx.RXMeshStatic(F, patch_size=256)
+    T = O.Topology(F)
+    inp, out, src, dst = m.query_global(rx.Op.EE)
+    oh = out.host_array()
+    sb, lb = m.slot_base(1).astype(np.int64), m.lin_base(1).astype(np.int64)
+    s2g = m.slot_to_global(1)
+    want = {}
+    for f in range(T.nf):
+        for j in range(3):
+            want.setdefault(int(T.fe[f, j]), []).append((int(T.fe[f, (j + 1) % 3]), int(T.fe[f, (j + 2) % 3])))
+    for p in range(m.get_num_patches()):
+        b, cap, no = int(sb[p]), int(sb[p + 1] - sb[p]), int(lb[p + 1] - lb[p])
+        rows = m.map_to_global(dst, oh[b * 4:b * 4 + 4 * cap].reshape(4, cap)[:, :no].T)
+        for i in range(no):
+            got = sorted((int(rows[i][2 * k]), int(rows[i][2 * k + 1])) for k in range(2) if rows[i][2 * k] != 0xFFFFFFFF)
+            assert got == sorted(want[int(s2g[b + i])]), (p, i, got, want[int(s2g[b + i])])
