@@ -616,7 +616,7 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
             M.total_local[t] += D.n[t];
         }
         D.n_stash    = (uint16_t)tmp[p].stash.size();
-        D.flags      = M.fans ? FLAG_FANS : 0;
+        D.flags      = (M.fans ? FLAG_FANS : 0) | (M.max_edge_incident_faces <= 2 ? FLAG_FF : 0);
         D.fan_total  = M.fans ? (uint32_t)fan_v[p].size() : 0;
         M.max_fan_total = std::max<uint32_t>(M.max_fan_total, D.fan_total);
         M.max_stash  = std::max<uint32_t>(M.max_stash, D.n_stash);
@@ -705,6 +705,28 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
             annotate(lev, 2 * nep, voe, nvp, 0, PK_ID_BITS);
             annotate(lfv, 3 * nfp, vof, nvp, 0, PK_ID_BITS);
             annotate(lfe, 3 * nfp, eof, nep, 1, PK_ID_BITS + 1);
+        }
+        if (D.flags & FLAG_FF) {
+            // stored FF: the (at most two) faces of every local edge, then per owned face the other face across
+            // edges 0, 1, 2, compacted to the front
+            const uint32_t        nep = D.n[ELEM_E], em = M.packed ? PK_ID_MASK : 0x7FFFu;
+            std::vector<uint16_t> ef2(2 * (size_t)nep, 0xFFFF);
+            for (uint32_t f = 0; f < D.n[ELEM_F]; ++f)
+                for (int j = 0; j < 3; ++j) {
+                    const uint32_t e = ((uint32_t)lfe[3 * f + j] >> 1) & em;
+                    ef2[2 * e + (ef2[2 * e] == 0xFFFF ? 0 : 1)] = (uint16_t)f;
+                }
+            uint16_t* ff = reinterpret_cast<uint16_t*>(B + D.off_ff());
+            for (uint32_t f = 0; f < D.n_owned[ELEM_F]; ++f) {
+                uint32_t k = 0;
+                for (int j = 0; j < 3; ++j) {
+                    const uint32_t e = ((uint32_t)lfe[3 * f + j] >> 1) & em;
+                    const uint16_t o = ef2[2 * e] == f ? ef2[2 * e + 1] : ef2[2 * e];
+                    if (o != 0xFFFF) ff[3 * f + k++] = o;
+                }
+                for (; k < 3; ++k)
+                    ff[3 * f + k] = 0xFFFF;
+            }
         }
         if (M.fans) {
             memcpy(B + D.off_fanoff(), fan_off[p].data(), fan_off[p].size() * 2);

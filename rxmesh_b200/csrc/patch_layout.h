@@ -96,6 +96,7 @@ constexpr uint32_t PK_MAX_VRANK = 32;      // ranks of vertex lists: 5 bits (ent
 constexpr uint32_t PK_MAX_ERANK = 16;      // ranks of edge lists: 4 bits (FE entry >> 12)
 constexpr uint16_t FLAG_PACKED  = 1;
 constexpr uint16_t FLAG_FANS    = 2;
+constexpr uint16_t FLAG_FF      = 4;       // bit 2: stored FF rows of the owned faces (edge-manifold input)
 constexpr uint16_t FAN_CLOSED   = 0x8000;  // bit 15 of a fan_off entry: the fan of this vertex is closed
 constexpr uint16_t FAN_OFF_MASK = 0x7FFF;
 constexpr uint64_t INVALID64_ = 0xFFFFFFFFFFFFFFFFull;
@@ -136,7 +137,8 @@ struct alignas(16) PatchDesc
     //      fan_off, fan_v, owner V/E/F, stash ----
     uint32_t o_fe, o_fv, o_voff_e, o_voff_f, o_eoff_f, o_fanoff, o_fanv, o_own[3], o_stash;
     uint32_t o_fanf;        // fan faces: fan_f[i] = local face between fan_v[i] and fan_v[i+1] (0xFFFF: none)
-    uint32_t pad1[4];
+    uint32_t o_ff;          // stored FF: 3 u16 per OWNED face, the faces across edge 0, 1, 2 compacted to the front, 0xFFFF after
+    uint32_t pad1[3];
 
     RXM_HD uint32_t ev_bytes() const { return o_fe; }
     RXM_HD uint32_t fe_bytes() const { return o_fv - o_fe; }
@@ -160,6 +162,8 @@ struct alignas(16) PatchDesc
     RXM_HD uint32_t off_own(uint32_t t) const { return o_own[t]; }
     RXM_HD uint32_t off_stash() const { return o_stash; }
     RXM_HD uint32_t stash_bytes() const { return 16u * n_stash; }
+    RXM_HD uint32_t off_ff() const { return o_ff; }
+    RXM_HD uint32_t ff_bytes() const { return (flags & FLAG_FF) ? round_up(6u * n_owned[ELEM_F], 16) : 0u; }
     RXM_HD uint32_t slot_cap(uint32_t t) const { return (n_owned[t] + 3u) & ~3u; }
 
     // builder: lay the sections out from the counts / flags already stored in this record
@@ -188,7 +192,8 @@ struct alignas(16) PatchDesc
             o += round_up(4u * (uint32_t)(n[t] - n_owned[t]), 16);
         }
         o_stash    = o;
-        topo_bytes = o + 16u * n_stash;
+        o_ff       = o + 16u * n_stash;
+        topo_bytes = o_ff + ff_bytes();
     }
 };
 static_assert(sizeof(PatchDesc) == 128, "PatchDesc must be 128 bytes");

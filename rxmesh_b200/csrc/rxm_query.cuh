@@ -120,6 +120,7 @@ struct PatchQuery
     uint32_t    n_rows;  // rows of the connectivity section that get loaded
     uint32_t    n_cols;  // columns whose lists are built
     bool        ff2;     // FF on edge-manifold input, packed format: pair table instead of the EF CSR
+    bool        ff3;     // FF read from the stored rows (patch_layout.h FLAG_FF): plain read + per-row count
 
     // shared-memory bytes this op needs for a patch with the given maxima
     // (host side; the role of calc_shared_memory, rxmesh_static.inl:498-841)
@@ -145,7 +146,20 @@ struct PatchQuery
     __device__ __forceinline__ void plan(const PatchDesc& d, Smem& sm, bool with_owner, bool all_sources,
                                          bool edge_manifold = false)
     {
-        ff2 = OP == OP_FF && PACKED && edge_manifold;
+        ff3 = OP == OP_FF && edge_manifold && (d.flags & FLAG_FF) && !all_sources;
+        ff2 = OP == OP_FF && PACKED && edge_manifold && !ff3;
+        if (ff3) {
+            n_rows = d.n_owned[ELEM_F], n_cols = 0, loff_bytes = 0;
+            conn_bytes = d.ff_bytes();
+            s_conn     = sm.alloc<uint16_t>(conn_bytes / 2);
+            s_val      = sm.alloc<uint16_t>(n_rows);  // per-row fill count
+            s_loff = nullptr, s_off = nullptr, s_off2 = nullptr, s_val2 = nullptr, s_own = nullptr, s_stash = nullptr;
+            if (with_owner) {
+                s_own   = sm.alloc<uint32_t>(d.own_bytes(Tr::dst) / 4);
+                s_stash = sm.alloc<StashEntry>(d.n_stash);
+            }
+            return;
+        }
         const uint32_t rows_all = Tr::conn == 0 ? d.n[ELEM_E] : d.n[ELEM_F];
         n_rows = (op_is_fixed<OP>() && !all_sources) ? d.n_owned[Tr::src] : rows_all;
         if (OP == OP_FF || op_is_edge4<OP>()) n_rows = rows_all;
@@ -194,7 +208,7 @@ struct PatchQuery
     // thread 0 only, after mbar_arrive_expect_tx
     __device__ __forceinline__ void issue(const PatchDesc& d, const uint8_t* blob, uint64_t* bar, bool with_owner) const
     {
-        const uint32_t o = Tr::conn == 0 ? d.off_ev() : (Tr::conn == 1 ? d.off_fe() : d.off_fv());
+        const uint32_t o = (OP == OP_FF && ff3) ? d.off_ff() : (Tr::conn == 0 ? d.off_ev() : (Tr::conn == 1 ? d.off_fe() : d.off_fv()));
         if (conn_bytes) bulk_g2s(s_conn, blob + o, conn_bytes, bar);
         if (OP == OP_EVDIAMOND && d.ev_bytes()) bulk_g2s(s_val2, blob + d.off_ev(), d.ev_bytes(), bar);
         if (loff_bytes) {
@@ -229,6 +243,13 @@ struct PatchQuery
         r.n_src = lim, r.shift = 0, r.stride = 0, r.mask = 0xFFFFu;
         r.off16 = nullptr, r.off32 = nullptr, r.cnt = nullptr;
         const uint16_t* c = s_conn;
+        if (OP == OP_FF && ff3) {
+            for (uint32_t f = threadIdx.x; f < lim; f += BT)
+                s_val[f] = (uint16_t)((c[3 * f] != 0xFFFFu) + (c[3 * f + 1] != 0xFFFFu) + (c[3 * f + 2] != 0xFFFFu));
+            __syncthreads();
+            r.val = c, r.stride = 3, r.cnt = s_val;
+            return r;
+        }
         if (op_is_edge4<OP>()) {
             const uint32_t em = PACKED ? PK_ID_MASK : 0x7FFFu;
             const uint32_t ne = n_cols;
