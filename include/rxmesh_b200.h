@@ -158,7 +158,8 @@ int rxm_query_store(rxm_mesh* m, int op, rxm_attr* in, rxm_attr* out, void* stre
 /* roofline "consume" variant: out(s) = sum_i in(iter[i]); in: 1 x fp32 on the op's output element type,
  * out: 1 x fp32 on its source element type. */
 int rxm_query_consume(rxm_mesh* m, int op, rxm_attr* in, rxm_attr* out, void* stream);
-/* compute_vertex_normal (apps/VertexNormal/vertex_normal_kernel.cuh:10-43), coords/normals: 3 x fp32 AoS.
+/* compute_vertex_normal (apps/VertexNormal/vertex_normal_kernel.cuh:10-43), coords/normals: 3 x fp32 vertex attributes
+ * in any layout (AoS is the fast path; AoSoA / SoA run through an AoS stand-in -- same for the two calls below).
  * unit_face_normals != 0 -> the Filtering variant (apps/Filtering/filtering_rxmesh_kernel.cuh:15-46). */
 int rxm_vertex_normals(rxm_mesh* m, rxm_attr* coords, rxm_attr* normals, int unit_face_normals, void* stream);
 /* manual smoothing (apps/Smoothing/manual.h:86-104): `iters` Jacobi steps x <- x - lr * sum_u 2(x - x_u);

@@ -8,6 +8,12 @@
 //   k_laplacian       apps/Smoothing/manual.h:86-104, the two kernels of an iteration fused
 //   k_bilateral       apps/Filtering/filtering_rxmesh_kernel.cuh:426-548 on a materialised VV CSR
 //   k_boundary        kernels/boundary.cuh:11-44
+// Kernel families (chosen per mesh by the launchers at the bottom of this file):
+//   *_fan2 / *_consume_fan<128>  one-ring fans: two vertices per thread with packed fp32x2 arithmetic (normals, Laplacian;
+//                                k_laplacian_fan2<true> also pushes halo rows to peer GPUs), plain-read VV / VF consume
+//   *_pk / <.., true>            rank-annotated ("packed") incidence: atomic-free transposes (no fans: non-manifold input)
+//   <.., false>                  wide format: shared atomics + scan (patches beyond the packed limits)
+//   k_persistent<Worker>         opt-in software-pipelined variants (RXM_PERSIST=1, rxm_persistent.cuh)
 //
 // One thread block per patch; every patch section and the patch's owned attribute
 // slice arrive by TMA bulk copies under one mbarrier phase.
