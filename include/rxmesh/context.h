@@ -24,6 +24,20 @@ class Context
         const uint32_t  pid  = reinterpret_cast<const rxm::StashEntry*>(blob + d.off_stash())[o >> 16].patch;
         return HandleT(pid, typename HandleT::LocalT((uint16_t)(o & 0xFFFFu)));
     }
+    // get_handle (context.h:330-352): the inverse of linear_id -- binary search over the per-patch prefix
+    template <typename HandleT>
+    __device__ HandleT get_handle(const uint32_t i) const
+    {
+        uint32_t lo = 0, hi = view.num_patches;  // last patch whose prefix <= i
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) / 2;
+            if (view.desc[mid].lin_base[HandleT::elem] <= i)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        return HandleT(view.desc[lo].patch_id, typename HandleT::LocalT((uint16_t)(i - view.desc[lo].lin_base[HandleT::elem])));
+    }
     // linear_id (context.h:275-290) of an OWNER handle: prefix[patch] + local
     template <typename HandleT>
     __device__ uint32_t linear_id(HandleT h) const

@@ -367,6 +367,18 @@ class RXMeshStatic
         for_each_elem<FaceHandle>(location, apply, stream, with_omp);
     }
 
+    // for_each<HandleT>(location, lambda) (rxmesh_static.h:387-410) and get_num_elements<HandleT>() (rxmesh.h)
+    template <typename HandleT, typename LambdaT>
+    void for_each(locationT location, LambdaT apply, cudaStream_t stream = NULL, bool with_omp = true) const
+    {
+        for_each_elem<HandleT>(location, apply, stream, with_omp);
+    }
+    template <typename HandleT>
+    uint32_t get_num_elements() const
+    {
+        return info(RXM_INFO_NUM_VERTICES + HandleT::elem);
+    }
+
     // ---- for_each<Op, blockThreads>(lambda) (rxmesh_static.h:524-566) ----
     template <Op op, uint32_t blockThreads, typename LambdaT>
     void for_each(const LambdaT user_lambda, const bool oriented = false, cudaStream_t stream = NULL) const

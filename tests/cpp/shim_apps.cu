@@ -235,6 +235,86 @@ __global__ static void user_split_api(const Context context, VertexAttribute<int
     for_each<Op::F, blockThreads>(context, [&](const FaceHandle fh) { touched(fh) = 1; });
 }
 
+// ---- tests/RXMesh_test/test_multi_queries.cu:10-92: vertex edge-length sums, once by an EV scatter with atomics and once
+// by a primary VE query whose lambda reads a SECONDARY EV query through prologue / get_iterator(local) / epilogue
+template <uint32_t blockThreads, typename T>
+__global__ static void user_sum_edges_ev(const Context context, const VertexAttribute<T> coords, VertexAttribute<T> vertex_sum)
+{
+    auto sum_edges = [&](const EdgeHandle&, const VertexIterator& iter) {
+        const T edge_len = glm::distance2(coords.template to_glm<3>(iter[0]), coords.template to_glm<3>(iter[1]));
+        ::atomicAdd(&vertex_sum(iter[0]), edge_len);
+        ::atomicAdd(&vertex_sum(iter[1]), edge_len);
+    };
+    auto                block = cooperative_groups::this_thread_block();
+    Query<blockThreads> query(context);
+    ShmemAllocator      shrd_alloc;
+    query.template dispatch<Op::EV>(block, shrd_alloc, sum_edges);
+}
+template <uint32_t blockThreads, typename T>
+__global__ static void user_sum_edges_multi_queries(const Context context, const VertexAttribute<T> coords,
+                                                    VertexAttribute<T> vertex_sum)
+{
+    auto                block = cooperative_groups::this_thread_block();
+    ShmemAllocator      shrd_alloc;
+    Query<blockThreads> ev_query(context);
+    ev_query.template prologue<Op::EV>(block, shrd_alloc);  // the secondary query
+    auto sum_edges = [&](const VertexHandle& vertex, const EdgeIterator& eiter) {
+        const vec3<T> p0 = coords.template to_glm<3>(vertex);
+        for (uint16_t i = 0; i < eiter.size(); ++i) {
+            VertexIterator     viter = ev_query.template get_iterator<VertexIterator>(eiter.local(i));
+            const VertexHandle vh0(viter[0]), vh1(viter[1]);
+            const vec3<T>      p1 = coords.template to_glm<3>(vertex != vh0 ? vh0 : vh1);
+            vertex_sum(vertex) += glm::distance2(p0, p1);
+        }
+    };
+    Query<blockThreads> ve_query(context);  // the primary query
+    ve_query.template dispatch<Op::VE>(block, shrd_alloc, sum_edges);
+    ev_query.epilogue(block, shrd_alloc);
+}
+
+// ---- tests/RXMesh_test/higher_query.cuh:15-90: 2-ring VV through query_block_dispatcher + higher_query_block_dispatcher
+template <uint32_t blockThreads, Op op>
+__global__ static void user_higher_query(const Context context, VertexAttribute<VertexHandle> input,
+                                         VertexAttribute<VertexHandle> output)
+{
+    VertexHandle thread_vertex;
+    uint32_t     num_vv_1st_ring(0), num_vv(0);
+    auto first_ring_lambda = [&](VertexHandle id, Iterator<VertexHandle>& iter) {
+        num_vv_1st_ring = iter.size();
+        num_vv          = num_vv_1st_ring;
+        thread_vertex        = id;
+        input(thread_vertex) = thread_vertex;
+        for (uint32_t i = 0; i < iter.size(); ++i)
+            output(thread_vertex, i) = iter[i];
+    };
+    query_block_dispatcher<op, blockThreads>(context, first_ring_lambda);
+    uint32_t next_id = 0;
+    while (true) {
+        VertexHandle next_vertex;
+        if (thread_vertex.is_valid() && next_id < num_vv_1st_ring) next_vertex = output(thread_vertex, next_id);
+        auto higher_rings_lambda = [&](const VertexHandle&, const VertexIterator& iter) {
+            for (uint32_t i = 0; i < iter.size(); ++i) {
+                if (iter[i] != thread_vertex) {
+                    bool duplicate = false;
+                    for (uint32_t j = 0; j < num_vv; ++j)
+                        if (iter[i] == output(thread_vertex, j)) {
+                            duplicate = true;
+                            break;
+                        }
+                    if (!duplicate) {
+                        output(thread_vertex, num_vv) = iter[i];
+                        num_vv++;
+                    }
+                }
+            }
+        };
+        higher_query_block_dispatcher<op, blockThreads>(context, next_vertex, higher_rings_lambda);
+        const bool is_done = (next_id >= num_vv_1st_ring) || !thread_vertex.is_valid();
+        if (__syncthreads_and(is_done)) break;
+        next_id++;
+    }
+}
+
 // a kernel launched through run_kernel: out(v) = scale * valence(v)
 template <uint32_t blockThreads>
 __global__ static void user_scaled_valence(const Context context, VertexAttribute<float> out, float scale)
@@ -487,6 +567,85 @@ static int app_api_surface(const char* obj_path, const char* export_path, uint32
     return bad;
 }
 
+// TEST(RXMeshStatic, MultiQueries) (tests/RXMesh_test/test_multi_queries.cu:94-153): both sums per vertex, global order
+static int app_multi_queries(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, float* out_ev,
+                             float* out_multi)
+{
+    rx_init(0);
+    RXMeshStatic rx(to_faces(fv, nf), "", patch_size);
+    constexpr uint32_t blockThreads = 320;
+    auto coords = rx.add_vertex_attribute<float>(to_verts(x, nv), "coords");
+    auto a      = rx.add_vertex_attribute<float>("sum_ev", 1, LOCATION_ALL);
+    auto b      = rx.add_vertex_attribute<float>("sum_multi", 1, LOCATION_ALL);
+    a->reset(0, DEVICE), b->reset(0, DEVICE);
+    rx.run_kernel<blockThreads>({Op::EV}, user_sum_edges_ev<blockThreads, float>, *coords, *a);
+    // two queries live at the same time: is_concurrent = true (test_multi_queries.cu:128-136)
+    rx.run_kernel<blockThreads>(user_sum_edges_multi_queries<blockThreads, float>, {Op::EV, Op::VE}, false, false, true,
+                                [](uint32_t, uint32_t, uint32_t) { return 0; }, NULL, *coords, *b);
+    if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+    a->move(DEVICE, HOST), b->move(DEVICE, HOST);
+    rx.for_each_vertex(HOST, [&](const VertexHandle& vh) {
+        out_ev[rx.map_to_global(vh)]    = (*a)(vh);
+        out_multi[rx.map_to_global(vh)] = (*b)(vh);
+    }, NULL, false);
+    return 0;
+}
+
+// TEST(RXMeshStatic, DISABLED_HigherQueries) (tests/RXMesh_test/test_higher_queries.cu:8-52): 2-ring VV; out_global is
+// [nv][width] global ids (0xFFFFFFFF = none)
+static int app_higher_query(const uint32_t* fv, uint32_t nf, uint32_t patch_size, uint32_t width, uint32_t* out_global)
+{
+    rx_init(0);
+    RXMeshStatic rx(to_faces(fv, nf), "", patch_size);
+    constexpr uint32_t blockThreads = 512;  // one vertex of the patch per thread (see app_filtering)
+    auto input  = rx.add_vertex_attribute<VertexHandle>("input", 1);
+    auto output = rx.add_vertex_attribute<VertexHandle>("output", width);
+    input->reset(VertexHandle(), DEVICE);
+    output->reset(VertexHandle(), DEVICE);
+    LaunchBox<blockThreads> lb;
+    rx.prepare_launch_box({Op::VV}, lb, (void*)user_higher_query<blockThreads, Op::VV>);
+    user_higher_query<blockThreads, Op::VV><<<lb.blocks, blockThreads, lb.smem_bytes_dyn>>>(rx.get_context(), *input, *output);
+    if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+    input->move(DEVICE, HOST), output->move(DEVICE, HOST);
+    int bad = 0;
+    rx.for_each_vertex(HOST, [&](const VertexHandle& vh) {
+        if ((*input)(vh) != vh) bad = 1;
+        for (uint32_t i = 0; i < width; ++i) {
+            const VertexHandle o = (*output)(vh, i);
+            out_global[(size_t)rx.map_to_global(vh) * width + i] = o.is_valid() ? rx.map_to_global(o) : 0xFFFFFFFFu;
+        }
+    }, NULL, false);
+    return bad ? -1 : 0;
+}
+
+// TEST(RXMeshStatic, Indices) (tests/RXMesh_test/test_indices.cu:11-63): linear_id(handle) <-> get_handle(i) on the device
+template <typename HandleT>
+static int indices_round_trip(RXMeshStatic& rx)
+{
+    const uint32_t size = rx.get_num_elements<HandleT>();
+    HandleT*       handles = nullptr;
+    int*           d_bad   = nullptr;
+    if (cudaMalloc((void**)&handles, sizeof(HandleT) * size) != cudaSuccess || cudaMalloc((void**)&d_bad, 4) != cudaSuccess) return 1;
+    cudaMemset(handles, 0xFF, sizeof(HandleT) * size);
+    cudaMemset(d_bad, 0, 4);
+    auto ctx = rx.get_context();
+    rx.for_each<HandleT>(DEVICE, [=] __device__(const HandleT h) { handles[ctx.template linear_id<HandleT>(h)] = h; });
+    rx.for_each<HandleT>(DEVICE, [=] __device__(const HandleT h) {
+        const uint32_t i = ctx.template linear_id<HandleT>(h);
+        if (i >= size || ctx.template get_handle<HandleT>(i) != handles[i] || handles[i] != h) *d_bad = 1;
+    });
+    int bad = 1;
+    if (cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost) != cudaSuccess) bad = 1;
+    cudaFree(handles), cudaFree(d_bad);
+    return bad;
+}
+static int app_indices(const uint32_t* fv, uint32_t nf, uint32_t patch_size)
+{
+    rx_init(0);
+    RXMeshStatic rx(to_faces(fv, nf), "", patch_size);
+    return indices_round_trip<VertexHandle>(rx) | (indices_round_trip<EdgeHandle>(rx) << 1) | (indices_round_trip<FaceHandle>(rx) << 2);
+}
+
 // the Filtering driver loop (apps/Filtering/filtering_rxmesh.cuh:60-100)
 static int app_filtering(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, int num_iter,
                          float* out)
@@ -590,6 +749,19 @@ int shim_time_vertex_normals(const uint32_t* fv, uint32_t nf, const float* x, ui
 int shim_api_surface(const char* obj_path, const char* export_path, uint32_t patch_size, float* out)
 {
     return app_api_surface(obj_path, export_path, patch_size, out);
+}
+int shim_multi_queries(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, float* out_ev,
+                       float* out_multi)
+{
+    return app_multi_queries(fv, nf, x, nv, patch_size, out_ev, out_multi);
+}
+int shim_higher_query(const uint32_t* fv, uint32_t nf, uint32_t patch_size, uint32_t width, uint32_t* out_global)
+{
+    return app_higher_query(fv, nf, patch_size, width, out_global);
+}
+int shim_indices(const uint32_t* fv, uint32_t nf, uint32_t patch_size)
+{
+    return app_indices(fv, nf, patch_size);
 }
 int shim_filtering(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, int num_iter, float* out)
 {

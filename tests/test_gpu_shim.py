@@ -194,3 +194,72 @@ def test_user_api_surface(shim, name, tmp_path):
     area = lambda X, G: np.linalg.norm(np.cross(X[G[:, 1]] - X[G[:, 0]], X[G[:, 2]] - X[G[:, 0]]), axis=1)
     assert np.allclose(np.sort(area(V2.astype(np.float64), F2)), np.sort(area(V.astype(np.float64), F)), rtol=1e-5, atol=1e-12)
     assert np.allclose(np.sort(V2, axis=0), np.sort(V, axis=0))
+
+
+@pytest.mark.parametrize("name", ["dragon", "bunnyhead"])
+def test_user_multi_queries(shim, name):
+    """TEST(RXMeshStatic, MultiQueries) (tests/RXMesh_test/test_multi_queries.cu): a primary VE query whose lambda reads a
+    secondary EV query (prologue / get_iterator(local) / epilogue) == the EV scatter, tol 1e-4 as in the reference."""
+    V, F = make_mesh(name)
+    T = O.Topology(F)
+    a, b = np.zeros(T.nv, np.float32), np.zeros(T.nv, np.float32)
+    assert shim.shim_multi_queries(_p(F), F.shape[0], _p(V), V.shape[0], 512, _p(a), _p(b)) == 0
+    assert np.abs(a - b).max() < 1e-4
+    l2 = ((V[T.ev[:, 0]].astype(np.float64) - V[T.ev[:, 1]]) ** 2).sum(1)
+    ref = np.zeros(T.nv)
+    np.add.at(ref, T.ev[:, 0], l2), np.add.at(ref, T.ev[:, 1], l2)
+    assert np.abs(b - ref).max() < 1e-4 * max(1.0, ref.max())
+
+
+@pytest.mark.parametrize("name", ["sphere3", "dragon"])
+def test_user_higher_query_two_ring(shim, name):
+    """TEST(RXMeshStatic, DISABLED_HigherQueries) (test_higher_queries.cu, higher_query.cuh): 2-ring VV vs the CPU
+    ground truth of rxmesh_test.h:84-121 (1-ring of the 1-ring, the vertex itself excluded)."""
+    V, F = make_mesh(name)
+    T = O.Topology(F)
+    off, val = T.query("VV")
+    ring1 = [set(int(u) for u in val[off[v]:off[v + 1]]) for v in range(T.nv)]
+    ring2 = [(r | set().union(*[ring1[u] for u in r])) - {v} for v, r in enumerate(ring1)]
+    width = max(len(r) for r in ring2) + 1
+    out = np.zeros((T.nv, width), dtype=np.uint32)
+    assert shim.shim_higher_query(_p(F), F.shape[0], 512, width, _p(out)) == 0
+    for v in range(T.nv):
+        got = [int(u) for u in out[v] if u != 0xFFFFFFFF]
+        assert len(got) == len(set(got)) and set(got) == ring2[v], v
+        assert set(got[:len(ring1[v])]) == ring1[v]  # the first ring comes first
+
+
+def test_user_indices_round_trip(shim):
+    """TEST(RXMeshStatic, Indices) (tests/RXMesh_test/test_indices.cu): linear_id(handle) <-> get_handle(i) on dragon.obj"""
+    V, F = make_mesh("dragon")
+    assert shim.shim_indices(_p(F), F.shape[0], 512) == 0
+
+
+@pytest.mark.parametrize("name,allowed,skip", [("plane", (90.0, 180.0), 4), ("cube", (90.0, 45.0), None)])
+def test_oriented_vv_angles(shim, name, allowed, skip):
+    """Oriented_VV_Open / Oriented_VV_Closed (tests/RXMesh_test/test_queries_oriented.cu:14-225): consecutive oriented
+    neighbours subtend 90 / 180 degrees summed over the first two pairs on plane.obj (centre vertex 4 excluded), and
+    90 / 45 degrees per pair on cube.obj."""
+    V, F = make_mesh(name)
+    T = O.Topology(F)
+    width = T.stats()["max_valence"]
+    out = np.zeros((T.nv, width), dtype=np.uint32)
+    assert shim.shim_query(int(rx.Op.VV), _p(F), F.shape[0], 512, width, 1, _p(out)) == 0
+
+    def angle(v, a, b):
+        p1, p2 = V[v].astype(np.float64) - V[a], V[v].astype(np.float64) - V[b]
+        return np.degrees(np.arccos(np.clip(p1 @ p2 / (np.linalg.norm(p1) * np.linalg.norm(p2)), -1, 1)))
+
+    for v in range(T.nv):
+        if name == "plane":
+            if v == skip:
+                continue
+            s = sum(angle(v, out[v][i], out[v][i + 1]) for i in range(2)
+                    if out[v][i] != 0xFFFFFFFF and out[v][i + 1] != 0xFFFFFFFF)
+            assert min(abs(s - a) for a in allowed) < 1e-3, (v, s)
+        else:
+            for i in range(width):
+                a, b = out[v][i], out[v][(i + 1) % width]
+                if a != 0xFFFFFFFF and b != 0xFFFFFFFF:
+                    th = angle(v, a, b)
+                    assert min(abs(th - x) for x in allowed) < 1e-3, (v, i, th)
