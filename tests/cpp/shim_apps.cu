@@ -315,6 +315,39 @@ __global__ static void user_higher_query(const Context context, VertexAttribute<
     }
 }
 
+// ---- unit tests of the device building blocks (the reference's Util.Scan / Util.BlockMatrixTranspose,
+// tests/RXMesh_test/test_util.cu:160-358): block_exclusive_scan and csr_transpose from rxm_device.cuh, one block
+template <int BT>
+__global__ static void unit_block_scan(uint32_t* a, uint32_t n)
+{
+    extern __shared__ __align__(16) uint8_t raw[];
+    uint32_t* s   = reinterpret_cast<uint32_t*>(raw);
+    uint32_t* tmp = s + n + 1;
+    for (uint32_t i = threadIdx.x; i < n; i += BT)
+        s[i] = a[i];
+    rxm::dev::block_exclusive_scan<BT>(s, n, tmp);
+    for (uint32_t i = threadIdx.x; i <= n; i += BT)
+        a[i] = s[i];
+}
+// src: [rows * deg] column ids; out: off[cols + 1], val[rows * deg] (row ids, each list sorted ascending)
+template <int BT, int KMAX>
+__global__ static void unit_block_transpose(const uint16_t* src, uint32_t rows, uint32_t cols, uint32_t deg, uint32_t* off,
+                                            uint16_t* val)
+{
+    extern __shared__ __align__(16) uint8_t raw[];
+    uint32_t*      s_off = reinterpret_cast<uint32_t*>(raw);
+    uint32_t*      tmp   = s_off + cols + 1;
+    uint16_t*      s_val = reinterpret_cast<uint16_t*>(tmp + 40);
+    const uint32_t nnz   = rows * deg;
+    rxm::dev::csr_transpose<BT, KMAX>(
+        nnz, cols, s_off, s_val, tmp, [=](uint32_t i) { return (uint32_t)src[i]; }, [=](uint32_t i) { return i / deg; });
+    rxm::dev::csr_sort_lists<BT>(cols, s_off, s_val);
+    for (uint32_t i = threadIdx.x; i <= cols; i += BT)
+        off[i] = s_off[i];
+    for (uint32_t i = threadIdx.x; i < nnz; i += BT)
+        val[i] = s_val[i];
+}
+
 // a kernel launched through run_kernel: out(v) = scale * valence(v)
 template <uint32_t blockThreads>
 __global__ static void user_scaled_valence(const Context context, VertexAttribute<float> out, float scale)
@@ -762,6 +795,30 @@ int shim_higher_query(const uint32_t* fv, uint32_t nf, uint32_t patch_size, uint
 int shim_indices(const uint32_t* fv, uint32_t nf, uint32_t patch_size)
 {
     return app_indices(fv, nf, patch_size);
+}
+int shim_unit_scan(uint32_t* host_a, uint32_t n)  // in place: a[0..n) -> exclusive prefix sums, a[n] = total
+{
+    uint32_t* d = nullptr;
+    if (cudaMalloc((void**)&d, 4 * (size_t)(n + 1)) != cudaSuccess) return 1;
+    cudaMemcpy(d, host_a, 4 * (size_t)n, cudaMemcpyHostToDevice);
+    unit_block_scan<256><<<1, 256, 4 * (n + 1) + 4 * 40>>>(d, n);
+    const int rc = cudaMemcpy(host_a, d, 4 * (size_t)(n + 1), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
+    cudaFree(d);
+    return rc;
+}
+int shim_unit_transpose(const uint16_t* host_src, uint32_t rows, uint32_t cols, uint32_t deg, uint32_t* host_off, uint16_t* host_val)
+{
+    const uint32_t nnz = rows * deg;
+    if (nnz > 12u * 256u) return 2;
+    uint16_t *d_src = nullptr, *d_val = nullptr;
+    uint32_t* d_off = nullptr;
+    cudaMalloc((void**)&d_src, 2 * (size_t)nnz), cudaMalloc((void**)&d_val, 2 * (size_t)nnz), cudaMalloc((void**)&d_off, 4 * (size_t)(cols + 1));
+    cudaMemcpy(d_src, host_src, 2 * (size_t)nnz, cudaMemcpyHostToDevice);
+    unit_block_transpose<256, 12><<<1, 256, 4 * (cols + 1) + 4 * 40 + 2 * nnz + 16>>>(d_src, rows, cols, deg, d_off, d_val);
+    int rc = cudaMemcpy(host_off, d_off, 4 * (size_t)(cols + 1), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
+    rc |= cudaMemcpy(host_val, d_val, 2 * (size_t)nnz, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
+    cudaFree(d_src), cudaFree(d_val), cudaFree(d_off);
+    return rc;
 }
 int shim_filtering(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, int num_iter, float* out)
 {

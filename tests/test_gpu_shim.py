@@ -263,3 +263,24 @@ def test_oriented_vv_angles(shim, name, allowed, skip):
                 if a != 0xFFFFFFFF and b != 0xFFFFFFFF:
                     th = angle(v, a, b)
                     assert min(abs(th - x) for x in allowed) < 1e-3, (v, i, th)
+
+
+def test_unit_block_scan_and_transpose(shim):
+    """Util.Scan / Util.BlockMatrixTranspose of the reference (tests/RXMesh_test/test_util.cu:160-358): our block-wide
+    exclusive scan and CSR transpose (rxm_device.cuh) against numpy, at the reference's test size (542 x 847 matrix,
+    3 non-zeros per row, no duplicate column inside a row)."""
+    rng = np.random.RandomState(11)
+    for n in (1, 31, 256, 1000, 2049):
+        a = np.zeros(n + 1, np.uint32)
+        a[:n] = rng.randint(0, 7, n)
+        want = np.concatenate([[0], np.cumsum(a[:n])]).astype(np.uint32)
+        assert shim.shim_unit_scan(_p(a), n) == 0
+        assert np.array_equal(a, want), n
+    rows, cols, deg = 542, 847, 3
+    src = np.stack([rng.permutation(cols)[:deg] for _ in range(rows)]).astype(np.uint16)
+    off, val = np.zeros(cols + 1, np.uint32), np.zeros(rows * deg, np.uint16)
+    assert shim.shim_unit_transpose(_p(src), rows, cols, deg, _p(off), _p(val)) == 0
+    assert off[0] == 0 and off[-1] == rows * deg
+    for c in range(cols):
+        want = np.sort(np.nonzero((src == c).any(axis=1))[0])
+        assert np.array_equal(val[off[c]:off[c + 1]], want), c
