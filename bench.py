@@ -311,7 +311,16 @@ def run_ours(args, rank, world, local_rank):
     fused = None
     if hx_v is not None and args.workload == "laplacian" and not os.environ.get("RXM_NO_FUSED"):
         from rxmesh_b200 import distributed as D
-        fused = D.FusedHalo(hx_v, x, nrm)  # needs the host patch store: before compact()
+        try:
+            fused = D.FusedHalo(hx_v, x, nrm)  # needs the host patch store: before compact()
+        except Exception as e:  # noqa: BLE001  (e.g. no peer access between the devices): packed NCCL exchange instead
+            print("rank %d: fused halo unavailable (%s), using NCCL send/recv" % (rank, str(e)[:200]), file=sys.stderr)
+            fused = None
+        # every rank must take the same path
+        ok = torch.tensor([1 if fused is not None else 0], device="cuda")
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+        if int(ok[0]) == 0:
+            fused = None
     mesh.compact()  # the 100 M-face mesh lives on the device; drop host helper arrays (halo plans are built)
     sv_in = rx.Attribute(mesh, 0, np.float32, 1, rx.DEVICE, rx.AoS)
     sv_out = rx.Attribute(mesh, 0, np.float32, 1, rx.DEVICE, rx.AoS)
