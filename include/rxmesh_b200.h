@@ -203,6 +203,8 @@ int rxm_attr_push_slots(rxm_attr* a, const uint32_t* dev_local_idx, void* remote
  * on neighbouring ranks into their ghost slots over NVLink P2P and raises a flag there; patches that read ghost slots
  * wait for the neighbours' flags.  Setup: create (allocates the flag words), export / exchange rxm_fused_halo_flags and
  * both attributes over cudaIpc, then set.  See rxmesh_b200/distributed.py: FusedHalo. */
+/* test hook: the chunk frontiers of the pipelined host-buffer calls (rxm_capi.cu: build_pipe_plan), host only */
+int rxm_mesh_pipe_plan(rxm_mesh* m, uint32_t chunks, uint32_t* pb, uint64_t* up_hi, uint64_t* down_lo, uint32_t* need);
 typedef struct rxm_fused_halo rxm_fused_halo;
 int   rxm_fused_halo_create(rxm_mesh* m, uint32_t npeers, rxm_fused_halo** out);
 void* rxm_fused_halo_flags(rxm_fused_halo* h);

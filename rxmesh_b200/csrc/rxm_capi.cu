@@ -160,13 +160,11 @@ int rxm_mesh_create(const uint32_t* fv, uint32_t num_faces, const uint32_t* face
 // [0, down_lo[c+1]) is final once chunks <= c are done.  Always correct; how much overlaps depends on how well patch
 // order follows global element order (row-major tiles of a grid: almost perfectly; Lloyd patches of a scrambled mesh:
 // the first piece is most of the array and the call degenerates to upload -> compute -> download).
-static void build_pipe_plan(rxm_mesh* m)
+static void build_pipe_plan(rxm_mesh* m, uint32_t K)
 {
     const HostMesh& h = m->h;
     auto&           P = m->plan;
     P.K               = 0;
-    const char* env   = getenv("RXM_PIPE_CHUNKS");
-    uint32_t    K     = env ? (uint32_t)atoi(env) : 8u;
     if (K < 2 || h.num_patches < 2 * K || h.topo.empty()) return;
     if (m->active_count && m->active_count != h.num_patches) return;  // shards with ghost patches: plain path
     P.pb.resize(K + 1);
@@ -214,6 +212,26 @@ static void build_pipe_plan(rxm_mesh* m)
     P.K = K;
 }
 
+// test hook: the pipeline frontiers for `chunks` chunks, computed on the host (no device needed).  Returns the number of
+// chunks actually planned (0: mesh too small); pb[chunks+1], up_hi[3][chunks], down_lo[3][chunks+1], need[chunks].
+int rxm_mesh_pipe_plan(rxm_mesh* m, uint32_t chunks, uint32_t* pb, uint64_t* up_hi, uint64_t* down_lo, uint32_t* need)
+{
+    if (!m || !pb || !up_hi || !down_lo || !need) return fail(RXM_ERR_INVALID, "rxm_mesh_pipe_plan: null argument");
+    const auto saved = m->plan;
+    build_pipe_plan(m, chunks);
+    const uint32_t K = m->plan.K;
+    if (K) {
+        memcpy(pb, m->plan.pb.data(), 4 * (size_t)(K + 1));
+        memcpy(need, m->plan.need.data(), 4 * (size_t)K);
+        for (int t = 0; t < 3; ++t) {
+            memcpy(up_hi + (size_t)t * K, m->plan.up_hi[t].data(), 8 * (size_t)K);
+            memcpy(down_lo + (size_t)t * (K + 1), m->plan.down_lo[t].data(), 8 * (size_t)(K + 1));
+        }
+    }
+    m->plan = saved;
+    return (int)K;
+}
+
 int rxm_mesh_to_device(rxm_mesh* m)
 {
     if (!m) return fail(RXM_ERR_INVALID, "rxm_mesh_to_device: null mesh");
@@ -245,7 +263,8 @@ int rxm_mesh_to_device(rxm_mesh* m)
         m->view.patch_slot_base[t] = m->d_slot_base[t];
     }
     m->on_device = true;
-    build_pipe_plan(m);
+    const char* env = getenv("RXM_PIPE_CHUNKS");
+    build_pipe_plan(m, env ? (uint32_t)atoi(env) : 8u);
     return RXM_OK;
 }
 

@@ -245,3 +245,46 @@ def test_reference_saved_patching_golden(name, tmp_path):
         assert np.array_equal(back[k], pf[k])
     assert np.array_equal(back["patches_offset"], pend) and np.array_equal(back["ribbon_ext_offset"], rend)
     assert np.array_equal(np.sort(back["patches_val"][:pend[0]]), np.sort(pf["patches_val"][:pend[0]]))
+
+
+@pytest.mark.parametrize("name,tiles", [("grid200x150", True), ("grid200x150", False), ("dragon", False), ("torus", False)])
+@pytest.mark.parametrize("chunks", [4, 8])
+def test_pipeline_frontiers(name, tiles, chunks):
+    """Frontiers of the chunked H2D / kernel / D2H pipeline of the host-buffer calls (rxm_capi.cu: build_pipe_plan), checked
+    against their definitions with numpy: before chunk c's slots are filled every owned element of patches < pb[c+1] has
+    arrived (up_hi); chunk c only reads ribbon elements owned by chunks <= need[c]; once chunks <= c are done every global id
+    below down_lo[c+1] is final."""
+    import ctypes as C
+    from rxmesh_b200 import meshio
+    from rxmesh_b200._lib import lib
+    V, F = make_mesh(name)
+    fp = meshio.grid_face_tiles(200, 150, 8) if tiles else None
+    m = rx.RXMeshStatic(F, face_patch=fp, patch_size=128, device=False)
+    P = m.get_num_patches()
+    pb = np.zeros(chunks + 1, np.uint32)
+    up, dn, need = np.zeros((3, chunks), np.uint64), np.zeros((3, chunks + 1), np.uint64), np.zeros(chunks, np.uint32)
+    K = lib().rxm_mesh_pipe_plan(m._h, chunks, pb.ctypes.data_as(C.c_void_p), up.ctypes.data_as(C.c_void_p),
+                                 dn.ctypes.data_as(C.c_void_p), need.ctypes.data_as(C.c_void_p))
+    assert K == chunks and pb[0] == 0 and pb[-1] == P and np.all(np.diff(pb.astype(np.int64)) > 0)
+    chunk_of = np.searchsorted(pb, np.arange(P), side="right") - 1
+    for t in range(3):
+        ep = m.elem_patch(t).astype(np.int64)            # owner patch of every global element
+        ec = chunk_of[ep]                                # ... and its chunk
+        n = ep.shape[0]
+        assert np.all(np.diff(up[t].astype(np.int64)) >= 0) and up[t][-1] == n
+        assert np.all(np.diff(dn[t].astype(np.int64)) >= 0) and dn[t][0] == 0 and dn[t][-1] == n
+        for c in range(chunks):
+            owned = np.nonzero(ec <= c)[0]
+            assert owned.max() < up[t][c]                 # all of them are inside the uploaded prefix
+            later = np.nonzero(ec > c)[0]
+            if later.size:
+                assert later.min() >= dn[t][c + 1]        # nothing below the download frontier is still pending
+    for c in range(chunks):
+        assert c <= need[c] < chunks
+        for p in range(int(pb[c]), int(pb[c + 1])):
+            pv = m.patch(p)
+            if pv["stash"].shape[0]:
+                assert chunk_of[pv["stash"][:, 0]].max() <= need[c]
+    if tiles:  # tile-ordered patches: a chunk needs at most the next chunk, and the frontiers advance with the chunks
+        assert np.all(need <= np.minimum(np.arange(chunks) + 1, chunks - 1))
+        assert up[0][0] < 0.6 * m.get_num_vertices()
