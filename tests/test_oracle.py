@@ -125,3 +125,40 @@ def test_all_cores_ports_match_serial():
     x = np.random.RandomState(0).rand(T.nv).astype(np.float32)
     a = O.consume_sum_mt(T.query("VV"), x, 4)
     assert np.allclose(a, O.consume_sum(T.query("VV"), x), rtol=1e-6)
+
+
+def test_gaussian_curvature_gauss_bonnet():
+    """Known-answer property of the restated GaussianCurvature accumulators (apps/GaussianCurvature): on a closed surface
+    sum_v (2 pi - sum of incident angles) = 2 pi chi (Gauss-Bonnet), and the mixed areas add up to the surface area."""
+    for name, chi in (("sphere3", 2), ("torus", 0), ("dragon", 0)):
+        g = load_golden(name)
+        V, F = g["V"], g["F"]
+        gcs, amix = O.gaussian_curvature(F, V)
+        assert abs((2 * np.pi + gcs).sum() - 2 * np.pi * chi) < 1e-6 * V.shape[0], name
+        X = V.astype(np.float64)
+        area = 0.5 * np.linalg.norm(np.cross(X[F[:, 1]] - X[F[:, 0]], X[F[:, 2]] - X[F[:, 0]]), axis=1).sum()
+        assert abs(amix.sum() - area) < 1e-6 * area, name
+
+
+def test_ev_diamond_and_ee_against_brute_force():
+    """rxo-side EVDiamond / EE restatements (oracle.Topology.ev_diamond / ee) against an independent per-edge search."""
+    for name in ("sphere3", "bunnyhead", "plane_5"):
+        F = load_golden(name)["F"]
+        T = O.Topology(F)
+        evd, ee = T.ev_diamond(), T.ee()
+        faces_of = {}
+        for f in range(T.nf):
+            for j in range(3):
+                faces_of.setdefault(int(T.fe[f, j]), []).append((f, j))
+        for e in range(T.ne):
+            v0, v1 = int(T.ev[e, 0]), int(T.ev[e, 1])
+            assert (evd[e, 0], evd[e, 2]) == (v0, v1)
+            want_v = {0: 0xFFFFFFFF, 1: 0xFFFFFFFF}
+            want_e = {0: (0xFFFFFFFF, 0xFFFFFFFF), 1: (0xFFFFFFFF, 0xFFFFFFFF)}
+            for f, j in faces_of[e]:
+                a, b, c = (int(F[f, j]), int(F[f, (j + 1) % 3]), int(F[f, (j + 2) % 3]))
+                d = 0 if (a, b) == (v0, v1) else 1
+                want_v[d] = c                                   # the vertex opposite to the edge in that face
+                want_e[d] = (int(T.fe[f, (j + 1) % 3]), int(T.fe[f, (j + 2) % 3]))
+            assert (evd[e, 1], evd[e, 3]) == (want_v[0], want_v[1]), (name, e)
+            assert tuple(ee[e]) == want_e[0] + want_e[1], (name, e)
