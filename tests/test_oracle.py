@@ -162,3 +162,19 @@ def test_ev_diamond_and_ee_against_brute_force():
                 want_e[d] = (int(T.fe[f, (j + 1) % 3]), int(T.fe[f, (j + 2) % 3]))
             assert (evd[e, 1], evd[e, 3]) == (want_v[0], want_v[1]), (name, e)
             assert tuple(ee[e]) == want_e[0] + want_e[1], (name, e)
+
+
+def test_mcf_matvec_constant_vector():
+    """Known answer for the restated MCF mat-vec (apps/MCF/mcf_kernels.cuh:117-205): the cotangent part annihilates a
+    constant vector whatever the time step, so out(p) = in / vw(p) with one positive factor per vertex shared by the three
+    components (vw = 0.5 / sum of the partial Voronoi areas in the reference's own scaling, geometry_util.cuh:120-172)."""
+    g = load_golden("sphere3")
+    V, F = g["V"], g["F"]
+    rings = O.oriented_rings(F, V.shape[0])
+    c = np.array([0.3, -1.2, 2.0], np.float32)
+    vin = np.tile(c, (V.shape[0], 1))
+    out10, out1 = O.mcf_matvec(rings, V, vin, 10.0), O.mcf_matvec(rings, V, vin, 1.0)
+    k = out10[:, 0] / np.float64(c[0])
+    assert np.all(k > 0)
+    assert np.allclose(out10, k[:, None] * vin.astype(np.float64), rtol=1e-7, atol=1e-9)
+    assert np.allclose(out10, out1, rtol=1e-6, atol=1e-8)  # independent of the time step
