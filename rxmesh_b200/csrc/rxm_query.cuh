@@ -121,6 +121,7 @@ struct PatchQuery
     uint32_t    n_cols;  // columns whose lists are built
     bool        ff2;     // FF on edge-manifold input, packed format: pair table instead of the EF CSR
     bool        ff3;     // FF read from the stored rows (patch_layout.h FLAG_FF): plain read + per-row count
+    bool        fanq;    // VV read from the stored one-ring fans (FLAG_FANS): plain read, oriented order
 
     // shared-memory bytes this op needs for a patch with the given maxima
     // (host side; the role of calc_shared_memory, rxmesh_static.inl:498-841)
@@ -146,6 +147,22 @@ struct PatchQuery
     __device__ __forceinline__ void plan(const PatchDesc& d, Smem& sm, bool with_owner, bool all_sources,
                                          bool edge_manifold = false)
     {
+        fanq = OP == OP_VV && edge_manifold && (d.flags & FLAG_FANS) && !all_sources;
+        if (fanq) {
+            // sections: fan_off (u16 offsets, bit 15 = closed fan) and fan_v; `edge_manifold` doubles as "stored sections
+            // may be used" (k_query_csr passes false: it needs the ascending-id order of the transposes)
+            n_rows = 0, n_cols = d.n_owned[ELEM_V];
+            loff_bytes = d.fanoff_bytes(), conn_bytes = d.fanv_bytes();
+            s_loff     = sm.alloc<uint16_t>(loff_bytes / 2);
+            s_conn     = sm.alloc<uint16_t>(conn_bytes / 2);
+            s_off = nullptr, s_val = nullptr, s_off2 = nullptr, s_val2 = nullptr, s_own = nullptr, s_stash = nullptr;
+            ff2 = ff3 = false;
+            if (with_owner) {
+                s_own   = sm.alloc<uint32_t>(d.own_bytes(Tr::dst) / 4);
+                s_stash = sm.alloc<StashEntry>(d.n_stash);
+            }
+            return;
+        }
         ff3 = OP == OP_FF && edge_manifold && (d.flags & FLAG_FF) && !all_sources;
         ff2 = OP == OP_FF && PACKED && edge_manifold && !ff3;
         if (ff3) {
@@ -208,6 +225,15 @@ struct PatchQuery
     // thread 0 only, after mbar_arrive_expect_tx
     __device__ __forceinline__ void issue(const PatchDesc& d, const uint8_t* blob, uint64_t* bar, bool with_owner) const
     {
+        if (OP == OP_VV && fanq) {
+            if (conn_bytes) bulk_g2s(s_conn, blob + d.off_fanv(), conn_bytes, bar);
+            bulk_g2s(s_loff, blob + d.off_fanoff(), loff_bytes, bar);
+            if (with_owner) {
+                if (d.own_bytes(Tr::dst)) bulk_g2s(s_own, blob + d.off_own(Tr::dst), d.own_bytes(Tr::dst), bar);
+                if (d.stash_bytes()) bulk_g2s(s_stash, blob + d.off_stash(), d.stash_bytes(), bar);
+            }
+            return;
+        }
         const uint32_t o = (OP == OP_FF && ff3) ? d.off_ff() : (Tr::conn == 0 ? d.off_ev() : (Tr::conn == 1 ? d.off_fe() : d.off_fv()));
         if (conn_bytes) bulk_g2s(s_conn, blob + o, conn_bytes, bar);
         if (OP == OP_EVDIAMOND && d.ev_bytes()) bulk_g2s(s_val2, blob + d.off_ev(), d.ev_bytes(), bar);
@@ -243,6 +269,13 @@ struct PatchQuery
         r.n_src = lim, r.shift = 0, r.stride = 0, r.mask = 0xFFFFu;
         r.off16 = nullptr, r.off32 = nullptr, r.cnt = nullptr;
         const uint16_t* c = s_conn;
+        if (OP == OP_VV && fanq) {
+            for (uint32_t i = threadIdx.x; i <= lim; i += BT)
+                s_loff[i] &= FAN_OFF_MASK;  // drop the closed-fan flag: plain list bounds
+            __syncthreads();
+            r.off16 = s_loff, r.val = c, r.mask = 0xFFFFu;
+            return r;
+        }
         if (OP == OP_FF && ff3) {
             for (uint32_t f = threadIdx.x; f < lim; f += BT)
                 s_val[f] = (uint16_t)((c[3 * f] != 0xFFFFu) + (c[3 * f + 1] != 0xFFFFu) + (c[3 * f + 2] != 0xFFFFu));
