@@ -213,7 +213,7 @@ struct Query
             for (uint32_t i = threadIdx.x; i <= d.n_owned[rxm::ELEM_V]; i += blockThreads)
                 s_fo[i] &= rxm::FAN_OFF_MASK;
             __syncthreads();
-            r.off16 = s_fo, r.off32 = nullptr, r.cnt = nullptr, r.val = s_fv, r.stride = 0, r.shift = 0, r.mask = 0xFFFFu;
+            r.off16 = s_fo, r.off32 = nullptr, r.cnt = nullptr, r.end16 = nullptr, r.val = s_fv, r.stride = 0, r.shift = 0, r.mask = 0xFFFFu;
             r.n_src = d.n_owned[rxm::ELEM_V];
             ot.own = s_own, ot.stash = s_stash, ot.n_owned = d.n_owned[rxm::ELEM_V], ot.patch = d.patch_id;
             ot.slot_base = d.slot_base[rxm::ELEM_V], ot.type = rxm::ELEM_V;

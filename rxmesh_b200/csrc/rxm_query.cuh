@@ -88,6 +88,7 @@ struct QueryResult
     uint32_t        mask;    // id mask applied after the shift
     uint32_t        n_src;   // number of source elements with a list
     const uint16_t* cnt;     // fixed stride with per-row fill count (FF on edge-manifold input), else null
+    const uint16_t* end16;   // explicit list ends next to off16 (VF through the fan faces: open fans end one slot early)
 
     __device__ __forceinline__ uint32_t begin(uint32_t s) const
     {
@@ -95,8 +96,9 @@ struct QueryResult
     }
     __device__ __forceinline__ uint32_t end(uint32_t s) const
     {
-        return off16 ? (uint32_t)off16[s + 1]
-                     : (off32 ? off32[s + 1] : (cnt ? s * stride + (uint32_t)cnt[s] : (s + 1) * stride));
+        return end16 ? (uint32_t)end16[s]
+                     : (off16 ? (uint32_t)off16[s + 1]
+                              : (off32 ? off32[s + 1] : (cnt ? s * stride + (uint32_t)cnt[s] : (s + 1) * stride)));
     }
     __device__ __forceinline__ uint32_t size(uint32_t s) const { return end(s) - begin(s); }
     __device__ __forceinline__ uint32_t at(uint32_t pos) const { return ((uint32_t)val[pos] >> shift) & mask; }
@@ -121,7 +123,7 @@ struct PatchQuery
     uint32_t    n_cols;  // columns whose lists are built
     bool        ff2;     // FF on edge-manifold input, packed format: pair table instead of the EF CSR
     bool        ff3;     // FF read from the stored rows (patch_layout.h FLAG_FF): plain read + per-row count
-    bool        fanq;    // VV read from the stored one-ring fans (FLAG_FANS): plain read, oriented order
+    bool        fanq;    // VV / VF read from the stored one-ring fans (FLAG_FANS): plain read, oriented order
 
     // shared-memory bytes this op needs for a patch with the given maxima
     // (host side; the role of calc_shared_memory, rxmesh_static.inl:498-841)
@@ -147,15 +149,16 @@ struct PatchQuery
     __device__ __forceinline__ void plan(const PatchDesc& d, Smem& sm, bool with_owner, bool all_sources,
                                          bool edge_manifold = false)
     {
-        fanq = OP == OP_VV && edge_manifold && (d.flags & FLAG_FANS) && !all_sources;
+        fanq = (OP == OP_VV || OP == OP_VF) && edge_manifold && (d.flags & FLAG_FANS) && !all_sources;
         if (fanq) {
             // sections: fan_off (u16 offsets, bit 15 = closed fan) and fan_v; `edge_manifold` doubles as "stored sections
             // may be used" (k_query_csr passes false: it needs the ascending-id order of the transposes)
             n_rows = 0, n_cols = d.n_owned[ELEM_V];
-            loff_bytes = d.fanoff_bytes(), conn_bytes = d.fanv_bytes();
+            loff_bytes = d.fanoff_bytes(), conn_bytes = OP == OP_VV ? d.fanv_bytes() : d.fanf_bytes();
             s_loff     = sm.alloc<uint16_t>(loff_bytes / 2);
             s_conn     = sm.alloc<uint16_t>(conn_bytes / 2);
             s_off = nullptr, s_val = nullptr, s_off2 = nullptr, s_val2 = nullptr, s_own = nullptr, s_stash = nullptr;
+            if (OP == OP_VF) s_val = sm.alloc<uint16_t>(n_cols + 1u);  // list ends
             ff2 = ff3 = false;
             if (with_owner) {
                 s_own   = sm.alloc<uint32_t>(d.own_bytes(Tr::dst) / 4);
@@ -225,8 +228,8 @@ struct PatchQuery
     // thread 0 only, after mbar_arrive_expect_tx
     __device__ __forceinline__ void issue(const PatchDesc& d, const uint8_t* blob, uint64_t* bar, bool with_owner) const
     {
-        if (OP == OP_VV && fanq) {
-            if (conn_bytes) bulk_g2s(s_conn, blob + d.off_fanv(), conn_bytes, bar);
+        if ((OP == OP_VV || OP == OP_VF) && fanq) {
+            if (conn_bytes) bulk_g2s(s_conn, blob + (OP == OP_VV ? d.off_fanv() : d.off_fanf()), conn_bytes, bar);
             bulk_g2s(s_loff, blob + d.off_fanoff(), loff_bytes, bar);
             if (with_owner) {
                 if (d.own_bytes(Tr::dst)) bulk_g2s(s_own, blob + d.off_own(Tr::dst), d.own_bytes(Tr::dst), bar);
@@ -267,13 +270,26 @@ struct PatchQuery
         QueryResult    r;
         const uint32_t lim = all_sources ? d.n[Tr::src] : d.n_owned[Tr::src];
         r.n_src = lim, r.shift = 0, r.stride = 0, r.mask = 0xFFFFu;
-        r.off16 = nullptr, r.off32 = nullptr, r.cnt = nullptr;
+        r.off16 = nullptr, r.off32 = nullptr, r.cnt = nullptr, r.end16 = nullptr;
         const uint16_t* c = s_conn;
         if (OP == OP_VV && fanq) {
             for (uint32_t i = threadIdx.x; i <= lim; i += BT)
                 s_loff[i] &= FAN_OFF_MASK;  // drop the closed-fan flag: plain list bounds
             __syncthreads();
             r.off16 = s_loff, r.val = c, r.mask = 0xFFFFu;
+            return r;
+        }
+        if (OP == OP_VF && fanq) {
+            // fan_f[i] = face between fan vertices i and i + 1: an open fan has no face after its last vertex
+            for (uint32_t v = threadIdx.x; v < lim; v += BT) {
+                const uint32_t o = s_loff[v], b = o & FAN_OFF_MASK, e = s_loff[v + 1] & FAN_OFF_MASK;
+                s_val[v]         = (uint16_t)((o & FAN_CLOSED) || e == b ? e : e - 1u);
+            }
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i <= lim; i += BT)
+                s_loff[i] &= FAN_OFF_MASK;
+            __syncthreads();
+            r.off16 = s_loff, r.end16 = s_val, r.val = c, r.mask = 0xFFFFu;
             return r;
         }
         if (OP == OP_FF && ff3) {
