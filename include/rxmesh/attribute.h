@@ -1,6 +1,7 @@
 // rxmesh/attribute.h -- Attribute<T, HandleT> (include/rxmesh/attribute.h:56-731, attribute.cu:30-590) over the
-// C ABI: storage for OWNED elements in slot order (rxmesh_b200/csrc/patch_layout.h), host + device copies,
-// the reference's three layouts and its operator()(handle, attr) on both sides.
+// C ABI: storage for OWNED elements (AoS / AoSoA in slot order, rxmesh_b200/csrc/patch_layout.h; SoA = the
+// reference's tensor layout, a gap-free column-major #elements x #attributes matrix over linear ids,
+// attribute.h:249-261,406-421), host + device copies and the reference's operator()(handle, attr) on both sides.
 #pragma once
 #include <cstdio>
 #include <cstdlib>
@@ -54,8 +55,13 @@ class Attribute : public AttributeBase
         m_h            = (T*)rxm_attr_data(a, RXM_HOST);
         m_d            = (T*)rxm_attr_data(a, RXM_DEVICE);
         m_num_slots    = (uint32_t)rxm_mesh_info(mesh, RXM_INFO_NUM_SLOTS_V + HandleT::elem);
+        m_num_elems    = (uint32_t)rxm_mesh_info(mesh, RXM_INFO_NUM_VERTICES + HandleT::elem);
+        m_num_patches  = (uint32_t)rxm_mesh_info(mesh, RXM_INFO_NUM_PATCHES);
+        m_storage      = rxm_attr_count(a);
         m_h_slot_base  = rxm_mesh_slot_base(mesh, HandleT::elem);
         m_d_slot_base  = rxm_mesh_device_slot_base(mesh, HandleT::elem);
+        m_h_lin_base   = rxm_mesh_lin_base(mesh, HandleT::elem);
+        m_d_lin_base   = rxm_mesh_device_lin_base(mesh, HandleT::elem);
     }
     Attribute(const Attribute&) = default;  // shallow, like the reference (attribute.h:194)
 
@@ -66,7 +72,18 @@ class Attribute : public AttributeBase
     __host__ __device__ bool      is_device_allocated() const { return (m_location & DEVICE) == DEVICE; }
     __host__ __device__ bool      is_host_allocated() const { return (m_location & HOST) == HOST; }
     __host__ __device__ T*        data(locationT location = DEVICE) const { return (location & DEVICE) ? m_d : m_h; }
-    uint32_t size() const { return m_num_slots; }
+    // number of T values in the raw allocation (attribute.h:249-252); SoA: rows() * cols()
+    __host__ __device__ size_t storage_size() const { return (size_t)m_storage; }
+    // true when the raw storage is one global column-major matrix (attribute.h:258-261)
+    __host__ __device__ bool is_tensor_layout() const { return m_layout == SoA; }
+    // rows = mesh elements of this type, cols = attributes per element (attribute.h:113-120)
+    __host__ __device__ size_t   rows() const { return m_num_elems; }
+    __host__ __device__ size_t   cols() const { return m_nattr; }
+    __host__ __device__ uint32_t size() const { return m_num_elems; }
+    __host__ __device__ uint32_t get_num_patches() const { return m_num_patches; }
+    // owned elements of patch p (the reference's size(p), attribute.h:692) and the linear-id prefix behind it
+    __host__ __device__ uint32_t size(const uint32_t p) const { return lin_base()[p + 1] - lin_base()[p]; }
+    __host__ __device__ const uint32_t* lin_base(locationT location) const { return (location & DEVICE) ? m_d_lin_base : m_h_lin_base; }
     rxm_attr* c_handle() const { return m_attr; }
 
     void reset(const T value, locationT location, cudaStream_t stream = NULL) { detail::rxm_check(rxm_attr_reset(m_attr, &value, (int)location, stream)); }
@@ -86,10 +103,30 @@ class Attribute : public AttributeBase
     __host__ __device__ __forceinline__ T& operator()(const HandleT handle, const uint32_t attr = 0) const
     {
 #ifdef __CUDA_ARCH__
-        return m_d[index(m_d_slot_base, handle.patch_id(), handle.local_id(), attr)];
+        return m_d[index(m_d_slot_base, m_d_lin_base, handle.patch_id(), handle.local_id(), attr)];
 #else
-        return m_h[index(m_h_slot_base, handle.patch_id(), handle.local_id(), attr)];
+        return m_h[index(m_h_slot_base, m_h_lin_base, handle.patch_id(), handle.local_id(), attr)];
 #endif
+    }
+    // operator()(i, j): element with LINEAR id i, attribute j (attribute.h:109-111), any layout
+    __host__ __device__ __forceinline__ T& operator()(const size_t i, const size_t j = 0) const
+    {
+#ifdef __CUDA_ARCH__
+        const uint32_t* lb = m_d_lin_base;
+        T*              base = m_d;
+        const uint32_t* sb = m_d_slot_base;
+#else
+        const uint32_t* lb = m_h_lin_base;
+        T*              base = m_h;
+        const uint32_t* sb = m_h_slot_base;
+#endif
+        if (m_layout == SoA) return base[j * m_num_elems + i];
+        uint32_t lo = 0, hi = m_num_patches;  // the patch whose linear-id range holds i
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) / 2;
+            if (lb[mid] <= i) lo = mid; else hi = mid;
+        }
+        return base[index(sb, lb, lo, (uint32_t)(i - lb[lo]), (uint32_t)j)];
     }
     template <int N>
     __host__ __device__ __forceinline__ glm::vec<N, T> to_glm(const HandleT& handle) const
@@ -105,18 +142,29 @@ class Attribute : public AttributeBase
     }
 
    private:
-    __host__ __device__ __forceinline__ uint64_t index(const uint32_t* sb, uint32_t p, uint32_t lid, uint32_t a) const
+    __host__ __device__ const uint32_t* lin_base() const
     {
+#ifdef __CUDA_ARCH__
+        return m_d_lin_base;
+#else
+        return m_h_lin_base;
+#endif
+    }
+    __host__ __device__ __forceinline__ uint64_t index(const uint32_t* sb, const uint32_t* lb, uint32_t p, uint32_t lid,
+                                                       uint32_t a) const
+    {
+        if (m_layout == SoA) return (uint64_t)a * m_num_elems + lb[p] + lid;  // attribute.h:406-421
         const uint32_t b = sb[p];
         if (m_layout == AoS) return (uint64_t)(b + lid) * m_nattr + a;
-        if (m_layout == SoA) return (uint64_t)a * m_num_slots + b + lid;
         return (uint64_t)b * m_nattr + (uint64_t)a * (sb[p + 1] - b) + lid;
     }
     char*                     m_name = nullptr;
     rxm_attr*                 m_attr = nullptr;
     T *                       m_h = nullptr, *m_d = nullptr;
     const uint32_t *          m_h_slot_base = nullptr, *m_d_slot_base = nullptr;
-    uint32_t                  m_num_slots = 0, m_nattr = 0;
+    const uint32_t *          m_h_lin_base = nullptr, *m_d_lin_base = nullptr;
+    uint64_t                  m_storage = 0;
+    uint32_t                  m_num_slots = 0, m_num_elems = 0, m_num_patches = 0, m_nattr = 0;
     layoutT                   m_layout   = AoSoA;
     locationT                 m_location = LOCATION_NONE;
 };

@@ -289,7 +289,7 @@ class RXMeshStatic
         static_assert(sizeof(T) == 4, "get_boundary_vertices needs a 32-bit attribute");
         detail::rxm_check(rxm_boundary_vertices(m_mesh, boundary_v.c_handle(), stream));
         if (!std::is_integral_v<T>)  // the kernel writes integer flags; convert in place for floating-point attributes
-            detail::flags_to_value<T><<<(boundary_v.size() + 255) / 256, 256, 0, stream>>>(boundary_v.data(DEVICE), boundary_v.size());
+            detail::flags_to_value<T><<<((uint32_t)boundary_v.storage_size() + 255) / 256, 256, 0, stream>>>(boundary_v.data(DEVICE), (uint32_t)boundary_v.storage_size());
         if (move_to_host) boundary_v.move(DEVICE, HOST, stream);
     }
     // export_obj (rxmesh_static.inl:365-397): vertices in linear-id order, faces in linear-id order with 1-based

@@ -63,6 +63,14 @@ using locationT = uint32_t;
 enum : locationT { LOCATION_NONE = 0x00, HOST = 0x01, DEVICE = 0x02, LOCATION_ALL = 0x0F };
 using layoutT = uint32_t;
 enum : layoutT { AoS = 0x00, AoSoA = 0x01, SoA = 0x02 };
+inline std::string layout_to_string(const layoutT layout)  // types.h:94-108
+{
+    return layout == AoS ? "AoS" : (layout == AoSoA ? "AoSoA" : (layout == SoA ? "SoA" : ""));
+}
+inline std::string location_to_string(const locationT location)  // types.h:63-79
+{
+    return location == LOCATION_NONE ? "NONE" : (location == HOST ? "HOST" : (location == DEVICE ? "DEVICE" : (location == LOCATION_ALL ? "ALL" : "")));
+}
 
 enum class Op { INVALID = -1, V = 0, E = 1, F = 2, VV = 3, VE = 4, VF = 5, FV = 6, FE = 7, FF = 8, EV = 9, EE = 10, EF = 11, EVDiamond = 12 };
 

@@ -120,6 +120,9 @@ const uint32_t* rxm_mesh_face_edges(const rxm_mesh* m);
 
 /* device copy of rxm_mesh_slot_base (what Attribute::operator() indexes on the device) */
 const uint32_t* rxm_mesh_device_slot_base(const rxm_mesh* m, int elem);
+/* device copy of rxm_mesh_lin_base: the SoA (tensor) layout indexes data[attr * N + lin_base[patch] + local id],
+ * the reference's m_d_linear_id_element_prefix (attribute.h:406-421,623-630) */
+const uint32_t* rxm_mesh_device_lin_base(const rxm_mesh* m, int elem);
 /* get_context() (rxmesh_static.h): copies the by-value kernel argument (rxm::MeshView of
  * rxmesh_b200/csrc/patch_layout.h, the counterpart of Context, context.h:15-441) into out_view;
  * out_bytes must equal sizeof(rxm::MeshView). Used by the C++ header shim (include/rxmesh/). */
@@ -131,12 +134,14 @@ int rxm_mesh_launch_box(const rxm_mesh* m, int op, uint32_t* blocks, uint32_t* t
 
 /* ----------------------------------------------------------- attributes ---- */
 /* add_{vertex,edge,face}_attribute<T>(name, n, location, layout) (rxmesh_static.h:608-806; attribute.cu:30-83,
- * 531-590). elem_bytes in {1,2,4,8}. Storage holds owned elements only: num_slots(elem) * num_attr values. */
+ * 531-590). elem_bytes in {1,2,4,8}. Storage holds owned elements only: num_slots(elem) * num_attr values in slot
+ * order for AoS / AoSoA (a patch's slots are padded to a multiple of 4); SoA is the reference's tensor layout, a
+ * gap-free column-major num_elements x num_attr matrix indexed by linear id (attribute.h:249-261,406-421). */
 int rxm_attr_create(rxm_mesh* m, int elem, uint32_t elem_bytes, uint32_t num_attr, int location, int layout,
                     rxm_attr** out);
 void     rxm_attr_destroy(rxm_attr* a);                                /* remove_attribute / release */
 void*    rxm_attr_data(rxm_attr* a, int location);                     /* Attribute::data(location) */
-uint64_t rxm_attr_count(const rxm_attr* a);                            /* num_slots * num_attr */
+uint64_t rxm_attr_count(const rxm_attr* a);                            /* values stored: storage_size(), attribute.h:249 */
 int      rxm_attr_reset(rxm_attr* a, const void* value, int location, void* stream); /* attribute.cu:306-357 */
 int      rxm_attr_move(rxm_attr* a, int source, int target, void* stream);           /* attribute.cu:359-364 */
 int      rxm_attr_copy_from(rxm_attr* dst, rxm_attr* src, int source, int target, void* stream);

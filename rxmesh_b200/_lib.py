@@ -47,6 +47,7 @@ SYMBOLS = {
     "rxm_mesh_edges": (u32p, [C.c_void_p]),
     "rxm_mesh_face_edges": (u32p, [C.c_void_p]),
     "rxm_mesh_device_slot_base": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "rxm_mesh_device_lin_base": (C.c_void_p, [C.c_void_p, C.c_int]),
     "rxm_mesh_view": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "rxm_mesh_launch_box": (C.c_int, [C.c_void_p, C.c_int, u32p, u32p, u32p]),
     "rxm_attr_create": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int,

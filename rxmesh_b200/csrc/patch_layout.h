@@ -217,7 +217,8 @@ enum : uint32_t
 {
     LAYOUT_AOS   = 0,  // data[(slot) * nattr + a]
     LAYOUT_AOSOA = 1,  // data[slot_base(p) * nattr + a * cap(p) + lid]  (patch-local SoA; reference default)
-    LAYOUT_SOA   = 2   // data[a * num_slots + slot]
+    LAYOUT_SOA   = 2   // data[a * num_elems + linear_id]: the reference's tensor layout (attribute.h:406-421), a gap-free
+                       // column-major #elements x nattr matrix indexed by linear id -- no padding slots
 };
 
 // Device/host view of an attribute (shallow, by value into kernels like the
@@ -230,20 +231,23 @@ struct AttrView
     uint32_t        num_slots;
     uint32_t        nattr;
     uint32_t        layout;
+    const uint32_t* lin_base;   // [num_patches+1] linear-id prefix of this element type (SoA only)
+    uint32_t        num_elems;  // elements of this type (SoA only)
 
     RXM_HD uint64_t index(uint32_t patch, uint32_t lid, uint32_t a) const
     {
+        if (layout == LAYOUT_SOA) return (uint64_t)a * num_elems + lin_base[patch] + lid;
         const uint32_t b = slot_base[patch];
         if (layout == LAYOUT_AOS) return (uint64_t)(b + lid) * nattr + a;
-        if (layout == LAYOUT_SOA) return (uint64_t)a * num_slots + b + lid;
         const uint32_t cap = slot_base[patch + 1] - b;
         return (uint64_t)b * nattr + (uint64_t)a * cap + lid;
     }
-    // same, when the caller already knows slot base and capacity (no global load)
-    RXM_HD uint64_t index_known(uint32_t b, uint32_t cap, uint32_t lid, uint32_t a) const
+    // same, when the caller already knows the patch's slot base, capacity and linear-id base (no global load).
+    // SoA has storage for the n_owned elements of a patch only: callers never pass a padding slot (lid >= n_owned).
+    RXM_HD uint64_t index_known(uint32_t b, uint32_t cap, uint32_t lb, uint32_t lid, uint32_t a) const
     {
         if (layout == LAYOUT_AOS) return (uint64_t)(b + lid) * nattr + a;
-        if (layout == LAYOUT_SOA) return (uint64_t)a * num_slots + b + lid;
+        if (layout == LAYOUT_SOA) return (uint64_t)a * num_elems + lb + lid;
         return (uint64_t)b * nattr + (uint64_t)a * cap + lid;
     }
 };

@@ -38,6 +38,7 @@ struct rxm_mesh
     PatchDesc*   d_desc    = nullptr;
     uint8_t*     d_topo    = nullptr;
     uint32_t*    d_slot_base[3] = {nullptr, nullptr, nullptr};
+    uint32_t*    d_lin_base[3]  = {nullptr, nullptr, nullptr};  // [P+1] linear-id prefixes (SoA attribute indexing)
     uint32_t*    d_s2g[3]       = {nullptr, nullptr, nullptr};
     uint64_t     topo_bytes   = 0;
     uint32_t     active_first = 0, active_count = 0;  // patches the kernels run on (a shard's real patches)
@@ -78,7 +79,7 @@ struct rxm_attr
     int       elem;
     uint32_t  elem_bytes, nattr;
     int       layout;
-    uint64_t  count;  // num_slots * nattr
+    uint64_t  count;  // T values in the storage: num_slots * nattr; SoA (tensor layout): num_elems * nattr
     void*     h = nullptr;
     void*     d = nullptr;
     bool      h_pinned = false;
@@ -93,7 +94,19 @@ static AttrView<T> view_of(rxm_attr* a)
     v.num_slots = a->m->h.num_slots[a->elem];
     v.nattr     = a->nattr;
     v.layout    = (uint32_t)a->layout;
+    v.lin_base  = a->m->d_lin_base[a->elem];
+    v.num_elems = a->m->h.num_elems[a->elem];
     return v;
+}
+
+// slot / linear-id prefixes of the patch range [p0, p0 + np) on the device
+static SlotMap slot_map(const rxm_mesh* m, int t, uint32_t p0, uint32_t np)
+{
+    return SlotMap{m->d_slot_base[t] + p0, m->d_lin_base[t] + p0, np, m->h.num_slots[t], m->h.num_elems[t]};
+}
+static SlotMap slot_map(const rxm_mesh* m, int t)
+{
+    return slot_map(m, t, 0, m->h.num_patches);
 }
 
 extern "C" {
@@ -244,6 +257,8 @@ int rxm_mesh_to_device(rxm_mesh* m)
     for (int t = 0; t < 3; ++t) {
         CU(cudaMalloc(&m->d_slot_base[t], h.slot_base[t].size() * 4));
         CU(cudaMemcpy(m->d_slot_base[t], h.slot_base[t].data(), h.slot_base[t].size() * 4, cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&m->d_lin_base[t], h.lin_base[t].size() * 4));
+        CU(cudaMemcpy(m->d_lin_base[t], h.lin_base[t].data(), h.lin_base[t].size() * 4, cudaMemcpyHostToDevice));
         CU(cudaMalloc(&m->d_s2g[t], std::max<size_t>(h.slot_to_global[t].size(), 1) * 4));
         CU(cudaMemcpy(m->d_s2g[t], h.slot_to_global[t].data(), h.slot_to_global[t].size() * 4, cudaMemcpyHostToDevice));
     }
@@ -308,6 +323,7 @@ void rxm_mesh_destroy(rxm_mesh* m)
         cudaFree(m->d_topo);
         for (int t = 0; t < 3; ++t) {
             cudaFree(m->d_slot_base[t]);
+            cudaFree(m->d_lin_base[t]);
             cudaFree(m->d_s2g[t]);
         }
         for (void* b : m->d_stage)
@@ -423,6 +439,10 @@ const uint32_t* rxm_mesh_device_slot_base(const rxm_mesh* m, int t)
 {
     return (m && m->on_device && t >= 0 && t < 3) ? m->d_slot_base[t] : nullptr;
 }
+const uint32_t* rxm_mesh_device_lin_base(const rxm_mesh* m, int t)
+{
+    return (m && m->on_device && t >= 0 && t < 3) ? m->d_lin_base[t] : nullptr;
+}
 
 int rxm_mesh_view(const rxm_mesh* m, void* out_view, uint32_t out_bytes)
 {
@@ -477,7 +497,7 @@ int rxm_attr_create(rxm_mesh* m, int elem, uint32_t elem_bytes, uint32_t nattr, 
     a->elem_bytes = elem_bytes;
     a->nattr      = nattr;
     a->layout     = layout;
-    a->count      = (uint64_t)m->h.num_slots[elem] * nattr;
+    a->count      = (uint64_t)(layout == RXM_SOA ? m->h.num_elems[elem] : m->h.num_slots[elem]) * nattr;
     const size_t bytes = std::max<size_t>(a->count * elem_bytes, 16);
     if (location & RXM_DEVICE) {
         if (!m->on_device) {
@@ -620,9 +640,8 @@ int rxm_attr_from_global_device(rxm_attr* a, const void* dev_global, void* strea
 {
     if (!a || !a->d || !dev_global) return fail(RXM_ERR_INVALID, "rxm_attr_from_global_device: bad argument");
     rxm_mesh* m = a->m;
-    cudaError_t e = launch_permute_to_slots(dev_global, a->d, m->d_s2g[a->elem], m->h.num_slots[a->elem],
-                                            a->elem_bytes, a->nattr, a->layout, m->d_slot_base[a->elem],
-                                            m->h.num_patches, (cudaStream_t)stream);
+    cudaError_t e = launch_permute_to_slots(dev_global, a->d, m->d_s2g[a->elem], slot_map(m, a->elem), a->elem_bytes,
+                                            a->nattr, a->layout, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(RXM_ERR_CUDA, std::string("permute: ") + cudaGetErrorString(e));
     return RXM_OK;
 }
@@ -631,9 +650,8 @@ int rxm_attr_to_global_device(rxm_attr* a, void* dev_global, void* stream)
 {
     if (!a || !a->d || !dev_global) return fail(RXM_ERR_INVALID, "rxm_attr_to_global_device: bad argument");
     rxm_mesh* m = a->m;
-    cudaError_t e = launch_permute_to_global(a->d, dev_global, m->d_s2g[a->elem], m->h.num_slots[a->elem],
-                                             a->elem_bytes, a->nattr, a->layout, m->d_slot_base[a->elem],
-                                             m->h.num_patches, (cudaStream_t)stream);
+    cudaError_t e = launch_permute_to_global(a->d, dev_global, m->d_s2g[a->elem], slot_map(m, a->elem), a->elem_bytes,
+                                             a->nattr, a->layout, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(RXM_ERR_CUDA, std::string("permute: ") + cudaGetErrorString(e));
     return RXM_OK;
 }
@@ -644,16 +662,18 @@ static void host_permute(rxm_attr* a, void* global, bool to_slots)
     const HostMesh& h  = a->m->h;
     const int       t  = a->elem;
     const uint32_t  eb = a->elem_bytes, na = a->nattr;
-    AttrView<uint8_t> v{nullptr, h.slot_base[t].data(), h.num_slots[t], na, (uint32_t)a->layout};
+    AttrView<uint8_t> v{nullptr, h.slot_base[t].data(), h.num_slots[t], na, (uint32_t)a->layout, h.lin_base[t].data(),
+                        h.num_elems[t]};
     uint8_t* S = (uint8_t*)a->h;
     uint8_t* G = (uint8_t*)global;
 #pragma omp parallel for schedule(static)
     for (int64_t p = 0; p < (int64_t)h.num_patches; ++p) {
-        const uint32_t b = h.slot_base[t][p], cap = h.slot_base[t][p + 1] - b;
-        for (uint32_t lid = 0; lid < cap; ++lid) {
+        const uint32_t b = h.slot_base[t][p], cap = h.slot_base[t][p + 1] - b, lb = h.lin_base[t][p];
+        const uint32_t n = a->layout == RXM_SOA ? h.lin_base[t][p + 1] - lb : cap;  // SoA: no padding slots
+        for (uint32_t lid = 0; lid < n; ++lid) {
             const uint32_t g = h.slot_to_global[t][b + lid];
             for (uint32_t k = 0; k < na; ++k) {
-                const uint64_t si = v.index_known(b, cap, lid, k);
+                const uint64_t si = v.index_known(b, cap, lb, lid, k);
                 if (to_slots) {
                     if (g != INVALID32_)
                         memcpy(S + si * eb, G + ((uint64_t)g * na + k) * eb, eb);
@@ -753,6 +773,8 @@ int rxm_query_consume(rxm_mesh* m, int op, rxm_attr* in, rxm_attr* out, void* st
     if (!in || !out || !in->d || !out->d || in->elem != op_dst(op) || out->elem != op_src(op) ||
         in->elem_bytes != 4 || out->elem_bytes != 4 || in->nattr != 1 || out->nattr != 1)
         return fail(RXM_ERR_INVALID, "rxm_query_consume: in = 1 x fp32 on the output type, out = 1 x fp32 on the source type");
+    if (in->layout == RXM_SOA || out->layout == RXM_SOA)  // the kernels stream the patches' slot slices
+        return fail(RXM_ERR_INVALID, "rxm_query_consume: SoA (tensor-layout) attributes are stored by linear id; use AoS or AoSoA");
     const char* why = nullptr;
     cudaError_t e   = launch_query_consume(op, m->view, m->lim, view_of<float>(in), view_of<float>(out),
                                            (cudaStream_t)stream, &why);
@@ -784,8 +806,7 @@ static int aos_standin(rxm_mesh* m, rxm_attr* a, int idx, bool load, void* strea
     int rc = get_scratch(m, idx, out);
     if (rc) return rc;
     if (load) {
-        cudaError_t e = launch_relayout(a->d, (*out)->d, m->d_slot_base[RXM_V], m->h.num_patches, m->h.num_slots[RXM_V], 3,
-                                        (uint32_t)a->layout, RXM_AOS, (cudaStream_t)stream);
+        cudaError_t e = launch_relayout(a->d, (*out)->d, slot_map(m, RXM_V), 3, (uint32_t)a->layout, RXM_AOS, (cudaStream_t)stream);
         if (e != cudaSuccess) return fail(RXM_ERR_CUDA, std::string("relayout: ") + cudaGetErrorString(e));
     }
     return RXM_OK;
@@ -793,8 +814,7 @@ static int aos_standin(rxm_mesh* m, rxm_attr* a, int idx, bool load, void* strea
 static int aos_writeback(rxm_mesh* m, rxm_attr* a, rxm_attr* standin, void* stream)
 {
     if (a == standin) return RXM_OK;
-    cudaError_t e = launch_relayout(standin->d, a->d, m->d_slot_base[RXM_V], m->h.num_patches, m->h.num_slots[RXM_V], 3, RXM_AOS,
-                                    (uint32_t)a->layout, (cudaStream_t)stream);
+    cudaError_t e = launch_relayout(standin->d, a->d, slot_map(m, RXM_V), 3, RXM_AOS, (uint32_t)a->layout, (cudaStream_t)stream);
     return e == cudaSuccess ? RXM_OK : fail(RXM_ERR_CUDA, std::string("relayout: ") + cudaGetErrorString(e));
 }
 
@@ -955,6 +975,12 @@ int rxm_boundary_vertices(rxm_mesh* m, rxm_attr* flag, void* stream)
     if (rc) return rc;
     if (!flag || !flag->d || flag->elem != RXM_V || flag->elem_bytes != 4 || flag->nattr != 1)
         return fail(RXM_ERR_INVALID, "rxm_boundary_vertices: flag must be a device 1 x u32 vertex attribute");
+    if (flag->layout == RXM_SOA) {  // the kernel addresses flags by slot: run on a slot-ordered stand-in, copy by linear id
+        if (!m->scratch[6] && (rc = rxm_attr_create(m, RXM_V, 4, 1, RXM_DEVICE, RXM_AOS, &m->scratch[6]))) return rc;
+        if ((rc = rxm_boundary_vertices(m, m->scratch[6], stream))) return rc;
+        cudaError_t e = launch_relayout(m->scratch[6]->d, flag->d, slot_map(m, RXM_V), 1, RXM_AOS, RXM_SOA, (cudaStream_t)stream);
+        return e == cudaSuccess ? RXM_OK : fail(RXM_ERR_CUDA, std::string("relayout: ") + cudaGetErrorString(e));
+    }
     const uint32_t zero = 0;
     rc                  = rxm_attr_reset(flag, &zero, RXM_DEVICE, stream);
     if (rc) return rc;
@@ -1013,16 +1039,16 @@ static int pipelined_host_call(rxm_mesh* m, rxm_attr* ain, rxm_attr* aout, const
     uint32_t q = 0;
     for (uint32_t c = 0; c < K; ++c) {
         CU(cudaStreamWaitEvent(S, pp.up[c], 0));
-        cudaError_t e = launch_permute_to_slots(din, ain->d, m->d_s2g[ti], m->h.num_slots[ti], ain->elem_bytes, ain->nattr,
-                                                ain->layout, m->d_slot_base[ti] + P.pb[c], P.pb[c + 1] - P.pb[c], S);
+        cudaError_t e = launch_permute_to_slots(din, ain->d, m->d_s2g[ti], slot_map(m, ti, P.pb[c], P.pb[c + 1] - P.pb[c]),
+                                                ain->elem_bytes, ain->nattr, ain->layout, S);
         if (e != cudaSuccess) return fail(RXM_ERR_CUDA, std::string("permute: ") + cudaGetErrorString(e));
         while (q < K && P.need[q] <= c) {
             MeshView v    = m->view;
             v.desc        = m->d_desc + P.pb[q];
             v.num_patches = P.pb[q + 1] - P.pb[q];
             if ((rc = launch(v, S))) return rc;
-            e = launch_permute_to_global(aout->d, dout, m->d_s2g[to], m->h.num_slots[to], aout->elem_bytes, aout->nattr,
-                                         aout->layout, m->d_slot_base[to] + P.pb[q], P.pb[q + 1] - P.pb[q], S);
+            e = launch_permute_to_global(aout->d, dout, m->d_s2g[to], slot_map(m, to, P.pb[q], P.pb[q + 1] - P.pb[q]),
+                                         aout->elem_bytes, aout->nattr, aout->layout, S);
             if (e != cudaSuccess) return fail(RXM_ERR_CUDA, std::string("permute: ") + cudaGetErrorString(e));
             CU(cudaEventRecord(pp.comp[q], S));
             CU(cudaStreamWaitEvent(pp.d2h, pp.comp[q], 0));
@@ -1152,7 +1178,8 @@ void rxm_free(void* p)
 static int rows_check(rxm_attr* a, const char* who)
 {
     if (!a || !a->d) return fail(RXM_ERR_INVALID, std::string(who) + ": attribute has no device storage");
-    if (a->layout != RXM_AOS && a->nattr != 1) return fail(RXM_ERR_INVALID, std::string(who) + ": AoS attributes only");
+    if (a->layout == RXM_SOA || (a->layout != RXM_AOS && a->nattr != 1))  // rows are addressed by slot
+        return fail(RXM_ERR_INVALID, std::string(who) + ": AoS attributes only");
     if ((a->elem_bytes * a->nattr) % 4) return fail(RXM_ERR_INVALID, std::string(who) + ": row size must be a multiple of 4 bytes");
     return RXM_OK;
 }

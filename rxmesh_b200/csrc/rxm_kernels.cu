@@ -87,12 +87,12 @@ __global__ void __launch_bounds__(BT) k_query_store(MeshView mv, AttrView<uint64
     const QueryResult r  = q.compute(d, warp_tmp, false, false);
     const OwnerTable  ot = q.owner_table(d);
     constexpr uint32_t S = OpTraits<OP>::src;
-    const uint32_t sb_in = d.slot_base[S], cap_in = d.slot_cap(S);
+    const uint32_t sb_in = d.slot_base[S], cap_in = d.slot_cap(S), lb_in = d.lin_base[S];
     for (uint32_t s = threadIdx.x; s < r.n_src; s += BT) {
-        in.data[in.index_known(sb_in, cap_in, s, 0)] = ((uint64_t)d.patch_id << 32) | s;
+        in.data[in.index_known(sb_in, cap_in, lb_in, s, 0)] = ((uint64_t)d.patch_id << 32) | s;
         const uint32_t b = r.begin(s), n = min(r.size(s), out.nattr);
         for (uint32_t i = 0; i < n; ++i)
-            out.data[out.index_known(sb_in, cap_in, s, i)] = ot.handle(r.at(b + i));
+            out.data[out.index_known(sb_in, cap_in, lb_in, s, i)] = ot.handle(r.at(b + i));
     }
 }
 
@@ -1248,13 +1248,14 @@ __global__ void __launch_bounds__(256) k_reduce_stage1(MeshView mv, AttrView<flo
     for (uint32_t p = blockIdx.x; p < mv.num_patches; p += gridDim.x) {
         const PatchDesc* d   = mv.desc + p;
         const uint32_t   no  = d->n_owned[elem], sb = d->slot_base[elem], cap = (no + 3u) & ~3u, pid = d->patch_id;
+        const uint32_t   lb  = d->lin_base[elem];
         const uint32_t   na  = attr_id == INVALID32_ ? a.nattr : 1u;
         for (uint32_t i = threadIdx.x; i < no * na; i += blockDim.x) {
             const uint32_t lid = i % no, k = attr_id == INVALID32_ ? i / no : attr_id;
-            const float    x = a.data[a.index_known(sb, cap, lid, k)];
+            const float    x = a.data[a.index_known(sb, cap, lb, lid, k)];
             RedPair        c;
             if (kind == 0)
-                c = RedPair{(double)x * (double)b.data[b.index_known(sb, cap, lid, k)], 0};
+                c = RedPair{(double)x * (double)b.data[b.index_known(sb, cap, lb, lid, k)], 0};
             else if (kind == 1)
                 c = RedPair{(double)x * (double)x, 0};
             else
@@ -1334,26 +1335,34 @@ __global__ void __launch_bounds__(BT) k_boundary(MeshView mv, uint32_t* __restri
 // same slots, another layout (AoS <-> AoSoA <-> SoA): lets the fixed-function kernels, which read AoS, serve attributes
 // created with the reference's default layout
 __global__ void k_relayout(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const uint32_t* __restrict__ slot_base,
-                           uint32_t num_patches, uint32_t num_slots, uint32_t nattr, uint32_t layout_src, uint32_t layout_dst)
+                           const uint32_t* __restrict__ lin_base, uint32_t num_patches, uint32_t num_slots, uint32_t num_elems,
+                           uint32_t nattr, uint32_t layout_src, uint32_t layout_dst)
 {
-    AttrView<uint32_t> vs{nullptr, slot_base, num_slots, nattr, layout_src}, vd{nullptr, slot_base, num_slots, nattr, layout_dst};
+    AttrView<uint32_t> vs{nullptr, slot_base, num_slots, nattr, layout_src, lin_base, num_elems},
+        vd{nullptr, slot_base, num_slots, nattr, layout_dst, lin_base, num_elems};
+    const bool owned_only = layout_src == LAYOUT_SOA || layout_dst == LAYOUT_SOA;  // SoA has no padding slots
     for (uint32_t p = blockIdx.x; p < num_patches; p += gridDim.x) {
-        const uint32_t b = slot_base[p], cap = slot_base[p + 1] - b;
-        for (uint32_t i = threadIdx.x; i < cap * nattr; i += blockDim.x) {
+        const uint32_t b = slot_base[p], cap = slot_base[p + 1] - b, lb = lin_base[p];
+        const uint32_t n = owned_only ? lin_base[p + 1] - lb : cap;
+        for (uint32_t i = threadIdx.x; i < n * nattr; i += blockDim.x) {
             const uint32_t lid = i / nattr, a = i % nattr;
-            dst[vd.index_known(b, cap, lid, a)] = src[vs.index_known(b, cap, lid, a)];
+            dst[vd.index_known(b, cap, lb, lid, a)] = src[vs.index_known(b, cap, lb, lid, a)];
         }
+        if (owned_only && layout_dst != LAYOUT_SOA)  // the source has no padding slots: define them in the copy
+            for (uint32_t i = n * nattr + threadIdx.x; i < cap * nattr; i += blockDim.x)
+                dst[vd.index_known(b, cap, lb, i / nattr, i % nattr)] = 0u;
     }
 }
 
 template <typename T, bool TO_SLOTS>
 __global__ void k_permute(const T* __restrict__ src, T* __restrict__ dst, const uint32_t* __restrict__ slot_to_global,
-                          const uint32_t* __restrict__ slot_base, uint32_t num_patches, uint32_t num_slots,
-                          uint32_t nattr, uint32_t layout)
+                          const uint32_t* __restrict__ slot_base, const uint32_t* __restrict__ lin_base, uint32_t num_patches,
+                          uint32_t num_slots, uint32_t num_elems, uint32_t nattr, uint32_t layout)
 {
     for (uint32_t p = blockIdx.x; p < num_patches; p += gridDim.x) {
         const uint32_t b = slot_base[p], cap = slot_base[p + 1] - b;
-        for (uint32_t i = threadIdx.x; i < cap * nattr; i += blockDim.x) {
+        const uint32_t lb = lin_base[p], n = layout == LAYOUT_SOA ? lin_base[p + 1] - lb : cap;  // SoA: owned elements only
+        for (uint32_t i = threadIdx.x; i < n * nattr; i += blockDim.x) {
             // enumerate in the slot-side storage order so the slot side is coalesced
             uint32_t lid, a;
             uint64_t sidx;
@@ -1361,8 +1370,8 @@ __global__ void k_permute(const T* __restrict__ src, T* __restrict__ dst, const 
                 lid = i / nattr, a = i % nattr;
                 sidx = (uint64_t)(b + lid) * nattr + a;
             } else if (layout == LAYOUT_SOA) {
-                a = i / cap, lid = i % cap;
-                sidx = (uint64_t)a * num_slots + b + lid;
+                a = i / n, lid = i % n;
+                sidx = (uint64_t)a * num_elems + lb + lid;
             } else {
                 a = i / cap, lid = i % cap;
                 sidx = (uint64_t)b * nattr + (uint64_t)a * cap + lid;
@@ -1467,7 +1476,7 @@ int pick_kmax(uint32_t nnz)
 #define RXM_LAUNCH_ONE(KERNEL, OPV, KM, PK, ...)                                         \
     do {                                                                                 \
         using Q = dev::PatchQuery<OPV, BT, KM, PK>;                                      \
-        smem    = Q::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, true) + extra_smem(OPV); \
+        smem    = Q::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, true, stored_ff) + extra_smem(OPV); \
         auto kern = KERNEL<OPV, KM, PK>;                                                 \
         e         = set_smem(kern, smem);                                                \
         if (e != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");    \
@@ -1556,6 +1565,7 @@ cudaError_t launch_query_store(int op, const MeshView& mv, const KernelLimits& l
     if (op == OP_FF && lim.max_face_adjacent_faces > 6) RXM_FAIL("FF: more than 6 adjacent faces per face");
     uint32_t    smem = 0;
     cudaError_t e    = cudaSuccess;
+    const uint32_t stored_ff  = mv.edge_manifold ? lim.max_owned[ELEM_F] : 0u;  // FF from the stored rows (plan(): ff3)
     auto        extra_smem = [&](int) { return 0u; };
     if (mv.packed)
         RXM_LAUNCH_OP(k_query_store, 1, true, mv, in, out);
@@ -1632,6 +1642,7 @@ cudaError_t launch_query_consume(int op, const MeshView& mv, const KernelLimits&
     if (op == OP_FF && lim.max_face_adjacent_faces > 6) RXM_FAIL("FF: more than 6 adjacent faces per face");
     uint32_t    smem = 0;
     cudaError_t e    = cudaSuccess;
+    const uint32_t stored_ff = mv.edge_manifold ? lim.max_owned[ELEM_F] : 0u;  // FF from the stored rows (plan(): ff3)
     auto extra_smem = [&](int opv) {
         uint32_t dst = 0;
         switch (opv) {
@@ -1809,6 +1820,7 @@ cudaError_t launch_query_csr(int op, const MeshView& mv, const KernelLimits& lim
     if (op == OP_FF && lim.max_face_adjacent_faces > 6) RXM_FAIL("FF: more than 6 adjacent faces per face");
     uint32_t    smem = 0;
     cudaError_t e    = cudaSuccess;
+    const uint32_t stored_ff  = 0;  // k_query_csr plans the generic path (gap-free ascending lists)
     auto        extra_smem = [&](int) { return 0u; };
     if (mv.packed)
         RXM_LAUNCH_OP(k_query_csr, 1, true, mv, patch_nnz_off, csr_off, csr_val);
@@ -1830,55 +1842,50 @@ cudaError_t launch_bilateral_step(const uint32_t* csr_off, const uint32_t* csr_v
 }
 
 template <bool TO_SLOTS>
-static cudaError_t permute_dispatch(const void* src, void* dst, const uint32_t* s2g, uint32_t num_slots,
-                                    uint32_t elem_bytes, uint32_t nattr, uint32_t layout, const uint32_t* slot_base,
-                                    uint32_t num_patches, cudaStream_t stream)
+static cudaError_t permute_dispatch(const void* src, void* dst, const uint32_t* s2g, const SlotMap& sm, uint32_t elem_bytes,
+                                    uint32_t nattr, uint32_t layout, cudaStream_t stream)
 {
-    const uint32_t grid = std::min<uint32_t>(num_patches, 148u * 16u);
+    const uint32_t grid = std::min<uint32_t>(sm.num_patches, 148u * 16u);
     if (grid == 0) return cudaSuccess;
+#define RXM_PERMUTE(T)                                                                                              \
+    k_permute<T, TO_SLOTS><<<grid, 128, 0, stream>>>((const T*)src, (T*)dst, s2g, sm.slot_base, sm.lin_base,        \
+                                                     sm.num_patches, sm.num_slots, sm.num_elems, nattr, layout)
     if (elem_bytes == 4)
-        k_permute<uint32_t, TO_SLOTS><<<grid, 128, 0, stream>>>((const uint32_t*)src, (uint32_t*)dst, s2g, slot_base,
-                                                                num_patches, num_slots, nattr, layout);
+        RXM_PERMUTE(uint32_t);
     else if (elem_bytes == 8)
-        k_permute<uint64_t, TO_SLOTS><<<grid, 128, 0, stream>>>((const uint64_t*)src, (uint64_t*)dst, s2g, slot_base,
-                                                                num_patches, num_slots, nattr, layout);
+        RXM_PERMUTE(uint64_t);
     else if (elem_bytes == 2)
-        k_permute<uint16_t, TO_SLOTS><<<grid, 128, 0, stream>>>((const uint16_t*)src, (uint16_t*)dst, s2g, slot_base,
-                                                                num_patches, num_slots, nattr, layout);
+        RXM_PERMUTE(uint16_t);
     else if (elem_bytes == 1)
-        k_permute<uint8_t, TO_SLOTS><<<grid, 128, 0, stream>>>((const uint8_t*)src, (uint8_t*)dst, s2g, slot_base,
-                                                               num_patches, num_slots, nattr, layout);
+        RXM_PERMUTE(uint8_t);
     else
         return cudaErrorInvalidValue;
+#undef RXM_PERMUTE
     ++g_launches;
     return cudaGetLastError();
 }
 
-cudaError_t launch_relayout(const void* src, void* dst, const uint32_t* slot_base, uint32_t num_patches, uint32_t num_slots,
-                            uint32_t nattr, uint32_t layout_src, uint32_t layout_dst, cudaStream_t stream)
+cudaError_t launch_relayout(const void* src, void* dst, const SlotMap& sm, uint32_t nattr, uint32_t layout_src,
+                            uint32_t layout_dst, cudaStream_t stream)
 {
-    const uint32_t grid = std::min<uint32_t>(num_patches, 148u * 16u);
+    const uint32_t grid = std::min<uint32_t>(sm.num_patches, 148u * 16u);
     if (grid == 0) return cudaSuccess;
-    k_relayout<<<grid, 128, 0, stream>>>((const uint32_t*)src, (uint32_t*)dst, slot_base, num_patches, num_slots, nattr,
-                                         layout_src, layout_dst);
+    k_relayout<<<grid, 128, 0, stream>>>((const uint32_t*)src, (uint32_t*)dst, sm.slot_base, sm.lin_base, sm.num_patches,
+                                         sm.num_slots, sm.num_elems, nattr, layout_src, layout_dst);
     ++g_launches;
     return cudaGetLastError();
 }
 
-cudaError_t launch_permute_to_slots(const void* in_global, void* out_slots, const uint32_t* s2g, uint32_t num_slots,
-                                    uint32_t elem_bytes, uint32_t nattr, uint32_t layout, const uint32_t* slot_base,
-                                    uint32_t num_patches, cudaStream_t stream)
+cudaError_t launch_permute_to_slots(const void* in_global, void* out_slots, const uint32_t* s2g, const SlotMap& sm,
+                                    uint32_t elem_bytes, uint32_t nattr, uint32_t layout, cudaStream_t stream)
 {
-    return permute_dispatch<true>(in_global, out_slots, s2g, num_slots, elem_bytes, nattr, layout, slot_base,
-                                  num_patches, stream);
+    return permute_dispatch<true>(in_global, out_slots, s2g, sm, elem_bytes, nattr, layout, stream);
 }
 
-cudaError_t launch_permute_to_global(const void* in_slots, void* out_global, const uint32_t* s2g, uint32_t num_slots,
-                                     uint32_t elem_bytes, uint32_t nattr, uint32_t layout, const uint32_t* slot_base,
-                                     uint32_t num_patches, cudaStream_t stream)
+cudaError_t launch_permute_to_global(const void* in_slots, void* out_global, const uint32_t* s2g, const SlotMap& sm,
+                                     uint32_t elem_bytes, uint32_t nattr, uint32_t layout, cudaStream_t stream)
 {
-    return permute_dispatch<false>(in_slots, out_global, s2g, num_slots, elem_bytes, nattr, layout, slot_base,
-                                   num_patches, stream);
+    return permute_dispatch<false>(in_slots, out_global, s2g, sm, elem_bytes, nattr, layout, stream);
 }
 
 cudaError_t launch_slot_rows(bool gather, void* attr, const uint32_t* idx, uint64_t n, uint32_t row_words, void* buf,

@@ -63,15 +63,24 @@ cudaError_t launch_boundary_vertices(const MeshView& mv, const KernelLimits& lim
                                      cudaStream_t stream, const char** err);
 
 // out_slot[slot*nattr + a] = in_global[global_of_slot*nattr + a] (AoS), 0 for padding slots
-// 32-bit attributes: copy between layouts over the same slots
-cudaError_t launch_relayout(const void* src, void* dst, const uint32_t* slot_base, uint32_t num_patches, uint32_t num_slots,
-                            uint32_t nattr, uint32_t layout_src, uint32_t layout_dst, cudaStream_t stream);
-cudaError_t launch_permute_to_slots(const void* in_global, void* out_slots, const uint32_t* slot_to_global,
-                                    uint32_t num_slots, uint32_t elem_bytes, uint32_t nattr, uint32_t layout,
-                                    const uint32_t* slot_base, uint32_t num_patches, cudaStream_t stream);
-cudaError_t launch_permute_to_global(const void* in_slots, void* out_global, const uint32_t* slot_to_global,
-                                     uint32_t num_slots, uint32_t elem_bytes, uint32_t nattr, uint32_t layout,
-                                     const uint32_t* slot_base, uint32_t num_patches, cudaStream_t stream);
+// Where the attribute storage of a range of patches lives, for the layout-aware copy kernels: slot_base / lin_base
+// point at the first patch of the range ([num_patches + 1] entries each, absolute values).
+struct SlotMap
+{
+    const uint32_t* slot_base;
+    const uint32_t* lin_base;
+    uint32_t        num_patches;
+    uint32_t        num_slots;  // of the whole mesh (AoS / AoSoA strides)
+    uint32_t        num_elems;  // of the whole mesh (SoA column stride)
+};
+
+// 32-bit attributes: copy between layouts over the same elements
+cudaError_t launch_relayout(const void* src, void* dst, const SlotMap& sm, uint32_t nattr, uint32_t layout_src,
+                            uint32_t layout_dst, cudaStream_t stream);
+cudaError_t launch_permute_to_slots(const void* in_global, void* out_slots, const uint32_t* slot_to_global, const SlotMap& sm,
+                                    uint32_t elem_bytes, uint32_t nattr, uint32_t layout, cudaStream_t stream);
+cudaError_t launch_permute_to_global(const void* in_slots, void* out_global, const uint32_t* slot_to_global, const SlotMap& sm,
+                                     uint32_t elem_bytes, uint32_t nattr, uint32_t layout, cudaStream_t stream);
 
 // halo exchange helpers (AoS attributes, rows of row_words 32-bit words)
 cudaError_t launch_slot_rows(bool gather, void* attr, const uint32_t* idx, uint64_t n, uint32_t row_words, void* buf,

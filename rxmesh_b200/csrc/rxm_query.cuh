@@ -127,11 +127,18 @@ struct PatchQuery
 
     // shared-memory bytes this op needs for a patch with the given maxima
     // (host side; the role of calc_shared_memory, rxmesh_static.inl:498-841)
+    // stored_ff_faces != 0: every patch answers FF from its stored rows (plan(): ff3) and owns at most that many faces;
+    // the launch then reserves the rows + counts instead of the transposes' scratch (5 -> 8 resident blocks per SM)
     __host__ static uint32_t smem_bytes(const uint32_t max_n[3], const uint32_t max_not_owned[3],
-                                        uint32_t max_stash, bool with_owner)
+                                        uint32_t max_stash, bool with_owner, uint32_t stored_ff_faces = 0)
     {
         auto           r16 = [](uint32_t x) { return (x + 15u) & ~15u; };
         uint32_t       b   = 0;
+        if (OP == OP_FF && stored_ff_faces) {
+            b = r16(6 * stored_ff_faces) + r16(2 * stored_ff_faces);
+            if (with_owner) b += r16(4 * max_not_owned[Tr::dst]) + 16 * max_stash;
+            return b;
+        }
         const uint32_t nr  = Tr::conn == 0 ? max_n[ELEM_E] : max_n[ELEM_F];
         b += r16(2 * W * nr);
         if (op_is_edge4<OP>()) {

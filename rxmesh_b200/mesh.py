@@ -72,7 +72,8 @@ def load_patcher_file(path):
 
 
 class Attribute:
-    """Attribute<T, HandleT> (attribute.h:56-731): storage for OWNED elements in slot order."""
+    """Attribute<T, HandleT> (attribute.h:56-731): storage for OWNED elements; AoS / AoSoA in slot order, SoA as the
+    reference's tensor layout (column-major #elements x #attributes over linear ids, attribute.h:249-261,406-421)."""
 
     def __init__(self, mesh, elem, dtype, num_attributes=1, location=LOCATION_ALL, layout=AoSoA,
                  name=""):
@@ -103,7 +104,7 @@ class Attribute:
         return lib().rxm_attr_data(self._h, int(location))
 
     def host_array(self):
-        """numpy view of the HOST copy in slot order (flat)."""
+        """numpy view of the HOST copy in storage order (flat; see index())."""
         p = lib().rxm_attr_data(self._h, HOST)
         if not p:
             raise RXMeshError("attribute has no HOST allocation")
@@ -166,8 +167,8 @@ class Attribute:
         b, cap = int(sb[patch]), int(sb[patch + 1] - sb[patch])
         if self.layout == AoS:
             return (b + lid) * self.num_attributes + attr
-        if self.layout == SoA:
-            return attr * self.mesh.num_slots(self.elem) + b + lid
+        if self.layout == SoA:  # the reference's tensor layout: column-major over linear ids, no padding slots
+            return attr * self.mesh._num(self.elem) + int(self.mesh.lin_base(self.elem)[patch]) + lid
         return b * self.num_attributes + attr * cap + lid
 
 

@@ -10,6 +10,7 @@
 #include "rxmesh/geometry_util.cuh"
 #include "rxmesh/kernels/query_dispatcher.cuh"
 #include "rxmesh/query.h"
+#include "rxmesh/reduce_handle.h"
 #include "rxmesh/rxmesh_static.h"
 
 using namespace rxmesh;
@@ -679,6 +680,168 @@ static int app_indices(const uint32_t* fv, uint32_t nf, uint32_t patch_size)
     return indices_round_trip<VertexHandle>(rx) | (indices_round_trip<EdgeHandle>(rx) << 1) | (indices_round_trip<FaceHandle>(rx) << 2);
 }
 
+// tests/RXMesh_test/test_attribute.cu restated as one user program: Norm2 / Dot / Reduce / ArgMax / CopyFrom /
+// AddingAndRemoving / DefaultLayoutIsAoSoA / TrueSoAHostStorageIsColumnMajor / TrueSoADeviceWritesColumnMajor /
+// ResetSetsAllComponents.  Returns a bit mask of the checks that FAILED (0 = all passed).
+struct UserCustomMin
+{
+    template <typename T>
+    __device__ __forceinline__ T operator()(const T& a, const T& b) const { return (b < a) ? b : a; }
+};
+static int app_attribute_tests(const uint32_t* fv, uint32_t nf, uint32_t patch_size)
+{
+    rx_init(0);
+    RXMeshStatic   rx(to_faces(fv, nf), "", patch_size);
+    int            failed = 0;
+    const uint32_t n = rx.get_num_vertices();
+    auto           near = [](double a, double b) { return std::fabs(a - b) <= 4e-7 * std::fabs(b); };  // EXPECT_FLOAT_EQ: 4 ulp
+    {   // Norm2 (test_attribute.cu:56-79)
+        auto        attr = rx.add_vertex_attribute<float>("v", 3, DEVICE);
+        const float val  = 2.0f;
+        auto        a    = *attr;
+        rx.for_each_vertex(DEVICE, [a, val] __device__(const VertexHandle vh) { a(vh, 0) = val, a(vh, 1) = val, a(vh, 2) = val; });
+        ReduceHandle reduce_handle(*attr);
+        const float  out = reduce_handle.norm2(*attr);
+        if (cudaDeviceSynchronize() != cudaSuccess || !near(out, std::sqrt(3.0 * val * val * n))) failed |= 1;
+        // one component only: the test's own expectation, sqrt(val^2 * #vertices)
+        if (!near(reduce_handle.norm2(*attr, 1), std::sqrt((double)val * val * n))) failed |= 1;
+        rx.remove_attribute("v");
+    }
+    {   // Dot (test_attribute.cu:82-103)
+        auto        v1 = rx.add_vertex_attribute<float>("v1", 3, DEVICE);
+        auto        v2 = rx.add_vertex_attribute<float>("v2", 3, DEVICE);
+        const float a1 = 2.0f, a2 = 3.0f;
+        auto        x = *v1, y = *v2;
+        rx.for_each_vertex(DEVICE, [x, y, a1, a2] __device__(const VertexHandle vh) {
+            for (int c = 0; c < 3; ++c) x(vh, c) = a1, y(vh, c) = a2;
+        });
+        ReduceHandle reduce_handle(*v1);
+        if (!near(reduce_handle.dot(*v1, *v2), 3.0 * a1 * a2 * n)) failed |= 2;
+        if (!near(reduce_handle.dot(*v1, *v2, 2), (double)a1 * a2 * n)) failed |= 2;
+    }
+    {   // Reduce (test_attribute.cu:105-138): max over the edges of patch id * local id, cub::Max and a user functor
+        auto attr = rx.add_edge_attribute<uint32_t>("e", 3, DEVICE);
+        auto e    = *attr;
+        rx.for_each_edge(DEVICE, [e] __device__(const EdgeHandle eh) {
+            auto pl = eh.unpack();
+            for (int c = 0; c < 3; ++c) e(eh, c) = pl.first * pl.second + 1u;
+        });
+        ReduceHandle   reduce_handle(*attr);
+        const uint32_t out_max = reduce_handle.reduce(*attr, cub::Max(), 0u);
+        const uint32_t out_min = reduce_handle.reduce(*attr, UserCustomMin(), 0xFFFFFFFFu);
+        uint32_t       result = 0, result_min = 0xFFFFFFFFu;
+        rx.for_each_edge(HOST, [&](const EdgeHandle eh) {
+            auto pl    = eh.unpack();
+            result     = std::max(result, pl.first * pl.second + 1u);
+            result_min = std::min(result_min, pl.first * pl.second + 1u);
+        }, NULL, false);
+        if (cudaDeviceSynchronize() != cudaSuccess || out_max != result || out_min != result_min) failed |= 4;
+    }
+    {   // ArgMax (test_attribute.cu:141-182) and its mirror ArgMin
+        auto        attr = *rx.add_vertex_attribute<float>("am", 1);
+        const float val  = 2.0f;
+        rx.for_each_vertex(DEVICE, [attr, val] __device__(const VertexHandle vh) { attr(vh) = val; });
+        attr.move(DEVICE, HOST);
+        const uint32_t chosen = n - 1, chosen_min = n / 2;
+        VertexHandle   chosenHandle, chosenMinHandle;
+        rx.for_each_vertex(HOST, [&](const VertexHandle vh) {
+            if (rx.linear_id(vh) == chosen) attr(vh) = 10.f, chosenHandle = vh;
+            if (rx.linear_id(vh) == chosen_min) attr(vh) = -3.f, chosenMinHandle = vh;
+        }, NULL, false);
+        attr.move(HOST, DEVICE);
+        ReduceHandle reduce_handle(attr);
+        auto         mx = reduce_handle.arg_max(attr);
+        auto         mn = reduce_handle.arg_min(attr, 0);
+        if (!chosenHandle.is_valid() || !(mx.key == chosenHandle) || mx.value != 10.f) failed |= 8;
+        if (!(mn.key == chosenMinHandle) || mn.value != -3.f) failed |= 8;
+    }
+    {   // CopyFrom (test_attribute.cu:185-203)
+        auto           f_device = rx.add_face_attribute<uint32_t>("d", 3, DEVICE);
+        auto           f_host   = rx.add_face_attribute<uint32_t>("h", 3, HOST);
+        const uint32_t val      = 99;
+        auto           fd       = *f_device;
+        rx.for_each_face(DEVICE, [fd, val] __device__(const FaceHandle fh) { fd(fh, 0) = val, fd(fh, 1) = val, fd(fh, 2) = val; });
+        f_host->copy_from(*f_device, DEVICE, HOST);
+        rx.for_each_face(HOST, [&](const FaceHandle fh) {
+            for (int c = 0; c < 3; ++c)
+                if ((*f_host)(fh, c) != val) failed |= 16;
+        }, NULL, false);
+    }
+    {   // AddingAndRemoving (test_attribute.cu:205-226)
+        auto vertex_attr = rx.add_vertex_attribute<float>("v_attr", 3, LOCATION_ALL);
+        if (!rx.does_attribute_exist("v_attr")) failed |= 32;
+        vertex_attr->move(HOST, DEVICE);
+        if (cudaDeviceSynchronize() != cudaSuccess) failed |= 32;
+        rx.remove_attribute("v_attr");
+        if (rx.does_attribute_exist("v_attr")) failed |= 32;
+    }
+    {   // DefaultLayoutIsAoSoA (test_attribute.cu:228-238)
+        auto attr = rx.add_vertex_attribute<float>("default_layout", 3, HOST);
+        if (attr->get_layout() != AoSoA || layout_to_string(attr->get_layout()) != "AoSoA") failed |= 64;
+    }
+    {   // TrueSoAHostStorageIsColumnMajor (test_attribute.cu:240-279)
+        auto attr = rx.add_vertex_attribute<float>("true_soa", 3, HOST, SoA);
+        if (!attr->is_tensor_layout() || attr->storage_size() != size_t(n) * attr->get_num_attributes() || attr->rows() != n ||
+            attr->cols() != 3)
+            failed |= 128;
+        float* data = attr->data(HOST);
+        for (uint32_t c = 0; c < attr->get_num_attributes(); ++c)
+            for (uint32_t i = 0; i < n; ++i)
+                data[c * n + i] = float(c * 1000 + i);
+        rx.for_each_vertex(HOST, [&](const VertexHandle vh) {
+            const uint32_t row = rx.linear_id(vh);
+            for (uint32_t c = 0; c < attr->get_num_attributes(); ++c)
+                if ((*attr)(vh, c) != float(c * 1000 + row) || (*attr)(row, c) != float(c * 1000 + row)) failed |= 128;
+        }, NULL, false);
+        // operator()(row, col) names the same element in the slot-ordered layouts
+        for (layoutT layout : {AoS, AoSoA}) {
+            auto other = rx.add_vertex_attribute<float>("rows_" + layout_to_string(layout), 3, HOST, layout);
+            rx.for_each_vertex(HOST, [&](const VertexHandle vh) {
+                for (uint32_t c = 0; c < 3; ++c) (*other)(vh, c) = float(c * 1000 + rx.linear_id(vh));
+            }, NULL, false);
+            for (uint32_t row = 0; row < n; row += 7)
+                for (uint32_t c = 0; c < 3; ++c)
+                    if ((*other)(row, c) != float(c * 1000 + row)) failed |= 128;
+        }
+    }
+    {   // TrueSoADeviceWritesColumnMajor (test_attribute.cu:281-303)
+        auto attr = rx.add_vertex_attribute<float>("true_soa_device", 3, LOCATION_ALL, SoA);
+        auto a    = *attr;
+        rx.for_each_vertex(DEVICE, [=] __device__(const VertexHandle vh) mutable { a(vh, 0) = 11.0f, a(vh, 1) = 22.0f, a(vh, 2) = 33.0f; });
+        if (cudaDeviceSynchronize() != cudaSuccess) failed |= 256;
+        attr->move(DEVICE, HOST);
+        const float* data = attr->data(HOST);
+        for (uint32_t i = 0; i < n; ++i)
+            if (data[i] != 11.0f || data[n + i] != 22.0f || data[2 * n + i] != 33.0f) failed |= 256;
+    }
+    {   // ResetSetsAllComponents (test_attribute.cu:305-329), host and device side
+        for (layoutT layout : {AoS, AoSoA, SoA}) {
+            auto attr = rx.add_vertex_attribute<float>("reset_" + layout_to_string(layout), 3, LOCATION_ALL, layout);
+            attr->reset(5.0f, HOST);
+            rx.for_each_vertex(HOST, [&](const VertexHandle vh) {
+                for (uint32_t c = 0; c < attr->get_num_attributes(); ++c)
+                    if ((*attr)(vh, c) != 5.0f) failed |= 512;
+            }, NULL, false);
+            attr->reset(7.0f, DEVICE);
+            attr->move(DEVICE, HOST);
+            rx.for_each_vertex(HOST, [&](const VertexHandle vh) {
+                for (uint32_t c = 0; c < attr->get_num_attributes(); ++c)
+                    if ((*attr)(vh, c) != 7.0f) failed |= 512;
+            }, NULL, false);
+        }
+    }
+    {   // the fixed-function path on a tensor-layout attribute: get_boundary_vertices writes flags by linear id
+        auto flags = rx.add_vertex_attribute<int>("bd_soa", 1, LOCATION_ALL, SoA);
+        auto ref   = rx.add_vertex_attribute<int>("bd_ref", 1, LOCATION_ALL, AoS);
+        rx.get_boundary_vertices(*flags);
+        rx.get_boundary_vertices(*ref);
+        rx.for_each_vertex(HOST, [&](const VertexHandle vh) {
+            if ((*flags)(vh) != (*ref)(vh) || flags->data(HOST)[rx.linear_id(vh)] != (*ref)(vh)) failed |= 1024;
+        }, NULL, false);
+    }
+    return failed;
+}
+
 // the Filtering driver loop (apps/Filtering/filtering_rxmesh.cuh:60-100)
 static int app_filtering(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, int num_iter,
                          float* out)
@@ -795,6 +958,10 @@ int shim_higher_query(const uint32_t* fv, uint32_t nf, uint32_t patch_size, uint
 int shim_indices(const uint32_t* fv, uint32_t nf, uint32_t patch_size)
 {
     return app_indices(fv, nf, patch_size);
+}
+int shim_attribute_tests(const uint32_t* fv, uint32_t nf, uint32_t patch_size)
+{
+    return app_attribute_tests(fv, nf, patch_size);
 }
 int shim_unit_scan(uint32_t* host_a, uint32_t n)  // in place: a[0..n) -> exclusive prefix sums, a[n] = total
 {

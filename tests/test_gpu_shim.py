@@ -235,6 +235,21 @@ def test_user_indices_round_trip(shim):
     assert shim.shim_indices(_p(F), F.shape[0], 512) == 0
 
 
+_ATTRIBUTE_CHECKS = ["Norm2", "Dot", "Reduce", "ArgMax", "CopyFrom", "AddingAndRemoving", "DefaultLayoutIsAoSoA",
+                     "TrueSoAHostStorageIsColumnMajor", "TrueSoADeviceWritesColumnMajor", "ResetSetsAllComponents",
+                     "get_boundary_vertices on a tensor-layout attribute"]
+
+
+@pytest.mark.parametrize("name,patch_size", [("sphere3", 512), ("bunnyhead", 256)])
+def test_user_attribute_tests(shim, name, patch_size):
+    """TEST(Attribute, *) (tests/RXMesh_test/test_attribute.cu:56-329) as a user program on the drop-in headers:
+    ReduceHandle norm2 / dot / reduce / arg_max, copy_from, add / remove, the default layout, the SoA tensor layout
+    (storage_size == #elements * #attributes, data[c * n + linear_id]) on host and device, reset in every layout."""
+    V, F = make_mesh(name)
+    failed = shim.shim_attribute_tests(_p(F), F.shape[0], patch_size)
+    assert failed == 0, [c for i, c in enumerate(_ATTRIBUTE_CHECKS) if failed >> i & 1]
+
+
 @pytest.mark.parametrize("name,allowed,skip", [("plane", (90.0, 180.0), 4), ("cube", (90.0, 45.0), None)])
 def test_oriented_vv_angles(shim, name, allowed, skip):
     """Oriented_VV_Open / Oriented_VV_Closed (tests/RXMesh_test/test_queries_oriented.cu:14-225): consecutive oriented

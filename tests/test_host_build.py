@@ -210,6 +210,35 @@ def test_host_attribute_roundtrip_all_layouts():
             assert [h[a.index(p, lid, k)] for k in range(3)] == V[g].tolist()
 
 
+def test_true_soa_host_storage_is_column_major():
+    """Attribute.TrueSoAHostStorageIsColumnMajor / ResetSetsAllComponents (tests/RXMesh_test/test_attribute.cu:240-279,
+    305-329): SoA is the reference's tensor layout -- storage_size == #elements * #attributes and
+    data[c * n + linear_id(handle)] is component c of that element (attribute.h:249-261,406-421)."""
+    V, F = make_mesh("sphere3")
+    m = rx.RXMeshStatic(F, device=False, patch_size=128)
+    n = m.get_num_vertices()
+    a = rx.Attribute(m, 0, np.float32, 3, rx.HOST, rx.SoA)
+    assert a.count() == 3 * n  # no padding slots
+    data = a.host_array()
+    for c in range(3):
+        data[c * n:(c + 1) * n] = c * 1000 + np.arange(n, dtype=np.float32)
+    lb = m.lin_base(0)
+    for p in range(m.get_num_patches()):
+        for lid in range(int(lb[p + 1] - lb[p])):
+            row = int(lb[p]) + lid  # Context::linear_id (context.h:275-290)
+            assert [data[a.index(p, lid, c)] for c in range(3)] == [c * 1000 + row for c in range(3)]
+    # to_global undoes linear id -> input id: row r of the tensor is element slot_to_global(owner slot of r)
+    g = a.to_global()
+    s2g, sb = m.slot_to_global(0), m.slot_base(0)
+    for p in range(m.get_num_patches()):
+        for lid in range(int(lb[p + 1] - lb[p])):
+            assert g[s2g[sb[p] + lid]].tolist() == [c * 1000 + int(lb[p]) + lid for c in range(3)]
+    for layout in (rx.AoS, rx.AoSoA, rx.SoA):
+        b = rx.Attribute(m, 0, np.float32, 3, rx.HOST, layout)
+        b.reset(np.float32(5.0), rx.HOST)
+        assert np.all(b.to_global() == 5.0)
+
+
 @pytest.mark.parametrize("name", ["sphere3", "torus"])
 def test_reference_saved_patching_golden(name, tmp_path):
     """tests/golden/<name>_patches are the patchings SAVED BY THE REFERENCE (input/sphere3_patches,
