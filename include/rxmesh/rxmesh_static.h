@@ -2,9 +2,11 @@
 // over librxmesh_b200 (C ABI in include/rxmesh_b200.h).  Same names / argument meaning; user kernels written
 // against the reference (Query::dispatch, for_each<Op>, Attribute::operator()) compile against this header.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <fstream>
 #include <functional>
+#include <limits>
 #include <map>
 #include <memory>
 #include <sstream>
@@ -121,6 +123,82 @@ class RXMeshStatic
         std::vector<std::vector<uint32_t>> faces;
         read_obj(file_path, verts, faces);
         add_vertex_coordinates(verts);
+    }
+    // RXMeshStatic(files_path, patch_size) (rxmesh_static.h:99-100, rxmesh_static.cu:66-161): several OBJ files loaded as
+    // ONE mesh (each file's vertex ids offset by the vertices read so far); every face / vertex / edge carries the index of
+    // the file it came from as its region label
+    explicit RXMeshStatic(const std::vector<std::string> files_path, const uint32_t patch_size = 512)
+    {
+        std::vector<std::vector<float>>    verts;
+        std::vector<std::vector<uint32_t>> faces;
+        std::vector<int>                   region_num_faces, region_num_vertices;
+        for (const auto& path : files_path) {
+            read_obj(path, verts, faces);
+            region_num_faces.push_back((int)faces.size());
+            region_num_vertices.push_back((int)verts.size());
+        }
+        const std::vector<uint32_t> flat = flatten(faces);
+        init(flat.data(), (uint32_t)faces.size(), {}, patch_size);
+        m_num_regions = (int)files_path.size();
+        add_vertex_coordinates(verts);
+        m_face_label   = add_face_attribute<int>("rx:face_label", 1, LOCATION_ALL);
+        m_edge_label   = add_edge_attribute<int>("rx:edge_label", 1, LOCATION_ALL);
+        m_vertex_label = add_vertex_attribute<int>("rx:vertex_label", 1, LOCATION_ALL);
+        auto label_of = [](const std::vector<int>& ends, int id) {  // first region whose end is past id
+            return (int)std::distance(ends.begin(), std::upper_bound(ends.begin(), ends.end(), id));
+        };
+        for_each_face(HOST, [&](const FaceHandle fh) { (*m_face_label)(fh) = label_of(region_num_faces, (int)map_to_global(fh)); }, NULL, false);
+        for_each_vertex(HOST, [&](const VertexHandle vh) { (*m_vertex_label)(vh) = label_of(region_num_vertices, (int)map_to_global(vh)); }, NULL, false);
+        m_face_label->move(HOST, DEVICE);
+        m_vertex_label->move(HOST, DEVICE);
+        add_edge_labels(*m_face_label, *m_edge_label);
+        m_edge_label->move(DEVICE, HOST);
+    }
+    // an edge takes the label of its faces (rxmesh_static.cu:716-727); public because nvcc wants extended lambdas in
+    // public member functions
+    void add_edge_labels(FaceAttribute<int>& face_label, EdgeAttribute<int>& edge_label)
+    {
+        for_each<Op::FE, 256>([face_label, edge_label] __device__(const FaceHandle fh, const EdgeIterator iter) {
+            const int label = face_label(fh);
+            edge_label(iter[0]) = label, edge_label(iter[1]) = label, edge_label(iter[2]) = label;
+        });
+        detail::rxm_check(cudaDeviceSynchronize() == cudaSuccess ? RXM_OK : RXM_ERR_CUDA);
+    }
+    // region labels (rxmesh_static.h:828-843): null for a mesh built from one input
+    int                                   get_num_regions() const { return m_num_regions; }
+    std::shared_ptr<FaceAttribute<int>>   get_face_region_label() { return m_face_label; }
+    std::shared_ptr<EdgeAttribute<int>>   get_edge_region_label() { return m_edge_label; }
+    std::shared_ptr<VertexAttribute<int>> get_vertex_region_label() { return m_vertex_label; }
+    // bounding_box / scale of the input coordinates (rxmesh_static.cu:600-667)
+    void bounding_box(glm::vec3& lower, glm::vec3& upper)
+    {
+        for (int i = 0; i < 3; ++i)
+            lower[i] = std::numeric_limits<float>::max(), upper[i] = std::numeric_limits<float>::lowest();
+        auto coord = *get_input_vertex_coordinates();
+        for_each_vertex(HOST, [&](const VertexHandle vh) {
+            for (int i = 0; i < 3; ++i)
+                lower[i] = std::min(lower[i], coord(vh, i)), upper[i] = std::max(upper[i], coord(vh, i));
+        }, NULL, false);
+    }
+    void scale(glm::fvec3 lower, glm::fvec3 upper)
+    {
+        if (lower[0] > upper[0] || lower[1] > upper[1] || lower[2] > upper[2]) {
+            fprintf(stderr, "RXMeshStatic::scale() can not scale the mesh since the lower corner is higher than upper corner\n");
+            return;
+        }
+        glm::vec3 bb_lower(0), bb_upper(0);
+        bounding_box(bb_lower, bb_upper);
+        float the_factor = std::numeric_limits<float>::max();
+        for (int i = 0; i < 3; ++i)
+            the_factor = std::min(the_factor, (upper[i] - lower[i]) / ((bb_upper[i] - bb_lower[i]) + std::numeric_limits<float>::epsilon()));
+        auto coord = *get_input_vertex_coordinates();
+        for_each_vertex(HOST, [&](const VertexHandle vh) {
+            for (int i = 0; i < 3; ++i) {
+                coord(vh, i) += (lower[i] - bb_lower[i]);
+                coord(vh, i) *= the_factor;
+            }
+        }, NULL, false);
+        coord.move(HOST, DEVICE);
     }
     // add_vertex_coordinates (rxmesh_static.h:110-112): attach positions to a mesh built from faces only
     void add_vertex_coordinates(std::vector<std::vector<float>>& vertices, std::string = "")
@@ -299,28 +377,92 @@ class RXMeshStatic
     {
         std::fstream file(filename, std::ios::out);
         file.precision(30);
-        const uint32_t                  nv = get_num_vertices(), nf = get_num_faces();
-        std::vector<std::array<T, 3>>   vl(nv);
+        std::vector<glm::vec3> v_list;
+        create_vertex_list(v_list, coords);
+        for (uint32_t v = 0; v < v_list.size(); ++v)
+            file << "v " << v_list[v][0] << " " << v_list[v][1] << " " << v_list[v][2] << " \n";
+        std::vector<glm::uvec3> f_list;
+        create_face_list(f_list);
+        for (uint32_t f = 0; f < f_list.size(); ++f)
+            file << "f " << f_list[f][0] + 1 << " " << f_list[f][1] + 1 << " " << f_list[f][2] + 1 << " \n";
+    }
+    // export_vtk (rxmesh_static.h:934-1076): legacy ASCII VTK polydata, vertex and face attributes with 1, 2 or 3
+    // components as SCALARS / COLOR_SCALARS / VECTORS in for_each order
+    template <typename T, typename... AttributesT>
+    void export_vtk(const std::string& filename, const VertexAttribute<T>& coords, AttributesT... attributes) const
+    {
+        std::fstream file(filename, std::ios::out);
+        file.precision(30);
+        std::string name = filename.substr(0, filename.find_last_of('.'));  // extract_file_name (util/util.h:334-341)
+        name             = name.substr(name.find_last_of("/\\") + 1);
+        file << "# vtk DataFile Version 3.0\n" << name << "\nASCII\nDATASET POLYDATA\n";
+        file << "POINTS " << get_num_vertices() << " float\n ";
+        std::vector<glm::vec3> v_list;
+        create_vertex_list(v_list, coords);
+        for (uint32_t v = 0; v < v_list.size(); ++v)
+            file << v_list[v][0] << " " << v_list[v][1] << " " << v_list[v][2] << " \n";
+        std::vector<glm::uvec3> f_list;
+        create_face_list(f_list);
+        file << "POLYGONS 3 " << 4 * f_list.size() << "\n";
+        for (uint32_t f = 0; f < f_list.size(); ++f)
+            file << "3 " << f_list[f][0] << " " << f_list[f][1] << " " << f_list[f][2] << " \n";
+        bool first_v_attr = true, first_f_attr = true;
+        ([&] { export_vtk_attribute(file, first_v_attr, first_f_attr, attributes); }(), ...);
+    }
+    // coordinates in linear-id order (rxmesh_static.inl:399-414)
+    template <typename T>
+    void create_vertex_list(std::vector<glm::vec3>& v_list, const VertexAttribute<T>& coords) const
+    {
+        v_list.resize(get_num_vertices());
         for_each_vertex(HOST, [&](const VertexHandle vh) {
-            for (int i = 0; i < 3; ++i) vl[linear_id(vh)][i] = coords(vh, i);
+            for (int i = 0; i < 3; ++i) v_list[linear_id(vh)][i] = (float)coords(vh, i);
         }, NULL, false);
-        for (uint32_t v = 0; v < nv; ++v)
-            file << "v " << vl[v][0] << " " << vl[v][1] << " " << vl[v][2] << " \n";
-        // global vertex id -> linear id
+    }
+    // faces in linear-id order over linear vertex ids
+    void create_face_list(std::vector<glm::uvec3>& f_list) const
+    {
         const uint32_t* g2s = rxm_mesh_global_to_slot(m_mesh, RXM_V);
         const uint32_t* ep  = rxm_mesh_elem_patch(m_mesh, RXM_V);
         const uint32_t* sb  = rxm_mesh_slot_base(m_mesh, RXM_V);
         const uint32_t* lb  = rxm_mesh_lin_base(m_mesh, RXM_V);
-        std::vector<std::array<uint32_t, 3>> fl(nf);
+        f_list.resize(get_num_faces());
         for_each_face(HOST, [&](const FaceHandle fh) {
             const uint32_t g = map_to_global(fh);
             for (int i = 0; i < 3; ++i) {
                 const uint32_t gv = m_fv[3 * (size_t)g + i];
-                fl[linear_id(fh)][i] = lb[ep[gv]] + (g2s[gv] - sb[ep[gv]]);
+                f_list[linear_id(fh)][i] = lb[ep[gv]] + (g2s[gv] - sb[ep[gv]]);
             }
         }, NULL, false);
-        for (uint32_t f = 0; f < nf; ++f)
-            file << "f " << fl[f][0] + 1 << " " << fl[f][1] + 1 << " " << fl[f][2] + 1 << " \n";
+    }
+    template <typename AttributeT>
+    void export_vtk_attribute(std::fstream& file, bool& first_v_attr, bool& first_f_attr, const AttributeT& attribute) const
+    {
+        using HandleT = typename AttributeT::HandleType;
+        static_assert(std::is_same_v<HandleT, FaceHandle> || std::is_same_v<HandleT, VertexHandle>,
+                      "export_vtk supports vertex and face attributes (edge attributes are NOT supported)");
+        bool& first = std::is_same_v<HandleT, FaceHandle> ? first_f_attr : first_v_attr;
+        if (first) {
+            if (std::is_same_v<HandleT, FaceHandle>)
+                file << "CELL_DATA " << get_num_faces() << "\n";
+            else
+                file << "POINT_DATA " << get_num_vertices() << "\n";
+            first = false;
+        }
+        const uint32_t num_attr = attribute.get_num_attributes();
+        if (num_attr == 1)
+            file << "SCALARS " << attribute.get_name() << " float 1\nLOOKUP_TABLE default\n";
+        else if (num_attr == 2)
+            file << "COLOR_SCALARS " << attribute.get_name() << " 2\n";
+        else if (num_attr == 3)
+            file << "VECTORS " << attribute.get_name() << " float \n";
+        else {
+            fprintf(stderr, "RXMeshStatic::export_vtk() The number of attributes (%u) is not support. Only 1, 2, or 3 attributes are supported\n", num_attr);
+            return;
+        }
+        for_each<HandleT>(HOST, [&](const HandleT& h) {
+            for (uint32_t i = 0; i < num_attr; ++i) file << attribute(h, i) << " ";
+            file << "\n";
+        }, NULL, false);
     }
 
     // ---- run_kernel (rxmesh_static.h:415-505) ----
@@ -427,6 +569,19 @@ class RXMeshStatic
         detail::rxm_check(rxm_mesh_view(m_mesh, &m_context.view, (uint32_t)sizeof(rxm::MeshView)));
     }
     uint32_t info(int k) const { return (uint32_t)rxm_mesh_info(m_mesh, k); }
+    static std::vector<uint32_t> flatten(const std::vector<std::vector<uint32_t>>& fv)
+    {
+        std::vector<uint32_t> flat;
+        flat.reserve(3 * fv.size());
+        for (const auto& f : fv) {
+            if (f.size() != 3) {  // rxmesh.cpp:590-597
+                fprintf(stderr, "rxmesh_b200: non-triangular faces are not supported\n");
+                exit(EXIT_FAILURE);
+            }
+            flat.insert(flat.end(), f.begin(), f.end());
+        }
+        return flat;
+    }
 
     template <typename AttrT, typename T>
     std::shared_ptr<AttrT> add_filled(const T* flat_global, uint32_t n, const std::string& name, layoutT layout)
@@ -443,6 +598,7 @@ class RXMeshStatic
             fprintf(stderr, "RXMeshStatic::RXMeshStatic could not read the input file %s\n", path.c_str());
             exit(EXIT_FAILURE);
         }
+        const long  vertex_offset = (long)verts.size();  // append semantics of import_obj (util/import_obj.h:34-40)
         std::string line;
         while (std::getline(in, line)) {
             std::istringstream ss(line);
@@ -457,7 +613,7 @@ class RXMeshStatic
                 std::string           tok;
                 while (ss >> tok) {
                     const long i = std::stol(tok.substr(0, tok.find('/')));
-                    f.push_back(i > 0 ? (uint32_t)(i - 1) : (uint32_t)((long)verts.size() + i));
+                    f.push_back(i > 0 ? (uint32_t)(vertex_offset + i - 1) : (uint32_t)((long)verts.size() + i));
                 }
                 faces.push_back(f);
             }
@@ -517,6 +673,10 @@ class RXMeshStatic
     rxm_mesh*                                             m_mesh = nullptr;
     std::vector<uint32_t>                                 m_fv;
     std::shared_ptr<VertexAttribute<float>>               m_input_coords;
+    int                                                   m_num_regions = 1;
+    std::shared_ptr<FaceAttribute<int>>                   m_face_label;
+    std::shared_ptr<EdgeAttribute<int>>                   m_edge_label;
+    std::shared_ptr<VertexAttribute<int>>                 m_vertex_label;
     Context                                               m_context;
     std::map<std::string, std::shared_ptr<AttributeBase>> m_attrs;
 };

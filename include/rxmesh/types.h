@@ -49,6 +49,10 @@ template <int N, typename T> __host__ __device__ inline T length(const vec<N, T>
 template <int N, typename T> __host__ __device__ inline T distance2(const vec<N, T>& a, const vec<N, T>& b) { return length2(a - b); }
 template <int N, typename T> __host__ __device__ inline T distance(const vec<N, T>& a, const vec<N, T>& b) { return length(a - b); }
 template <int N, typename T> __host__ __device__ inline vec<N, T> normalize(const vec<N, T>& a) { return a / length(a); }
+using vec2  = vec<2, float>;
+using vec3  = vec<3, float>;
+using fvec3 = vec<3, float>;
+using uvec3 = vec<3, uint32_t>;
 }  // namespace glm
 
 namespace rxmesh {

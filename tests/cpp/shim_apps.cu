@@ -842,6 +842,84 @@ static int app_attribute_tests(const uint32_t* fv, uint32_t nf, uint32_t patch_s
     return failed;
 }
 
+// TEST(RXMeshStatic, MultipleMeshes) + TEST(RXMeshStatic, Export) (tests/RXMesh_test/test_multiple_meshes.cu,
+// test_export.cu): several OBJ files as one mesh with region labels, bounding_box / scale, export_obj / export_vtk.
+// Returns a bit mask of failed checks.
+static int app_multiple_meshes(const char* path_a, const char* path_b, const char* out_obj, const char* out_vtk)
+{
+    rx_init(0);
+    int failed = 0;
+    const std::string file_a = path_a, file_b = path_b;
+    RXMeshStatic      ra(file_a), rb(file_b);  // the parts on their own, for the expected counts
+    const uint32_t nva = ra.get_num_vertices(), nfa = ra.get_num_faces();
+    std::vector<std::string> inputs = {path_a, path_b};
+    RXMeshStatic             rx(inputs);
+    if (rx.get_num_regions() != 2 || rx.get_num_vertices() != nva + rb.get_num_vertices() ||
+        rx.get_num_faces() != nfa + rb.get_num_faces() || rx.get_num_edges() != ra.get_num_edges() + rb.get_num_edges())
+        failed |= 1;
+    auto x       = *rx.get_input_vertex_coordinates();
+    auto v_label = *rx.get_vertex_region_label();
+    auto f_label = *rx.get_face_region_label();
+    auto e_label = *rx.get_edge_region_label();
+    rx.for_each_vertex(HOST, [&](const VertexHandle vh) {
+        if (v_label(vh) != (rx.map_to_global(vh) < nva ? 0 : 1)) failed |= 2;
+    }, NULL, false);
+    rx.for_each_face(HOST, [&](const FaceHandle fh) {
+        if (f_label(fh) != (rx.map_to_global(fh) < nfa ? 0 : 1)) failed |= 4;
+    }, NULL, false);
+    // an edge lies in the region of its end vertices: EV on the device against the host copy of the edge labels
+    auto bad = rx.add_edge_attribute<int>("bad", 1, LOCATION_ALL);
+    bad->reset(0, DEVICE);
+    auto badv = *bad;
+    rx.for_each<Op::EV, 256>([=] __device__(const EdgeHandle eh, const VertexIterator& iter) {
+        if (e_label(eh) != v_label(iter[0]) || e_label(eh) != v_label(iter[1])) badv(eh) = 1;
+    });
+    if (cudaDeviceSynchronize() != cudaSuccess) failed |= 8;
+    bad->move(DEVICE, HOST);
+    rx.for_each_edge(HOST, [&](const EdgeHandle eh) {
+        if ((*bad)(eh) != 0 || (e_label(eh) != 0 && e_label(eh) != 1)) failed |= 8;
+    }, NULL, false);
+    // bounding_box, then the test's own move of region i along axis i % 3, then scale into the unit cube
+    glm::vec3 lower, upper;
+    rx.bounding_box(lower, upper);
+    glm::vec3 lo2(1e30f), up2(-1e30f);
+    rx.for_each_vertex(HOST, [&](const VertexHandle vh) {
+        for (int i = 0; i < 3; ++i) lo2[i] = std::min(lo2[i], x(vh, i)), up2[i] = std::max(up2[i], x(vh, i));
+    }, NULL, false);
+    for (int i = 0; i < 3; ++i)
+        if (lower[i] != lo2[i] || upper[i] != up2[i] || !(lower[i] < upper[i])) failed |= 16;
+    const glm::vec3 bb = upper - lower;
+    for (int i = 0; i < rx.get_num_regions(); ++i)
+        rx.for_each_vertex(HOST, [&](const VertexHandle vh) {
+            const int j = i % 3;
+            if (v_label(vh) == i) x(vh, j) += 0.5f * (i + 1) * bb[j];
+        }, NULL, false);
+    rx.scale(glm::fvec3(0.f, 0.f, 0.f), glm::fvec3(1.f, 1.f, 1.f));
+    rx.bounding_box(lower, upper);
+    for (int i = 0; i < 3; ++i)
+        if (lower[i] < -1e-5f || upper[i] > 1.f + 1e-5f) failed |= 32;
+    if (std::max(upper[0], std::max(upper[1], upper[2])) < 0.999f) failed |= 32;  // the longest side fills the cube
+    // Export: scalar / 2- / 3-component vertex and face attributes tied to the exported coordinates
+    auto vs = *rx.add_vertex_attribute<float>("vScalar", 1);
+    auto v2 = *rx.add_vertex_attribute<float>("vVector2", 2);
+    auto v3 = *rx.add_vertex_attribute<float>("vVector3", 3);
+    auto fs = *rx.add_face_attribute<float>("fScalar", 1);
+    auto f3 = *rx.add_face_attribute<float>("fVector3", 3);
+    rx.for_each_vertex(HOST, [&](const VertexHandle& vh) {
+        vs(vh, 0) = 2.f * x(vh, 0);
+        v2(vh, 0) = x(vh, 1), v2(vh, 1) = x(vh, 2);
+        for (uint32_t i = 0; i < 3; ++i) v3(vh, i) = -x(vh, i);
+    }, NULL, false);
+    rx.for_each_face(HOST, [&](const FaceHandle& fh) {
+        fs(fh, 0) = (float)f_label(fh);
+        for (uint32_t i = 0; i < 3; ++i) f3(fh, i) = (float)(rx.linear_id(fh) + i);
+    }, NULL, false);
+    rx.export_obj(out_obj, x);
+    rx.export_vtk(out_vtk, x, vs, v2, v3, fs, f3);
+    if (cudaDeviceSynchronize() != cudaSuccess) failed |= 64;
+    return failed;
+}
+
 // the Filtering driver loop (apps/Filtering/filtering_rxmesh.cuh:60-100)
 static int app_filtering(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, int num_iter,
                          float* out)
@@ -962,6 +1040,10 @@ int shim_indices(const uint32_t* fv, uint32_t nf, uint32_t patch_size)
 int shim_attribute_tests(const uint32_t* fv, uint32_t nf, uint32_t patch_size)
 {
     return app_attribute_tests(fv, nf, patch_size);
+}
+int shim_multiple_meshes(const char* path_a, const char* path_b, const char* out_obj, const char* out_vtk)
+{
+    return app_multiple_meshes(path_a, path_b, out_obj, out_vtk);
 }
 int shim_unit_scan(uint32_t* host_a, uint32_t n)  // in place: a[0..n) -> exclusive prefix sums, a[n] = total
 {

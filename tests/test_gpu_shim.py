@@ -250,6 +250,63 @@ def test_user_attribute_tests(shim, name, patch_size):
     assert failed == 0, [c for i, c in enumerate(_ATTRIBUTE_CHECKS) if failed >> i & 1]
 
 
+def _write_obj(path, V, F):
+    with open(path, "w") as fh:
+        for v in V:
+            fh.write("v %.9g %.9g %.9g\n" % tuple(v))
+        for f in F:
+            fh.write("f %d %d %d\n" % tuple(int(i) + 1 for i in f))
+
+
+def test_user_multiple_meshes_and_export(shim, tmp_path):
+    """TEST(RXMeshStatic, MultipleMeshes) and TEST(RXMeshStatic, Export) (tests/RXMesh_test/test_multiple_meshes.cu,
+    test_export.cu) on the drop-in headers: RXMeshStatic(vector<path>) with face / vertex / edge region labels,
+    bounding_box, scale, export_obj, export_vtk (the files are parsed back here)."""
+    (Va, Fa), (Vb, Fb) = make_mesh("sphere3"), make_mesh("bunnyhead")
+    pa, pb = str(tmp_path / "a.obj"), str(tmp_path / "b.obj")
+    _write_obj(pa, Va, Fa)
+    _write_obj(pb, Vb, Fb)
+    out_obj, out_vtk = str(tmp_path / "out.obj"), str(tmp_path / "out.vtk")
+    shim.shim_multiple_meshes.argtypes = [C.c_char_p] * 4
+    failed = shim.shim_multiple_meshes(pa.encode(), pb.encode(), out_obj.encode(), out_vtk.encode())
+    checks = ["counts", "vertex labels", "face labels", "edge labels", "bounding_box", "scale", "export"]
+    assert failed == 0, [c for i, c in enumerate(checks) if failed >> i & 1]
+    nv, nf = Va.shape[0] + Vb.shape[0], Fa.shape[0] + Fb.shape[0]
+    # OBJ: same triangle soup (as coordinates) as the scaled input; both regions present
+    Vo, Fo = rx.meshio.import_obj(out_obj)
+    assert Vo.shape == (nv, 3) and Fo.shape == (nf, 3)
+    assert Vo.min() >= -1e-5 and Vo.max() <= 1 + 1e-5
+    # VTK: header, sections and per-row relations between the attributes and the exported points
+    lines = open(out_vtk).read().split("\n")
+    assert lines[0] == "# vtk DataFile Version 3.0" and lines[1] == "out" and lines[2] == "ASCII"
+    assert lines[3] == "DATASET POLYDATA" and lines[4].startswith("POINTS %d float" % nv)
+    P = np.array([[float(t) for t in ln.split()] for ln in lines[5:5 + nv]], dtype=np.float32)
+    assert np.allclose(P, Vo, atol=1e-6)
+    assert lines[5 + nv] == "POLYGONS 3 %d" % (4 * nf)
+    T = np.array([[int(t) for t in ln.split()] for ln in lines[6 + nv:6 + nv + nf]])
+    assert np.all(T[:, 0] == 3) and np.array_equal(T[:, 1:], Fo)
+    k = 6 + nv + nf
+    assert lines[k] == "POINT_DATA %d" % nv and lines[k + 1] == "SCALARS vScalar float 1" and lines[k + 2] == "LOOKUP_TABLE default"
+    vs = np.array([float(ln) for ln in lines[k + 3:k + 3 + nv]], dtype=np.float32)
+    assert np.allclose(vs, 2 * P[:, 0], atol=1e-6)
+    k += 3 + nv
+    assert lines[k] == "COLOR_SCALARS vVector2 2"
+    v2 = np.array([[float(t) for t in ln.split()] for ln in lines[k + 1:k + 1 + nv]], dtype=np.float32)
+    assert np.allclose(v2, P[:, 1:], atol=1e-6)
+    k += 1 + nv
+    assert lines[k].startswith("VECTORS vVector3 float")
+    v3 = np.array([[float(t) for t in ln.split()] for ln in lines[k + 1:k + 1 + nv]], dtype=np.float32)
+    assert np.allclose(v3, -P, atol=1e-6)
+    k += 1 + nv
+    assert lines[k] == "CELL_DATA %d" % nf and lines[k + 1] == "SCALARS fScalar float 1"
+    fs = np.array([float(ln) for ln in lines[k + 3:k + 3 + nf]])
+    assert set(fs.tolist()) == {0.0, 1.0} and int((fs == 0).sum()) == Fa.shape[0]
+    k += 3 + nf
+    assert lines[k].startswith("VECTORS fVector3 float")
+    f3 = np.array([[float(t) for t in ln.split()] for ln in lines[k + 1:k + 1 + nf]])
+    assert np.array_equal(f3, np.arange(nf)[:, None] + np.arange(3)[None, :])
+
+
 @pytest.mark.parametrize("name,allowed,skip", [("plane", (90.0, 180.0), 4), ("cube", (90.0, 45.0), None)])
 def test_oriented_vv_angles(shim, name, allowed, skip):
     """Oriented_VV_Open / Oriented_VV_Closed (tests/RXMesh_test/test_queries_oriented.cu:14-225): consecutive oriented
