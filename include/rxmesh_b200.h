@@ -104,6 +104,10 @@ typedef struct {
     const uint32_t* stash;       /* 4*n_stash u32: patch, slot base V, E, F */
     uint32_t        n_stash;
     const uint32_t* ltog[3];     /* n[t] global ids (owned first, each half ascending) */
+    /* stored adjacency rows of the OWNED faces / edges (NULL unless the input is edge-manifold): ff = 3 per face, the
+     * local faces across edges 0, 1, 2 compacted to the front; ef = 2 per edge, its local faces ascending; 0xFFFF = none */
+    const uint16_t* ff;
+    const uint16_t* ef;
 } rxm_patch_view;
 int rxm_mesh_patch(const rxm_mesh* m, uint32_t patch, rxm_patch_view* out);
 

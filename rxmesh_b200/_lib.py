@@ -18,7 +18,7 @@ class PatchView(C.Structure):
                 ("packed", C.c_uint32), ("ev", u16p), ("fe", u16p), ("fv", u16p),
                 ("voff_e", u16p), ("voff_f", u16p), ("eoff_f", u16p), ("fan_off", u16p), ("fan_v", u16p),
                 ("fan_f", u16p), ("fan_total", C.c_uint32), ("owner", u32p * 3), ("stash", u32p),
-                ("n_stash", C.c_uint32), ("ltog", u32p * 3)]
+                ("n_stash", C.c_uint32), ("ltog", u32p * 3), ("ff", u16p), ("ef", u16p)]
 
 
 class PatcherFile(C.Structure):

@@ -727,6 +727,8 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
                 for (; k < 3; ++k)
                     ff[3 * f + k] = 0xFFFF;
             }
+            // stored EF: the pairs of the owned edges as they are (faces were visited in ascending local id)
+            memcpy(B + D.off_ef(), ef2.data(), 4 * (size_t)D.n_owned[ELEM_E]);
         }
         if (M.fans) {
             memcpy(B + D.off_fanoff(), fan_off[p].data(), fan_off[p].size() * 2);

@@ -138,7 +138,8 @@ struct alignas(16) PatchDesc
     uint32_t o_fe, o_fv, o_voff_e, o_voff_f, o_eoff_f, o_fanoff, o_fanv, o_own[3], o_stash;
     uint32_t o_fanf;        // fan faces: fan_f[i] = local face between fan_v[i] and fan_v[i+1] (0xFFFF: none)
     uint32_t o_ff;          // stored FF: 3 u16 per OWNED face, the faces across edge 0, 1, 2 compacted to the front, 0xFFFF after
-    uint32_t pad1[3];
+    uint32_t o_ef;          // stored EF: 2 u16 per OWNED edge, its (at most two) faces in ascending local id, 0xFFFF after
+    uint32_t pad1[2];
 
     RXM_HD uint32_t ev_bytes() const { return o_fe; }
     RXM_HD uint32_t fe_bytes() const { return o_fv - o_fe; }
@@ -164,6 +165,8 @@ struct alignas(16) PatchDesc
     RXM_HD uint32_t stash_bytes() const { return 16u * n_stash; }
     RXM_HD uint32_t off_ff() const { return o_ff; }
     RXM_HD uint32_t ff_bytes() const { return (flags & FLAG_FF) ? round_up(6u * n_owned[ELEM_F], 16) : 0u; }
+    RXM_HD uint32_t off_ef() const { return o_ef; }
+    RXM_HD uint32_t ef_bytes() const { return (flags & FLAG_FF) ? round_up(4u * n_owned[ELEM_E], 16) : 0u; }
     RXM_HD uint32_t slot_cap(uint32_t t) const { return (n_owned[t] + 3u) & ~3u; }
 
     // builder: lay the sections out from the counts / flags already stored in this record
@@ -193,7 +196,8 @@ struct alignas(16) PatchDesc
         }
         o_stash    = o;
         o_ff       = o + 16u * n_stash;
-        topo_bytes = o_ff + ff_bytes();
+        o_ef       = o_ff + ff_bytes();
+        topo_bytes = o_ef + ef_bytes();
     }
 };
 static_assert(sizeof(PatchDesc) == 128, "PatchDesc must be 128 bytes");

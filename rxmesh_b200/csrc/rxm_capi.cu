@@ -400,6 +400,8 @@ int rxm_mesh_patch(const rxm_mesh* m, uint32_t p, rxm_patch_view* o)
     o->fan_off = (D.flags & FLAG_FANS) ? reinterpret_cast<const uint16_t*>(B + D.off_fanoff()) : nullptr;
     o->fan_v   = (D.flags & FLAG_FANS) ? reinterpret_cast<const uint16_t*>(B + D.off_fanv()) : nullptr;
     o->fan_f   = (D.flags & FLAG_FANS) ? reinterpret_cast<const uint16_t*>(B + D.off_fanf()) : nullptr;
+    o->ff      = (D.flags & FLAG_FF) ? reinterpret_cast<const uint16_t*>(B + D.off_ff()) : nullptr;
+    o->ef      = (D.flags & FLAG_FF) ? reinterpret_cast<const uint16_t*>(B + D.off_ef()) : nullptr;
     o->fan_total = D.fan_total;
     o->stash   = reinterpret_cast<const uint32_t*>(B + D.off_stash());
     o->n_stash = D.n_stash;

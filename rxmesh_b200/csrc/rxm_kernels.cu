@@ -1476,7 +1476,7 @@ int pick_kmax(uint32_t nnz)
 #define RXM_LAUNCH_ONE(KERNEL, OPV, KM, PK, ...)                                         \
     do {                                                                                 \
         using Q = dev::PatchQuery<OPV, BT, KM, PK>;                                      \
-        smem    = Q::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, true, stored_ff) + extra_smem(OPV); \
+        smem    = Q::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, true, OPV == OP_EF ? stored_ef : stored_ff) + extra_smem(OPV); \
         auto kern = KERNEL<OPV, KM, PK>;                                                 \
         e         = set_smem(kern, smem);                                                \
         if (e != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");    \
@@ -1566,6 +1566,7 @@ cudaError_t launch_query_store(int op, const MeshView& mv, const KernelLimits& l
     uint32_t    smem = 0;
     cudaError_t e    = cudaSuccess;
     const uint32_t stored_ff  = mv.edge_manifold ? lim.max_owned[ELEM_F] : 0u;  // FF from the stored rows (plan(): ff3)
+    const uint32_t stored_ef  = mv.edge_manifold ? lim.max_owned[ELEM_E] : 0u;  // EF from the stored pairs (plan(): ef3)
     auto        extra_smem = [&](int) { return 0u; };
     if (mv.packed)
         RXM_LAUNCH_OP(k_query_store, 1, true, mv, in, out);
@@ -1643,6 +1644,7 @@ cudaError_t launch_query_consume(int op, const MeshView& mv, const KernelLimits&
     uint32_t    smem = 0;
     cudaError_t e    = cudaSuccess;
     const uint32_t stored_ff = mv.edge_manifold ? lim.max_owned[ELEM_F] : 0u;  // FF from the stored rows (plan(): ff3)
+    const uint32_t stored_ef = mv.edge_manifold ? lim.max_owned[ELEM_E] : 0u;  // EF from the stored pairs (plan(): ef3)
     auto extra_smem = [&](int opv) {
         uint32_t dst = 0;
         switch (opv) {
@@ -1820,7 +1822,7 @@ cudaError_t launch_query_csr(int op, const MeshView& mv, const KernelLimits& lim
     if (op == OP_FF && lim.max_face_adjacent_faces > 6) RXM_FAIL("FF: more than 6 adjacent faces per face");
     uint32_t    smem = 0;
     cudaError_t e    = cudaSuccess;
-    const uint32_t stored_ff  = 0;  // k_query_csr plans the generic path (gap-free ascending lists)
+    const uint32_t stored_ff = 0, stored_ef = 0;  // k_query_csr plans the generic path (gap-free ascending lists)
     auto        extra_smem = [&](int) { return 0u; };
     if (mv.packed)
         RXM_LAUNCH_OP(k_query_csr, 1, true, mv, patch_nnz_off, csr_off, csr_val);

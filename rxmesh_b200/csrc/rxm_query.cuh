@@ -123,19 +123,21 @@ struct PatchQuery
     uint32_t    n_cols;  // columns whose lists are built
     bool        ff2;     // FF on edge-manifold input, packed format: pair table instead of the EF CSR
     bool        ff3;     // FF read from the stored rows (patch_layout.h FLAG_FF): plain read + per-row count
+    bool        ef3;     // EF read from the stored pairs of the owned edges (same flag): plain read + per-row count
     bool        fanq;    // VV / VF read from the stored one-ring fans (FLAG_FANS): plain read, oriented order
 
     // shared-memory bytes this op needs for a patch with the given maxima
     // (host side; the role of calc_shared_memory, rxmesh_static.inl:498-841)
-    // stored_ff_faces != 0: every patch answers FF from its stored rows (plan(): ff3) and owns at most that many faces;
-    // the launch then reserves the rows + counts instead of the transposes' scratch (5 -> 8 resident blocks per SM)
+    // stored_rows != 0: every patch answers FF / EF from its stored rows (plan(): ff3 / ef3) and owns at most that many
+    // faces / edges; the launch then reserves the rows + counts instead of the transposes' scratch (FF: 5 -> 8 resident
+    // blocks per SM)
     __host__ static uint32_t smem_bytes(const uint32_t max_n[3], const uint32_t max_not_owned[3],
-                                        uint32_t max_stash, bool with_owner, uint32_t stored_ff_faces = 0)
+                                        uint32_t max_stash, bool with_owner, uint32_t stored_rows = 0)
     {
         auto           r16 = [](uint32_t x) { return (x + 15u) & ~15u; };
         uint32_t       b   = 0;
-        if (OP == OP_FF && stored_ff_faces) {
-            b = r16(6 * stored_ff_faces) + r16(2 * stored_ff_faces);
+        if ((OP == OP_FF || OP == OP_EF) && stored_rows) {
+            b = r16((OP == OP_FF ? 6 : 4) * stored_rows) + r16(2 * stored_rows);
             if (with_owner) b += r16(4 * max_not_owned[Tr::dst]) + 16 * max_stash;
             return b;
         }
@@ -156,6 +158,7 @@ struct PatchQuery
     __device__ __forceinline__ void plan(const PatchDesc& d, Smem& sm, bool with_owner, bool all_sources,
                                          bool edge_manifold = false)
     {
+        ef3  = false;
         fanq = (OP == OP_VV || OP == OP_VF) && edge_manifold && (d.flags & FLAG_FANS) && !all_sources;
         if (fanq) {
             // sections: fan_off (u16 offsets, bit 15 = closed fan) and fan_v; `edge_manifold` doubles as "stored sections
@@ -174,10 +177,11 @@ struct PatchQuery
             return;
         }
         ff3 = OP == OP_FF && edge_manifold && (d.flags & FLAG_FF) && !all_sources;
+        ef3 = OP == OP_EF && edge_manifold && (d.flags & FLAG_FF) && !all_sources;
         ff2 = OP == OP_FF && PACKED && edge_manifold && !ff3;
-        if (ff3) {
-            n_rows = d.n_owned[ELEM_F], n_cols = 0, loff_bytes = 0;
-            conn_bytes = d.ff_bytes();
+        if (ff3 || ef3) {
+            n_rows = ff3 ? d.n_owned[ELEM_F] : d.n_owned[ELEM_E], n_cols = 0, loff_bytes = 0;
+            conn_bytes = ff3 ? d.ff_bytes() : d.ef_bytes();
             s_conn     = sm.alloc<uint16_t>(conn_bytes / 2);
             s_val      = sm.alloc<uint16_t>(n_rows);  // per-row fill count
             s_loff = nullptr, s_off = nullptr, s_off2 = nullptr, s_val2 = nullptr, s_own = nullptr, s_stash = nullptr;
@@ -244,7 +248,8 @@ struct PatchQuery
             }
             return;
         }
-        const uint32_t o = (OP == OP_FF && ff3) ? d.off_ff() : (Tr::conn == 0 ? d.off_ev() : (Tr::conn == 1 ? d.off_fe() : d.off_fv()));
+        const uint32_t o = (OP == OP_FF && ff3) ? d.off_ff()
+                           : ((OP == OP_EF && ef3) ? d.off_ef() : (Tr::conn == 0 ? d.off_ev() : (Tr::conn == 1 ? d.off_fe() : d.off_fv())));
         if (conn_bytes) bulk_g2s(s_conn, blob + o, conn_bytes, bar);
         if (OP == OP_EVDIAMOND && d.ev_bytes()) bulk_g2s(s_val2, blob + d.off_ev(), d.ev_bytes(), bar);
         if (loff_bytes) {
@@ -304,6 +309,13 @@ struct PatchQuery
                 s_val[f] = (uint16_t)((c[3 * f] != 0xFFFFu) + (c[3 * f + 1] != 0xFFFFu) + (c[3 * f + 2] != 0xFFFFu));
             __syncthreads();
             r.val = c, r.stride = 3, r.cnt = s_val;
+            return r;
+        }
+        if (OP == OP_EF && ef3) {
+            for (uint32_t e = threadIdx.x; e < lim; e += BT)
+                s_val[e] = (uint16_t)((c[2 * e] != 0xFFFFu) + (c[2 * e + 1] != 0xFFFFu));
+            __syncthreads();
+            r.val = c, r.stride = 2, r.cnt = s_val;
             return r;
         }
         if (op_is_edge4<OP>()) {

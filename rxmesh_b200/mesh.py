@@ -339,6 +339,8 @@ class RXMeshStatic:
                     fan_off=arr(v.fan_off, no[0] + 1) if v.fan_off else None,
                     fan_v=arr(v.fan_v, v.fan_total) if v.fan_off else None,
                     fan_f=arr(v.fan_f, v.fan_total) if v.fan_off else None,
+                    ff=arr(v.ff, 3 * no[2]).reshape(-1, 3) if v.ff else None,
+                    ef=arr(v.ef, 2 * no[1]).reshape(-1, 2) if v.ef else None,
                     owner=[arr(v.owner[t], n[t] - no[t]) for t in range(3)],
                     stash=arr(v.stash, 4 * v.n_stash).reshape(-1, 4),
                     ltog=[arr(v.ltog[t], n[t]) for t in range(3)])

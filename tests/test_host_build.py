@@ -150,6 +150,29 @@ def test_one_ring_fans(built):
                 assert ff[-1] == 0xFFFF
 
 
+def test_stored_ff_and_ef_rows(built):
+    # stored FF rows (owned faces) and EF pairs (owned edges): what the FF / EF kernels read as plain rows on
+    # edge-manifold input must be the oracle's adjacency restricted to the patch (the ribbon makes it complete)
+    name, V, F, m, T = built
+    if not m.is_edge_manifold():
+        assert m.patch(0)["ff"] is None and m.patch(0)["ef"] is None
+        return
+    ff_ref, ef_ref = O.csr_to_sets(T.query("FF")), O.csr_to_sets(T.query("EF"))
+    for p in range(m.get_num_patches()):
+        pv = m.patch(p)
+        ltf, lte = pv["ltog"][2], pv["ltog"][1]
+        for f in range(pv["n_owned"][2]):
+            row = pv["ff"][f]
+            got = [int(ltf[x]) for x in row if x != 0xFFFF]
+            assert all(x == 0xFFFF for x in row[len(got):])  # compacted to the front
+            assert tuple(sorted(got)) == ff_ref[int(ltf[f])], (p, f)
+        for e in range(pv["n_owned"][1]):
+            row = pv["ef"][e]
+            loc = [int(x) for x in row if x != 0xFFFF]
+            assert loc == sorted(loc) and (row[0] != 0xFFFF)
+            assert tuple(sorted(int(ltf[x]) for x in loc)) == ef_ref[int(lte[e])], (p, e)
+
+
 def test_fans_absent_on_inconsistent_orientation():
     # two triangles sharing an edge with the SAME direction: not consistently oriented -> no fans
     F = np.array([[0, 1, 2], [1, 3, 2][::-1]], dtype=np.uint32)  # second face flipped
