@@ -10,6 +10,7 @@
 #include <map>
 #include <memory>
 #include <sstream>
+#include <unordered_map>
 #include <vector>
 
 #include "rxmesh/attribute.h"
@@ -239,6 +240,51 @@ class RXMeshStatic
     uint32_t get_per_patch_max_edges() const { return info(RXM_INFO_MAX_EDGES_PER_PATCH); }
     uint32_t get_per_patch_max_faces() const { return info(RXM_INFO_MAX_FACES_PER_PATCH); }
     const Context& get_context() const { return m_context; }
+    uint32_t get_max_num_patches() const { return get_num_patches(); }  // static meshes never add patches (rxmesh.h:209)
+    // per-patch counts (rxmesh.h:355-399): owned elements, and all elements of the patch, ribbon included
+    uint16_t get_num_owned_vertices(const uint32_t p) const { return (uint16_t)patch_view(p).n_owned[RXM_V]; }
+    uint16_t get_num_owned_edges(const uint32_t p) const { return (uint16_t)patch_view(p).n_owned[RXM_E]; }
+    uint16_t get_num_owned_faces(const uint32_t p) const { return (uint16_t)patch_view(p).n_owned[RXM_F]; }
+    uint16_t get_num_vertices(const uint32_t p) const { return (uint16_t)patch_view(p).n[RXM_V]; }
+    uint16_t get_num_edges(const uint32_t p) const { return (uint16_t)patch_view(p).n[RXM_E]; }
+    uint16_t get_num_faces(const uint32_t p) const { return (uint16_t)patch_view(p).n[RXM_F]; }
+    // faces per patch, ribbon included (patcher/patcher.h:115-133) and ribbon faces in percent of #faces (:139-142)
+    void get_max_min_avg_patch_size(uint32_t& min_p, uint32_t& max_p, uint32_t& avg_p) const
+    {
+        max_p = 0, min_p = get_num_faces();
+        uint64_t sum = 0;
+        for (uint32_t p = 0; p < get_num_patches(); ++p) {
+            const uint32_t n = get_num_faces(p);
+            sum += n, max_p = std::max(max_p, n), min_p = std::min(min_p, n);
+        }
+        avg_p = (uint32_t)((float)sum / (float)get_num_patches());
+    }
+    double get_ribbon_overhead() const
+    {
+        return 100.0 * (double(info(RXM_INFO_TOTAL_LOCAL_F)) - double(get_num_faces())) / double(get_num_faces());
+    }
+    // the linear-id prefix per patch (rxmesh.h:425-447)
+    template <typename HandleT>
+    const uint32_t* get_element_prefix(locationT location) const
+    {
+        return (location & DEVICE) ? rxm_mesh_device_lin_base(m_mesh, HandleT::elem) : rxm_mesh_lin_base(m_mesh, HandleT::elem);
+    }
+    // map_to_local_vertex / edge / face (rxmesh.h:336-350, rxmesh.cpp:998-1049): linear id -> handle of the owner
+    const VertexHandle map_to_local_vertex(uint32_t i) const { return map_to_local<VertexHandle>(i); }
+    const EdgeHandle   map_to_local_edge(uint32_t i) const { return map_to_local<EdgeHandle>(i); }
+    const FaceHandle   map_to_local_face(uint32_t i) const { return map_to_local<FaceHandle>(i); }
+    // get_edge_id (rxmesh.h:320, rxmesh.cpp:1052-1083): id of the edge between two INPUT vertex ids in the reference's
+    // numbering (order of first appearance over the faces), INVALID32 when they share no edge
+    uint32_t get_edge_id(const uint32_t v0, const uint32_t v1) const
+    {
+        if (m_edge_ids.empty()) {
+            const uint32_t* ev = rxm_mesh_edges(m_mesh);
+            for (uint32_t e = 0; e < get_num_edges(); ++e)
+                m_edge_ids[((uint64_t)std::max(ev[2 * e], ev[2 * e + 1]) << 32) | std::min(ev[2 * e], ev[2 * e + 1])] = e;
+        }
+        auto it = m_edge_ids.find(((uint64_t)std::max(v0, v1) << 32) | std::min(v0, v1));
+        return it == m_edge_ids.end() ? INVALID32 : it->second;
+    }
     rxm_mesh*      c_handle() const { return m_mesh; }
 
     // ---- attributes (rxmesh_static.h:608-806) ----
@@ -569,6 +615,25 @@ class RXMeshStatic
         detail::rxm_check(rxm_mesh_view(m_mesh, &m_context.view, (uint32_t)sizeof(rxm::MeshView)));
     }
     uint32_t info(int k) const { return (uint32_t)rxm_mesh_info(m_mesh, k); }
+    rxm_patch_view patch_view(uint32_t p) const
+    {
+        rxm_patch_view v;
+        detail::rxm_check(rxm_mesh_patch(m_mesh, p, &v));
+        return v;
+    }
+    template <typename HandleT>
+    HandleT map_to_local(uint32_t i) const
+    {
+        const uint32_t* lb  = rxm_mesh_lin_base(m_mesh, HandleT::elem);
+        const uint32_t* end = lb + get_num_patches() + 1;
+        const uint32_t* p   = std::upper_bound(lb, end, i);  // first prefix past i
+        if (p == end || p == lb) {
+            fprintf(stderr, "RXMeshStatic::map_to_local can not its patch. Input is out of range!\n");
+            return HandleT();
+        }
+        --p;
+        return HandleT((uint32_t)(p - lb), typename HandleT::LocalT((uint16_t)(i - *p)));
+    }
     static std::vector<uint32_t> flatten(const std::vector<std::vector<uint32_t>>& fv)
     {
         std::vector<uint32_t> flat;
@@ -673,6 +738,7 @@ class RXMeshStatic
     rxm_mesh*                                             m_mesh = nullptr;
     std::vector<uint32_t>                                 m_fv;
     std::shared_ptr<VertexAttribute<float>>               m_input_coords;
+    mutable std::unordered_map<uint64_t, uint32_t>        m_edge_ids;  // get_edge_id, built on first use
     int                                                   m_num_regions = 1;
     std::shared_ptr<FaceAttribute<int>>                   m_face_label;
     std::shared_ptr<EdgeAttribute<int>>                   m_edge_label;

@@ -677,7 +677,31 @@ static int app_indices(const uint32_t* fv, uint32_t nf, uint32_t patch_size)
 {
     rx_init(0);
     RXMeshStatic rx(to_faces(fv, nf), "", patch_size);
-    return indices_round_trip<VertexHandle>(rx) | (indices_round_trip<EdgeHandle>(rx) << 1) | (indices_round_trip<FaceHandle>(rx) << 2);
+    int bad = indices_round_trip<VertexHandle>(rx) | (indices_round_trip<EdgeHandle>(rx) << 1) | (indices_round_trip<FaceHandle>(rx) << 2);
+    // the host side of the same maps: map_to_local_*(linear_id(h)) == h, per-patch counts, get_edge_id, patch statistics
+    rx.for_each_vertex(HOST, [&](const VertexHandle h) { if (rx.map_to_local_vertex(rx.linear_id(h)) != h) bad |= 8; }, NULL, false);
+    rx.for_each_edge(HOST, [&](const EdgeHandle h) { if (rx.map_to_local_edge(rx.linear_id(h)) != h) bad |= 8; }, NULL, false);
+    rx.for_each_face(HOST, [&](const FaceHandle h) { if (rx.map_to_local_face(rx.linear_id(h)) != h) bad |= 8; }, NULL, false);
+    uint32_t ov = 0, oe = 0, of = 0, lf = 0;
+    for (uint32_t p = 0; p < rx.get_num_patches(); ++p) {
+        ov += rx.get_num_owned_vertices(p), oe += rx.get_num_owned_edges(p), of += rx.get_num_owned_faces(p), lf += rx.get_num_faces(p);
+        if (rx.get_num_vertices(p) < rx.get_num_owned_vertices(p) || rx.get_element_prefix<FaceHandle>(HOST)[p + 1] != of) bad |= 16;
+    }
+    if (ov != rx.get_num_vertices() || oe != rx.get_num_edges() || of != rx.get_num_faces()) bad |= 16;
+    uint32_t mn, mx, avg;
+    rx.get_max_min_avg_patch_size(mn, mx, avg);
+    if (mn > avg || avg > mx || mx != rx.get_per_patch_max_faces() || avg != (uint32_t)((float)lf / (float)rx.get_num_patches())) bad |= 32;
+    if (std::fabs(rx.get_ribbon_overhead() - 100.0 * (double(lf) - nf) / nf) > 1e-9 || rx.get_max_num_patches() != rx.get_num_patches()) bad |= 32;
+    // get_edge_id: every face's three vertex pairs name an edge, the numbering is the order of first appearance
+    uint32_t next = 0;
+    for (uint32_t f = 0; f < nf; ++f)
+        for (int j = 0; j < 3; ++j) {
+            const uint32_t e = rx.get_edge_id(fv[3 * f + j], fv[3 * f + (j + 1) % 3]);
+            if (e == INVALID32 || e > next || e != rx.get_edge_id(fv[3 * f + (j + 1) % 3], fv[3 * f + j])) bad |= 64;
+            if (e == next) ++next;
+        }
+    if (next != rx.get_num_edges() || rx.get_edge_id(fv[0], fv[0]) != INVALID32) bad |= 64;
+    return bad;
 }
 
 // tests/RXMesh_test/test_attribute.cu restated as one user program: Norm2 / Dot / Reduce / ArgMax / CopyFrom /
