@@ -21,7 +21,13 @@
 
 namespace rxmesh {
 
-inline void rx_init(int device_id = 0) { detail::rxm_check(rxm_init(device_id)); }  // rxmesh.h:23-30
+// rx_init(device_id, log level) (rxmesh.h:23-30): a negative device id skips the device selection, like the reference;
+// the second argument is the reference's spdlog level (any integral / enum value), there is no logger to configure here
+template <typename LevelT = int>
+inline void rx_init(int device_id = 0, LevelT = LevelT())
+{
+    if (device_id >= 0) detail::rxm_check(rxm_init(device_id));
+}
 
 namespace detail {
 inline void check_launch(const char* what)
@@ -87,8 +93,11 @@ class RXMeshStatic
     }
     // RXMeshStatic(fv, patcher_file, patch_size): replay a patching saved by Patcher::save / RXMesh::save
     // (rxmesh_static.h:61-66, patcher/patcher.h:154-182)
+    // capacity_factor / patch_alloc_factor / lp_hashtable_load_factor size the reference's slack for DYNAMIC changes and
+    // its cuckoo tables; a static mesh with direct owner tables has neither, the arguments are accepted and ignored
     explicit RXMeshStatic(const std::vector<std::vector<uint32_t>>& fv, const std::string patcher_file = "",
-                          const uint32_t patch_size = 512)
+                          const uint32_t patch_size = 512, const float /*capacity_factor*/ = 1.0,
+                          const float /*patch_alloc_factor*/ = 1.0, const float /*lp_hashtable_load_factor*/ = 0.8)
     {
         std::vector<uint32_t> flat;
         flat.reserve(3 * fv.size());
@@ -117,7 +126,9 @@ class RXMeshStatic
     // RXMeshStatic(file_path, patcher_file, patch_size) (rxmesh_static.h:61-66): OBJ input, positions kept as the
     // input vertex coordinates (import_obj semantics of util/import_obj.h: "v x y z" and "f a b c" / "f a/b/c ..." lines,
     // 1-based or negative indices, triangles only)
-    explicit RXMeshStatic(const std::string file_path, const std::string patcher_file = "", const uint32_t patch_size = 512)
+    explicit RXMeshStatic(const std::string file_path, const std::string patcher_file = "", const uint32_t patch_size = 512,
+                          const float /*capacity_factor*/ = 1.0, const float /*patch_alloc_factor*/ = 1.0,
+                          const float /*lp_hashtable_load_factor*/ = 0.8)
         : RXMeshStatic(read_obj_faces(file_path), patcher_file, patch_size)
     {
         std::vector<std::vector<float>> verts;

@@ -675,8 +675,9 @@ static int indices_round_trip(RXMeshStatic& rx)
 }
 static int app_indices(const uint32_t* fv, uint32_t nf, uint32_t patch_size)
 {
-    rx_init(0);
-    RXMeshStatic rx(to_faces(fv, nf), "", patch_size);
+    rx_init(0, 2);  // (device, log level) as in the reference's mains
+    auto         faces = to_faces(fv, nf);
+    RXMeshStatic rx(faces, "", patch_size, 1.0, 1.0, 0.8);  // the reference's full constructor signature
     int bad = indices_round_trip<VertexHandle>(rx) | (indices_round_trip<EdgeHandle>(rx) << 1) | (indices_round_trip<FaceHandle>(rx) << 2);
     // the host side of the same maps: map_to_local_*(linear_id(h)) == h, per-patch counts, get_edge_id, patch statistics
     rx.for_each_vertex(HOST, [&](const VertexHandle h) { if (rx.map_to_local_vertex(rx.linear_id(h)) != h) bad |= 8; }, NULL, false);
