@@ -376,11 +376,20 @@ def run_ours(args, rank, world, local_rank):
     sampler.start()
     t_w = time.perf_counter()
     n_warm = 0
-    while n_warm < args.warmup or time.perf_counter() - t_w < 0.6:  # >= W steps and long enough for the
-        step()                                                      # clocks to settle / sampler to start
-        n_warm += 1
-        if n_warm % 16 == 0:
-            torch.cuda.synchronize()
+    while True:  # >= W steps and long enough for the clocks to settle / the sampler to start
+        for _ in range(16):
+            step()
+        n_warm += 16
+        torch.cuda.synchronize()
+        more = n_warm < args.warmup or time.perf_counter() - t_w < 0.6
+        if world > 1:
+            # every step holds a send/recv pair with the neighbours: all ranks must run the SAME number of steps, so the
+            # time-based decision is taken collectively (a rank-local clock would leave unmatched exchanges behind)
+            flag = torch.tensor([1 if more else 0], device="cuda")
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX)
+            more = bool(int(flag[0]))
+        if not more:
+            break
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     barrier()
     l0 = rx.launch_count()

@@ -491,7 +491,7 @@ class RXMeshStatic:
                                            _stream_ptr(stream)))
 
     # ---- helper used by the tests: run a query and return per-source global neighbour lists ----
-    def query_global(self, op, width=None, stream=None):
+    def query_global(self, op, width=None, stream=None, layout=AoSoA):
         op = Op(op)
         src, dst = _SRC[op], _DST[op]
         if width is None:
@@ -499,8 +499,8 @@ class RXMeshStatic:
                      Op.EF: self.get_input_max_edge_incident_faces(),
                      Op.FF: self.get_input_max_face_adjacent_faces() + 2}.get(
                          op, self.get_input_max_valence())
-        inp = Attribute(self, src, np.uint64, 1, LOCATION_ALL, AoSoA)
-        out = Attribute(self, src, np.uint64, width, LOCATION_ALL, AoSoA)
+        inp = Attribute(self, src, np.uint64, 1, LOCATION_ALL, layout)
+        out = Attribute(self, src, np.uint64, width, LOCATION_ALL, layout)
         inp.reset(INVALID64, DEVICE, stream)
         out.reset(INVALID64, DEVICE, stream)
         self.query_store(op, inp, out, stream)

@@ -87,6 +87,25 @@ def test_query(built, op):
     verify(m, op, inp, out, src, dst, csr, ordered)
 
 
+@pytest.mark.parametrize("op", ["VV", "EF", "FV", "FF"])
+def test_query_output_layouts(built, op):
+    """the query kernels write through Attribute::operator(): handles stored into AoS and SoA (tensor layout, by linear
+    id) attributes are the ones stored into the default AoSoA attributes, element by element"""
+    name, V, F, m, T = built
+    ref_in, ref_out, src, dst = m.query_global(rx.Op[op])
+    sb, lb = m.slot_base(src), m.lin_base(src)
+    W = ref_out.num_attributes
+    for layout in (rx.AoS, rx.SoA):
+        inp, out, _, _ = m.query_global(rx.Op[op], layout=layout)
+        a, b, ra, rb = inp.host_array(), out.host_array(), ref_in.host_array(), ref_out.host_array()
+        if layout == rx.SoA:
+            assert out.count() == W * m._num(src)
+        for p in range(0, m.get_num_patches(), 3):
+            for lid in range(0, int(lb[p + 1] - lb[p]), 5):
+                assert a[inp.index(p, lid, 0)] == ra[ref_in.index(p, lid, 0)]
+                assert [b[out.index(p, lid, k)] for k in range(W)] == [rb[ref_out.index(p, lid, k)] for k in range(W)]
+
+
 def test_launch_box(built):
     name, V, F, m, T = built
     blocks, threads, smem = m.launch_box(rx.Op.VV)
