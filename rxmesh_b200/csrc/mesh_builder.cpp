@@ -165,8 +165,122 @@ void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_
         seeds[i] = (uint32_t)(((2ull * i + 1) * nf) / (2ull * K));
 
     std::vector<uint32_t> queue(nf), dist(nf), psize;
+    // RXM_PATCHER_SERIAL=1 keeps the single-threaded FIFO passes (the definition the parallel ones are tested against;
+    // also what runs with fewer than three threads, where the level-synchronous form does not pay)
+    const bool serial = getenv("RXM_PATCHER_SERIAL") != nullptr || (omp_get_max_threads() < 3 && !getenv("RXM_PATCHER_PARALLEL"));
 
-    auto assign = [&]() {
+    // compact away patches that received no face (duplicate seeds)
+    auto drop_empty_patches = [&]() {
+        psize.assign(seeds.size(), 0);
+#pragma omp parallel
+        {
+            std::vector<uint32_t> mine(seeds.size(), 0);  // per-thread histogram, merged under a lock: counts only
+#pragma omp for schedule(static) nowait
+            for (int64_t f = 0; f < (int64_t)nf; ++f)
+                mine[face_patch[f]]++;
+#pragma omp critical
+            for (size_t i = 0; i < mine.size(); ++i)
+                psize[i] += mine[i];
+        }
+        std::vector<uint32_t> remap(seeds.size());
+        uint32_t              k = 0;
+        for (uint32_t i = 0; i < seeds.size(); ++i) {
+            remap[i] = k;
+            if (psize[i]) {
+                seeds[k] = seeds[i];
+                psize[k] = psize[i];
+                ++k;
+            }
+        }
+        if (k != seeds.size()) {
+            seeds.resize(k);
+            psize.resize(k);
+#pragma omp parallel for schedule(static)
+            for (int64_t f = 0; f < (int64_t)nf; ++f)
+                face_patch[f] = remap[face_patch[f]];
+        }
+    };
+
+    // Multi-source BFS from the seeds, level by level on all cores, with exactly the outcome of the FIFO version below:
+    // an unvisited face goes to the frontier face with the smallest queue position among its neighbours (atomic min of
+    // positions), and the next frontier is written in (claimer position, neighbour-list index) order through a prefix sum
+    // -- the order the FIFO queue would have produced.  Same face_patch, dist and queue contents for any thread count.
+    std::vector<uint32_t>              claim, emit_n((size_t)omp_get_max_threads(), 0);
+    std::vector<std::vector<uint32_t>> emit_buf((size_t)omp_get_max_threads());
+    auto assign_parallel = [&]() {
+        claim.resize(nf);
+#pragma omp parallel for schedule(static)
+        for (int64_t f = 0; f < (int64_t)nf; ++f)
+            face_patch[f] = INVALID32_, claim[f] = INVALID32_;
+        uint32_t tail = 0;
+        for (uint32_t i = 0; i < seeds.size(); ++i) {
+            if (face_patch[seeds[i]] != INVALID32_) continue;  // duplicate seed: dropped below
+            face_patch[seeds[i]] = i;
+            dist[seeds[i]]       = 0;
+            queue[tail++]        = seeds[i];
+        }
+        uint32_t lo = 0, scan = 0;
+        while (true) {
+            while (lo < tail) {
+                const uint32_t hi = tail, n = hi - lo;
+                std::fill(emit_n.begin(), emit_n.end(), 0u);
+#pragma omp parallel if (n > 2048)
+                {
+                    // thread t owns the contiguous positions [i0, i1): concatenating the threads' outputs in thread order
+                    // is the (claimer position, neighbour index) order
+                    const int      t = omp_get_thread_num(), T = omp_get_num_threads();
+                    const uint32_t i0 = lo + (uint32_t)((uint64_t)n * t / T), i1 = lo + (uint32_t)((uint64_t)n * (t + 1) / T);
+                    for (uint32_t i = i0; i < i1; ++i) {
+                        const uint32_t f = queue[i];
+                        for (uint32_t k = ff_off[f]; k < ff_off[f + 1]; ++k) {
+                            const uint32_t g = ff_val[k];
+                            if (face_patch[g] != INVALID32_) continue;
+                            uint32_t old = __atomic_load_n(&claim[g], __ATOMIC_RELAXED);
+                            while (i < old && !__atomic_compare_exchange_n(&claim[g], &old, i, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+                            }
+                        }
+                    }
+#pragma omp barrier
+                    std::vector<uint32_t>& mine = emit_buf[t];
+                    mine.clear();
+                    for (uint32_t i = i0; i < i1; ++i) {
+                        const uint32_t f = queue[i];
+                        for (uint32_t k = ff_off[f]; k < ff_off[f + 1]; ++k) {
+                            const uint32_t g = ff_val[k];
+                            if (claim[g] != i) continue;
+                            bool again = false;  // a face listed twice (two shared edges) is taken at its first occurrence
+                            for (uint32_t k2 = ff_off[f]; k2 < k; ++k2)
+                                again |= (ff_val[k2] == g);
+                            if (again) continue;
+                            face_patch[g] = face_patch[f];
+                            dist[g]       = dist[f] + 1;
+                            mine.push_back(g);
+                        }
+                    }
+                    emit_n[t] = (uint32_t)mine.size();
+#pragma omp barrier
+                    uint32_t w = hi;
+                    for (int u = 0; u < t; ++u)
+                        w += emit_n[u];
+                    std::copy(mine.begin(), mine.end(), queue.begin() + w);
+                }
+                lo = hi;
+                for (uint32_t c : emit_n)
+                    tail += c;
+            }
+            // components no seed reached get a seed of their own
+            while (scan < nf && face_patch[scan] != INVALID32_)
+                ++scan;
+            if (scan == nf) break;
+            seeds.push_back(scan);
+            face_patch[scan] = (uint32_t)seeds.size() - 1;
+            dist[scan]       = 0;
+            queue[tail++]    = scan;
+        }
+        drop_empty_patches();
+    };
+
+    auto assign_serial = [&]() {
         std::fill(face_patch.begin(), face_patch.end(), INVALID32_);
         uint32_t head = 0, tail = 0;
         for (uint32_t i = 0; i < seeds.size(); ++i) {
@@ -196,30 +310,88 @@ void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_
             dist[scan]       = 0;
             queue[tail++]    = scan;
         }
-        // compact away patches that received no face (duplicate seeds)
-        psize.assign(seeds.size(), 0);
-        for (uint32_t f = 0; f < nf; ++f)
-            psize[face_patch[f]]++;
-        std::vector<uint32_t> remap(seeds.size());
-        uint32_t              k = 0;
-        for (uint32_t i = 0; i < seeds.size(); ++i) {
-            remap[i] = k;
-            if (psize[i]) {
-                seeds[k] = seeds[i];
-                psize[k] = psize[i];
-                ++k;
-            }
-        }
-        if (k != seeds.size()) {
-            seeds.resize(k);
-            psize.resize(k);
-            for (uint32_t f = 0; f < nf; ++f)
-                face_patch[f] = remap[face_patch[f]];
-        }
+        drop_empty_patches();
+    };
+    double t_assign = 0, t_recenter = 0;  // reported with RXM_VERBOSE
+    auto   assign   = [&]() {
+        const double t0 = now_s();
+        if (serial)
+            assign_serial();
+        else
+            assign_parallel();
+        t_assign += now_s() - t0;
     };
 
     std::vector<uint32_t> depth(nf);
-    auto recenter = [&]() -> bool {
+    // parallel form of recenter_serial: BFS distances do not depend on the visiting order, so every level claims its
+    // faces with a compare-and-swap and appends them in any order; the per-patch arg-max keeps the smallest face id
+    // among equals by merging per-thread results in thread (= ascending face) order
+    auto recenter_parallel = [&]() -> bool {
+        uint32_t tail = 0;
+#pragma omp parallel for schedule(static)
+        for (int64_t f = 0; f < (int64_t)nf; ++f) {
+            bool border = false;
+            for (uint32_t k = ff_off[f]; k < ff_off[f + 1]; ++k)
+                border |= (face_patch[ff_val[k]] != face_patch[f]);
+            depth[f] = border ? 0u : INVALID32_;
+        }
+        for (uint32_t f = 0; f < nf; ++f)
+            if (depth[f] == 0) queue[tail++] = f;
+        uint32_t lo = 0;
+        while (lo < tail) {
+            const uint32_t hi = tail;
+#pragma omp parallel if (hi - lo > 2048)
+            {
+                std::vector<uint32_t> mine;  // this thread's share of the next level, appended with ONE reservation
+#pragma omp for schedule(static) nowait
+                for (int64_t i = lo; i < (int64_t)hi; ++i) {
+                    const uint32_t f = queue[i], d1 = depth[f] + 1;
+                    for (uint32_t k = ff_off[f]; k < ff_off[f + 1]; ++k) {
+                        const uint32_t g = ff_val[k];
+                        if (face_patch[g] != face_patch[f]) continue;
+                        uint32_t expect = INVALID32_;
+                        if (__atomic_load_n(&depth[g], __ATOMIC_RELAXED) == INVALID32_ &&
+                            __atomic_compare_exchange_n(&depth[g], &expect, d1, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED))
+                            mine.push_back(g);
+                    }
+                }
+                if (!mine.empty()) {
+                    const uint32_t w = __atomic_fetch_add(&tail, (uint32_t)mine.size(), __ATOMIC_RELAXED);
+                    std::copy(mine.begin(), mine.end(), queue.begin() + w);
+                }
+            }
+            lo = hi;
+        }
+        const int                          nt = omp_get_max_threads();
+        std::vector<std::vector<uint32_t>> best_t(nt);
+#pragma omp parallel num_threads(nt)
+        {
+            const int              t = omp_get_thread_num(), T = omp_get_num_threads();
+            std::vector<uint32_t>& b = best_t[t];
+            b.assign(seeds.size(), INVALID32_);
+            const uint64_t f0 = (uint64_t)nf * t / T, f1 = (uint64_t)nf * (t + 1) / T;
+            for (uint64_t f = f0; f < f1; ++f) {
+                if (depth[f] == INVALID32_) continue;  // patch without border: keep its seed
+                uint32_t& x = b[face_patch[f]];
+                if (x == INVALID32_ || depth[f] > depth[x]) x = (uint32_t)f;
+            }
+        }
+        bool changed = false;
+        for (uint32_t p = 0; p < seeds.size(); ++p) {
+            uint32_t b = INVALID32_;
+            for (int t = 0; t < nt; ++t) {
+                if (best_t[t].empty()) continue;  // fewer threads ran than asked for
+                const uint32_t x = best_t[t][p];
+                if (x != INVALID32_ && (b == INVALID32_ || depth[x] > depth[b])) b = x;
+            }
+            if (b != INVALID32_ && b != seeds[p]) {
+                seeds[p] = b;
+                changed  = true;
+            }
+        }
+        return changed;
+    };
+    auto recenter_serial = [&]() -> bool {
         // distance of every face to its patch boundary; the deepest face becomes the seed
         uint32_t head = 0, tail = 0;
         std::fill(depth.begin(), depth.end(), INVALID32_);
@@ -253,6 +425,12 @@ void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_
                 changed  = true;
             }
         return changed;
+    };
+    auto recenter = [&]() -> bool {
+        const double t0 = now_s();
+        const bool   r  = serial ? recenter_serial() : recenter_parallel();
+        t_recenter += now_s() - t0;
+        return r;
     };
 
     int n_assign = 0, n_outer = 0;
@@ -309,8 +487,8 @@ void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_
     }
     num_patches = (uint32_t)seeds.size();
     if (getenv("RXM_VERBOSE"))
-        fprintf(stderr, "[rxmesh_b200] lloyd: %d outer rounds, %d recentre+assign passes, %u patches\n", n_outer, n_assign,
-                num_patches);
+        fprintf(stderr, "[rxmesh_b200] lloyd: %d outer rounds, %d recentre+assign passes, %u patches (assign %.2fs, recentre %.2fs, %s)\n",
+                n_outer, n_assign, num_patches, t_assign, t_recenter, serial ? "serial" : "parallel");
 }
 
 // ---------------------------------------------------------------------------

@@ -194,6 +194,28 @@ def test_wide_format_fallback(monkeypatch):
     assert not rx.RXMeshStatic(fan, device=False).is_packed()
 
 
+def test_parallel_lloyd_equals_serial(monkeypatch):
+    """patcher_lloyd (patcher/patcher.cu:828-987 in role): the level-synchronous multi-threaded multi-source BFS and
+    re-centring passes give bit for bit the face -> patch assignment of the single-threaded FIFO passes, for any thread
+    count -- several components (seeds added for unreached components), frontiers above and below the parallel
+    threshold, a size bound that needs splits"""
+    Va, Fa = make_mesh("sphere3")
+    Vb, Fb = make_mesh("torus")
+    two = np.concatenate([Fa, Fb + Va.shape[0]]).astype(np.uint32)
+    Vc, Fc = rx.meshio.icosphere(100)  # 200 000 faces: frontiers of several thousand faces
+    for F, ps in ((Fa, 64), (make_mesh("dragon")[1], 512), (two, 128), (Fc, 256)):
+        monkeypatch.setenv("RXM_PATCHER_SERIAL", "1")
+        m = rx.RXMeshStatic(F, patch_size=ps, device=False)
+        ref = m.elem_patch(2).copy()  # elem_patch is a view into the mesh: copy while it is alive
+        monkeypatch.delenv("RXM_PATCHER_SERIAL")
+        monkeypatch.setenv("RXM_PATCHER_PARALLEL", "1")  # also with fewer than three threads
+        for nt in (1, 2, 5, 8):
+            m = rx.RXMeshStatic(F, patch_size=ps, device=False, num_threads=nt)
+            assert np.array_equal(ref, m.elem_patch(2)), (F.shape[0], ps, nt)
+        monkeypatch.delenv("RXM_PATCHER_PARALLEL")
+        assert np.bincount(ref).max() <= ps
+
+
 def test_user_patching_is_honoured():
     from rxmesh_b200 import meshio
     V, F = meshio.grid(33, 33)
