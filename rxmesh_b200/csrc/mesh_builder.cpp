@@ -498,6 +498,18 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
                        const BuildOptions& opt, HostMesh& M)
 {
     const double t_start = now_s();
+    // RXM_VERBOSE: seconds per build phase
+    const bool   verbose = getenv("RXM_VERBOSE") != nullptr;
+    double       t_lap   = t_start;
+    std::string  laps;
+    auto lap = [&](const char* what) {
+        if (!verbose) return;
+        const double t = now_s();
+        char         b[64];
+        snprintf(b, sizeof(b), " %s %.2f", what, t - t_lap);
+        laps += b;
+        t_lap = t;
+    };
     if (opt.num_threads > 0) omp_set_num_threads(opt.num_threads);
     if (nf == 0) return "build_mesh: empty face list";
     if (opt.patch_size == 0 || opt.patch_size > 16384) return "build_mesh: patch_size must be in [1, 16384]";
@@ -517,6 +529,7 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
     if (nv == INVALID32_) return "build_mesh: vertex id 0xFFFFFFFF is reserved";
     nv += 1;
 
+    lap("check");
     // ---- global edges ----
     const uint32_t ne = build_edges(fv, nf, nv, M.ev, M.fe);
     M.num_elems[ELEM_V] = nv;
@@ -524,6 +537,7 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
     M.num_elems[ELEM_F] = nf;
     const uint32_t* fe = M.fe.data();
 
+    lap("edges");
     // ---- input statistics (rxmesh.cpp:560-650) ----
     std::vector<uint32_t> ef_cnt(ne, 0);
     for (uint64_t i = 0; i < 3ull * nf; ++i)
@@ -551,6 +565,7 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
     }
     std::vector<uint32_t>().swap(ef_cnt);
 
+    lap("stats");
     // ---- face -> patch ----
     std::vector<uint32_t>& fpatch = M.elem_patch[ELEM_F];
     uint32_t               P      = 0;
@@ -577,6 +592,7 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
     M.patcher_seconds = now_s() - t_p0;
     M.num_patches     = P;
 
+    lap("patcher");
     // ---- vertex / edge owner = lowest patch id among the incident faces'
     //      patches (patcher/patcher.cu:730-756: first claim in patch order) ----
     std::vector<uint32_t>& vpatch = M.elem_patch[ELEM_V];
@@ -597,6 +613,7 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
     for (uint32_t v = 0; v < nv; ++v)
         if (vpatch[v] == INVALID32_) return "build_mesh: isolated vertex id (not referenced by any face): " + std::to_string(v);
 
+    lap("owners");
     // ---- faces of every patch (ascending id) and vertex -> faces CSR ----
     std::vector<uint32_t> pf_off((size_t)P + 1, 0), pf_val(nf);
     for (uint32_t f = 0; f < nf; ++f)
@@ -621,6 +638,7 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
                 vf_val[cur[fv[3ull * f + j]]++] = f;
     }
 
+    lap("patch faces");
     // ---- phase A: per patch element lists (owned first, each half sorted by
     //      global id: rxmesh.cpp:845-869) and the neighbour-patch stash ----
     struct Tmp
@@ -685,6 +703,7 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
     std::vector<uint32_t>().swap(vf_off);
     std::vector<uint32_t>().swap(vf_val);
 
+    lap("lists");
     // ---- phase A2: one-ring fans of the owned vertices (local ids), if the input allows ----
     // For owned vertex v every incident face (v, a, b) (a cyclic rotation of its stored corner
     // order) is a directed link a -> b; the links must chain into ONE open or closed sequence.
@@ -768,6 +787,7 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
     }
     M.fans = fans_ok;
 
+    lap("fans");
     // ---- prefixes: attribute slots (padded to 4), linear ids, ltog offsets, blob offsets ----
     M.desc.assign(P, PatchDesc());
     for (int t = 0; t < 3; ++t) {
@@ -817,6 +837,7 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
     }
     M.topo.assign(topo_total + 16, 0);
 
+    lap("prefixes");
     // ---- phase B: id maps ----
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t p = 0; p < (int64_t)P; ++p)
@@ -829,6 +850,7 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
             }
         }
 
+    lap("id maps");
     // ---- phase C: local topology (rxmesh.cpp:872-996), owner tables, stash ----
 #pragma omp parallel for schedule(dynamic, 16)
     for (int64_t p = 0; p < (int64_t)P; ++p) {
@@ -933,7 +955,9 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
         for (int t = 0; t < 3; ++t) {
             std::vector<uint32_t>().swap(M.ltog[t]);
         }
+    lap("topology");
     M.build_seconds = now_s() - t_start;
+    if (verbose) fprintf(stderr, "[rxmesh_b200] build phases (s):%s\n", laps.c_str());
     if (opt.verbose)
         fprintf(stderr, "[rxmesh_b200] build: V=%u E=%u F=%u patches=%u (patcher %.2fs, total %.2fs)\n",
                 nv, ne, nf, P, M.patcher_seconds, M.build_seconds);
