@@ -49,6 +49,10 @@ template <int N, typename T> __host__ __device__ inline T length(const vec<N, T>
 template <int N, typename T> __host__ __device__ inline T distance2(const vec<N, T>& a, const vec<N, T>& b) { return length2(a - b); }
 template <int N, typename T> __host__ __device__ inline T distance(const vec<N, T>& a, const vec<N, T>& b) { return length(a - b); }
 template <int N, typename T> __host__ __device__ inline vec<N, T> normalize(const vec<N, T>& a) { return a / length(a); }
+template <typename T> __host__ __device__ constexpr T pi() { return T(3.14159265358979323846264338327950288); }
+template <typename T> __host__ __device__ constexpr T half_pi() { return T(1.57079632679489661923132169163975144); }
+template <typename T> __host__ __device__ constexpr T two_pi() { return T(6.28318530717958647692528676655900576); }
+template <typename T> __host__ __device__ inline T acos(T x) { return ::acos(x); }
 using vec2  = vec<2, float>;
 using vec3  = vec<3, float>;
 using fvec3 = vec<3, float>;

@@ -1,0 +1,70 @@
+"""The reference's OWN user-kernel source files, compiled UNMODIFIED against the drop-in headers (include/rxmesh,
+include/glm) and run on the GPU: oracle/_ref/libshim_refsrc1.so holds apps/VertexNormal/vertex_normal_kernel.cuh,
+apps/GaussianCurvature/gaussian_curvature_kernel.cuh and tests/RXMesh_test/query_kernel.cuh; libshim_refsrc2.so holds
+apps/Filtering/filtering_rxmesh_kernel.cuh (+ filtering_util.h).  They are built by `make -C oracle ref_user_kernels`
+where /root/reference exists (sources are included from there, never copied) behind the drivers of tests/cpp/shim_apps.cu,
+so the checks are those of tests/test_gpu_shim.py -- same inputs, same oracle comparisons -- with the reference's kernels
+in place of the restated ones.  (The file name sorts last on purpose: these are the newest checks.)"""
+import ctypes as C
+import os
+
+import pytest
+
+import rxmesh_b200 as rx
+import test_gpu_shim as S
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _load(name):
+    path = os.path.join(REFDIR, name)
+    if not os.path.exists(path):
+        pytest.skip("%s not built (needs /root/reference at build time: make -C oracle ref_user_kernels)" % name)
+    rx.lib()
+    return C.CDLL(path)
+
+
+@pytest.fixture(scope="module")
+def refsrc1():
+    return _load("libshim_refsrc1.so")
+
+
+@pytest.fixture(scope="module")
+def refsrc2():
+    return _load("libshim_refsrc2.so")
+
+
+@pytest.mark.parametrize("name", ["sphere3", "dragon", "bunnyhead"])
+def test_reference_vertex_normal_kernel(refsrc1, name):
+    """apps/VertexNormal/vertex_normal_kernel.cuh: compute_vertex_normal<float, 256>"""
+    S.test_user_vertex_normal_kernel(refsrc1, name)
+
+
+@pytest.mark.parametrize("op", ["VV", "VE", "VF", "EV", "EF", "FV", "FE", "FF"])
+def test_reference_query_kernel(refsrc1, op):
+    """tests/RXMesh_test/query_kernel.cuh: query_kernel<256, op, ...> for the eight static queries"""
+    S.test_user_query_kernel(refsrc1, op)
+
+
+@pytest.mark.parametrize("op", ["EVDiamond", "EE"])
+def test_reference_query_kernel_edge4(refsrc1, op):
+    S.test_user_edge4_query_kernel(refsrc1, op)
+
+
+def test_reference_query_kernel_oriented_vv(refsrc1):
+    S.test_oriented_vv(refsrc1)
+
+
+@pytest.mark.parametrize("name", ["sphere3", "dragon"])
+def test_reference_gaussian_curvature_kernel(refsrc1, name):
+    """apps/GaussianCurvature/gaussian_curvature_kernel.cuh: compute_gaussian_curvature<float, 256>"""
+    S.test_user_gaussian_curvature(refsrc1, name)
+
+
+@pytest.mark.parametrize("name", ["sphere3", "dragon"])
+def test_reference_filtering_kernels(refsrc2, name):
+    """apps/Filtering/filtering_rxmesh_kernel.cuh: compute_vertex_normal<float, 512> + bilateral_filtering<float, 512, 80>
+    (query_block_dispatcher / higher_query_block_dispatcher inside a per-vertex k-ring search)"""
+    S.test_user_filtering_app(refsrc2, name)
