@@ -19,18 +19,22 @@ using namespace rxmesh;
 // in this file but THE REFERENCE'S OWN SOURCE FILES, included unmodified from the reference tree and compiled against
 // the drop-in headers; everything else (the drivers, the exported entry points) is shared, so tests/test_gpu_shim.py runs
 // the same checks on them.  1: apps/VertexNormal/vertex_normal_kernel.cuh, apps/GaussianCurvature/
-// gaussian_curvature_kernel.cuh, tests/RXMesh_test/query_kernel.cuh.  2: apps/Filtering/filtering_rxmesh_kernel.cuh (its
+// gaussian_curvature_kernel.cuh, apps/MCF/mcf_kernels.cuh (the matrix-free mat-vec), tests/RXMesh_test/query_kernel.cuh,
+// tests/RXMesh_test/higher_query.cuh.  2: apps/Filtering/filtering_rxmesh_kernel.cuh (its
 // compute_vertex_normal has the VertexNormal app's name and signature, hence a second translation unit).
 #ifndef RXM_REFSRC
 #define RXM_REFSRC 0
 #endif
 #if RXM_REFSRC == 1
 #include "gaussian_curvature_kernel.cuh"
+#include "higher_query.cuh"
+#include "mcf_kernels.cuh"
 #include "query_kernel.cuh"
 #include "vertex_normal_kernel.cuh"
 #define user_vertex_normal compute_vertex_normal
 #define user_gaussian_curvature compute_gaussian_curvature
 #define user_query_kernel query_kernel
+#define user_higher_query higher_query
 #elif RXM_REFSRC == 2
 #include "filtering_rxmesh_kernel.cuh"
 #define user_filter_vertex_normal compute_vertex_normal
@@ -60,6 +64,7 @@ __global__ static void user_vertex_normal(const Context context, VertexAttribute
 #endif
 
 // the MCF matrix-free mat-vec with cotan weights (apps/MCF/mcf_kernels.cuh:117-205): oriented VV
+#if RXM_REFSRC != 1
 template <typename T, uint32_t blockThreads>
 __global__ static void user_mcf_matvec(const Context context, const VertexAttribute<T> coords, const VertexAttribute<T> in,
                                        VertexAttribute<T> out, const T time_step)
@@ -96,6 +101,7 @@ __global__ static void user_mcf_matvec(const Context context, const VertexAttrib
     ShmemAllocator      shrd_alloc;
     query.template dispatch<Op::VV>(block, shrd_alloc, matvec_lambda, [](VertexHandle) { return true; }, true);
 }
+#endif
 
 // Gaussian curvature accumulators (apps/GaussianCurvature/gaussian_curvature_kernel.cuh:10-69): FV + atomics
 #if RXM_REFSRC != 1
@@ -302,6 +308,7 @@ __global__ static void user_sum_edges_multi_queries(const Context context, const
 }
 
 // ---- tests/RXMesh_test/higher_query.cuh:15-90: 2-ring VV through query_block_dispatcher + higher_query_block_dispatcher
+#if RXM_REFSRC != 1
 template <uint32_t blockThreads, Op op>
 __global__ static void user_higher_query(const Context context, VertexAttribute<VertexHandle> input,
                                          VertexAttribute<VertexHandle> output)
@@ -343,6 +350,7 @@ __global__ static void user_higher_query(const Context context, VertexAttribute<
         next_id++;
     }
 }
+#endif
 
 // ---- unit tests of the device building blocks (the reference's Util.Scan / Util.BlockMatrixTranspose,
 // tests/RXMesh_test/test_util.cu:160-358): block_exclusive_scan and csr_transpose from rxm_device.cuh, one block
@@ -459,8 +467,13 @@ static int app_mcf_matvec(const uint32_t* fv, uint32_t nf, const float* x, const
     auto in     = rx.add_vertex_attribute<float>(to_verts(vin, nv), "in");
     auto res    = rx.add_vertex_attribute<float>("out", 3, LOCATION_ALL);
     LaunchBox<blockThreads> lb;
+#if RXM_REFSRC == 1  // the reference's kernel: matvec(context, coords, in, out, use_uniform_laplace, time_step)
+    rx.prepare_launch_box({Op::VV}, lb, (void*)matvec<float, blockThreads>, true);
+    matvec<float, blockThreads><<<lb.blocks, lb.num_threads, lb.smem_bytes_dyn>>>(rx.get_context(), *coords, *in, *res, false, time_step);
+#else
     rx.prepare_launch_box({Op::VV}, lb, (void*)user_mcf_matvec<float, blockThreads>, true);
     user_mcf_matvec<float, blockThreads><<<lb.blocks, lb.num_threads, lb.smem_bytes_dyn>>>(rx.get_context(), *coords, *in, *res, time_step);
+#endif
     if (cudaDeviceSynchronize() != cudaSuccess) return 1;
     res->move(DEVICE, HOST);
     rx.for_each_vertex(HOST, [&](const VertexHandle& vh) {

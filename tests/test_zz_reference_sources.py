@@ -1,6 +1,7 @@
 """The reference's OWN user-kernel source files, compiled UNMODIFIED against the drop-in headers (include/rxmesh,
 include/glm) and run on the GPU: oracle/_ref/libshim_refsrc1.so holds apps/VertexNormal/vertex_normal_kernel.cuh,
-apps/GaussianCurvature/gaussian_curvature_kernel.cuh and tests/RXMesh_test/query_kernel.cuh; libshim_refsrc2.so holds
+apps/GaussianCurvature/gaussian_curvature_kernel.cuh, apps/MCF/mcf_kernels.cuh (matrix-free mat-vec),
+tests/RXMesh_test/query_kernel.cuh and tests/RXMesh_test/higher_query.cuh; libshim_refsrc2.so holds
 apps/Filtering/filtering_rxmesh_kernel.cuh (+ filtering_util.h).  They are built by `make -C oracle ref_user_kernels`
 where /root/reference exists (sources are included from there, never copied) behind the drivers of tests/cpp/shim_apps.cu,
 so the checks are those of tests/test_gpu_shim.py -- same inputs, same oracle comparisons -- with the reference's kernels
@@ -61,6 +62,18 @@ def test_reference_query_kernel_oriented_vv(refsrc1):
 def test_reference_gaussian_curvature_kernel(refsrc1, name):
     """apps/GaussianCurvature/gaussian_curvature_kernel.cuh: compute_gaussian_curvature<float, 256>"""
     S.test_user_gaussian_curvature(refsrc1, name)
+
+
+@pytest.mark.parametrize("name", ["sphere3", "torus", "dragon"])
+def test_reference_mcf_matvec_kernel(refsrc1, name):
+    """apps/MCF/mcf_kernels.cuh: matvec<float, 256> (cotan weights over ORIENTED VV, use_uniform_laplace = false)"""
+    S.test_user_mcf_matvec(refsrc1, name)
+
+
+@pytest.mark.parametrize("name", ["sphere3", "dragon"])
+def test_reference_higher_query_kernel(refsrc1, name):
+    """tests/RXMesh_test/higher_query.cuh: higher_query<512, Op::VV> (2-ring through higher_query_block_dispatcher)"""
+    S.test_user_higher_query_two_ring(refsrc1, name)
 
 
 @pytest.mark.parametrize("name", ["sphere3", "dragon"])
