@@ -12,6 +12,7 @@
 
 #include "../rxmesh_b200.h"
 #include "rxmesh/handle.h"
+#include "rxmesh/matrix/dense_matrix.h"
 
 namespace rxmesh {
 namespace detail {
@@ -127,6 +128,24 @@ class Attribute : public AttributeBase
             if (lb[mid] <= i) lo = mid; else hi = mid;
         }
         return base[index(sb, lb, lo, (uint32_t)(i - lb[lo]), (uint32_t)j)];
+    }
+    // to_matrix / from_matrix (attribute.h:125-145): the HOST copy as a #elements x #attributes matrix whose row i is the
+    // element with linear id i, and back; any layout
+    template <int Order = 0>
+    std::shared_ptr<DenseMatrix<T, Order>> to_matrix() const
+    {
+        auto mat = std::make_shared<DenseMatrix<T, Order>>(m_num_elems, m_nattr);
+        for (uint32_t i = 0; i < m_num_elems; ++i)
+            for (uint32_t j = 0; j < m_nattr; ++j)
+                (*mat)(i, j) = (*this)((size_t)i, (size_t)j);
+        return mat;
+    }
+    template <int Order>
+    void from_matrix(DenseMatrix<T, Order>* mat)
+    {
+        for (uint32_t i = 0; i < m_num_elems; ++i)
+            for (uint32_t j = 0; j < m_nattr; ++j)
+                (*this)((size_t)i, (size_t)j) = (*mat)(i, j);
     }
     template <int N>
     __host__ __device__ __forceinline__ glm::vec<N, T> to_glm(const HandleT& handle) const

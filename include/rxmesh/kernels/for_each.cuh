@@ -16,8 +16,10 @@ __device__ __inline__ void for_each(const Context& context, computeT compute_op)
     if (p_id < context.get_num_patches()) {
         const rxm::PatchDesc* d = context.view.desc + p_id;
         const uint32_t        n = d->n_owned[HandleT::elem], pid = d->patch_id;
-        for (uint32_t i = threadIdx.x; i < n; i += blockThreads)
-            compute_op(HandleT(pid, typename HandleT::LocalT((uint16_t)i)));
+        for (uint32_t i = threadIdx.x; i < n; i += blockThreads) {
+            HandleT h(pid, typename HandleT::LocalT((uint16_t)i));  // an lvalue: user lambdas may take HandleT&
+            compute_op(h);
+        }
     }
     __syncthreads();
 }

@@ -18,6 +18,9 @@
 #include "rxmesh/kernels/for_each.cuh"
 #include "rxmesh/launch_box.h"
 #include "rxmesh/query.h"
+#include "rxmesh/util/import_obj.h"
+#include "rxmesh/util/macros.h"
+#include "rxmesh/util/timer.h"
 
 namespace rxmesh {
 
@@ -417,14 +420,26 @@ class RXMeshStatic
         const uint32_t o = v.owner[t][lid - v.n_owned[t]];
         return HandleT(v.stash[4 * (o >> 16)], typename HandleT::LocalT((uint16_t)(o & 0xFFFFu)));
     }
-    // get_boundary_vertices (rxmesh_static.h:816-819, kernels/boundary.cuh:11-44): boundary_v(vh) = 1 on the boundary
+    // get_boundary_vertices (rxmesh_static.h:816-819, kernels/boundary.cuh:11-44): boundary_v(vh) = 1 on the boundary,
+    // 0 elsewhere, for any single-component attribute type (the reference's test uses VertexAttribute<bool>)
     template <typename T>
-    void get_boundary_vertices(VertexAttribute<T>& boundary_v, bool move_to_host = true, cudaStream_t stream = NULL) const
+    void get_boundary_vertices(VertexAttribute<T>& boundary_v, bool move_to_host = true, cudaStream_t stream = NULL)
     {
-        static_assert(sizeof(T) == 4, "get_boundary_vertices needs a 32-bit attribute");
-        detail::rxm_check(rxm_boundary_vertices(m_mesh, boundary_v.c_handle(), stream));
-        if (!std::is_integral_v<T>)  // the kernel writes integer flags; convert in place for floating-point attributes
-            detail::flags_to_value<T><<<((uint32_t)boundary_v.storage_size() + 255) / 256, 256, 0, stream>>>(boundary_v.data(DEVICE), (uint32_t)boundary_v.storage_size());
+        if constexpr (sizeof(T) == 4) {
+            detail::rxm_check(rxm_boundary_vertices(m_mesh, boundary_v.c_handle(), stream));
+            if (!std::is_integral_v<T>)  // the kernel writes integer flags; convert in place for 32-bit floating point
+                detail::flags_to_value<T><<<((uint32_t)boundary_v.storage_size() + 255) / 256, 256, 0, stream>>>(boundary_v.data(DEVICE), (uint32_t)boundary_v.storage_size());
+        } else {
+            // the kernel writes 32-bit integer flags: run it on a 32-bit attribute of the same layout, convert per vertex
+            const std::string tmp_name = std::string("rx:boundary_flags_") + boundary_v.get_name();
+            auto              flags    = add_vertex_attribute<int>(tmp_name, 1, DEVICE, boundary_v.get_layout());
+            detail::rxm_check(rxm_boundary_vertices(m_mesh, flags->c_handle(), stream));
+            auto f = *flags;
+            auto b = boundary_v;
+            for_each_vertex(DEVICE, [f, b] __device__(const VertexHandle vh) { b(vh) = f(vh) ? T(1) : T(0); }, stream);
+            detail::rxm_check(cudaStreamSynchronize(stream) == cudaSuccess ? RXM_OK : RXM_ERR_CUDA);
+            remove_attribute(tmp_name);
+        }
         if (move_to_host) boundary_v.move(DEVICE, HOST, stream);
     }
     // export_obj (rxmesh_static.inl:365-397): vertices in linear-id order, faces in linear-id order with 1-based
@@ -599,9 +614,10 @@ class RXMeshStatic
         (void)oriented;
         size_t   dyn = with_vertex_valence ? 4 * (size_t)get_per_patch_max_vertices() + 16 : 0;  // compute_vertex_valence
         dyn += 4 * ((size_t)std::max(get_per_patch_max_edges(), get_per_patch_max_faces()) / 32 + 8);  // prologue mask
-        uint32_t blocks = 0, threads = 0;
+        uint32_t blocks = get_num_patches(), threads = 0;
         for (Op o : op) {
             uint32_t b = 0;
+            if (o == Op::V || o == Op::E || o == Op::F) continue;  // device for_each<Op::V|E|F>: one block per patch, no staging
             detail::rxm_check(rxm_mesh_launch_box(m_mesh, (int)o, &blocks, &threads, &b));
             dyn = is_concurrent ? dyn + b : std::max<size_t>(dyn, b);
         }
@@ -667,32 +683,12 @@ class RXMeshStatic
         detail::rxm_check(cudaDeviceSynchronize() == cudaSuccess ? RXM_OK : RXM_ERR_CUDA);
         return a;
     }
+    // append semantics of import_obj (util/import_obj.h): positions and faces of `path` are added to what the vectors hold
     static void read_obj(const std::string& path, std::vector<std::vector<float>>& verts, std::vector<std::vector<uint32_t>>& faces)
     {
-        std::ifstream in(path);
-        if (!in) {
+        if (!import_obj(path, verts, faces, true)) {
             fprintf(stderr, "RXMeshStatic::RXMeshStatic could not read the input file %s\n", path.c_str());
             exit(EXIT_FAILURE);
-        }
-        const long  vertex_offset = (long)verts.size();  // append semantics of import_obj (util/import_obj.h:34-40)
-        std::string line;
-        while (std::getline(in, line)) {
-            std::istringstream ss(line);
-            std::string        tag;
-            ss >> tag;
-            if (tag == "v") {
-                std::vector<float> p(3);
-                ss >> p[0] >> p[1] >> p[2];
-                verts.push_back(p);
-            } else if (tag == "f") {
-                std::vector<uint32_t> f;
-                std::string           tok;
-                while (ss >> tok) {
-                    const long i = std::stol(tok.substr(0, tok.find('/')));
-                    f.push_back(i > 0 ? (uint32_t)(vertex_offset + i - 1) : (uint32_t)((long)verts.size() + i));
-                }
-                faces.push_back(f);
-            }
         }
     }
     static std::vector<std::vector<uint32_t>> read_obj_faces(const std::string& path)

@@ -96,5 +96,7 @@ inline std::string op_to_string(Op op)
 #define INVALID32 0xFFFFFFFFu
 #define INVALID16 0xFFFFu
 #endif
+#ifndef DIVIDE_UP
 #define DIVIDE_UP(a, b) (((a) + (b) - 1) / (b))
+#endif
 }  // namespace rxmesh

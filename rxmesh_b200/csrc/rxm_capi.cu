@@ -507,7 +507,10 @@ int rxm_attr_create(rxm_mesh* m, int elem, uint32_t elem_bytes, uint32_t nattr, 
             return fail(RXM_ERR_CUDA, "rxm_attr_create: DEVICE location requested but the mesh is not on a device");
         }
         cudaError_t e = cudaMalloc(&a->d, bytes);
+        if (e == cudaSuccess) e = cudaMemset(a->d, 0, bytes);  // defined contents: the reference's own tests read components
+                                                               // they never wrote and expect zero (test_attribute.cu:56-79)
         if (e != cudaSuccess) {
+            if (a->d) cudaFree(a->d);
             delete a;
             return fail(RXM_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
         }

@@ -81,3 +81,32 @@ def test_reference_filtering_kernels(refsrc2, name):
     """apps/Filtering/filtering_rxmesh_kernel.cuh: compute_vertex_normal<float, 512> + bilateral_filtering<float, 512, 80>
     (query_block_dispatcher / higher_query_block_dispatcher inside a per-vertex k-ring search)"""
     S.test_user_filtering_app(refsrc2, name)
+
+
+def test_reference_gtest_files(tmp_path):
+    """The reference's own gtest FILES -- tests/RXMesh_test/test_attribute.cu (11 tests: ReduceHandle norm2 / dot / reduce /
+    arg_max, copy_from, add / remove, layouts, tensor SoA on host and device, reset, to_matrix / from_matrix),
+    test_boundary.cu (bunnyhead: 98 boundary vertices through a VertexAttribute<bool>), test_ev_diamond.cu (plane_5: the two
+    triangles of every interior diamond have area 1), test_export.cu (export_obj / export_vtk) and test_for_each.cu (host
+    and device for_each) -- compiled unmodified into oracle/_ref/ref_gtests and run in a directory holding the meshes they
+    name, written from the committed fixtures (input/bumpy-cube.obj is not among them: dragon stands in, the ArgMax test
+    does not depend on the geometry).  Runs in its own process: some of these tests call cudaDeviceReset()."""
+    import subprocess
+
+    import numpy as np
+
+    from conftest import make_mesh
+    exe = os.path.join(REFDIR, "ref_gtests")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_gtests not built (needs /root/reference at build time: make -C oracle ref_user_kernels)")
+    inp = tmp_path / "rxm_input"
+    inp.mkdir()
+    for obj, mesh in (("sphere3", "sphere3"), ("cube", "cube"), ("bunnyhead", "bunnyhead"), ("plane_5", "plane_5"),
+                      ("bumpy-cube", "dragon")):
+        V, F = make_mesh(mesh)
+        S._write_obj(str(inp / (obj + ".obj")), np.asarray(V), np.asarray(F))
+    r = subprocess.run([exe], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0, tail
+    assert "[==========] 16 tests ran, 0 failed" in r.stdout, tail
+    assert os.path.exists(tmp_path / "sphere3.vtk") and os.path.exists(tmp_path / "sphere3.obj")
