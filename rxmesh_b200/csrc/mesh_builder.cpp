@@ -22,8 +22,8 @@ double now_s()
 }
 
 // exclusive prefix sum in place over n+1 entries (entry n receives the total)
-template <typename T>
-void exclusive_scan(std::vector<T>& a)
+template <typename T, typename A>
+void exclusive_scan(std::vector<T, A>& a)
 {
     T run = 0;
     for (size_t i = 0; i < a.size(); ++i) {
@@ -60,7 +60,7 @@ uint32_t build_edges(const uint32_t* fv, uint32_t nf, uint32_t nv, std::vector<u
     {
         uint32_t hi, h;
     };
-    std::vector<HE>       bucket(H);
+    std::vector<HE, NoInitAlloc<HE>> bucket(H);  // every slot is written by the scatter below
     std::vector<uint32_t> cur(off.begin(), off.end() - 1);
 #pragma omp parallel for schedule(static)
     for (int64_t h = 0; h < (int64_t)H; ++h) {
@@ -72,8 +72,11 @@ uint32_t build_edges(const uint32_t* fv, uint32_t nf, uint32_t nv, std::vector<u
     }
     // 2. inside a bucket, equal `hi` = same edge; its first half-edge (smallest h)
     //    decides the edge id.
-    std::vector<uint32_t> rep(H);          // half-edge -> first half-edge of its edge
-    std::vector<uint32_t> first(H + 1, 0);  // 1 at the first half-edge of every edge
+    std::vector<uint32_t, NoInitAlloc<uint32_t>> rep(H);        // half-edge -> first half-edge of its edge (all written)
+    std::vector<uint32_t, NoInitAlloc<uint32_t>> first(H + 1);  // 1 at the first half-edge of every edge
+#pragma omp parallel for schedule(static)
+    for (int64_t h = 0; h <= (int64_t)H; ++h)
+        first[h] = 0;
 #pragma omp parallel for schedule(dynamic, 4096)
     for (int64_t v = 0; v < (int64_t)nv; ++v) {
         HE* b = bucket.data() + off[v];
@@ -835,7 +838,13 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
         M.global_to_slot[t].assign(M.num_elems[t], INVALID32_);
         M.ltog[t].resize(M.ltog_off[t][P]);
     }
-    M.topo.assign(topo_total + 16, 0);
+    M.topo.resize(topo_total + 16);
+    {
+        const uint64_t nb = topo_total + 16, chunk = 1ull << 22;
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < (int64_t)((nb + chunk - 1) / chunk); ++c)
+            memset(M.topo.data() + c * chunk, 0, (size_t)std::min<uint64_t>(chunk, nb - c * chunk));
+    }
 
     lap("prefixes");
     // ---- phase B: id maps ----

@@ -8,12 +8,35 @@
 // linearly in the number of faces (the reference is O(P*(V+E))).
 #pragma once
 #include <cstdint>
+#include <memory>
+#include <utility>
 #include <string>
 #include <vector>
 
 #include "patch_layout.h"
 
 namespace rxm {
+
+// std::vector storage whose resize() leaves trivially constructible elements uninitialised: the 5.6 GB patch store of a
+// 100 M-face mesh is then zero-filled by all cores instead of one
+template <typename T>
+struct NoInitAlloc : std::allocator<T>
+{
+    template <typename U>
+    struct rebind
+    {
+        using other = NoInitAlloc<U>;
+    };
+    template <typename U, typename... A>
+    void construct(U* p, A&&... a)
+    {
+        if constexpr (sizeof...(A) == 0)
+            ::new ((void*)p) U;
+        else
+            ::new ((void*)p) U(std::forward<A>(a)...);
+    }
+};
+using ByteBuf = std::vector<uint8_t, NoInitAlloc<uint8_t>>;
 
 struct HostMesh
 {
@@ -40,7 +63,7 @@ struct HostMesh
 
     // ---- the patch store ----
     std::vector<PatchDesc> desc;
-    std::vector<uint8_t>   topo;
+    ByteBuf                topo;          // all patch blobs back to back (zero-filled in parallel by the builder)
     std::vector<uint32_t>  slot_base[3];  // [P+1]
     std::vector<uint32_t>  lin_base[3];   // [P+1]
 

@@ -293,7 +293,7 @@ int rxm_mesh_compact(rxm_mesh* m)
     }
     std::vector<uint32_t>().swap(h.ev);
     std::vector<uint32_t>().swap(h.fe);
-    if (m->on_device) std::vector<uint8_t>().swap(h.topo);  // the device holds the patch store
+    if (m->on_device) ByteBuf().swap(h.topo);  // the device holds the patch store
     return RXM_OK;
 }
 
