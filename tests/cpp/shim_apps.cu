@@ -35,6 +35,13 @@ using namespace rxmesh;
 #define user_gaussian_curvature compute_gaussian_curvature
 #define user_query_kernel query_kernel
 #define user_higher_query higher_query
+// compile-only: the Geodesic app's PTP relaxation kernel (apps/Geodesic/geodesic_kernel.cuh:95-185, a VV consumer outside
+// this repo's app list) instantiates against the drop-in headers as it stands
+#include "geodesic_kernel.cuh"
+template __global__ void relax_ptp_rxmesh<float, 256>(const rxmesh::Context, const rxmesh::VertexAttribute<float>,
+                                                      rxmesh::VertexAttribute<float>, const rxmesh::VertexAttribute<float>,
+                                                      const rxmesh::VertexAttribute<int>, const int, const int, int*, const float,
+                                                      const float);
 #elif RXM_REFSRC == 2
 #include "filtering_rxmesh_kernel.cuh"
 #define user_filter_vertex_normal compute_vertex_normal
