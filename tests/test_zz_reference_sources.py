@@ -83,14 +83,19 @@ def test_reference_filtering_kernels(refsrc2, name):
     S.test_user_filtering_app(refsrc2, name)
 
 
-def test_reference_gtest_files(tmp_path):
-    """The reference's own gtest FILES -- tests/RXMesh_test/test_attribute.cu (11 tests: ReduceHandle norm2 / dot / reduce /
-    arg_max, copy_from, add / remove, layouts, tensor SoA on host and device, reset, to_matrix / from_matrix),
-    test_boundary.cu (bunnyhead: 98 boundary vertices through a VertexAttribute<bool>), test_ev_diamond.cu (plane_5: the two
-    triangles of every interior diamond have area 1), test_export.cu (export_obj / export_vtk) and test_for_each.cu (host
-    and device for_each) -- compiled unmodified into oracle/_ref/ref_gtests and run in a directory holding the meshes they
-    name, written from the committed fixtures (input/bumpy-cube.obj is not among them: dragon stands in, the ArgMax test
-    does not depend on the geometry).  Runs in its own process: some of these tests call cudaDeviceReset()."""
+_GTESTS = ["Attribute.Norm2", "Attribute.Dot", "Attribute.Reduce", "Attribute.ArgMax", "Attribute.CopyFrom",
+           "Attribute.AddingAndRemoving", "Attribute.DefaultLayoutIsAoSoA", "Attribute.TrueSoAHostStorageIsColumnMajor",
+           "Attribute.TrueSoADeviceWritesColumnMajor", "Attribute.ResetSetsAllComponents",
+           "Attribute.ToAndFromMatrixPreserveLayouts", "RXMeshStatic.BoundaryVertex", "RXMeshStatic.EVDiamond",
+           "RXMeshStatic.Export", "RXMeshStatic.ForEach", "RXMeshStatic.ForEachOnDevice"]
+
+
+@pytest.fixture(scope="module")
+def gtest_run(tmp_path_factory):
+    """The reference's own gtest FILES -- tests/RXMesh_test/test_attribute.cu, test_boundary.cu, test_ev_diamond.cu,
+    test_export.cu, test_for_each.cu -- compiled unmodified into oracle/_ref/ref_gtests, run ONCE in a directory holding the
+    meshes they name, written from the committed fixtures (input/bumpy-cube.obj is not among them: dragon stands in, the
+    ArgMax test does not depend on the geometry).  Own process: some of these tests call cudaDeviceReset()."""
     import subprocess
 
     import numpy as np
@@ -99,14 +104,31 @@ def test_reference_gtest_files(tmp_path):
     exe = os.path.join(REFDIR, "ref_gtests")
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref/ref_gtests not built (needs /root/reference at build time: make -C oracle ref_user_kernels)")
-    inp = tmp_path / "rxm_input"
+    work = tmp_path_factory.mktemp("ref_gtests")
+    inp = work / "rxm_input"
     inp.mkdir()
     for obj, mesh in (("sphere3", "sphere3"), ("cube", "cube"), ("bunnyhead", "bunnyhead"), ("plane_5", "plane_5"),
                       ("bumpy-cube", "dragon")):
         V, F = make_mesh(mesh)
         S._write_obj(str(inp / (obj + ".obj")), np.asarray(V), np.asarray(F))
-    r = subprocess.run([exe], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
-    tail = (r.stdout + r.stderr)[-3000:]
-    assert r.returncode == 0, tail
-    assert "[==========] 16 tests ran, 0 failed" in r.stdout, tail
-    assert os.path.exists(tmp_path / "sphere3.vtk") and os.path.exists(tmp_path / "sphere3.obj")
+    r = subprocess.run([exe], cwd=str(work), capture_output=True, text=True, timeout=600)
+    status = {}
+    for line in r.stdout.split("\n"):
+        if line.startswith("[       OK ] "):
+            status[line[13:].strip()] = True
+        elif line.startswith("[  FAILED  ] "):
+            status[line[13:].strip()] = False
+    return dict(rc=r.returncode, status=status, tail=(r.stdout + r.stderr)[-3000:], work=work)
+
+
+@pytest.mark.parametrize("name", _GTESTS)
+def test_reference_gtest(gtest_run, name):
+    """one of the reference's own TEST()s (see gtest_run): ReduceHandle norm2 / dot / reduce / arg_max, copy_from, add /
+    remove, layouts, tensor SoA on host and device, reset, to_matrix / from_matrix; bunnyhead's 98 boundary vertices through
+    a VertexAttribute<bool>; plane_5's unit diamonds; export_obj / export_vtk; host and device for_each"""
+    assert gtest_run["status"].get(name) is True, gtest_run["tail"]
+
+
+def test_reference_gtest_binary_summary(gtest_run):
+    assert gtest_run["rc"] == 0 and len(gtest_run["status"]) == len(_GTESTS), gtest_run["tail"]
+    assert os.path.exists(gtest_run["work"] / "sphere3.vtk") and os.path.exists(gtest_run["work"] / "sphere3.obj")
