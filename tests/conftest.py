@@ -40,5 +40,33 @@ def make_mesh(name):
     if name.startswith("torus") and "x" in name:
         nu, nv = name[5:].split("x")
         return meshio.torus(int(nu), int(nv), noise=0.2)
+    if name.startswith("damaged"):
+        return damaged_mesh(int(name[7:]))
     g = load_golden(name)
     return g["V"], g["F"]
+
+
+def damaged_mesh(seed):
+    """An icosphere put through what real inputs do (deterministic per seed): a third of the faces removed at random
+    (holes, boundary chains, pieces that hang together by one vertex, several components), some faces flipped (inconsistent
+    orientation: no one-ring fans), and for odd seeds one extra face glued onto an existing edge (a non-manifold edge with
+    three faces: no stored FF / EF rows, EE / EVDiamond unsupported)."""
+    from rxmesh_b200 import meshio
+    rng = np.random.RandomState(1000 + seed)
+    V, F = meshio.icosphere(6)
+    keep = rng.rand(F.shape[0]) > (0.33 if seed < 4 else 0.04)  # seeds >= 4: a few holes, orientation kept -> open fans
+    F = F[keep].copy()
+    flip = rng.rand(F.shape[0]) < (0.1 if seed < 4 else 0.0)
+    F[flip] = F[flip][:, [0, 2, 1]]
+    if seed % 2:
+        a, b = int(F[0, 0]), int(F[0, 1])
+        V = np.concatenate([V, (1.3 * V[a:a + 1] + 0.2).astype(V.dtype)])
+        F = np.concatenate([F, np.asarray([[a, b, V.shape[0] - 1]], dtype=F.dtype)])
+    F = np.ascontiguousarray(F, dtype=np.uint32)
+    # vertices no face references any more are dropped (the builder rejects isolated vertex ids, tested in test_errors)
+    used = np.unique(F)
+    remap = np.full(V.shape[0], -1, np.int64)
+    remap[used] = np.arange(used.shape[0])
+    F = remap[F].astype(np.uint32)
+    V = V[used]
+    return np.ascontiguousarray(V, dtype=np.float32), F

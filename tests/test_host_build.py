@@ -11,7 +11,7 @@ from conftest import make_mesh
 from oracle import oracle as O
 
 MESHES = ["sphere3", "dragon", "cube", "bunnyhead", "plane", "plane_5", "diamond", "sphere1",
-          "torus", "ico6", "grid23x17"]
+          "torus", "ico6", "grid23x17", "damaged0", "damaged1", "damaged2", "damaged3", "damaged4", "damaged8"]
 
 
 @pytest.fixture(scope="module", params=MESHES)

@@ -132,3 +132,20 @@ def test_reference_gtest(gtest_run, name):
 def test_reference_gtest_binary_summary(gtest_run):
     assert gtest_run["rc"] == 0 and len(gtest_run["status"]) == len(_GTESTS), gtest_run["tail"]
     assert os.path.exists(gtest_run["work"] / "sphere3.vtk") and os.path.exists(gtest_run["work"] / "sphere3.obj")
+
+
+# ---- not reference sources, but also added after the last GPU session: the eight queries on damaged inputs ----
+@pytest.fixture(scope="module", params=["damaged0", "damaged1", "damaged3", "damaged8"])
+def damaged(request):
+    """conftest.damaged_mesh: holes, several components, flipped faces (no fans), a non-manifold edge with three faces
+    (odd seeds: the generic FF / EF paths, no stored rows), or holes with the orientation kept (8: open fans)"""
+    from conftest import make_mesh
+    from oracle import oracle as O
+    V, F = make_mesh(request.param)
+    return request.param, V, F, rx.RXMeshStatic(F, patch_size=64), O.Topology(F)
+
+
+@pytest.mark.parametrize("op", ["VV", "VE", "VF", "EV", "EF", "FV", "FE", "FF"])
+def test_queries_on_damaged_meshes(damaged, op):
+    import test_gpu_queries as Q
+    Q.test_query(damaged, op)
