@@ -149,3 +149,24 @@ def damaged(request):
 def test_queries_on_damaged_meshes(damaged, op):
     import test_gpu_queries as Q
     Q.test_query(damaged, op)
+
+
+@pytest.fixture(scope="module", params=["damaged5", "damaged8"])
+def damaged_apps(request):
+    """orientation kept, a few holes: 5 adds a non-manifold edge (no fans: the transposing fallbacks of the fixed-function
+    kernels), 8 keeps the fans with open ones around the holes"""
+    from conftest import make_mesh
+    from oracle import oracle as O
+    rx.rx_init(0)
+    V, F = make_mesh(request.param)
+    return request.param, V, F, rx.RXMeshStatic(F, patch_size=64), O.Topology(F)
+
+
+def test_vertex_normals_on_damaged_meshes(damaged_apps):
+    import test_gpu_apps as A
+    A.test_vertex_normals(damaged_apps)
+
+
+def test_laplacian_on_damaged_meshes(damaged_apps):
+    import test_gpu_apps as A
+    A.test_laplacian(damaged_apps)
