@@ -5,7 +5,9 @@ tests/RXMesh_test/query_kernel.cuh and tests/RXMesh_test/higher_query.cuh; libsh
 apps/Filtering/filtering_rxmesh_kernel.cuh (+ filtering_util.h).  They are built by `make -C oracle ref_user_kernels`
 where /root/reference exists (sources are included from there, never copied) behind the drivers of tests/cpp/shim_apps.cu,
 so the checks are those of tests/test_gpu_shim.py -- same inputs, same oracle comparisons -- with the reference's kernels
-in place of the restated ones.  (The file name sorts last on purpose: these are the newest checks.)"""
+in place of the restated ones.  (The file name sorts last on purpose: these are the newest checks.)  The end of the file
+also holds the other GPU checks written after the last GPU session of round 1: queries, vertex normals and Laplacian
+smoothing on damaged meshes (conftest.damaged_mesh)."""
 import ctypes as C
 import os
 
