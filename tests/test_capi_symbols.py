@@ -23,3 +23,15 @@ def test_all_declared_symbols_exported():
 def test_version_and_error_string():
     assert b"sm_100a" in rx.lib().rxm_version()
     assert rx.lib().rxm_mesh_info(None, 0) == 0
+
+
+def test_header_is_plain_c(tmp_path):
+    """the boundary is a C ABI: include/rxmesh_b200.h must compile as C99 (no torch / C++ types in the signatures)"""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        return
+    src = tmp_path / "c_abi.c"
+    src.write_text('#include "rxmesh_b200.h"\nint main(void) { return 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-c", str(src), "-o", str(tmp_path / "c_abi.o")])
