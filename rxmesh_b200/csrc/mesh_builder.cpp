@@ -37,17 +37,19 @@ void exclusive_scan(std::vector<T, A>& a)
 // ---------------------------------------------------------------------------
 // Edge numbering (reference semantics: rxmesh.cpp:589-611, util/util.h:410-416)
 // ---------------------------------------------------------------------------
-uint32_t build_edges(const uint32_t* fv, uint32_t nf, uint32_t nv, std::vector<uint32_t>& ev,
-                     std::vector<uint32_t>& fe)
+uint32_t build_edges(const uint32_t* fv, uint32_t nf, uint32_t nv, U32Buf& ev, U32Buf& fe)
 {
     const uint64_t H = 3ull * nf;
-    fe.assign(H, 0);
+    fe.resize(H);  // uninitialised: every entry is written by the last pass
     if (nf == 0) {
         ev.clear();
         return 0;
     }
     // 1. bucket half-edges by their smaller endpoint
-    std::vector<uint32_t> off((size_t)nv + 1, 0);
+    U32Buf off((size_t)nv + 1);
+#pragma omp parallel for schedule(static)
+    for (int64_t v = 0; v <= (int64_t)nv; ++v)
+        off[v] = 0;
 #pragma omp parallel for schedule(static)
     for (int64_t h = 0; h < (int64_t)H; ++h) {
         const uint32_t f = (uint32_t)(h / 3), j = (uint32_t)(h % 3);
@@ -61,7 +63,10 @@ uint32_t build_edges(const uint32_t* fv, uint32_t nf, uint32_t nv, std::vector<u
         uint32_t hi, h;
     };
     std::vector<HE, NoInitAlloc<HE>> bucket(H);  // every slot is written by the scatter below
-    std::vector<uint32_t> cur(off.begin(), off.end() - 1);
+    U32Buf cur((size_t)nv);
+#pragma omp parallel for schedule(static)
+    for (int64_t v = 0; v < (int64_t)nv; ++v)
+        cur[v] = off[v];
 #pragma omp parallel for schedule(static)
     for (int64_t h = 0; h < (int64_t)H; ++h) {
         const uint32_t f = (uint32_t)(h / 3), j = (uint32_t)(h % 3);
@@ -94,7 +99,7 @@ uint32_t build_edges(const uint32_t* fv, uint32_t nf, uint32_t nv, std::vector<u
     }
     exclusive_scan(first);
     const uint32_t ne = first[H];
-    ev.assign(2ull * ne, 0);
+    ev.resize(2ull * ne);  // uninitialised: the first half-edge of every edge writes its pair
 #pragma omp parallel for schedule(static)
     for (int64_t h = 0; h < (int64_t)H; ++h) {
         const uint32_t e = first[rep[h]];
@@ -834,8 +839,15 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
     for (int t = 0; t < 3; ++t) {
         M.num_slots[t] = M.slot_base[t][P];
         if (M.lin_base[t][P] != M.num_elems[t]) return "build_mesh: internal error, ownership does not partition the mesh";
-        M.slot_to_global[t].assign(M.num_slots[t], INVALID32_);
-        M.global_to_slot[t].assign(M.num_elems[t], INVALID32_);
+        M.slot_to_global[t].resize(M.num_slots[t]);  // uninitialised: filled in parallel below
+        M.global_to_slot[t].resize(M.num_elems[t]);
+        uint32_t *s2g = M.slot_to_global[t].data(), *g2s = M.global_to_slot[t].data();
+        const int64_t ns = M.num_slots[t], ng = M.num_elems[t];
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < std::max(ns, ng); ++i) {
+            if (i < ns) s2g[i] = INVALID32_;
+            if (i < ng) g2s[i] = INVALID32_;
+        }
         M.ltog[t].resize(M.ltog_off[t][P]);
     }
     M.topo.resize(topo_total + 16);
@@ -962,7 +974,7 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
     }
     if (!opt.keep_ltog)
         for (int t = 0; t < 3; ++t) {
-            std::vector<uint32_t>().swap(M.ltog[t]);
+            U32Buf().swap(M.ltog[t]);
         }
     lap("topology");
     M.build_seconds = now_s() - t_start;

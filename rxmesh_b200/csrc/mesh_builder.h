@@ -37,6 +37,7 @@ struct NoInitAlloc : std::allocator<T>
     }
 };
 using ByteBuf = std::vector<uint8_t, NoInitAlloc<uint8_t>>;
+using U32Buf  = std::vector<uint32_t, NoInitAlloc<uint32_t>>;  // the element-count-sized id maps: filled by all cores
 
 struct HostMesh
 {
@@ -68,15 +69,15 @@ struct HostMesh
     std::vector<uint32_t>  lin_base[3];   // [P+1]
 
     // ---- id maps ----
-    std::vector<uint32_t> ltog[3];      // concatenated local->global, per patch (owned first)
+    U32Buf                ltog[3];      // concatenated local->global, per patch (owned first)
     std::vector<uint64_t> ltog_off[3];  // [P+1]
-    std::vector<uint32_t> slot_to_global[3];  // [num_slots], INVALID32_ for padding slots
-    std::vector<uint32_t> global_to_slot[3];  // [num_elems]
+    U32Buf                slot_to_global[3];  // [num_slots], INVALID32_ for padding slots
+    U32Buf                global_to_slot[3];  // [num_elems]
     std::vector<uint32_t> elem_patch[3];      // [num_elems] owner patch of every element
 
     // global edges (kept for host-side queries such as get_edge_id)
-    std::vector<uint32_t> ev;  // 2*E: (larger id, smaller id)
-    std::vector<uint32_t> fe;  // 3*F: global edge ids
+    U32Buf ev;  // 2*E: (larger id, smaller id)
+    U32Buf fe;  // 3*F: global edge ids
 };
 
 struct BuildOptions
@@ -93,8 +94,7 @@ struct BuildOptions
 // Global edge numbering identical to the reference (first appearance while
 // scanning faces, rxmesh.cpp:589-611) computed with counting sorts instead of a
 // hash map. ev: 2*E (max id, min id); fe: 3*F. Returns the number of edges.
-uint32_t build_edges(const uint32_t* fv, uint32_t nf, uint32_t nv, std::vector<uint32_t>& ev,
-                     std::vector<uint32_t>& fe);
+uint32_t build_edges(const uint32_t* fv, uint32_t nf, uint32_t nv, U32Buf& ev, U32Buf& fe);
 
 // Deterministic Lloyd clustering of faces over the face-adjacency graph; the
 // role of patcher::Patcher::run_lloyd (patcher/patcher.cu:828-987).

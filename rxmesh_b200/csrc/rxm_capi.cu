@@ -288,11 +288,11 @@ int rxm_mesh_compact(rxm_mesh* m)
     if (!m) return fail(RXM_ERR_INVALID, "rxm_mesh_compact: null mesh");
     HostMesh& h = m->h;
     for (int t = 0; t < 3; ++t) {
-        std::vector<uint32_t>().swap(h.ltog[t]);
+        U32Buf().swap(h.ltog[t]);
         std::vector<uint64_t>().swap(h.ltog_off[t]);
     }
-    std::vector<uint32_t>().swap(h.ev);
-    std::vector<uint32_t>().swap(h.fe);
+    U32Buf().swap(h.ev);
+    U32Buf().swap(h.fe);
     if (m->on_device) ByteBuf().swap(h.topo);  // the device holds the patch store
     return RXM_OK;
 }
