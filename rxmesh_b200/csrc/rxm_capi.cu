@@ -507,8 +507,11 @@ int rxm_attr_create(rxm_mesh* m, int elem, uint32_t elem_bytes, uint32_t nattr, 
             return fail(RXM_ERR_CUDA, "rxm_attr_create: DEVICE location requested but the mesh is not on a device");
         }
         cudaError_t e = cudaMalloc(&a->d, bytes);
-        if (e == cudaSuccess) e = cudaMemset(a->d, 0, bytes);  // defined contents: the reference's own tests read components
-                                                               // they never wrote and expect zero (test_attribute.cu:56-79)
+        // defined contents: the reference's own tests read components they never wrote and expect zero
+        // (test_attribute.cu:56-79).  The fill runs on the legacy default stream, which non-blocking streams (PyTorch's, the
+        // pipeline's) do not wait for: it must be complete before the caller can launch anything that writes the attribute.
+        if (e == cudaSuccess) e = cudaMemset(a->d, 0, bytes);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(0);
         if (e != cudaSuccess) {
             if (a->d) cudaFree(a->d);
             delete a;
