@@ -148,11 +148,13 @@ def cpu_pass_seconds(V, F, T, vv, vf, repeats, threads=1):
 
 
 def host_threads():
-    from oracle import oracle as O
+    """cores this process may run on.  NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to every rank, which
+    would silently turn the all-cores CPU arm into a 1-thread run at N > 1 (the oracle's *_mt entry points take the thread
+    count explicitly)."""
     try:
-        return max(1, min(O.max_threads(), len(os.sched_getaffinity(0))))
+        return max(1, len(os.sched_getaffinity(0)))
     except Exception:  # noqa: BLE001
-        return 1
+        return max(1, os.cpu_count() or 1)
 
 
 def cpu_baseline(sample_faces, repeats):
@@ -279,7 +281,7 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = grid_side(args.faces)
-    ncores = os.cpu_count() or 8
+    ncores = host_threads()
     t0 = time.perf_counter()
     hx_v = hx_f = None
     if world == 1:
@@ -443,7 +445,7 @@ def run_ours(args, rank, world, local_rank):
     total_ms, te = float(tm[0]), float(tm[1])
     k_ms = [float(v) for v in tm[2:5]]
     if rank != 0:
-        return
+        return None
     ms_step = total_ms / args.steps
     peak, peak_src = peaks()
     kern = {}
@@ -492,7 +494,7 @@ def run_ours(args, rank, world, local_rank):
         cb, _ = cpu_baseline(min(args.faces, args.cpu_sample_faces), 3)
         line["cpu_baseline"] = cb
         line["reference_gpu"] = reference_gpu_sample(min(args.faces, args.cpu_sample_faces))
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def run_laplacian(args, rank, world, local_rank, mesh, x, y, hx_v, nv_single, n, t_build, torch, rx, stream, fused=None):
@@ -574,6 +576,10 @@ def main():
     ap.add_argument("--workload", default="queries", choices=["queries", "laplacian"],
                     help="queries = the headline VV+VF+normals pass; laplacian = iterated smoothing (configs[4])")
     ap.add_argument("--iters", type=int, default=100, help="Laplacian iterations per step")
+    ap.add_argument("--sub", default="all",
+                    help="sub-records next to the headline: all | none | comma list of dragon,queries,bilateral,hardwired,laplacian")
+    ap.add_argument("--lap-faces", type=int, default=0, help="faces of the strong-scaled Laplacian mesh (default: 400M, configs[4])")
+    ap.add_argument("--sub-timeout", type=int, default=600, help="seconds after which the sub-records are abandoned")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -581,8 +587,38 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
+    import gc
+    line, done = None, threading.Event()
+
+    def emit():
+        if rank == 0 and line is not None and not done.is_set():
+            done.set()
+            print(json.dumps(line), flush=True)
+
+    def watchdog():
+        # a hung sub-record (one rank failing inside a collective) must not cost the headline: print what we have and leave
+        if rank == 0 and line is not None:
+            line.setdefault("sub_records_error", "watchdog: sub-records exceeded %d s" % args.sub_timeout)
+        emit()
+        os._exit(0 if line is not None or rank != 0 else 1)
+
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.workload == "laplacian":
+            run_ours(args, rank, world, local_rank)
+            return
+        line = run_ours(args, rank, world, local_rank)
+        gc.collect()
+        import torch
+        torch.cuda.empty_cache()
+        subs = set() if args.sub == "none" else set(args.sub.split(","))
+        timer = threading.Timer(args.sub_timeout, watchdog)
+        timer.daemon = True
+        timer.start()
+        try:
+            run_sub_records(args, rank, world, local_rank, line, subs)
+        finally:
+            timer.cancel()
+        emit()
     finally:
         if world > 1:
             import torch.distributed as dist
@@ -590,5 +626,48 @@ def main():
                 dist.destroy_process_group()
 
 
-if __name__ == "__main__":
-    main()
+def run_sub_records(args, rank, world, local_rank, line, subs):
+    """BASELINE.json configs[0..2] (1 GPU only) and configs[4] (every N) next to the headline, each with an in-run parity
+    flag; bench_configs.py holds the workloads.  A failing sub-record reports its error and leaves the rest alone."""
+    import traceback
+
+    import torch
+
+    import bench_configs as BC
+    import rxmesh_b200 as rx
+    stream = torch.cuda.current_stream()
+    want = lambda k: "all" in subs or k in subs  # noqa: E731
+
+    def guarded(fn):
+        t0 = time.perf_counter()
+        try:
+            r = fn()
+        except Exception as e:  # noqa: BLE001
+            r = {"error": (type(e).__name__ + ": " + str(e))[:300], "trace": traceback.format_exc()[-600:]}
+        if isinstance(r, dict):
+            r["wall_seconds"] = round(time.perf_counter() - t0, 2)
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        return r
+
+    if world == 1:
+        cfg = {}
+        if want("dragon"):
+            cfg["1_vertex_normal_dragon"] = guarded(lambda: BC.config_dragon(torch, rx, stream))
+        if want("queries"):
+            cfg["2_eight_queries_10m_sphere"] = guarded(lambda: BC.config_queries(torch, rx, stream))
+        if want("bilateral"):
+            cfg["3_bilateral_10m_torus"] = guarded(lambda: BC.config_bilateral(torch, rx, stream))
+        if cfg and line is not None:
+            line["configs"] = cfg
+        if want("hardwired") and line is not None and isinstance(line.get("reference_gpu"), dict):
+            hw = guarded(lambda: BC.hardwired_baseline(grid_side(args.faces)))
+            line["reference_gpu"]["hardwired"] = hw
+            if "hardwired_ms" in hw:
+                line["reference_gpu"]["hardwired_ms"] = hw["hardwired_ms"]
+                line["reference_gpu"]["ours_vn_ms"] = line["kernels"]["VN"]["ms"]
+    if want("laplacian"):
+        rec = guarded(lambda: BC.laplacian_400m(args, rank, world, local_rank, torch, rx, TILE, TILE_I))
+        if line is not None:
+            line["laplacian_400m"] = rec

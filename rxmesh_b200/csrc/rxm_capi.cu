@@ -907,6 +907,8 @@ int rxm_query_csr(rxm_mesh* m, int op, uint32_t** dev_off, uint32_t** dev_val, u
     if (op_src(op) < 0 || !dev_off || !dev_val || !nnz) return fail(RXM_ERR_INVALID, "rxm_query_csr: bad argument");
     if (m->active_count && m->active_count != m->h.num_patches)
         return fail(RXM_ERR_UNSUPPORTED, "rxm_query_csr: not available on a shard (active patch range set)");
+    if (op == RXM_OP_EE || op == RXM_OP_EVDIAMOND)
+        return fail(RXM_ERR_UNSUPPORTED, "rxm_query_csr: Op::EE / Op::EVDiamond have no CSR form (fixed-width results; use rxm_query_store)");
     auto& C = m->csr[op];
     if (!C.off && m->h.topo.empty())
         return fail(RXM_ERR_INVALID, "rxm_query_csr: host patch store was released (rxm_mesh_compact)");
@@ -921,19 +923,30 @@ int rxm_query_csr(rxm_mesh* m, int op, uint32_t** dev_off, uint32_t** dev_val, u
         if (run > 0xFFFFFFFFull) return fail(RXM_ERR_UNSUPPORTED, "rxm_query_csr: more than 2^32 entries");
         pno[h.num_patches] = (uint32_t)run;
         const uint32_t ns  = h.num_slots[op_src(op)];
-        uint32_t*      d_pno = nullptr;
-        CU(cudaMalloc(&d_pno, pno.size() * 4));
-        CU(cudaMemcpyAsync(d_pno, pno.data(), pno.size() * 4, cudaMemcpyHostToDevice, (cudaStream_t)stream));
-        CU(cudaMalloc(&C.off, ((size_t)ns + 1) * 4));
-        CU(cudaMalloc(&C.val, std::max<size_t>(run, 1) * 4));
-        const char* why = nullptr;
-        cudaError_t e   = launch_query_csr(op, m->view, m->lim, d_pno, C.off, C.val, (cudaStream_t)stream, &why);
-        if (e != cudaSuccess) return kernel_status(e, why, "rxm_query_csr");
-        const uint32_t total = (uint32_t)run;
-        CU(cudaMemcpyAsync(C.off + ns, &total, 4, cudaMemcpyHostToDevice, (cudaStream_t)stream));
-        CU(cudaStreamSynchronize((cudaStream_t)stream));
-        CU(cudaFree(d_pno));
-        C.nnz = run;
+        // built into local pointers and published to the cache only when the kernel and the stream sync succeeded: a failed
+        // build must not leave a half-initialised CSR behind for the next call to return
+        uint32_t *d_pno = nullptr, *off = nullptr, *val = nullptr;
+        auto      build = [&]() -> int {
+            CU(cudaMalloc(&d_pno, pno.size() * 4));
+            CU(cudaMemcpyAsync(d_pno, pno.data(), pno.size() * 4, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+            CU(cudaMalloc(&off, ((size_t)ns + 1) * 4));
+            CU(cudaMalloc(&val, std::max<size_t>(run, 1) * 4));
+            const char* why = nullptr;
+            cudaError_t e   = launch_query_csr(op, m->view, m->lim, d_pno, off, val, (cudaStream_t)stream, &why);
+            if (e != cudaSuccess) return kernel_status(e, why, "rxm_query_csr");
+            const uint32_t total = (uint32_t)run;
+            CU(cudaMemcpyAsync(off + ns, &total, 4, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+            CU(cudaStreamSynchronize((cudaStream_t)stream));
+            return RXM_OK;
+        };
+        rc = build();
+        if (d_pno) cudaFree(d_pno);
+        if (rc) {
+            if (off) cudaFree(off);
+            if (val) cudaFree(val);
+            return rc;
+        }
+        C.off = off, C.val = val, C.nnz = run;
     }
     *dev_off = C.off, *dev_val = C.val, *nnz = C.nnz;
     return RXM_OK;
@@ -1224,7 +1237,8 @@ int rxm_attr_push_slots(rxm_attr* a, const uint32_t* dev_local_idx, void* remote
 struct rxm_fused_halo
 {
     rxm_mesh* m        = nullptr;
-    uint32_t  npeers   = 0, n_push_blocks = 0, shift = 0;
+    uint32_t  npeers   = 0, n_sync_blocks = 0, shift = 0;
+    std::vector<uint8_t> reads;  // host copy of d_reads
     uint32_t *d_flags = nullptr, *d_ctr = nullptr, *d_push_off = nullptr;
     uint2*    d_push  = nullptr;
     uint8_t*  d_reads = nullptr;
@@ -1257,6 +1271,7 @@ int rxm_fused_halo_create(rxm_mesh* m, uint32_t npeers, rxm_fused_halo** out)
     }
     CU(cudaMalloc(&h->d_reads, std::max<size_t>(reads.size(), 1)));
     CU(cudaMemcpy(h->d_reads, reads.data(), reads.size(), cudaMemcpyHostToDevice));
+    h->reads.swap(reads);
     *out = h;
     return RXM_OK;
 }
@@ -1275,9 +1290,18 @@ int rxm_fused_halo_set(rxm_fused_halo* h, const uint32_t* push_off, const uint32
     if (!h || !push_off || !peer_attr_a || !peer_attr_b || !peer_flag) return fail(RXM_ERR_INVALID, "rxm_fused_halo_set: null argument");
     const uint32_t P = h->m->h.num_patches;
     if (push_off[P] != n_push) return fail(RXM_ERR_INVALID, "rxm_fused_halo_set: push_off does not end at n_push");
-    h->n_push_blocks = 0;
-    for (uint32_t p = 0; p < P; ++p)
-        h->n_push_blocks += push_off[p + 1] > push_off[p] ? 1u : 0u;
+    uint32_t n_push_blocks = 0;
+    h->n_sync_blocks       = 0;
+    {   // blocks that check in at the step counter: the ACTIVE patches that read ghost slots or push rows
+        const uint32_t a0 = h->m->active_count ? h->m->active_first : 0, cnt = h->m->active_count ? h->m->active_count : P;
+        for (uint32_t p = 0; p < P; ++p) {
+            const bool pushes = push_off[p + 1] > push_off[p];
+            if (pushes && (p < a0 || p >= a0 + cnt))
+                return fail(RXM_ERR_INVALID, "rxm_fused_halo_set: a patch outside the active range has rows to push");
+            n_push_blocks += pushes ? 1u : 0u;
+            if (p >= a0 && p < a0 + cnt && (pushes || h->reads[p])) ++h->n_sync_blocks;
+        }
+    }
     {   // rotation: start the launch at the first pushing patch of the upper half of the active range
         const uint32_t a0 = h->m->active_count ? h->m->active_first : 0, cnt = h->m->active_count ? h->m->active_count : P;
         h->shift = 0;
@@ -1287,7 +1311,7 @@ int rxm_fused_halo_set(rxm_fused_halo* h, const uint32_t* push_off, const uint32
                 break;
             }
     }
-    if (h->n_push_blocks == 0) return fail(RXM_ERR_INVALID, "rxm_fused_halo_set: nothing to push (no neighbour shares an element)");
+    if (n_push_blocks == 0) return fail(RXM_ERR_INVALID, "rxm_fused_halo_set: nothing to push (no neighbour shares an element)");
     std::vector<uint2> e(std::max<uint64_t>(n_push, 1));
     for (uint64_t i = 0; i < n_push; ++i)
         e[i] = make_uint2(push_lid_peer[i], push_slot[i]);
@@ -1325,7 +1349,7 @@ int rxm_laplacian_smooth_fused(rxm_mesh* m, rxm_attr* in, rxm_attr* out, double 
     v.push_off = h->d_push_off, v.push = h->d_push, v.peer_out = h->d_peer_attr[out_is_b ? 1 : 0];
     v.peer_flag = h->d_peer_flag, v.reads_ghost = h->d_reads, v.flags = h->d_flags, v.done_ctr = h->d_ctr;
     v.npeers = h->npeers, v.first = m->active_count ? m->active_first : 0, v.step = step;
-    v.n_push_blocks = h->n_push_blocks, v.shift = h->shift;
+    v.n_sync_blocks = h->n_sync_blocks, v.shift = h->shift;
     const char* why = nullptr;
     cudaError_t e   = launch_laplacian_step_fused(m->view, m->lim, (const float*)in->d, (float*)out->d, lr, v,
                                                   (cudaStream_t)stream, &why);

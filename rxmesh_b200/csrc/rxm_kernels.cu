@@ -523,6 +523,10 @@ struct FanPatch2
     uint32_t        nv, nov, cap;
 };
 
+// COHERENT: the ribbon gathers may read ghost slots that a peer GPU wrote WHILE this kernel is running (fused halo
+// exchange): they must not go through the non-coherent (.nc) path, which lies outside the PTX memory model and could
+// serve a stale L1 sector; ld.global.cg is an ordinary (weak) load cached in L2 only, ordered by the acquire + barrier.
+template <bool COHERENT = false>
 __device__ __forceinline__ FanPatch2 fan_load2(const MeshView& mv, const PatchDesc& d, const float* __restrict__ x,
                                                uint8_t* smem_raw, uint64_t* bar)
 {
@@ -552,7 +556,8 @@ __device__ __forceinline__ FanPatch2 fan_load2(const MeshView& mv, const PatchDe
     for (uint32_t i = F.nov + threadIdx.x; i < F.nv; i += BT2) {  // ribbon vertices: from their owners' slots
         const uint32_t o = s_own[i - F.nov];
         const float*   g = x + 3ull * ((uint64_t)s_stash[o >> 16].slot_base[ELEM_V] + (o & 0xFFFFu));
-        const float    a = ldg_stream(g), b = ldg_stream(g + 1), c = ldg_stream(g + 2);
+        const float    a = COHERENT ? __ldcg(g) : ldg_stream(g), b = COHERENT ? __ldcg(g + 1) : ldg_stream(g + 1),
+                    c = COHERENT ? __ldcg(g + 2) : ldg_stream(g + 2);
         s_x[3 * i] = a, s_x[3 * i + 1] = b, s_x[3 * i + 2] = c;
     }
     __syncthreads();
@@ -693,6 +698,14 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Flag protocol of the fused variant (two attribute buffers A / B, step s reads buf[s & 1] and writes buf[~s & 1], also
+// into the neighbours' ghost slots of that buffer).  flag value s on a neighbour means "every row of my steps < s has
+// landed in your ghost slots AND every block of mine that reads ghost slots has finished reading for steps < s".  The
+// second half matters: the neighbour's step-s pushes overwrite the ghost slots my step s-1 blocks read, so the flag may
+// only go up once ALL of them -- including patches that read ghost values but push nothing, e.g. a patch that touches the
+// rank boundary only through vertices owned by lower-id patches -- are past their loads.  Every block that reads ghost
+// slots or pushes rows therefore checks in at done_ctr (readers right after their gathers, pushers after their fenced
+// stores) and the last one raises the flags.
 template <bool FUSED>
 __global__ void __launch_bounds__(BT2, 8) k_laplacian_fan2(MeshView mv, const float* __restrict__ x, float* __restrict__ xo,
                                                          double lr, FusedHaloView fh)
@@ -703,16 +716,29 @@ __global__ void __launch_bounds__(BT2, 8) k_laplacian_fan2(MeshView mv, const fl
     // first and the neighbours' flags are raised early in the launch, not at its end
     const uint32_t  bidx = FUSED ? (blockIdx.x + fh.shift) % gridDim.x : blockIdx.x;
     const PatchDesc d    = load_desc(mv.desc + bidx);
+    bool            syncs = false, pushes = false;
     if (FUSED) {
         // ghost slots hold what the neighbours pushed at the end of THEIR previous step: wait for their flags
         const uint32_t lp0 = fh.first + bidx;
-        if (fh.reads_ghost[lp0] || fh.push_off[lp0 + 1] > fh.push_off[lp0]) {
+        pushes = fh.push_off[lp0 + 1] > fh.push_off[lp0];
+        syncs  = fh.reads_ghost[lp0] || pushes;
+        if (syncs) {
             if (threadIdx.x < fh.npeers)
                 while (ld_acquire_sys(fh.flags + threadIdx.x) < fh.step) {}
             __syncthreads();
         }
     }
-    const FanPatch2 F = fan_load2(mv, d, x, smem_raw, &bar);
+    const FanPatch2 F = fan_load2<FUSED>(mv, d, x, smem_raw, &bar);
+    auto check_in = [&]() {  // thread 0 of a block whose ghost reads (and pushes) are complete
+        if (atomicAdd(fh.done_ctr, 1u) == fh.n_sync_blocks - 1) {
+            *fh.done_ctr = 0;
+            __threadfence_system();
+            for (uint32_t q = 0; q < fh.npeers; ++q)
+                st_release_sys(fh.peer_flag[q], fh.step + 1);
+        }
+    };
+    // fan_load2 ends with a barrier behind the ribbon gathers: a block that only READS ghost slots is done with them
+    if (FUSED && syncs && !pushes && threadIdx.x == 0) check_in();
     for (uint32_t vA = threadIdx.x; vA < F.cap; vA += 2 * BT2) {
         const uint32_t vB = vA + BT2;
         bool           fast = false;
@@ -762,28 +788,20 @@ __global__ void __launch_bounds__(BT2, 8) k_laplacian_fan2(MeshView mv, const fl
         bulk_commit();
         bulk_wait_all_read();
     }
-    if (FUSED) {
+    if (FUSED && pushes) {
         // rows mirrored on other GPUs go straight into the neighbours' ghost slots (NVLink P2P stores); only the few
-        // blocks that have such rows pay for the system-scope fence, and the last of THEM tells every neighbour that
-        // this step's rows are all there
+        // blocks that have such rows pay for the system-scope fence
         const uint32_t lp = fh.first + bidx;
         const uint32_t pb = fh.push_off[lp], pe = fh.push_off[lp + 1];
-        if (pe > pb) {
-            for (uint32_t i = pb + threadIdx.x; i < pe; i += BT2) {
-                const uint2  e   = fh.push[i];
-                const float* src = F.s_out + 3u * (e.x & 0xFFFFu);
-                float*       dst = fh.peer_out[e.x >> 16] + 3ull * e.y;
-                dst[0] = src[0], dst[1] = src[1], dst[2] = src[2];
-            }
-            __threadfence_system();
-            __syncthreads();
-            if (threadIdx.x == 0 && atomicAdd(fh.done_ctr, 1u) == fh.n_push_blocks - 1) {
-                *fh.done_ctr = 0;
-                __threadfence_system();
-                for (uint32_t q = 0; q < fh.npeers; ++q)
-                    st_release_sys(fh.peer_flag[q], fh.step + 1);
-            }
+        for (uint32_t i = pb + threadIdx.x; i < pe; i += BT2) {
+            const uint2  e   = fh.push[i];
+            const float* src = F.s_out + 3u * (e.x & 0xFFFFu);
+            float*       dst = fh.peer_out[e.x >> 16] + 3ull * e.y;
+            dst[0] = src[0], dst[1] = src[1], dst[2] = src[2];
         }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) check_in();
     }
 }
 

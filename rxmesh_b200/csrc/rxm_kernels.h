@@ -40,10 +40,10 @@ struct FusedHaloView
     uint32_t* const* peer_flag;    // [npeers] address, in the neighbour's memory, of its flags[me]
     const uint8_t*   reads_ghost;  // [P] the patch has ribbon elements owned by a ghost patch
     uint32_t*        flags;        // [npeers] raised by the neighbours (step count they have finished)
-    uint32_t*        done_ctr;     // blocks of this launch that have pushed their rows
+    uint32_t*        done_ctr;     // blocks of this launch that are past their ghost reads and pushes
     uint32_t         npeers, first, step;
     uint32_t         shift;          // block b works on patch (b + shift) % #patches
-    uint32_t         n_push_blocks;  // patches of the active range with at least one row to push
+    uint32_t         n_sync_blocks;  // patches of the active range that read ghost slots or have rows to push
 };
 cudaError_t launch_laplacian_step_fused(const MeshView& mv, const KernelLimits& lim, const float* x_in_aos, float* x_out_aos,
                                         double lr, const FusedHaloView& fh, cudaStream_t stream, const char** err);

@@ -22,7 +22,7 @@ import numpy as np
 
 from . import meshio
 from ._lib import check, lib, u32p
-from .mesh import AoS, DEVICE, HOST, RXMeshStatic, _stream_ptr
+from .mesh import AoS, DEVICE, HOST, RXMeshStatic, SoA, _stream_ptr
 
 
 def patch_ranges(face_patch, world):
@@ -156,7 +156,9 @@ class HaloExchange:
         if key not in self._dev["bufs"]:
             import torch
             dev = torch.device("cuda", torch.cuda.current_device())
-            words = attr.num_attributes * attr.dtype.itemsize // 4
+            row_bytes = attr.num_attributes * attr.dtype.itemsize
+            assert row_bytes % 4 == 0, "halo rows travel as 32-bit words: the row size must be a multiple of 4 bytes"
+            words = row_bytes // 4
             self._dev["bufs"][key] = (
                 {p: torch.empty((len(v), words), dtype=torch.int32, device=dev) for p, v in self.send.items()},
                 {p: torch.empty((len(v), words), dtype=torch.int32, device=dev) for p, v in self.recv.items()})
@@ -164,7 +166,8 @@ class HaloExchange:
 
     def exchange(self, attr, stream=None):
         """Fill the ghost slots of `attr` (AoS) with the owners' current values."""
-        assert attr.elem == self.elem and attr.layout == AoS or attr.num_attributes == 1
+        assert attr.elem == self.elem and (attr.layout == AoS or (attr.num_attributes == 1 and attr.layout != SoA)), \
+            "halo rows are addressed by slot: an AoS (or single-component AoSoA) attribute of the plan's element type"
         if attr.location & DEVICE and self.dist.get_backend(self.group) == "nccl":
             return self._exchange_device(attr, stream)
         return self._exchange_host(attr)
@@ -172,22 +175,26 @@ class HaloExchange:
     def _exchange_device(self, attr, stream):
         import torch
         st, (sbuf, rbuf) = self._device_state(attr)
-        sp = _stream_ptr(stream if stream is not None else torch.cuda.current_stream())
-        for p, idx in st["send_idx"].items():
-            check(lib().rxm_attr_gather_slots(attr._h, C.c_void_p(idx.data_ptr()), idx.numel(),
-                                              C.c_void_p(sbuf[p].data_ptr()), sp))
-        ops = []
-        for p in sorted(set(sbuf) | set(rbuf)):
-            if p in sbuf:
-                ops.append(self.dist.P2POp(self.dist.isend, sbuf[p], p, group=self.group))
-            if p in rbuf:
-                ops.append(self.dist.P2POp(self.dist.irecv, rbuf[p], p, group=self.group))
-        if ops:
-            for w in self.dist.batch_isend_irecv(ops):
-                w.wait()
-        for p, idx in st["recv_idx"].items():
-            check(lib().rxm_attr_scatter_slots(attr._h, C.c_void_p(idx.data_ptr()), idx.numel(),
-                                               C.c_void_p(rbuf[p].data_ptr()), sp))
+        stream = stream if stream is not None else torch.cuda.current_stream()
+        sp = _stream_ptr(stream)
+        # gather, NCCL send/recv and scatter are all ordered on `stream`: torch's collectives order against the CURRENT
+        # stream, so it is made current for the duration of the exchange
+        with torch.cuda.stream(stream):
+            for p, idx in st["send_idx"].items():
+                check(lib().rxm_attr_gather_slots(attr._h, C.c_void_p(idx.data_ptr()), idx.numel(),
+                                                  C.c_void_p(sbuf[p].data_ptr()), sp))
+            ops = []
+            for p in sorted(set(sbuf) | set(rbuf)):
+                if p in sbuf:
+                    ops.append(self.dist.P2POp(self.dist.isend, sbuf[p], p, group=self.group))
+                if p in rbuf:
+                    ops.append(self.dist.P2POp(self.dist.irecv, rbuf[p], p, group=self.group))
+            if ops:
+                for w in self.dist.batch_isend_irecv(ops):
+                    w.wait()
+            for p, idx in st["recv_idx"].items():
+                check(lib().rxm_attr_scatter_slots(attr._h, C.c_void_p(idx.data_ptr()), idx.numel(),
+                                                   C.c_void_p(rbuf[p].data_ptr()), sp))
 
     def _exchange_host(self, attr):
         import torch
@@ -234,12 +241,13 @@ class HaloExchange:
         """One store kernel per neighbour writes my owned boundary rows straight into the neighbour's
         ghost slots over NVLink; the barrier makes the pushes visible before anyone reads."""
         import torch
-        sp = _stream_ptr(stream if stream is not None else torch.cuda.current_stream())
+        stream = stream if stream is not None else torch.cuda.current_stream()
+        sp = _stream_ptr(stream)
         for p, (ptr, lidx, ridx) in peers.items():
             check(lib().rxm_attr_push_slots(attr._h, C.c_void_p(lidx.data_ptr()), ptr, C.c_void_p(ridx.data_ptr()),
                                             lidx.numel(), sp))
         if barrier:
-            torch.cuda.current_stream().synchronize()
+            stream.synchronize()  # the stream the pushes were issued on
             self.dist.barrier(group=self.group)
 
 
@@ -313,6 +321,10 @@ class FusedHalo:
                                        slot.ctypes.data_as(C.c_void_p), len(lp), pa, pb, pf))
         self._keep = (pa, pb, pf)
         dist.barrier(group=hx.group)
+
+    def buffers(self):
+        """(attribute the next fused step reads, attribute it writes)"""
+        return (self.a, self.b) if self.step % 2 == 0 else (self.b, self.a)
 
     def smooth(self, lr, iters, stream=None):
         """iters fused steps starting from attribute A if an even number of steps has been run, else B; returns the

@@ -42,15 +42,15 @@ def _global_patching(F, patch_size):
     return g, g.elem_patch(2).copy()
 
 
-def _host_worker(rank, world, port, kind, q):
+def _host_worker(rank, world, port, kind, ps, q):
     try:
         import rxmesh_b200 as rx
         from rxmesh_b200 import distributed as D
         dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
         V, F = _mesh(kind)
-        g, fp = _global_patching(F, 128)
+        g, fp = _global_patching(F, ps)
         sh = D.shard_faces(F, fp, rank, world)
-        sm = D.ShardedMesh(sh, rank, world, patch_size=128, device=False)
+        sm = D.ShardedMesh(sh, rank, world, patch_size=ps, device=False)
         m = sm.mesh
         assert sm.count > 0 and sm.first + sm.count <= m.get_num_patches()
         # 1. every real patch is IDENTICAL to the same patch of the global mesh (ids mapped to global)
@@ -90,29 +90,39 @@ def _host_worker(rank, world, port, kind, q):
                     assert np.array_equal((sbv[pat[sel]] + lid[sel]), hx.send[p].astype(np.int64)[pos[sel]])
                 assert np.all(pat >= sm.first) and np.all(pat < sm.first + sm.count)
                 assert np.all(np.diff(pat) >= 0) and np.array_equal(np.bincount(pat, minlength=m.get_num_patches()), np.diff(off))
+                # patches that READ ghost slots but push nothing (they touch the rank boundary only through vertices that
+                # lower-id patches own): the fused kernel must count them before it lets the neighbour overwrite the
+                # ghost slots.  Lloyd patches produce them; the GPU test runs the same partition.
+                reads = np.array([np.any((m.patch(q_)["stash"][:, 0] < sm.first) |
+                                         (m.patch(q_)["stash"][:, 0] >= sm.first + sm.count))
+                                  for q_ in range(sm.first, sm.first + sm.count)])
+                pushes = np.diff(off)[sm.first:sm.first + sm.count] > 0
+                n_read_only = int((reads & ~pushes).sum())
         # 3. every element referenced by a real patch now has a value (owned by real or filled halo)
         dist.barrier()
-        q.put((rank, "ok", sm.count, int(hx.halo_elements())))
+        q.put((rank, "ok", sm.count, int(hx.halo_elements()), n_read_only))
     except Exception as e:  # pragma: no cover
         import traceback
-        q.put((rank, "fail: " + traceback.format_exc(), 0, 0))
+        q.put((rank, "fail: " + traceback.format_exc(), 0, 0, 0))
         raise e
     finally:
         if dist.is_initialized():
             dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind", ["torus", "grid", "ico"])
-def test_shards_and_halo_gloo(kind):
+@pytest.mark.parametrize("kind,ps", [("torus", 128), ("grid", 128), ("ico", 128), ("torus", 64)])
+def test_shards_and_halo_gloo(kind, ps):
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_host_worker, args=(r, world, port, kind, q)) for r in range(world)]
+    procs = [ctx.Process(target=_host_worker, args=(r, world, port, kind, ps, q)) for r in range(world)]
     [p.start() for p in procs]
     res = [q.get(timeout=240) for _ in range(world)]
     [p.join(60) for p in procs]
     assert all(r[1] == "ok" for r in res), res
     assert all(p.exitcode == 0 for p in procs)
+    if ps == 64:  # the partition the 2-GPU fused-halo test uses must contain read-only boundary patches
+        assert sum(r[4] for r in res) > 0, res
 
 
 def test_grid_slab_matches_global_grid():
@@ -197,6 +207,43 @@ def _gpu_worker(rank, world, port, q):
         dist.barrier()
         got = res.to_global()
         assert np.array_equal(got[real], got_nccl[real]), np.abs(got[real] - got_nccl[real]).max()
+        # ---- generic mesh (Lloyd patches, shard_faces): the partition holds patches that read ghost slots but push
+        #      nothing; many short steps so that a flag raised too early would let a neighbour overwrite ghost slots a
+        #      pending block still has to read (non-deterministic without the reader check-in)
+        Vi, Fi = _mesh("torus")
+        gi, fpi = _global_patching(Fi, 64)
+        shi = D.shard_faces(Fi, fpi, rank, world)
+        smi = D.ShardedMesh(shi, rank, world, patch_size=64)
+        hxi = D.HaloExchange(smi, 0)
+        xi = rx.Attribute(smi.mesh, 0, np.float32, 3, rx.LOCATION_ALL, rx.AoS)
+        yi = rx.Attribute(smi.mesh, 0, np.float32, 3, rx.LOCATION_ALL, rx.AoS)
+        Vloc = Vi[smi.l2g[0].astype(np.int64)]
+        it2 = 40
+        Ti = O.Topology(Fi)
+        refi, vvi = Vi.astype(np.float64), Ti.query("VV")
+        for _ in range(it2):
+            refi = O.laplacian_step(vvi, refi, lr, np.float64)
+        xi.from_global(Vloc), yi.from_global(Vloc)
+        a, b = xi, yi
+        for _ in range(it2):
+            smi.mesh.laplacian_smooth(a, b, lr, 1)
+            hxi.exchange(b)
+            a, b = b, a
+        got_n = a.to_global()
+        reali, gidi = smi.real_owned_mask(0), smi.l2g[0].astype(np.int64)
+        assert np.abs(got_n[reali] - refi[gidi[reali]]).max() < 1e-5 * it2
+        for rep in range(3):
+            xi.from_global(Vloc), yi.from_global(Vloc)
+            hxi.exchange(xi)
+            torch.cuda.synchronize()
+            dist.barrier()
+            if rep == 0:
+                fhi = D.FusedHalo(hxi, xi, yi)
+            res = fhi.smooth(lr, it2)
+            torch.cuda.synchronize()
+            dist.barrier()
+            got_f = res.to_global()
+            assert np.array_equal(got_f[reali], got_n[reali]), (rep, np.abs(got_f[reali] - got_n[reali]).max())
         # vertex normals after an exchange of the coordinates
         x.from_global(sh["verts"])
         hx.exchange(x)
