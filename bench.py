@@ -671,3 +671,7 @@ def run_sub_records(args, rank, world, local_rank, line, subs):
         rec = guarded(lambda: BC.laplacian_400m(args, rank, world, local_rank, torch, rx, TILE, TILE_I))
         if line is not None:
             line["laplacian_400m"] = rec
+
+
+if __name__ == "__main__":
+    main()

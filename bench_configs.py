@@ -117,15 +117,21 @@ def config_queries(torch, rx, stream, nu=707, patch_size=1024):
     for op, bpf in QUERY_ALG_BYTES.items():
         o = rx.Op[op]
         width = {"EV": 2, "FV": 3, "FE": 3, "EF": 2, "FF": 3}.get(op, m.get_input_max_valence())
-        inp = rx.Attribute(m, _SRC[o], np.uint64, 1, rx.LOCATION_ALL, rx.AoS)
-        out = rx.Attribute(m, _SRC[o], np.uint64, width, rx.LOCATION_ALL, rx.AoS)
+        inp = rx.Attribute(m, _SRC[o], np.uint64, 1, rx.LOCATION_ALL, rx.AoSoA)  # the reference's default layout
+        out = rx.Attribute(m, _SRC[o], np.uint64, width, rx.LOCATION_ALL, rx.AoSoA)
         inp.reset(rx.INVALID64, rx.DEVICE)
         out.reset(rx.INVALID64, rx.DEVICE)
         ms = timed(lambda: m.query_store(o, inp, out, stream), stream, torch, 50)
         gbs = bpf * nF / (ms * 1e-3) / 1e9
         # parity of what the timed kernel wrote
         inp.move(rx.DEVICE, rx.HOST), out.move(rx.DEVICE, rx.HOST)
-        hi, ho = inp.host_array(), out.host_array().reshape(-1, width)
+        # AoSoA -> one row per slot: value (slot s of patch p, attribute a) sits at base(p) * width + a * cap(p) + lid
+        sb = m.slot_base(_SRC[o]).astype(np.int64)
+        cap = np.diff(sb)
+        base, capr = np.repeat(sb[:-1], cap), np.repeat(cap, cap)
+        lid = np.arange(sb[-1], dtype=np.int64) - base
+        hi = inp.host_array()
+        ho = out.host_array()[(base * width + lid)[:, None] + capr[:, None] * np.arange(width, dtype=np.int64)[None, :]]
         valid_src = hi != np.uint64(rx.INVALID64)
         src_g = m.map_to_global(_SRC[o], hi)
         dst_g = m.map_to_global(_DST[o], ho.reshape(-1)).reshape(-1, width)

@@ -88,16 +88,27 @@ class Attribute : public AttributeBase
     rxm_attr* c_handle() const { return m_attr; }
 
     void reset(const T value, locationT location, cudaStream_t stream = NULL) { detail::rxm_check(rxm_attr_reset(m_attr, &value, (int)location, stream)); }
-    void move(locationT source, locationT target, cudaStream_t stream = NULL) { detail::rxm_check(rxm_attr_move(m_attr, (int)source, (int)target, stream)); }
+    void move(locationT source, locationT target, cudaStream_t stream = NULL)
+    {
+        detail::rxm_check(rxm_attr_move(m_attr, (int)source, (int)target, stream));
+        refresh_pointers();  // a missing target side was allocated (attribute.cu:348-353)
+    }
     void copy_from(Attribute<T, HandleT>& source, locationT source_flag, locationT dst_flag, cudaStream_t stream = NULL)
     {
         detail::rxm_check(rxm_attr_copy_from(m_attr, source.m_attr, (int)source_flag, (int)dst_flag, stream));
     }
-    void release(locationT = LOCATION_ALL) override
+    // release(location) (attribute.cu:375-390): frees only the requested side(s); the handle and the name go with the
+    // last side (shallow copies handed to kernels keep dangling pointers, exactly as in the reference)
+    void release(locationT location = LOCATION_ALL) override
     {
-        if (m_attr) rxm_attr_destroy(m_attr);
-        free(m_name);
-        m_attr = nullptr, m_h = nullptr, m_d = nullptr, m_name = nullptr;
+        if (!m_attr) return;
+        rxm_attr_release(m_attr, (int)location);
+        refresh_pointers();
+        if (!m_h && !m_d) {
+            rxm_attr_destroy(m_attr);
+            free(m_name);
+            m_attr = nullptr, m_name = nullptr;
+        }
     }
 
     // Attribute::operator()(handle, attr) (attribute.h:313-319,406-434)
@@ -179,6 +190,12 @@ class Attribute : public AttributeBase
     }
     char*                     m_name = nullptr;
     rxm_attr*                 m_attr = nullptr;
+    void refresh_pointers()
+    {
+        m_h        = m_attr ? (T*)rxm_attr_data(m_attr, RXM_HOST) : nullptr;
+        m_d        = m_attr ? (T*)rxm_attr_data(m_attr, RXM_DEVICE) : nullptr;
+        m_location = (locationT)((m_h ? HOST : 0) | (m_d ? DEVICE : 0));
+    }
     T *                       m_h = nullptr, *m_d = nullptr;
     const uint32_t *          m_h_slot_base = nullptr, *m_d_slot_base = nullptr;
     const uint32_t *          m_h_lin_base = nullptr, *m_d_lin_base = nullptr;

@@ -143,11 +143,15 @@ int rxm_mesh_launch_box(const rxm_mesh* m, int op, uint32_t* blocks, uint32_t* t
  * gap-free column-major num_elements x num_attr matrix indexed by linear id (attribute.h:249-261,406-421). */
 int rxm_attr_create(rxm_mesh* m, int elem, uint32_t elem_bytes, uint32_t num_attr, int location, int layout,
                     rxm_attr** out);
-void     rxm_attr_destroy(rxm_attr* a);                                /* remove_attribute / release */
+void     rxm_attr_destroy(rxm_attr* a);                                /* remove_attribute */
+int      rxm_attr_release(rxm_attr* a, int location);                  /* Attribute::release(location), attribute.cu:375-390: frees only that side */
 void*    rxm_attr_data(rxm_attr* a, int location);                     /* Attribute::data(location) */
 uint64_t rxm_attr_count(const rxm_attr* a);                            /* values stored: storage_size(), attribute.h:249 */
 int      rxm_attr_reset(rxm_attr* a, const void* value, int location, void* stream); /* attribute.cu:306-357 */
-int      rxm_attr_move(rxm_attr* a, int source, int target, void* stream);           /* attribute.cu:359-364 */
+/* attribute.cu:325-373: HOST <-> DEVICE; a target side that is not allocated yet is allocated first */
+int      rxm_attr_move(rxm_attr* a, int source, int target, void* stream);
+/* attribute.cu:392-500: source / target are location MASKS; every (source side, target side) pair whose bits are set is
+ * copied (host->host, device->device, device->host, host->device) */
 int      rxm_attr_copy_from(rxm_attr* dst, rxm_attr* src, int source, int target, void* stream);
 /* add_vertex_attribute(Verts, name): fill from / read back to an array in GLOBAL element order
  * ([num_elems][num_attr], AoS), the role of rxmesh_static.inl:147-189 and of the

@@ -574,38 +574,110 @@ int rxm_attr_reset(rxm_attr* a, const void* value, int location, void* stream)
     return RXM_OK;
 }
 
-int rxm_attr_move(rxm_attr* a, int source, int target, void* stream)
+// allocate the side(s) of `location` that the attribute does not have yet (Attribute::allocate, attribute.cu:531-590)
+static int attr_allocate(rxm_attr* a, int location)
 {
-    if (!a) return fail(RXM_ERR_INVALID, "rxm_attr_move: null attribute");
-    if (source == target) return RXM_OK;
-    if (!a->h || !a->d) return fail(RXM_ERR_INVALID, "rxm_attr_move: attribute is not allocated on both sides");
-    const size_t bytes = a->count * a->elem_bytes;
-    if (source == RXM_HOST && target == RXM_DEVICE)
-        CU(cudaMemcpyAsync(a->d, a->h, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
-    else if (source == RXM_DEVICE && target == RXM_HOST) {
-        CU(cudaMemcpyAsync(a->h, a->d, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-        CU(cudaStreamSynchronize((cudaStream_t)stream));
-    } else
-        return fail(RXM_ERR_INVALID, "rxm_attr_move: source/target must be HOST or DEVICE");
+    rxm_mesh*    m     = a->m;
+    const size_t bytes = std::max<size_t>(a->count * a->elem_bytes, 16);
+    if ((location & RXM_DEVICE) && !a->d) {
+        if (!m->on_device) return fail(RXM_ERR_CUDA, "attribute: DEVICE location requested but the mesh is not on a device");
+        cudaError_t e = cudaMalloc(&a->d, bytes);
+        if (e == cudaSuccess) e = cudaMemset(a->d, 0, bytes);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+        if (e != cudaSuccess) {
+            if (a->d) cudaFree(a->d);
+            a->d = nullptr;
+            return fail(RXM_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        }
+    }
+    if ((location & RXM_HOST) && !a->h) {
+        if (m->on_device && cudaMallocHost(&a->h, bytes) == cudaSuccess) {
+            a->h_pinned = true;
+        } else {
+            cudaGetLastError();
+            a->h        = malloc(bytes);
+            a->h_pinned = false;
+        }
+        if (!a->h) return fail(RXM_ERR_INVALID, "attribute: host allocation failed");
+        memset(a->h, 0, bytes);
+    }
     return RXM_OK;
 }
 
+// Attribute::release(location) (attribute.cu:375-390): frees only the requested side(s)
+int rxm_attr_release(rxm_attr* a, int location)
+{
+    if (!a) return fail(RXM_ERR_INVALID, "rxm_attr_release: null attribute");
+    if ((location & RXM_DEVICE) && a->d) {
+        cudaFree(a->d);
+        a->d = nullptr;
+    }
+    if ((location & RXM_HOST) && a->h) {
+        if (a->h_pinned)
+            cudaFreeHost(a->h);
+        else
+            free(a->h);
+        a->h = nullptr, a->h_pinned = false;
+    }
+    return RXM_OK;
+}
+
+int rxm_attr_move(rxm_attr* a, int source, int target, void* stream)
+{
+    if (!a) return fail(RXM_ERR_INVALID, "rxm_attr_move: null attribute");
+    if (source == target) return RXM_OK;  // the reference warns and returns (attribute.cu:331-338)
+    if (!((source == RXM_HOST && target == RXM_DEVICE) || (source == RXM_DEVICE && target == RXM_HOST)))
+        return fail(RXM_ERR_INVALID, "rxm_attr_move: source/target must be HOST or DEVICE");
+    if (!(source == RXM_HOST ? a->h : a->d)) return fail(RXM_ERR_INVALID, "rxm_attr_move: the source side is not allocated");
+    int rc = attr_allocate(a, target);  // the reference allocates a missing target before moving (attribute.cu:348-353)
+    if (rc) return rc;
+    const size_t bytes = a->count * a->elem_bytes;
+    if (source == RXM_HOST)
+        CU(cudaMemcpyAsync(a->d, a->h, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    else {
+        CU(cudaMemcpyAsync(a->h, a->d, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        CU(cudaStreamSynchronize((cudaStream_t)stream));
+    }
+    return RXM_OK;
+}
+
+// Attribute::copy_from (attribute.cu:392-500): every (source side, target side) pair whose bits are set in the two flags is
+// copied, in the reference's order host->host, device->device, device->host, host->device; e.g. (LOCATION_ALL,
+// LOCATION_ALL) refreshes both copies, (HOST, LOCATION_ALL) fans the host copy out to both sides.
 int rxm_attr_copy_from(rxm_attr* dst, rxm_attr* src, int source, int target, void* stream)
 {
     if (!dst || !src) return fail(RXM_ERR_INVALID, "rxm_attr_copy_from: null attribute");
     if (dst->count != src->count || dst->elem_bytes != src->elem_bytes || dst->layout != src->layout ||
         dst->elem != src->elem)
         return fail(RXM_ERR_INVALID, "rxm_attr_copy_from: attributes differ in shape");
+    if ((source & RXM_LOCATION_ALL) == RXM_LOCATION_ALL && (target & RXM_LOCATION_ALL) != RXM_LOCATION_ALL)
+        return fail(RXM_ERR_INVALID, "rxm_attr_copy_from: invalid configuration (source LOCATION_ALL needs target LOCATION_ALL)");
     const size_t bytes = dst->count * dst->elem_bytes;
-    void*        s     = (source & RXM_DEVICE) ? src->d : src->h;
-    void*        d     = (target & RXM_DEVICE) ? dst->d : dst->h;
-    if (!s || !d) return fail(RXM_ERR_INVALID, "rxm_attr_copy_from: side not allocated");
-    if (!(source & RXM_DEVICE) && !(target & RXM_DEVICE)) {
-        memcpy(d, s, bytes);
+    cudaStream_t S     = (cudaStream_t)stream;
+    int          done = 0, missing = 0;
+    bool         d2h = false;
+    auto pair = [&](int sbit, int tbit) -> int {
+        if (!(source & sbit) || !(target & tbit)) return RXM_OK;
+        void* s = sbit == RXM_DEVICE ? src->d : src->h;
+        void* d = tbit == RXM_DEVICE ? dst->d : dst->h;
+        if (!s || !d) {
+            ++missing;
+            return RXM_OK;
+        }
+        if (sbit == RXM_HOST && tbit == RXM_HOST)
+            memcpy(d, s, bytes);
+        else
+            CU(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDefault, S));
+        d2h |= (sbit == RXM_DEVICE && tbit == RXM_HOST);
+        ++done;
         return RXM_OK;
-    }
-    CU(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
-    if (!(target & RXM_DEVICE)) CU(cudaStreamSynchronize((cudaStream_t)stream));
+    };
+    int rc;
+    if ((rc = pair(RXM_HOST, RXM_HOST)) || (rc = pair(RXM_DEVICE, RXM_DEVICE)) || (rc = pair(RXM_DEVICE, RXM_HOST)) ||
+        (rc = pair(RXM_HOST, RXM_DEVICE)))
+        return rc;
+    if (d2h) CU(cudaStreamSynchronize(S));
+    if (!done) return fail(RXM_ERR_INVALID, missing ? "rxm_attr_copy_from: side not allocated" : "rxm_attr_copy_from: no location selected");
     return RXM_OK;
 }
 
