@@ -3,6 +3,7 @@
 // (InputHandle, OutputIterator&) once per OWNED source element that passes the active-set predicate.
 #pragma once
 #include <cooperative_groups.h>
+#include <cstdio>
 #include <type_traits>
 #include "rxmesh/context.h"
 #include "rxmesh/iterator.cuh"
@@ -172,16 +173,28 @@ struct Query
         const rxm::PatchDesc& d    = m_desc;
         const uint8_t*        blob = m_ctx.view.topo + d.topo_off;
         const uint32_t        used0 = sa.m_sm.used;
-        // oriented VV (kernels/rxmesh_queries.cuh:375-499): served by the stored one-ring fans
-        const bool use_fans = (op == Op::VV) && oriented && m_ctx.view.fans && !all_sources;
+        // oriented VV / VE (orient_edges_around_vertices, kernels/rxmesh_queries.cuh:375-499,905-914): served by the stored
+        // one-ring fans (fan_v / fan_e).  The reference can only orient on edge-manifold input and asserts inside its
+        // kernels; here a mesh without fans (non-manifold or inconsistently oriented input, RXM_NO_FANS) or a request for
+        // the lists of not-owned sources stops the kernel with a message instead of silently handing out unoriented lists.
+        if ((op == Op::VV || op == Op::VE) && oriented && (!m_ctx.view.fans || all_sources)) {
+            if (threadIdx.x == 0 && blockIdx.x == 0)
+                printf("rxmesh: oriented %s needs %s\n", op == Op::VV ? "Op::VV" : "Op::VE",
+                       all_sources ? "allow_not_owned = false (the one-ring fans cover owned vertices only)"
+                                   : "an edge-manifold, consistently oriented input mesh (no one-ring fans were stored)");
+            __syncthreads();
+            __trap();
+        }
+        const bool use_fans = (op == Op::VV || op == Op::VE) && oriented;
         PatchQuery<OPV, (int)blockThreads, 12, PACKED> q;
         uint16_t *s_fo = nullptr, *s_fv = nullptr;
+        constexpr uint32_t fan_dst = op == Op::VE ? rxm::ELEM_E : rxm::ELEM_V;  // fan_e names edges, fan_v vertices
         uint32_t* s_own = nullptr;
         rxm::StashEntry* s_stash = nullptr;
         if (use_fans) {
             s_fo    = sa.template alloc<uint16_t>(d.fanoff_bytes() / 2);
             s_fv    = sa.template alloc<uint16_t>(d.fanv_bytes() / 2);
-            s_own   = sa.template alloc<uint32_t>(d.own_bytes(rxm::ELEM_V) / 4);
+            s_own   = sa.template alloc<uint32_t>(d.own_bytes(fan_dst) / 4);
             s_stash = sa.template alloc<rxm::StashEntry>(d.n_stash);
         } else {
             q.plan(d, sa.m_sm, true, all_sources, m_ctx.view.edge_manifold != 0);
@@ -192,10 +205,10 @@ struct Query
                 fence_mbar_init();
             }
             if (use_fans) {
-                mbar_arrive_expect_tx(&bar, d.fanoff_bytes() + d.fanv_bytes() + d.own_bytes(rxm::ELEM_V) + d.stash_bytes());
+                mbar_arrive_expect_tx(&bar, d.fanoff_bytes() + d.fanv_bytes() + d.own_bytes(fan_dst) + d.stash_bytes());
                 bulk_g2s(s_fo, blob + d.off_fanoff(), d.fanoff_bytes(), &bar);
-                if (d.fanv_bytes()) bulk_g2s(s_fv, blob + d.off_fanv(), d.fanv_bytes(), &bar);
-                if (d.own_bytes(rxm::ELEM_V)) bulk_g2s(s_own, blob + d.off_own(rxm::ELEM_V), d.own_bytes(rxm::ELEM_V), &bar);
+                if (d.fanv_bytes()) bulk_g2s(s_fv, blob + (op == Op::VE ? d.off_fane() : d.off_fanv()), d.fanv_bytes(), &bar);
+                if (d.own_bytes(fan_dst)) bulk_g2s(s_own, blob + d.off_own(fan_dst), d.own_bytes(fan_dst), &bar);
                 if (d.stash_bytes()) bulk_g2s(s_stash, blob + d.off_stash(), d.stash_bytes(), &bar);
             } else {
                 mbar_arrive_expect_tx(&bar, q.tx_bytes(d, true));
@@ -215,8 +228,8 @@ struct Query
             __syncthreads();
             r.off16 = s_fo, r.off32 = nullptr, r.cnt = nullptr, r.end16 = nullptr, r.val = s_fv, r.stride = 0, r.shift = 0, r.mask = 0xFFFFu;
             r.n_src = d.n_owned[rxm::ELEM_V];
-            ot.own = s_own, ot.stash = s_stash, ot.n_owned = d.n_owned[rxm::ELEM_V], ot.patch = d.patch_id;
-            ot.slot_base = d.slot_base[rxm::ELEM_V], ot.type = rxm::ELEM_V;
+            ot.own = s_own, ot.stash = s_stash, ot.n_owned = d.n_owned[fan_dst], ot.patch = d.patch_id;
+            ot.slot_base = d.slot_base[fan_dst], ot.type = fan_dst;
         } else {
             r = q.compute(d, warp_tmp, all_sources, false);
             if (op_is_fixed<OPV>()) __syncthreads();

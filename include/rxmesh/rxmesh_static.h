@@ -611,7 +611,11 @@ class RXMeshStatic
                             std::function<size_t(uint32_t, uint32_t, uint32_t)> user_shmem =
                                 [](uint32_t, uint32_t, uint32_t) { return 0; }) const
     {
-        (void)oriented;
+        if (oriented && !info(RXM_INFO_FANS))
+            for (Op o : op)
+                if (o == Op::VV || o == Op::VE)
+                    fprintf(stderr, "RXMeshStatic::prepare_launch_box() oriented %s needs an edge-manifold, consistently oriented input "
+                                    "mesh: this mesh stores no one-ring fans and the kernel will stop\n", op_to_string(o).c_str());
         size_t   dyn = with_vertex_valence ? 4 * (size_t)get_per_patch_max_vertices() + 16 : 0;  // compute_vertex_valence
         dyn += 4 * ((size_t)std::max(get_per_patch_max_edges(), get_per_patch_max_faces()) / 32 + 8);  // prologue mask
         uint32_t blocks = get_num_patches(), threads = 0;

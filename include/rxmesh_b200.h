@@ -54,6 +54,11 @@ int rxm_init(int device);
  * constructing from a saved `patcher_file`.  Host-only work: succeeds without a GPU. */
 int rxm_mesh_create(const uint32_t* fv, uint32_t num_faces, const uint32_t* face_patch, uint32_t patch_size,
                     int num_threads, rxm_mesh** out);
+/* same, with build flags: sections of the patch store a mesh will never need can be left out */
+#define RXM_BUILD_NO_RING2 1u /* no ring-2 extension (rxm_bilateral_filter then runs its cross-patch path for every vertex
+                                 whose neighbourhood leaves the patch); saves build time and ~3 bytes per face */
+int rxm_mesh_create_ex(const uint32_t* fv, uint32_t num_faces, const uint32_t* face_patch, uint32_t patch_size,
+                       int num_threads, uint32_t flags, rxm_mesh** out);
 /* RXMesh::build_device (rxmesh.cpp:1139-1615): upload the patch store to the current device. */
 int rxm_mesh_to_device(rxm_mesh* m);
 /* Release host-side helper arrays of a large mesh once it is on the device (local->global lists, global edge
@@ -72,7 +77,7 @@ enum {
     RXM_INFO_NUM_SLOTS_V = 13, RXM_INFO_NUM_SLOTS_E = 14, RXM_INFO_NUM_SLOTS_F = 15,
     RXM_INFO_TOPO_BYTES = 16, RXM_INFO_TOTAL_LOCAL_V = 17, RXM_INFO_TOTAL_LOCAL_E = 18,
     RXM_INFO_TOTAL_LOCAL_F = 19, RXM_INFO_MAX_STASH = 20, RXM_INFO_ON_DEVICE = 21, RXM_INFO_PACKED = 22,
-    RXM_INFO_FANS = 23
+    RXM_INFO_FANS = 23, RXM_INFO_RING2 = 24
 };
 uint64_t rxm_mesh_info(const rxm_mesh* m, int what);
 double   rxm_mesh_build_seconds(const rxm_mesh* m, int patcher_only);
@@ -108,6 +113,17 @@ typedef struct {
      * local faces across edges 0, 1, 2 compacted to the front; ef = 2 per edge, its local faces ascending; 0xFFFF = none */
     const uint16_t* ff;
     const uint16_t* ef;
+    /* fan_e[i] = local edge between the fan's vertex and fan_v[i] (NULL without fans): VE in oriented order */
+    const uint16_t* fan_e;
+    /* ring-2 extension (NULL / 0 when built with RXM_BUILD_NO_RING2): the complete one-ring of every NOT-OWNED vertex that is
+     * adjacent to an owned one, as extended local ids: < n[V] = a vertex of the patch, n[V] + k = ext vertex k (two rings
+     * out, not held by the patch), whose owner record is ext_owner[k] (same encoding as owner[]).
+     * r2_idx[n[V] - n_owned[V]] = ring index or 0xFFFF; ring r = r2_val[r2_off[r] .. r2_off[r + 1]) */
+    const uint16_t* r2_idx;
+    const uint16_t* r2_off;
+    const uint16_t* r2_val;
+    const uint32_t* ext_owner;
+    uint32_t        n_r2, n_ext, r2_total;
 } rxm_patch_view;
 int rxm_mesh_patch(const rxm_mesh* m, uint32_t patch, rxm_patch_view* out);
 
@@ -181,6 +197,9 @@ int rxm_laplacian_smooth(rxm_mesh* m, rxm_attr* in, rxm_attr* out, double lr, ui
 /* bilateral filtering (apps/Filtering/filtering_rxmesh.cuh:75-95): `iters` iterations of
  * unit-face vertex normals + bilateral_filtering; result in `out`. */
 int rxm_bilateral_filter(rxm_mesh* m, rxm_attr* in, rxm_attr* out, uint32_t iters, void* stream);
+/* vertex-iterations of the last rxm_bilateral_filter call whose neighbourhood walk left the patch (+ its ring-2 extension)
+ * and ran on the cross-patch path instead (diagnostic; the role of the reference's higher_query_block_dispatcher rounds) */
+uint64_t rxm_bilateral_deferred(const rxm_mesh* m);
 /* Materialise a query as a CSR over attribute SLOTS on the device (cached in the mesh): off[num_slots(src)+1],
  * val[nnz] = owner slots of the neighbours, lists grouped by patch. The k-ring consumer (bilateral filtering)
  * traverses this instead of re-running whole-patch queries per foreign patch like the reference's

@@ -216,7 +216,8 @@ def laplacian_step(vv, x, lr, dtype=np.float32):
 
 def bilateral_step(vv, fv, x, max_nbrs=80, use_f64=True):
     """One bilateral iteration = unit-face normals + rxo_bilateral_step
-    (apps/Filtering/filtering_rxmesh.cuh:75-95). Returns (x_new, max neighbourhood)."""
+    (apps/Filtering/filtering_rxmesh.cuh:75-95). Returns (x_new, max neighbourhood).
+    use_f64 = 2: neighbourhood membership decided in fp32 (the decisions a fp32 implementation makes), the rest in float64."""
     off, val = vv
     x = _f32(x).reshape(-1, 3)
     n = vertex_normals_unit_faces(fv, x, np.float64)

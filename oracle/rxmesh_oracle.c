@@ -420,8 +420,19 @@ void rxo_laplacian_step_f64(const uint32_t* vv_off, const uint32_t* vv_val, uint
 /* assert in the reference; here the count is reported and the list clipped.  */
 /* `normals` = output of rxo_vertex_normals_unit_faces (unnormalised sum).    */
 /* Computed in float64 from fp32 inputs when use_f64 != 0, else in fp32.      */
+/* use_f64 == 2: the MEMBERSHIP decisions (squared distances, sigma_c^2, the  */
+/* <= 4 sigma_c^2 test) are made in fp32 exactly as a fp32 implementation of   */
+/* glm::distance2 makes them -- differences in fp32, then                      */
+/* fmaf(dz, dz, fmaf(dy, dy, dx * dx)) -- so that the neighbourhoods are the   */
+/* same SETS as the GPU's; everything after membership stays in float64.       */
 /* Returns the maximum neighbourhood size seen.                               */
 /* ------------------------------------------------------------------------ */
+static double rxo_dist2_f32(const float* a, const float* b)
+{
+    const float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+    return (double)fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+
 uint32_t rxo_bilateral_step(const uint32_t* vv_off, const uint32_t* vv_val, uint32_t nv,
                             const float* x, const double* normals, float* x_out,
                             uint32_t max_nbrs, int use_f64)
@@ -446,6 +457,7 @@ uint32_t rxo_bilateral_step(const uint32_t* vv_off, const uint32_t* vv_val, uint
                 d += t * t;
             }
             if (!use_f64) d = (float)d;
+            if (use_f64 == 2) d = rxo_dist2_f32(x + 3 * (uint64_t)u, x + 3 * (uint64_t)v);
             if (d < sc2) sc2 = d;
         }
         double   radius = 4.0 * sc2;
@@ -469,6 +481,7 @@ uint32_t rxo_bilateral_step(const uint32_t* vv_off, const uint32_t* vv_val, uint
                     d += t * t;
                 }
                 if (!use_f64) d = (float)d;
+                if (use_f64 == 2) d = rxo_dist2_f32(x + 3 * (uint64_t)u, x + 3 * (uint64_t)v);
                 if (d <= radius) {
                     if (cnt < max_nbrs) list[cnt] = u;
                     cnt++;

@@ -18,7 +18,9 @@ class PatchView(C.Structure):
                 ("packed", C.c_uint32), ("ev", u16p), ("fe", u16p), ("fv", u16p),
                 ("voff_e", u16p), ("voff_f", u16p), ("eoff_f", u16p), ("fan_off", u16p), ("fan_v", u16p),
                 ("fan_f", u16p), ("fan_total", C.c_uint32), ("owner", u32p * 3), ("stash", u32p),
-                ("n_stash", C.c_uint32), ("ltog", u32p * 3), ("ff", u16p), ("ef", u16p)]
+                ("n_stash", C.c_uint32), ("ltog", u32p * 3), ("ff", u16p), ("ef", u16p), ("fan_e", u16p),
+                ("r2_idx", u16p), ("r2_off", u16p), ("r2_val", u16p), ("ext_owner", u32p),
+                ("n_r2", C.c_uint32), ("n_ext", C.c_uint32), ("r2_total", C.c_uint32)]
 
 
 class PatcherFile(C.Structure):
@@ -33,6 +35,8 @@ SYMBOLS = {
     "rxm_init": (C.c_int, [C.c_int]),
     "rxm_mesh_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int,
                                   C.POINTER(C.c_void_p)]),
+    "rxm_mesh_create_ex": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_uint32,
+                                     C.POINTER(C.c_void_p)]),
     "rxm_mesh_to_device": (C.c_int, [C.c_void_p]),
     "rxm_mesh_compact": (C.c_int, [C.c_void_p]),
     "rxm_mesh_destroy": (None, [C.c_void_p]),
@@ -53,6 +57,7 @@ SYMBOLS = {
     "rxm_attr_create": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
                                   C.POINTER(C.c_void_p)]),
     "rxm_attr_destroy": (None, [C.c_void_p]),
+    "rxm_attr_release": (C.c_int, [C.c_void_p, C.c_int]),
     "rxm_attr_data": (C.c_void_p, [C.c_void_p, C.c_int]),
     "rxm_attr_count": (C.c_uint64, [C.c_void_p]),
     "rxm_attr_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
@@ -68,6 +73,7 @@ SYMBOLS = {
     "rxm_laplacian_smooth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_uint32,
                                        C.c_void_p]),
     "rxm_bilateral_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "rxm_bilateral_deferred": (C.c_uint64, [C.c_void_p]),
     "rxm_query_csr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                 C.POINTER(C.c_uint64), C.c_void_p]),
     "rxm_boundary_vertices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -654,9 +654,14 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
         std::vector<uint32_t> l[3];
         std::vector<uint32_t> stash;
         uint32_t              n_owned[3];
+        // ring-2 extension: ext = global ids (ascending) of the vertices two rings out; r2_idx per not-owned vertex,
+        // r2_off / r2_val = the stored rings as extended local ids
+        std::vector<uint32_t> ext;
+        std::vector<uint16_t> r2_idx, r2_off, r2_val;
     };
     std::vector<Tmp> tmp(P);
     std::string      err;
+    const bool       ring2 = !opt.no_ring2;
 #pragma omp parallel
     {
         std::vector<uint32_t> scratch;
@@ -694,8 +699,65 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
                 T.n_owned[t] = (uint32_t)(mid - scratch.begin());
                 T.l[t]       = scratch;
             }
-            // neighbour patches referenced by not-owned elements
+            if (ring2) {
+                // ---- ring-2 extension: the COMPLETE one-ring of every not-owned vertex adjacent to an owned vertex ----
+                const auto&    LV  = T.l[ELEM_V];
+                const uint32_t nov = T.n_owned[ELEM_V], nvp = (uint32_t)LV.size();
+                auto lv = [&](uint32_t g) -> uint32_t {  // global vertex -> local id, INVALID32_ if not in the patch
+                    auto b = vpatch[g] == (uint32_t)p ? LV.begin() : LV.begin() + nov;
+                    auto e = vpatch[g] == (uint32_t)p ? LV.begin() + nov : LV.end();
+                    auto it = std::lower_bound(b, e, g);
+                    return (it != e && *it == g) ? (uint32_t)(it - LV.begin()) : INVALID32_;
+                };
+                std::vector<uint8_t> adj(nvp - nov, 0);
+                for (uint32_t f : T.l[ELEM_F]) {
+                    const uint32_t g[3] = {fv[3ull * f], fv[3ull * f + 1], fv[3ull * f + 2]};
+                    if (vpatch[g[0]] != (uint32_t)p && vpatch[g[1]] != (uint32_t)p && vpatch[g[2]] != (uint32_t)p) continue;
+                    for (int j = 0; j < 3; ++j)
+                        if (vpatch[g[j]] != (uint32_t)p) adj[lv(g[j]) - nov] = 1;
+                }
+                std::vector<uint32_t> ring_g, ring_off(1, 0);  // rings as global ids
+                T.r2_idx.assign(nvp - nov, 0xFFFFu);
+                uint32_t nr = 0;
+                T.ext.clear();
+                for (uint32_t i = 0; i < nvp - nov; ++i) {
+                    if (!adj[i]) continue;
+                    const uint32_t w = LV[nov + i];
+                    scratch.clear();
+                    for (uint32_t k = vf_off[w]; k < vf_off[w + 1]; ++k)
+                        for (int j = 0; j < 3; ++j) {
+                            const uint32_t g = fv[3ull * vf_val[k] + j];
+                            if (g != w) scratch.push_back(g);
+                        }
+                    std::sort(scratch.begin(), scratch.end());
+                    scratch.erase(std::unique(scratch.begin(), scratch.end()), scratch.end());
+                    for (uint32_t g : scratch) {
+                        ring_g.push_back(g);
+                        if (lv(g) == INVALID32_) T.ext.push_back(g);
+                    }
+                    ring_off.push_back((uint32_t)ring_g.size());
+                    T.r2_idx[i] = (uint16_t)nr++;
+                }
+                std::sort(T.ext.begin(), T.ext.end());
+                T.ext.erase(std::unique(T.ext.begin(), T.ext.end()), T.ext.end());
+                if (nvp + T.ext.size() > 65535u || ring_g.size() > 65535u) {
+#pragma omp critical
+                    err = "build_mesh: patch " + std::to_string(p) + " exceeds 65535 entries in its ring-2 extension; use a smaller patch_size";
+                    T.ext.clear(), T.r2_idx.clear();
+                } else {
+                    T.r2_off.assign(ring_off.begin(), ring_off.end());
+                    T.r2_val.resize(ring_g.size());
+                    for (size_t i = 0; i < ring_g.size(); ++i) {
+                        const uint32_t l = lv(ring_g[i]);
+                        T.r2_val[i] = (uint16_t)(l != INVALID32_ ? l
+                                                                 : nvp + (uint32_t)(std::lower_bound(T.ext.begin(), T.ext.end(), ring_g[i]) - T.ext.begin()));
+                    }
+                }
+            }
+            // neighbour patches referenced by not-owned elements (and by the ext vertices)
             scratch.clear();
+            for (uint32_t g : T.ext)
+                scratch.push_back(vpatch[g]);
             for (int t = 0; t < 3; ++t)
                 for (uint32_t i = T.n_owned[t]; i < T.l[t].size(); ++i)
                     scratch.push_back(M.elem_patch[t][T.l[t][i]]);
@@ -704,10 +766,18 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
             T.stash = scratch;
         }
     }
+    if (!err.empty()) return err;
     for (uint32_t p = 0; p < P; ++p)
         for (int t = 0; t < 3; ++t)
             if (tmp[p].l[t].size() > 65535u || tmp[p].stash.size() > 65535u)
                 return "build_mesh: patch " + std::to_string(p) + " exceeds 65535 local elements; use a smaller patch_size";
+    // the 16-bit encodings of the patch store: local face-edge entries are (edge << 1) | dir, the list offsets are u16
+    // prefix sums over 2 nE and 3 nF entries
+    for (uint32_t p = 0; p < P; ++p)
+        if (tmp[p].l[ELEM_E].size() > 32767u || 3 * tmp[p].l[ELEM_F].size() > 65535u || 2 * tmp[p].l[ELEM_E].size() > 65535u)
+            return "build_mesh: patch " + std::to_string(p) + " has " + std::to_string(tmp[p].l[ELEM_E].size()) + " edges / " +
+                   std::to_string(tmp[p].l[ELEM_F].size()) + " faces with its ribbon: beyond the 16-bit local encodings (at most 32767 "
+                   "edges and 21845 faces per patch); use a smaller patch_size";
     std::vector<uint32_t>().swap(vf_off);
     std::vector<uint32_t>().swap(vf_val);
 
@@ -715,7 +785,7 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
     // ---- phase A2: one-ring fans of the owned vertices (local ids), if the input allows ----
     // For owned vertex v every incident face (v, a, b) (a cyclic rotation of its stored corner
     // order) is a directed link a -> b; the links must chain into ONE open or closed sequence.
-    std::vector<std::vector<uint16_t>> fan_v(P), fan_off(P), fan_f(P);
+    std::vector<std::vector<uint16_t>> fan_v(P), fan_off(P), fan_f(P), fan_e(P);
     bool fans_ok = !opt.no_fans && M.is_edge_manifold && M.max_valence < 4096;
     if (fans_ok) {
         int bad = 0;
@@ -729,6 +799,12 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
                 if (vpatch[g] == (uint32_t)p) return (uint32_t)(std::lower_bound(L.begin(), L.begin() + nov, g) - L.begin());
                 return (uint32_t)(std::lower_bound(L.begin() + nov, L.end(), g) - L.begin());
             };
+            auto le = [&](uint32_t g) -> uint32_t {  // global edge -> local id in this patch
+                const auto&    L   = T.l[ELEM_E];
+                const uint32_t noe = T.n_owned[ELEM_E];
+                if (epatch[g] == (uint32_t)p) return (uint32_t)(std::lower_bound(L.begin(), L.begin() + noe, g) - L.begin());
+                return (uint32_t)(std::lower_bound(L.begin() + noe, L.end(), g) - L.begin());
+            };
             // links grouped by owned vertex
             std::vector<uint32_t> cnt(nov + 1, 0);
             std::vector<std::array<uint16_t, 3>> lf(T.l[ELEM_F].size());
@@ -740,14 +816,21 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
             std::vector<uint32_t> off(nov + 1, 0);
             for (uint32_t v = 0; v < nov; ++v)
                 off[v + 1] = off[v] + cnt[v];
-            std::vector<std::array<uint16_t, 3>> links(off[nov]);  // (first, second, face)
+            // (first, second, face, edge to first, edge to second): corner j of a face sees its edge j towards corner j+1
+            // and its edge j+2 coming back from corner j+2
+            std::vector<std::array<uint16_t, 5>> links(off[nov]);
             std::vector<uint32_t>                cur(off.begin(), off.end() - 1);
             for (size_t f = 0; f < lf.size(); ++f)
                 for (int j = 0; j < 3; ++j)
-                    if (lf[f][j] < nov) links[cur[lf[f][j]]++] = {lf[f][(j + 1) % 3], lf[f][(j + 2) % 3], (uint16_t)f};
+                    if (lf[f][j] < nov) {
+                        const uint64_t gf = T.l[ELEM_F][f];
+                        links[cur[lf[f][j]]++] = {lf[f][(j + 1) % 3], lf[f][(j + 2) % 3], (uint16_t)f,
+                                                  (uint16_t)le(fe[3ull * gf + j]), (uint16_t)le(fe[3ull * gf + (j + 2) % 3])};
+                    }
             auto& FO = fan_off[p];
             auto& FV = fan_v[p];
             auto& FF = fan_f[p];
+            auto& FE = fan_e[p];
             FO.assign(nov + 1, 0);
             for (uint32_t v = 0; v < nov && !bad; ++v) {
                 auto*          L = links.data() + off[v];
@@ -772,12 +855,13 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
                 uint32_t curl = start, used = 0;
                 FV.push_back(L[curl][0]);
                 FF.push_back(L[curl][2]);
+                FE.push_back(L[curl][3]);
                 while (used < k) {
                     ++used;
                     const uint16_t nxt = L[curl][1];
                     if (used == k) {
                         if (closed) { if (nxt != L[start][0]) bad = 1; }
-                        else { FV.push_back(nxt); FF.push_back(0xFFFFu); }
+                        else { FV.push_back(nxt); FF.push_back(0xFFFFu); FE.push_back(L[curl][4]); }
                         break;
                     }
                     FV.push_back(nxt);
@@ -787,13 +871,15 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
                     if (nf_ != 1) { bad = 1; break; }
                     curl = found;
                     FF.push_back(L[curl][2]);
+                    FE.push_back(L[curl][3]);
                 }
             }
             FO[nov] = (uint16_t)FV.size();
         }
         fans_ok = !bad;
     }
-    M.fans = fans_ok;
+    M.fans  = fans_ok;
+    M.ring2 = ring2;
 
     lap("fans");
     // ---- prefixes: attribute slots (padded to 4), linear ids, ltog offsets, blob offsets ----
@@ -822,7 +908,15 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
             M.total_local[t] += D.n[t];
         }
         D.n_stash    = (uint16_t)tmp[p].stash.size();
-        D.flags      = (M.fans ? FLAG_FANS : 0) | (M.max_edge_incident_faces <= 2 ? FLAG_FF : 0);
+        D.flags      = (M.fans ? FLAG_FANS : 0) | (M.max_edge_incident_faces <= 2 ? FLAG_FF : 0) | (ring2 ? FLAG_RING2 : 0);
+        if (ring2) {
+            D.n_r2     = (uint16_t)(tmp[p].r2_off.empty() ? 0 : tmp[p].r2_off.size() - 1);
+            D.n_ext    = (uint16_t)tmp[p].ext.size();
+            D.r2_total = (uint32_t)tmp[p].r2_val.size();
+            M.max_ext      = std::max<uint32_t>(M.max_ext, D.n_ext);
+            M.max_r2       = std::max<uint32_t>(M.max_r2, D.n_r2);
+            M.max_r2_total = std::max<uint32_t>(M.max_r2_total, D.r2_total);
+        }
         D.fan_total  = M.fans ? (uint32_t)fan_v[p].size() : 0;
         M.max_fan_total = std::max<uint32_t>(M.max_fan_total, D.fan_total);
         M.max_stash  = std::max<uint32_t>(M.max_stash, D.n_stash);
@@ -955,6 +1049,19 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
             memcpy(B + D.off_fanoff(), fan_off[p].data(), fan_off[p].size() * 2);
             memcpy(B + D.off_fanv(), fan_v[p].data(), fan_v[p].size() * 2);
             memcpy(B + D.off_fanf(), fan_f[p].data(), fan_f[p].size() * 2);
+            memcpy(B + D.off_fane(), fan_e[p].data(), fan_e[p].size() * 2);
+        }
+        if (D.flags & FLAG_RING2) {
+            if (!T.r2_idx.empty()) memcpy(B + D.o_r2idx, T.r2_idx.data(), T.r2_idx.size() * 2);
+            if (!T.r2_off.empty())
+                memcpy(B + D.o_r2off, T.r2_off.data(), T.r2_off.size() * 2);
+            if (!T.r2_val.empty()) memcpy(B + D.o_r2val, T.r2_val.data(), T.r2_val.size() * 2);
+            uint32_t* eo = reinterpret_cast<uint32_t*>(B + D.o_ext);
+            for (size_t k = 0; k < T.ext.size(); ++k) {
+                const uint32_t g = T.ext[k], q = vpatch[g];
+                const uint32_t s = (uint32_t)(std::lower_bound(T.stash.begin(), T.stash.end(), q) - T.stash.begin());
+                eo[k]            = pack_owner(s, M.global_to_slot[ELEM_V][g] - M.slot_base[ELEM_V][q]);
+            }
         }
         for (int t = 0; t < 3; ++t) {
             uint32_t* own = reinterpret_cast<uint32_t*>(B + D.off_own(t));

@@ -59,6 +59,8 @@ struct HostMesh
     bool     packed                 = false;  // rank-annotated patch format (patch_layout.h)
     bool     fans                   = false;  // one-ring fans stored (manifold, consistently oriented input)
     uint32_t max_fan_total          = 0;
+    bool     ring2                  = false;  // ring-2 extension stored (patch_layout.h, FLAG_RING2)
+    uint32_t max_ext = 0, max_r2 = 0, max_r2_total = 0;
     double   build_seconds          = 0;
     double   patcher_seconds        = 0;
 
@@ -89,6 +91,8 @@ struct BuildOptions
     uint32_t lloyd_iters  = 5;
     bool     force_wide   = false;  // never use the packed format (tests of the atomic path)
     bool     no_fans      = false;  // never store one-ring fans (tests of the generic kernels)
+    bool     no_ring2     = false;  // skip the ring-2 extension (meshes that never run a k-ring consumer: saves build time
+                                    // and ~3 bytes per face of patch store)
 };
 
 // Global edge numbering identical to the reference (first appearance while

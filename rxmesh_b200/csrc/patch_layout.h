@@ -5,7 +5,7 @@
 // lp_hashtable.h:46-290, context.h:15-441) for the STATIC path.
 //
 // Design (see DESIGN.md "Data layout in HBM"):
-//  * one 128-byte PatchDesc per patch in a dense array: counts, slot bases and the
+//  * one 160-byte PatchDesc per patch in a dense array: counts, slot bases and the
 //    PRECOMPUTED byte offset of every section, so a block issues its TMA bulk
 //    copies without any layout arithmetic;
 //  * one contiguous, 16-byte-aligned "topology blob" per patch holding, in this
@@ -97,6 +97,7 @@ constexpr uint32_t PK_MAX_ERANK = 16;      // ranks of edge lists: 4 bits (FE en
 constexpr uint16_t FLAG_PACKED  = 1;
 constexpr uint16_t FLAG_FANS    = 2;
 constexpr uint16_t FLAG_FF      = 4;       // bit 2: stored FF rows of the owned faces (edge-manifold input)
+constexpr uint16_t FLAG_RING2   = 8;       // bit 3: full one-rings of the ribbon vertices next to owned vertices (k-ring consumers)
 constexpr uint16_t FAN_CLOSED   = 0x8000;  // bit 15 of a fan_off entry: the fan of this vertex is closed
 constexpr uint16_t FAN_OFF_MASK = 0x7FFF;
 constexpr uint64_t INVALID64_ = 0xFFFFFFFFFFFFFFFFull;
@@ -140,6 +141,19 @@ struct alignas(16) PatchDesc
     uint32_t o_ff;          // stored FF: 3 u16 per OWNED face, the faces across edge 0, 1, 2 compacted to the front, 0xFFFF after
     uint32_t o_ef;          // stored EF: 2 u16 per OWNED edge, its (at most two) faces in ascending local id, 0xFFFF after
     uint32_t pad1[2];
+    // ---- sections appended in round 2 (after EF, so every older offset keeps its meaning) ----
+    uint32_t o_fane;        // fan edges: fan_e[i] = local edge between the fan's vertex and fan_v[i] (VE as a plain read, oriented VE)
+    // RING-2 EXTENSION (FLAG_RING2): a k-ring walk that starts at an owned vertex may have to expand a RIBBON vertex, whose
+    // one-ring is only partly inside the patch.  For every not-owned vertex that is adjacent to an owned one the builder
+    // stores the COMPLETE ring as ids in an extended local space: [0, n[V]) = the patch's vertices, n[V] + k = the k-th
+    // "ext" vertex (a vertex two rings out that the patch does not hold), resolved through ext_own like a ribbon vertex.
+    uint32_t o_r2idx;       // u16[n[V] - n_owned[V]]: ring index of the not-owned vertex, 0xFFFF = ring not stored
+    uint32_t o_r2off;       // u16[n_r2 + 1]
+    uint32_t o_r2val;       // u16[r2_total] extended local ids
+    uint32_t o_ext;         // u32[n_ext] owner records (stash slot << 16 | local id in owner)
+    uint16_t n_r2, n_ext;
+    uint32_t r2_total;
+    uint32_t pad2;
 
     RXM_HD uint32_t ev_bytes() const { return o_fe; }
     RXM_HD uint32_t fe_bytes() const { return o_fv - o_fe; }
@@ -168,6 +182,12 @@ struct alignas(16) PatchDesc
     RXM_HD uint32_t off_ef() const { return o_ef; }
     RXM_HD uint32_t ef_bytes() const { return (flags & FLAG_FF) ? round_up(4u * n_owned[ELEM_E], 16) : 0u; }
     RXM_HD uint32_t slot_cap(uint32_t t) const { return (n_owned[t] + 3u) & ~3u; }
+    RXM_HD uint32_t off_fane() const { return o_fane; }
+    RXM_HD uint32_t fane_bytes() const { return o_r2idx - o_fane; }
+    RXM_HD uint32_t r2idx_bytes() const { return o_r2off - o_r2idx; }
+    RXM_HD uint32_t r2off_bytes() const { return o_r2val - o_r2off; }
+    RXM_HD uint32_t r2val_bytes() const { return o_ext - o_r2val; }
+    RXM_HD uint32_t ext_bytes() const { return (flags & FLAG_RING2) ? round_up(4u * n_ext, 16) : 0u; }
 
     // builder: lay the sections out from the counts / flags already stored in this record
     inline void compute_layout()
@@ -197,10 +217,22 @@ struct alignas(16) PatchDesc
         o_stash    = o;
         o_ff       = o + 16u * n_stash;
         o_ef       = o_ff + ff_bytes();
-        topo_bytes = o_ef + ef_bytes();
+        o          = o_ef + ef_bytes();
+        o_fane     = o;
+        o += (flags & FLAG_FANS) ? round_up(2u * fan_total, 16) : 0u;
+        const bool r2 = (flags & FLAG_RING2) != 0;
+        o_r2idx = o;
+        o += r2 ? round_up(2u * (uint32_t)(n[ELEM_V] - n_owned[ELEM_V]), 16) : 0u;
+        o_r2off = o;
+        o += r2 ? round_up(2u * (n_r2 + 1u), 16) : 0u;
+        o_r2val = o;
+        o += r2 ? round_up(2u * r2_total, 16) : 0u;
+        o_ext = o;
+        o += r2 ? round_up(4u * n_ext, 16) : 0u;
+        topo_bytes = o;
     }
 };
-static_assert(sizeof(PatchDesc) == 128, "PatchDesc must be 128 bytes");
+static_assert(sizeof(PatchDesc) == 160, "PatchDesc must be 160 bytes");
 
 // By-value kernel argument: the static-path equivalent of the reference Context.
 struct MeshView
@@ -214,6 +246,7 @@ struct MeshView
     uint32_t         packed;              // 1: every patch uses the rank-annotated format
     uint32_t         fans;                // 1: every patch stores the one-ring fans of its owned vertices
     uint32_t         edge_manifold;       // 1: no edge of the input has more than two incident faces
+    uint32_t         ring2;               // 1: every patch stores the ring-2 extension (FLAG_RING2)
 };
 
 // Attribute layouts: numeric values of the reference's layoutT (types.h:84-90).

@@ -55,6 +55,7 @@ struct rxm_mesh
     };
     Csr       csr[16];      // materialised queries (rxm_query_csr), indexed by op
     uint32_t* d_flag = nullptr;
+    uint64_t  bilateral_deferred = 0;  // vertices the last rxm_bilateral_filter call sent down the cross-patch path
     rxm_attr* scratch1[32]  = {};  // per query op: [2*op] input, [2*op+1] output of rxm_query_consume_host
     // ---- chunked upload / compute / download pipeline of the host-buffer entry points (see pipelined_host_call) ----
     struct PipePlan
@@ -135,6 +136,12 @@ int rxm_init(int device)
 int rxm_mesh_create(const uint32_t* fv, uint32_t num_faces, const uint32_t* face_patch, uint32_t patch_size,
                     int num_threads, rxm_mesh** out)
 {
+    return rxm_mesh_create_ex(fv, num_faces, face_patch, patch_size, num_threads, getenv("RXM_NO_RING2") ? RXM_BUILD_NO_RING2 : 0u, out);
+}
+
+int rxm_mesh_create_ex(const uint32_t* fv, uint32_t num_faces, const uint32_t* face_patch, uint32_t patch_size,
+                       int num_threads, uint32_t flags, rxm_mesh** out)
+{
     if (!fv || !out) return fail(RXM_ERR_INVALID, "rxm_mesh_create: null argument");
     rxm_mesh* m = new (std::nothrow) rxm_mesh();
     if (!m) return fail(RXM_ERR_INVALID, "rxm_mesh_create: out of memory");
@@ -144,6 +151,7 @@ int rxm_mesh_create(const uint32_t* fv, uint32_t num_faces, const uint32_t* face
     opt.verbose     = getenv("RXM_VERBOSE") != nullptr;
     opt.force_wide  = getenv("RXM_FORCE_WIDE") != nullptr;  // tests: exercise the atomic (wide-format) kernels
     opt.no_fans     = getenv("RXM_NO_FANS") != nullptr;     // tests: exercise the generic (transpose) kernels
+    opt.no_ring2    = (flags & RXM_BUILD_NO_RING2) != 0;
     std::string e;
     try {
         e = build_mesh(fv, num_faces, face_patch, opt, m->h);
@@ -163,6 +171,9 @@ int rxm_mesh_create(const uint32_t* fv, uint32_t num_faces, const uint32_t* face
     m->lim.max_stash               = m->h.max_stash;
     m->lim.max_face_adjacent_faces = m->h.max_face_adjacent_faces;
     m->lim.max_fan_total           = m->h.max_fan_total;
+    m->lim.max_ext                 = m->h.max_ext;
+    m->lim.max_r2                  = m->h.max_r2;
+    m->lim.max_r2_total            = m->h.max_r2_total;
     *out                           = m;
     return RXM_OK;
 }
@@ -272,6 +283,7 @@ int rxm_mesh_to_device(rxm_mesh* m)
     m->view.packed      = h.packed ? 1u : 0u;
     m->view.fans        = h.fans ? 1u : 0u;
     m->view.edge_manifold = h.max_edge_incident_faces <= 2 ? 1u : 0u;
+    m->view.ring2         = h.ring2 ? 1u : 0u;
     for (int t = 0; t < 3; ++t) {
         m->view.num_slots[t]       = h.num_slots[t];
         m->view.num_elems[t]       = h.num_elems[t];
@@ -366,6 +378,7 @@ uint64_t rxm_mesh_info(const rxm_mesh* m, int what)
         case RXM_INFO_ON_DEVICE: return m->on_device;
         case RXM_INFO_PACKED: return h.packed;
         case RXM_INFO_FANS: return h.fans;
+        case RXM_INFO_RING2: return h.ring2;
         default: return 0;
     }
 }
@@ -403,6 +416,13 @@ int rxm_mesh_patch(const rxm_mesh* m, uint32_t p, rxm_patch_view* o)
     o->ff      = (D.flags & FLAG_FF) ? reinterpret_cast<const uint16_t*>(B + D.off_ff()) : nullptr;
     o->ef      = (D.flags & FLAG_FF) ? reinterpret_cast<const uint16_t*>(B + D.off_ef()) : nullptr;
     o->fan_total = D.fan_total;
+    o->fan_e   = (D.flags & FLAG_FANS) ? reinterpret_cast<const uint16_t*>(B + D.off_fane()) : nullptr;
+    const bool r2 = (D.flags & FLAG_RING2) != 0;
+    o->r2_idx  = r2 ? reinterpret_cast<const uint16_t*>(B + D.o_r2idx) : nullptr;
+    o->r2_off  = r2 ? reinterpret_cast<const uint16_t*>(B + D.o_r2off) : nullptr;
+    o->r2_val  = r2 ? reinterpret_cast<const uint16_t*>(B + D.o_r2val) : nullptr;
+    o->ext_owner = r2 ? reinterpret_cast<const uint32_t*>(B + D.o_ext) : nullptr;
+    o->n_r2 = D.n_r2, o->n_ext = D.n_ext, o->r2_total = D.r2_total;
     o->stash   = reinterpret_cast<const uint32_t*>(B + D.off_stash());
     o->n_stash = D.n_stash;
     return RXM_OK;
@@ -428,13 +448,14 @@ const uint32_t* rxm_mesh_lin_base(const rxm_mesh* m, int t)
 {
     return (m && t >= 0 && t < 3) ? m->h.lin_base[t].data() : nullptr;
 }
+// NULL once rxm_mesh_compact released the global edge arrays (callers check)
 const uint32_t* rxm_mesh_edges(const rxm_mesh* m)
 {
-    return m ? m->h.ev.data() : nullptr;
+    return (m && !m->h.ev.empty()) ? m->h.ev.data() : nullptr;
 }
 const uint32_t* rxm_mesh_face_edges(const rxm_mesh* m)
 {
-    return m ? m->h.fe.data() : nullptr;
+    return (m && !m->h.fe.empty()) ? m->h.fe.data() : nullptr;
 }
 
 const uint32_t* rxm_mesh_device_slot_base(const rxm_mesh* m, int t)
@@ -1041,25 +1062,41 @@ int rxm_bilateral_filter(rxm_mesh* m, rxm_attr* in, rxm_attr* out, uint32_t iter
     uint64_t  nnz = 0;
     if ((rc = rxm_query_csr(m, RXM_OP_VV, &off, &val, &nnz, stream))) return rc;
     rxm_attr *nrm = nullptr, *tmp = nullptr;
-    if ((rc = get_scratch(m, 3, &nrm))) return rc;
+    // default: one patch-local kernel per iteration with the normals fused in (k_bilateral_patch); meshes without one-ring
+    // fans (non-manifold / inconsistently oriented input) and RXM_BILATERAL_CSR=1 keep the two-kernel path over the CSR
+    const bool patch_local = m->view.fans && !getenv("RXM_BILATERAL_CSR");
+    if (!patch_local && (rc = get_scratch(m, 3, &nrm))) return rc;
     if (iters > 1 && (rc = get_scratch(m, 0, &tmp))) return rc;
-    if (!m->d_flag) CU(cudaMalloc(&m->d_flag, 4));
-    CU(cudaMemsetAsync(m->d_flag, 0, 4, (cudaStream_t)stream));
+    if (!m->d_flag) CU(cudaMalloc(&m->d_flag, 8));
+    CU(cudaMemsetAsync(m->d_flag, 0, 8, (cudaStream_t)stream));
     rxm_attr* src = in;
     for (uint32_t k = 1; k <= iters; ++k) {
         rxm_attr* dst = ((iters - k) % 2 == 0) ? out : tmp;
-        // filtering_rxmesh.cuh:75-95: vertex normals of the current positions, then the filter
-        if ((rc = rxm_vertex_normals(m, src, nrm, 1, stream))) return rc;
-        cudaError_t e = launch_bilateral_step(off, val, m->h.num_slots[ELEM_V], (const float*)src->d, (const float*)nrm->d,
-                                              (float*)dst->d, m->d_flag, (cudaStream_t)stream);
-        if (e != cudaSuccess) return fail(RXM_ERR_CUDA, std::string("bilateral: ") + cudaGetErrorString(e));
+        if (patch_local) {
+            const char* why = nullptr;
+            cudaError_t e   = launch_bilateral_patch(m->view, m->lim, off, val, (const float*)src->d, (float*)dst->d, m->d_flag,
+                                                     (cudaStream_t)stream, &why);
+            if ((rc = kernel_status(e, why, "rxm_bilateral_filter"))) return rc;
+        } else {
+            // filtering_rxmesh.cuh:75-95: vertex normals of the current positions, then the filter
+            if ((rc = rxm_vertex_normals(m, src, nrm, 1, stream))) return rc;
+            cudaError_t e = launch_bilateral_step(off, val, m->h.num_slots[ELEM_V], (const float*)src->d, (const float*)nrm->d,
+                                                  (float*)dst->d, m->d_flag, (cudaStream_t)stream);
+            if (e != cudaSuccess) return fail(RXM_ERR_CUDA, std::string("bilateral: ") + cudaGetErrorString(e));
+        }
         src = dst;
     }
-    uint32_t flag = 0;
-    CU(cudaMemcpyAsync(&flag, m->d_flag, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    uint32_t flag[2] = {0, 0};
+    CU(cudaMemcpyAsync(flag, m->d_flag, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU(cudaStreamSynchronize((cudaStream_t)stream));
-    if (flag) return fail(RXM_ERR_UNSUPPORTED, "rxm_bilateral_filter: a neighbourhood exceeded 80 vertices (maxVVSize of the reference)");
+    m->bilateral_deferred = flag[1];
+    if (flag[0]) return fail(RXM_ERR_UNSUPPORTED, "rxm_bilateral_filter: a neighbourhood exceeded 80 vertices (maxVVSize of the reference)");
     return RXM_OK;
+}
+
+uint64_t rxm_bilateral_deferred(const rxm_mesh* m)
+{
+    return m ? m->bilateral_deferred : 0;
 }
 
 int rxm_boundary_vertices(rxm_mesh* m, rxm_attr* flag, void* stream)

@@ -1239,6 +1239,282 @@ __global__ void __launch_bounds__(128) k_bilateral(const uint32_t* __restrict__ 
 }
 
 // --------------------------------------------------------------------------
+// bilateral mesh denoising, PATCH-LOCAL (round 2; replaces the thread-per-slot walk over a global CSR above as the default)
+// apps/Filtering/filtering_rxmesh_kernel.cuh:15-46 (unit-face vertex normals) + :426-548 (the filter) in ONE kernel.
+//
+// Evidence for the redesign (profiles/r01c_ncu_full.csv, k_bilateral): 82 % issue-active at 6 % DRAM, 3600 thread
+// instructions per vertex, 48 % of them the O(cnt^2) duplicate scan over an 80-entry LOCAL-memory list, a separate normals
+// kernel and a 28 B/vertex global CSR.  Here one block owns one patch:
+//   * the fans, the ribbon / ext owner tables, the ring-2 extension and the patch's coordinate slice arrive by TMA bulk
+//     copies; ribbon and ext coordinates are gathered once per patch; every k-ring walk then runs out of shared memory;
+//   * the vertex normal (sum of unit face normals) falls out of the first pass over the vertex's own fan -- the filter needs
+//     no other vertex's normal, so the normals kernel and its attribute round trip are gone;
+//   * "seen" is a per-thread BITMAP over the patch's extended local ids (word-interleaved in shared memory: conflict-free),
+//     so a duplicate visit costs a load and a test instead of a list scan, and rejected vertices are not measured twice;
+//   * the accepted list lives in shared memory (no LDL); sigma_s' sums accumulate while vertices are accepted, and the two
+//     exponentials of a weight are one: exp(-t^2 / 2 sigma_c^2) exp(-h^2 / 2 sigma_s^2) = exp(-(t^2/sigma_c^2 + h^2/sigma_s^2) / 2);
+//   * rings: owned vertices -> their fan; ribbon vertices next to an owned vertex -> the ring-2 extension (complete ring in
+//     extended local ids, patch_layout.h); a walk that has to expand any other vertex (outer ribbon, ext, or more than
+//     BIL_FAST_CAP accepted) is DEFERRED: the block compacts those vertices and reruns them on the cross-patch path (slot
+//     space, the materialised VV CSR, the reference's 80-entry cap), a few full warps instead of stragglers in every warp.
+// Membership (dist^2 <= 4 sigma_c^2) is evaluated as fmaf(dz, dz, fmaf(dy, dy, dx * dx)) on fp32 differences in BOTH paths
+// and in the oracle's fp32-membership mode, so the neighbourhoods are the same sets everywhere.
+// --------------------------------------------------------------------------
+constexpr int BIL_BT       = 128;
+constexpr int BIL_FAST_CAP = 32;  // accepted neighbours the fast path keeps per vertex before it defers
+
+__device__ __forceinline__ float dist2f(float dx, float dy, float dz)
+{
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+struct BilPatch
+{
+    const uint16_t *fo, *fv, *r2idx, *r2off, *r2val;
+    const float*    x;  // AoS xyz of every extended local vertex
+    uint32_t        nv, nov, next;
+};
+
+// pass over the vertex's own fan: unit vertex normal (normalised sum of unit face normals) and sigma_c^2 = min ring dist^2
+__device__ __forceinline__ void bil_normal_sigma(const BilPatch& B, uint32_t v, float px, float py, float pz, float& nx,
+                                                 float& ny, float& nz, float& sc2)
+{
+    const uint32_t o = B.fo[v], b = o & FAN_OFF_MASK, e = B.fo[v + 1] & FAN_OFF_MASK;
+    nx = ny = nz = 0.f;
+    const float* q   = B.x + 3u * B.fv[b];
+    const float  d0x = q[0] - px, d0y = q[1] - py, d0z = q[2] - pz;
+    sc2              = dist2f(d0x, d0y, d0z);
+    float ax = d0x, ay = d0y, az = d0z;
+    auto  face = [&](float cx, float cy, float cz) {
+        const float fx = ay * cz - az * cy, fy = az * cx - ax * cz, fz = ax * cy - ay * cx;
+        const float w  = rsqrtf(fx * fx + fy * fy + fz * fz);
+        nx += fx * w, ny += fy * w, nz += fz * w;
+    };
+    for (uint32_t i = b + 1; i < e; ++i) {
+        q              = B.x + 3u * B.fv[i];
+        const float cx = q[0] - px, cy = q[1] - py, cz = q[2] - pz;
+        sc2            = fminf(sc2, dist2f(cx, cy, cz));
+        face(cx, cy, cz);
+        ax = cx, ay = cy, az = cz;
+    }
+    if (o & FAN_CLOSED) face(d0x, d0y, d0z);
+    const float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
+    nx *= inv, ny *= inv, nz *= inv;
+}
+
+// fast path of one owned vertex; false = the walk left what the patch can answer (caller defers the vertex)
+template <int BT>
+__device__ __forceinline__ bool bil_fast(const BilPatch& B, uint32_t v, uint32_t* bm, uint32_t bm_words, uint16_t* lst, float* out)
+{
+    const uint32_t tid = threadIdx.x;
+    const float    px = B.x[3 * v], py = B.x[3 * v + 1], pz = B.x[3 * v + 2];
+    float          nx, ny, nz, sc2;
+    bil_normal_sigma(B, v, px, py, pz, nx, ny, nz, sc2);
+    const float radius = 4.0f * sc2;
+    for (uint32_t w = 0; w < bm_words; ++w)
+        bm[w * BT + tid] = 0u;
+    auto seen_or_mark = [&](uint32_t u) -> bool {  // true if u was seen before; marks it either way
+        uint32_t&      word = bm[(u >> 5) * BT + tid];
+        const uint32_t bit = 1u << (u & 31u), old = word;
+        word = old | bit;
+        return (old & bit) != 0u;
+    };
+    seen_or_mark(v);
+    uint32_t na  = 0;
+    float    sum = 0.f, sum_sq = 0.f;
+    bool     ok  = true;
+    auto visit = [&](uint32_t u) {
+        if (seen_or_mark(u)) return;
+        const float* q  = B.x + 3u * u;
+        const float  cx = q[0] - px, cy = q[1] - py, cz = q[2] - pz;
+        if (dist2f(cx, cy, cz) > radius) return;
+        if (na == (uint32_t)BIL_FAST_CAP) {
+            ok = false;
+            return;
+        }
+        lst[na * BT + tid] = (uint16_t)u;
+        ++na;
+        const float h = fabsf(cx * nx + cy * ny + cz * nz);
+        sum += h, sum_sq += h * h;
+    };
+    {
+        const uint32_t b = B.fo[v] & FAN_OFF_MASK, e = B.fo[v + 1] & FAN_OFF_MASK;
+        for (uint32_t i = b; i < e; ++i)
+            visit(B.fv[i]);
+    }
+    for (uint32_t head = 0; ok && head < na; ++head) {
+        const uint32_t  w = lst[head * BT + tid];
+        const uint16_t* ring;
+        uint32_t        rb, re;
+        if (w < B.nov) {
+            ring = B.fv, rb = B.fo[w] & FAN_OFF_MASK, re = B.fo[w + 1] & FAN_OFF_MASK;
+        } else {
+            const uint32_t r = w < B.nv ? (uint32_t)B.r2idx[w - B.nov] : 0xFFFFu;
+            if (r == 0xFFFFu) return false;  // ring not in this patch
+            ring = B.r2val, rb = B.r2off[r], re = B.r2off[r + 1];
+        }
+        for (uint32_t i = rb; i < re; ++i)
+            visit(ring[i]);
+    }
+    if (!ok) return false;
+    const float c   = (float)(na + 1u);  // the vertex itself is the first member of its neighbourhood (h = 0, t = 0)
+    float       ss2 = sum_sq / c - (sum * sum) / (c * c);
+    if (ss2 < 1.0e-20f) ss2 += 1.0e-20f;
+    const float ic = -0.5f / sc2, is = -0.5f / ss2;
+    float       num = 0.f, den = 1.f;
+    for (uint32_t k = 0; k < na; ++k) {
+        const float* q  = B.x + 3u * lst[k * BT + tid];
+        const float  cx = q[0] - px, cy = q[1] - py, cz = q[2] - pz;
+        const float  t2 = dist2f(cx, cy, cz), h = cx * nx + cy * ny + cz * nz;
+        const float  w  = __expf(t2 * ic + h * h * is);
+        num += w * h, den += w;
+    }
+    const float kk = num / den;
+    out[0] = px + nx * kk, out[1] = py + ny * kk, out[2] = pz + nz * kk;
+    return true;
+}
+
+// cross-patch path of one (deferred) owned vertex: slot space, VV CSR, accepted list of R-interleaved u32 slots in shared
+// memory, duplicate check by list scan, the reference's cap of 80 (filtering_rxmesh.cuh: maxVVSize)
+__device__ __forceinline__ void bil_slow(const BilPatch& B, uint32_t v, uint32_t slot_v, const uint32_t* __restrict__ off,
+                                         const uint32_t* __restrict__ val, const float* __restrict__ xg, uint32_t* lst, uint32_t R,
+                                         uint32_t j, uint32_t* __restrict__ overflow, float* out)
+{
+    const float px = B.x[3 * v], py = B.x[3 * v + 1], pz = B.x[3 * v + 2];
+    float       nx, ny, nz, sc2;
+    bil_normal_sigma(B, v, px, py, pz, nx, ny, nz, sc2);
+    const float radius = 4.0f * sc2;
+    uint32_t    cnt    = 1;
+    lst[j]             = slot_v;
+    float sum = 0.f, sum_sq = 0.f;
+    for (uint32_t head = 0; head < cnt; ++head) {
+        const uint32_t w = lst[head * R + j];
+        for (uint32_t i = off[w]; i < off[w + 1]; ++i) {
+            const uint32_t u = val[i];
+            bool           dup = false;
+            for (uint32_t k = 0; k < cnt; ++k)
+                dup |= (lst[k * R + j] == u);
+            if (dup) continue;
+            const float cx = xg[3ull * u] - px, cy = xg[3ull * u + 1] - py, cz = xg[3ull * u + 2] - pz;
+            if (dist2f(cx, cy, cz) > radius) continue;
+            if (cnt < (uint32_t)BILATERAL_MAX_VV) {
+                lst[cnt * R + j] = u;
+                ++cnt;
+                const float h = fabsf(cx * nx + cy * ny + cz * nz);
+                sum += h, sum_sq += h * h;
+            } else
+                *overflow = 1u;  // the reference asserts here
+        }
+    }
+    const float c   = (float)cnt;
+    float       ss2 = sum_sq / c - (sum * sum) / (c * c);
+    if (ss2 < 1.0e-20f) ss2 += 1.0e-20f;
+    const float ic = -0.5f / sc2, is = -0.5f / ss2;
+    float       num = 0.f, den = 1.f;
+    for (uint32_t k = 1; k < cnt; ++k) {
+        const uint32_t u  = lst[k * R + j];
+        const float    cx = xg[3ull * u] - px, cy = xg[3ull * u + 1] - py, cz = xg[3ull * u + 2] - pz;
+        const float    t2 = dist2f(cx, cy, cz), h = cx * nx + cy * ny + cz * nz;
+        const float    w  = __expf(t2 * ic + h * h * is);
+        num += w * h, den += w;
+    }
+    const float kk = num / den;
+    out[0] = px + nx * kk, out[1] = py + ny * kk, out[2] = pz + nz * kk;
+}
+
+__global__ void __launch_bounds__(BIL_BT) k_bilateral_patch(MeshView mv, const float* __restrict__ x, float* __restrict__ xo,
+                                                            const uint32_t* __restrict__ csr_off, const uint32_t* __restrict__ csr_val,
+                                                            uint32_t bm_words, uint32_t* __restrict__ flags /* [0] overflow, [1] deferred */)
+{
+    constexpr int BT = BIL_BT;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint64_t                      bar;
+    __shared__ uint32_t                      s_ndef;
+    const PatchDesc d    = load_desc(mv.desc + blockIdx.x);
+    const uint8_t*  blob = mv.topo + d.topo_off;
+    const bool      r2   = (d.flags & FLAG_RING2) != 0;
+    const uint32_t  nv = d.n[ELEM_V], nov = d.n_owned[ELEM_V], cap = d.slot_cap(ELEM_V), next = r2 ? d.n_ext : 0u;
+    Smem            sm(smem_raw);
+    uint16_t*       s_fo    = sm.alloc<uint16_t>(d.fanoff_bytes() / 2);
+    uint16_t*       s_fv    = sm.alloc<uint16_t>(d.fanv_bytes() / 2);
+    uint32_t*       s_own   = sm.alloc<uint32_t>(d.own_bytes(ELEM_V) / 4);
+    StashEntry*     s_stash = sm.alloc<StashEntry>(d.n_stash);
+    uint16_t*       s_r2i   = sm.alloc<uint16_t>(r2 ? d.r2idx_bytes() / 2 : 8);
+    uint16_t*       s_r2o   = sm.alloc<uint16_t>(r2 ? d.r2off_bytes() / 2 : 8);
+    uint16_t*       s_r2v   = sm.alloc<uint16_t>(r2 ? d.r2val_bytes() / 2 : 8);
+    uint32_t*       s_ext   = sm.alloc<uint32_t>(r2 ? d.ext_bytes() / 4 : 4);
+    float*          s_x     = sm.alloc<float>(3 * max(nv + next, cap));
+    float*          s_out   = sm.alloc<float>(3 * cap);
+    uint16_t*       s_def   = sm.alloc<uint16_t>(nov + 8u);
+    uint32_t*       s_priv  = sm.alloc<uint32_t>((bm_words + BIL_FAST_CAP / 2) * BT);  // bitmaps, then the u16 lists
+    if (threadIdx.x == 0) {
+        s_ndef = 0;
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+        const uint32_t r2b = r2 ? d.r2idx_bytes() + d.r2off_bytes() + d.r2val_bytes() + d.ext_bytes() : 0u;
+        mbar_arrive_expect_tx(&bar, d.fanoff_bytes() + d.fanv_bytes() + d.own_bytes(ELEM_V) + d.stash_bytes() + r2b + 12u * cap);
+        bulk_g2s(s_fo, blob + d.off_fanoff(), d.fanoff_bytes(), &bar);
+        if (d.fanv_bytes()) bulk_g2s(s_fv, blob + d.off_fanv(), d.fanv_bytes(), &bar);
+        if (d.own_bytes(ELEM_V)) bulk_g2s(s_own, blob + d.off_own(ELEM_V), d.own_bytes(ELEM_V), &bar);
+        if (d.stash_bytes()) bulk_g2s(s_stash, blob + d.off_stash(), d.stash_bytes(), &bar);
+        if (r2) {
+            if (d.r2idx_bytes()) bulk_g2s(s_r2i, blob + d.o_r2idx, d.r2idx_bytes(), &bar);
+            bulk_g2s(s_r2o, blob + d.o_r2off, d.r2off_bytes(), &bar);
+            if (d.r2val_bytes()) bulk_g2s(s_r2v, blob + d.o_r2val, d.r2val_bytes(), &bar);
+            if (d.ext_bytes()) bulk_g2s(s_ext, blob + d.o_ext, d.ext_bytes(), &bar);
+        }
+        if (cap) bulk_g2s(s_x, x + 3ull * d.slot_base[ELEM_V], 12u * cap, &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    for (uint32_t i = nov + threadIdx.x; i < nv + next; i += BT) {  // ribbon and ext vertices: from their owners' slots
+        const uint32_t o = i < nv ? s_own[i - nov] : s_ext[i - nv];
+        const float*   g = x + 3ull * ((uint64_t)s_stash[o >> 16].slot_base[ELEM_V] + (o & 0xFFFFu));
+        const float    a = ldg_stream(g), b = ldg_stream(g + 1), c = ldg_stream(g + 2);
+        s_x[3 * i] = a, s_x[3 * i + 1] = b, s_x[3 * i + 2] = c;
+    }
+    __syncthreads();
+    BilPatch B;
+    B.fo = s_fo, B.fv = s_fv, B.r2idx = s_r2i, B.r2off = s_r2o, B.r2val = s_r2v, B.x = s_x;
+    B.nv = r2 ? nv : nov, B.nov = nov, B.next = next;  // without ring-2 data any not-owned vertex defers (w >= B.nv)
+    uint32_t* bm  = s_priv;
+    uint16_t* lst = reinterpret_cast<uint16_t*>(s_priv + bm_words * BT);
+    for (uint32_t v = threadIdx.x; v < cap; v += BT) {
+        float o[3] = {0.f, 0.f, 0.f};
+        if (v < nov) {
+            const uint32_t fb = s_fo[v] & FAN_OFF_MASK, fe = s_fo[v + 1] & FAN_OFF_MASK;
+            if (fb == fe) {  // no neighbours: keeps its position
+                o[0] = s_x[3 * v], o[1] = s_x[3 * v + 1], o[2] = s_x[3 * v + 2];
+            } else if (!bil_fast<BT>(B, v, bm, bm_words, lst, o)) {
+                s_def[atomicAdd(&s_ndef, 1u)] = (uint16_t)v;
+            }
+        }
+        s_out[3 * v] = o[0], s_out[3 * v + 1] = o[1], s_out[3 * v + 2] = o[2];
+    }
+    __syncthreads();
+    const uint32_t ndef = s_ndef;
+    if (ndef) {
+        // the private area as R interleaved lists of 80 slots; deferred vertices run R at a time on the first R threads
+        const uint32_t R = min((uint32_t)BT, ((bm_words + BIL_FAST_CAP / 2) * BT) / (uint32_t)BILATERAL_MAX_VV);
+        for (uint32_t base = 0; base < ndef; base += R) {
+            const uint32_t j = threadIdx.x;
+            if (j < R && base + j < ndef) {
+                const uint32_t v = s_def[base + j];
+                bil_slow(B, v, d.slot_base[ELEM_V] + v, csr_off, csr_val, x, s_priv, R, j, flags, s_out + 3 * v);
+            }
+        }
+        if (threadIdx.x == 0) atomicAdd(flags + 1, ndef);
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0 && cap) {
+        bulk_s2g(xo + 3ull * d.slot_base[ELEM_V], s_out, 12u * cap);
+        bulk_commit();
+        bulk_wait_all_read();
+    }
+}
+
+// --------------------------------------------------------------------------
 // reductions over OWNED elements (ReduceHandle: reduce_handle.cu:53-156, kernels/reduce.cuh:43-191)
 // kind: 0 dot, 1 sum of squares, 2 sum, 3 min, 4 max, 5 arg-min, 6 arg-max.  fp32 values, fp64 partials.
 // --------------------------------------------------------------------------
@@ -1494,7 +1770,9 @@ int pick_kmax(uint32_t nnz)
 #define RXM_LAUNCH_ONE(KERNEL, OPV, KM, PK, ...)                                         \
     do {                                                                                 \
         using Q = dev::PatchQuery<OPV, BT, KM, PK>;                                      \
-        smem    = Q::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, true, OPV == OP_EF ? stored_ef : stored_ff) + extra_smem(OPV); \
+        smem    = Q::smem_bytes(lim.max_n, lim.max_not_owned, lim.max_stash, true,                                \
+                                (OPV == OP_VV || OPV == OP_VE || OPV == OP_VF) ? fan_rows : (OPV == OP_EF ? stored_ef : stored_ff), \
+                                fan_entries) + extra_smem(OPV);                                                \
         auto kern = KERNEL<OPV, KM, PK>;                                                 \
         e         = set_smem(kern, smem);                                                \
         if (e != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");    \
@@ -1585,6 +1863,8 @@ cudaError_t launch_query_store(int op, const MeshView& mv, const KernelLimits& l
     cudaError_t e    = cudaSuccess;
     const uint32_t stored_ff  = mv.edge_manifold ? lim.max_owned[ELEM_F] : 0u;  // FF from the stored rows (plan(): ff3)
     const uint32_t stored_ef  = mv.edge_manifold ? lim.max_owned[ELEM_E] : 0u;  // EF from the stored pairs (plan(): ef3)
+    const bool     fanq = mv.edge_manifold && mv.fans;                             // VV / VE / VF from the fans (plan(): fanq)
+    const uint32_t fan_rows = fanq ? lim.max_owned[ELEM_V] : 0u, fan_entries = fanq ? lim.max_fan_total + 8u : 0u;
     auto        extra_smem = [&](int) { return 0u; };
     if (mv.packed)
         RXM_LAUNCH_OP(k_query_store, 1, true, mv, in, out);
@@ -1663,6 +1943,8 @@ cudaError_t launch_query_consume(int op, const MeshView& mv, const KernelLimits&
     cudaError_t e    = cudaSuccess;
     const uint32_t stored_ff = mv.edge_manifold ? lim.max_owned[ELEM_F] : 0u;  // FF from the stored rows (plan(): ff3)
     const uint32_t stored_ef = mv.edge_manifold ? lim.max_owned[ELEM_E] : 0u;  // EF from the stored pairs (plan(): ef3)
+    const bool     fanq = mv.edge_manifold && mv.fans;
+    const uint32_t fan_rows = fanq ? lim.max_owned[ELEM_V] : 0u, fan_entries = fanq ? lim.max_fan_total + 8u : 0u;
     auto extra_smem = [&](int opv) {
         uint32_t dst = 0;
         switch (opv) {
@@ -1840,7 +2122,7 @@ cudaError_t launch_query_csr(int op, const MeshView& mv, const KernelLimits& lim
     if (op == OP_FF && lim.max_face_adjacent_faces > 6) RXM_FAIL("FF: more than 6 adjacent faces per face");
     uint32_t    smem = 0;
     cudaError_t e    = cudaSuccess;
-    const uint32_t stored_ff = 0, stored_ef = 0;  // k_query_csr plans the generic path (gap-free ascending lists)
+    const uint32_t stored_ff = 0, stored_ef = 0, fan_rows = 0, fan_entries = 0;  // k_query_csr plans the generic path (gap-free ascending lists)
     auto        extra_smem = [&](int) { return 0u; };
     if (mv.packed)
         RXM_LAUNCH_OP(k_query_csr, 1, true, mv, patch_nnz_off, csr_off, csr_val);
@@ -1857,6 +2139,22 @@ cudaError_t launch_bilateral_step(const uint32_t* csr_off, const uint32_t* csr_v
 {
     if (num_slots == 0) return cudaSuccess;
     k_bilateral<<<(num_slots + 127) / 128, 128, 0, stream>>>(csr_off, csr_val, x, normals, xo, num_slots, overflow_flag);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bilateral_patch(const MeshView& mv, const KernelLimits& lim, const uint32_t* csr_off, const uint32_t* csr_val,
+                                   const float* x, float* xo, uint32_t* flags, cudaStream_t stream, const char** err)
+{
+    if (!mv.fans) RXM_FAIL("the patch-local bilateral kernel needs the one-ring fans");
+    const uint32_t capv = lim.max_owned[ELEM_V] + 4, nvx = lim.max_n[ELEM_V] + lim.max_ext;
+    const uint32_t bm_words = (nvx + 31u) / 32u;
+    const uint32_t smem = fan_smem(lim) + r16(2u * lim.max_not_owned[ELEM_V] + 16) + r16(2u * (lim.max_r2 + 1) + 16) +
+                          r16(2u * lim.max_r2_total + 16) + r16(4u * lim.max_ext + 16) + r16(12u * std::max(nvx, capv)) +
+                          r16(12u * capv) + r16(2u * (lim.max_owned[ELEM_V] + 8)) + r16(4u * (bm_words + BIL_FAST_CAP / 2) * BIL_BT) + 64u;
+    if ((bm_words + BIL_FAST_CAP / 2) * BIL_BT < (uint32_t)BILATERAL_MAX_VV) RXM_FAIL("internal: private area too small");
+    if (set_smem(k_bilateral_patch, smem) != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
+    k_bilateral_patch<<<mv.num_patches, BIL_BT, smem, stream>>>(mv, x, xo, csr_off, csr_val, bm_words, flags);
     ++g_launches;
     return cudaGetLastError();
 }

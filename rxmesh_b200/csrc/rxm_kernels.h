@@ -14,6 +14,7 @@ struct KernelLimits
     uint32_t max_stash;
     uint32_t max_face_adjacent_faces;
     uint32_t max_fan_total;
+    uint32_t max_ext, max_r2, max_r2_total;  // ring-2 extension (patch_layout.h)
 };
 
 // Every launcher returns cudaSuccess or the launch error; `err` (may be null)
@@ -58,6 +59,11 @@ cudaError_t launch_query_csr(int op, const MeshView& mv, const KernelLimits& lim
 
 cudaError_t launch_bilateral_step(const uint32_t* csr_off, const uint32_t* csr_val, uint32_t num_slots, const float* x_aos,
                                   const float* normals_aos, float* x_out_aos, uint32_t* overflow_flag, cudaStream_t stream);
+
+// bilateral filtering, one block per patch, normals fused (the default): flags[0] = a neighbourhood exceeded 80 vertices,
+// flags[1] += vertices that took the cross-patch path (csr_off / csr_val = the VV CSR over slots)
+cudaError_t launch_bilateral_patch(const MeshView& mv, const KernelLimits& lim, const uint32_t* csr_off, const uint32_t* csr_val,
+                                   const float* x_aos, float* x_out_aos, uint32_t* flags, cudaStream_t stream, const char** err);
 
 cudaError_t launch_boundary_vertices(const MeshView& mv, const KernelLimits& lim, uint32_t* flag_per_slot,
                                      cudaStream_t stream, const char** err);

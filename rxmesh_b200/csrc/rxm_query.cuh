@@ -11,7 +11,8 @@
 // patch's attribute slice, into the same phase), and then builds the adjacency:
 //   EV, FV, FE : the stored rows themselves (fixed stride 2 / 3 / 3); only the
 //                OWNED prefix of the rows is loaded;
-//   VV, VE     : transpose of EV (VV stores the other endpoint directly);
+//   VV, VE     : the stored one-ring fans (fan_v / fan_e: plain read, oriented order) when the mesh has them, else the
+//                transpose of EV (VV stores the other endpoint directly);
 //   VF         : transpose of FV;   EF : transpose of FE;
 //   FF         : EF, then per owned face the faces across its three edges, in
 //                edge order (the reference's order on manifold input,
@@ -124,18 +125,25 @@ struct PatchQuery
     bool        ff2;     // FF on edge-manifold input, packed format: pair table instead of the EF CSR
     bool        ff3;     // FF read from the stored rows (patch_layout.h FLAG_FF): plain read + per-row count
     bool        ef3;     // EF read from the stored pairs of the owned edges (same flag): plain read + per-row count
-    bool        fanq;    // VV / VF read from the stored one-ring fans (FLAG_FANS): plain read, oriented order
+    bool        fanq;    // VV / VE / VF read from the stored one-ring fans (FLAG_FANS): plain read, oriented order
 
     // shared-memory bytes this op needs for a patch with the given maxima
     // (host side; the role of calc_shared_memory, rxmesh_static.inl:498-841)
     // stored_rows != 0: every patch answers FF / EF from its stored rows (plan(): ff3 / ef3) and owns at most that many
     // faces / edges; the launch then reserves the rows + counts instead of the transposes' scratch (FF: 5 -> 8 resident
     // blocks per SM)
+    // VV / VE / VF with fan_entries != 0 (every patch stores fans): fan offsets of at most stored_rows owned vertices + that
+    // many fan entries (+ the list ends of VF) instead of the transposes' scratch
     __host__ static uint32_t smem_bytes(const uint32_t max_n[3], const uint32_t max_not_owned[3],
-                                        uint32_t max_stash, bool with_owner, uint32_t stored_rows = 0)
+                                        uint32_t max_stash, bool with_owner, uint32_t stored_rows = 0, uint32_t fan_entries = 0)
     {
         auto           r16 = [](uint32_t x) { return (x + 15u) & ~15u; };
         uint32_t       b   = 0;
+        if ((OP == OP_VV || OP == OP_VE || OP == OP_VF) && fan_entries) {
+            b = r16(2 * (stored_rows + 1) + 16) + r16(2 * fan_entries + 16) + (OP == OP_VF ? r16(2 * (stored_rows + 1)) : 0u);
+            if (with_owner) b += r16(4 * max_not_owned[Tr::dst]) + 16 * max_stash;
+            return b;
+        }
         if ((OP == OP_FF || OP == OP_EF) && stored_rows) {
             b = r16((OP == OP_FF ? 6 : 4) * stored_rows) + r16(2 * stored_rows);
             if (with_owner) b += r16(4 * max_not_owned[Tr::dst]) + 16 * max_stash;
@@ -159,12 +167,13 @@ struct PatchQuery
                                          bool edge_manifold = false)
     {
         ef3  = false;
-        fanq = (OP == OP_VV || OP == OP_VF) && edge_manifold && (d.flags & FLAG_FANS) && !all_sources;
+        fanq = (OP == OP_VV || OP == OP_VE || OP == OP_VF) && edge_manifold && (d.flags & FLAG_FANS) && !all_sources;
         if (fanq) {
             // sections: fan_off (u16 offsets, bit 15 = closed fan) and fan_v; `edge_manifold` doubles as "stored sections
             // may be used" (k_query_csr passes false: it needs the ascending-id order of the transposes)
             n_rows = 0, n_cols = d.n_owned[ELEM_V];
-            loff_bytes = d.fanoff_bytes(), conn_bytes = OP == OP_VV ? d.fanv_bytes() : d.fanf_bytes();
+            // fan_v, fan_e and fan_f are parallel arrays of fan_total entries (same byte size)
+            loff_bytes = d.fanoff_bytes(), conn_bytes = d.fanv_bytes();
             s_loff     = sm.alloc<uint16_t>(loff_bytes / 2);
             s_conn     = sm.alloc<uint16_t>(conn_bytes / 2);
             s_off = nullptr, s_val = nullptr, s_off2 = nullptr, s_val2 = nullptr, s_own = nullptr, s_stash = nullptr;
@@ -239,8 +248,9 @@ struct PatchQuery
     // thread 0 only, after mbar_arrive_expect_tx
     __device__ __forceinline__ void issue(const PatchDesc& d, const uint8_t* blob, uint64_t* bar, bool with_owner) const
     {
-        if ((OP == OP_VV || OP == OP_VF) && fanq) {
-            if (conn_bytes) bulk_g2s(s_conn, blob + (OP == OP_VV ? d.off_fanv() : d.off_fanf()), conn_bytes, bar);
+        if ((OP == OP_VV || OP == OP_VE || OP == OP_VF) && fanq) {
+            if (conn_bytes)
+                bulk_g2s(s_conn, blob + (OP == OP_VV ? d.off_fanv() : (OP == OP_VE ? d.off_fane() : d.off_fanf())), conn_bytes, bar);
             bulk_g2s(s_loff, blob + d.off_fanoff(), loff_bytes, bar);
             if (with_owner) {
                 if (d.own_bytes(Tr::dst)) bulk_g2s(s_own, blob + d.off_own(Tr::dst), d.own_bytes(Tr::dst), bar);
@@ -284,7 +294,7 @@ struct PatchQuery
         r.n_src = lim, r.shift = 0, r.stride = 0, r.mask = 0xFFFFu;
         r.off16 = nullptr, r.off32 = nullptr, r.cnt = nullptr, r.end16 = nullptr;
         const uint16_t* c = s_conn;
-        if (OP == OP_VV && fanq) {
+        if ((OP == OP_VV || OP == OP_VE) && fanq) {
             for (uint32_t i = threadIdx.x; i <= lim; i += BT)
                 s_loff[i] &= FAN_OFF_MASK;  // drop the closed-fan flag: plain list bounds
             __syncthreads();

@@ -87,12 +87,19 @@ class Attribute:
         self._h = h
         self._keep = mesh  # the mesh must outlive its attributes
 
-    def release(self):
-        if getattr(self, "_h", None):
+    def release(self, location=None):
+        """release() frees the attribute; release(HOST | DEVICE) only that side (attribute.cu:375-390)."""
+        if not getattr(self, "_h", None):
+            return
+        if location is None or (int(location) & 0x03) == 0x03:
             lib().rxm_attr_destroy(self._h)
             self._h = None
+        else:
+            check(lib().rxm_attr_release(self._h, int(location)))
+            self.location &= ~int(location)
 
-    __del__ = release
+    def __del__(self):
+        self.release()
 
     def get_num_attributes(self):
         return self.num_attributes
@@ -179,7 +186,7 @@ class RXMeshStatic:
     """
 
     def __init__(self, faces_or_path, face_patch=None, patch_size=512, num_threads=0, device=True,
-                 verts=None, patcher_file=None):
+                 verts=None, patcher_file=None, ring2=None):
         if isinstance(faces_or_path, str):
             verts, faces = meshio.import_obj(faces_or_path)
         else:
@@ -197,9 +204,12 @@ class RXMeshStatic:
             if fp.shape[0] != self._fv.shape[0]:
                 raise RXMeshError("face_patch must have one entry per face")
         h = C.c_void_p()
-        check(lib().rxm_mesh_create(self._fv.ctypes.data_as(C.c_void_p), self._fv.shape[0],
-                                    None if fp is None else fp.ctypes.data_as(C.c_void_p),
-                                    int(patch_size), int(num_threads), C.byref(h)))
+        # ring2=False: leave out the ring-2 extension (RXM_BUILD_NO_RING2) -- meshes that never run a k-ring consumer
+        import os
+        flags = 1 if (ring2 is False or (ring2 is None and os.environ.get("RXM_NO_RING2"))) else 0
+        check(lib().rxm_mesh_create_ex(self._fv.ctypes.data_as(C.c_void_p), self._fv.shape[0],
+                                       None if fp is None else fp.ctypes.data_as(C.c_void_p),
+                                       int(patch_size), int(num_threads), flags, C.byref(h)))
         self._h = h
         self._attrs = {}
         if device:
@@ -279,6 +289,10 @@ class RXMeshStatic:
         """True when the patch store uses the rank-annotated (atomic-free) format."""
         return bool(self._info(22))
 
+    def has_ring2(self):
+        """True when the patches store the ring-2 extension (complete rings of the ribbon vertices next to owned ones)."""
+        return bool(self._info(24))
+
     def has_fans(self):
         """True when the patches store the oriented one-ring fans of their owned vertices."""
         return bool(self._info(23))
@@ -310,9 +324,13 @@ class RXMeshStatic:
         return self._arr(lib().rxm_mesh_lin_base, elem, self.get_num_patches() + 1)
 
     def edges(self):
+        if not lib().rxm_mesh_edges(self._h):
+            raise RXMeshError("the global edge arrays were released (rxm_mesh_compact)")
         return self._arr(lib().rxm_mesh_edges, None, 2 * self.get_num_edges()).reshape(-1, 2)
 
     def face_edges(self):
+        if not lib().rxm_mesh_face_edges(self._h):
+            raise RXMeshError("the global edge arrays were released (rxm_mesh_compact)")
         return self._arr(lib().rxm_mesh_face_edges, None, 3 * self.get_num_faces()).reshape(-1, 3)
 
     def patch(self, p):
@@ -341,6 +359,11 @@ class RXMeshStatic:
                     fan_f=arr(v.fan_f, v.fan_total) if v.fan_off else None,
                     ff=arr(v.ff, 3 * no[2]).reshape(-1, 3) if v.ff else None,
                     ef=arr(v.ef, 2 * no[1]).reshape(-1, 2) if v.ef else None,
+                    fan_e=arr(v.fan_e, v.fan_total) if v.fan_e else None,
+                    r2_idx=arr(v.r2_idx, n[0] - no[0]) if v.r2_idx else None,
+                    r2_off=arr(v.r2_off, v.n_r2 + 1) if v.r2_idx else None,
+                    r2_val=arr(v.r2_val, v.r2_total) if v.r2_idx else None,
+                    ext_owner=arr(v.ext_owner, v.n_ext) if v.r2_idx else None,
                     owner=[arr(v.owner[t], n[t] - no[t]) for t in range(3)],
                     stash=arr(v.stash, 4 * v.n_stash).reshape(-1, 4),
                     ltog=[arr(v.ltog[t], n[t]) for t in range(3)])
@@ -440,6 +463,10 @@ class RXMeshStatic:
 
     def bilateral_filter(self, inp, out, iters=1, stream=None):
         check(lib().rxm_bilateral_filter(self._h, inp._h, out._h, int(iters), _stream_ptr(stream)))
+
+    def bilateral_deferred(self):
+        """vertex-iterations of the last bilateral_filter call that ran on the cross-patch path"""
+        return int(lib().rxm_bilateral_deferred(self._h))
 
     def query_csr(self, op, stream=None):
         """Materialised query in slot space, downloaded: (off[num_slots+1], val[nnz]) numpy arrays."""

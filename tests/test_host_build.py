@@ -148,6 +148,51 @@ def test_one_ring_fans(built):
                 assert set(F[lf[f]].tolist()) == {g, a, c}
             if not closed:
                 assert ff[-1] == 0xFFFF
+            # fan_e names the edge between the vertex and every fan vertex (VE in oriented order)
+            le, ev = pv["ltog"][1], pv["ev"]
+            for u, e_ in zip(fvv[b:e], pv["fan_e"][b:e]):
+                assert {int(x) for x in ev[e_]} == {v, int(u)}
+                assert {int(x) for x in T.ev[le[e_]]} == {g, int(lv[u])}
+
+
+def test_ring2_extension(built):
+    # ring-2 extension: every NOT-OWNED vertex adjacent to an owned one carries its complete one-ring, as ids of the
+    # patch's vertices or of "ext" vertices (two rings out) that resolve through their owner patch like ribbon vertices
+    name, V, F, m, T = built
+    assert m.has_ring2()
+    vv = O.csr_to_sets(T.query("VV"))
+    P = m.get_num_patches()
+    views = [m.patch(p) for p in range(P)]
+    for p, pv in enumerate(views):
+        nv, nov = pv["n"][0], pv["n_owned"][0]
+        lv = pv["ltog"][0]
+        adj = np.zeros(nv, bool)
+        for f in pv["fv"]:
+            if (f < nov).any():
+                adj[f[f >= nov]] = True
+        assert len(pv["r2_idx"]) == nv - nov
+        ext_g = []
+        for o in pv["ext_owner"]:
+            q = int(pv["stash"][o >> 16][0])
+            ext_g.append(int(views[q]["ltog"][0][o & 0xFFFF]))
+            assert (o & 0xFFFF) < views[q]["n_owned"][0]
+        assert not set(ext_g) & set(lv.tolist())  # ext vertices are NOT in the patch
+        for i in range(nv - nov):
+            r = int(pv["r2_idx"][i])
+            assert (r != 0xFFFF) == bool(adj[nov + i]), (name, p, i)
+            if r == 0xFFFF:
+                continue
+            ids = pv["r2_val"][pv["r2_off"][r]:pv["r2_off"][r + 1]]
+            ring = [int(lv[u]) if u < nv else ext_g[u - nv] for u in ids]
+            assert tuple(sorted(ring)) == vv[int(lv[nov + i])], (name, p, i)
+
+
+def test_ring2_can_be_left_out():
+    V, F = make_mesh("ico6")
+    m = rx.RXMeshStatic(F, device=False, patch_size=64, ring2=False)
+    assert not m.has_ring2() and m.patch(0)["r2_idx"] is None
+    m2 = rx.RXMeshStatic(F, device=False, patch_size=64)
+    assert m2.topo_bytes() > m.topo_bytes()
 
 
 def test_stored_ff_and_ef_rows(built):
