@@ -174,10 +174,11 @@ def config_bilateral(torch, rx, stream, nu=2236, iters=5):
     from rxmesh_b200 import meshio
     peak, _ = peaks()
     V, F = meshio.torus(nu, nu, noise=0.2)
-    fp = (np.arange(F.shape[0] // 2, dtype=np.uint32) // nu // 16 * ((nu + 31) // 32) +
-          np.arange(F.shape[0] // 2, dtype=np.uint32) % nu // 32).repeat(2)
+    tj, ti = (int(t) for t in os.environ.get("RXM_BIL_TILE", "32x16").split("x"))  # quads per patch: columns x rows
+    q = np.arange(F.shape[0] // 2, dtype=np.uint32)
+    fp = (q // nu // ti * ((nu + tj - 1) // tj) + q % nu // tj).repeat(2)
     t0 = time.perf_counter()
-    m = rx.RXMeshStatic(F, face_patch=fp, patch_size=1024, num_threads=os.cpu_count() or 8)
+    m = rx.RXMeshStatic(F, face_patch=fp, patch_size=2 * tj * ti, num_threads=os.cpu_count() or 8)
     tb = time.perf_counter() - t0
     x = rx.Attribute(m, 0, np.float32, 3, rx.DEVICE, rx.AoS)
     y = rx.Attribute(m, 0, np.float32, 3, rx.DEVICE, rx.AoS)
@@ -204,7 +205,8 @@ def config_bilateral(torch, rx, stream, nu=2236, iters=5):
         n_chk += int(sel.sum())
     tol = 2e-5 * scale
     return {"what": "bilateral filtering, %d-face torus (%d^2 quads), %d iterations (unit-face normals + filter)" % (nF, nu, iters),
-            "faces": nF, "patches": m.get_num_patches(), "build_seconds": tb, "ms_total": ms, "ms_per_iteration": ms / iters,
+            "faces": nF, "patches": m.get_num_patches(), "patch_tile_quads": "%dx%d" % (tj, ti), "build_seconds": tb, "ms_total": ms,
+            "ms_per_iteration": ms / iters,
             "vertex_iterations_per_s": nV * iters / (ms * 1e-3), "alg_bytes_per_iteration": 54.0 * nF,
             "achieved_gbs": gbs, "hbm_frac": gbs / peak, "peak_gbs": peak,
             "kernel": "k_bilateral_patch (one launch per iteration: unit-face normals + filter, patch-local)",

@@ -115,10 +115,11 @@ typedef struct {
     const uint16_t* ef;
     /* fan_e[i] = local edge between the fan's vertex and fan_v[i] (NULL without fans): VE in oriented order */
     const uint16_t* fan_e;
-    /* ring-2 extension (NULL / 0 when built with RXM_BUILD_NO_RING2): the complete one-ring of every NOT-OWNED vertex that is
-     * adjacent to an owned one, as extended local ids: < n[V] = a vertex of the patch, n[V] + k = ext vertex k (two rings
-     * out, not held by the patch), whose owner record is ext_owner[k] (same encoding as owner[]).
-     * r2_idx[n[V] - n_owned[V]] = ring index or 0xFFFF; ring r = r2_val[r2_off[r] .. r2_off[r + 1]) */
+    /* ring extension (NULL / 0 when built with RXM_BUILD_NO_RING2): the complete one-ring of every NOT-OWNED vertex within
+     * two rings of an owned one, as extended local ids: < n[V] = a vertex of the patch, n[V] + k = ext vertex k (not held by
+     * the patch), whose owner record is ext_owner[k] (same encoding as owner[]).
+     * r2_idx[n[V] - n_owned[V] + n_ext] (index = extended id - n_owned[V]) = ring index or 0xFFFF;
+     * ring r = r2_val[r2_off[r] .. r2_off[r + 1]) */
     const uint16_t* r2_idx;
     const uint16_t* r2_off;
     const uint16_t* r2_val;

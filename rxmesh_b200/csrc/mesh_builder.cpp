@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <iterator>
 #include <numeric>
 
 namespace rxm {
@@ -700,7 +701,9 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
                 T.l[t]       = scratch;
             }
             if (ring2) {
-                // ---- ring-2 extension: the COMPLETE one-ring of every not-owned vertex adjacent to an owned vertex ----
+                // ---- ring extension: the COMPLETE one-ring of every not-owned vertex within `ring_depth` rings of an owned
+                //      vertex.  Level-by-level over the global vertex -> faces map; vertices of those rings that the patch
+                //      does not hold become "ext" vertices (extended local id n[V] + k, resolved through their owner) ----
                 const auto&    LV  = T.l[ELEM_V];
                 const uint32_t nov = T.n_owned[ELEM_V], nvp = (uint32_t)LV.size();
                 auto lv = [&](uint32_t g) -> uint32_t {  // global vertex -> local id, INVALID32_ if not in the patch
@@ -709,49 +712,64 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
                     auto it = std::lower_bound(b, e, g);
                     return (it != e && *it == g) ? (uint32_t)(it - LV.begin()) : INVALID32_;
                 };
-                std::vector<uint8_t> adj(nvp - nov, 0);
-                for (uint32_t f : T.l[ELEM_F]) {
-                    const uint32_t g[3] = {fv[3ull * f], fv[3ull * f + 1], fv[3ull * f + 2]};
-                    if (vpatch[g[0]] != (uint32_t)p && vpatch[g[1]] != (uint32_t)p && vpatch[g[2]] != (uint32_t)p) continue;
-                    for (int j = 0; j < 3; ++j)
-                        if (vpatch[g[j]] != (uint32_t)p) adj[lv(g[j]) - nov] = 1;
-                }
-                std::vector<uint32_t> ring_g, ring_off(1, 0);  // rings as global ids
-                T.r2_idx.assign(nvp - nov, 0xFFFFu);
-                uint32_t nr = 0;
-                T.ext.clear();
-                for (uint32_t i = 0; i < nvp - nov; ++i) {
-                    if (!adj[i]) continue;
-                    const uint32_t w = LV[nov + i];
-                    scratch.clear();
+                auto ring_of = [&](uint32_t w, std::vector<uint32_t>& out) {  // sorted unique global ids of w's one-ring
+                    out.clear();
                     for (uint32_t k = vf_off[w]; k < vf_off[w + 1]; ++k)
                         for (int j = 0; j < 3; ++j) {
                             const uint32_t g = fv[3ull * vf_val[k] + j];
-                            if (g != w) scratch.push_back(g);
+                            if (g != w) out.push_back(g);
                         }
-                    std::sort(scratch.begin(), scratch.end());
-                    scratch.erase(std::unique(scratch.begin(), scratch.end()), scratch.end());
-                    for (uint32_t g : scratch) {
+                    std::sort(out.begin(), out.end());
+                    out.erase(std::unique(out.begin(), out.end()), out.end());
+                };
+                std::vector<uint32_t> ringed, frontier(LV.begin(), LV.begin() + nov), next_f, ring;  // global ids
+                for (uint32_t depth = 0; depth < opt.ring_depth; ++depth) {
+                    next_f.clear();
+                    for (uint32_t g : frontier) {
+                        ring_of(g, ring);
+                        for (uint32_t u : ring)
+                            if (vpatch[u] != (uint32_t)p) next_f.push_back(u);
+                    }
+                    std::sort(next_f.begin(), next_f.end());
+                    next_f.erase(std::unique(next_f.begin(), next_f.end()), next_f.end());
+                    // new = next_f \ ringed (both sorted)
+                    std::vector<uint32_t> fresh;
+                    std::set_difference(next_f.begin(), next_f.end(), ringed.begin(), ringed.end(), std::back_inserter(fresh));
+                    std::vector<uint32_t> merged(ringed.size() + fresh.size());
+                    std::merge(ringed.begin(), ringed.end(), fresh.begin(), fresh.end(), merged.begin());
+                    ringed.swap(merged);
+                    frontier.swap(fresh);
+                }
+                // rings of the ringed vertices; members the patch does not hold are ext vertices (ringed ext vertices too)
+                std::vector<uint32_t> ring_g, ring_off(1, 0);
+                T.ext.clear();
+                for (uint32_t w : ringed) {
+                    if (lv(w) == INVALID32_) T.ext.push_back(w);
+                    ring_of(w, ring);
+                    for (uint32_t g : ring) {
                         ring_g.push_back(g);
                         if (lv(g) == INVALID32_) T.ext.push_back(g);
                     }
                     ring_off.push_back((uint32_t)ring_g.size());
-                    T.r2_idx[i] = (uint16_t)nr++;
                 }
                 std::sort(T.ext.begin(), T.ext.end());
                 T.ext.erase(std::unique(T.ext.begin(), T.ext.end()), T.ext.end());
-                if (nvp + T.ext.size() > 65535u || ring_g.size() > 65535u) {
+                auto xid = [&](uint32_t g) -> uint32_t {  // extended local id
+                    const uint32_t l = lv(g);
+                    return l != INVALID32_ ? l : nvp + (uint32_t)(std::lower_bound(T.ext.begin(), T.ext.end(), g) - T.ext.begin());
+                };
+                if (nvp + T.ext.size() > 65535u || ring_g.size() > 65535u || ringed.size() >= 0xFFFFu) {
 #pragma omp critical
-                    err = "build_mesh: patch " + std::to_string(p) + " exceeds 65535 entries in its ring-2 extension; use a smaller patch_size";
+                    err = "build_mesh: patch " + std::to_string(p) + " exceeds 65535 entries in its ring extension; use a smaller patch_size";
                     T.ext.clear(), T.r2_idx.clear();
                 } else {
+                    T.r2_idx.assign(nvp - nov + T.ext.size(), 0xFFFFu);
+                    for (size_t r = 0; r < ringed.size(); ++r)
+                        T.r2_idx[xid(ringed[r]) - nov] = (uint16_t)r;
                     T.r2_off.assign(ring_off.begin(), ring_off.end());
                     T.r2_val.resize(ring_g.size());
-                    for (size_t i = 0; i < ring_g.size(); ++i) {
-                        const uint32_t l = lv(ring_g[i]);
-                        T.r2_val[i] = (uint16_t)(l != INVALID32_ ? l
-                                                                 : nvp + (uint32_t)(std::lower_bound(T.ext.begin(), T.ext.end(), ring_g[i]) - T.ext.begin()));
-                    }
+                    for (size_t i = 0; i < ring_g.size(); ++i)
+                        T.r2_val[i] = (uint16_t)xid(ring_g[i]);
                 }
             }
             // neighbour patches referenced by not-owned elements (and by the ext vertices)

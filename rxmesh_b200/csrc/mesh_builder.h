@@ -91,6 +91,7 @@ struct BuildOptions
     uint32_t lloyd_iters  = 5;
     bool     force_wide   = false;  // never use the packed format (tests of the atomic path)
     bool     no_fans      = false;  // never store one-ring fans (tests of the generic kernels)
+    uint32_t ring_depth   = 2;      // rings around the owned vertices whose vertices carry their complete one-ring
     bool     no_ring2     = false;  // skip the ring-2 extension (meshes that never run a k-ring consumer: saves build time
                                     // and ~3 bytes per face of patch store)
 };

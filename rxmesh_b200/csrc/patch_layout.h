@@ -143,11 +143,12 @@ struct alignas(16) PatchDesc
     uint32_t pad1[2];
     // ---- sections appended in round 2 (after EF, so every older offset keeps its meaning) ----
     uint32_t o_fane;        // fan edges: fan_e[i] = local edge between the fan's vertex and fan_v[i] (VE as a plain read, oriented VE)
-    // RING-2 EXTENSION (FLAG_RING2): a k-ring walk that starts at an owned vertex may have to expand a RIBBON vertex, whose
-    // one-ring is only partly inside the patch.  For every not-owned vertex that is adjacent to an owned one the builder
-    // stores the COMPLETE ring as ids in an extended local space: [0, n[V]) = the patch's vertices, n[V] + k = the k-th
-    // "ext" vertex (a vertex two rings out that the patch does not hold), resolved through ext_own like a ribbon vertex.
-    uint32_t o_r2idx;       // u16[n[V] - n_owned[V]]: ring index of the not-owned vertex, 0xFFFF = ring not stored
+    // RING EXTENSION (FLAG_RING2): a k-ring walk that starts at an owned vertex may have to expand a vertex whose one-ring
+    // is only partly inside the patch (a ribbon vertex) or that the patch does not hold at all.  For every NOT-OWNED vertex
+    // within ring_depth (default 2) rings of an owned one the builder stores the COMPLETE ring as ids in an extended local
+    // space: [0, n[V]) = the patch's vertices, n[V] + k = the k-th "ext" vertex (beyond the ribbon), resolved through
+    // ext_own like a ribbon vertex.
+    uint32_t o_r2idx;       // u16[n[V] - n_owned[V] + n_ext]: ring index of the not-owned / ext vertex, 0xFFFF = ring not stored
     uint32_t o_r2off;       // u16[n_r2 + 1]
     uint32_t o_r2val;       // u16[r2_total] extended local ids
     uint32_t o_ext;         // u32[n_ext] owner records (stash slot << 16 | local id in owner)
@@ -222,7 +223,7 @@ struct alignas(16) PatchDesc
         o += (flags & FLAG_FANS) ? round_up(2u * fan_total, 16) : 0u;
         const bool r2 = (flags & FLAG_RING2) != 0;
         o_r2idx = o;
-        o += r2 ? round_up(2u * (uint32_t)(n[ELEM_V] - n_owned[ELEM_V]), 16) : 0u;
+        o += r2 ? round_up(2u * ((uint32_t)(n[ELEM_V] - n_owned[ELEM_V]) + n_ext), 16) : 0u;
         o_r2off = o;
         o += r2 ? round_up(2u * (n_r2 + 1u), 16) : 0u;
         o_r2val = o;

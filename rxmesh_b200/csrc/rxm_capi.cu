@@ -1067,15 +1067,16 @@ int rxm_bilateral_filter(rxm_mesh* m, rxm_attr* in, rxm_attr* out, uint32_t iter
     const bool patch_local = m->view.fans && !getenv("RXM_BILATERAL_CSR");
     if (!patch_local && (rc = get_scratch(m, 3, &nrm))) return rc;
     if (iters > 1 && (rc = get_scratch(m, 0, &tmp))) return rc;
-    if (!m->d_flag) CU(cudaMalloc(&m->d_flag, 8));
-    CU(cudaMemsetAsync(m->d_flag, 0, 8, (cudaStream_t)stream));
+    if (!m->d_flag) CU(cudaMalloc(&m->d_flag, 16));
+    CU(cudaMemsetAsync(m->d_flag, 0, 16, (cudaStream_t)stream));
+    if (patch_local && (rc = ensure_stage(m, 20ull * m->h.num_slots[ELEM_V] + 16, 31))) return rc;  // deferred work list
     rxm_attr* src = in;
     for (uint32_t k = 1; k <= iters; ++k) {
         rxm_attr* dst = ((iters - k) % 2 == 0) ? out : tmp;
         if (patch_local) {
             const char* why = nullptr;
             cudaError_t e   = launch_bilateral_patch(m->view, m->lim, off, val, (const float*)src->d, (float*)dst->d, m->d_flag,
-                                                     (cudaStream_t)stream, &why);
+                                                     m->d_stage[31], k - 1, (cudaStream_t)stream, &why);
             if ((rc = kernel_status(e, why, "rxm_bilateral_filter"))) return rc;
         } else {
             // filtering_rxmesh.cuh:75-95: vertex normals of the current positions, then the filter

@@ -1260,8 +1260,8 @@ __global__ void __launch_bounds__(128) k_bilateral(const uint32_t* __restrict__ 
 // Membership (dist^2 <= 4 sigma_c^2) is evaluated as fmaf(dz, dz, fmaf(dy, dy, dx * dx)) on fp32 differences in BOTH paths
 // and in the oracle's fp32-membership mode, so the neighbourhoods are the same sets everywhere.
 // --------------------------------------------------------------------------
-constexpr int BIL_BT       = 128;
-constexpr int BIL_FAST_CAP = 32;  // accepted neighbours the fast path keeps per vertex before it defers
+constexpr int BIL_BT       = 128;  // block size of the cross-patch pass
+constexpr int BIL_FAST_CAP = 16;   // accepted neighbours the fast path keeps per vertex before it defers
 
 __device__ __forceinline__ float dist2f(float dx, float dy, float dz)
 {
@@ -1271,8 +1271,8 @@ __device__ __forceinline__ float dist2f(float dx, float dy, float dz)
 struct BilPatch
 {
     const uint16_t *fo, *fv, *r2idx, *r2off, *r2val;
-    const float*    x;  // AoS xyz of every extended local vertex
-    uint32_t        nv, nov, next;
+    const float4*   x;  // xyz of every extended local vertex, one LDS.128 each
+    uint32_t        nx_, nov;  // nx_ = extended local vertices (patch + ext)
 };
 
 // pass over the vertex's own fan: unit vertex normal (normalised sum of unit face normals) and sigma_c^2 = min ring dist^2
@@ -1281,9 +1281,9 @@ __device__ __forceinline__ void bil_normal_sigma(const BilPatch& B, uint32_t v, 
 {
     const uint32_t o = B.fo[v], b = o & FAN_OFF_MASK, e = B.fo[v + 1] & FAN_OFF_MASK;
     nx = ny = nz = 0.f;
-    const float* q   = B.x + 3u * B.fv[b];
-    const float  d0x = q[0] - px, d0y = q[1] - py, d0z = q[2] - pz;
-    sc2              = dist2f(d0x, d0y, d0z);
+    float4      q   = B.x[B.fv[b]];
+    const float d0x = q.x - px, d0y = q.y - py, d0z = q.z - pz;
+    sc2             = dist2f(d0x, d0y, d0z);
     float ax = d0x, ay = d0y, az = d0z;
     auto  face = [&](float cx, float cy, float cz) {
         const float fx = ay * cz - az * cy, fy = az * cx - ax * cz, fz = ax * cy - ay * cx;
@@ -1291,145 +1291,161 @@ __device__ __forceinline__ void bil_normal_sigma(const BilPatch& B, uint32_t v, 
         nx += fx * w, ny += fy * w, nz += fz * w;
     };
     for (uint32_t i = b + 1; i < e; ++i) {
-        q              = B.x + 3u * B.fv[i];
-        const float cx = q[0] - px, cy = q[1] - py, cz = q[2] - pz;
+        q              = B.x[B.fv[i]];
+        const float cx = q.x - px, cy = q.y - py, cz = q.z - pz;
         sc2            = fminf(sc2, dist2f(cx, cy, cz));
         face(cx, cy, cz);
         ax = cx, ay = cy, az = cz;
     }
     if (o & FAN_CLOSED) face(d0x, d0y, d0z);
-    const float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
+    const float inv = rsqrtf(nx * nx + ny * ny + nz * nz);
     nx *= inv, ny *= inv, nz *= inv;
 }
 
-// fast path of one owned vertex; false = the walk left what the patch can answer (caller defers the vertex)
-template <int BT>
+// fast path of one owned vertex; false = the walk left what the patch can answer (caller defers the vertex).
+// ONE flattened loop over "visits" (the vertex's own ring, then the ring of every accepted vertex in turn): the lanes of a
+// warp stay together until their TOTAL number of visits is used up, instead of diverging on every ring's length.
+template <uint32_t BT>
 __device__ __forceinline__ bool bil_fast(const BilPatch& B, uint32_t v, uint32_t* bm, uint32_t bm_words, uint16_t* lst, float* out)
 {
     const uint32_t tid = threadIdx.x;
-    const float    px = B.x[3 * v], py = B.x[3 * v + 1], pz = B.x[3 * v + 2];
+    const float4   P   = B.x[v];
+    const float    px = P.x, py = P.y, pz = P.z;
     float          nx, ny, nz, sc2;
     bil_normal_sigma(B, v, px, py, pz, nx, ny, nz, sc2);
     const float radius = 4.0f * sc2;
     for (uint32_t w = 0; w < bm_words; ++w)
         bm[w * BT + tid] = 0u;
-    auto seen_or_mark = [&](uint32_t u) -> bool {  // true if u was seen before; marks it either way
+    bm[(v >> 5) * BT + tid] = 1u << (v & 31u);
+    uint32_t        na = 0, head = 0;
+    float           sum = 0.f, sum_sq = 0.f;
+    const uint16_t* ring = B.fv;
+    uint32_t        i = B.fo[v] & FAN_OFF_MASK, re = B.fo[v + 1] & FAN_OFF_MASK;
+    while (true) {
+        if (i == re) {  // next ring: the next accepted vertex
+            if (head == na) break;
+            const uint32_t w = lst[head * BT + tid];
+            ++head;
+            if (w < B.nov) {
+                ring = B.fv, i = B.fo[w] & FAN_OFF_MASK, re = B.fo[w + 1] & FAN_OFF_MASK;
+            } else {
+                const uint32_t r = B.r2idx[w - B.nov];
+                if (r == 0xFFFFu) return false;  // its ring is not in this patch
+                ring = B.r2val, i = B.r2off[r], re = B.r2off[r + 1];
+            }
+            continue;
+        }
+        const uint32_t u    = ring[i++];
         uint32_t&      word = bm[(u >> 5) * BT + tid];
         const uint32_t bit = 1u << (u & 31u), old = word;
-        word = old | bit;
-        return (old & bit) != 0u;
-    };
-    seen_or_mark(v);
-    uint32_t na  = 0;
-    float    sum = 0.f, sum_sq = 0.f;
-    bool     ok  = true;
-    auto visit = [&](uint32_t u) {
-        if (seen_or_mark(u)) return;
-        const float* q  = B.x + 3u * u;
-        const float  cx = q[0] - px, cy = q[1] - py, cz = q[2] - pz;
-        if (dist2f(cx, cy, cz) > radius) return;
-        if (na == (uint32_t)BIL_FAST_CAP) {
-            ok = false;
-            return;
-        }
+        if (old & bit) continue;  // seen before (accepted or rejected)
+        word             = old | bit;
+        const float4 q   = B.x[u];
+        const float  cx = q.x - px, cy = q.y - py, cz = q.z - pz;
+        if (dist2f(cx, cy, cz) > radius) continue;
+        if (na == (uint32_t)BIL_FAST_CAP) return false;
         lst[na * BT + tid] = (uint16_t)u;
         ++na;
         const float h = fabsf(cx * nx + cy * ny + cz * nz);
         sum += h, sum_sq += h * h;
-    };
-    {
-        const uint32_t b = B.fo[v] & FAN_OFF_MASK, e = B.fo[v + 1] & FAN_OFF_MASK;
-        for (uint32_t i = b; i < e; ++i)
-            visit(B.fv[i]);
     }
-    for (uint32_t head = 0; ok && head < na; ++head) {
-        const uint32_t  w = lst[head * BT + tid];
-        const uint16_t* ring;
-        uint32_t        rb, re;
-        if (w < B.nov) {
-            ring = B.fv, rb = B.fo[w] & FAN_OFF_MASK, re = B.fo[w + 1] & FAN_OFF_MASK;
-        } else {
-            const uint32_t r = w < B.nv ? (uint32_t)B.r2idx[w - B.nov] : 0xFFFFu;
-            if (r == 0xFFFFu) return false;  // ring not in this patch
-            ring = B.r2val, rb = B.r2off[r], re = B.r2off[r + 1];
-        }
-        for (uint32_t i = rb; i < re; ++i)
-            visit(ring[i]);
-    }
-    if (!ok) return false;
-    const float c   = (float)(na + 1u);  // the vertex itself is the first member of its neighbourhood (h = 0, t = 0)
-    float       ss2 = sum_sq / c - (sum * sum) / (c * c);
+    const float rc  = fast_rcp((float)(na + 1u));  // the vertex itself is the first member of its neighbourhood (h = 0, t = 0)
+    const float m1  = sum * rc;
+    float       ss2 = sum_sq * rc - m1 * m1;
     if (ss2 < 1.0e-20f) ss2 += 1.0e-20f;
-    const float ic = -0.5f / sc2, is = -0.5f / ss2;
+    const float ic = -0.5f * fast_rcp(sc2), is = -0.5f * fast_rcp(ss2);
     float       num = 0.f, den = 1.f;
     for (uint32_t k = 0; k < na; ++k) {
-        const float* q  = B.x + 3u * lst[k * BT + tid];
-        const float  cx = q[0] - px, cy = q[1] - py, cz = q[2] - pz;
+        const float4 q  = B.x[lst[k * BT + tid]];
+        const float  cx = q.x - px, cy = q.y - py, cz = q.z - pz;
         const float  t2 = dist2f(cx, cy, cz), h = cx * nx + cy * ny + cz * nz;
         const float  w  = __expf(t2 * ic + h * h * is);
         num += w * h, den += w;
     }
-    const float kk = num / den;
+    const float kk = num * fast_rcp(den);
     out[0] = px + nx * kk, out[1] = py + ny * kk, out[2] = pz + nz * kk;
     return true;
 }
 
-// cross-patch path of one (deferred) owned vertex: slot space, VV CSR, accepted list of R-interleaved u32 slots in shared
-// memory, duplicate check by list scan, the reference's cap of 80 (filtering_rxmesh.cuh: maxVVSize)
-__device__ __forceinline__ void bil_slow(const BilPatch& B, uint32_t v, uint32_t slot_v, const uint32_t* __restrict__ off,
-                                         const uint32_t* __restrict__ val, const float* __restrict__ xg, uint32_t* lst, uint32_t R,
-                                         uint32_t j, uint32_t* __restrict__ overflow, float* out)
+// A vertex the patch could not finish: its slot, unit normal and sigma_c^2 (already computed from its fan)
+struct BilDeferred
 {
-    const float px = B.x[3 * v], py = B.x[3 * v + 1], pz = B.x[3 * v + 2];
-    float       nx, ny, nz, sc2;
-    bil_normal_sigma(B, v, px, py, pz, nx, ny, nz, sc2);
-    const float radius = 4.0f * sc2;
-    uint32_t    cnt    = 1;
-    lst[j]             = slot_v;
-    float sum = 0.f, sum_sq = 0.f;
-    for (uint32_t head = 0; head < cnt; ++head) {
-        const uint32_t w = lst[head * R + j];
-        for (uint32_t i = off[w]; i < off[w + 1]; ++i) {
-            const uint32_t u = val[i];
-            bool           dup = false;
-            for (uint32_t k = 0; k < cnt; ++k)
-                dup |= (lst[k * R + j] == u);
-            if (dup) continue;
-            const float cx = xg[3ull * u] - px, cy = xg[3ull * u + 1] - py, cz = xg[3ull * u + 2] - pz;
-            if (dist2f(cx, cy, cz) > radius) continue;
-            if (cnt < (uint32_t)BILATERAL_MAX_VV) {
-                lst[cnt * R + j] = u;
-                ++cnt;
-                const float h = fabsf(cx * nx + cy * ny + cz * nz);
-                sum += h, sum_sq += h * h;
-            } else
-                *overflow = 1u;  // the reference asserts here
+    uint32_t slot;
+    float    nx, ny, nz, sc2;
+};
+
+// cross-patch path: the DEFERRED vertices of all patches, compacted into one work list by k_bilateral_patch, one thread
+// each with every warp full (inside the patch kernel they were a handful of stragglers per block whose dependent global
+// loads -- CSR row, then coordinates -- nothing could hide).  Slot space, VV CSR, accepted list of interleaved u32 slots in
+// shared memory, duplicate check by list scan, the reference's cap of 80 (filtering_rxmesh.cuh: maxVVSize).
+__global__ void __launch_bounds__(BIL_BT) k_bilateral_deferred(const uint32_t* __restrict__ count, uint32_t* __restrict__ next_count,
+                                                               const BilDeferred* __restrict__ work,
+                                                               const uint32_t* __restrict__ off, const uint32_t* __restrict__ val,
+                                                               const float* __restrict__ xg, float* __restrict__ xo,
+                                                               uint32_t* __restrict__ flags)
+{
+    constexpr uint32_t R = BIL_BT;
+    __shared__ uint32_t lst_all[BILATERAL_MAX_VV * BIL_BT];
+    const uint32_t      n = *count, j = threadIdx.x;
+    if (blockIdx.x == 0 && j == 0) {
+        flags[1] += n;    // statistics: deferred vertices of the call
+        *next_count = 0;  // the counter the NEXT iteration's patch kernel fills (the two alternate)
+    }
+    uint32_t*           lst = lst_all;
+    for (uint32_t i = blockIdx.x * BIL_BT + j; i < n; i += gridDim.x * BIL_BT) {
+        const BilDeferred w  = work[i];
+        const float       px = xg[3ull * w.slot], py = xg[3ull * w.slot + 1], pz = xg[3ull * w.slot + 2];
+        const float       nx = w.nx, ny = w.ny, nz = w.nz, sc2 = w.sc2, radius = 4.0f * sc2;
+        uint32_t          cnt = 1;
+        lst[j]                = w.slot;
+        float sum = 0.f, sum_sq = 0.f;
+        for (uint32_t head = 0; head < cnt; ++head) {
+            const uint32_t c = lst[head * R + j], rb = off[c], re = off[c + 1];
+            for (uint32_t k = rb; k < re; ++k) {
+                const uint32_t u   = val[k];
+                bool           dup = false;
+                for (uint32_t q = 0; q < cnt; ++q)
+                    dup |= (lst[q * R + j] == u);
+                if (dup) continue;
+                const float cx = xg[3ull * u] - px, cy = xg[3ull * u + 1] - py, cz = xg[3ull * u + 2] - pz;
+                if (dist2f(cx, cy, cz) > radius) continue;
+                if (cnt < (uint32_t)BILATERAL_MAX_VV) {
+                    lst[cnt * R + j] = u;
+                    ++cnt;
+                    const float h = fabsf(cx * nx + cy * ny + cz * nz);
+                    sum += h, sum_sq += h * h;
+                } else
+                    flags[0] = 1u;  // the reference asserts here
+            }
         }
+        const float c   = (float)cnt;
+        float       ss2 = sum_sq / c - (sum * sum) / (c * c);
+        if (ss2 < 1.0e-20f) ss2 += 1.0e-20f;
+        const float ic = -0.5f / sc2, is = -0.5f / ss2;
+        float       num = 0.f, den = 1.f;
+        for (uint32_t q = 1; q < cnt; ++q) {
+            const uint32_t u  = lst[q * R + j];
+            const float    cx = xg[3ull * u] - px, cy = xg[3ull * u + 1] - py, cz = xg[3ull * u + 2] - pz;
+            const float    t2 = dist2f(cx, cy, cz), h = cx * nx + cy * ny + cz * nz;
+            const float    wgt = __expf(t2 * ic + h * h * is);
+            num += wgt * h, den += wgt;
+        }
+        const float kk = num / den;
+        xo[3ull * w.slot] = px + nx * kk, xo[3ull * w.slot + 1] = py + ny * kk, xo[3ull * w.slot + 2] = pz + nz * kk;
     }
-    const float c   = (float)cnt;
-    float       ss2 = sum_sq / c - (sum * sum) / (c * c);
-    if (ss2 < 1.0e-20f) ss2 += 1.0e-20f;
-    const float ic = -0.5f / sc2, is = -0.5f / ss2;
-    float       num = 0.f, den = 1.f;
-    for (uint32_t k = 1; k < cnt; ++k) {
-        const uint32_t u  = lst[k * R + j];
-        const float    cx = xg[3ull * u] - px, cy = xg[3ull * u + 1] - py, cz = xg[3ull * u + 2] - pz;
-        const float    t2 = dist2f(cx, cy, cz), h = cx * nx + cy * ny + cz * nz;
-        const float    w  = __expf(t2 * ic + h * h * is);
-        num += w * h, den += w;
-    }
-    const float kk = num / den;
-    out[0] = px + nx * kk, out[1] = py + ny * kk, out[2] = pz + nz * kk;
 }
 
-__global__ void __launch_bounds__(BIL_BT) k_bilateral_patch(MeshView mv, const float* __restrict__ x, float* __restrict__ xo,
-                                                            const uint32_t* __restrict__ csr_off, const uint32_t* __restrict__ csr_val,
-                                                            uint32_t bm_words, uint32_t* __restrict__ flags /* [0] overflow, [1] deferred */)
+// Block size = the patch's owned vertices split into equal rounds (chosen by the launcher): a fixed 512 left 14 of 16 warps
+// waiting at the barrier while 2 finished the tail of a 561-vertex patch (profiles/r02e: barrier stall 1.8 per issue).
+// (a compile-time block size: with blockDim.x as the stride of the interleaved bitmaps / lists the kernel was 25 % slower)
+template <uint32_t BT>
+__global__ void __launch_bounds__(BT) k_bilateral_patch(MeshView mv, const float* __restrict__ x, float* __restrict__ xo,
+                                                        uint32_t bm_words, uint32_t* __restrict__ work_count,
+                                                        BilDeferred* __restrict__ work)
 {
-    constexpr int BT = BIL_BT;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t                      bar;
-    __shared__ uint32_t                      s_ndef;
+    __shared__ uint32_t                      s_ndef, s_wbase;
     const PatchDesc d    = load_desc(mv.desc + blockIdx.x);
     const uint8_t*  blob = mv.topo + d.topo_off;
     const bool      r2   = (d.flags & FLAG_RING2) != 0;
@@ -1439,14 +1455,14 @@ __global__ void __launch_bounds__(BIL_BT) k_bilateral_patch(MeshView mv, const f
     uint16_t*       s_fv    = sm.alloc<uint16_t>(d.fanv_bytes() / 2);
     uint32_t*       s_own   = sm.alloc<uint32_t>(d.own_bytes(ELEM_V) / 4);
     StashEntry*     s_stash = sm.alloc<StashEntry>(d.n_stash);
-    uint16_t*       s_r2i   = sm.alloc<uint16_t>(r2 ? d.r2idx_bytes() / 2 : 8);
+    uint16_t*       s_r2i   = sm.alloc<uint16_t>(r2 ? d.r2idx_bytes() / 2 : nv - nov + 8u);
     uint16_t*       s_r2o   = sm.alloc<uint16_t>(r2 ? d.r2off_bytes() / 2 : 8);
     uint16_t*       s_r2v   = sm.alloc<uint16_t>(r2 ? d.r2val_bytes() / 2 : 8);
     uint32_t*       s_ext   = sm.alloc<uint32_t>(r2 ? d.ext_bytes() / 4 : 4);
-    float*          s_x     = sm.alloc<float>(3 * max(nv + next, cap));
-    float*          s_out   = sm.alloc<float>(3 * cap);
+    float4*         s_x     = sm.alloc<float4>(nv + next);
+    float*          s_out   = sm.alloc<float>(3 * cap);  // the owned slice as it arrives (AoS), later the results
     uint16_t*       s_def   = sm.alloc<uint16_t>(nov + 8u);
-    uint32_t*       s_priv  = sm.alloc<uint32_t>((bm_words + BIL_FAST_CAP / 2) * BT);  // bitmaps, then the u16 lists
+    uint32_t*       s_priv  = sm.alloc<uint32_t>((bm_words + BIL_FAST_CAP / 2) * BT);  // per-thread bitmaps, then the u16 lists
     if (threadIdx.x == 0) {
         s_ndef = 0;
         mbar_init(&bar, 1);
@@ -1463,20 +1479,30 @@ __global__ void __launch_bounds__(BIL_BT) k_bilateral_patch(MeshView mv, const f
             if (d.r2val_bytes()) bulk_g2s(s_r2v, blob + d.o_r2val, d.r2val_bytes(), &bar);
             if (d.ext_bytes()) bulk_g2s(s_ext, blob + d.o_ext, d.ext_bytes(), &bar);
         }
-        if (cap) bulk_g2s(s_x, x + 3ull * d.slot_base[ELEM_V], 12u * cap, &bar);
+        if (cap) bulk_g2s(s_out, x + 3ull * d.slot_base[ELEM_V], 12u * cap, &bar);
     }
     __syncthreads();
     mbar_wait(&bar, 0);
-    for (uint32_t i = nov + threadIdx.x; i < nv + next; i += BT) {  // ribbon and ext vertices: from their owners' slots
-        const uint32_t o = i < nv ? s_own[i - nov] : s_ext[i - nv];
-        const float*   g = x + 3ull * ((uint64_t)s_stash[o >> 16].slot_base[ELEM_V] + (o & 0xFFFFu));
-        const float    a = ldg_stream(g), b = ldg_stream(g + 1), c = ldg_stream(g + 2);
-        s_x[3 * i] = a, s_x[3 * i + 1] = b, s_x[3 * i + 2] = c;
+    // every extended local vertex as one float4: owned from the slice the TMA delivered, ribbon and ext vertices from
+    // their owners' slots
+    for (uint32_t i = threadIdx.x; i < nv + next; i += BT) {
+        float4 q;
+        if (i < nov) {
+            q = make_float4(s_out[3 * i], s_out[3 * i + 1], s_out[3 * i + 2], 0.f);
+        } else {
+            const uint32_t o = i < nv ? s_own[i - nov] : s_ext[i - nv];
+            const float*   g = x + 3ull * ((uint64_t)s_stash[o >> 16].slot_base[ELEM_V] + (o & 0xFFFFu));
+            q = make_float4(ldg_stream(g), ldg_stream(g + 1), ldg_stream(g + 2), 0.f);
+        }
+        s_x[i] = q;
     }
+    if (!r2)  // no ring extension: no not-owned vertex has a stored ring
+        for (uint32_t i = threadIdx.x; i < nv - nov; i += BT)
+            s_r2i[i] = 0xFFFFu;
     __syncthreads();
     BilPatch B;
     B.fo = s_fo, B.fv = s_fv, B.r2idx = s_r2i, B.r2off = s_r2o, B.r2val = s_r2v, B.x = s_x;
-    B.nv = r2 ? nv : nov, B.nov = nov, B.next = next;  // without ring-2 data any not-owned vertex defers (w >= B.nv)
+    B.nx_ = nv + next, B.nov = nov;
     uint32_t* bm  = s_priv;
     uint16_t* lst = reinterpret_cast<uint16_t*>(s_priv + bm_words * BT);
     for (uint32_t v = threadIdx.x; v < cap; v += BT) {
@@ -1484,7 +1510,7 @@ __global__ void __launch_bounds__(BIL_BT) k_bilateral_patch(MeshView mv, const f
         if (v < nov) {
             const uint32_t fb = s_fo[v] & FAN_OFF_MASK, fe = s_fo[v + 1] & FAN_OFF_MASK;
             if (fb == fe) {  // no neighbours: keeps its position
-                o[0] = s_x[3 * v], o[1] = s_x[3 * v + 1], o[2] = s_x[3 * v + 2];
+                o[0] = s_x[v].x, o[1] = s_x[v].y, o[2] = s_x[v].z;
             } else if (!bil_fast<BT>(B, v, bm, bm_words, lst, o)) {
                 s_def[atomicAdd(&s_ndef, 1u)] = (uint16_t)v;
             }
@@ -1494,16 +1520,17 @@ __global__ void __launch_bounds__(BIL_BT) k_bilateral_patch(MeshView mv, const f
     __syncthreads();
     const uint32_t ndef = s_ndef;
     if (ndef) {
-        // the private area as R interleaved lists of 80 slots; deferred vertices run R at a time on the first R threads
-        const uint32_t R = min((uint32_t)BT, ((bm_words + BIL_FAST_CAP / 2) * BT) / (uint32_t)BILATERAL_MAX_VV);
-        for (uint32_t base = 0; base < ndef; base += R) {
-            const uint32_t j = threadIdx.x;
-            if (j < R && base + j < ndef) {
-                const uint32_t v = s_def[base + j];
-                bil_slow(B, v, d.slot_base[ELEM_V] + v, csr_off, csr_val, x, s_priv, R, j, flags, s_out + 3 * v);
-            }
+        // the vertices this patch could not finish go to the global work list of k_bilateral_deferred (one reservation per
+        // block), with the normal and sigma_c^2 their fan gives; their rows of s_out are overwritten by that kernel
+        if (threadIdx.x == 0) s_wbase = atomicAdd(work_count, ndef);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < ndef; i += BT) {
+            const uint32_t v = s_def[i];
+            BilDeferred    w;
+            w.slot = d.slot_base[ELEM_V] + v;
+            bil_normal_sigma(B, v, s_x[v].x, s_x[v].y, s_x[v].z, w.nx, w.ny, w.nz, w.sc2);
+            work[s_wbase + i] = w;
         }
-        if (threadIdx.x == 0) atomicAdd(flags + 1, ndef);
     }
     fence_proxy_async();
     __syncthreads();
@@ -2144,18 +2171,46 @@ cudaError_t launch_bilateral_step(const uint32_t* csr_off, const uint32_t* csr_v
 }
 
 cudaError_t launch_bilateral_patch(const MeshView& mv, const KernelLimits& lim, const uint32_t* csr_off, const uint32_t* csr_val,
-                                   const float* x, float* xo, uint32_t* flags, cudaStream_t stream, const char** err)
+                                   const float* x, float* xo, uint32_t* flags, void* work, uint32_t iteration, cudaStream_t stream,
+                                   const char** err)
 {
     if (!mv.fans) RXM_FAIL("the patch-local bilateral kernel needs the one-ring fans");
     const uint32_t capv = lim.max_owned[ELEM_V] + 4, nvx = lim.max_n[ELEM_V] + lim.max_ext;
     const uint32_t bm_words = (nvx + 31u) / 32u;
-    const uint32_t smem = fan_smem(lim) + r16(2u * lim.max_not_owned[ELEM_V] + 16) + r16(2u * (lim.max_r2 + 1) + 16) +
-                          r16(2u * lim.max_r2_total + 16) + r16(4u * lim.max_ext + 16) + r16(12u * std::max(nvx, capv)) +
-                          r16(12u * capv) + r16(2u * (lim.max_owned[ELEM_V] + 8)) + r16(4u * (bm_words + BIL_FAST_CAP / 2) * BIL_BT) + 64u;
-    if ((bm_words + BIL_FAST_CAP / 2) * BIL_BT < (uint32_t)BILATERAL_MAX_VV) RXM_FAIL("internal: private area too small");
-    if (set_smem(k_bilateral_patch, smem) != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");
-    k_bilateral_patch<<<mv.num_patches, BIL_BT, smem, stream>>>(mv, x, xo, csr_off, csr_val, bm_words, flags);
-    ++g_launches;
+    const uint32_t fixed = fan_smem(lim) + r16(2u * (lim.max_not_owned[ELEM_V] + lim.max_ext) + 32) + r16(2u * (lim.max_r2 + 1) + 16) +
+                           r16(2u * lim.max_r2_total + 16) + r16(4u * lim.max_ext + 16) + 16u * nvx + r16(12u * capv) +
+                           r16(2u * (lim.max_owned[ELEM_V] + 8)) + 64u;
+    // block size: the compiled size that keeps most warps resident (per-thread bitmap + list storage grows with the block,
+    // the staged patch does not); measured on the 10 M-face torus (561 owned vertices per patch, profiles/r02_bilateral_bt.txt):
+    // 512 threads x 2 blocks = 32 warps 0.454 ms, 256 x 3 = 24 warps 0.470, 128 x 4 = 16 warps 0.553, 576 x 1 = 18 warps
+    // 0.705 -- resident warps decide, idle warps of a half-empty second round cost nothing; larger block on a tie
+    static const uint32_t sizes[] = {128, 192, 256, 288, 320, 384, 448, 512, 576};
+    uint32_t    bt = 0, smem = 0, best_warps = 0;
+    const char* force = getenv("RXM_BILATERAL_BT");  // experiment knob
+    for (uint32_t t : sizes) {
+        if (force && t != (uint32_t)atoi(force)) continue;
+        if (!force && t > 128u && t >= 2u * lim.max_owned[ELEM_V]) break;  // more than half the block would never have a vertex
+        const uint32_t sm = fixed + r16(4u * (bm_words + BIL_FAST_CAP / 2) * t);
+        if (sm > 227u * 1024u) continue;
+        const uint32_t blocks = std::min(227u * 1024u / (sm + 1024u), 2048u / t), warps = blocks * t / 32u;
+        if (warps >= best_warps) best_warps = warps, bt = t, smem = sm;
+    }
+    if (!bt) RXM_FAIL("patch needs more shared memory than 227 KB");
+    // flags: [0] overflow, [1] deferred vertices of the call, [2], [3] work-list fill of even / odd iterations
+    uint32_t* cnt = flags + 2 + (iteration & 1u);
+#define RXM_BIL(T)                                                                                                       \
+    case T:                                                                                                              \
+        if (set_smem(k_bilateral_patch<T>, smem) != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");  \
+        k_bilateral_patch<T><<<mv.num_patches, T, smem, stream>>>(mv, x, xo, bm_words, cnt, (BilDeferred*)work);          \
+        break;
+    switch (bt) {
+        RXM_BIL(128) RXM_BIL(192) RXM_BIL(256) RXM_BIL(288) RXM_BIL(320) RXM_BIL(384) RXM_BIL(448) RXM_BIL(512) RXM_BIL(576)
+        default: RXM_FAIL("internal: block size not compiled");
+    }
+#undef RXM_BIL
+    k_bilateral_deferred<<<148 * 8, BIL_BT, 0, stream>>>(cnt, flags + 2 + ((iteration + 1u) & 1u), (const BilDeferred*)work, csr_off,
+                                                          csr_val, x, xo, flags);
+    g_launches += 2;
     return cudaGetLastError();
 }
 

@@ -60,10 +60,13 @@ cudaError_t launch_query_csr(int op, const MeshView& mv, const KernelLimits& lim
 cudaError_t launch_bilateral_step(const uint32_t* csr_off, const uint32_t* csr_val, uint32_t num_slots, const float* x_aos,
                                   const float* normals_aos, float* x_out_aos, uint32_t* overflow_flag, cudaStream_t stream);
 
-// bilateral filtering, one block per patch, normals fused (the default): flags[0] = a neighbourhood exceeded 80 vertices,
-// flags[1] += vertices that took the cross-patch path (csr_off / csr_val = the VV CSR over slots)
+// bilateral filtering, one block per patch, normals fused (the default), followed by the compacted cross-patch pass over
+// the vertices the patches deferred.  flags: 3 x u32 -- [0] = a neighbourhood exceeded 80 vertices, [1] += deferred
+// vertices, [2] / [3] work-list fill of even / odd iterations (all zero before iteration 0); work: 20 bytes per vertex slot
+// (worst case: every vertex deferred); csr_* = the VV CSR over slots
 cudaError_t launch_bilateral_patch(const MeshView& mv, const KernelLimits& lim, const uint32_t* csr_off, const uint32_t* csr_val,
-                                   const float* x_aos, float* x_out_aos, uint32_t* flags, cudaStream_t stream, const char** err);
+                                   const float* x_aos, float* x_out_aos, uint32_t* flags, void* work, uint32_t iteration,
+                                   cudaStream_t stream, const char** err);
 
 cudaError_t launch_boundary_vertices(const MeshView& mv, const KernelLimits& lim, uint32_t* flag_per_slot,
                                      cudaStream_t stream, const char** err);

@@ -360,7 +360,7 @@ class RXMeshStatic:
                     ff=arr(v.ff, 3 * no[2]).reshape(-1, 3) if v.ff else None,
                     ef=arr(v.ef, 2 * no[1]).reshape(-1, 2) if v.ef else None,
                     fan_e=arr(v.fan_e, v.fan_total) if v.fan_e else None,
-                    r2_idx=arr(v.r2_idx, n[0] - no[0]) if v.r2_idx else None,
+                    r2_idx=arr(v.r2_idx, n[0] - no[0] + v.n_ext) if v.r2_idx else None,
                     r2_off=arr(v.r2_off, v.n_r2 + 1) if v.r2_idx else None,
                     r2_val=arr(v.r2_val, v.r2_total) if v.r2_idx else None,
                     ext_owner=arr(v.ext_owner, v.n_ext) if v.r2_idx else None,

@@ -156,8 +156,8 @@ def test_one_ring_fans(built):
 
 
 def test_ring2_extension(built):
-    # ring-2 extension: every NOT-OWNED vertex adjacent to an owned one carries its complete one-ring, as ids of the
-    # patch's vertices or of "ext" vertices (two rings out) that resolve through their owner patch like ribbon vertices
+    # ring extension: every NOT-OWNED vertex within two rings of an owned one carries its complete one-ring, as ids of the
+    # patch's vertices or of "ext" vertices (beyond the ribbon) that resolve through their owner patch like ribbon vertices
     name, V, F, m, T = built
     assert m.has_ring2()
     vv = O.csr_to_sets(T.query("VV"))
@@ -166,25 +166,27 @@ def test_ring2_extension(built):
     for p, pv in enumerate(views):
         nv, nov = pv["n"][0], pv["n_owned"][0]
         lv = pv["ltog"][0]
-        adj = np.zeros(nv, bool)
-        for f in pv["fv"]:
-            if (f < nov).any():
-                adj[f[f >= nov]] = True
-        assert len(pv["r2_idx"]) == nv - nov
         ext_g = []
         for o in pv["ext_owner"]:
             q = int(pv["stash"][o >> 16][0])
             ext_g.append(int(views[q]["ltog"][0][o & 0xFFFF]))
             assert (o & 0xFFFF) < views[q]["n_owned"][0]
         assert not set(ext_g) & set(lv.tolist())  # ext vertices are NOT in the patch
-        for i in range(nv - nov):
-            r = int(pv["r2_idx"][i])
-            assert (r != 0xFFFF) == bool(adj[nov + i]), (name, p, i)
+        gid = [int(x) for x in lv] + ext_g         # extended local id -> global id
+        owned = set(gid[:nov])
+        d1 = set().union(*[set(vv[g]) for g in owned]) - owned if owned else set()
+        d2 = (set().union(*[set(vv[g]) for g in d1]) - owned - d1) if d1 else set()
+        want = d1 | d2
+        assert len(pv["r2_idx"]) == nv - nov + len(ext_g)
+        got = set()
+        for i, r in enumerate(pv["r2_idx"]):
             if r == 0xFFFF:
                 continue
+            g = gid[nov + i]
+            got.add(g)
             ids = pv["r2_val"][pv["r2_off"][r]:pv["r2_off"][r + 1]]
-            ring = [int(lv[u]) if u < nv else ext_g[u - nv] for u in ids]
-            assert tuple(sorted(ring)) == vv[int(lv[nov + i])], (name, p, i)
+            assert tuple(sorted(gid[u] for u in ids)) == vv[g], (name, p, i)
+        assert got == want, (name, p)
 
 
 def test_ring2_can_be_left_out():
