@@ -282,14 +282,16 @@ def oriented_rings(fv, nv):
     return off, val
 
 
-def mcf_matvec(rings, X, vec_in, time_step):
-    """rxo_mcf_matvec (apps/MCF/mcf_kernels.cuh:117-205), float64."""
+def mcf_matvec(rings, X, vec_in, time_step, with_scale=False):
+    """rxo_mcf_matvec (apps/MCF/mcf_kernels.cuh:117-205), float64.  with_scale: also the per-vertex magnitude of the terms the
+    result is a difference of (|diag| |in_p| + sum |w_i| |in_i|), the scale a fp32 evaluation is accurate against."""
     off, val = rings
     X, vin = _f32(X).reshape(-1, 3), _f32(vec_in).reshape(-1, 3)
     out = np.empty(X.shape, dtype=np.float64)
-    lib().rxo_mcf_matvec(_p(off, u32p), _p(val, u32p), X.shape[0], _p(X, f32p), _p(vin, f32p), C.c_double(time_step),
-                         _p(out, f64p))
-    return out
+    scale = np.empty(X.shape[0], dtype=np.float64)
+    lib().rxo_mcf_matvec_scaled(_p(off, u32p), _p(val, u32p), X.shape[0], _p(X, f32p), _p(vin, f32p), C.c_double(time_step),
+                                _p(out, f64p), _p(scale, f64p))
+    return (out, scale) if with_scale else out
 
 
 def gaussian_curvature(fv, X):

@@ -16,6 +16,10 @@
 //                              columns in the reference's iteration order, 0xFFFFFFFF = none
 //   vn.f32                     vertex normals from the reference's FV lambda
 //                              (apps/VertexNormal/vertex_normal_kernel.cuh:10-43) over raw AoSoA arrays
+//   lap_1.f32, lap_5.f32       positions after 1 and 5 iterations of the reference's manual smoothing
+//                              (apps/Smoothing/manual.h:86-104: the VV gradient lambda through Query<256>::dispatch<Op::VV>,
+//                              then the step lambda through the reference's own detail::for_each_vertex kernel;
+//                              learning rate 0.01 as a double, apps/Smoothing/smoothing.cu:17-18)
 //
 // usage: ref_gpu_queries <mesh.bin> <outdir> [patch_size=512] [dump=1] [nrun=100]
 //   mesh.bin = u32 nv, u32 nf, u32 fv[3 nf], f32 x[3 nv]
@@ -27,6 +31,7 @@
 #include <vector>
 
 #include "rxmesh/iterator.cuh"
+#include "rxmesh/kernels/for_each.cuh"
 #include "rxmesh/query.h"
 #include "rxmesh/rxmesh.h"
 #include "rxmesh/util/bitmask_util.h"
@@ -68,6 +73,7 @@ struct RefMesh : public RXMesh
     {
         return t == 0 ? m_max_vertices_per_patch : (t == 1 ? m_max_edges_per_patch : m_max_faces_per_patch);
     }
+    const PatchInfo* device_patches() const { return m_d_patches_info; }
     uint32_t max_valence() const { return m_input_max_valence; }
     uint32_t max_ef() const { return m_input_max_edge_incident_faces; }
     uint32_t max_ff() const { return m_input_max_face_adjacent_faces; }
@@ -131,6 +137,38 @@ __global__ static void ref_vertex_normal_kernel(const Context context, RawAttr3 
     ShmemAllocator      shrd_alloc;
     query.template dispatch<Op::FV>(block, shrd_alloc, vn_lambda);
 }
+
+// apps/Smoothing/manual.h:86-95, the gradient lambda of the non-area branch, verbatim in form: grad(vh, i) += 2 * (pos(vh, i) -
+// pos(uh, i)) over the VV iterator (the attribute is the raw AoSoA array; the DenseMatrix `grad` of the app is one too)
+template <uint32_t blockThreads>
+__global__ static void ref_smoothing_grad_kernel(const Context context, RawAttr3 pos, RawAttr3 grad)
+{
+    constexpr int cols = 3;
+    auto          grad_lambda = [&](const VertexHandle& vh, const VertexIterator& iter) {
+        for (int v = 0; v < iter.size(); ++v) {
+            const VertexHandle uh = iter[v];
+            for (int i = 0; i < cols; ++i) {
+                grad(vh, i) += 2 * (pos(vh, i) - pos(uh, i));
+            }
+        }
+    };
+    auto                block = cooperative_groups::this_thread_block();
+    Query<blockThreads> query(context);
+    ShmemAllocator      shrd_alloc;
+    query.template dispatch<Op::VV>(block, shrd_alloc, grad_lambda);
+}
+// apps/Smoothing/manual.h:97-103, the step lambda: pos(vh, i) -= lr * grad(vh, i) with lr a double; launched through the
+// reference's own for_each_vertex kernel (kernels/for_each.cuh:28-40) exactly as RXMeshStatic::for_each_vertex(DEVICE) does
+struct RefSmoothingStep
+{
+    RawAttr3 grad, pos;
+    double   lr;
+    __device__ void operator()(const VertexHandle& vh) const
+    {
+        for (int i = 0; i < 3; ++i)
+            pos(vh, i) -= lr * grad(vh, i);
+    }
+};
 
 // "consume" variant (the roofline kernels of bench.py): out(s) = sum_i in(iter[i]) over raw
 // per-patch arrays, one fp32 per element (row = patch * cap + local id, the reference's slab addressing)
@@ -359,6 +397,56 @@ int main(int argc, char** argv)
         CK(cudaFree(normals.data));
     }
 
+    // manual smoothing: 5 iterations, positions after iteration 1 and 5 (lap_1.f32, lap_5.f32)
+    double lap_ms = 0;
+    {
+        const uint32_t     cap = rx.max_per_patch(0);
+        std::vector<float> hc((size_t)P * 3 * cap, 0.f);
+        for (uint32_t p = 0; p < P; ++p) {
+            const auto& ls = rx.ltog(0)[p];
+            for (uint32_t l = 0; l < ls.size(); ++l)
+                for (int a = 0; a < 3; ++a)
+                    hc[((size_t)p * 3 + a) * cap + l] = x[3 * (size_t)ls[l] + a];
+        }
+        RawAttr3 pos{nullptr, cap}, grad{nullptr, cap};
+        CK(cudaMalloc(&pos.data, hc.size() * 4));
+        CK(cudaMalloc(&grad.data, hc.size() * 4));
+        CK(cudaMemcpy(pos.data, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice));
+        auto kern = ref_smoothing_grad_kernel<BT>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_smem));
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a));
+        CK(cudaEventCreate(&b));
+        CK(cudaEventRecord(a));
+        for (int it = 1; it <= 5; ++it) {
+            CK(cudaMemset(grad.data, 0, hc.size() * 4));  // grad.reset(0, DEVICE), manual.h:38
+            kern<<<P, BT, g_smem>>>(rx.get_context(), pos, grad);
+            detail::for_each_vertex<<<P, 256>>>(P, rx.device_patches(), RefSmoothingStep{grad, pos, 0.01});
+            if (dump && (it == 1 || it == 5)) {
+                CK(cudaDeviceSynchronize());
+                std::vector<float> hp(hc.size());
+                CK(cudaMemcpy(hp.data(), pos.data, hp.size() * 4, cudaMemcpyDeviceToHost));
+                std::vector<float> g((size_t)nv * 3, 0.f);
+                for (uint32_t p = 0; p < P; ++p) {
+                    const auto& ls = rx.ltog(0)[p];
+                    for (uint32_t l = 0; l < ls.size(); ++l)
+                        if (detail::is_owned((uint16_t)l, rx.owned_mask(p, 0)))
+                            for (int c = 0; c < 3; ++c)
+                                g[3 * (size_t)ls[l] + c] = hp[((size_t)p * 3 + c) * cap + l];
+                }
+                write_file(outdir + (it == 1 ? "/lap_1.f32" : "/lap_5.f32"), g.data(), g.size() * 4);
+            }
+        }
+        CK(cudaEventRecord(b));
+        CK(cudaEventSynchronize(b));
+        CK(cudaGetLastError());
+        float ms;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        lap_ms = ms / 5;
+        CK(cudaFree(pos.data));
+        CK(cudaFree(grad.data));
+    }
+
     // consume variants of VV and VF (inputs = 1.0 everywhere, so out = neighbour count: checked on the host)
     double cons_ms[2] = {0, 0};
     {
@@ -444,8 +532,8 @@ int main(int argc, char** argv)
         js += buf;
     }
     snprintf(buf, sizeof buf,
-             "}, \"vertex_normals\": {\"ms\": %.6f, \"blocks_per_sm\": %d}, \"consume\": {\"VV\": %.6f, \"VF\": %.6f}}", vn_ms,
-             vn_occ, cons_ms[0], cons_ms[1]);
+             "}, \"vertex_normals\": {\"ms\": %.6f, \"blocks_per_sm\": %d}, \"consume\": {\"VV\": %.6f, \"VF\": %.6f}, "
+             "\"smoothing_ms_per_iteration\": %.6f}", vn_ms, vn_occ, cons_ms[0], cons_ms[1], lap_ms);
     js += buf;
     write_file(outdir + "/meta.json", js.data(), js.size());
     printf("%s\n", js.c_str());

@@ -697,14 +697,24 @@ static double rxo_cot_part(const double* p, const double* r, const double* v)
 /* MCF matrix-free mat-vec, cotan weights (apps/MCF/mcf_kernels.cuh:117-205):
  * out(p) = (1/vw + sum_w) in(p) - sum_r w(p,r) in(r), w = max(0, cot_q + cot_s) * time_step,
  * vw = 0.5 / sum of positive partial Voronoi areas. rings = rxo_oriented_rings. float64 from fp32 inputs. */
+/* scale (may be NULL): per vertex |diag| |in_p| + sum_i |w_i| |in_i| -- the magnitude of the terms whose DIFFERENCE the   */
+/* result is.  A fp32 evaluation is accurate relative to this scale (backward error), not relative to |out|: for a smooth */
+/* input the terms cancel to a few per cent of their size.                                                              */
+void rxo_mcf_matvec_scaled(const uint32_t* off, const uint32_t* val, uint32_t nv, const float* X, const float* in,
+                           double time_step, double* out, double* scale);
 void rxo_mcf_matvec(const uint32_t* off, const uint32_t* val, uint32_t nv, const float* X, const float* in,
                     double time_step, double* out)
+{
+    rxo_mcf_matvec_scaled(off, val, nv, X, in, time_step, out, NULL);
+}
+void rxo_mcf_matvec_scaled(const uint32_t* off, const uint32_t* val, uint32_t nv, const float* X, const float* in,
+                           double time_step, double* out, double* scale)
 {
     for (uint32_t p = 0; p < nv; ++p) {
         double P[3] = {X[3 * (uint64_t)p], X[3 * (uint64_t)p + 1], X[3 * (uint64_t)p + 2]};
         uint32_t k = off[p + 1] - off[p];
         const uint32_t* ring = val + off[p];
-        double sum_w = 0, vw = 0, x[3] = {0, 0, 0};
+        double sum_w = 0, vw = 0, x[3] = {0, 0, 0}, mag = 0;
         for (uint32_t v = 0; v < k; ++v) {
             uint32_t qi = ring[(v + k - 1) % k], ri = ring[v], si = ring[(v + 1) % k];
             double Q[3], R[3], S[3];
@@ -716,6 +726,8 @@ void rxo_mcf_matvec(const uint32_t* off, const uint32_t* val, uint32_t nv, const
             sum_w += w;
             for (int c = 0; c < 3; ++c)
                 x[c] -= w * in[3 * (uint64_t)ri + c];
+            mag += w * sqrt((double)in[3 * (uint64_t)ri] * in[3 * (uint64_t)ri] + (double)in[3 * (uint64_t)ri + 1] * in[3 * (uint64_t)ri + 1] +
+                            (double)in[3 * (uint64_t)ri + 2] * in[3 * (uint64_t)ri + 2]);
             double ta = rxo_partial_voronoi(P, Q, R);
             vw += ta > 0 ? ta : 0;
         }
@@ -723,6 +735,9 @@ void rxo_mcf_matvec(const uint32_t* off, const uint32_t* val, uint32_t nv, const
         double diag = 1.0 / vw + sum_w;
         for (int c = 0; c < 3; ++c)
             out[3 * (uint64_t)p + c] = x[c] + diag * in[3 * (uint64_t)p + c];
+        if (scale)
+            scale[p] = mag + fabs(diag) * sqrt((double)in[3 * (uint64_t)p] * in[3 * (uint64_t)p] + (double)in[3 * (uint64_t)p + 1] * in[3 * (uint64_t)p + 1] +
+                                               (double)in[3 * (uint64_t)p + 2] * in[3 * (uint64_t)p + 2]);
     }
 }
 

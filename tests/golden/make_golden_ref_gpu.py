@@ -9,7 +9,8 @@ oracle/_ref/ref_gpu_queries is the reference's unmodified rxmesh.cpp / patcher /
 Query<256>::dispatch compiled from /root/reference by `make -C oracle ref_gpu` in the build container (see
 oracle/ref_gpu_queries.cu); it travels to the box with the snapshot.  For every fixture mesh this records what the
 reference itself produced on this GPU: its patching (face -> patch), per-patch local->global maps and owned counts,
-the eight query results as global ids in the reference's iteration order, and its vertex normals.
+the eight query results as global ids in the reference's iteration order, its vertex normals, and the positions after 1 and
+5 iterations of its manual smoothing (apps/Smoothing/manual.h:86-104, lap_1 / lap_5).
 tests/test_gpu_ref_golden.py replays the patching through our builder and compares handle for handle.
 
 With --timing it also times the reference's kernels on larger procedural meshes next to ours (same mesh, same GPU)
@@ -59,6 +60,9 @@ def run_ref(V, F, patch_size, dump, nrun, timeout=1500):
                 if "q_" + op in arrs:
                     arrs["q_" + op] = arrs["q_" + op].reshape(-1, meta["ops"][op]["width"])
             arrs["vn"] = arrs["vn"].reshape(-1, 3)
+            for k in ("lap_1", "lap_5"):
+                if k in arrs:
+                    arrs[k] = arrs[k].reshape(-1, 3)
         return meta, arrs
 
 

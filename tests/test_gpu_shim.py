@@ -160,9 +160,15 @@ def test_user_mcf_matvec(shim, name):
     out = np.zeros_like(V)
     dt = 10.0
     assert shim.shim_mcf_matvec(_p(F), F.shape[0], _p(V), _p(vin), V.shape[0], 512, C.c_float(dt), _p(out)) == 0
-    ref = O.mcf_matvec(O.oriented_rings(F, V.shape[0]), V, vin, dt)
-    rel = np.linalg.norm(out - ref, axis=1) / np.maximum(np.linalg.norm(ref, axis=1), 1e-30)
-    assert np.quantile(rel, 0.999) < 2e-4 and rel.max() < 2e-2, (np.quantile(rel, 0.999), rel.max())
+    ref, scale = O.mcf_matvec(O.oriented_rings(F, V.shape[0]), V, vin, dt, with_scale=True)
+    err = np.linalg.norm(out - ref, axis=1)
+    # The mat-vec is diag * in_p - sum_i w_i in_i: for a smooth input the two sides cancel to ~1/300 of their size, so the
+    # meaningful (backward) error of a fp32 evaluation is relative to the magnitude of the terms, |diag||in_p| + sum|w_i||in_i|
+    # (rxo_mcf_matvec_scaled): every vertex within 1e-6 of it (observed 1.2e-7 = one fp32 ulp; north_star asks 1e-5) ...
+    assert (err / scale).max() < 1e-6, (err / scale).max()
+    # ... and relative to the cancelled result itself that is the 1e-4 seen here (round 1 allowed 2e-2 without saying why)
+    rel = err / np.maximum(np.linalg.norm(ref, axis=1), 1e-30)
+    assert rel.max() < 1e-3, rel.max()
 
 
 @pytest.mark.parametrize("name", ["sphere3", "dragon", "bunnyhead"])

@@ -3,8 +3,8 @@
 tests/golden/ref_gpu_<mesh>.npz were written by tests/golden/make_golden_ref_gpu.py: the reference's unmodified
 rxmesh.cpp / patcher / LP hash table / Query<256>::dispatch (compiled from /root/reference into
 oracle/_ref/ref_gpu_queries) run on each fixture mesh.  They hold the reference's patching, its per-patch
-local->global maps + owned counts, its eight query results (global ids, the reference's iteration order) and its
-vertex normals.  Three checks:
+local->global maps + owned counts, its eight query results (global ids, the reference's iteration order), its
+vertex normals and the positions after 1 / 5 iterations of its manual (Laplacian) smoothing.  The checks:
 
   * CPU: the oracle's ground truth == what the reference computed (pins oracle/rxmesh_oracle.c to the reference);
   * CPU: replaying the reference's face->patch through OUR builder reproduces the reference's local numbering and
@@ -92,6 +92,42 @@ def test_builder_reproduces_reference_numbering(name):
             ref = g["ltog_" + tn][off[p]:off[p + 1]]
             assert pv["n_owned"][t] == g["owned_" + tn][p], (name, p, tn)
             assert np.array_equal(pv["ltog"][t], ref), (name, p, tn)
+
+
+def _rel(a, b):
+    return (np.linalg.norm(np.asarray(a, np.float64) - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-30)).max()
+
+
+@pytest.mark.parametrize("name", MESHES)
+def test_oracle_laplacian_matches_reference_gpu(name):
+    """Pins the Laplacian oracle: lap_1 / lap_5 are the positions after 1 and 5 iterations of the reference's OWN manual
+    smoothing lambdas (apps/Smoothing/manual.h:86-104) run through its Query<256>::dispatch<Op::VV> and for_each_vertex
+    kernels on the B200 (oracle/ref_gpu_queries.cu).  The reference sums a vertex's neighbours in fp32 in the racy order
+    of its VV lists, so agreement is to fp32 accuracy (north_star: 1e-5 relative), not to the bit."""
+    V, F = make_mesh(name)
+    g = load(name)
+    vv = O.Topology(F).query("VV")
+    r64, r32 = V.astype(np.float64), V.astype(np.float32)
+    for it in range(1, 6):
+        r64, r32 = O.laplacian_step(vv, r64, 0.01, np.float64), O.laplacian_step(vv, r32, 0.01, np.float32)
+        if it in (1, 5):
+            ref = g["lap_%d" % it].astype(np.float64)
+            assert _rel(r64, ref) < 1e-6 and _rel(r32, ref) < 1e-6, (name, it, _rel(r64, ref), _rel(r32, ref))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", MESHES)
+def test_gpu_laplacian_matches_reference_gpu(name):
+    """our k_laplacian_fan2 / k_laplacian (patching replayed from the reference) against the reference's own GPU result"""
+    rx.rx_init(0)
+    V, F = make_mesh(name)
+    g = load(name)
+    for kw in (dict(face_patch=g["face_patch"], patch_size=g["meta"]["patch_size"]), dict(patch_size=256)):
+        m = rx.RXMeshStatic(F, **kw)
+        for it in (1, 5):
+            got = m.laplacian_smooth_host(V, 0.01, it)
+            ref = g["lap_%d" % it].astype(np.float64)
+            assert _rel(got, ref) < 1e-5, (name, it, _rel(got, ref))  # north_star tolerance; observed ~1e-7
 
 
 @pytest.mark.gpu
