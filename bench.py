@@ -287,7 +287,8 @@ def run_ours(args, rank, world, local_rank):
     if world == 1:
         V, F = meshio.grid(n, n)
         fp = meshio.grid_face_tiles(n, n, TILE, TILE_I)
-        mesh = rx.RXMeshStatic(F, face_patch=fp, patch_size=2 * TILE * TILE_I, num_threads=ncores)
+        # ring2=False: the ring extension serves k-ring consumers (bilateral filtering) only; this mesh never runs one
+        mesh = rx.RXMeshStatic(F, face_patch=fp, patch_size=2 * TILE * TILE_I, num_threads=ncores, ring2=False)
         del fp
         nF, nV = mesh.get_num_faces(), mesh.get_num_vertices()
         nE_real = mesh.get_num_edges()
@@ -297,7 +298,7 @@ def run_ours(args, rank, world, local_rank):
         # mirrors one ghost tile row per neighbour (rxmesh_b200/distributed.py)
         from rxmesh_b200 import distributed as D
         sh = D.grid_slab(n, world * (n - 1) + 1, TILE, TILE_I, rank, world)
-        sm = D.ShardedMesh(sh, rank, world, patch_size=2 * TILE * TILE_I, num_threads=max(1, ncores // world))
+        sm = D.ShardedMesh(sh, rank, world, patch_size=2 * TILE * TILE_I, num_threads=max(1, ncores // world), ring2=False)
         mesh, V = sm.mesh, sh["verts"]
         hx_v, hx_f = D.HaloExchange(sm, 0), D.HaloExchange(sm, 2)
         _ = mesh.ribbon_overhead()

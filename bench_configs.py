@@ -280,14 +280,14 @@ def laplacian_400m(args, rank, world, local_rank, torch, rx, tile, tile_i):
     if world == 1:
         V, F = meshio.grid(n, n)
         fp = meshio.grid_face_tiles(n, n, tile, tile_i)
-        mesh = rx.RXMeshStatic(F, face_patch=fp, patch_size=2 * tile * tile_i, num_threads=ncores)
+        mesh = rx.RXMeshStatic(F, face_patch=fp, patch_size=2 * tile * tile_i, num_threads=ncores, ring2=False)
         del F, fp
         sm = hx = None
         l2g0, nloc = 0, V.shape[0]
         real = None
     else:
         sh = D.grid_slab(n, n, tile, tile_i, rank, world)
-        sm = D.ShardedMesh(sh, rank, world, patch_size=2 * tile * tile_i, num_threads=max(1, ncores // world))
+        sm = D.ShardedMesh(sh, rank, world, patch_size=2 * tile * tile_i, num_threads=max(1, ncores // world), ring2=False)
         mesh, V = sm.mesh, sh["verts"]
         hx = D.HaloExchange(sm, 0)
         l2g0, nloc = int(sh["l2g_v"][0]), V.shape[0]

@@ -79,7 +79,7 @@ def grid_slab(nx, ny_global, tile, tile_i, rank, world, dx=1.0):
 class ShardedMesh:
     """A rank's part of a patch-sharded mesh."""
 
-    def __init__(self, shard, rank, world, patch_size=512, device=True, num_threads=0):
+    def __init__(self, shard, rank, world, patch_size=512, device=True, num_threads=0, ring2=None):
         self.rank, self.world = rank, world
         self.l2g = {0: np.asarray(shard["l2g_v"], dtype=np.uint64), 2: np.asarray(shard["l2g_f"], dtype=np.uint64)}
         self.bounds = np.asarray(shard["bounds"], dtype=np.int64)
@@ -87,7 +87,7 @@ class ShardedMesh:
         gp = np.asarray(shard["face_patch"], dtype=np.uint32)
         self.patch_global = np.unique(gp)  # local patch q <-> global patch patch_global[q]
         self.mesh = RXMeshStatic(shard["fv"], face_patch=gp, patch_size=patch_size, device=device,
-                                 num_threads=num_threads)
+                                 num_threads=num_threads, ring2=ring2)
         g0, g1 = self.bounds[rank], self.bounds[rank + 1]
         self.first = int(np.searchsorted(self.patch_global, g0))
         self.count = int(np.searchsorted(self.patch_global, g1)) - self.first
