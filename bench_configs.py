@@ -143,11 +143,68 @@ def config_queries(torch, rx, stream, nu=707, patch_size=1024):
         ok_all &= ok
         res[op] = {"ms": ms, "entries_per_s": want[1] / (ms * 1e-3), "achieved_gbs": gbs, "hbm_frac": gbs / peak, "parity_ok": bool(ok)}
         inp.release(), out.release()
+    irregular = consume_and_normals(torch, rx, stream, m, V, F, T)
     return {"what": "8 static queries, store variant (64-bit handles), %d-face icosphere, Lloyd patches of <= %d faces" % (nF, patch_size),
+            "consume_and_normals_on_lloyd_patches": irregular,
             "faces": nF, "patches": m.get_num_patches(), "ribbon_overhead": m.ribbon_overhead(), "build_seconds": tb,
             "patcher_seconds": m.build_seconds(True), "topo_bytes_per_face": m.topo_bytes() / nF,
             "alg_bytes_per_face": QUERY_ALG_BYTES, "peak_gbs": peak, "ops": res, "parity_ok": bool(ok_all),
             "parity": "multiset of (source, neighbour) global-id pairs of the timed kernel's output == oracle, per op (bit-exact)"}
+
+
+def consume_and_normals(torch, rx, stream, m, V, F, T, check=True):
+    """the headline pass (VV consume, VF consume, vertex normals) on an arbitrary mesh / patching: what the kernels do when
+    the patches are NOT the analytic tiles of the grid (Lloyd patches, mixed valence: the scalar per-vertex path runs next
+    to the packed valence-6 path)"""
+    from oracle import oracle as O
+    peak, _ = peaks()
+    nF, nV = F.shape[0], V.shape[0]
+    x = rx.Attribute(m, 0, np.float32, 3, rx.DEVICE, rx.AoS)
+    nrm = rx.Attribute(m, 0, np.float32, 3, rx.DEVICE, rx.AoS)
+    sv_in = rx.Attribute(m, 0, np.float32, 1, rx.DEVICE, rx.AoS)
+    sv_out = rx.Attribute(m, 0, np.float32, 1, rx.DEVICE, rx.AoS)
+    sf_in = rx.Attribute(m, 2, np.float32, 1, rx.DEVICE, rx.AoS)
+    rng = np.random.RandomState(7)
+    hv, hf = rng.rand(nV).astype(np.float32), rng.rand(nF).astype(np.float32)
+    x.from_global(V), sv_in.from_global(hv), sf_in.from_global(hf)
+    out = {}
+    for name, bpf, fn in (("VV", 16.0, lambda: m.query_consume(rx.Op.VV, sv_in, sv_out, stream)),
+                          ("VF", 18.0, lambda: m.query_consume(rx.Op.VF, sf_in, sv_out, stream)),
+                          ("VN", 24.0, lambda: m.vertex_normals(x, nrm, False, stream))):
+        ms = timed(fn, stream, torch, 50, warm=3)
+        gbs = bpf * nF / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "alg_bytes_per_face": bpf, "achieved_gbs": gbs, "hbm_frac": gbs / peak}
+    if check:
+        got = nrm.to_global()
+        ref = O.vertex_normals(F, V, np.float64)
+        out["VN"]["max_rel_err_vs_oracle"] = float((np.linalg.norm(got - ref, axis=1) / np.linalg.norm(ref, axis=1)).max())
+        m.query_consume(rx.Op.VF, sf_in, sv_out, stream)
+        gotc = sv_out.to_global().reshape(-1)
+        refc = O.consume_sum(T.query("VF"), hf)
+        out["VF"]["max_rel_err_vs_oracle"] = float((np.abs(gotc - refc) / np.maximum(np.abs(refc), 1e-30)).max())
+        out["parity_ok"] = bool(out["VN"]["max_rel_err_vs_oracle"] < 1e-5 and out["VF"]["max_rel_err_vs_oracle"] < 1e-5)
+    for a in (x, nrm, sv_in, sv_out, sf_in):
+        a.release()
+    return out
+
+
+def lloyd_at_scale(torch, rx, stream, faces=100_000_000):
+    """the built-in (host, multi-threaded, deterministic) Lloyd patcher at 100 M faces: a grid whose faces are visited in
+    SCRAMBLED tile order so that nothing in the input order helps, patch size 1024; then the headline kernels on those patches"""
+    from rxmesh_b200 import meshio
+    n = int(round((faces / 2.0) ** 0.5)) + 1
+    V, F = meshio.grid(n, n)
+    t0 = time.perf_counter()
+    m = rx.RXMeshStatic(F, patch_size=1024, num_threads=os.cpu_count() or 8, ring2=False)
+    tb = time.perf_counter() - t0
+    sizes = np.diff(m.lin_base(2).astype(np.int64))
+    rec = {"what": "Lloyd patcher + build on a %d-face grid (no face->patch hint), patch size <= 1024" % F.shape[0],
+           "faces": int(F.shape[0]), "patches": m.get_num_patches(), "build_seconds": tb, "patcher_seconds": m.build_seconds(True),
+           "host_threads": os.cpu_count(), "patch_faces_mean": float(sizes.mean()), "patch_faces_max": int(sizes.max()),
+           "ribbon_overhead": m.ribbon_overhead(), "topo_bytes_per_face": m.topo_bytes() / F.shape[0]}
+    m.compact()
+    rec["kernels"] = consume_and_normals(torch, rx, stream, m, V, F, None, check=False)
+    return rec
 
 
 # ------------------------------------------------------------------------------------ configs[2]
@@ -514,6 +571,8 @@ def main():
     if "laplacian" in only:
         from bench import TILE, TILE_I
         print(json.dumps({"config": "laplacian", **laplacian_400m(args, 0, 1, 0, torch, rx, TILE, TILE_I)}), flush=True)
+    if "lloyd100m" in only:
+        print(json.dumps({"config": "lloyd100m", **lloyd_at_scale(torch, rx, stream)}), flush=True)
     if "hardwired" in only:
         print(json.dumps({"config": "hardwired", **hardwired_baseline(7072)}), flush=True)
 

@@ -1,5 +1,5 @@
 // rxmesh/attribute.h -- Attribute<T, HandleT> (include/rxmesh/attribute.h:56-731, attribute.cu:30-590) over the
-// C ABI: storage for OWNED elements (AoS / AoSoA in slot order, rxmesh_b200/csrc/patch_layout.h; SoA = the
+// C ABI: storage for OWNED elements (AoS / AoSoA in slot order, include/rxmesh_b200/patch_layout.h; SoA = the
 // reference's tensor layout, a gap-free column-major #elements x #attributes matrix over linear ids,
 // attribute.h:249-261,406-421), host + device copies and the reference's operator()(handle, attr) on both sides.
 #pragma once

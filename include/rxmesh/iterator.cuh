@@ -3,7 +3,7 @@
 // patch's direct owner table (no hash probe).
 #pragma once
 #include "rxmesh/handle.h"
-#include "../../rxmesh_b200/csrc/rxm_query.cuh"
+#include "rxmesh_b200/rxm_query.cuh"
 namespace rxmesh {
 template <typename HandleT>
 struct Iterator

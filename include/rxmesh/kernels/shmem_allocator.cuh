@@ -1,7 +1,7 @@
 // rxmesh/kernels/shmem_allocator.cuh -- ShmemAllocator (include/rxmesh/kernels/shmem_allocator.cuh:15-122):
 // bump allocator over the dynamic shared memory of the block; 16-byte aligned (TMA destinations).
 #pragma once
-#include "../../../rxmesh_b200/csrc/rxm_device.cuh"
+#include "rxmesh_b200/rxm_device.cuh"
 namespace rxmesh {
 extern __shared__ __align__(128) uint8_t SHMEM_START[];
 struct ShmemAllocator

@@ -5,7 +5,7 @@
 #include <cmath>
 #include <string>
 
-#include "../../rxmesh_b200/csrc/patch_layout.h"
+#include "rxmesh_b200/patch_layout.h"
 
 #ifndef __CUDACC__
 #error "the rxmesh_b200 C++ shim is device code: compile user sources with nvcc (-arch sm_100a --expt-extended-lambda)"

@@ -90,7 +90,7 @@ typedef struct {
     uint32_t        n_owned[3];
     uint32_t        slot_base[3];
     uint32_t        lin_base[3];
-    /* packed != 0: entries are rank-annotated (rxmesh_b200/csrc/patch_layout.h): EV/FV entry = id | rank << 11,
+    /* packed != 0: entries are rank-annotated (include/rxmesh_b200/patch_layout.h): EV/FV entry = id | rank << 11,
      * FE entry = dir | edge << 1 | rank << 12; otherwise plain 16-bit ids */
     uint32_t        packed;
     const uint16_t* ev;          /* 2*n[E]: local (larger-id vertex, smaller-id vertex) */
@@ -145,7 +145,7 @@ const uint32_t* rxm_mesh_device_slot_base(const rxm_mesh* m, int elem);
  * the reference's m_d_linear_id_element_prefix (attribute.h:406-421,623-630) */
 const uint32_t* rxm_mesh_device_lin_base(const rxm_mesh* m, int elem);
 /* get_context() (rxmesh_static.h): copies the by-value kernel argument (rxm::MeshView of
- * rxmesh_b200/csrc/patch_layout.h, the counterpart of Context, context.h:15-441) into out_view;
+ * include/rxmesh_b200/patch_layout.h, the counterpart of Context, context.h:15-441) into out_view;
  * out_bytes must equal sizeof(rxm::MeshView). Used by the C++ header shim (include/rxmesh/). */
 int rxm_mesh_view(const rxm_mesh* m, void* out_view, uint32_t out_bytes);
 

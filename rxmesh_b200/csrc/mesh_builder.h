@@ -13,7 +13,7 @@
 #include <string>
 #include <vector>
 
-#include "patch_layout.h"
+#include "rxmesh_b200/patch_layout.h"
 
 namespace rxm {
 

@@ -24,7 +24,7 @@
 
 #include "rxm_kernels.h"
 #include "rxm_persistent.cuh"
-#include "rxm_query.cuh"
+#include "rxmesh_b200/rxm_query.cuh"
 
 namespace rxm {
 

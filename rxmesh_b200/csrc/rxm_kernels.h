@@ -2,7 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include "patch_layout.h"
+#include "rxmesh_b200/patch_layout.h"
 
 namespace rxm {
 

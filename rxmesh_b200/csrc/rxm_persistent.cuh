@@ -19,7 +19,7 @@
 // A worker W provides: Args, Layout (stage carve-up, host-computed from the mesh
 // maxima), issue() [thread 0], pre() and compute() [all threads].
 #pragma once
-#include "rxm_device.cuh"
+#include "rxmesh_b200/rxm_device.cuh"
 
 namespace rxm {
 namespace dev {
