@@ -57,6 +57,8 @@ int rxm_mesh_create(const uint32_t* fv, uint32_t num_faces, const uint32_t* face
 /* same, with build flags: sections of the patch store a mesh will never need can be left out */
 #define RXM_BUILD_NO_RING2 1u /* no ring-2 extension (rxm_bilateral_filter then runs its cross-patch path for every vertex
                                  whose neighbourhood leaves the patch); saves build time and ~3 bytes per face */
+#define RXM_BUILD_NO_PATCH_REORDER 2u /* keep the Lloyd patcher's seed-order patch ids (default: renumbered breadth-first over the
+                                        patch graph from a peripheral patch, so that contiguous id ranges are compact slabs) */
 int rxm_mesh_create_ex(const uint32_t* fv, uint32_t num_faces, const uint32_t* face_patch, uint32_t patch_size,
                        int num_threads, uint32_t flags, rxm_mesh** out);
 /* RXMesh::build_device (rxmesh.cpp:1139-1615): upload the patch store to the current device. */
@@ -246,6 +248,26 @@ int   rxm_fused_halo_set(rxm_fused_halo* h, const uint32_t* push_off, const uint
 void  rxm_fused_halo_destroy(rxm_fused_halo* h);
 int   rxm_laplacian_smooth_fused(rxm_mesh* m, rxm_attr* in, rxm_attr* out, double lr, rxm_fused_halo* h, int out_is_b,
                                  uint32_t step, void* stream);
+/* ---- single-process multi-GPU mode: one host process, one shard per device (rxmesh_b200/csrc/rxm_multi.cu) ----
+ * What SURVEY.md 8(e) asks of RXMeshStatic ("device-list / shard options", rxmesh_static.h:61-100 has a single device): the
+ * mesh is cut into contiguous patch-id ranges, one per device; every device holds its range plus two vertex-rings of ghost
+ * faces; mirrored rows travel by direct NVLink peer stores from the kernel that computes them (k_laplacian_fan2<true>).
+ * devices == NULL: host-only plan (no CUDA call; the compute entry points then fail with RXM_ERR_CUDA).
+ * face_patch == NULL: built-in Lloyd patcher with locality-ordered patch ids. */
+typedef struct rxm_multi rxm_multi;
+int  rxm_multi_create(const uint32_t* fv, uint32_t num_faces, const uint32_t* face_patch, uint32_t patch_size, const int* devices,
+                      int num_shards, int num_threads, rxm_multi** out);
+void rxm_multi_destroy(rxm_multi* m);
+/* what: 0 shards, 1 patches, 2 ghost vertex rows refreshed per exchange (all shards), 3 vertices, 4 faces; per shard:
+ * 10 real patches, 11 faces held, 12 vertices owned by its real patches, 13 ghost rows received, 14 rows pushed, 15 neighbours */
+uint64_t  rxm_multi_info(const rxm_multi* m, int what, int shard);
+rxm_mesh* rxm_multi_shard_mesh(rxm_multi* m, int shard);
+/* manual smoothing (apps/Smoothing/manual.h:86-104) over all devices: host buffers in GLOBAL vertex order, [V][3] fp32;
+ * one fused compute + halo kernel per device and iteration, no host synchronisation inside the loop */
+int rxm_multi_laplacian_smooth(rxm_multi* m, const float* coords, float* out, double lr, uint32_t iters);
+/* compute_vertex_normal (apps/VertexNormal/vertex_normal_kernel.cuh:10-43) over all devices */
+int rxm_multi_vertex_normals(rxm_multi* m, const float* coords, float* normals);
+
 int rxm_ipc_export(void* dev_ptr, void* handle64);        /* cudaIpcGetMemHandle */
 int rxm_ipc_open(const void* handle64, void** dev_ptr);   /* cudaIpcOpenMemHandle */
 int rxm_ipc_close(void* dev_ptr);

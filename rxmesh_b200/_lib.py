@@ -97,6 +97,13 @@ SYMBOLS = {
     "rxm_fused_halo_destroy": (None, [C.c_void_p]),
     "rxm_laplacian_smooth_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int,
                                              C.c_uint32, C.c_void_p]),
+    "rxm_multi_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int,
+                                   C.POINTER(C.c_void_p)]),
+    "rxm_multi_destroy": (None, [C.c_void_p]),
+    "rxm_multi_info": (C.c_uint64, [C.c_void_p, C.c_int, C.c_int]),
+    "rxm_multi_shard_mesh": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "rxm_multi_laplacian_smooth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_uint32]),
+    "rxm_multi_vertex_normals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "rxm_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rxm_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "rxm_ipc_close": (C.c_int, [C.c_void_p]),

@@ -501,6 +501,100 @@ void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_
 }
 
 // ---------------------------------------------------------------------------
+// Locality ordering of the patch ids (the role of the reference's disabled Patcher::bfs, patcher/patcher.cu:583-638):
+// Lloyd numbers patches by the position of their seed in the input face order, which says nothing about where the patch
+// lies.  Patches are renumbered in breadth-first order over the patch adjacency graph, started from a pseudo-peripheral
+// patch (the last patch a first sweep reaches), so that consecutive ids form layers that sweep across the mesh: a
+// contiguous id range -- what a rank of the multi-GPU mode owns -- is then a slab with a short frontier, and neighbouring
+// blocks of a launch touch neighbouring memory.  Deterministic: neighbours are visited in ascending id.
+// ---------------------------------------------------------------------------
+static void reorder_patches_bfs(const uint32_t* fe, uint32_t nf, uint32_t ne, std::vector<uint32_t>& fpatch, uint32_t P)
+{
+    // patch adjacency: an edge whose faces lie in different patches
+    std::vector<uint32_t> first(ne, INVALID32_);
+    std::vector<uint64_t> pairs;
+    for (uint32_t f = 0; f < nf; ++f)
+        for (int j = 0; j < 3; ++j) {
+            const uint32_t e = fe[3ull * f + j];
+            if (first[e] == INVALID32_) {
+                first[e] = f;
+            } else {
+                const uint32_t a = fpatch[first[e]], b = fpatch[f];
+                if (a != b) pairs.push_back(((uint64_t)a << 32) | b), pairs.push_back(((uint64_t)b << 32) | a);
+            }
+        }
+    std::vector<uint32_t>().swap(first);
+    std::sort(pairs.begin(), pairs.end());
+    pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+    std::vector<uint32_t> off((size_t)P + 1, 0);
+    for (uint64_t k : pairs)
+        off[(k >> 32) + 1]++;
+    for (uint32_t p = 0; p < P; ++p)
+        off[p + 1] += off[p];
+    auto bfs = [&](uint32_t start, std::vector<uint32_t>& order) {
+        std::vector<uint8_t> seen(P, 0);
+        order.clear();
+        order.reserve(P);
+        uint32_t scan = 0;
+        for (uint32_t s = start;;) {
+            seen[s] = 1;
+            size_t head = order.size();
+            order.push_back(s);
+            while (head < order.size()) {
+                const uint32_t p = order[head++];
+                for (uint32_t i = off[p]; i < off[p + 1]; ++i) {
+                    const uint32_t q = (uint32_t)(pairs[i] & 0xFFFFFFFFu);
+                    if (!seen[q]) seen[q] = 1, order.push_back(q);
+                }
+            }
+            while (scan < P && seen[scan]) ++scan;  // next component
+            if (scan == P) break;
+            s = scan;
+        }
+    };
+    std::vector<uint32_t> order;
+    bfs(0, order);
+    // the last patch of the component of patch 0 (pseudo-peripheral): the first sweep's order ends with the other components
+    // when there are any, so take the last patch REACHED from 0 by redoing the sweep's first phase
+    uint32_t far = 0;
+    {
+        std::vector<uint8_t> seen(P, 0);
+        std::vector<uint32_t> q(1, 0u);
+        seen[0] = 1;
+        for (size_t head = 0; head < q.size(); ++head)
+            for (uint32_t i = off[q[head]]; i < off[q[head] + 1]; ++i) {
+                const uint32_t t = (uint32_t)(pairs[i] & 0xFFFFFFFFu);
+                if (!seen[t]) seen[t] = 1, q.push_back(t);
+            }
+        far = q.back();
+    }
+    bfs(far, order);
+    std::vector<uint32_t> label(P);
+    for (uint32_t i = 0; i < P; ++i)
+        label[order[i]] = i;
+#pragma omp parallel for schedule(static)
+    for (int64_t f = 0; f < (int64_t)nf; ++f)
+        fpatch[f] = label[fpatch[f]];
+}
+
+// face -> patch of the built-in patcher alone (edges + Lloyd + locality ordering), without building the patch store: what the
+// multi-GPU mode needs to cut a mesh into shards before any shard is built
+std::string compute_face_patch(const uint32_t* fv, uint32_t nf, const BuildOptions& opt, std::vector<uint32_t>& fpatch, uint32_t& P)
+{
+    if (opt.num_threads > 0) omp_set_num_threads(opt.num_threads);
+    if (nf == 0) return "compute_face_patch: empty face list";
+    uint32_t nv = 0;
+    for (uint64_t i = 0; i < 3ull * nf; ++i)
+        nv = std::max(nv, fv[i]);
+    nv += 1;
+    U32Buf ev, fe;
+    const uint32_t ne = build_edges(fv, nf, nv, ev, fe);
+    patcher_lloyd(fe.data(), nf, ne, opt.patch_size, opt.lloyd_iters, fpatch, P);
+    if (opt.reorder_patches && P > 2) reorder_patches_bfs(fe.data(), nf, ne, fpatch, P);
+    return "";
+}
+
+// ---------------------------------------------------------------------------
 // build_mesh
 // ---------------------------------------------------------------------------
 std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_patch_in,
@@ -597,6 +691,7 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
             fpatch[f] = used[face_patch_in[f]];
     } else {
         patcher_lloyd(fe, nf, ne, opt.patch_size, opt.lloyd_iters, fpatch, P);
+        if (opt.reorder_patches && P > 2) reorder_patches_bfs(fe, nf, ne, fpatch, P);
     }
     M.patcher_seconds = now_s() - t_p0;
     M.num_patches     = P;

@@ -92,6 +92,8 @@ struct BuildOptions
     bool     force_wide   = false;  // never use the packed format (tests of the atomic path)
     bool     no_fans      = false;  // never store one-ring fans (tests of the generic kernels)
     uint32_t ring_depth   = 2;      // rings around the owned vertices whose vertices carry their complete one-ring
+    bool     reorder_patches = true;  // renumber the Lloyd patches in breadth-first (locality) order; a caller-supplied
+                                      // face->patch array is always honoured as is
     bool     no_ring2     = false;  // skip the ring-2 extension (meshes that never run a k-ring consumer: saves build time
                                     // and ~3 bytes per face of patch store)
 };
@@ -105,6 +107,10 @@ uint32_t build_edges(const uint32_t* fv, uint32_t nf, uint32_t nv, U32Buf& ev, U
 // role of patcher::Patcher::run_lloyd (patcher/patcher.cu:828-987).
 void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_size,
                    uint32_t lloyd_iters, std::vector<uint32_t>& face_patch, uint32_t& num_patches);
+
+// The built-in patcher alone: face -> patch (Lloyd + locality ordering of the ids), no patch store.
+std::string compute_face_patch(const uint32_t* fv, uint32_t nf, const BuildOptions& opt, std::vector<uint32_t>& face_patch,
+                               uint32_t& num_patches);
 
 // Builds everything. face_patch may be null (run the Lloyd patcher) or a
 // user-supplied face->patch assignment (the analogue of the reference's

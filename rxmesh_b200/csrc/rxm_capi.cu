@@ -117,6 +117,12 @@ const char* rxm_last_error(void)
     return g_err.c_str();
 }
 
+// for the other translation units of the library (rxm_multi.cu): record an error, return its code
+int rxm_set_last_error(int code, const char* msg)
+{
+    return fail(code, msg ? msg : "");
+}
+
 const char* rxm_version(void)
 {
     return "rxmesh_b200 0.1 (sm_100a)";
@@ -152,6 +158,7 @@ int rxm_mesh_create_ex(const uint32_t* fv, uint32_t num_faces, const uint32_t* f
     opt.force_wide  = getenv("RXM_FORCE_WIDE") != nullptr;  // tests: exercise the atomic (wide-format) kernels
     opt.no_fans     = getenv("RXM_NO_FANS") != nullptr;     // tests: exercise the generic (transpose) kernels
     opt.no_ring2    = (flags & RXM_BUILD_NO_RING2) != 0;
+    opt.reorder_patches = !(flags & RXM_BUILD_NO_PATCH_REORDER) && getenv("RXM_NO_PATCH_REORDER") == nullptr;
     std::string e;
     try {
         e = build_mesh(fv, num_faces, face_patch, opt, m->h);

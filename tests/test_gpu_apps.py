@@ -206,6 +206,26 @@ def test_bilateral_filter(built):
         del os.environ["RXM_BILATERAL_CSR"]
 
 
+@pytest.mark.parametrize("n", [9, 14, 40])
+def test_bilateral_high_valence(n):
+    """Fans of more than 8 neighbours leave the patch kernel's register-resident ring (deferred to the cross-patch kernel):
+    a bipyramid's apexes (valence n) next to valence-4 rim vertices, every vertex against the oracle."""
+    rx.rx_init(0)
+    ang = 2 * np.pi * np.arange(n) / n
+    rng = np.random.RandomState(n)
+    V = np.concatenate([np.stack([np.cos(ang), np.sin(ang), 0.1 * rng.randn(n)], 1), [[0, 0, 0.8], [0, 0, -0.7]]]).astype(np.float32)
+    F = np.array([[n, i, (i + 1) % n] for i in range(n)] + [[n + 1, (i + 1) % n, i] for i in range(n)], np.uint32)
+    m = rx.RXMeshStatic(F, patch_size=64)
+    T = O.Topology(F)
+    x = rx.Attribute(m, 0, np.float32, 3, rx.LOCATION_ALL, rx.AoS)
+    y = rx.Attribute(m, 0, np.float32, 3, rx.LOCATION_ALL, rx.AoS)
+    x.from_global(V)
+    m.bilateral_filter(x, y, 1)
+    ref, worst = O.bilateral_step(T.query("VV"), F, V, 80, 2)
+    assert np.abs(y.to_global() - ref).max() < 2e-5
+    assert m.bilateral_deferred() >= 2  # the two apexes at least
+
+
 def test_reduce_handle(built):
     """ReduceHandle: dot / norm2 / reduce / arg-min / arg-max over owned elements (tests/RXMesh_test/test_attribute.cu)"""
     name, V, F, m, T = built
