@@ -443,7 +443,21 @@ void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_
     };
 
     int n_assign = 0, n_outer = 0;
-    for (int outer = 0; outer < 64; ++outer) {
+    // the same passes on the GPU when there is one and the mesh is large enough to pay for the launches
+    // (rxm_patcher_gpu.cu: identical face -> patch array); RXM_PATCHER_GPU=0 / 1 forces the choice
+    bool on_gpu = false;
+    {
+        const char* g    = getenv("RXM_PATCHER_GPU");
+        const bool  want = g ? atoi(g) != 0 : nf >= 500000u;
+        if (want && !getenv("RXM_PATCHER_SERIAL")) {
+            const std::vector<uint32_t> seeds0 = seeds;
+            const double                t0     = now_s();
+            on_gpu = patcher_lloyd_gpu(ff_off, ff_val, nf, patch_size, lloyd_iters, seeds, face_patch, queue, psize, &n_assign);
+            if (!on_gpu) seeds = seeds0;
+            t_assign += now_s() - t0;
+        }
+    }
+    for (int outer = 0; outer < 64 && !on_gpu; ++outer) {
         ++n_outer;
         assign();
         for (uint32_t it = 0; it < lloyd_iters; ++it) {
@@ -468,7 +482,7 @@ void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_
             }
         if (!any) break;
     }
-    assign();
+    if (!on_gpu) assign();
     // last-resort guarantee of the size bound: chop oversized patches by BFS order
     {
         bool over = false;
@@ -497,7 +511,7 @@ void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_
     num_patches = (uint32_t)seeds.size();
     if (getenv("RXM_VERBOSE"))
         fprintf(stderr, "[rxmesh_b200] lloyd: %d outer rounds, %d recentre+assign passes, %u patches (assign %.2fs, recentre %.2fs, %s)\n",
-                n_outer, n_assign, num_patches, t_assign, t_recenter, serial ? "serial" : "parallel");
+                n_outer, n_assign, num_patches, t_assign, t_recenter, on_gpu ? "gpu" : serial ? "serial" : "parallel");
 }
 
 // ---------------------------------------------------------------------------

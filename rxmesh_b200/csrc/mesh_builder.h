@@ -108,6 +108,11 @@ uint32_t build_edges(const uint32_t* fv, uint32_t nf, uint32_t nv, U32Buf& ev, U
 void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_size,
                    uint32_t lloyd_iters, std::vector<uint32_t>& face_patch, uint32_t& num_patches);
 
+// The outer Lloyd loop of patcher_lloyd on the current CUDA device (rxm_patcher_gpu.cu); false = not run, use the host passes.
+bool patcher_lloyd_gpu(const std::vector<uint32_t>& ff_off, const std::vector<uint32_t>& ff_val, uint32_t nf, uint32_t patch_size,
+                       uint32_t lloyd_iters, std::vector<uint32_t>& seeds, std::vector<uint32_t>& face_patch,
+                       std::vector<uint32_t>& queue, std::vector<uint32_t>& psize, int* n_assign);
+
 // The built-in patcher alone: face -> patch (Lloyd + locality ordering of the ids), no patch store.
 std::string compute_face_patch(const uint32_t* fv, uint32_t nf, const BuildOptions& opt, std::vector<uint32_t>& face_patch,
                                uint32_t& num_patches);
