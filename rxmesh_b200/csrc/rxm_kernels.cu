@@ -1323,120 +1323,52 @@ __device__ __forceinline__ void bil_normal_sigma(const BilPatch& B, uint32_t v, 
     nx *= inv, ny *= inv, nz *= inv;
 }
 
-// fast path of one owned vertex; false = the walk left what the patch can answer (caller defers the vertex to the cross-patch
-// kernel): a ring outside the patch, more than BIL_FAST_CAP accepted vertices, or a fan of more than 8 neighbours.
-//   * no "seen" set: a visit measures the distance first and only a candidate INSIDE the radius is compared with the vertex
-//     itself and with the accepted list (3-4 entries on average).  A candidate outside the radius is measured again when
-//     another ring names it: same answer, nothing to remember.  (r02e kept a 144 B per-thread bitmap over the patch's
-//     extended local ids: 109 KB of shared memory per block of 512, two resident blocks.)
-//   * the pass over the vertex's own fan that yields the normal and sigma_c already measures every ring-1 distance: they
-//     stay in registers (the loop is unrolled over 8 guarded slots), so ring 1 is accepted without a second visit, without
-//     reloading a coordinate and without a duplicate test (a fan names each neighbour once, never the vertex itself);
-//   * the rings of accepted vertices are read two ids per LDS.32 and measured two candidates per instruction (FADD2 / FMUL2 /
-//     FFMA2): a candidate outside the radius -- most of them -- costs half the arithmetic of a scalar visit.
-// Visit order, accepted set and every sum are those of the reference's walk (packed and scalar fp32 operations round alike).
+// fast path of one owned vertex; false = the walk left what the patch can answer (caller defers the vertex).
+// ONE flattened loop over "visits" (the vertex's own ring, then the ring of every accepted vertex in turn): the lanes of a
+// warp stay together until their TOTAL number of visits is used up, instead of diverging on every ring's length.
 template <uint32_t BT>
-__device__ __forceinline__ bool bil_fast(const BilPatch& B, uint32_t v, uint16_t* lst, float* out)
+__device__ __forceinline__ bool bil_fast(const BilPatch& B, uint32_t v, uint32_t* bm, uint32_t bm_words, uint16_t* lst, float* out)
 {
-    const uint32_t o0 = B.fo[v], b = o0 & FAN_OFF_MASK, e = B.fo[v + 1] & FAN_OFF_MASK, val = e - b;
-    if (val > 8u) return false;
-    const float4 P  = B.x[v];
-    const float  px = P.x, py = P.y, pz = P.z;
-    float        d2[8];
-    float        nx = 0.f, ny = 0.f, nz = 0.f, sc2;
-    {
-        float4      q   = B.x[B.fv[b]];
-        const float d0x = q.x - px, d0y = q.y - py, d0z = q.z - pz;
-        d2[0] = sc2 = dist2f(d0x, d0y, d0z);
-        float ax = d0x, ay = d0y, az = d0z;
-        auto  face = [&](float cx, float cy, float cz) {
-            const float fx = ay * cz - az * cy, fy = az * cx - ax * cz, fz = ax * cy - ay * cx;
-            const float w  = rsqrtf(fx * fx + fy * fy + fz * fz);
-            nx += fx * w, ny += fy * w, nz += fz * w;
-        };
-#pragma unroll
-        for (uint32_t k = 1; k < 8; ++k) {
-            d2[k] = 0.f;
-            if (k < val) {
-                q              = B.x[B.fv[b + k]];
-                const float cx = q.x - px, cy = q.y - py, cz = q.z - pz;
-                d2[k]          = dist2f(cx, cy, cz);
-                sc2            = fminf(sc2, d2[k]);
-                face(cx, cy, cz);
-                ax = cx, ay = cy, az = cz;
-            }
-        }
-        if (o0 & FAN_CLOSED) face(d0x, d0y, d0z);
-        const float inv = rsqrtf(nx * nx + ny * ny + nz * nz);
-        nx *= inv, ny *= inv, nz *= inv;
-    }
-    const float     radius = 4.0f * sc2;
-    uint16_t* const my     = lst + threadIdx.x;
-    uint32_t        na     = 0;
+    const uint32_t tid = threadIdx.x;
+    const float4   P   = B.x[v];
+    const float    px = P.x, py = P.y, pz = P.z;
+    float          nx, ny, nz, sc2;
+    bil_normal_sigma(B, v, px, py, pz, nx, ny, nz, sc2);
+    const float radius = 4.0f * sc2;
+    for (uint32_t w = 0; w < bm_words; ++w)
+        bm[w * BT + tid] = 0u;
+    bm[(v >> 5) * BT + tid] = 1u << (v & 31u);
+    uint32_t        na = 0, head = 0;
     float           sum = 0.f, sum_sq = 0.f;
-    auto accept = [&](uint32_t u, float cx, float cy, float cz) {
-        my[na * BT] = (uint16_t)u;
+    const uint16_t* ring = B.fv;
+    uint32_t        i = B.fo[v] & FAN_OFF_MASK, re = B.fo[v + 1] & FAN_OFF_MASK;
+    while (true) {
+        if (i == re) {  // next ring: the next accepted vertex
+            if (head == na) break;
+            const uint32_t w = lst[head * BT + tid];
+            ++head;
+            if (w < B.nov) {
+                ring = B.fv, i = B.fo[w] & FAN_OFF_MASK, re = B.fo[w + 1] & FAN_OFF_MASK;
+            } else {
+                const uint32_t r = B.r2idx[w - B.nov];
+                if (r == 0xFFFFu) return false;  // its ring is not in this patch
+                ring = B.r2val, i = B.r2off[r], re = B.r2off[r + 1];
+            }
+            continue;
+        }
+        const uint32_t u    = ring[i++];
+        uint32_t&      word = bm[(u >> 5) * BT + tid];
+        const uint32_t bit = 1u << (u & 31u), old = word;
+        if (old & bit) continue;  // seen before (accepted or rejected)
+        word             = old | bit;
+        const float4 q   = B.x[u];
+        const float  cx = q.x - px, cy = q.y - py, cz = q.z - pz;
+        if (dist2f(cx, cy, cz) > radius) continue;
+        if (na == (uint32_t)BIL_FAST_CAP) return false;
+        lst[na * BT + tid] = (uint16_t)u;
         ++na;
         const float h = fabsf(cx * nx + cy * ny + cz * nz);
         sum += h, sum_sq += h * h;
-    };
-    // ring 1 from the distances in registers
-#pragma unroll
-    for (uint32_t k = 0; k < 8; ++k)
-        if (k < val && !(d2[k] > radius)) {
-            const uint32_t u = B.fv[b + k];
-            const float4   q = B.x[u];
-            accept(u, q.x - px, q.y - py, q.z - pz);
-        }
-    // a candidate inside the radius: false = the accepted list is full
-    auto inside = [&](uint32_t u, float cx, float cy, float cz) -> bool {
-        if (u == v) return true;
-        bool dup = false;
-        for (uint32_t k = 0; k < na; ++k)
-            dup |= my[k * BT] == (uint16_t)u;
-        if (dup) return true;
-        if (na == (uint32_t)BIL_FAST_CAP) return false;
-        accept(u, cx, cy, cz);
-        return true;
-    };
-    const f2 PX = pk(px, px), PY = pk(py, py), PZ = pk(pz, pz);
-    for (uint32_t head = 0; head < na; ++head) {
-        const uint32_t  w = my[head * BT];
-        const uint16_t* ring;
-        uint32_t        i, re;
-        if (w < B.nov) {
-            ring = B.fv, i = B.fo[w] & FAN_OFF_MASK, re = B.fo[w + 1] & FAN_OFF_MASK;
-        } else {
-            const uint32_t r = B.r2idx[w - B.nov];
-            if (r == 0xFFFFu) return false;  // its ring is not in this patch
-            ring = B.r2val, i = B.r2off[r], re = B.r2off[r + 1];
-        }
-        while (i < re) {
-            if (!(i & 1u) && i + 1u < re) {
-                const uint32_t two = *reinterpret_cast<const uint32_t*>(ring + i);
-                const uint32_t uA = two & 0xFFFFu, uB = two >> 16;
-                const float4   qa = B.x[uA], qb = B.x[uB];
-                const f2       cx = sub2(pk(qa.x, qb.x), PX), cy = sub2(pk(qa.y, qb.y), PY), cz = sub2(pk(qa.z, qb.z), PZ);
-                float          da, db;
-                upk(fma2(cz, cz, fma2(cy, cy, mul2(cx, cx))), da, db);
-                i += 2;
-                if (!(da > radius)) {
-                    float x0, x1, y0, y1, z0, z1;
-                    upk(cx, x0, x1), upk(cy, y0, y1), upk(cz, z0, z1);
-                    if (!inside(uA, x0, y0, z0)) return false;
-                }
-                if (!(db > radius)) {
-                    float x0, x1, y0, y1, z0, z1;
-                    upk(cx, x0, x1), upk(cy, y0, y1), upk(cz, z0, z1);
-                    if (!inside(uB, x1, y1, z1)) return false;
-                }
-            } else {
-                const uint32_t u  = ring[i++];
-                const float4   q  = B.x[u];
-                const float    cx = q.x - px, cy = q.y - py, cz = q.z - pz;
-                if (!(dist2f(cx, cy, cz) > radius) && !inside(u, cx, cy, cz)) return false;
-            }
-        }
     }
     const float rc  = fast_rcp((float)(na + 1u));  // the vertex itself is the first member of its neighbourhood (h = 0, t = 0)
     const float m1  = sum * rc;
@@ -1445,7 +1377,7 @@ __device__ __forceinline__ bool bil_fast(const BilPatch& B, uint32_t v, uint16_t
     const float ic = -0.5f * fast_rcp(sc2), is = -0.5f * fast_rcp(ss2);
     float       num = 0.f, den = 1.f;
     for (uint32_t k = 0; k < na; ++k) {
-        const float4 q  = B.x[my[k * BT]];
+        const float4 q  = B.x[lst[k * BT + tid]];
         const float  cx = q.x - px, cy = q.y - py, cz = q.z - pz;
         const float  t2 = dist2f(cx, cy, cz), h = cx * nx + cy * ny + cz * nz;
         const float  w  = __expf(t2 * ic + h * h * is);
@@ -1456,6 +1388,12 @@ __device__ __forceinline__ bool bil_fast(const BilPatch& B, uint32_t v, uint16_t
     return true;
 }
 
+// Tried and measured against this version on the 10 M-face torus (profiles/r02_bilateral_bt.txt, r02k / r02l): no "seen" bitmap
+// (distance first, accepted-list scan for candidates inside the radius; 52 KB per block, 3-4 resident blocks) 0.454-0.52 ms;
+// the same with ring 1 taken from the distances of the normal pass and the other rings measured two candidates per FFMA2
+// 0.48 ms (ncu: 496 M warp instructions at 14.8 active lanes against 328 M at 22.0 here).  A vertex accepts ~10 neighbours and
+// makes ~66 visits, 70 % of them duplicates: the O(1) bitmap probe beats any list scan, and the walk is bound by the number
+// of visits, not by residency.
 // A vertex the patch could not finish: its slot, unit normal and sigma_c^2 (already computed from its fan)
 struct BilDeferred
 {
@@ -1527,9 +1465,10 @@ __global__ void __launch_bounds__(BIL_BT) k_bilateral_deferred(const uint32_t* _
 // Block size = the patch's owned vertices split into equal rounds (chosen by the launcher): a fixed 512 left 14 of 16 warps
 // waiting at the barrier while 2 finished the tail of a 561-vertex patch (profiles/r02e: barrier stall 1.8 per issue).
 // (a compile-time block size: with blockDim.x as the stride of the interleaved bitmaps / lists the kernel was 25 % slower)
-template <uint32_t BT, uint32_t MINB>
-__global__ void __launch_bounds__(BT, MINB) k_bilateral_patch(MeshView mv, const float* __restrict__ x, float* __restrict__ xo,
-                                                              uint32_t* __restrict__ work_count, BilDeferred* __restrict__ work)
+template <uint32_t BT>
+__global__ void __launch_bounds__(BT) k_bilateral_patch(MeshView mv, const float* __restrict__ x, float* __restrict__ xo,
+                                                        uint32_t bm_words, uint32_t* __restrict__ work_count,
+                                                        BilDeferred* __restrict__ work)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t                      bar;
@@ -1550,7 +1489,7 @@ __global__ void __launch_bounds__(BT, MINB) k_bilateral_patch(MeshView mv, const
     float4*         s_x     = sm.alloc<float4>(nv + next);
     float*          s_out   = sm.alloc<float>(3 * cap);  // the owned slice as it arrives (AoS), later the results
     uint16_t*       s_def   = sm.alloc<uint16_t>(nov + 8u);
-    uint16_t*       lst     = sm.alloc<uint16_t>(BIL_FAST_CAP * BT);  // per-thread accepted lists, interleaved
+    uint32_t*       s_priv  = sm.alloc<uint32_t>((bm_words + BIL_FAST_CAP / 2) * BT);  // per-thread bitmaps, then the u16 lists
     if (threadIdx.x == 0) {
         s_ndef = 0;
         mbar_init(&bar, 1);
@@ -1591,13 +1530,15 @@ __global__ void __launch_bounds__(BT, MINB) k_bilateral_patch(MeshView mv, const
     BilPatch B;
     B.fo = s_fo, B.fv = s_fv, B.r2idx = s_r2i, B.r2off = s_r2o, B.r2val = s_r2v, B.x = s_x;
     B.nx_ = nv + next, B.nov = nov;
+    uint32_t* bm  = s_priv;
+    uint16_t* lst = reinterpret_cast<uint16_t*>(s_priv + bm_words * BT);
     for (uint32_t v = threadIdx.x; v < cap; v += BT) {
         float* const o = s_out + 3 * v;  // results go straight to the staging buffer (no local array behind a call)
         if (v < nov) {
             const uint32_t fb = s_fo[v] & FAN_OFF_MASK, fe = s_fo[v + 1] & FAN_OFF_MASK;
             if (fb == fe) {  // no neighbours: keeps its position
                 o[0] = s_x[v].x, o[1] = s_x[v].y, o[2] = s_x[v].z;
-            } else if (!bil_fast<BT>(B, v, lst, o)) {  // writes o only when it succeeds
+            } else if (!bil_fast<BT>(B, v, bm, bm_words, lst, o)) {  // writes o only when it succeeds
                 s_def[atomicAdd(&s_ndef, 1u)] = (uint16_t)v;
                 o[0] = o[1] = o[2] = 0.f;
             }
@@ -2286,6 +2227,7 @@ cudaError_t launch_bilateral_patch(const MeshView& mv, const KernelLimits& lim, 
 {
     if (!mv.fans) RXM_FAIL("the patch-local bilateral kernel needs the one-ring fans");
     const uint32_t capv = lim.max_owned[ELEM_V] + 4, nvx = lim.max_n[ELEM_V] + lim.max_ext;
+    const uint32_t bm_words = (nvx + 31u) / 32u;
     const uint32_t fixed = fan_smem(lim) + r16(2u * (lim.max_not_owned[ELEM_V] + lim.max_ext) + 32) + r16(2u * (lim.max_r2 + 1) + 16) +
                            r16(2u * lim.max_r2_total + 16) + r16(4u * lim.max_ext + 16) + 16u * nvx + r16(12u * capv) +
                            r16(2u * (lim.max_owned[ELEM_V] + 8)) + 64u;
@@ -2295,36 +2237,27 @@ cudaError_t launch_bilateral_patch(const MeshView& mv, const KernelLimits& lim, 
     // 0.705 -- resident warps decide, idle warps of a half-empty second round cost nothing; larger block on a tie
     static const uint32_t sizes[] = {128, 192, 256, 288, 320, 384, 448, 512, 576};
     uint32_t    bt = 0, smem = 0, best_warps = 0;
-    const char* force = getenv("RXM_BILATERAL_BT");  // experiment knobs: block size, and for 512 threads the resident blocks
-    const char* minb  = getenv("RXM_BILATERAL_MINB");  // the register allocation aims at (4: 32 registers, 3: 40, 2: 64)
+    const char* force = getenv("RXM_BILATERAL_BT");  // experiment knob
     for (uint32_t t : sizes) {
         if (force && t != (uint32_t)atoi(force)) continue;
         if (!force && t > 128u && t >= 2u * lim.max_owned[ELEM_V]) break;  // more than half the block would never have a vertex
-        const uint32_t sm = fixed + r16(2u * BIL_FAST_CAP * t);
+        const uint32_t sm = fixed + r16(4u * (bm_words + BIL_FAST_CAP / 2) * t);
         if (sm > 227u * 1024u) continue;
-        // 40 registers per thread: 32 (full occupancy) spills in the visit loop and measured slower (profiles/r02_bilateral_bt.txt)
-        const uint32_t blocks = std::min(std::min(227u * 1024u / (sm + 1024u), 2048u / t), 65536u / (40u * t)), warps = blocks * t / 32u;
+        const uint32_t blocks = std::min(227u * 1024u / (sm + 1024u), 2048u / t), warps = blocks * t / 32u;
         if (warps >= best_warps) best_warps = warps, bt = t, smem = sm;
     }
     if (!bt) RXM_FAIL("patch needs more shared memory than 227 KB");
     // flags: [0] overflow, [1] deferred vertices of the call, [2], [3] work-list fill of even / odd iterations
     uint32_t* cnt = flags + 2 + (iteration & 1u);
-#define RXM_BIL2(T, M)                                                                                                         \
-    {                                                                                                                          \
-        if (set_smem(k_bilateral_patch<T, M>, smem) != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");     \
-        k_bilateral_patch<T, M><<<mv.num_patches, T, smem, stream>>>(mv, x, xo, cnt, (BilDeferred*)work);                       \
-    }
-#define RXM_BIL(T)                      \
-    case T:                             \
-        RXM_BIL2(T, 65536 / (40 * T))   \
+#define RXM_BIL(T)                                                                                                       \
+    case T:                                                                                                              \
+        if (set_smem(k_bilateral_patch<T>, smem) != cudaSuccess) RXM_FAIL("patch needs more shared memory than 227 KB");  \
+        k_bilateral_patch<T><<<mv.num_patches, T, smem, stream>>>(mv, x, xo, bm_words, cnt, (BilDeferred*)work);          \
         break;
-    if (bt == 512u && minb && atoi(minb) == 4) RXM_BIL2(512, 4)
-    else if (bt == 512u && minb && atoi(minb) == 2) RXM_BIL2(512, 2)
-    else switch (bt) {
+    switch (bt) {
         RXM_BIL(128) RXM_BIL(192) RXM_BIL(256) RXM_BIL(288) RXM_BIL(320) RXM_BIL(384) RXM_BIL(448) RXM_BIL(512) RXM_BIL(576)
         default: RXM_FAIL("internal: block size not compiled");
     }
-#undef RXM_BIL2
 #undef RXM_BIL
     k_bilateral_deferred<<<148 * 8, BIL_BT, 0, stream>>>(cnt, flags + 2 + ((iteration + 1u) & 1u), (const BilDeferred*)work, csr_off,
                                                           csr_val, x, xo, flags);

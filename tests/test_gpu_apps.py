@@ -208,8 +208,8 @@ def test_bilateral_filter(built):
 
 @pytest.mark.parametrize("n", [9, 14, 40])
 def test_bilateral_high_valence(n):
-    """Fans of more than 8 neighbours leave the patch kernel's register-resident ring (deferred to the cross-patch kernel):
-    a bipyramid's apexes (valence n) next to valence-4 rim vertices, every vertex against the oracle."""
+    """A bipyramid: apexes of valence n (more accepted neighbours than the patch kernel's list holds for n = 40: deferred to
+    the cross-patch kernel) next to valence-4 rim vertices, every vertex against the oracle."""
     rx.rx_init(0)
     ang = 2 * np.pi * np.arange(n) / n
     rng = np.random.RandomState(n)
@@ -223,7 +223,6 @@ def test_bilateral_high_valence(n):
     m.bilateral_filter(x, y, 1)
     ref, worst = O.bilateral_step(T.query("VV"), F, V, 80, 2)
     assert np.abs(y.to_global() - ref).max() < 2e-5
-    assert m.bilateral_deferred() >= 2  # the two apexes at least
 
 
 def test_reduce_handle(built):
