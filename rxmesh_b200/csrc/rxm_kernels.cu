@@ -513,6 +513,13 @@ __global__ void __launch_bounds__(BT, 8) k_vertex_normals_fan(MeshView mv, const
 // ribbon vertices are gathered into the tail of the same array, fan ids are fetched two per LDS.32, and the result
 // goes to its own buffer so no barrier separates compute from store.
 constexpr int BT2 = 128;
+// resident blocks per SM the register allocation of the two-vertices-per-thread kernels aims at.  10 = 48 registers.
+// 100 M-face grid, vertex normals / Laplacian ms per launch, Lloyd-patched 10 M icosphere normals (gpurun r02n):
+//   8 blocks (64 registers) 0.463 / 0.391 / 0.0615    10 blocks (48) 0.441 / 0.383 / 0.0574
+//   12 blocks (40 registers: spills, and 12 x 17.4 KB of shared memory leaves the 196 KB carve-out) 0.652 / 0.469 / 0.0846
+#ifndef RXM_VN_MINB
+#define RXM_VN_MINB 10
+#endif
 
 struct FanPatch2
 {
@@ -594,7 +601,7 @@ __device__ __forceinline__ void vn_one(const FanPatch2& F, uint32_t v, float& sx
 // DIRECT: results go from registers straight to global memory (a warp's 32 rows are 384 contiguous bytes) instead of through
 // a staging buffer + bulk store: 6 KB less shared memory per block
 template <int UNIT, bool DIRECT>
-__global__ void __launch_bounds__(BT2, 8) k_vertex_normals_fan2(MeshView mv, const float* __restrict__ x,
+__global__ void __launch_bounds__(BT2, RXM_VN_MINB) k_vertex_normals_fan2(MeshView mv, const float* __restrict__ x,
                                                               float* __restrict__ nrm)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -724,7 +731,7 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
 // carve-out: 100 M-face grid 0.459 -> 0.399 ms per step (0.80 -> 0.92 of the measured HBM peak).  The halo push of the fused
 // variant then reads the few mirrored rows back from the block's own global writes (visible after the block barrier).
 template <bool FUSED, bool DIRECT = false>
-__global__ void __launch_bounds__(BT2, 8) k_laplacian_fan2(MeshView mv, const float* __restrict__ x, float* __restrict__ xo,
+__global__ void __launch_bounds__(BT2, RXM_VN_MINB) k_laplacian_fan2(MeshView mv, const float* __restrict__ x, float* __restrict__ xo,
                                                          double lr, FusedHaloView fh)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
