@@ -125,15 +125,34 @@ void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_
     num_patches = 0;
     if (nf == 0) return;
     // edge -> faces CSR
-    std::vector<uint32_t> ef_off((size_t)ne + 1, 0), ef_val(3ull * nf);
-    for (uint64_t i = 0; i < 3ull * nf; ++i)
-        ef_off[fe[i]]++;
+    // (all cores: counts and cursors by relaxed atomics, then every edge's short list is sorted -- the ascending face order
+    // the serial fill in face order produces; 100 M faces: 3.5 s -> under 1 s of the patcher's time)
+    U32Buf ef_off((size_t)ne + 1), ef_val(3ull * nf);
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e <= (int64_t)ne; ++e)
+        ef_off[e] = 0;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)(3ull * nf); ++i)
+        __atomic_fetch_add(&ef_off[fe[i]], 1u, __ATOMIC_RELAXED);
     exclusive_scan(ef_off);
     {
-        std::vector<uint32_t> cur(ef_off.begin(), ef_off.end() - 1);
-        for (uint32_t f = 0; f < nf; ++f)
-            for (int j = 0; j < 3; ++j)
-                ef_val[cur[fe[3ull * f + j]]++] = f;
+        U32Buf cur((size_t)ne);
+#pragma omp parallel for schedule(static)
+        for (int64_t e = 0; e < (int64_t)ne; ++e)
+            cur[e] = ef_off[e];
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < (int64_t)(3ull * nf); ++i)
+            ef_val[__atomic_fetch_add(&cur[fe[i]], 1u, __ATOMIC_RELAXED)] = (uint32_t)(i / 3);
+#pragma omp parallel for schedule(static)
+        for (int64_t e = 0; e < (int64_t)ne; ++e) {
+            uint32_t* b = &ef_val[ef_off[e]];
+            const uint32_t n = ef_off[e + 1] - ef_off[e];
+            if (n == 2) {
+                if (b[1] < b[0]) std::swap(b[0], b[1]);
+            } else if (n > 2) {
+                std::sort(b, b + n);
+            }
+        }
     }
     // face -> adjacent faces CSR (one indirection per visit instead of face -> edge -> faces)
     std::vector<uint32_t> ff_off((size_t)nf + 1, 0);
@@ -158,8 +177,8 @@ void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_
                 if (ef_val[i] != (uint32_t)f) ff_val[w++] = ef_val[i];
         }
     }
-    std::vector<uint32_t>().swap(ef_off);
-    std::vector<uint32_t>().swap(ef_val);
+    U32Buf().swap(ef_off);
+    U32Buf().swap(ef_val);
     auto for_each_nbr = [&](uint32_t f, auto&& fn) {
         for (uint32_t i = ff_off[f]; i < ff_off[f + 1]; ++i)
             fn(ff_val[i]);
@@ -525,19 +544,36 @@ void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_
 static void reorder_patches_bfs(const uint32_t* fe, uint32_t nf, uint32_t ne, std::vector<uint32_t>& fpatch, uint32_t P)
 {
     // patch adjacency: an edge whose faces lie in different patches
-    std::vector<uint32_t> first(ne, INVALID32_);
-    std::vector<uint64_t> pairs;
-    for (uint32_t f = 0; f < nf; ++f)
-        for (int j = 0; j < 3; ++j) {
-            const uint32_t e = fe[3ull * f + j];
-            if (first[e] == INVALID32_) {
-                first[e] = f;
-            } else {
-                const uint32_t a = fpatch[first[e]], b = fpatch[f];
-                if (a != b) pairs.push_back(((uint64_t)a << 32) | b), pairs.push_back(((uint64_t)b << 32) | a);
-            }
+    // first[e] = the smallest face on edge e; every other face of the edge is paired with it (all cores; the pair SET is what
+    // counts: it is sorted and made unique below)
+    U32Buf first((size_t)ne);
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < (int64_t)ne; ++e)
+        first[e] = INVALID32_;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)(3ull * nf); ++i) {
+        const uint32_t f   = (uint32_t)(i / 3);
+        uint32_t       old = __atomic_load_n(&first[fe[i]], __ATOMIC_RELAXED);
+        while (f < old && !__atomic_compare_exchange_n(&first[fe[i]], &old, f, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
         }
-    std::vector<uint32_t>().swap(first);
+    }
+    std::vector<uint64_t> pairs;
+#pragma omp parallel
+    {
+        std::vector<uint64_t> mine;
+#pragma omp for schedule(static) nowait
+        for (int64_t i = 0; i < (int64_t)(3ull * nf); ++i) {
+            const uint32_t f = (uint32_t)(i / 3), g = first[fe[i]];
+            if (g == f) continue;
+            const uint32_t a = fpatch[g], b = fpatch[f];
+            if (a != b) mine.push_back(((uint64_t)a << 32) | b), mine.push_back(((uint64_t)b << 32) | a);
+        }
+        std::sort(mine.begin(), mine.end());
+        mine.erase(std::unique(mine.begin(), mine.end()), mine.end());
+#pragma omp critical
+        pairs.insert(pairs.end(), mine.begin(), mine.end());
+    }
+    U32Buf().swap(first);
     std::sort(pairs.begin(), pairs.end());
     pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
     std::vector<uint32_t> off((size_t)P + 1, 0);

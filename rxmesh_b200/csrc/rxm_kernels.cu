@@ -18,6 +18,7 @@
 // One thread block per patch; every patch section and the patch's owned attribute
 // slice arrive by TMA bulk copies under one mbarrier phase.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -28,7 +29,7 @@
 
 namespace rxm {
 
-static uint64_t g_launches = 0;
+static std::atomic<uint64_t> g_launches{0};  // launches may be queued from several host threads (rxm_multi.cu)
 uint64_t        launch_counter()
 {
     return g_launches;
