@@ -85,14 +85,15 @@ struct Query
         // not-owned source when allow_not_owned
         const uint32_t words = (m_r.n_src + 31u) / 32u;
         m_participant        = shrd_alloc.template alloc<uint32_t>(words ? words : 1u);
-        for (uint32_t w = threadIdx.x; w < words; w += blockThreads) {
-            uint32_t bits = 0;
-            for (uint32_t b = 0; b < 32u && 32u * w + b < m_r.n_src; ++b) {
-                const uint32_t s = 32u * w + b;
-                if (s >= m_desc.n_owned[InH::elem] || compute_active_set(InH(m_desc.patch_id, typename InH::LocalT((uint16_t)s))))
-                    bits |= 1u << b;
-            }
-            m_participant[w] = bits;
+        // one source per lane, one ballot per word (blockThreads is a multiple of 32, so the 32 sources of a word always
+        // sit in the lanes of one warp; every lane of the warp runs the same number of rounds)
+        static_assert(blockThreads % 32u == 0, "Query<blockThreads>: whole warps");
+        for (uint32_t s0 = threadIdx.x & ~31u; s0 < 32u * words; s0 += blockThreads) {
+            const uint32_t s  = s0 + (threadIdx.x & 31u);
+            const bool     in = s < m_r.n_src && (s >= m_desc.n_owned[InH::elem] ||
+                                              compute_active_set(InH(m_desc.patch_id, typename InH::LocalT((uint16_t)s))));
+            const uint32_t bits = __ballot_sync(0xFFFFFFFFu, in);
+            if ((threadIdx.x & 31u) == 0) m_participant[s0 >> 5] = bits;
         }
         __syncthreads();
     }
