@@ -256,6 +256,54 @@ def run_reference(args, rank):
 METRIC = "faces/s through one VV-query + VF-query + vertex-normal pass (100M-face grid); per-kernel entries/s, faces/s and HBM fraction in `kernels`"
 
 
+def headline_oracle_check(n, mesh, rx, sv_in, sv_out, sf_in, nrm, in_v, in_f, stream, torch):
+    """What the timed kernels left in their output attributes (vertex normals, VF consume) plus one more VV consume, against
+    the oracle on 81 x 81-vertex windows of the n x n grid (corners, edges, centre); vertices on a window side that is a cut
+    through the mesh, not a mesh border, lack neighbours inside the window and are left out."""
+    from bench_configs import grid_window
+    from oracle import oracle as O
+    got_vn = nrm.to_global()
+    got_vf = sv_out.to_global().reshape(-1)  # the step's last query
+    mesh.query_consume(rx.Op.VV, sv_in, sv_out, stream)
+    torch.cuda.synchronize()
+    got_vv = sv_out.to_global().reshape(-1)
+    worst = {"VV": 0.0, "VF": 0.0, "VN": 0.0}
+    cnt = 0
+    for r0 in (0, n // 2 - 40, n - 81):
+        for c0 in (0, n // 2 - 40, n - 81):
+            r1, c1 = r0 + 80, c0 + 80
+            Vw, Fw, gid = grid_window(n, r0, r1, c0, c1)
+            h, w = r1 - r0 + 1, c1 - c0 + 1
+            ok = np.ones((h, w), bool)
+            if r0 > 0:
+                ok[0, :] = False
+            if r1 < n - 1:
+                ok[-1, :] = False
+            if c0 > 0:
+                ok[:, 0] = False
+            if c1 < n - 1:
+                ok[:, -1] = False
+            sel = ok.reshape(-1)
+            T = O.Topology(Fw)
+            lq = np.arange((h - 1) * (w - 1), dtype=np.int64)
+            gq = (r0 + lq // (w - 1)) * (n - 1) + c0 + lq % (w - 1)
+            gf = np.stack([2 * gq, 2 * gq + 1], 1).reshape(-1)  # global ids of the window's faces, in its face order
+            for name, op, src, got in (("VV", "VV", in_v[gid].astype(np.float64), got_vv), ("VF", "VF", in_f[gf].astype(np.float64), got_vf)):
+                off, val = T.query(op)
+                ref = np.add.reduceat(np.concatenate([src[val], [0.0]]), np.minimum(off[:-1], val.shape[0]))
+                ref[np.diff(off) == 0] = 0.0
+                d = np.abs(got[gid][sel] - ref[sel]) / np.maximum(np.abs(ref[sel]), 1e-30)
+                worst[name] = max(worst[name], float(d.max()))
+            refn = O.vertex_normals(Fw, Vw, np.float64)
+            d = np.linalg.norm(got_vn[gid][sel] - refn[sel], axis=1) / np.maximum(np.linalg.norm(refn[sel], axis=1), 1e-30)
+            worst["VN"] = max(worst["VN"], float(d.max()))
+            cnt += int(sel.sum())
+    tol = {"VV": 1e-6, "VF": 1e-6, "VN": 1e-5}
+    return {"what": "results of the timed kernels on the full mesh against the oracle, nine 81 x 81-vertex windows (corners, "
+                    "edges, centre), relative error", "vertices_checked": cnt, "max_rel_err": worst, "tolerance_rel": tol,
+            "ok": bool(all(worst[k] <= tol[k] for k in tol))}
+
+
 def config_dict(args, n, faces, mesh):
     c = {"workload": "VV + VF query (consume) + vertex normals on a %d x %d procedurally generated grid "
                      "(create_plane semantics + height field), %d faces per GPU" % (n, n, faces),
@@ -407,6 +455,11 @@ def run_ours(args, rank, world, local_rank):
     total_ms = evs[0][0].elapsed_time(evs[-1][3])
     k_ms = [sum(e[i].elapsed_time(e[i + 1]) for e in evs) / args.steps for i in range(3)]
 
+    # ---- the timed kernels' results against the oracle, at full size, on windows of the grid (N = 1) ----
+    parity = None
+    if world == 1 and not args.no_cpu:
+        parity = headline_oracle_check(n, mesh, rx, sv_in, sv_out, sf_in, nrm, h_sv.numpy(), h_sf.numpy(), stream, torch)
+
     # ---- end to end through the C ABI with pinned HOST buffers (H2D + kernel + D2H per call) ----
     h_n = torch.empty((nV, 3), dtype=torch.float32).pin_memory()
     h_o1 = torch.empty(nV, dtype=torch.float32).pin_memory()
@@ -524,6 +577,8 @@ def run_ours(args, rank, world, local_rank):
         "wall_ms_per_step": t_wall / args.steps * 1e3, "build_seconds": t_build,
         "host_peak_rss_gb": __import__("resource").getrusage(__import__("resource").RUSAGE_SELF).ru_maxrss / 1048576.0,
     }
+    if parity is not None:
+        line["parity"] = parity
     if world == 1 and not args.no_cpu:
         cb, _ = cpu_baseline(min(args.faces, args.cpu_sample_faces), 3)
         line["cpu_baseline"] = cb
