@@ -243,6 +243,8 @@ int rxm_mesh_pipe_plan(rxm_mesh* m, uint32_t chunks, uint32_t* pb, uint64_t* up_
 typedef struct rxm_fused_halo rxm_fused_halo;
 int   rxm_fused_halo_create(rxm_mesh* m, uint32_t npeers, rxm_fused_halo** out);
 void* rxm_fused_halo_flags(rxm_fused_halo* h);
+/* blocks of a fused step that wait for neighbour flags or push rows (known after rxm_fused_halo_set) */
+uint32_t rxm_fused_halo_sync_blocks(const rxm_fused_halo* h);
 int   rxm_fused_halo_set(rxm_fused_halo* h, const uint32_t* push_off, const uint32_t* push_lid_peer, const uint32_t* push_slot,
                          uint64_t n_push, void* const* peer_attr_a, void* const* peer_attr_b, void* const* peer_flag);
 void  rxm_fused_halo_destroy(rxm_fused_halo* h);

@@ -92,6 +92,7 @@ SYMBOLS = {
     "rxm_mesh_pipe_plan": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rxm_fused_halo_create": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]),
     "rxm_fused_halo_flags": (C.c_void_p, [C.c_void_p]),
+    "rxm_fused_halo_sync_blocks": (C.c_uint32, [C.c_void_p]),
     "rxm_fused_halo_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                      C.c_void_p]),
     "rxm_fused_halo_destroy": (None, [C.c_void_p]),

@@ -1398,6 +1398,11 @@ void* rxm_fused_halo_flags(rxm_fused_halo* h)
     return h ? h->d_flags : nullptr;
 }
 
+uint32_t rxm_fused_halo_sync_blocks(const rxm_fused_halo* h)
+{
+    return h ? h->n_sync_blocks : 0u;
+}
+
 // push lists: for patch index p the entries [push_off[p], push_off[p+1]) of (local vertex id | neighbour << 16) and the
 // slot on that neighbour; peer_attr_a / _b: neighbour-side base pointers (rxm_ipc_open) of the two attributes the
 // iteration ping-pongs between; peer_flag: neighbour-side address of the flag word this rank raises

@@ -279,6 +279,18 @@ int rxm_multi_create(const uint32_t* fv, uint32_t num_faces, const uint32_t* fac
         }
         int rc = rxm_fused_halo_set(S.halo, off.data(), lp.data(), slot.data(), ent.size(), pa.data(), pb.data(), pf.data());
         if (rc) return fail_free(rc);
+        // Shards that SHARE a device (tests, debugging): a fused step's boundary blocks spin until the neighbour's previous
+        // step has raised its flags.  If that neighbour runs on the same device and the spinning blocks could fill it, the
+        // neighbour's kernel might never be scheduled.  Refuse such plans instead of risking a hang.
+        bool shared = false;
+        for (int q = 0; q < num_shards; ++q)
+            shared |= q != r && M->sh[q].device == S.device;
+        if (shared && rxm_fused_halo_sync_blocks(S.halo) > 592u) {
+            rxm_set_last_error(RXM_ERR_UNSUPPORTED,
+                               "rxm_multi: shards that share a device have too many boundary patches (more than 592 waiting blocks "
+                               "per step could keep the neighbour's kernel off the device): give every shard its own device");
+            return fail_free(RXM_ERR_UNSUPPORTED);
+        }
     }
     *out = M;
     return RXM_OK;
