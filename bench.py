@@ -394,7 +394,9 @@ def run_ours(args, rank, world, local_rank):
         return run_laplacian(args, rank, world, local_rank, mesh, x, nrm, hx_v, nV if world == 1 else None,
                              n, t_build, torch, rx, stream, fused)
 
-    comm = torch.cuda.Stream() if hx_v is not None else None
+    # high priority: the exchange's small kernels (gather, NCCL send/recv, scatter) are scheduled as soon as a block slot frees
+    # up instead of behind the ~100 000 blocks the query kernel of the same step still has to dispatch
+    comm = torch.cuda.Stream(priority=-1) if hx_v is not None else None
 
     def step(evs=None):
         if evs:

@@ -180,3 +180,24 @@ def test_cpp_multi_header_run(tmp_path):
     for devs in lists:
         r = subprocess.run([exe, "run", devs], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and r.stdout.startswith("ok"), (devs, r.stdout, r.stderr)
+
+
+@pytest.mark.gpu
+def test_same_device_shards_with_a_long_cut_are_refused():
+    """Shards on ONE device exist for tests: a fused step's boundary blocks spin on flags the neighbour's kernel raises, so a
+    plan whose waiting blocks could fill the device is refused instead of risking a hang; on separate devices it is fine."""
+    import torch
+    import rxmesh_b200 as rx
+    from rxmesh_b200 import meshio
+    from rxmesh_b200.multi import RXMeshMulti
+    rx.rx_init(0)
+    nx, ny = 6001, 65
+    V, F = meshio.grid(nx, ny)
+    fp = meshio.grid_face_tiles(nx, ny, 8, 8)  # row-major 8 x 8-quad tiles: the cut between two shards runs along 750 tiles
+    with pytest.raises(RuntimeError, match="share a device"):
+        RXMeshMulti(F, [0, 0], face_patch=fp, patch_size=128)
+    if torch.cuda.device_count() >= 2:
+        mm = RXMeshMulti(F, [0, 1], face_patch=fp, patch_size=128)
+        one = RXMeshMulti(F, [0], face_patch=fp, patch_size=128)
+        Vf = V.astype(np.float32)
+        assert np.array_equal(mm.laplacian_smooth(Vf, 0.01, 10), one.laplacian_smooth(Vf, 0.01, 10))
