@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librxmesh_b200.so")
+# RXM_LIB: another build of the same library (kernel tuning experiments: make NVFLAGS+=-DRXM_BT2=160 OUT=...)
+LIB_PATH = os.environ.get("RXM_LIB") or os.path.join(_HERE, "librxmesh_b200.so")
 
 u32p = C.POINTER(C.c_uint32)
 u16p = C.POINTER(C.c_uint16)

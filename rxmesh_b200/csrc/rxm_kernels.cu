@@ -513,7 +513,13 @@ __global__ void __launch_bounds__(BT, 8) k_vertex_normals_fan(MeshView mv, const
 // 12-byte stride = 3 conflict-free wavefronts; the old float4 copy cost 4 per gather plus the conversion pass),
 // ribbon vertices are gathered into the tail of the same array, fan ids are fetched two per LDS.32, and the result
 // goes to its own buffer so no barrier separates compute from store.
-constexpr int BT2 = 128;
+#ifndef RXM_BT2
+#define RXM_BT2 128
+#endif
+constexpr int BT2 = RXM_BT2;  // block size of the two-vertices-per-thread kernels.  Measured (gpurun r02u; 100 M-face grid VN /
+                              // Laplacian ms, Lloyd-patched icosphere VN): 128 x 10 blocks 0.440 / 0.383 / 0.0574, 160 x 8 (two
+                              // rounds instead of three for a 561-vertex tile) 0.461 / 0.402 / 0.0606, 192 x 6 0.519 / 0.473 /
+                              // 0.0697, 96 x 13 0.473 / 0.438 / 0.0684: more, smaller blocks overlap their phases better
 // resident blocks per SM the register allocation of the two-vertices-per-thread kernels aims at.  10 = 48 registers.
 // 100 M-face grid, vertex normals / Laplacian ms per launch, Lloyd-patched 10 M icosphere normals (gpurun r02n):
 //   8 blocks (64 registers) 0.463 / 0.391 / 0.0615    10 blocks (48) 0.441 / 0.383 / 0.0574
