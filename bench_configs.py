@@ -261,7 +261,22 @@ def config_bilateral(torch, rx, stream, nu=2236, iters=5):
         worst = max(worst, float(err.max()))
         n_chk += int(sel.sum())
     tol = 2e-5 * scale
+    # the CPU beside it (north_star): one iteration of the restated filter (oracle port; the reference's CPU side is OpenMesh +
+    # OpenMP schedule(static), filtering_openmesh.h:112-116, OpenMesh is not in the tree) on a bounded sample of the same
+    # generator, one thread and all host threads
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ns = 700
+    Vs, Fs = meshio.torus(ns, ns, noise=0.2)
+    vvs = O.Topology(Fs).query("VV")
+    _, t1 = O.bilateral_step_mt(vvs, Fs, Vs, 1)
+    _, tn = O.bilateral_step_mt(vvs, Fs, Vs, ncpu)
+    _, tn2 = O.bilateral_step_mt(vvs, Fs, Vs, ncpu)
+    tn = min(tn, tn2)
+    cpu = {"value": Vs.shape[0] / min(t1, tn), "unit": "vertex-iterations/s", "cores": ncpu if tn < t1 else 1, "kind": "port",
+           "sample": "%d-face torus of the same generator (%d^2 quads), one iteration of the filter (normals excluded): "
+                     "1 thread %.3g, %d threads %.3g vertex-iterations/s" % (Fs.shape[0], ns, Vs.shape[0] / t1, ncpu, Vs.shape[0] / tn)}
     return {"what": "bilateral filtering, %d-face torus (%d^2 quads), %d iterations (unit-face normals + filter)" % (nF, nu, iters),
+            "cpu_baseline": cpu,
             "faces": nF, "patches": m.get_num_patches(), "patch_tile_quads": "%dx%d" % (tj, ti), "build_seconds": tb, "ms_total": ms,
             "ms_per_iteration": ms / iters,
             "vertex_iterations_per_s": nV * iters / (ms * 1e-3), "alg_bytes_per_iteration": 54.0 * nF,
@@ -503,6 +518,21 @@ def laplacian_400m(args, rank, world, local_rank, torch, rx, tile, tile_i):
                    "windows": "81 x 81-vertex windows at rows %s (cuts between ranks included) x 3 column positions" % rows,
                    "ok": bool(worst < 1e-5 and worst_y < 1e-6 and cnt > 0 and bit_ok)},
     }
+    if rank == 0:
+        # the CPU beside it: the manual smoothing step (oracle port; the reference app has no CPU side) on a bounded sample of
+        # the same generator, one thread and all host threads
+        try:
+            from oracle import oracle as O
+            ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            Vs, Fs, _ = grid_window(1415, 0, 1414, 0, 1414)
+            vvs = O.Topology(Fs).query("VV")
+            _, t1 = O.laplacian_step_mt(vvs, Vs, LAP_LR, 1)
+            tn = min(O.laplacian_step_mt(vvs, Vs, LAP_LR, ncpu)[1] for _ in range(3))
+            rec["cpu_baseline"] = {"value": Vs.shape[0] / min(t1, tn), "unit": "vertex-updates/s", "cores": ncpu if tn < t1 else 1,
+                                   "kind": "port", "sample": "1415 x 1415 grid (%d faces) of the same generator, one step: 1 thread "
+                                   "%.3g, %d threads %.3g vertex-updates/s" % (Fs.shape[0], Vs.shape[0] / t1, ncpu, Vs.shape[0] / tn)}
+        except Exception as e:  # noqa: BLE001
+            rec["cpu_baseline"] = {"unavailable": str(e)[:200]}
     # speed-up against this configuration's own N = 1 run: same lease when bench.py ran N = 1 before (the scaling run does)
     if world == 1:
         try:

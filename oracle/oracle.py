@@ -227,6 +227,32 @@ def bilateral_step(vv, fv, x, max_nbrs=80, use_f64=True):
     return out, int(worst)
 
 
+def bilateral_step_mt(vv, fv, x, threads, max_nbrs=80, use_f64=2):
+    """rxo_bilateral_step_mt: the same iteration, vertices split statically over `threads` OpenMP threads (the reference's CPU
+    side of the app: filtering_openmesh.h:112-116).  Returns (x_new, seconds of the filter step alone, normals excluded)."""
+    import time
+    off, val = vv
+    x = _f32(x).reshape(-1, 3)
+    n = vertex_normals_unit_faces(fv, x, np.float64)
+    out = np.empty_like(x)
+    fn = lib().rxo_bilateral_step_mt
+    fn.restype = C.c_uint32
+    t = time.perf_counter()
+    fn(_p(off, u32p), _p(val, u32p), x.shape[0], _p(x, f32p), _p(n, f64p), _p(out, f32p), int(max_nbrs), int(use_f64), int(threads))
+    return out, time.perf_counter() - t
+
+
+def laplacian_step_mt(vv, x, lr, threads):
+    """rxo_laplacian_step_f32_mt -> (x_new, seconds)."""
+    import time
+    off, val = vv
+    x = _f32(x).reshape(-1, 3)
+    out = np.empty_like(x)
+    t = time.perf_counter()
+    lib().rxo_laplacian_step_f32_mt(_p(off, u32p), _p(val, u32p), x.shape[0], _p(x, f32p), _p(out, f32p), C.c_double(lr), int(threads))
+    return out, time.perf_counter() - t
+
+
 def consume_sum(csr, src):
     """rxo_consume_sum: out[s] = sum_{t in list(s)} src[t] in float64."""
     off, val = csr

@@ -28,6 +28,7 @@
  *                8.1 is not in the tree).
  */
 #include <math.h>
+#include <omp.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -433,13 +434,13 @@ static double rxo_dist2_f32(const float* a, const float* b)
     return (double)fmaf(dz, dz, fmaf(dy, dy, dx * dx));
 }
 
-uint32_t rxo_bilateral_step(const uint32_t* vv_off, const uint32_t* vv_val, uint32_t nv,
-                            const float* x, const double* normals, float* x_out,
-                            uint32_t max_nbrs, int use_f64)
+static uint32_t rxo_bilateral_range(const uint32_t* vv_off, const uint32_t* vv_val, uint32_t v_begin, uint32_t v_end,
+                                    const float* x, const double* normals, float* x_out,
+                                    uint32_t max_nbrs, int use_f64)
 {
     uint32_t* list = (uint32_t*)malloc((size_t)(max_nbrs + 1) * sizeof(uint32_t));
     uint32_t  worst = 0;
-    for (uint32_t v = 0; v < nv; ++v) {
+    for (uint32_t v = v_begin; v < v_end; ++v) {
         double p[3], n[3];
         for (int c = 0; c < 3; ++c) {
             p[c] = x[3 * (uint64_t)v + c];
@@ -520,6 +521,51 @@ uint32_t rxo_bilateral_step(const uint32_t* vv_off, const uint32_t* vv_val, uint
     }
     free(list);
     return worst;
+}
+
+uint32_t rxo_bilateral_step(const uint32_t* vv_off, const uint32_t* vv_val, uint32_t nv,
+                            const float* x, const double* normals, float* x_out,
+                            uint32_t max_nbrs, int use_f64)
+{
+    return rxo_bilateral_range(vv_off, vv_val, 0, nv, x, normals, x_out, max_nbrs, use_f64);
+}
+
+/* the same iteration over `threads` OpenMP threads, vertices split statically as the reference's CPU side of the app     */
+/* does (apps/Filtering/filtering_openmesh.h:112-116: omp parallel for schedule(static)); every vertex is independent, so  */
+/* the result is the serial one bit for bit.  Used as the CPU baseline of bench_configs.py.                               */
+uint32_t rxo_bilateral_step_mt(const uint32_t* vv_off, const uint32_t* vv_val, uint32_t nv,
+                               const float* x, const double* normals, float* x_out,
+                               uint32_t max_nbrs, int use_f64, int threads)
+{
+    uint32_t worst = 0;
+    if (threads < 1) threads = 1;
+#pragma omp parallel num_threads(threads) reduction(max : worst)
+    {
+        const int      t = omp_get_thread_num(), T = omp_get_num_threads();
+        const uint32_t b = (uint32_t)((uint64_t)nv * t / T), e = (uint32_t)((uint64_t)nv * (t + 1) / T);
+        const uint32_t w = rxo_bilateral_range(vv_off, vv_val, b, e, x, normals, x_out, max_nbrs, use_f64);
+        if (w > worst) worst = w;
+    }
+    return worst;
+}
+
+/* manual smoothing step (rxo_laplacian_step_f32) over `threads` OpenMP threads; the reference app has no CPU side, the     */
+/* split over vertices is the obvious one.  Bit-identical to the serial step.                                             */
+void rxo_laplacian_step_f32_mt(const uint32_t* vv_off, const uint32_t* vv_val, uint32_t nv,
+                               const float* x_in, float* x_out, double lr, int threads)
+{
+    if (threads < 1) threads = 1;
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (int64_t v = 0; v < (int64_t)nv; ++v) {
+        float g[3] = {0.f, 0.f, 0.f};
+        for (uint32_t i = vv_off[v]; i < vv_off[v + 1]; ++i) {
+            uint32_t u = vv_val[i];
+            for (int c = 0; c < 3; ++c)
+                g[c] += 2 * (x_in[3 * (uint64_t)v + c] - x_in[3 * (uint64_t)u + c]);
+        }
+        for (int c = 0; c < 3; ++c)
+            x_out[3 * (uint64_t)v + c] = (float)((double)x_in[3 * (uint64_t)v + c] - lr * (double)g[c]);
+    }
 }
 
 /* ------------------------------------------------------------------------ */

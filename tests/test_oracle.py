@@ -178,3 +178,18 @@ def test_mcf_matvec_constant_vector():
     assert np.all(k > 0)
     assert np.allclose(out10, k[:, None] * vin.astype(np.float64), rtol=1e-7, atol=1e-9)
     assert np.allclose(out10, out1, rtol=1e-6, atol=1e-8)  # independent of the time step
+
+
+def test_mt_ports_equal_the_serial_oracle():
+    """The OpenMP forms used as CPU baselines (bilateral filter split over vertices like filtering_openmesh.h:112-116, the
+    manual-smoothing step) give the serial oracle's result bit for bit, for any thread count."""
+    from rxmesh_b200 import meshio
+    V, F = meshio.torus(60, 44, noise=0.2)
+    vv = O.Topology(F).query("VV")
+    ref, _ = O.bilateral_step(vv, F, V, 80, 2)
+    lap = O.laplacian_step(vv, V, 0.01, np.float32)
+    for threads in (1, 3, 8):
+        got, _ = O.bilateral_step_mt(vv, F, V, threads)
+        assert np.array_equal(got, ref)
+        got, _ = O.laplacian_step_mt(vv, V, 0.01, threads)
+        assert np.array_equal(got, lap)
