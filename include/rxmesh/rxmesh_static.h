@@ -273,6 +273,11 @@ class RXMeshStatic
         }
         avg_p = (uint32_t)((float)sum / (float)get_num_patches());
     }
+    // Patcher statistics the reference reports (rxmesh.h:242-262, patcher/patcher.h:95-113): connected components of the
+    // input, assignment passes of the Lloyd patcher, patching time in milliseconds
+    uint32_t get_num_components() const { return info(RXM_INFO_NUM_COMPONENTS); }
+    uint32_t get_num_lloyd_run() const { return info(RXM_INFO_LLOYD_RUNS); }
+    float    get_patching_time() const { return (float)(1e3 * rxm_mesh_build_seconds(m_mesh, 1)); }
     double get_ribbon_overhead() const
     {
         return 100.0 * (double(info(RXM_INFO_TOTAL_LOCAL_F)) - double(get_num_faces())) / double(get_num_faces());

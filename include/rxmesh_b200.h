@@ -79,7 +79,9 @@ enum {
     RXM_INFO_NUM_SLOTS_V = 13, RXM_INFO_NUM_SLOTS_E = 14, RXM_INFO_NUM_SLOTS_F = 15,
     RXM_INFO_TOPO_BYTES = 16, RXM_INFO_TOTAL_LOCAL_V = 17, RXM_INFO_TOTAL_LOCAL_E = 18,
     RXM_INFO_TOTAL_LOCAL_F = 19, RXM_INFO_MAX_STASH = 20, RXM_INFO_ON_DEVICE = 21, RXM_INFO_PACKED = 22,
-    RXM_INFO_FANS = 23, RXM_INFO_RING2 = 24
+    RXM_INFO_FANS = 23, RXM_INFO_RING2 = 24,
+    RXM_INFO_LLOYD_RUNS = 25,     /* Patcher::get_num_lloyd_run: assignment passes of the built-in patcher */
+    RXM_INFO_NUM_COMPONENTS = 26  /* RXMesh::get_num_components (computed on first request; 0 after rxm_mesh_compact) */
 };
 uint64_t rxm_mesh_info(const rxm_mesh* m, int what);
 double   rxm_mesh_build_seconds(const rxm_mesh* m, int patcher_only);

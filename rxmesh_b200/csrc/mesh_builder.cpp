@@ -119,8 +119,9 @@ uint32_t build_edges(const uint32_t* fv, uint32_t nf, uint32_t nv, U32Buf& ev, U
 // Lloyd patcher
 // ---------------------------------------------------------------------------
 void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_size,
-                   uint32_t lloyd_iters, std::vector<uint32_t>& face_patch, uint32_t& num_patches)
+                   uint32_t lloyd_iters, std::vector<uint32_t>& face_patch, uint32_t& num_patches, uint32_t* lloyd_runs)
 {
+    if (lloyd_runs) *lloyd_runs = 0;
     face_patch.assign(nf, INVALID32_);
     num_patches = 0;
     if (nf == 0) return;
@@ -528,6 +529,7 @@ void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_
         }
     }
     num_patches = (uint32_t)seeds.size();
+    if (lloyd_runs) *lloyd_runs = (uint32_t)n_assign + (on_gpu ? 0u : (uint32_t)n_outer + 1u);  // every assign() pass
     if (getenv("RXM_VERBOSE"))
         fprintf(stderr, "[rxmesh_b200] lloyd: %d outer rounds, %d recentre+assign passes, %u patches (assign %.2fs, recentre %.2fs, %s)\n",
                 n_outer, n_assign, num_patches, t_assign, t_recenter, on_gpu ? "gpu" : serial ? "serial" : "parallel");
@@ -740,7 +742,7 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
         for (int64_t f = 0; f < (int64_t)nf; ++f)
             fpatch[f] = used[face_patch_in[f]];
     } else {
-        patcher_lloyd(fe, nf, ne, opt.patch_size, opt.lloyd_iters, fpatch, P);
+        patcher_lloyd(fe, nf, ne, opt.patch_size, opt.lloyd_iters, fpatch, P, &M.lloyd_runs);
         if (opt.reorder_patches && P > 2) reorder_patches_bfs(fe, nf, ne, fpatch, P);
     }
     M.patcher_seconds = now_s() - t_p0;

@@ -63,6 +63,7 @@ struct HostMesh
     uint32_t max_ext = 0, max_r2 = 0, max_r2_total = 0;
     double   build_seconds          = 0;
     double   patcher_seconds        = 0;
+    uint32_t lloyd_runs             = 0;  // assignment passes of the built-in patcher (0: caller-supplied patches)
 
     // ---- the patch store ----
     std::vector<PatchDesc> desc;
@@ -106,7 +107,8 @@ uint32_t build_edges(const uint32_t* fv, uint32_t nf, uint32_t nv, U32Buf& ev, U
 // Deterministic Lloyd clustering of faces over the face-adjacency graph; the
 // role of patcher::Patcher::run_lloyd (patcher/patcher.cu:828-987).
 void patcher_lloyd(const uint32_t* fe, uint32_t nf, uint32_t ne, uint32_t patch_size,
-                   uint32_t lloyd_iters, std::vector<uint32_t>& face_patch, uint32_t& num_patches);
+                   uint32_t lloyd_iters, std::vector<uint32_t>& face_patch, uint32_t& num_patches,
+                   uint32_t* lloyd_runs = nullptr);  // lloyd_runs: assignment passes run (Patcher::get_num_lloyd_run)
 
 // The outer Lloyd loop of patcher_lloyd on the current CUDA device (rxm_patcher_gpu.cu); false = not run, use the host passes.
 bool patcher_lloyd_gpu(const std::vector<uint32_t>& ff_off, const std::vector<uint32_t>& ff_val, uint32_t nf, uint32_t patch_size,

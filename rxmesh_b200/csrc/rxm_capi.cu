@@ -356,6 +356,31 @@ void rxm_mesh_destroy(rxm_mesh* m)
     delete m;
 }
 
+
+// connected components of the input mesh (union-find over the edge list; the reference counts them while patching)
+static uint64_t count_components(const rxm::HostMesh& h)
+{
+    if (h.ev.empty()) return 0;
+    std::vector<uint32_t> parent(h.num_elems[0]);
+    for (uint32_t v = 0; v < h.num_elems[0]; ++v)
+        parent[v] = v;
+    auto find = [&](uint32_t v) {
+        while (parent[v] != v) {
+            parent[v] = parent[parent[v]];
+            v         = parent[v];
+        }
+        return v;
+    };
+    for (size_t e = 0; e + 1 < h.ev.size(); e += 2) {
+        const uint32_t a = find(h.ev[e]), b = find(h.ev[e + 1]);
+        if (a != b) parent[std::max(a, b)] = std::min(a, b);
+    }
+    uint64_t n = 0;
+    for (uint32_t v = 0; v < h.num_elems[0]; ++v)
+        n += parent[v] == v;
+    return n;
+}
+
 uint64_t rxm_mesh_info(const rxm_mesh* m, int what)
 {
     if (!m) return 0;
@@ -386,6 +411,8 @@ uint64_t rxm_mesh_info(const rxm_mesh* m, int what)
         case RXM_INFO_PACKED: return h.packed;
         case RXM_INFO_FANS: return h.fans;
         case RXM_INFO_RING2: return h.ring2;
+        case RXM_INFO_LLOYD_RUNS: return h.lloyd_runs;
+        case RXM_INFO_NUM_COMPONENTS: return count_components(h);
         default: return 0;
     }
 }

@@ -17,8 +17,9 @@ from conftest import make_mesh  # noqa: E402
 
 rx.rx_init(0)
 DST = {"V": 0, "E": 1, "F": 2}
-for mode in ({}, {"RXM_NO_FANS": "1"}, {"RXM_NO_FANS": "1", "RXM_FORCE_WIDE": "1"}, {"RXM_PERSIST": "1"},
-             {"RXM_VN_SCALAR": "1", "RXM_CONSUME_BT256": "1", "RXM_PIPE_CHUNKS": "0"}):
+ONLY_MULTI = bool(os.environ.get("SANITIZE_MULTI"))  # just the multi-shard part at the end
+for mode in () if ONLY_MULTI else ({}, {"RXM_NO_FANS": "1"}, {"RXM_NO_FANS": "1", "RXM_FORCE_WIDE": "1"}, {"RXM_PERSIST": "1"},
+                                   {"RXM_VN_SCALAR": "1", "RXM_CONSUME_BT256": "1", "RXM_PIPE_CHUNKS": "0"}):
     for k in ("RXM_NO_FANS", "RXM_FORCE_WIDE", "RXM_PERSIST", "RXM_VN_SCALAR", "RXM_CONSUME_BT256", "RXM_PIPE_CHUNKS"):
         os.environ.pop(k, None)
     os.environ.update(mode)
@@ -39,6 +40,28 @@ for mode in ({}, {"RXM_NO_FANS": "1"}, {"RXM_NO_FANS": "1", "RXM_FORCE_WIDE": "1
         flag = rx.Attribute(m, 0, np.uint32, 1, rx.LOCATION_ALL, rx.AoS)
         m.boundary_vertices(flag)
     print("mode", mode, "ok", flush=True)
+# round 2: the Lloyd passes on the GPU (rxm_patcher_gpu.cu) and the single-process multi-GPU mode with three shards on this
+# device -- the fused compute + halo kernel (peer stores into ghost slots, flag words, reader check-in)
+for k in ("RXM_NO_FANS", "RXM_FORCE_WIDE", "RXM_PERSIST", "RXM_VN_SCALAR", "RXM_CONSUME_BT256", "RXM_PIPE_CHUNKS"):
+    os.environ.pop(k, None)
+os.environ["RXM_PATCHER_GPU"] = "1"
+V, F = make_mesh("bunnyhead")
+m = rx.RXMeshStatic(F, patch_size=128)
+os.environ["RXM_PATCHER_GPU"] = "0"
+m0 = rx.RXMeshStatic(F, device=False, patch_size=128)
+assert np.array_equal(m.elem_patch(2), m0.elem_patch(2))
+del os.environ["RXM_PATCHER_GPU"]
+print("gpu patcher ok", flush=True)
+if os.environ.get("SANITIZE_MULTI"):
+    # three shards on this device: their fused kernels wait for each other's flags, i.e. they must be able to run
+    # CONCURRENTLY -- run this part on its own and under a timeout (a tool that serialises kernels would make it wait forever)
+    from rxmesh_b200.multi import RXMeshMulti  # noqa: E402
+    mm = RXMeshMulti(F, [0, 0, 0], patch_size=64)
+    a = mm.laplacian_smooth(V.astype(np.float32), 0.01, 6)
+    assert np.array_equal(a, rx.RXMeshStatic(F, patch_size=64).laplacian_smooth_host(V.astype(np.float32), 0.01, 6))
+    mm.vertex_normals(V.astype(np.float32))
+    print("multi ok", flush=True)
+    sys.exit(0)
 # the user-kernel path through the drop-in headers (Query::dispatch, higher_query_block_dispatcher, split API)
 if os.environ.get("SANITIZE_SKIP_SHIM"):
     sys.exit(0)

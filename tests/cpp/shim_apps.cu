@@ -12,6 +12,7 @@
 #include "rxmesh/query.h"
 #include "rxmesh/reduce_handle.h"
 #include "rxmesh/rxmesh_static.h"
+#include "rxmesh/util/report.h"
 
 using namespace rxmesh;
 
@@ -1085,7 +1086,41 @@ static int app_query(int op, const uint32_t* fv, uint32_t nf, uint32_t patch_siz
     }
 }
 
+// The record a reference app writes around its run (apps/VertexNormal/vertex_normal.cu:136-157: Report, command_line, device,
+// system, model_data, add_member, TestData + add_test, write), as a user program on the drop-in headers.
+static int app_report(const char* obj_path, const char* out_dir, uint32_t patch_size)
+{
+    rx_init(0);
+    RXMeshStatic rx(std::string(obj_path), "", patch_size);
+    Report       report("VertexNormal_RXMesh");
+    char         a0[] = "shim_apps", a1[] = "-input", a2[] = "in.obj";
+    char*        argv[] = {a0, a1, a2};
+    report.command_line(3, argv);
+    report.device();
+    report.system();
+    report.model_data("in.obj", rx);
+    report.add_member("method", std::string("RXMesh"));
+    report.add_member("num_run", 3);
+    TestData td;
+    td.test_name   = "VertexNormal";
+    td.num_threads = 256;
+    td.num_blocks  = (int32_t)rx.get_num_patches();
+    td.dyn_smem    = 1024;
+    td.time_ms     = {0.25f, 0.5f, 1.0f};
+    td.passed      = {true, true, false};
+    report.add_test(td);
+    report.write(out_dir, "record.obj", false);  // -> <out_dir>/record.json
+    CustomReport custom("Other");
+    custom.model_data("in.obj", rx.get_num_vertices(), rx.get_num_faces());
+    custom.write(out_dir, "custom", false);
+    return 0;
+}
+
 extern "C" {
+int shim_report(const char* obj_path, const char* out_dir, uint32_t patch_size)
+{
+    return app_report(obj_path, out_dir, patch_size);
+}
 int shim_vertex_normals(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, float* out)
 {
     return app_vertex_normals(fv, nf, x, nv, patch_size, out);

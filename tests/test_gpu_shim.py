@@ -253,6 +253,38 @@ def test_user_api_surface(shim, name, tmp_path):
     assert np.allclose(np.sort(V2, axis=0), np.sort(V, axis=0))
 
 
+def test_user_report_json(shim, tmp_path):
+    """Report / TestData / CustomReport (util/report.h:36-471) write the reference's JSON members: command line, device,
+    system, model and patch statistics (incl. components, Lloyd passes, ribbon overhead), per-test data."""
+    import json
+    V, F = make_mesh("dragon")
+    src = str(tmp_path / "in.obj")
+    with open(src, "w") as fh:
+        for v in V:
+            fh.write("v %.9g %.9g %.9g\n" % tuple(v))
+        for f in F:
+            fh.write("f %d %d %d\n" % tuple(f + 1))
+    shim.shim_report.restype = C.c_int
+    assert shim.shim_report(src.encode(), str(tmp_path / "out" / "records").encode(), 512) == 0
+    rec = json.load(open(tmp_path / "out" / "records" / "record.json"))
+    assert rec["Record Name"] == "VertexNormal_RXMesh" and rec["command_line"] == "shim_apps -input in.obj"
+    assert rec["GPU Device"]["Multiprocessors"] > 0 and "Peak Memory Bandwidth (GB/s)" in rec["GPU Device"]
+    assert "Hostname" in rec["System"] and rec["System"]["Build Mode"] in ("Release", "Debug")
+    T = O.Topology(F)
+    mdl = rec["Model"]
+    assert (mdl["num_vertices"], mdl["num_edges"], mdl["num_faces"]) == (T.nv, T.ne, T.nf)
+    assert mdl["patch_size"] == 512 and mdl["num_patches"] >= T.nf // 512 and mdl["num_components"] == 1
+    assert mdl["num_lloyd_run"] >= 1 and mdl["patching_time"] > 0 and 0 < mdl["ribbon_overhead (%)"] < 100
+    assert mdl["min_patch_size"] <= mdl["avg_patch_size"] <= mdl["max_patch_size"] == mdl["per_patch_max_faces"]
+    assert mdl["is_edge_manifold"] is True and mdl["max_valence"] == int(np.diff(T.query("VV")[0].astype(np.int64)).max())
+    assert rec["method"] == "RXMesh" and rec["num_run"] == 3
+    t = rec["VertexNormal"]
+    assert t["num_threads"] == 256 and t["dynamic_shared_memory (b)"] == 1024 and "num_register_per_thread" not in t
+    assert t["time (ms)"] == [0.25, 0.5, 1.0] and t["passed"] == [True, True, False]
+    cus = json.load(open(tmp_path / "out" / "records" / "custom.json"))
+    assert cus["Model"] == {"model_name": "in.obj", "num_vertices": T.nv, "num_faces": T.nf}
+
+
 @pytest.mark.parametrize("name", ["dragon", "bunnyhead"])
 def test_user_multi_queries(shim, name):
     """TEST(RXMeshStatic, MultiQueries) (tests/RXMesh_test/test_multi_queries.cu): a primary VE query whose lambda reads a
