@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rxmesh_b200.h"
@@ -220,7 +221,10 @@ int rxm_multi_create(const uint32_t* fv, uint32_t num_faces, const uint32_t* fac
     // ---- 5. devices: upload, peer access, attributes, fused-halo state ----
     for (int r = 0; r < num_shards; ++r) {
         Shard& S = M->sh[r];
-        MCU(cudaSetDevice(S.device));
+        if (cudaSetDevice(S.device) != cudaSuccess) {
+            rxm_set_last_error(RXM_ERR_CUDA, "rxm_multi: cudaSetDevice failed");
+            return fail_free(RXM_ERR_CUDA);
+        }
         int rc = rxm_mesh_to_device(S.mesh);
         if (rc) return fail_free(rc);
         for (int q = 0; q < num_shards; ++q)
@@ -247,7 +251,10 @@ int rxm_multi_create(const uint32_t* fv, uint32_t num_faces, const uint32_t* fac
     for (int r = 0; r < num_shards; ++r) {
         Shard& S = M->sh[r];
         if (S.peers.empty()) continue;
-        MCU(cudaSetDevice(S.device));
+        if (cudaSetDevice(S.device) != cudaSuccess) {
+            rxm_set_last_error(RXM_ERR_CUDA, "rxm_multi: cudaSetDevice failed");
+            return fail_free(RXM_ERR_CUDA);
+        }
         const uint32_t  np = (uint32_t)rxm_mesh_info(S.mesh, RXM_INFO_NUM_PATCHES);
         const uint32_t* sb = rxm_mesh_slot_base(S.mesh, RXM_V);
         struct E
@@ -373,19 +380,32 @@ int rxm_multi_laplacian_smooth(rxm_multi* M, const float* coords, float* out, do
     const uint32_t    step0 = M->step;
     std::vector<int>         rcs((size_t)n, RXM_OK);
     std::vector<std::string> msgs((size_t)n);
-#pragma omp parallel for num_threads(n) schedule(static, 1)
-    for (int r = 0; r < n; ++r) {
+    auto run_shard = [&](int r) {
         Shard& S = M->sh[r];
         bool   sb = src_b;
         if (cudaSetDevice(S.device) != cudaSuccess) {
             rcs[r] = RXM_ERR_CUDA, msgs[r] = "cudaSetDevice failed";
-            continue;
+            return;
         }
         for (uint32_t it = 0; it < iters && rcs[r] == RXM_OK; ++it, sb = !sb) {
             rcs[r] = rxm_laplacian_smooth_fused(S.mesh, sb ? S.b : S.a, sb ? S.a : S.b, lr, S.halo, sb ? 0 : 1, step0 + it, S.stream);
             if (rcs[r]) msgs[r] = rxm_last_error();  // the message is thread-local: carry it to the caller's thread
         }
-        if (rcs[r] == RXM_OK && cudaStreamSynchronize(S.stream) != cudaSuccess) rcs[r] = RXM_ERR_CUDA, msgs[r] = "stream synchronize failed";
+    };
+    {
+        // plain threads, not an OpenMP team: every shard MUST have its own launching thread (a thread that queued one shard's
+        // whole series before another shard's first kernel would fill the launch queue with kernels that wait for each other)
+        std::vector<std::thread> team;
+        for (int r = 1; r < n; ++r)
+            team.emplace_back(run_shard, r);
+        run_shard(0);
+        for (auto& t : team)
+            t.join();
+    }
+    for (int r = 0; r < n; ++r) {
+        Shard& S = M->sh[r];
+        if (rcs[r] == RXM_OK && (cudaSetDevice(S.device) != cudaSuccess || cudaStreamSynchronize(S.stream) != cudaSuccess))
+            rcs[r] = RXM_ERR_CUDA, msgs[r] = "stream synchronize failed";
     }
     for (int r = 0; r < n; ++r)
         if (rcs[r]) return rxm_set_last_error(rcs[r], msgs[r].c_str());
