@@ -883,6 +883,15 @@ __device__ __forceinline__ float gather_sum(const float* __restrict__ s_in, cons
         a += s_in[w2 >> 16];
         return a;
     }
+    // any other list of up to 8 entries (mixed-valence meshes: most vertices): eight predicated steps instead of a loop whose
+    // trip count differs from lane to lane -- no divergence, no loop bookkeeping; additions still in list order
+    const uint32_t n = e - b;
+    if (n <= 8u) {
+#pragma unroll
+        for (uint32_t k = 0; k < 8u; ++k)
+            if (k < n) a += s_in[ids[b + k]];
+        return a;
+    }
     for (uint32_t i = b; i < e; ++i)
         a += s_in[ids[i]];
     return a;

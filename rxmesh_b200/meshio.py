@@ -47,6 +47,20 @@ def grid(nx, ny, dx=1.0, height=True):
     return verts, faces.reshape(-1, 3)
 
 
+def grid_random_diagonals(n, seed=1):
+    """an n x n grid (same vertices and height field as grid()) whose quads are split along a RANDOM diagonal: a manifold,
+    consistently oriented mesh of mixed valence (4..8, mean 6) -- what real inputs look like to the valence-6 fast paths"""
+    verts, _ = grid(n, n)
+    idx = (np.arange(n - 1, dtype=np.uint32)[:, None] * np.uint32(n) + np.arange(n - 1, dtype=np.uint32)[None, :]).reshape(-1)
+    a, b, c, d = idx, idx + np.uint32(n), idx + np.uint32(1), idx + np.uint32(n + 1)
+    flip = np.random.RandomState(seed).rand(idx.shape[0]) < 0.5
+    faces = np.empty((idx.shape[0], 2, 3), dtype=np.uint32)
+    # (a,b,c),(c,b,d) or, the other diagonal with the same orientation, (a,b,d),(a,d,c)
+    faces[:, 0, 0], faces[:, 0, 1], faces[:, 0, 2] = a, b, np.where(flip, d, c)
+    faces[:, 1, 0], faces[:, 1, 1], faces[:, 1, 2] = np.where(flip, a, c), np.where(flip, d, b), np.where(flip, c, d)
+    return verts, faces.reshape(-1, 3)
+
+
 def grid_face_tiles(nx, ny, tile, tile_i=None):
     """Analytic patching of grid(): face -> patch id by tile (columns) x tile_i (rows) quad blocks
     (2*tile*tile_i faces per full patch), the role of the reference's dead
