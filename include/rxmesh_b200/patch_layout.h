@@ -98,6 +98,8 @@ constexpr uint16_t FLAG_PACKED  = 1;
 constexpr uint16_t FLAG_FANS    = 2;
 constexpr uint16_t FLAG_FF      = 4;       // bit 2: stored FF rows of the owned faces (edge-manifold input)
 constexpr uint16_t FLAG_RING2   = 8;       // bit 3: full one-rings of the ribbon vertices next to owned vertices (k-ring consumers)
+constexpr uint16_t FLAG_UNIFORM6 = 16;     // bit 4: EVERY owned vertex has a closed fan of six: fan_off[v] = 6 v | FAN_CLOSED, so the
+                                           //        fan kernels synthesise the offsets instead of loading the section (2 B / vertex)
 constexpr uint16_t FAN_CLOSED   = 0x8000;  // bit 15 of a fan_off entry: the fan of this vertex is closed
 constexpr uint16_t FAN_OFF_MASK = 0x7FFF;
 constexpr uint64_t INVALID64_ = 0xFFFFFFFFFFFFFFFFull;

@@ -1074,6 +1074,14 @@ std::string build_mesh(const uint32_t* fv, uint32_t nf, const uint32_t* face_pat
         }
         D.n_stash    = (uint16_t)tmp[p].stash.size();
         D.flags      = (M.fans ? FLAG_FANS : 0) | (M.max_edge_incident_faces <= 2 ? FLAG_FF : 0) | (ring2 ? FLAG_RING2 : 0);
+        if (M.fans) {  // all owned fans closed with six neighbours: the offsets are 6 v (patch_layout.h FLAG_UNIFORM6)
+            const auto& FO  = fan_off[p];
+            bool        u6  = D.n_owned[ELEM_V] > 0;
+            for (uint32_t v = 0; v < D.n_owned[ELEM_V] && u6; ++v)
+                u6 = FO[v] == (uint16_t)((6u * v) | FAN_CLOSED);
+            u6 = u6 && FO[D.n_owned[ELEM_V]] == (uint16_t)(6u * D.n_owned[ELEM_V]);
+            if (u6) D.flags |= FLAG_UNIFORM6;
+        }
         if (ring2) {
             D.n_r2     = (uint16_t)(tmp[p].r2_off.empty() ? 0 : tmp[p].r2_off.size() - 1);
             D.n_ext    = (uint16_t)tmp[p].ext.size();

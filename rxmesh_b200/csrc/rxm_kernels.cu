@@ -555,16 +555,22 @@ __device__ __forceinline__ FanPatch2 fan_load2(const MeshView& mv, const PatchDe
     float*      s_x     = sm.alloc<float>(3 * max(F.nv, F.cap));
     F.s_out             = WITH_OUT ? sm.alloc<float>(3 * F.cap) : nullptr;
     F.s_fo = s_fo, F.s_fv = s_fv, F.s_x = s_x;
+    const bool u6 = (d.flags & FLAG_UNIFORM6) != 0;
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
-        mbar_arrive_expect_tx(bar, d.fanoff_bytes() + d.fanv_bytes() + d.own_bytes(ELEM_V) + d.stash_bytes() + 12u * F.cap);
-        bulk_g2s(s_fo, blob + d.off_fanoff(), d.fanoff_bytes(), bar);
+        // FLAG_UNIFORM6: every owned fan is closed with six neighbours -- the offsets are written below, the section stays in HBM
+        const uint32_t fo_bytes = u6 ? 0u : d.fanoff_bytes();
+        mbar_arrive_expect_tx(bar, fo_bytes + d.fanv_bytes() + d.own_bytes(ELEM_V) + d.stash_bytes() + 12u * F.cap);
+        if (fo_bytes) bulk_g2s(s_fo, blob + d.off_fanoff(), fo_bytes, bar);
         if (d.fanv_bytes()) bulk_g2s(s_fv, blob + d.off_fanv(), d.fanv_bytes(), bar);
         if (d.own_bytes(ELEM_V)) bulk_g2s(s_own, blob + d.off_own(ELEM_V), d.own_bytes(ELEM_V), bar);
         if (d.stash_bytes()) bulk_g2s(s_stash, blob + d.off_stash(), d.stash_bytes(), bar);
         if (F.cap) bulk_g2s(s_x, x + 3ull * d.slot_base[ELEM_V], 12u * F.cap, bar);
     }
+    if (u6)
+        for (uint32_t v = threadIdx.x; v <= F.nov; v += BT2)
+            s_fo[v] = (uint16_t)(6u * v) | (v < F.nov ? FAN_CLOSED : (uint16_t)0);
     __syncthreads();
     mbar_wait(bar, 0);
     for (uint32_t i = F.nov + threadIdx.x; i < F.nv; i += BT2) {  // ribbon vertices: from their owners' slots
@@ -913,16 +919,21 @@ __global__ void __launch_bounds__(BTC, 2048 / BTC) k_vf_consume_fan(MeshView mv,
     uint32_t*       s_own   = sm.alloc<uint32_t>(d.own_bytes(ELEM_F) / 4);
     StashEntry*     s_stash = sm.alloc<StashEntry>(d.n_stash);
     float*          s_in    = sm.alloc<float>(max(nf, cap));
+    const bool      u6      = (d.flags & FLAG_UNIFORM6) != 0;
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
-        mbar_arrive_expect_tx(&bar, d.fanoff_bytes() + d.fanf_bytes() + d.own_bytes(ELEM_F) + d.stash_bytes() + 4u * cap);
-        bulk_g2s(s_fo, blob + d.off_fanoff(), d.fanoff_bytes(), &bar);
+        const uint32_t fo_bytes = u6 ? 0u : d.fanoff_bytes();  // FLAG_UNIFORM6: offsets written below
+        mbar_arrive_expect_tx(&bar, fo_bytes + d.fanf_bytes() + d.own_bytes(ELEM_F) + d.stash_bytes() + 4u * cap);
+        if (fo_bytes) bulk_g2s(s_fo, blob + d.off_fanoff(), fo_bytes, &bar);
         if (d.fanf_bytes()) bulk_g2s(s_ff, blob + d.off_fanf(), d.fanf_bytes(), &bar);
         if (d.own_bytes(ELEM_F)) bulk_g2s(s_own, blob + d.off_own(ELEM_F), d.own_bytes(ELEM_F), &bar);
         if (d.stash_bytes()) bulk_g2s(s_stash, blob + d.off_stash(), d.stash_bytes(), &bar);
         if (cap) bulk_g2s(s_in, in + d.slot_base[ELEM_F], 4u * cap, &bar);
     }
+    if (u6)
+        for (uint32_t v = threadIdx.x; v <= nov; v += BT)
+            s_fo[v] = (uint16_t)(6u * v) | (v < nov ? FAN_CLOSED : (uint16_t)0);
     __syncthreads();
     mbar_wait(&bar, 0);
     for (uint32_t i = nof + threadIdx.x; i < nf; i += BT) {
@@ -953,16 +964,21 @@ __global__ void __launch_bounds__(BTC, 2048 / BTC) k_vv_consume_fan(MeshView mv,
     uint32_t*       s_own   = sm.alloc<uint32_t>(d.own_bytes(ELEM_V) / 4);
     StashEntry*     s_stash = sm.alloc<StashEntry>(d.n_stash);
     float*          s_in    = sm.alloc<float>(max(nv, cap));
+    const bool      u6      = (d.flags & FLAG_UNIFORM6) != 0;
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
-        mbar_arrive_expect_tx(&bar, d.fanoff_bytes() + d.fanv_bytes() + d.own_bytes(ELEM_V) + d.stash_bytes() + 4u * cap);
-        bulk_g2s(s_fo, blob + d.off_fanoff(), d.fanoff_bytes(), &bar);
+        const uint32_t fo_bytes = u6 ? 0u : d.fanoff_bytes();  // FLAG_UNIFORM6: offsets written below
+        mbar_arrive_expect_tx(&bar, fo_bytes + d.fanv_bytes() + d.own_bytes(ELEM_V) + d.stash_bytes() + 4u * cap);
+        if (fo_bytes) bulk_g2s(s_fo, blob + d.off_fanoff(), fo_bytes, &bar);
         if (d.fanv_bytes()) bulk_g2s(s_fv, blob + d.off_fanv(), d.fanv_bytes(), &bar);
         if (d.own_bytes(ELEM_V)) bulk_g2s(s_own, blob + d.off_own(ELEM_V), d.own_bytes(ELEM_V), &bar);
         if (d.stash_bytes()) bulk_g2s(s_stash, blob + d.off_stash(), d.stash_bytes(), &bar);
         if (cap) bulk_g2s(s_in, in + d.slot_base[ELEM_V], 4u * cap, &bar);
     }
+    if (u6)
+        for (uint32_t v = threadIdx.x; v <= nov; v += BT)
+            s_fo[v] = (uint16_t)(6u * v) | (v < nov ? FAN_CLOSED : (uint16_t)0);
     __syncthreads();
     mbar_wait(&bar, 0);
     for (uint32_t i = nov + threadIdx.x; i < nv; i += BT) {
