@@ -396,6 +396,7 @@ struct FanPatch
     float*          s_xp;  // 3*cap floats: owned slice as it arrived; reused for the result
     float4*         s_x;
     uint32_t        nv, nov, cap;
+    bool            u6;  // FLAG_UNIFORM6: every owned fan is closed with six neighbours, fan v starts at 6 v
 };
 
 __device__ __forceinline__ FanPatch fan_load(const MeshView& mv, const PatchDesc& d, const float* __restrict__ x,
@@ -535,6 +536,7 @@ struct FanPatch2
     const float*    s_x;    // AoS xyz of every local vertex: [0, 3 nov) by TMA, [3 nov, 3 nv) gathered from the owners
     float*          s_out;  // 3*cap floats, bulk-stored to the patch's owned slice
     uint32_t        nv, nov, cap;
+    bool            u6;  // FLAG_UNIFORM6: every owned fan is closed with six neighbours, fan v starts at 6 v
 };
 
 // COHERENT: the ribbon gathers may read ghost slots that a peer GPU wrote WHILE this kernel is running (fused halo
@@ -556,6 +558,7 @@ __device__ __forceinline__ FanPatch2 fan_load2(const MeshView& mv, const PatchDe
     F.s_out             = WITH_OUT ? sm.alloc<float>(3 * F.cap) : nullptr;
     F.s_fo = s_fo, F.s_fv = s_fv, F.s_x = s_x;
     const bool u6 = (d.flags & FLAG_UNIFORM6) != 0;
+    F.u6          = u6;
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
@@ -636,11 +639,15 @@ __global__ void __launch_bounds__(BT2, RXM_VN_MINB) k_vertex_normals_fan2(MeshVi
         bool           fast = false;
         uint32_t       bA = 0, bB = 0;
         if (vB < F.nov) {
-            const uint32_t oA = F.s_fo[vA], eA = F.s_fo[vA + 1] & FAN_OFF_MASK;
-            const uint32_t oB = F.s_fo[vB], eB = F.s_fo[vB + 1] & FAN_OFF_MASK;
-            bA = oA & FAN_OFF_MASK, bB = oB & FAN_OFF_MASK;
-            // both fans closed with valence 6 (the regular case), ids readable as aligned 32-bit pairs
-            fast = (oA & oB & FAN_CLOSED) && eA - bA == 6 && eB - bB == 6 && ((bA | bB) & 1u) == 0;
+            if (F.u6) {  // the whole patch is regular: no offsets to read, nothing to check
+                bA = 6u * vA, bB = 6u * vB, fast = true;
+            } else {
+                const uint32_t oA = F.s_fo[vA], eA = F.s_fo[vA + 1] & FAN_OFF_MASK;
+                const uint32_t oB = F.s_fo[vB], eB = F.s_fo[vB + 1] & FAN_OFF_MASK;
+                bA = oA & FAN_OFF_MASK, bB = oB & FAN_OFF_MASK;
+                // both fans closed with valence 6 (the regular case), ids readable as aligned 32-bit pairs
+                fast = (oA & oB & FAN_CLOSED) && eA - bA == 6 && eB - bB == 6 && ((bA | bB) & 1u) == 0;
+            }
         }
         if (fast) {
             // straight-line packed code: lane 0 of every f2 belongs to vertex A, lane 1 to vertex B
@@ -785,9 +792,13 @@ __global__ void __launch_bounds__(BT2, RXM_VN_MINB) k_laplacian_fan2(MeshView mv
         bool           fast = false;
         uint32_t       bA = 0, bB = 0;
         if (vB < F.nov) {
-            const uint32_t eA = F.s_fo[vA + 1] & FAN_OFF_MASK, eB = F.s_fo[vB + 1] & FAN_OFF_MASK;
-            bA = F.s_fo[vA] & FAN_OFF_MASK, bB = F.s_fo[vB] & FAN_OFF_MASK;
-            fast = eA - bA == 6 && eB - bB == 6 && ((bA | bB) & 1u) == 0;
+            if (F.u6) {
+                bA = 6u * vA, bB = 6u * vB, fast = true;
+            } else {
+                const uint32_t eA = F.s_fo[vA + 1] & FAN_OFF_MASK, eB = F.s_fo[vB + 1] & FAN_OFF_MASK;
+                bA = F.s_fo[vA] & FAN_OFF_MASK, bB = F.s_fo[vB] & FAN_OFF_MASK;
+                fast = eA - bA == 6 && eB - bB == 6 && ((bA | bB) & 1u) == 0;
+            }
         }
         if (fast) {
             const float *   pa = F.s_x + 3u * vA, *pb = F.s_x + 3u * vB;
