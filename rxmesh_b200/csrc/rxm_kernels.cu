@@ -942,9 +942,6 @@ __global__ void __launch_bounds__(BTC, 2048 / BTC) k_vf_consume_fan(MeshView mv,
         if (d.stash_bytes()) bulk_g2s(s_stash, blob + d.off_stash(), d.stash_bytes(), &bar);
         if (cap) bulk_g2s(s_in, in + d.slot_base[ELEM_F], 4u * cap, &bar);
     }
-    if (u6)
-        for (uint32_t v = threadIdx.x; v <= nov; v += BT)
-            s_fo[v] = (uint16_t)(6u * v) | (v < nov ? FAN_CLOSED : (uint16_t)0);
     __syncthreads();
     mbar_wait(&bar, 0);
     for (uint32_t i = nof + threadIdx.x; i < nf; i += BT) {
@@ -952,6 +949,11 @@ __global__ void __launch_bounds__(BTC, 2048 / BTC) k_vf_consume_fan(MeshView mv,
         s_in[i]          = ldg_stream(in + s_stash[o >> 16].slot_base[ELEM_F] + (o & 0xFFFFu));
     }
     __syncthreads();
+    if (u6) {  // regular patch: fan v is entries [6 v, 6 v + 6)
+        for (uint32_t v = threadIdx.x; v < nov; v += BT)
+            out[d.slot_base[ELEM_V] + v] = gather_sum(s_in, s_ff, 6u * v, 6u * v + 6u);
+        return;
+    }
     for (uint32_t v = threadIdx.x; v < nov; v += BT) {
         const uint32_t o = s_fo[v], b = o & FAN_OFF_MASK;
         const uint32_t e = (s_fo[v + 1] & FAN_OFF_MASK) - ((o & FAN_CLOSED) ? 0u : 1u);  // open fan: last slot has no face
@@ -987,9 +989,6 @@ __global__ void __launch_bounds__(BTC, 2048 / BTC) k_vv_consume_fan(MeshView mv,
         if (d.stash_bytes()) bulk_g2s(s_stash, blob + d.off_stash(), d.stash_bytes(), &bar);
         if (cap) bulk_g2s(s_in, in + d.slot_base[ELEM_V], 4u * cap, &bar);
     }
-    if (u6)
-        for (uint32_t v = threadIdx.x; v <= nov; v += BT)
-            s_fo[v] = (uint16_t)(6u * v) | (v < nov ? FAN_CLOSED : (uint16_t)0);
     __syncthreads();
     mbar_wait(&bar, 0);
     for (uint32_t i = nov + threadIdx.x; i < nv; i += BT) {
@@ -997,6 +996,11 @@ __global__ void __launch_bounds__(BTC, 2048 / BTC) k_vv_consume_fan(MeshView mv,
         s_in[i]          = ldg_stream(in + s_stash[o >> 16].slot_base[ELEM_V] + (o & 0xFFFFu));
     }
     __syncthreads();
+    if (u6) {  // regular patch: fan v is entries [6 v, 6 v + 6)
+        for (uint32_t v = threadIdx.x; v < nov; v += BT)
+            out[d.slot_base[ELEM_V] + v] = gather_sum(s_in, s_fv, 6u * v, 6u * v + 6u);
+        return;
+    }
     for (uint32_t v = threadIdx.x; v < nov; v += BT) {
         const uint32_t b = s_fo[v] & FAN_OFF_MASK, e = s_fo[v + 1] & FAN_OFF_MASK;
         out[d.slot_base[ELEM_V] + v] = gather_sum(s_in, s_fv, b, e);
