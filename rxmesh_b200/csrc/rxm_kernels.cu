@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(BT) k_vertex_normals_pk(MeshView mv, const flo
         } else {  // ribbon vertex: gather from the owner patch's slots
             const uint32_t o = s_own[i - nov];
             const float*   g = x + 3ull * ((uint64_t)s_stash[o >> 16].slot_base[ELEM_V] + (o & 0xFFFFu));
-            q = make_float4(ldg_stream(g), ldg_stream(g + 1), ldg_stream(g + 2), 0.f);
+            q = make_float4(__ldg(g), __ldg(g + 1), __ldg(g + 2), 0.f);  // L1 keeps the row's sector between the three loads
         }
         s_x[i] = q;
     }
@@ -275,9 +275,9 @@ __global__ void __launch_bounds__(BT) k_vertex_normals(MeshView mv, const float*
         const uint32_t o    = s_own[i];
         const uint64_t slot = (uint64_t)s_stash[o >> 16].slot_base[ELEM_V] + (o & 0xFFFFu);
         const float*   g    = x + 3ull * slot;
-        s_x[3 * (nov + i) + 0] = ldg_stream(g + 0);
-        s_x[3 * (nov + i) + 1] = ldg_stream(g + 1);
-        s_x[3 * (nov + i) + 2] = ldg_stream(g + 2);
+        s_x[3 * (nov + i) + 0] = __ldg(g + 0);
+        s_x[3 * (nov + i) + 1] = __ldg(g + 1);
+        s_x[3 * (nov + i) + 2] = __ldg(g + 2);
     }
     __syncthreads();
     for (uint32_t f = threadIdx.x; f < nf; f += BT) {
@@ -354,9 +354,9 @@ __global__ void __launch_bounds__(BT) k_laplacian(MeshView mv, const float* __re
     const OwnerTable ot = q.owner_table(d);
     for (uint32_t i = nov + threadIdx.x; i < nv; i += BT) {
         const float* g = x + 3ull * ot.slot(i);
-        s_x[3 * i + 0] = ldg_stream(g + 0);
-        s_x[3 * i + 1] = ldg_stream(g + 1);
-        s_x[3 * i + 2] = ldg_stream(g + 2);
+        s_x[3 * i + 0] = __ldg(g + 0);
+        s_x[3 * i + 1] = __ldg(g + 1);
+        s_x[3 * i + 2] = __ldg(g + 2);
     }
     const QueryResult r = q.compute(d, warp_tmp, false, true);
     for (uint32_t v = threadIdx.x; v < nov; v += BT) {
@@ -432,7 +432,7 @@ __device__ __forceinline__ FanPatch fan_load(const MeshView& mv, const PatchDesc
         } else {
             const uint32_t o = s_own[i - F.nov];
             const float*   g = x + 3ull * ((uint64_t)s_stash[o >> 16].slot_base[ELEM_V] + (o & 0xFFFFu));
-            q = make_float4(ldg_stream(g), ldg_stream(g + 1), ldg_stream(g + 2), 0.f);
+            q = make_float4(__ldg(g), __ldg(g + 1), __ldg(g + 2), 0.f);  // L1 keeps the row's sector between the three loads
         }
         F.s_x[i] = q;
     }
@@ -579,8 +579,9 @@ __device__ __forceinline__ FanPatch2 fan_load2(const MeshView& mv, const PatchDe
     for (uint32_t i = F.nov + threadIdx.x; i < F.nv; i += BT2) {  // ribbon vertices: from their owners' slots
         const uint32_t o = s_own[i - F.nov];
         const float*   g = x + 3ull * ((uint64_t)s_stash[o >> 16].slot_base[ELEM_V] + (o & 0xFFFFu));
-        const float    a = COHERENT ? __ldcg(g) : ldg_stream(g), b = COHERENT ? __ldcg(g + 1) : ldg_stream(g + 1),
-                    c = COHERENT ? __ldcg(g + 2) : ldg_stream(g + 2);
+        // the three words of a row share a sector and neighbouring ribbon rows share lines: let L1 keep them between the loads
+        const float    a = COHERENT ? __ldcg(g) : __ldg(g), b = COHERENT ? __ldcg(g + 1) : __ldg(g + 1),
+                    c = COHERENT ? __ldcg(g + 2) : __ldg(g + 2);
         s_x[3 * i] = a, s_x[3 * i + 1] = b, s_x[3 * i + 2] = c;
     }
     __syncthreads();
@@ -1589,7 +1590,7 @@ __global__ void __launch_bounds__(BT) k_bilateral_patch(MeshView mv, const float
         } else {
             const uint32_t o = i < nv ? s_own[i - nov] : s_ext[i - nv];
             const float*   g = x + 3ull * ((uint64_t)s_stash[o >> 16].slot_base[ELEM_V] + (o & 0xFFFFu));
-            q = make_float4(ldg_stream(g), ldg_stream(g + 1), ldg_stream(g + 2), 0.f);
+            q = make_float4(__ldg(g), __ldg(g + 1), __ldg(g + 2), 0.f);  // L1 keeps the row's sector between the three loads
         }
         s_x[i] = q;
     }
