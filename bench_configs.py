@@ -188,6 +188,67 @@ def consume_and_normals(torch, rx, stream, m, V, F, T, check=True):
     return out
 
 
+def mcf_cg(torch, rx, stream, m, V, F):
+    """SURVEY.md 8(f)1 widened to its caller: the MCF app's matrix-free CG solve (apps/MCF/mcf_cg_mat_free.h) on the noisy
+    torus of config 3 (a fairing problem: the Laplacian of the noise is far above fp32 rounding), through rxm_mcf_solve
+    (two kernels per iteration, solver scalars on the device).  Two runs: the app's defaults (apps/MCF/mcf.cu:19-23: uniform
+    Laplacian, dt = 10, tol_abs 1e-6, at most 100 iterations) and the cotangent Laplacian with dt of the order of a vertex
+    area and a relative tolerance (with the app's dt = 10 on a unit-size mesh that system does not converge in 100
+    iterations, in float64 either).  Parity in the run: the float64 oracle solve of the same system (also the CPU baseline)
+    and the true residual B - A X of the GPU's result."""
+    from oracle import oracle as O
+    peak, _ = peaks()
+    nV = V.shape[0]
+    V = np.ascontiguousarray(V, np.float32)
+    x0 = rx.Attribute(m, 0, np.float32, 3, rx.DEVICE, rx.AoS)
+    x = rx.Attribute(m, 0, np.float32, 3, rx.DEVICE, rx.AoS)
+    x0.from_global(V)
+    out = {"what": "MCF, matrix-free CG, %d vertices (the noisy torus of this config, 32x16-quad tiles)" % nV}
+    rings = O.oriented_rings(F, nV)
+    scale = float(np.abs(V).max())
+    for label, uniform, dt, ta, tr in (("uniform_laplace_app_defaults", True, 10.0, 1e-6, 0.0),
+                                       ("cotangent_laplace", False, 1e-5, 0.0, 1e-6)):
+        kw = dict(time_step=dt, use_uniform_laplace=uniform, max_iter=100, tol_abs=ta, tol_rel=tr, stream=stream)
+        m.mcf_solve(x0, x, **kw)  # warm-up (allocations, module load)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        info = m.mcf_solve(x0, x, **kw)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        got = x.to_global()
+        steps = info["iterations"] + (1 if info["converged"] else 0)  # mat-vec + update pairs that did work
+        # algorithmic bytes per vertex: setup 12 (X0) + 12 (fan ids) + 12 (R) + 4 (diag) [+ 24 (W)] + 24 (X = X0 copy);
+        # iteration: mat-vec 24 (R, P) + 12 (fan ids) + 4 (diag) [+ 24 (W)] + 24 (P', S), update 48 (X, R, P', S) + 24 (X, R)
+        per_it = (136.0 if uniform else 160.0) * nV
+        setup = (64.0 if uniform else 88.0) * nV
+        gbs = (setup + per_it * steps) / (ms * 1e-3) / 1e9
+        t0 = time.perf_counter()
+        ref, oinfo = O.mcf_solve(rings, V, dt, uniform, 100, ta, tr)
+        t_cpu = time.perf_counter() - t0
+        res, bb = O.mcf_residual(rings, V, got, dt, uniform)
+        r2 = float((res ** 2).sum())
+        err, move = float(np.abs(got - ref).max()), float(np.abs(ref - V).max())
+        # both stop at the same residual; what is left of the solution error at that point is a fraction of the move
+        tol = 1e-5 * scale + move * float(np.sqrt(max(oinfo["final_residual"] / oinfo["start_residual"], 0.0)))
+        ok = bool(info["converged"] and oinfo["converged"] and abs(info["iterations"] - oinfo["iterations"]) <= 2 + oinfo["iterations"] // 10
+                  and err < tol)
+        out[label] = {"time_step": dt, "tol_abs": ta, "tol_rel": tr, "iterations": info["iterations"], "converged": info["converged"],
+                      "start_residual": info["start_residual"], "final_residual": info["final_residual"],
+                      "ms_total": ms, "ms_per_iteration": ms / max(steps, 1), "vertex_iterations_per_s": nV * steps / (ms * 1e-3),
+                      "alg_bytes_per_vertex_iteration": per_it / nV, "achieved_gbs": gbs, "hbm_frac": gbs / peak,
+                      "oracle": {"iterations": oinfo["iterations"], "converged": oinfo["converged"],
+                                 "start_residual": oinfo["start_residual"], "final_residual": oinfo["final_residual"]},
+                      "true_residual_sq_of_gpu_result": r2, "rhs_sq": bb, "max_abs_diff_vs_oracle_f64": err, "max_move": move,
+                      "tolerance_abs": tol, "parity_ok": ok,
+                      "cpu_baseline": {"value": nV * (oinfo["iterations"] + 1) / t_cpu, "unit": "vertex-iterations/s", "cores": 1,
+                                       "kind": "port", "sample": "the same mesh and solve, float64, 1 thread (%.1f s)" % t_cpu}}
+    out["parity_ok"] = bool(all(v["parity_ok"] for v in out.values() if isinstance(v, dict)))
+    x0.release(), x.release()
+    return out
+
+
 def lloyd_at_scale(torch, rx, stream, faces=100_000_000):
     """the built-in (host, multi-threaded, deterministic) Lloyd patcher at 100 M faces: a grid whose faces are visited in
     SCRAMBLED tile order so that nothing in the input order helps, patch size 1024; then the headline kernels on those patches"""
@@ -275,8 +336,13 @@ def config_bilateral(torch, rx, stream, nu=2236, iters=5):
     cpu = {"value": Vs.shape[0] / min(t1, tn), "unit": "vertex-iterations/s", "cores": ncpu if tn < t1 else 1, "kind": "port",
            "sample": "%d-face torus of the same generator (%d^2 quads), one iteration of the filter (normals excluded): "
                      "1 thread %.3g, %d threads %.3g vertex-iterations/s" % (Fs.shape[0], ns, Vs.shape[0] / t1, ncpu, Vs.shape[0] / tn)}
+    x.release(), y.release()
+    try:
+        mcf = mcf_cg(torch, rx, stream, m, V, F)
+    except Exception as e:  # noqa: BLE001 -- the widening row must not take the config-3 record down with it
+        mcf = {"error": (type(e).__name__ + ": " + str(e))[:300]}
     return {"what": "bilateral filtering, %d-face torus (%d^2 quads), %d iterations (unit-face normals + filter)" % (nF, nu, iters),
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "mcf_cg_same_mesh": mcf,
             "faces": nF, "patches": m.get_num_patches(), "patch_tile_quads": "%dx%d" % (tj, ti), "build_seconds": tb, "ms_total": ms,
             "ms_per_iteration": ms / iters,
             "vertex_iterations_per_s": nV * iters / (ms * 1e-3), "alg_bytes_per_iteration": 54.0 * nF,

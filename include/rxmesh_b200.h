@@ -205,6 +205,22 @@ int rxm_bilateral_filter(rxm_mesh* m, rxm_attr* in, rxm_attr* out, uint32_t iter
 /* vertex-iterations of the last rxm_bilateral_filter call whose neighbourhood walk left the patch (+ its ring-2 extension)
  * and ran on the cross-patch path instead (diagnostic; the role of the reference's higher_query_block_dispatcher rounds) */
 uint64_t rxm_bilateral_deferred(const rxm_mesh* m);
+/* Mean-curvature-flow smoothing, matrix-free conjugate gradients (apps/MCF/mcf_cg_mat_free.h:13-178 driving
+ * CGMatFreeAttrSolver, include/rxmesh/matrix/cg_mat_free_attr_solver.h:45-125, over init_B / matvec of
+ * apps/MCF/mcf_kernels.cuh:57-205): solves (M + time_step L) X = M X0 for the three coordinates together; L = cotangent
+ * (use_uniform_laplace == 0) or uniform Laplacian, M = lumped mixed-Voronoi / valence mass. Stops like
+ * IterativeSolver::is_converged (iterative_solver.h:57-63): <R,R> < tol_abs or <R,R> / <R0,R0> < tol_rel, or after max_iter
+ * iterations. Reference defaults (apps/MCF/mcf.cu:19-23): time_step 10, tol_abs 1e-6, tol_rel 0, max_iter 100, uniform.
+ * The mesh must be closed and edge-manifold (mcf_cg_mat_free.h:39-43, mcf.cu:106-109). coords / out: distinct 3 x fp32
+ * vertex attributes. */
+typedef struct {
+    uint32_t iterations;      /* completed iterations (IterativeSolver::iter_taken) */
+    uint32_t converged;       /* 1: the tolerance test held; 0: stopped at max_iter */
+    float    start_residual;  /* <R0, R0> */
+    float    final_residual;  /* <R, R> at the stop */
+} rxm_mcf_info;
+int rxm_mcf_solve(rxm_mesh* m, rxm_attr* coords, rxm_attr* out, float time_step, int use_uniform_laplace, uint32_t max_iter,
+                  float tol_abs, float tol_rel, rxm_mcf_info* info, void* stream);
 /* Materialise a query as a CSR over attribute SLOTS on the device (cached in the mesh): off[num_slots(src)+1],
  * val[nnz] = owner slots of the neighbours, lists grouped by patch. The k-ring consumer (bilateral filtering)
  * traverses this instead of re-running whole-patch queries per foreign patch like the reference's

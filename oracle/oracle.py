@@ -320,6 +320,36 @@ def mcf_matvec(rings, X, vec_in, time_step, with_scale=False):
     return (out, scale) if with_scale else out
 
 
+def mcf_solve(rings, X0, time_step=10.0, uniform=True, max_iter=100, tol_abs=1e-6, tol_rel=0.0, with_residual=False):
+    """rxo_mcf_solve (apps/MCF/mcf_cg_mat_free.h + matrix/cg_mat_free_attr_solver.h:45-125), float64 CG.
+    Returns (X, info) with info = dict(iterations, converged, start_residual, final_residual) [, residual B - A X]."""
+    off, val = rings
+    X0 = _f32(X0).reshape(-1, 3)
+    out = np.empty(X0.shape, dtype=np.float64)
+    res = np.empty(X0.shape, dtype=np.float64)
+    info = np.zeros(4, dtype=np.float64)
+    rc = lib().rxo_mcf_solve(_p(off, u32p), _p(val, u32p), X0.shape[0], _p(X0, f32p), C.c_double(time_step), int(bool(uniform)),
+                             int(max_iter), C.c_double(tol_abs), C.c_double(tol_rel), _p(out, f64p), _p(res, f64p), _p(info, f64p))
+    if rc:
+        raise MemoryError("rxo_mcf_solve")
+    d = dict(iterations=int(info[0]), converged=bool(info[1]), start_residual=float(info[2]), final_residual=float(info[3]))
+    return (out, d, res) if with_residual else (out, d)
+
+
+def mcf_residual(rings, X0, X, time_step=10.0, uniform=True):
+    """B - A X (float64) for a candidate solution X of the MCF system built from X0, and <B, B>."""
+    off, val = rings
+    X0 = _f32(X0).reshape(-1, 3)
+    X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, 3)
+    res = np.empty(X0.shape, dtype=np.float64)
+    bb = C.c_double(0)
+    rc = lib().rxo_mcf_residual(_p(off, u32p), _p(val, u32p), X0.shape[0], _p(X0, f32p), C.c_double(time_step), int(bool(uniform)),
+                                _p(X, f64p), _p(res, f64p), C.byref(bb))
+    if rc:
+        raise MemoryError("rxo_mcf_residual")
+    return res, bb.value
+
+
 def gaussian_curvature(fv, X):
     """rxo_gaussian_curvature (apps/GaussianCurvature/gaussian_curvature_kernel.cuh:10-69): (gcs, amix), float64."""
     fv, X = _u32(fv).reshape(-1, 3), _f32(X).reshape(-1, 3)

@@ -787,6 +787,121 @@ void rxo_mcf_matvec_scaled(const uint32_t* off, const uint32_t* val, uint32_t nv
     }
 }
 
+/* MCF solve, matrix-free CG: apps/MCF/mcf_cg_mat_free.h:13-178 (driver), mcf_kernels.cuh:57-115 (init_B: B = X * valence or
+ * X / v_weight), :117-205 (matvec, both Laplacians), matrix/cg_mat_free_attr_solver.h:45-125 (pre_solve: S = A X, R = B - S,
+ * P = R, delta = <R,R>; solve: S = A P, alpha = delta / <S,P>, X += alpha P, R -= alpha S, delta' = <R,R>, stop when
+ * delta' < tol_abs or delta' / delta0 < tol_rel (iterative_solver.h:57-63) -- the converging iteration is not counted --
+ * else beta = delta' / delta, P = R + beta P).  float64 from fp32 coordinates; the three coordinates share one alpha / beta
+ * (the reference's dot / norm2 run over all attributes).  info: [0] iterations, [1] converged, [2] <R0,R0>, [3] final <R,R>.
+ * PARITY: the reference app has no correctness check for the solve; its mat-vec is pinned (tests/test_gpu_shim.py runs the
+ * reference's unmodified mcf_kernels.cuh against rxo_mcf_matvec), the solve is pinned by the property A X = B. */
+static void rxo_mcf_weights(const uint32_t* off, const uint32_t* val, uint32_t nv, const float* X, double time_step, int uniform,
+                            double* W, double* diag, double* mass)
+{
+    for (uint32_t p = 0; p < nv; ++p) {
+        double P[3] = {X[3 * (uint64_t)p], X[3 * (uint64_t)p + 1], X[3 * (uint64_t)p + 2]};
+        uint32_t k = off[p + 1] - off[p];
+        const uint32_t* ring = val + off[p];
+        double sum_w = 0, vw = 0;
+        for (uint32_t v = 0; v < k; ++v) {
+            uint32_t qi = ring[(v + k - 1) % k], ri = ring[v], si = ring[(v + 1) % k];
+            double Q[3], R[3], S[3], w = 1;
+            for (int c = 0; c < 3; ++c)
+                Q[c] = X[3 * (uint64_t)qi + c], R[c] = X[3 * (uint64_t)ri + c], S[c] = X[3 * (uint64_t)si + c];
+            if (!uniform) {
+                w = rxo_cot_part(P, R, Q) + rxo_cot_part(P, R, S);
+                if (w < 0) w = 0;
+            }
+            w *= time_step;
+            W[off[p] + v] = w;
+            sum_w += w;
+            if (uniform) {
+                vw += 1;
+            } else {
+                double ta = rxo_partial_voronoi(P, Q, R);
+                vw += ta > 0 ? ta : 0;
+            }
+        }
+        /* 1 / v_weight with v_weight = 1 / valence (uniform) or 0.5 / area (cotangent) */
+        mass[p] = k ? (uniform ? vw : 2.0 * vw) : 0.0;
+        diag[p] = mass[p] + sum_w;
+    }
+}
+static void rxo_mcf_apply(const uint32_t* off, const uint32_t* val, uint32_t nv, const double* W, const double* diag,
+                          const double* in, double* out)
+{
+    for (uint32_t p = 0; p < nv; ++p) {
+        double x[3] = {0, 0, 0};
+        for (uint32_t i = off[p]; i < off[p + 1]; ++i)
+            for (int c = 0; c < 3; ++c)
+                x[c] -= W[i] * in[3 * (uint64_t)val[i] + c];
+        for (int c = 0; c < 3; ++c)
+            out[3 * (uint64_t)p + c] = x[c] + diag[p] * in[3 * (uint64_t)p + c];
+    }
+}
+static double rxo_dot3(const double* a, const double* b, uint64_t n)
+{
+    double s = 0;
+    for (uint64_t i = 0; i < n; ++i) s += a[i] * b[i];
+    return s;
+}
+/* residual (may be NULL): B - A out, the property the tests check */
+int rxo_mcf_solve(const uint32_t* off, const uint32_t* val, uint32_t nv, const float* X0, double time_step, int uniform,
+                  uint32_t max_iter, double tol_abs, double tol_rel, double* out, double* residual, double* info)
+{
+    const uint64_t n = 3 * (uint64_t)nv;
+    double* W = (double*)malloc(sizeof(double) * (off[nv] + 1));
+    double* buf = (double*)malloc(sizeof(double) * (2 * (uint64_t)nv + 4 * n));
+    if (!W || !buf) { free(W); free(buf); return 1; }
+    double *diag = buf, *mass = buf + nv, *B = mass + nv, *R = B + n, *P = R + n, *S = P + n;
+    rxo_mcf_weights(off, val, nv, X0, time_step, uniform, W, diag, mass);
+    for (uint64_t i = 0; i < n; ++i) out[i] = X0[i], B[i] = X0[i] * mass[i / 3];
+    rxo_mcf_apply(off, val, nv, W, diag, out, S);
+    for (uint64_t i = 0; i < n; ++i) R[i] = B[i] - S[i], P[i] = R[i];
+    double delta_new = rxo_dot3(R, R, n), start = delta_new;
+    uint32_t it = 0;
+    int conv = start == 0.0;
+    while (!conv && it < max_iter) {
+        rxo_mcf_apply(off, val, nv, W, diag, P, S);
+        double alpha = delta_new / rxo_dot3(S, P, n);
+        for (uint64_t i = 0; i < n; ++i) out[i] += alpha * P[i], R[i] -= alpha * S[i];
+        double delta_old = delta_new;
+        delta_new = rxo_dot3(R, R, n);
+        if (delta_new < tol_abs || delta_new / start < tol_rel) { conv = 1; break; }
+        double beta = delta_new / delta_old;
+        for (uint64_t i = 0; i < n; ++i) P[i] = R[i] + beta * P[i];
+        ++it;
+    }
+    if (residual) {
+        rxo_mcf_apply(off, val, nv, W, diag, out, S);
+        for (uint64_t i = 0; i < n; ++i) residual[i] = B[i] - S[i];
+    }
+    info[0] = it, info[1] = conv, info[2] = start, info[3] = delta_new;
+    free(W); free(buf);
+    return 0;
+}
+/* B - A x for a candidate solution x (double): the size-independent check of a solve done elsewhere; also returns <B,B> */
+int rxo_mcf_residual(const uint32_t* off, const uint32_t* val, uint32_t nv, const float* X0, double time_step, int uniform,
+                     const double* x, double* residual, double* bb)
+{
+    const uint64_t n = 3 * (uint64_t)nv;
+    double* W = (double*)malloc(sizeof(double) * (off[nv] + 1));
+    double* buf = (double*)malloc(sizeof(double) * (2 * (uint64_t)nv));
+    if (!W || !buf) { free(W); free(buf); return 1; }
+    double *diag = buf, *mass = buf + nv;
+    rxo_mcf_weights(off, val, nv, X0, time_step, uniform, W, diag, mass);
+    rxo_mcf_apply(off, val, nv, W, diag, x, residual);
+    double s = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        double b = X0[i] * mass[i / 3];
+        residual[i] = b - residual[i];
+        s += b * b;
+    }
+    *bb = s;
+    free(W); free(buf);
+    return 0;
+}
+
 /* Gaussian curvature accumulators (apps/GaussianCurvature/gaussian_curvature_kernel.cuh:10-69):
  * per face corner v: gcs(v) -= angle_v; amix(v) += mixed Voronoi area share. float64 from fp32 inputs. */
 void rxo_gaussian_curvature(const uint32_t* fv, uint32_t nf, const float* X, uint32_t nv, double* gcs, double* amix)

@@ -55,6 +55,8 @@ struct rxm_mesh
     };
     Csr       csr[16];      // materialised queries (rxm_query_csr), indexed by op
     uint32_t* d_flag = nullptr;
+    uint32_t* d_fan_base = nullptr;  // [P] prefix of the patches' fan entries, rounded up to 4 (rxm_mcf_solve: slices of W)
+    uint64_t  fan_entries = 0;
     uint64_t  bilateral_deferred = 0;  // vertices the last rxm_bilateral_filter call sent down the cross-patch path
     rxm_attr* scratch1[32]  = {};  // per query op: [2*op] input, [2*op+1] output of rxm_query_consume_host
     // ---- chunked upload / compute / download pipeline of the host-buffer entry points (see pipelined_host_call) ----
@@ -348,6 +350,7 @@ void rxm_mesh_destroy(rxm_mesh* m)
         for (void* b : m->d_stage)
             if (b) cudaFree(b);
         if (m->d_flag) cudaFree(m->d_flag);
+        if (m->d_fan_base) cudaFree(m->d_fan_base);
         for (auto& c : m->csr) {
             if (c.off) cudaFree(c.off);
             if (c.val) cudaFree(c.val);
@@ -997,6 +1000,92 @@ int rxm_laplacian_smooth(rxm_mesh* m, rxm_attr* in, rxm_attr* out, double lr, ui
         cudaError_t e   = launch_laplacian_step(m->view, m->lim, src, dst, lr, (cudaStream_t)stream, &why);
         if (e != cudaSuccess) return kernel_status(e, why, "rxm_laplacian_smooth");
         src = dst;
+    }
+    return RXM_OK;
+}
+
+// Mean-curvature flow, matrix-free CG (apps/MCF/mcf_cg_mat_free.h:13-178 with CGMatFreeAttrSolver,
+// matrix/cg_mat_free_attr_solver.h:45-125): see rxm_mcf.cu.
+int rxm_mcf_solve(rxm_mesh* m, rxm_attr* coords, rxm_attr* out, float time_step, int use_uniform_laplace, uint32_t max_iter,
+                  float tol_abs, float tol_rel, rxm_mcf_info* info, void* stream)
+{
+    int rc = check_dev(m, "rxm_mcf_solve");
+    if (rc) return rc;
+    if (!is_vec3(coords) || !is_vec3(out) || coords == out)
+        return fail(RXM_ERR_INVALID, "rxm_mcf_solve: coords/out must be distinct device 3 x fp32 vertex attributes");
+    // mcf_cg_mat_free.h:39-43 ("only takes watertight/closed mesh without boundaries"), mcf.cu:106-109 (edge-manifold)
+    if (!m->h.is_closed || !m->h.is_edge_manifold)
+        return fail(RXM_ERR_INVALID, "rxm_mcf_solve: MCF needs a closed, edge-manifold mesh");
+    if (!m->h.fans)
+        return fail(RXM_ERR_UNSUPPORTED, "rxm_mcf_solve: the mesh stores no one-ring fans (inconsistently oriented input)");
+    if (m->active_first != 0 || m->active_count != m->h.num_patches)
+        return fail(RXM_ERR_UNSUPPORTED, "rxm_mcf_solve: runs on a whole mesh, not on a shard's active patch range");
+    if (coords->layout != RXM_AOS || out->layout != RXM_AOS) {
+        rxm_attr *x, *y;
+        if ((rc = aos_standin(m, coords, 4, true, stream, &x)) || (rc = aos_standin(m, out, 5, false, stream, &y))) return rc;
+        if ((rc = rxm_mcf_solve(m, x, y, time_step, use_uniform_laplace, max_iter, tol_abs, tol_rel, info, stream))) return rc;
+        return aos_writeback(m, out, y, stream);
+    }
+    cudaStream_t   st      = (cudaStream_t)stream;
+    const bool     uniform = use_uniform_laplace != 0;
+    const uint32_t P       = m->h.num_patches;
+    if (!m->d_fan_base) {  // where every patch's slice of the weight array starts
+        std::vector<uint32_t> fb(P);
+        uint64_t              acc = 0;
+        for (uint32_t p = 0; p < P; ++p) {
+            fb[p] = (uint32_t)acc;
+            acc += (m->h.desc[p].fan_total + 3u) & ~3u;
+        }
+        if (acc > 0xFFFFFFF0ull) return fail(RXM_ERR_UNSUPPORTED, "rxm_mcf_solve: more than 2^32 fan entries");
+        CU(cudaMalloc((void**)&m->d_fan_base, 4 * (size_t)std::max<uint32_t>(P, 1u)));
+        CU(cudaMemcpy(m->d_fan_base, fb.data(), 4 * (size_t)P, cudaMemcpyHostToDevice));
+        m->fan_entries = acc;
+    }
+    // one allocation: state | partials | diag | W | R | S | P0 | P1   (X is `out` itself)
+    const uint64_t slots = m->h.num_slots[ELEM_V];
+    auto           al    = [](uint64_t b) { return (b + 255ull) & ~255ull; };
+    const uint64_t b_state = al(sizeof(McfState)), b_part = al(8ull * (P + mcf_update_grid())), b_diag = al(4ull * slots),
+                   b_w = uniform ? 0ull : al(4ull * (m->fan_entries + 4ull)), b_vec = al(12ull * slots);
+    uint8_t* base = nullptr;
+    CU(cudaMalloc((void**)&base, b_state + b_part + b_diag + b_w + 4ull * b_vec));
+    McfBuffers B{};
+    uint8_t*   q       = base;
+    B.state            = (McfState*)q, q += b_state;
+    B.partials         = (double*)q, q += b_part;
+    B.diag             = (float*)q, q += b_diag;
+    B.W                = uniform ? nullptr : (float*)q, q += b_w;
+    B.R                = (float*)q, q += b_vec;
+    B.S                = (float*)q, q += b_vec;
+    B.P[0]             = (float*)q, q += b_vec;
+    B.P[1]             = (float*)q, q += b_vec;
+    B.X                = (float*)out->d;
+    B.fan_base         = m->d_fan_base;
+    B.partials_split   = P;
+    McfState    hs{};
+    const char* why = nullptr;
+    cudaError_t e   = cudaMemsetAsync(base, 0, b_state + b_part, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(B.P[0], 0, 2ull * b_vec, st);  // P = 0: the first iteration's beta is 0
+    if (e == cudaSuccess && !uniform) e = cudaMemsetAsync(B.W, 0, b_w, st);  // the padding entries between the patches' slices
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out->d, coords->d, 12ull * slots, cudaMemcpyDeviceToDevice, st);  // X = X0
+    if (e == cudaSuccess) e = launch_mcf_setup(m->view, m->lim, (const float*)coords->d, B, uniform, time_step, st, &why);
+    // iterations are queued in batches; the device-side state says when to stop (a converged solve turns the rest of a
+    // batch into empty kernels)
+    const uint32_t batch = 8;
+    uint32_t       it    = 0;
+    while (e == cudaSuccess) {
+        e = cudaMemcpyAsync(&hs, B.state, sizeof(McfState), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess || hs.converged || it >= max_iter) break;
+        for (uint32_t k = 0; k < batch && it < max_iter && e == cudaSuccess; ++k, ++it)
+            e = launch_mcf_iteration(m->view, m->lim, B, it, uniform, time_step, tol_abs, tol_rel, max_iter, st, &why);
+    }
+    cudaFree(base);
+    if (e != cudaSuccess) return kernel_status(e, why, "rxm_mcf_solve");
+    if (info) {
+        info->iterations     = hs.iters;
+        info->converged      = hs.converged;
+        info->start_residual = (float)hs.start;
+        info->final_residual = (float)hs.final_res;
     }
     return RXM_OK;
 }

@@ -103,6 +103,38 @@ cudaError_t launch_reduce(const MeshView& mv, AttrView<float> a, AttrView<float>
 
 cudaError_t launch_fill(void* data, uint64_t count, uint32_t elem_bytes, const void* value, cudaStream_t stream);
 
+// ---- mean-curvature flow by matrix-free CG (rxm_mcf.cu; apps/MCF/mcf_cg_mat_free.h, matrix/cg_mat_free_attr_solver.h) ----
+// The solver's scalars live on the device: the last block of every kernel reduces the per-block partial sums in block order
+// and does the scalar step (alpha, beta, convergence, iteration count), so an iteration needs no host synchronisation.
+struct McfState
+{
+    double   dot_sp, delta_new, delta_old, start, final_res;
+    float    alpha, beta;
+    uint32_t iters;      // completed iterations (IterativeSolver::m_iter_taken)
+    uint32_t converged;  // is_converged() held (or the start residual is exactly 0)
+    uint32_t ctr;        // blocks that have published their partial sum in the running kernel
+    uint32_t pad[3];
+};
+struct McfBuffers
+{
+    const uint32_t* fan_base;  // [P] first entry of every patch's slice of W (multiples of 4 entries)
+    float*          W;         // time_step * max(0, cotangent weight) per fan entry (null for the uniform Laplacian)
+    float*          diag;      // [num_slots(V)] 1 / v_weight + sum of the edge weights
+    float *         R, *S, *X; // [num_slots(V)][3], AoS
+    float*          P[2];      // search direction, double-buffered (iteration k reads P[k & 1], writes P[(k + 1) & 1])
+    double*         partials;  // [partials_split + mcf_update_grid()]
+    McfState*       state;
+    uint32_t        partials_split;  // = number of patches
+};
+uint32_t    mcf_update_grid();
+cudaError_t launch_mcf_setup(const MeshView& mv, const KernelLimits& lim, const float* x0_aos, const McfBuffers& B, bool uniform,
+                             float time_step, cudaStream_t stream, const char** err);
+// iteration `it` (0-based): mat-vec kernel + update kernel
+cudaError_t launch_mcf_iteration(const MeshView& mv, const KernelLimits& lim, const McfBuffers& B, uint32_t it, bool uniform,
+                                 float time_step, float tol_abs, float tol_rel, uint32_t max_iter, cudaStream_t stream,
+                                 const char** err);
+void count_launches(uint64_t n);  // adds to launch_counter() (kernels launched from other translation units)
+
 // number of kernels launched by this library since load (bench.py "gpu_launches")
 uint64_t launch_counter();
 
