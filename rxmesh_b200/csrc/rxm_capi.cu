@@ -57,6 +57,8 @@ struct rxm_mesh
     uint32_t* d_flag = nullptr;
     uint32_t* d_fan_base = nullptr;  // [P] prefix of the patches' fan entries, rounded up to 4 (rxm_mcf_solve: slices of W)
     uint64_t  fan_entries = 0;
+    void*     d_mcf_ws = nullptr;  // workspace of rxm_mcf_solve, kept between solves (an MCF flow solves once per time step)
+    uint64_t  mcf_ws_bytes = 0;
     uint64_t  bilateral_deferred = 0;  // vertices the last rxm_bilateral_filter call sent down the cross-patch path
     rxm_attr* scratch1[32]  = {};  // per query op: [2*op] input, [2*op+1] output of rxm_query_consume_host
     // ---- chunked upload / compute / download pipeline of the host-buffer entry points (see pipelined_host_call) ----
@@ -351,6 +353,7 @@ void rxm_mesh_destroy(rxm_mesh* m)
             if (b) cudaFree(b);
         if (m->d_flag) cudaFree(m->d_flag);
         if (m->d_fan_base) cudaFree(m->d_fan_base);
+        if (m->d_mcf_ws) cudaFree(m->d_mcf_ws);
         for (auto& c : m->csr) {
             if (c.off) cudaFree(c.off);
             if (c.val) cudaFree(c.val);
@@ -1018,7 +1021,7 @@ int rxm_mcf_solve(rxm_mesh* m, rxm_attr* coords, rxm_attr* out, float time_step,
         return fail(RXM_ERR_INVALID, "rxm_mcf_solve: MCF needs a closed, edge-manifold mesh");
     if (!m->h.fans)
         return fail(RXM_ERR_UNSUPPORTED, "rxm_mcf_solve: the mesh stores no one-ring fans (inconsistently oriented input)");
-    if (m->active_first != 0 || m->active_count != m->h.num_patches)
+    if (m->active_count && (m->active_first != 0 || m->active_count != m->h.num_patches))
         return fail(RXM_ERR_UNSUPPORTED, "rxm_mcf_solve: runs on a whole mesh, not on a shard's active patch range");
     if (coords->layout != RXM_AOS || out->layout != RXM_AOS) {
         rxm_attr *x, *y;
@@ -1046,8 +1049,14 @@ int rxm_mcf_solve(rxm_mesh* m, rxm_attr* coords, rxm_attr* out, float time_step,
     auto           al    = [](uint64_t b) { return (b + 255ull) & ~255ull; };
     const uint64_t b_state = al(sizeof(McfState)), b_part = al(8ull * (P + mcf_update_grid())), b_diag = al(4ull * slots),
                    b_w = uniform ? 0ull : al(4ull * (m->fan_entries + 4ull)), b_vec = al(12ull * slots);
-    uint8_t* base = nullptr;
-    CU(cudaMalloc((void**)&base, b_state + b_part + b_diag + b_w + 4ull * b_vec));
+    const uint64_t need = b_state + b_part + b_diag + b_w + 4ull * b_vec;
+    if (m->mcf_ws_bytes < need) {
+        if (m->d_mcf_ws) cudaFree(m->d_mcf_ws);
+        m->d_mcf_ws = nullptr, m->mcf_ws_bytes = 0;
+        CU(cudaMalloc(&m->d_mcf_ws, need));
+        m->mcf_ws_bytes = need;
+    }
+    uint8_t* base = (uint8_t*)m->d_mcf_ws;
     McfBuffers B{};
     uint8_t*   q       = base;
     B.state            = (McfState*)q, q += b_state;
@@ -1064,22 +1073,19 @@ int rxm_mcf_solve(rxm_mesh* m, rxm_attr* coords, rxm_attr* out, float time_step,
     McfState    hs{};
     const char* why = nullptr;
     cudaError_t e   = cudaMemsetAsync(base, 0, b_state + b_part, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(B.P[0], 0, 2ull * b_vec, st);  // P = 0: the first iteration's beta is 0
-    if (e == cudaSuccess && !uniform) e = cudaMemsetAsync(B.W, 0, b_w, st);  // the padding entries between the patches' slices
     if (e == cudaSuccess) e = cudaMemcpyAsync(out->d, coords->d, 12ull * slots, cudaMemcpyDeviceToDevice, st);  // X = X0
     if (e == cudaSuccess) e = launch_mcf_setup(m->view, m->lim, (const float*)coords->d, B, uniform, time_step, st, &why);
-    // iterations are queued in batches; the device-side state says when to stop (a converged solve turns the rest of a
-    // batch into empty kernels)
+    // iterations are queued in batches with no host synchronisation inside; the device-side state says when to stop (a
+    // converged solve turns the rest of a batch into kernels that return at their first instruction)
     const uint32_t batch = 8;
     uint32_t       it    = 0;
     while (e == cudaSuccess) {
-        e = cudaMemcpyAsync(&hs, B.state, sizeof(McfState), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess || hs.converged || it >= max_iter) break;
         for (uint32_t k = 0; k < batch && it < max_iter && e == cudaSuccess; ++k, ++it)
             e = launch_mcf_iteration(m->view, m->lim, B, it, uniform, time_step, tol_abs, tol_rel, max_iter, st, &why);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&hs, B.state, sizeof(McfState), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess || hs.converged || it >= max_iter) break;
     }
-    cudaFree(base);
     if (e != cudaSuccess) return kernel_status(e, why, "rxm_mcf_solve");
     if (info) {
         info->iterations     = hs.iters;

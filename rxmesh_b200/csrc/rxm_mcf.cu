@@ -27,6 +27,7 @@
 //     update 48 + 24: about 165 B against about 230 B + the weight arithmetic for the six-kernel form.
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 #include "rxm_kernels.h"
 #include "rxmesh_b200/rxm_device.cuh"
@@ -36,7 +37,7 @@ namespace {
 
 using namespace dev;
 
-constexpr int MBT = 256;  // threads per block of the three kernels
+constexpr int MBT = 256;  // threads per block of the setup and update kernels
 
 __device__ __forceinline__ PatchDesc mcf_load_desc(const PatchDesc* g)
 {
@@ -50,6 +51,7 @@ __device__ __forceinline__ PatchDesc mcf_load_desc(const PatchDesc* g)
 }
 
 // sum of `v` over the block, valid in thread 0.  Fixed shuffle tree + fixed order over the warps: deterministic.
+template <int BT = MBT>
 __device__ __forceinline__ double block_sum(double v, double* s_red)
 {
 #pragma unroll
@@ -60,7 +62,7 @@ __device__ __forceinline__ double block_sum(double v, double* s_red)
     __syncthreads();
     double a = 0.0;
     if (threadIdx.x == 0)
-        for (int w = 0; w < MBT / 32; ++w)
+        for (int w = 0; w < BT / 32; ++w)
             a += s_red[w];
     return a;
 }
@@ -77,13 +79,14 @@ __device__ __forceinline__ bool publish_partial(double part, double* partials, u
     __syncthreads();
     return *s_flag != 0u;
 }
+template <int BT = MBT>
 __device__ __forceinline__ double sum_partials(const double* partials, double* s_red)
 {
     __threadfence();
     double a = 0.0;
-    for (uint32_t i = threadIdx.x; i < gridDim.x; i += MBT)
+    for (uint32_t i = threadIdx.x; i < gridDim.x; i += BT)
         a += __ldcg(partials + i);
-    return block_sum(a, s_red);
+    return block_sum<BT>(a, s_red);
 }
 
 // ---- the reference's geometry helpers in fp32 (include/rxmesh/geometry_util.cuh:52-58 tri_area, :107-113 clamp_cot,
@@ -259,14 +262,17 @@ __global__ void __launch_bounds__(MBT) k_mcf_setup(MeshView mv, const float* __r
 // --------------------------------------------------------------------------
 // iteration, first half: P' = R + beta P, S = A P', <S, P'>
 // --------------------------------------------------------------------------
-template <bool UNIFORM>
-__global__ void __launch_bounds__(MBT) k_mcf_matvec(MeshView mv, McfBuffers B, const float* __restrict__ Pold,
-                                                    float* __restrict__ Pnew, float dt)
+// BT: the launcher picks the block size that leaves the fewest idle threads in the last round over the owned vertices
+// (561-vertex tiles: 3 x 192 instead of 256 + 256 + 49).  FIRST: iteration 0, P' = R (beta = 0; P is not read, so the
+// solve needs no zeroed P buffer).
+template <bool UNIFORM, int BT>
+__global__ void __launch_bounds__(BT) k_mcf_matvec(MeshView mv, McfBuffers B, const float* __restrict__ Pold,
+                                                   float* __restrict__ Pnew, float dt, int first)
 {
     if (B.state->converged) return;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t                      bar;
-    __shared__ double                        s_red[MBT / 32];
+    __shared__ double                        s_red[BT / 32];
     __shared__ uint32_t                      s_flag;
     const float     beta = B.state->beta;
     const PatchDesc d    = mcf_load_desc(mv.desc + blockIdx.x);
@@ -288,32 +294,59 @@ __global__ void __launch_bounds__(MBT) k_mcf_matvec(MeshView mv, McfBuffers B, c
         if (cap) bulk_g2s(s_dg, B.diag + d.slot_base[ELEM_V], 4u * cap, &bar);
     }
     // while the copies fly: the new search direction of the patch's own vertices (the owner writes it back below)
-    for (uint32_t j = threadIdx.x; j < 3u * cap; j += MBT) {
-        const float pn = j < 3u * nov ? __fmaf_rn(beta, Pold[g + j], B.R[g + j]) : 0.f;
-        s_p[j]         = pn;
-        Pnew[g + j]    = pn;
+    for (uint32_t j = threadIdx.x; j < 3u * cap; j += BT) {
+        float pn = 0.f;
+        if (j < 3u * nov) pn = first ? B.R[g + j] : __fmaf_rn(beta, Pold[g + j], B.R[g + j]);
+        s_p[j]      = pn;
+        Pnew[g + j] = pn;
     }
     __syncthreads();
     mbar_wait(&bar, 0);
     // ribbon vertices: the SAME expression on the rows of their owners (bit-identical to what the owner stores)
-    for (uint32_t i = nov + threadIdx.x; i < nv; i += MBT) {
+    for (uint32_t i = nov + threadIdx.x; i < nv; i += BT) {
         const uint32_t o = T.own[i - nov];
         const uint64_t s = 3ull * ((uint64_t)T.stash[o >> 16].slot_base[ELEM_V] + (o & 0xFFFFu));
-        s_p[3 * i]       = __fmaf_rn(beta, __ldg(Pold + s), __ldg(B.R + s));
-        s_p[3 * i + 1]   = __fmaf_rn(beta, __ldg(Pold + s + 1), __ldg(B.R + s + 1));
-        s_p[3 * i + 2]   = __fmaf_rn(beta, __ldg(Pold + s + 2), __ldg(B.R + s + 2));
+        const float    r0 = __ldg(B.R + s), r1 = __ldg(B.R + s + 1), r2 = __ldg(B.R + s + 2);
+        if (first) {
+            s_p[3 * i] = r0, s_p[3 * i + 1] = r1, s_p[3 * i + 2] = r2;
+        } else {
+            s_p[3 * i]     = __fmaf_rn(beta, __ldg(Pold + s), r0);
+            s_p[3 * i + 1] = __fmaf_rn(beta, __ldg(Pold + s + 1), r1);
+            s_p[3 * i + 2] = __fmaf_rn(beta, __ldg(Pold + s + 2), r2);
+        }
     }
     __syncthreads();
     double part = 0.0;
-    for (uint32_t v = threadIdx.x; v < cap; v += MBT) {
+    for (uint32_t v = threadIdx.x; v < cap; v += BT) {
         float ox = 0.f, oy = 0.f, oz = 0.f;
         if (v < nov) {
             const uint32_t b = T.fo[v] & FAN_OFF_MASK, e = T.fo[v + 1] & FAN_OFF_MASK;
             float          x = 0.f, y = 0.f, z = 0.f;
-            for (uint32_t i = b; i < e; ++i) {
-                const float  w = UNIFORM ? dt : s_w[i];
-                const float* q = s_p + 3u * T.fv[i];
-                x -= w * q[0], y -= w * q[1], z -= w * q[2];
+            if (e - b == 6u && (b & 1u) == 0u) {
+                // the regular vertex: ids two per LDS.32, no loop bookkeeping, every load in flight at once; the same
+                // subtractions in the same order as the loop below
+                const uint32_t* w32 = reinterpret_cast<const uint32_t*>(T.fv + b);
+                const uint32_t  i01 = w32[0], i23 = w32[1], i45 = w32[2];
+                float           w0 = dt, w1 = dt, w2 = dt, w3 = dt, w4 = dt, w5 = dt;
+                if (!UNIFORM) {
+                    const float2* wp = reinterpret_cast<const float2*>(s_w + b);
+                    const float2  a = wp[0], c = wp[1], f = wp[2];
+                    w0 = a.x, w1 = a.y, w2 = c.x, w3 = c.y, w4 = f.x, w5 = f.y;
+                }
+                const float *q0 = s_p + 3u * (i01 & 0xFFFFu), *q1 = s_p + 3u * (i01 >> 16), *q2 = s_p + 3u * (i23 & 0xFFFFu),
+                            *q3 = s_p + 3u * (i23 >> 16), *q4 = s_p + 3u * (i45 & 0xFFFFu), *q5 = s_p + 3u * (i45 >> 16);
+                x -= w0 * q0[0], y -= w0 * q0[1], z -= w0 * q0[2];
+                x -= w1 * q1[0], y -= w1 * q1[1], z -= w1 * q1[2];
+                x -= w2 * q2[0], y -= w2 * q2[1], z -= w2 * q2[2];
+                x -= w3 * q3[0], y -= w3 * q3[1], z -= w3 * q3[2];
+                x -= w4 * q4[0], y -= w4 * q4[1], z -= w4 * q4[2];
+                x -= w5 * q5[0], y -= w5 * q5[1], z -= w5 * q5[2];
+            } else {
+                for (uint32_t i = b; i < e; ++i) {
+                    const float  w = UNIFORM ? dt : s_w[i];
+                    const float* q = s_p + 3u * T.fv[i];
+                    x -= w * q[0], y -= w * q[1], z -= w * q[2];
+                }
             }
             const float dg = s_dg[v], px = s_p[3 * v], py = s_p[3 * v + 1], pz = s_p[3 * v + 2];
             ox = x + dg * px, oy = y + dg * py, oz = z + dg * pz;
@@ -321,9 +354,9 @@ __global__ void __launch_bounds__(MBT) k_mcf_matvec(MeshView mv, McfBuffers B, c
         }
         B.S[g + 3 * v] = ox, B.S[g + 3 * v + 1] = oy, B.S[g + 3 * v + 2] = oz;
     }
-    part = block_sum(part, s_red);
+    part = block_sum<BT>(part, s_red);
     if (publish_partial(part, B.partials, &B.state->ctr, &s_flag)) {
-        const double a = sum_partials(B.partials, s_red);
+        const double a = sum_partials<BT>(B.partials, s_red);
         if (threadIdx.x == 0) {
             B.state->ctr    = 0;
             B.state->dot_sp = a;
@@ -433,14 +466,34 @@ cudaError_t launch_mcf_iteration(const MeshView& mv, const KernelLimits& lim, co
     const uint32_t capv = lim.max_owned[ELEM_V] + 4u;
     const uint32_t smem = staged_smem(lim) + (uniform ? 16u : a16(4u * (lim.max_fan_total + 8u))) + a16(4u * (capv + 4u)) +
                           a16(12u * std::max(lim.max_n[ELEM_V], capv) + 16u) + 64u;
-    cudaError_t e = uniform ? mcf_set_smem(k_mcf_matvec<true>, smem) : mcf_set_smem(k_mcf_matvec<false>, smem);
+    // block size: the fewest idle threads in the last round over a full patch's owned vertices (ties: the larger block)
+    int      bt   = 256;
+    uint32_t idle = ~0u;
+    for (int c : {256, 192, 128}) {
+        const uint32_t nov = std::max(lim.max_owned[ELEM_V], 1u), w = (nov + c - 1) / c * c - nov;
+        if (w < idle) idle = w, bt = c;
+    }
+    if (const char* f = getenv("RXM_MCF_BT")) bt = atoi(f);
+    const float* pold  = B.P[it & 1u];
+    float*       pnew  = B.P[(it + 1u) & 1u];
+    const int    first = it == 0;
+    cudaError_t  e     = cudaSuccess;
+#define RXM_MCF_MV(U, BTV)                                                                                      \
+    do {                                                                                                        \
+        e = mcf_set_smem(k_mcf_matvec<U, BTV>, smem);                                                           \
+        if (e == cudaSuccess) k_mcf_matvec<U, BTV><<<mv.num_patches, BTV, smem, stream>>>(mv, B, pold, pnew, dt, first); \
+    } while (0)
+    if (uniform) {
+        if (bt == 128) RXM_MCF_MV(true, 128);
+        else if (bt == 192) RXM_MCF_MV(true, 192);
+        else RXM_MCF_MV(true, 256);
+    } else {
+        if (bt == 128) RXM_MCF_MV(false, 128);
+        else if (bt == 192) RXM_MCF_MV(false, 192);
+        else RXM_MCF_MV(false, 256);
+    }
+#undef RXM_MCF_MV
     if (e != cudaSuccess) RXM_MCF_FAIL("patch needs more shared memory than 227 KB");
-    const float* pold = B.P[it & 1u];
-    float*       pnew = B.P[(it + 1u) & 1u];
-    if (uniform)
-        k_mcf_matvec<true><<<mv.num_patches, MBT, smem, stream>>>(mv, B, pold, pnew, dt);
-    else
-        k_mcf_matvec<false><<<mv.num_patches, MBT, smem, stream>>>(mv, B, pold, pnew, dt);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const uint64_t n4 = 3ull * mv.num_slots[ELEM_V] / 4ull;  // slot caps are multiples of 4: 3 * slots floats = n4 float4

@@ -9,6 +9,7 @@
 #include "rxmesh/attribute.h"
 #include "rxmesh/geometry_util.cuh"
 #include "rxmesh/kernels/query_dispatcher.cuh"
+#include "rxmesh/matrix/cg_mat_free_attr_solver.h"
 #include "rxmesh/query.h"
 #include "rxmesh/reduce_handle.h"
 #include "rxmesh/rxmesh_static.h"
@@ -487,6 +488,53 @@ static int app_mcf_matvec(const uint32_t* fv, uint32_t nf, const float* x, const
     rx.for_each_vertex(HOST, [&](const VertexHandle& vh) {
         for (uint32_t i = 0; i < 3; ++i)
             out[rx.map_to_global(vh) * 3 + i] = (*res)(vh, i);
+    }, NULL, false);
+    return 0;
+}
+
+// The MCF app's solve (apps/MCF/mcf_cg_mat_free.h:13-178) as user code: init_B, then CGMatFreeAttrSolver (the drop-in
+// header include/rxmesh/matrix/cg_mat_free_attr_solver.h) driving the matrix-free mat-vec kernel through run_kernel.  With
+// RXM_REFSRC == 1 both kernels are the reference's own (apps/MCF/mcf_kernels.cuh, unmodified, either Laplacian); otherwise the
+// restated cotangent mat-vec above, with B = M X0 taken from a mat-vec at time step 0.  info: iterations, start, final residual.
+static int app_mcf_cg(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, float time_step,
+                      int uniform, int max_iter, float tol_abs, float tol_rel, float* out, float* info)
+{
+    rx_init(0);
+    RXMeshStatic rx(to_faces(fv, nf), "", patch_size);
+    if (!rx.is_closed()) return 2;
+    constexpr uint32_t blockThreads = 256;
+    auto coords = rx.add_vertex_attribute<float>(to_verts(x, nv), "coords");
+    auto B      = rx.add_vertex_attribute<float>("B", 3, DEVICE);
+    auto X      = rx.add_vertex_attribute<float>("X", 3, LOCATION_ALL);
+    B->reset(0.f, DEVICE);
+    X->copy_from(*coords, DEVICE, DEVICE);
+    LaunchBox<blockThreads> lb;
+#if RXM_REFSRC == 1
+    const bool uni = uniform != 0;
+    rx.prepare_launch_box({Op::VV}, lb, (void*)init_B<float, blockThreads>, !uni);
+    init_B<float, blockThreads><<<lb.blocks, lb.num_threads, lb.smem_bytes_dyn>>>(rx.get_context(), *X, *B, uni);
+    rx.prepare_launch_box({Op::VV}, lb, (void*)matvec<float, blockThreads>, !uni);
+    auto mat_vec = [&](const VertexAttribute<float>& in, VertexAttribute<float>& o, cudaStream_t stream) {
+        rx.run_kernel(lb, matvec<float, blockThreads>, stream, *coords, in, o, uni, time_step);
+    };
+#else
+    if (uniform) return 3;  // the restated kernel has the cotangent weights only
+    rx.prepare_launch_box({Op::VV}, lb, (void*)user_mcf_matvec<float, blockThreads>, true);
+    user_mcf_matvec<float, blockThreads><<<lb.blocks, lb.num_threads, lb.smem_bytes_dyn>>>(rx.get_context(), *coords, *X, *B, 0.f);
+    auto mat_vec = [&](const VertexAttribute<float>& in, VertexAttribute<float>& o, cudaStream_t stream) {
+        rx.run_kernel(lb, user_mcf_matvec<float, blockThreads>, stream, *coords, in, o, time_step);
+    };
+#endif
+    if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+    CGMatFreeAttrSolver<float, VertexHandle> solver(rx, mat_vec, 3, max_iter, tol_abs, tol_rel);
+    solver.pre_solve(*B, *X);
+    solver.solve(*B, *X);
+    if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+    info[0] = (float)solver.iter_taken(), info[1] = solver.start_residual(), info[2] = solver.final_residual();
+    X->move(DEVICE, HOST);
+    rx.for_each_vertex(HOST, [&](const VertexHandle& vh) {
+        for (uint32_t i = 0; i < 3; ++i)
+            out[rx.map_to_global(vh) * 3 + i] = (*X)(vh, i);
     }, NULL, false);
     return 0;
 }
@@ -1196,6 +1244,11 @@ int shim_mcf_matvec(const uint32_t* fv, uint32_t nf, const float* x, const float
                     float time_step, float* out)
 {
     return app_mcf_matvec(fv, nf, x, vin, nv, patch_size, time_step, out);
+}
+int shim_mcf_cg(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, float time_step, int uniform,
+                int max_iter, float tol_abs, float tol_rel, float* out, float* info)
+{
+    return app_mcf_cg(fv, nf, x, nv, patch_size, time_step, uniform, max_iter, tol_abs, tol_rel, out, info);
 }
 int shim_gaussian_curvature(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, float* out_gcs,
                             float* out_amix)
