@@ -266,16 +266,18 @@ __global__ void __launch_bounds__(MBT) k_mcf_setup(MeshView mv, const float* __r
 // (561-vertex tiles: 3 x 192 instead of 256 + 256 + 49).  FIRST: iteration 0, P' = R (beta = 0; P is not read, so the
 // solve needs no zeroed P buffer).
 template <bool UNIFORM, int BT>
-__global__ void __launch_bounds__(BT) k_mcf_matvec(MeshView mv, McfBuffers B, const float* __restrict__ Pold,
+__global__ void __launch_bounds__(BT, 1536 / BT) k_mcf_matvec(MeshView mv, McfBuffers B, const float* __restrict__ Pold,
                                                    float* __restrict__ Pnew, float dt, int first)
 {
-    if (B.state->converged) return;
+    // the descriptor and the solver state are fetched together (one DRAM round trip at the head of the block, not two)
+    const PatchDesc d    = mcf_load_desc(mv.desc + blockIdx.x);
+    const uint32_t  conv = B.state->converged;
+    const float     beta = B.state->beta;
+    if (conv) return;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t                      bar;
     __shared__ double                        s_red[BT / 32];
     __shared__ uint32_t                      s_flag;
-    const float     beta = B.state->beta;
-    const PatchDesc d    = mcf_load_desc(mv.desc + blockIdx.x);
     const uint8_t*  blob = mv.topo + d.topo_off;
     const uint32_t  nv = d.n[ELEM_V], nov = d.n_owned[ELEM_V], cap = d.slot_cap(ELEM_V);
     const uint32_t  nw = (d.fan_total + 3u) & ~3u;  // entries of this patch's slice of W
@@ -293,14 +295,44 @@ __global__ void __launch_bounds__(BT) k_mcf_matvec(MeshView mv, McfBuffers B, co
         if (!UNIFORM && nw) bulk_g2s(s_w, B.W + B.fan_base[blockIdx.x], 4u * nw, &bar);
         if (cap) bulk_g2s(s_dg, B.diag + d.slot_base[ELEM_V], 4u * cap, &bar);
     }
-    // while the copies fly: the new search direction of the patch's own vertices (the owner writes it back below)
-    for (uint32_t j = threadIdx.x; j < 3u * cap; j += BT) {
-        float pn = 0.f;
-        if (j < 3u * nov) pn = first ? B.R[g + j] : __fmaf_rn(beta, Pold[g + j], B.R[g + j]);
-        s_p[j]      = pn;
-        Pnew[g + j] = pn;
+    __syncthreads();  // the barrier object is initialised for everyone who waits on it below
+    // while the copies fly: the new search direction of the patch's own vertices (the owner writes it back).  The slice
+    // is 3 * cap floats = 3 * cap / 4 float4 (slot caps are multiples of 4, slices 48-byte aligned); three load pairs per thread
+    // are issued before the first store -- written as a plain load / store loop the compiler keeps every load behind the
+    // previous store (R comes through a struct member, it may alias P') and the block pays one DRAM latency per step
+    // (profiles/r02M: 14.8 us per block, long-scoreboard 18 per issue).
+    {
+        const float4* R4 = reinterpret_cast<const float4*>(B.R + g);
+        const float4* O4 = reinterpret_cast<const float4*>(Pold + g);
+        float4*       N4 = reinterpret_cast<float4*>(Pnew + g);
+        float4*       s4 = reinterpret_cast<float4*>(s_p);
+        const uint32_t n4 = 3u * cap / 4u, lim = 3u * nov;
+        for (uint32_t j0 = threadIdx.x; j0 < n4; j0 += 3u * BT) {
+            float4 r[3], o[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t j = j0 + k * BT;
+                r[k] = o[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < n4) {
+                    r[k] = __ldg(R4 + j);
+                    if (!first) o[k] = __ldg(O4 + j);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t j = j0 + k * BT;
+                if (j < n4) {
+                    float4 pn;  // rows past the owned vertices stay zero
+                    pn.x = 4u * j < lim ? (first ? r[k].x : __fmaf_rn(beta, o[k].x, r[k].x)) : 0.f;
+                    pn.y = 4u * j + 1u < lim ? (first ? r[k].y : __fmaf_rn(beta, o[k].y, r[k].y)) : 0.f;
+                    pn.z = 4u * j + 2u < lim ? (first ? r[k].z : __fmaf_rn(beta, o[k].z, r[k].z)) : 0.f;
+                    pn.w = 4u * j + 3u < lim ? (first ? r[k].w : __fmaf_rn(beta, o[k].w, r[k].w)) : 0.f;
+                    s4[j] = pn;
+                    N4[j] = pn;
+                }
+            }
+        }
     }
-    __syncthreads();
     mbar_wait(&bar, 0);
     // ribbon vertices: the SAME expression on the rows of their owners (bit-identical to what the owner stores)
     for (uint32_t i = nov + threadIdx.x; i < nv; i += BT) {
@@ -469,7 +501,7 @@ cudaError_t launch_mcf_iteration(const MeshView& mv, const KernelLimits& lim, co
     // block size: the fewest idle threads in the last round over a full patch's owned vertices (ties: the larger block)
     int      bt   = 256;
     uint32_t idle = ~0u;
-    for (int c : {256, 192, 128}) {
+    for (int c : {256, 192, 128}) {  // (288 = two rounds over a 561-vertex tile: RXM_MCF_BT, measured)
         const uint32_t nov = std::max(lim.max_owned[ELEM_V], 1u), w = (nov + c - 1) / c * c - nov;
         if (w < idle) idle = w, bt = c;
     }
@@ -486,10 +518,12 @@ cudaError_t launch_mcf_iteration(const MeshView& mv, const KernelLimits& lim, co
     if (uniform) {
         if (bt == 128) RXM_MCF_MV(true, 128);
         else if (bt == 192) RXM_MCF_MV(true, 192);
+        else if (bt == 288) RXM_MCF_MV(true, 288);
         else RXM_MCF_MV(true, 256);
     } else {
         if (bt == 128) RXM_MCF_MV(false, 128);
         else if (bt == 192) RXM_MCF_MV(false, 192);
+        else if (bt == 288) RXM_MCF_MV(false, 288);
         else RXM_MCF_MV(false, 256);
     }
 #undef RXM_MCF_MV
