@@ -221,6 +221,11 @@ typedef struct {
 } rxm_mcf_info;
 int rxm_mcf_solve(rxm_mesh* m, rxm_attr* coords, rxm_attr* out, float time_step, int use_uniform_laplace, uint32_t max_iter,
                   float tol_abs, float tol_rel, rxm_mcf_info* info, void* stream);
+/* jacobi != 0: the Jacobi-preconditioned form, mcf_pcg_mat_free (apps/MCF/mcf_cg_mat_free.h:181-254): PCGMatFreeAttrSolver
+ * (include/rxmesh/matrix/pcg_mat_free_attr_solver.h:40-140) with precond_matvec (apps/MCF/mcf_kernels.cuh:216-295, out = in /
+ * diagonal); the residual the tolerances apply to is then <R, M^-1 R>. jacobi == 0 is rxm_mcf_solve. */
+int rxm_mcf_solve_ex(rxm_mesh* m, rxm_attr* coords, rxm_attr* out, float time_step, int use_uniform_laplace, int jacobi,
+                     uint32_t max_iter, float tol_abs, float tol_rel, rxm_mcf_info* info, void* stream);
 /* Materialise a query as a CSR over attribute SLOTS on the device (cached in the mesh): off[num_slots(src)+1],
  * val[nnz] = owner slots of the neighbours, lists grouped by patch. The k-ring consumer (bilateral filtering)
  * traverses this instead of re-running whole-patch queries per foreign patch like the reference's

@@ -320,16 +320,19 @@ def mcf_matvec(rings, X, vec_in, time_step, with_scale=False):
     return (out, scale) if with_scale else out
 
 
-def mcf_solve(rings, X0, time_step=10.0, uniform=True, max_iter=100, tol_abs=1e-6, tol_rel=0.0, with_residual=False):
-    """rxo_mcf_solve (apps/MCF/mcf_cg_mat_free.h + matrix/cg_mat_free_attr_solver.h:45-125), float64 CG.
+def mcf_solve(rings, X0, time_step=10.0, uniform=True, max_iter=100, tol_abs=1e-6, tol_rel=0.0, with_residual=False,
+              precond=False):
+    """rxo_mcf_solve_ex (apps/MCF/mcf_cg_mat_free.h + matrix/cg_mat_free_attr_solver.h:45-125; precond: the Jacobi form of
+    pcg_mat_free_attr_solver.h:40-140 with precond_matvec), float64 CG.
     Returns (X, info) with info = dict(iterations, converged, start_residual, final_residual) [, residual B - A X]."""
     off, val = rings
     X0 = _f32(X0).reshape(-1, 3)
     out = np.empty(X0.shape, dtype=np.float64)
     res = np.empty(X0.shape, dtype=np.float64)
     info = np.zeros(4, dtype=np.float64)
-    rc = lib().rxo_mcf_solve(_p(off, u32p), _p(val, u32p), X0.shape[0], _p(X0, f32p), C.c_double(time_step), int(bool(uniform)),
-                             int(max_iter), C.c_double(tol_abs), C.c_double(tol_rel), _p(out, f64p), _p(res, f64p), _p(info, f64p))
+    rc = lib().rxo_mcf_solve_ex(_p(off, u32p), _p(val, u32p), X0.shape[0], _p(X0, f32p), C.c_double(time_step), int(bool(uniform)),
+                                int(bool(precond)), int(max_iter), C.c_double(tol_abs), C.c_double(tol_rel), _p(out, f64p),
+                                _p(res, f64p), _p(info, f64p))
     if rc:
         raise MemoryError("rxo_mcf_solve")
     d = dict(iterations=int(info[0]), converged=bool(info[1]), start_residual=float(info[2]), final_residual=float(info[3]))

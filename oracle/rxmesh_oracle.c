@@ -845,31 +845,39 @@ static double rxo_dot3(const double* a, const double* b, uint64_t n)
     for (uint64_t i = 0; i < n; ++i) s += a[i] * b[i];
     return s;
 }
-/* residual (may be NULL): B - A out, the property the tests check */
-int rxo_mcf_solve(const uint32_t* off, const uint32_t* val, uint32_t nv, const float* X0, double time_step, int uniform,
-                  uint32_t max_iter, double tol_abs, double tol_rel, double* out, double* residual, double* info)
+/* residual (may be NULL): B - A out, the property the tests check.
+ * precond != 0: the Jacobi-preconditioned form, apps/MCF/mcf_cg_mat_free.h:181-254 with precond_matvec (mcf_kernels.cuh:216-295:
+ * out = in / diag) under matrix/pcg_mat_free_attr_solver.h:40-140: P = Z = R / diag, delta = |<R,Z>| at the start, <R,Z> after,
+ * the same stopping rule applied to delta, P = Z + beta P. */
+int rxo_mcf_solve_ex(const uint32_t* off, const uint32_t* val, uint32_t nv, const float* X0, double time_step, int uniform,
+                     int precond, uint32_t max_iter, double tol_abs, double tol_rel, double* out, double* residual, double* info)
 {
     const uint64_t n = 3 * (uint64_t)nv;
     double* W = (double*)malloc(sizeof(double) * (off[nv] + 1));
-    double* buf = (double*)malloc(sizeof(double) * (2 * (uint64_t)nv + 4 * n));
+    double* buf = (double*)malloc(sizeof(double) * (2 * (uint64_t)nv + 5 * n));
     if (!W || !buf) { free(W); free(buf); return 1; }
-    double *diag = buf, *mass = buf + nv, *B = mass + nv, *R = B + n, *P = R + n, *S = P + n;
+    double *diag = buf, *mass = buf + nv, *B = mass + nv, *R = B + n, *P = R + n, *S = P + n, *Z = S + n;
     rxo_mcf_weights(off, val, nv, X0, time_step, uniform, W, diag, mass);
     for (uint64_t i = 0; i < n; ++i) out[i] = X0[i], B[i] = X0[i] * mass[i / 3];
     rxo_mcf_apply(off, val, nv, W, diag, out, S);
-    for (uint64_t i = 0; i < n; ++i) R[i] = B[i] - S[i], P[i] = R[i];
-    double delta_new = rxo_dot3(R, R, n), start = delta_new;
+    for (uint64_t i = 0; i < n; ++i) {
+        R[i] = B[i] - S[i];
+        Z[i] = precond ? (diag[i / 3] != 0 ? R[i] / diag[i / 3] : 0.0) : R[i];
+        P[i] = Z[i];
+    }
+    double delta_new = fabs(rxo_dot3(R, Z, n)), start = delta_new;
     uint32_t it = 0;
     int conv = start == 0.0;
     while (!conv && it < max_iter) {
         rxo_mcf_apply(off, val, nv, W, diag, P, S);
         double alpha = delta_new / rxo_dot3(S, P, n);
         for (uint64_t i = 0; i < n; ++i) out[i] += alpha * P[i], R[i] -= alpha * S[i];
+        for (uint64_t i = 0; i < n; ++i) Z[i] = precond ? (diag[i / 3] != 0 ? R[i] / diag[i / 3] : 0.0) : R[i];
         double delta_old = delta_new;
-        delta_new = rxo_dot3(R, R, n);
+        delta_new = rxo_dot3(R, Z, n);
         if (delta_new < tol_abs || delta_new / start < tol_rel) { conv = 1; break; }
         double beta = delta_new / delta_old;
-        for (uint64_t i = 0; i < n; ++i) P[i] = R[i] + beta * P[i];
+        for (uint64_t i = 0; i < n; ++i) P[i] = Z[i] + beta * P[i];
         ++it;
     }
     if (residual) {
@@ -879,6 +887,11 @@ int rxo_mcf_solve(const uint32_t* off, const uint32_t* val, uint32_t nv, const f
     info[0] = it, info[1] = conv, info[2] = start, info[3] = delta_new;
     free(W); free(buf);
     return 0;
+}
+int rxo_mcf_solve(const uint32_t* off, const uint32_t* val, uint32_t nv, const float* X0, double time_step, int uniform,
+                  uint32_t max_iter, double tol_abs, double tol_rel, double* out, double* residual, double* info)
+{
+    return rxo_mcf_solve_ex(off, val, nv, X0, time_step, uniform, 0, max_iter, tol_abs, tol_rel, out, residual, info);
 }
 /* B - A x for a candidate solution x (double): the size-independent check of a solve done elsewhere; also returns <B,B> */
 int rxo_mcf_residual(const uint32_t* off, const uint32_t* val, uint32_t nv, const float* X0, double time_step, int uniform,

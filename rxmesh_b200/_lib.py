@@ -77,6 +77,8 @@ SYMBOLS = {
     "rxm_bilateral_deferred": (C.c_uint64, [C.c_void_p]),
     "rxm_mcf_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_uint32, C.c_float, C.c_float,
                                 C.c_void_p, C.c_void_p]),
+    "rxm_mcf_solve_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_uint32, C.c_float,
+                                   C.c_float, C.c_void_p, C.c_void_p]),
     "rxm_query_csr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                 C.POINTER(C.c_uint64), C.c_void_p]),
     "rxm_boundary_vertices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1012,6 +1012,13 @@ int rxm_laplacian_smooth(rxm_mesh* m, rxm_attr* in, rxm_attr* out, double lr, ui
 int rxm_mcf_solve(rxm_mesh* m, rxm_attr* coords, rxm_attr* out, float time_step, int use_uniform_laplace, uint32_t max_iter,
                   float tol_abs, float tol_rel, rxm_mcf_info* info, void* stream)
 {
+    return rxm_mcf_solve_ex(m, coords, out, time_step, use_uniform_laplace, 0, max_iter, tol_abs, tol_rel, info, stream);
+}
+
+// jacobi != 0: mcf_pcg_mat_free (apps/MCF/mcf_cg_mat_free.h:181-254): PCGMatFreeAttrSolver with precond_matvec
+int rxm_mcf_solve_ex(rxm_mesh* m, rxm_attr* coords, rxm_attr* out, float time_step, int use_uniform_laplace, int jacobi,
+                     uint32_t max_iter, float tol_abs, float tol_rel, rxm_mcf_info* info, void* stream)
+{
     int rc = check_dev(m, "rxm_mcf_solve");
     if (rc) return rc;
     if (!is_vec3(coords) || !is_vec3(out) || coords == out)
@@ -1026,11 +1033,11 @@ int rxm_mcf_solve(rxm_mesh* m, rxm_attr* coords, rxm_attr* out, float time_step,
     if (coords->layout != RXM_AOS || out->layout != RXM_AOS) {
         rxm_attr *x, *y;
         if ((rc = aos_standin(m, coords, 4, true, stream, &x)) || (rc = aos_standin(m, out, 5, false, stream, &y))) return rc;
-        if ((rc = rxm_mcf_solve(m, x, y, time_step, use_uniform_laplace, max_iter, tol_abs, tol_rel, info, stream))) return rc;
+        if ((rc = rxm_mcf_solve_ex(m, x, y, time_step, use_uniform_laplace, jacobi, max_iter, tol_abs, tol_rel, info, stream))) return rc;
         return aos_writeback(m, out, y, stream);
     }
     cudaStream_t   st      = (cudaStream_t)stream;
-    const bool     uniform = use_uniform_laplace != 0;
+    const bool     uniform = use_uniform_laplace != 0, precond = jacobi != 0;
     const uint32_t P       = m->h.num_patches;
     if (!m->d_fan_base) {  // where every patch's slice of the weight array starts
         std::vector<uint32_t> fb(P);
@@ -1074,14 +1081,14 @@ int rxm_mcf_solve(rxm_mesh* m, rxm_attr* coords, rxm_attr* out, float time_step,
     const char* why = nullptr;
     cudaError_t e   = cudaMemsetAsync(base, 0, b_state + b_part, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out->d, coords->d, 12ull * slots, cudaMemcpyDeviceToDevice, st);  // X = X0
-    if (e == cudaSuccess) e = launch_mcf_setup(m->view, m->lim, (const float*)coords->d, B, uniform, time_step, st, &why);
+    if (e == cudaSuccess) e = launch_mcf_setup(m->view, m->lim, (const float*)coords->d, B, uniform, precond, time_step, st, &why);
     // iterations are queued in batches with no host synchronisation inside; the device-side state says when to stop (a
     // converged solve turns the rest of a batch into kernels that return at their first instruction)
     const uint32_t batch = 8;
     uint32_t       it    = 0;
     while (e == cudaSuccess) {
         for (uint32_t k = 0; k < batch && it < max_iter && e == cudaSuccess; ++k, ++it)
-            e = launch_mcf_iteration(m->view, m->lim, B, it, uniform, time_step, tol_abs, tol_rel, max_iter, st, &why);
+            e = launch_mcf_iteration(m->view, m->lim, B, it, uniform, precond, time_step, tol_abs, tol_rel, max_iter, st, &why);
         if (e == cudaSuccess) e = cudaMemcpyAsync(&hs, B.state, sizeof(McfState), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess || hs.converged || it >= max_iter) break;

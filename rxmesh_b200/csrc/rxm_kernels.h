@@ -127,11 +127,12 @@ struct McfBuffers
     uint32_t        partials_split;  // = number of patches
 };
 uint32_t    mcf_update_grid();
+// precond: Jacobi-preconditioned CG (the MCF app's pcg_mat_free: Z = R / diag, delta = <R, Z>)
 cudaError_t launch_mcf_setup(const MeshView& mv, const KernelLimits& lim, const float* x0_aos, const McfBuffers& B, bool uniform,
-                             float time_step, cudaStream_t stream, const char** err);
+                             bool precond, float time_step, cudaStream_t stream, const char** err);
 // iteration `it` (0-based): mat-vec kernel + update kernel
 cudaError_t launch_mcf_iteration(const MeshView& mv, const KernelLimits& lim, const McfBuffers& B, uint32_t it, bool uniform,
-                                 float time_step, float tol_abs, float tol_rel, uint32_t max_iter, cudaStream_t stream,
+                                 bool precond, float time_step, float tol_abs, float tol_rel, uint32_t max_iter, cudaStream_t stream,
                                  const char** err);
 void count_launches(uint64_t n);  // adds to launch_counter() (kernels launched from other translation units)
 

@@ -164,7 +164,7 @@ __device__ __forceinline__ void stage_issue(const Staged& s, const PatchDesc& d,
 // --------------------------------------------------------------------------
 // setup: W, diag, R0 = B - A X0, <R0, R0>           (init_B + the pre_solve mat-vec + init_PR + norm2, one pass)
 // --------------------------------------------------------------------------
-template <bool UNIFORM>
+template <bool UNIFORM, bool PRECOND>
 __global__ void __launch_bounds__(MBT) k_mcf_setup(MeshView mv, const float* __restrict__ x0, McfBuffers B, float dt)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -238,11 +238,16 @@ __global__ void __launch_bounds__(MBT) k_mcf_setup(MeshView mv, const float* __r
         }
         B.diag[d.slot_base[ELEM_V] + v] = dg;
         B.R[g + 3 * v] = r0, B.R[g + 3 * v + 1] = r1, B.R[g + 3 * v + 2] = r2;
-        part += (double)r0 * r0 + (double)r1 * r1 + (double)r2 * r2;
+        if (PRECOND) {  // delta = <R0, Z0>, Z0 = R0 / diag (precond_matvec, mcf_kernels.cuh:216-295)
+            const float z0 = dg != 0.f ? r0 / dg : 0.f, z1 = dg != 0.f ? r1 / dg : 0.f, z2 = dg != 0.f ? r2 / dg : 0.f;
+            part += (double)r0 * z0 + (double)r1 * z1 + (double)r2 * z2;
+        } else {
+            part += (double)r0 * r0 + (double)r1 * r1 + (double)r2 * r2;
+        }
     }
     part = block_sum(part, s_red);
     if (publish_partial(part, B.partials, &B.state->ctr, &s_flag)) {
-        const double a = sum_partials(B.partials, s_red);
+        const double a = fabs(sum_partials(B.partials, s_red));  // pcg_mat_free_attr_solver.h:61-62 takes |<R, P>|
         if (threadIdx.x == 0) {
             McfState* st  = B.state;
             st->ctr       = 0;
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(MBT) k_mcf_setup(MeshView mv, const float* __r
 // BT: the launcher picks the block size that leaves the fewest idle threads in the last round over the owned vertices
 // (561-vertex tiles: 3 x 192 instead of 256 + 256 + 49).  FIRST: iteration 0, P' = R (beta = 0; P is not read, so the
 // solve needs no zeroed P buffer).
-template <bool UNIFORM, int BT>
+template <bool UNIFORM, int BT, bool PRECOND>
 __global__ void __launch_bounds__(BT, 1536 / BT) k_mcf_matvec(MeshView mv, McfBuffers B, const float* __restrict__ Pold,
                                                    float* __restrict__ Pnew, float dt, int first)
 {
@@ -302,6 +307,7 @@ __global__ void __launch_bounds__(BT, 1536 / BT) k_mcf_matvec(MeshView mv, McfBu
     // previous store (R comes through a struct member, it may alias P') and the block pays one DRAM latency per step
     // (profiles/r02M: 14.8 us per block, long-scoreboard 18 per issue).
     {
+        const float*  dgp = B.diag + d.slot_base[ELEM_V];  // PRECOND: Z = R / diag stands where R stands (P' = Z + beta P)
         const float4* R4 = reinterpret_cast<const float4*>(B.R + g);
         const float4* O4 = reinterpret_cast<const float4*>(Pold + g);
         float4*       N4 = reinterpret_cast<float4*>(Pnew + g);
@@ -316,6 +322,13 @@ __global__ void __launch_bounds__(BT, 1536 / BT) k_mcf_matvec(MeshView mv, McfBu
                 if (j < n4) {
                     r[k] = __ldg(R4 + j);
                     if (!first) o[k] = __ldg(O4 + j);
+                    if (PRECOND) {
+                        const uint32_t e  = 4u * j;  // element e belongs to vertex e / 3
+                        const float    d0 = __ldg(dgp + e / 3u), d1 = __ldg(dgp + (e + 1u) / 3u), d2 = __ldg(dgp + (e + 2u) / 3u),
+                                    d3 = __ldg(dgp + (e + 3u) / 3u);
+                        r[k].x = d0 != 0.f ? r[k].x / d0 : 0.f, r[k].y = d1 != 0.f ? r[k].y / d1 : 0.f;
+                        r[k].z = d2 != 0.f ? r[k].z / d2 : 0.f, r[k].w = d3 != 0.f ? r[k].w / d3 : 0.f;
+                    }
                 }
             }
 #pragma unroll
@@ -338,7 +351,11 @@ __global__ void __launch_bounds__(BT, 1536 / BT) k_mcf_matvec(MeshView mv, McfBu
     for (uint32_t i = nov + threadIdx.x; i < nv; i += BT) {
         const uint32_t o = T.own[i - nov];
         const uint64_t s = 3ull * ((uint64_t)T.stash[o >> 16].slot_base[ELEM_V] + (o & 0xFFFFu));
-        const float    r0 = __ldg(B.R + s), r1 = __ldg(B.R + s + 1), r2 = __ldg(B.R + s + 2);
+        float          r0 = __ldg(B.R + s), r1 = __ldg(B.R + s + 1), r2 = __ldg(B.R + s + 2);
+        if (PRECOND) {
+            const float dr = __ldg(B.diag + s / 3ull);
+            r0 = dr != 0.f ? r0 / dr : 0.f, r1 = dr != 0.f ? r1 / dr : 0.f, r2 = dr != 0.f ? r2 / dr : 0.f;
+        }
         if (first) {
             s_p[3 * i] = r0, s_p[3 * i + 1] = r1, s_p[3 * i + 2] = r2;
         } else {
@@ -401,6 +418,7 @@ __global__ void __launch_bounds__(BT, 1536 / BT) k_mcf_matvec(MeshView mv, McfBu
 // --------------------------------------------------------------------------
 // iteration, second half: X += alpha P', R -= alpha S, <R, R>; then the scalar step of the solver
 // --------------------------------------------------------------------------
+template <bool PRECOND>
 __global__ void __launch_bounds__(MBT) k_mcf_update(uint64_t n4, McfBuffers B, const float4* __restrict__ P, float tol_abs,
                                                     float tol_rel, uint32_t max_iter)
 {
@@ -408,20 +426,49 @@ __global__ void __launch_bounds__(MBT) k_mcf_update(uint64_t n4, McfBuffers B, c
     __shared__ double   s_red[MBT / 32];
     __shared__ uint32_t s_flag;
     const float         alpha = B.state->alpha;
-    float4*             X     = reinterpret_cast<float4*>(B.X);
-    float4*             R     = reinterpret_cast<float4*>(B.R);
-    const float4*       S     = reinterpret_cast<const float4*>(B.S);
-    double              part  = 0.0;
-    for (uint64_t i = blockIdx.x * (uint64_t)MBT + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * MBT) {
-        const float4 p = P[i], s = S[i];
-        float4       x = X[i], r = R[i];
-        // axpy(X, P, alpha, 1): X = alpha P + X;  axpy(R, S, -alpha, 1): R = -alpha S + R
+    float4* __restrict__       X = reinterpret_cast<float4*>(B.X);
+    float4* __restrict__       R = reinterpret_cast<float4*>(B.R);
+    const float4* __restrict__ S = reinterpret_cast<const float4*>(B.S);
+    double                     part = 0.0;
+    // axpy(X, P, alpha, 1): X = alpha P + X;  axpy(R, S, -alpha, 1): R = -alpha S + R
+    // PRECOND: delta = <R, Z> with Z = R / diag; dg = the diagonals of the (at most two) vertices the four elements belong to
+    auto step = [&](float4 p, float4 s, float4& x, float4& r, float4 dg) {
         x.x = __fmaf_rn(alpha, p.x, x.x), x.y = __fmaf_rn(alpha, p.y, x.y), x.z = __fmaf_rn(alpha, p.z, x.z),
         x.w = __fmaf_rn(alpha, p.w, x.w);
         r.x = __fmaf_rn(-alpha, s.x, r.x), r.y = __fmaf_rn(-alpha, s.y, r.y), r.z = __fmaf_rn(-alpha, s.z, r.z),
         r.w = __fmaf_rn(-alpha, s.w, r.w);
-        X[i] = x, R[i] = r;
-        part += (double)r.x * r.x + (double)r.y * r.y + (double)r.z * r.z + (double)r.w * r.w;
+        if (PRECOND) {
+            const float zx = dg.x != 0.f ? r.x / dg.x : 0.f, zy = dg.y != 0.f ? r.y / dg.y : 0.f,
+                        zz = dg.z != 0.f ? r.z / dg.z : 0.f, zw = dg.w != 0.f ? r.w / dg.w : 0.f;
+            part += (double)r.x * zx + (double)r.y * zy + (double)r.z * zz + (double)r.w * zw;
+        } else {
+            part += (double)r.x * r.x + (double)r.y * r.y + (double)r.z * r.z + (double)r.w * r.w;
+        }
+    };
+    auto diag4 = [&](uint64_t i) {  // element 4 i + c belongs to slot (4 i + c) / 3
+        if (!PRECOND) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint64_t e = 4ull * i;
+        return make_float4(__ldg(B.diag + e / 3ull), __ldg(B.diag + (e + 1ull) / 3ull), __ldg(B.diag + (e + 2ull) / 3ull),
+                           __ldg(B.diag + (e + 3ull) / 3ull));
+    };
+    // two elements per trip, all eight loads before the first store (see k_mcf_matvec on why)
+    const uint64_t stride = (uint64_t)gridDim.x * MBT;
+    uint64_t       i      = blockIdx.x * (uint64_t)MBT + threadIdx.x;
+    for (; i + stride < n4; i += 2 * stride) {
+        const uint64_t k  = i + stride;
+        const float4   p0 = __ldg(P + i), s0 = __ldg(S + i), p1 = __ldg(P + k), s1 = __ldg(S + k);
+        const float4   d0 = diag4(i), d1 = diag4(k);
+        float4         x0 = X[i], r0 = R[i], x1 = X[k], r1 = R[k];
+        step(p0, s0, x0, r0, d0);
+        step(p1, s1, x1, r1, d1);
+        X[i] = x0, R[i] = r0, X[k] = x1, R[k] = r1;
+    }
+    if (i < n4) {
+        const float4 p0 = __ldg(P + i), s0 = __ldg(S + i);
+        const float4 d0 = diag4(i);
+        float4       x0 = X[i], r0 = R[i];
+        step(p0, s0, x0, r0, d0);
+        X[i] = x0, R[i] = r0;
     }
     part = block_sum(part, s_red);
     if (publish_partial(part, B.partials + B.partials_split, &B.state->ctr, &s_flag)) {
@@ -475,24 +522,50 @@ uint32_t mcf_update_grid()
     return 148u * 8u;
 }
 
+namespace {
+template <bool U, bool PC>
+cudaError_t launch_mv(int bt, const MeshView& mv, const McfBuffers& B, const float* pold, float* pnew, float dt, int first,
+                      uint32_t smem, cudaStream_t stream)
+{
+    cudaError_t e = cudaSuccess;
+#define RXM_MCF_MV(BTV)                                                                                              \
+    do {                                                                                                             \
+        e = mcf_set_smem(k_mcf_matvec<U, BTV, PC>, smem);                                                            \
+        if (e == cudaSuccess) k_mcf_matvec<U, BTV, PC><<<mv.num_patches, BTV, smem, stream>>>(mv, B, pold, pnew, dt, first); \
+    } while (0)
+    if (bt == 128) RXM_MCF_MV(128);
+    else if (bt == 192) RXM_MCF_MV(192);
+    else if (bt == 288) RXM_MCF_MV(288);
+    else RXM_MCF_MV(256);
+#undef RXM_MCF_MV
+    return e;
+}
+}  // namespace
+
 cudaError_t launch_mcf_setup(const MeshView& mv, const KernelLimits& lim, const float* x0, const McfBuffers& B, bool uniform,
-                             float dt, cudaStream_t stream, const char** err)
+                             bool precond, float dt, cudaStream_t stream, const char** err)
 {
     if (!mv.fans) RXM_MCF_FAIL("the mesh stores no one-ring fans (non-manifold or inconsistently oriented input)");
     const uint32_t capv = lim.max_owned[ELEM_V] + 4u;
     const uint32_t smem = staged_smem(lim) + a16(12u * std::max(lim.max_n[ELEM_V], capv) + 16u) + 64u;
-    cudaError_t    e    = uniform ? mcf_set_smem(k_mcf_setup<true>, smem) : mcf_set_smem(k_mcf_setup<false>, smem);
+    cudaError_t    e;
+#define RXM_MCF_SETUP(U, PC)                                                                        \
+    do {                                                                                            \
+        e = mcf_set_smem(k_mcf_setup<U, PC>, smem);                                                 \
+        if (e == cudaSuccess) k_mcf_setup<U, PC><<<mv.num_patches, MBT, smem, stream>>>(mv, x0, B, dt); \
+    } while (0)
+    if (uniform && precond) RXM_MCF_SETUP(true, true);
+    else if (uniform) RXM_MCF_SETUP(true, false);
+    else if (precond) RXM_MCF_SETUP(false, true);
+    else RXM_MCF_SETUP(false, false);
+#undef RXM_MCF_SETUP
     if (e != cudaSuccess) RXM_MCF_FAIL("patch needs more shared memory than 227 KB");
-    if (uniform)
-        k_mcf_setup<true><<<mv.num_patches, MBT, smem, stream>>>(mv, x0, B, dt);
-    else
-        k_mcf_setup<false><<<mv.num_patches, MBT, smem, stream>>>(mv, x0, B, dt);
     count_launches(1);
     return cudaGetLastError();
 }
 
 cudaError_t launch_mcf_iteration(const MeshView& mv, const KernelLimits& lim, const McfBuffers& B, uint32_t it, bool uniform,
-                                 float dt, float tol_abs, float tol_rel, uint32_t max_iter, cudaStream_t stream,
+                                 bool precond, float dt, float tol_abs, float tol_rel, uint32_t max_iter, cudaStream_t stream,
                                  const char** err)
 {
     const uint32_t capv = lim.max_owned[ELEM_V] + 4u;
@@ -509,29 +582,19 @@ cudaError_t launch_mcf_iteration(const MeshView& mv, const KernelLimits& lim, co
     const float* pold  = B.P[it & 1u];
     float*       pnew  = B.P[(it + 1u) & 1u];
     const int    first = it == 0;
-    cudaError_t  e     = cudaSuccess;
-#define RXM_MCF_MV(U, BTV)                                                                                      \
-    do {                                                                                                        \
-        e = mcf_set_smem(k_mcf_matvec<U, BTV>, smem);                                                           \
-        if (e == cudaSuccess) k_mcf_matvec<U, BTV><<<mv.num_patches, BTV, smem, stream>>>(mv, B, pold, pnew, dt, first); \
-    } while (0)
-    if (uniform) {
-        if (bt == 128) RXM_MCF_MV(true, 128);
-        else if (bt == 192) RXM_MCF_MV(true, 192);
-        else if (bt == 288) RXM_MCF_MV(true, 288);
-        else RXM_MCF_MV(true, 256);
-    } else {
-        if (bt == 128) RXM_MCF_MV(false, 128);
-        else if (bt == 192) RXM_MCF_MV(false, 192);
-        else if (bt == 288) RXM_MCF_MV(false, 288);
-        else RXM_MCF_MV(false, 256);
-    }
-#undef RXM_MCF_MV
+    cudaError_t  e;
+    if (uniform && precond) e = launch_mv<true, true>(bt, mv, B, pold, pnew, dt, first, smem, stream);
+    else if (uniform) e = launch_mv<true, false>(bt, mv, B, pold, pnew, dt, first, smem, stream);
+    else if (precond) e = launch_mv<false, true>(bt, mv, B, pold, pnew, dt, first, smem, stream);
+    else e = launch_mv<false, false>(bt, mv, B, pold, pnew, dt, first, smem, stream);
     if (e != cudaSuccess) RXM_MCF_FAIL("patch needs more shared memory than 227 KB");
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const uint64_t n4 = 3ull * mv.num_slots[ELEM_V] / 4ull;  // slot caps are multiples of 4: 3 * slots floats = n4 float4
-    k_mcf_update<<<mcf_update_grid(), MBT, 0, stream>>>(n4, B, reinterpret_cast<const float4*>(pnew), tol_abs, tol_rel, max_iter);
+    if (precond)
+        k_mcf_update<true><<<mcf_update_grid(), MBT, 0, stream>>>(n4, B, reinterpret_cast<const float4*>(pnew), tol_abs, tol_rel, max_iter);
+    else
+        k_mcf_update<false><<<mcf_update_grid(), MBT, 0, stream>>>(n4, B, reinterpret_cast<const float4*>(pnew), tol_abs, tol_rel, max_iter);
     count_launches(2);
     return cudaGetLastError();
 }

@@ -465,12 +465,14 @@ class RXMeshStatic:
         check(lib().rxm_bilateral_filter(self._h, inp._h, out._h, int(iters), _stream_ptr(stream)))
 
     def mcf_solve(self, coords, out, time_step=10.0, use_uniform_laplace=True, max_iter=100, tol_abs=1e-6, tol_rel=0.0,
-                  stream=None):
-        """Mean-curvature flow by matrix-free CG (apps/MCF/mcf_cg_mat_free.h; defaults of apps/MCF/mcf.cu:19-23).
+                  stream=None, precondition=False):
+        """Mean-curvature flow by matrix-free CG (apps/MCF/mcf_cg_mat_free.h; defaults of apps/MCF/mcf.cu:19-23);
+        precondition: the Jacobi-preconditioned solver of the same file (mcf_pcg_mat_free).
         Returns dict(iterations, converged, start_residual, final_residual) like the solver's getters."""
         buf = np.zeros(4, dtype=np.uint32)
-        check(lib().rxm_mcf_solve(self._h, coords._h, out._h, float(time_step), int(bool(use_uniform_laplace)), int(max_iter),
-                                  float(tol_abs), float(tol_rel), buf.ctypes.data, _stream_ptr(stream)))
+        check(lib().rxm_mcf_solve_ex(self._h, coords._h, out._h, float(time_step), int(bool(use_uniform_laplace)),
+                                     int(bool(precondition)), int(max_iter), float(tol_abs), float(tol_rel), buf.ctypes.data,
+                                     _stream_ptr(stream)))
         f = buf.view(np.float32)
         return dict(iterations=int(buf[0]), converged=bool(buf[1]), start_residual=float(f[2]), final_residual=float(f[3]))
 
