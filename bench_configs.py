@@ -206,9 +206,10 @@ def mcf_cg(torch, rx, stream, m, V, F):
     out = {"what": "MCF, matrix-free CG, %d vertices (the noisy torus of this config, 32x16-quad tiles)" % nV}
     rings = O.oriented_rings(F, nV)
     scale = float(np.abs(V).max())
-    for label, uniform, dt, ta, tr in (("uniform_laplace_app_defaults", True, 10.0, 1e-6, 0.0),
-                                       ("cotangent_laplace", False, 1e-5, 0.0, 1e-6)):
-        kw = dict(time_step=dt, use_uniform_laplace=uniform, max_iter=100, tol_abs=ta, tol_rel=tr, stream=stream)
+    for label, uniform, dt, ta, tr, pc in (("uniform_laplace_app_defaults", True, 10.0, 1e-6, 0.0, False),
+                                           ("cotangent_laplace", False, 1e-5, 0.0, 1e-6, False),
+                                           ("uniform_laplace_jacobi_pcg", True, 10.0, 1e-6, 0.0, True)):
+        kw = dict(time_step=dt, use_uniform_laplace=uniform, max_iter=100, tol_abs=ta, tol_rel=tr, stream=stream, precondition=pc)
         m.mcf_solve(x0, x, **kw)  # warm-up (allocations, module load)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -221,11 +222,12 @@ def mcf_cg(torch, rx, stream, m, V, F):
         steps = info["iterations"] + (1 if info["converged"] else 0)  # mat-vec + update pairs that did work
         # algorithmic bytes per vertex: setup 12 (X0) + 12 (fan ids) + 12 (R) + 4 (diag) [+ 24 (W)] + 24 (X = X0 copy);
         # iteration: mat-vec 24 (R, P) + 12 (fan ids) + 4 (diag) [+ 24 (W)] + 24 (P', S), update 48 (X, R, P', S) + 24 (X, R)
-        per_it = (136.0 if uniform else 160.0) * nV
+        # (the Jacobi-preconditioned form reads the diagonal twice more per iteration: + 8)
+        per_it = ((136.0 if uniform else 160.0) + (8.0 if pc else 0.0)) * nV
         setup = (64.0 if uniform else 88.0) * nV
         gbs = (setup + per_it * steps) / (ms * 1e-3) / 1e9
         t0 = time.perf_counter()
-        ref, oinfo = O.mcf_solve(rings, V, dt, uniform, 100, ta, tr)
+        ref, oinfo = O.mcf_solve(rings, V, dt, uniform, 100, ta, tr, precond=pc)
         t_cpu = time.perf_counter() - t0
         res, bb = O.mcf_residual(rings, V, got, dt, uniform)
         r2 = float((res ** 2).sum())
@@ -234,7 +236,7 @@ def mcf_cg(torch, rx, stream, m, V, F):
         tol = 1e-5 * scale + move * float(np.sqrt(max(oinfo["final_residual"] / oinfo["start_residual"], 0.0)))
         ok = bool(info["converged"] and oinfo["converged"] and abs(info["iterations"] - oinfo["iterations"]) <= 2 + oinfo["iterations"] // 10
                   and err < tol)
-        out[label] = {"time_step": dt, "tol_abs": ta, "tol_rel": tr, "iterations": info["iterations"], "converged": info["converged"],
+        out[label] = {"time_step": dt, "tol_abs": ta, "tol_rel": tr, "jacobi_preconditioner": pc, "iterations": info["iterations"], "converged": info["converged"],
                       "start_residual": info["start_residual"], "final_residual": info["final_residual"],
                       "ms_total": ms, "ms_per_iteration": ms / max(steps, 1), "vertex_iterations_per_s": nV * steps / (ms * 1e-3),
                       "alg_bytes_per_vertex_iteration": per_it / nV, "achieved_gbs": gbs, "hbm_frac": gbs / peak,

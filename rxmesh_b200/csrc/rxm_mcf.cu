@@ -340,8 +340,16 @@ __global__ void __launch_bounds__(BT, 1536 / BT) k_mcf_matvec(MeshView mv, McfBu
                     pn.y = 4u * j + 1u < lim ? (first ? r[k].y : __fmaf_rn(beta, o[k].y, r[k].y)) : 0.f;
                     pn.z = 4u * j + 2u < lim ? (first ? r[k].z : __fmaf_rn(beta, o[k].z, r[k].z)) : 0.f;
                     pn.w = 4u * j + 3u < lim ? (first ? r[k].w : __fmaf_rn(beta, o[k].w, r[k].w)) : 0.f;
-                    s4[j] = pn;
                     N4[j] = pn;
+                    // shared memory: the OWNED rows only.  The floats from 3 * nov on belong to the ribbon rows, which other
+                    // threads fill below without a barrier in between -- zeros written here would race with them
+                    if (4u * j + 3u < lim) {
+                        s4[j] = pn;
+                    } else {
+                        if (4u * j < lim) s_p[4u * j] = pn.x;
+                        if (4u * j + 1u < lim) s_p[4u * j + 1u] = pn.y;
+                        if (4u * j + 2u < lim) s_p[4u * j + 2u] = pn.z;
+                    }
                 }
             }
         }

@@ -23,7 +23,8 @@ for name, ps in (("sphere3", 64), ("ico10", 128)):
     x = rx.Attribute(m, 0, np.float32, 3, rx.LOCATION_ALL, rx.AoS)
     x0.from_global(V)
     for uniform, dt in ((True, 10.0), (False, 1e-2)):
-        info = m.mcf_solve(x0, x, time_step=dt, use_uniform_laplace=uniform, max_iter=12, tol_abs=1e-6, tol_rel=0.0)
-        assert np.isfinite(x.to_global()).all()
-        print(name, "uniform" if uniform else "cotangent", info, flush=True)
+        for pc in (False, True):
+            info = m.mcf_solve(x0, x, time_step=dt, use_uniform_laplace=uniform, max_iter=12, tol_abs=1e-6, tol_rel=0.0, precondition=pc)
+            assert np.isfinite(x.to_global()).all()
+            print(name, "uniform" if uniform else "cotangent", "pcg" if pc else "cg", info, flush=True)
 print("mcf ok", flush=True)

@@ -4,12 +4,14 @@
 // of the reference apps (apps/VertexNormal/vertex_normal_kernel.cuh:10-43, apps/Smoothing/manual.h:86-104,
 // tests/RXMesh_test/query_kernel.cuh:13-46) so that a reader can see the same call sites compile unchanged.
 // Exposed through extern "C" so tests/test_gpu_shim.py can drive it with ctypes.
+#include <memory>
 #include <vector>
 
 #include "rxmesh/attribute.h"
 #include "rxmesh/geometry_util.cuh"
 #include "rxmesh/kernels/query_dispatcher.cuh"
 #include "rxmesh/matrix/cg_mat_free_attr_solver.h"
+#include "rxmesh/matrix/pcg_mat_free_attr_solver.h"
 #include "rxmesh/query.h"
 #include "rxmesh/reduce_handle.h"
 #include "rxmesh/rxmesh_static.h"
@@ -109,6 +111,40 @@ __global__ static void user_mcf_matvec(const Context context, const VertexAttrib
     Query<blockThreads> query(context);
     ShmemAllocator      shrd_alloc;
     query.template dispatch<Op::VV>(block, shrd_alloc, matvec_lambda, [](VertexHandle) { return true; }, true);
+}
+#endif
+
+// the Jacobi preconditioner of the MCF system (apps/MCF/mcf_kernels.cuh:216-295): out = in / diagonal of the mat-vec above
+#if RXM_REFSRC != 1
+template <typename T, uint32_t blockThreads>
+__global__ static void user_mcf_precond(const Context context, const VertexAttribute<T> coords, const VertexAttribute<T> in,
+                                        VertexAttribute<T> out, const T time_step)
+{
+    auto lambda = [&](VertexHandle& p_id, const VertexIterator& iter) {
+        T             sum_e_weight(0), v_weight(0);
+        const vec3<T> p    = coords.template to_glm<3>(p_id);
+        VertexHandle  q_id = iter.back();
+        for (uint32_t v = 0; v < iter.size(); ++v) {
+            VertexHandle  r_id = iter[v];
+            VertexHandle  s_id = (v == iter.size() - 1) ? iter[0] : iter[v + 1];
+            const vec3<T> r = coords.template to_glm<3>(r_id), q = coords.template to_glm<3>(q_id),
+                          s = coords.template to_glm<3>(s_id);
+            T e_weight = edge_cotan_weight(p, r, q, s);
+            e_weight   = (static_cast<T>(e_weight >= 0.0)) * e_weight;
+            sum_e_weight += e_weight * time_step;
+            T tri = partial_voronoi_area(p, q, r);
+            v_weight += (tri > 0) ? tri : 0;
+            q_id = r_id;
+        }
+        v_weight = 0.5 / v_weight;
+        T diag   = ((1.0 / v_weight) + sum_e_weight);
+        for (uint32_t i = 0; i < 3; ++i)
+            out(p_id, i) = in(p_id, i) / diag;
+    };
+    auto                block = cooperative_groups::this_thread_block();
+    Query<blockThreads> query(context);
+    ShmemAllocator      shrd_alloc;
+    query.template dispatch<Op::VV>(block, shrd_alloc, lambda, [](VertexHandle) { return true; }, true);
 }
 #endif
 
@@ -497,7 +533,7 @@ static int app_mcf_matvec(const uint32_t* fv, uint32_t nf, const float* x, const
 // RXM_REFSRC == 1 both kernels are the reference's own (apps/MCF/mcf_kernels.cuh, unmodified, either Laplacian); otherwise the
 // restated cotangent mat-vec above, with B = M X0 taken from a mat-vec at time step 0.  info: iterations, start, final residual.
 static int app_mcf_cg(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, float time_step,
-                      int uniform, int max_iter, float tol_abs, float tol_rel, float* out, float* info)
+                      int uniform, int pcg, int max_iter, float tol_abs, float tol_rel, float* out, float* info)
 {
     rx_init(0);
     RXMeshStatic rx(to_faces(fv, nf), "", patch_size);
@@ -525,10 +561,28 @@ static int app_mcf_cg(const uint32_t* fv, uint32_t nf, const float* x, uint32_t 
         rx.run_kernel(lb, user_mcf_matvec<float, blockThreads>, stream, *coords, in, o, time_step);
     };
 #endif
+    // pcg: mcf_pcg_mat_free (mcf_cg_mat_free.h:181-254): the Jacobi kernel as the second std::function
+    LaunchBox<blockThreads> plb;
+#if RXM_REFSRC == 1
+    rx.prepare_launch_box({Op::VV}, plb, (void*)precond_matvec<float, blockThreads>, !uni);
+    auto precond = [&](const VertexAttribute<float>& in, VertexAttribute<float>& o, cudaStream_t stream) {
+        rx.run_kernel(plb, precond_matvec<float, blockThreads>, stream, *coords, in, o, uni, time_step);
+    };
+#else
+    rx.prepare_launch_box({Op::VV}, plb, (void*)user_mcf_precond<float, blockThreads>, true);
+    auto precond = [&](const VertexAttribute<float>& in, VertexAttribute<float>& o, cudaStream_t stream) {
+        rx.run_kernel(plb, user_mcf_precond<float, blockThreads>, stream, *coords, in, o, time_step);
+    };
+#endif
     if (cudaDeviceSynchronize() != cudaSuccess) return 1;
-    CGMatFreeAttrSolver<float, VertexHandle> solver(rx, mat_vec, 3, max_iter, tol_abs, tol_rel);
-    solver.pre_solve(*B, *X);
-    solver.solve(*B, *X);
+    std::unique_ptr<IterativeSolver<float, VertexAttribute<float>>> sp;  // one solver: both register the attributes CG:S / P / R
+    if (pcg)
+        sp.reset(new PCGMatFreeAttrSolver<float, VertexHandle>(rx, mat_vec, precond, 3, max_iter, tol_abs, tol_rel));
+    else
+        sp.reset(new CGMatFreeAttrSolver<float, VertexHandle>(rx, mat_vec, 3, max_iter, tol_abs, tol_rel));
+    IterativeSolver<float, VertexAttribute<float>>& solver = *sp;
+    solver.pre_solve(*B, *X, NULL);
+    solver.solve(*B, *X, NULL);
     if (cudaDeviceSynchronize() != cudaSuccess) return 1;
     info[0] = (float)solver.iter_taken(), info[1] = solver.start_residual(), info[2] = solver.final_residual();
     X->move(DEVICE, HOST);
@@ -1246,9 +1300,9 @@ int shim_mcf_matvec(const uint32_t* fv, uint32_t nf, const float* x, const float
     return app_mcf_matvec(fv, nf, x, vin, nv, patch_size, time_step, out);
 }
 int shim_mcf_cg(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, float time_step, int uniform,
-                int max_iter, float tol_abs, float tol_rel, float* out, float* info)
+                int pcg, int max_iter, float tol_abs, float tol_rel, float* out, float* info)
 {
-    return app_mcf_cg(fv, nf, x, nv, patch_size, time_step, uniform, max_iter, tol_abs, tol_rel, out, info);
+    return app_mcf_cg(fv, nf, x, nv, patch_size, time_step, uniform, pcg, max_iter, tol_abs, tol_rel, out, info);
 }
 int shim_gaussian_curvature(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, float* out_gcs,
                             float* out_amix)

@@ -171,22 +171,26 @@ def test_user_mcf_matvec(shim, name):
     assert rel.max() < 1e-3, rel.max()
 
 
+@pytest.mark.parametrize("pcg", [0, 1])
 @pytest.mark.parametrize("name,uniform", [("sphere3", 0), ("torus40x30", 0), ("dragon", 0), ("sphere3", 1), ("dragon", 1)])
-def test_user_mcf_cg(shim, name, uniform, kernels_have_uniform=False):
+def test_user_mcf_cg(shim, name, uniform, pcg, kernels_have_uniform=False):
     """The MCF app's solve (apps/MCF/mcf_cg_mat_free.h) as user code: init_B + CGMatFreeAttrSolver (drop-in header
     rxmesh/matrix/cg_mat_free_attr_solver.h) over the mat-vec kernel, against the float64 oracle solve AND against the
     fixed-function rxm_mcf_solve -- two independent GPU paths (generic for_each / ReduceHandle / user kernel vs the fused
-    two-kernel iteration) that must give the same iteration count and the same solution."""
+    two-kernel iteration) that must give the same iteration count and the same solution.  pcg: PCGMatFreeAttrSolver with the
+    Jacobi kernel (mcf_pcg_mat_free) against the oracle's preconditioned solve and rxm_mcf_solve_ex(jacobi = 1)."""
     if uniform and not kernels_have_uniform:
         pytest.skip("the restated mat-vec kernel of shim_apps.cu has the cotangent weights only (the reference's own has both)")
     V, F = make_mesh(name)
     V = np.ascontiguousarray(V, np.float32)
     dt, ta, tr, mi = (10.0, 1e-6, 0.0, 200) if uniform else (1e-2, 0.0, 1e-9, 500)
     out, info = np.zeros_like(V), np.zeros(3, np.float32)
-    assert shim.shim_mcf_cg(_p(F), F.shape[0], _p(V), V.shape[0], 512, C.c_float(dt), uniform, mi, C.c_float(ta), C.c_float(tr),
+    if pcg:
+        ta, tr = 0.0, 1e-9  # its residual is <R, M^-1 R>: compare solutions at a relative tolerance
+    assert shim.shim_mcf_cg(_p(F), F.shape[0], _p(V), V.shape[0], 512, C.c_float(dt), uniform, pcg, mi, C.c_float(ta), C.c_float(tr),
                             _p(out), _p(info)) == 0
     rings = O.oriented_rings(F, V.shape[0])
-    ref, oinfo = O.mcf_solve(rings, V, dt, bool(uniform), mi, ta, tr)
+    ref, oinfo = O.mcf_solve(rings, V, dt, bool(uniform), mi, ta, tr, precond=bool(pcg))
     scale = np.abs(V).max()
     slack = 2 + oinfo["iterations"] // 10
     assert abs(int(info[0]) - oinfo["iterations"]) <= slack, (info, oinfo)
@@ -197,7 +201,8 @@ def test_user_mcf_cg(shim, name, uniform, kernels_have_uniform=False):
     x0 = m.add_vertex_attribute("cg_x0", np.float32, 3, rx.LOCATION_ALL, rx.AoS)
     x1 = m.add_vertex_attribute("cg_x1", np.float32, 3, rx.LOCATION_ALL, rx.AoS)
     x0.from_global(V)
-    finfo = m.mcf_solve(x0, x1, time_step=dt, use_uniform_laplace=bool(uniform), max_iter=mi, tol_abs=ta, tol_rel=tr)
+    finfo = m.mcf_solve(x0, x1, time_step=dt, use_uniform_laplace=bool(uniform), max_iter=mi, tol_abs=ta, tol_rel=tr,
+                        precondition=bool(pcg))
     got = x1.to_global()
     assert abs(finfo["iterations"] - int(info[0])) <= slack, (finfo, info)
     assert np.abs(got - out).max() < (1e-5 if uniform else 5e-5) * scale, np.abs(got - out).max()

@@ -63,6 +63,21 @@ def test_oracle_sphere_shrinks_uniformly():
     assert cosang.min() > 0.999
 
 
+@pytest.mark.parametrize("name", CLOSED)
+@pytest.mark.parametrize("uniform", [True, False])
+def test_oracle_jacobi_pcg_solves_the_same_system(name, uniform):
+    """The preconditioned form (pcg_mat_free_attr_solver.h:40-140 with precond_matvec) reaches the same solution; its
+    residual is measured in the M^-1 norm, so compare at tight relative tolerances."""
+    V, F = _mesh(name)
+    rings = O.oriented_rings(F, V.shape[0])
+    dt = 10.0 if uniform else 1e-2
+    a, ia = O.mcf_solve(rings, V, dt, uniform, 1000, 0.0, 1e-14)
+    b, ib, res = O.mcf_solve(rings, V, dt, uniform, 1000, 0.0, 1e-14, with_residual=True, precond=True)
+    assert ia["converged"] and ib["converged"] and ib["iterations"] <= ia["iterations"]
+    assert np.abs(a - b).max() < 1e-7 * np.abs(V).max()
+    assert (res ** 2).sum() < 1e-10 * ia["start_residual"]
+
+
 def test_oracle_zero_iterations_and_max_iter():
     V, F = _mesh("sphere3")
     rings = O.oriented_rings(F, V.shape[0])
@@ -136,6 +151,45 @@ def test_gpu_solve_vs_oracle(name, uniform):
         assert info["converged"] and abs(info["iterations"] - oinfo["iterations"]) <= 2 + oinfo["iterations"] // 10
         res, bb = O.mcf_residual(rings, V, got, dt, False)
         assert (res ** 2).sum() < 10.0 * (1e-6 + floor2)
+
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CLOSED + ["ico40"])
+@pytest.mark.parametrize("uniform", [True, False])
+def test_gpu_jacobi_pcg_vs_oracle(name, uniform):
+    """rxm_mcf_solve_ex(jacobi = 1) against the oracle's preconditioned solve: the three-iteration state, then the converged
+    solve (same iteration count, same solution, the system solved).  Tolerances as in test_gpu_solve_vs_oracle."""
+    import rxmesh_b200 as rx
+    rx.rx_init(0)
+    V, F = _mesh(name)
+    m = rx.RXMeshStatic(F, patch_size=512 if F.shape[0] > 600 else 64)
+    rings = O.oriented_rings(F, V.shape[0])
+    dt = 10.0 if uniform else 1e-2
+    scale = np.abs(V).max()
+    floor2, mag = _res_floor(V, dt, uniform, rings)
+    got3, info3 = _gpu_solve(m, rx, V, time_step=dt, use_uniform_laplace=uniform, max_iter=3, tol_abs=0.0, tol_rel=0.0,
+                             precondition=True)
+    ref3, oinfo3 = O.mcf_solve(rings, V, dt, uniform, 3, 0.0, 0.0, precond=True)
+    plain3, pinfo3 = O.mcf_solve(rings, V, dt, uniform, 3, 0.0, 0.0)
+    assert info3["iterations"] == 3 and not info3["converged"]
+    rho = 3e-7 * mag.max() / np.sqrt(pinfo3["start_residual"] / (3 * V.shape[0]))
+    tol3 = 1e-5 * scale + (0.0 if uniform else 10.0 * rho * np.abs(ref3 - V).max())
+    assert np.abs(got3 - ref3).max() < tol3, (name, uniform, np.abs(got3 - ref3).max(), tol3)
+    assert abs(info3["start_residual"] - oinfo3["start_residual"]) < (1e-4 + 20 * rho) * oinfo3["start_residual"]
+    ta, tr, mi = (0.0, 1e-9, 500)
+    got, info = _gpu_solve(m, rx, V, time_step=dt, use_uniform_laplace=uniform, max_iter=mi, tol_abs=ta, tol_rel=tr,
+                           precondition=True)
+    ref, oinfo = O.mcf_solve(rings, V, dt, uniform, mi, ta, tr, precond=True)
+    assert info["converged"] and oinfo["converged"]
+    assert abs(info["iterations"] - oinfo["iterations"]) <= 2 + oinfo["iterations"] // 10, (info, oinfo)
+    res, bb = O.mcf_residual(rings, V, got, dt, uniform)
+    assert (res ** 2).sum() < 10.0 * (1e-7 * pinfo3["start_residual"] + floor2), (name, uniform, (res ** 2).sum(), floor2)
+    assert np.abs(got - ref).max() < (1e-5 if uniform else 5e-5) * scale, (name, uniform, np.abs(got - ref).max())
+    # fewer iterations than the plain solver needs for the same reduction of ITS residual is not guaranteed in general, but
+    # the two must meet at the solution
+    plain, _ = O.mcf_solve(rings, V, dt, uniform, 1000, 0.0, 1e-12)
+    assert np.abs(got - plain).max() < (1e-5 if uniform else 5e-5) * scale
 
 
 @pytest.mark.gpu

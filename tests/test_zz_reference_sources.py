@@ -72,11 +72,13 @@ def test_reference_mcf_matvec_kernel(refsrc1, name):
     S.test_user_mcf_matvec(refsrc1, name)
 
 
+@pytest.mark.parametrize("pcg", [0, 1])
 @pytest.mark.parametrize("name,uniform", [("sphere3", 0), ("torus40x30", 0), ("dragon", 0), ("sphere3", 1), ("dragon", 1)])
-def test_reference_mcf_cg(refsrc1, name, uniform):
-    """apps/MCF/mcf_kernels.cuh: init_B<float, 256> and matvec<float, 256> (both Laplacians), unmodified, under the drop-in
-    CGMatFreeAttrSolver -- the MCF app's solve -- against the oracle and the fixed-function rxm_mcf_solve"""
-    S.test_user_mcf_cg(refsrc1, name, uniform, kernels_have_uniform=True)
+def test_reference_mcf_cg(refsrc1, name, uniform, pcg):
+    """apps/MCF/mcf_kernels.cuh: init_B<float, 256>, matvec<float, 256> and precond_matvec<float, 256> (both Laplacians),
+    unmodified, under the drop-in CGMatFreeAttrSolver / PCGMatFreeAttrSolver -- the MCF app's two matrix-free solves --
+    against the oracle and the fixed-function rxm_mcf_solve / rxm_mcf_solve_ex"""
+    S.test_user_mcf_cg(refsrc1, name, uniform, pcg, kernels_have_uniform=True)
 
 
 @pytest.mark.parametrize("name", ["sphere3", "dragon"])
