@@ -284,6 +284,10 @@ def test_errors():
     b = m.add_vertex_attribute("n", np.float32, 3, rx.HOST, rx.AoS)
     with pytest.raises(rx.RXMeshError, match="no CPU fallback"):
         m.vertex_normals(a, b)
+    with pytest.raises(rx.RXMeshError, match="no CPU fallback"):
+        m.mcf_solve(a, b)
+    with pytest.raises(rx.RXMeshError, match="no CPU fallback"):
+        m.mcf_solve(a, b, precondition=True)
 
 
 def test_host_attribute_roundtrip_all_layouts():
