@@ -270,7 +270,10 @@ __global__ void __launch_bounds__(MBT) k_mcf_setup(MeshView mv, const float* __r
 // BT: the launcher picks the block size that leaves the fewest idle threads in the last round over the owned vertices
 // (561-vertex tiles: 3 x 192 instead of 256 + 256 + 49).  FIRST: iteration 0, P' = R (beta = 0; P is not read, so the
 // solve needs no zeroed P buffer).
-template <bool UNIFORM, int BT, bool PRECOND>
+// WSTAGE = false (cotangent only): the weights are read from global memory where they are used (a thread's six are 24
+// contiguous bytes, a warp's 768) instead of being staged: 13.5 KB less shared memory per 561-vertex tile, 8 resident blocks
+// instead of 6.
+template <bool UNIFORM, int BT, bool PRECOND, bool WSTAGE = true>
 __global__ void __launch_bounds__(BT, 1536 / BT) k_mcf_matvec(MeshView mv, McfBuffers B, const float* __restrict__ Pold,
                                                    float* __restrict__ Pnew, float dt, int first)
 {
@@ -288,16 +291,17 @@ __global__ void __launch_bounds__(BT, 1536 / BT) k_mcf_matvec(MeshView mv, McfBu
     const uint32_t  nw = (d.fan_total + 3u) & ~3u;  // entries of this patch's slice of W
     Smem            sm(smem_raw);
     const Staged    T    = stage_alloc(sm, d);
-    float*          s_w  = sm.alloc<float>(UNIFORM ? 4u : nw + 4u);
+    float*          s_w  = sm.alloc<float>(UNIFORM || !WSTAGE ? 4u : nw + 4u);
+    const float*    Wg   = UNIFORM ? nullptr : B.W + B.fan_base[blockIdx.x];
     float*          s_dg = sm.alloc<float>(cap + 4u);
     float*          s_p  = sm.alloc<float>(3u * max(nv, cap) + 4u);
     const uint64_t  g    = 3ull * d.slot_base[ELEM_V];
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
-        mbar_arrive_expect_tx(&bar, T.bytes + (UNIFORM ? 0u : 4u * nw) + 4u * cap);
+        mbar_arrive_expect_tx(&bar, T.bytes + (UNIFORM || !WSTAGE ? 0u : 4u * nw) + 4u * cap);
         stage_issue(T, d, blob, &bar);
-        if (!UNIFORM && nw) bulk_g2s(s_w, B.W + B.fan_base[blockIdx.x], 4u * nw, &bar);
+        if (!UNIFORM && WSTAGE && nw) bulk_g2s(s_w, Wg, 4u * nw, &bar);
         if (cap) bulk_g2s(s_dg, B.diag + d.slot_base[ELEM_V], 4u * cap, &bar);
     }
     __syncthreads();  // the barrier object is initialised for everyone who waits on it below
@@ -386,8 +390,14 @@ __global__ void __launch_bounds__(BT, 1536 / BT) k_mcf_matvec(MeshView mv, McfBu
                 const uint32_t  i01 = w32[0], i23 = w32[1], i45 = w32[2];
                 float           w0 = dt, w1 = dt, w2 = dt, w3 = dt, w4 = dt, w5 = dt;
                 if (!UNIFORM) {
-                    const float2* wp = reinterpret_cast<const float2*>(s_w + b);
-                    const float2  a = wp[0], c = wp[1], f = wp[2];
+                    float2 a, c, f;
+                    if (WSTAGE) {
+                        const float2* wp = reinterpret_cast<const float2*>(s_w + b);
+                        a = wp[0], c = wp[1], f = wp[2];
+                    } else {
+                        const float2* wp = reinterpret_cast<const float2*>(Wg + b);
+                        a = __ldg(wp), c = __ldg(wp + 1), f = __ldg(wp + 2);
+                    }
                     w0 = a.x, w1 = a.y, w2 = c.x, w3 = c.y, w4 = f.x, w5 = f.y;
                 }
                 const float *q0 = s_p + 3u * (i01 & 0xFFFFu), *q1 = s_p + 3u * (i01 >> 16), *q2 = s_p + 3u * (i23 & 0xFFFFu),
@@ -400,7 +410,7 @@ __global__ void __launch_bounds__(BT, 1536 / BT) k_mcf_matvec(MeshView mv, McfBu
                 x -= w5 * q5[0], y -= w5 * q5[1], z -= w5 * q5[2];
             } else {
                 for (uint32_t i = b; i < e; ++i) {
-                    const float  w = UNIFORM ? dt : s_w[i];
+                    const float  w = UNIFORM ? dt : (WSTAGE ? s_w[i] : __ldg(Wg + i));
                     const float* q = s_p + 3u * T.fv[i];
                     x -= w * q[0], y -= w * q[1], z -= w * q[2];
                 }
@@ -531,15 +541,15 @@ uint32_t mcf_update_grid()
 }
 
 namespace {
-template <bool U, bool PC>
+template <bool U, bool PC, bool WS = true>
 cudaError_t launch_mv(int bt, const MeshView& mv, const McfBuffers& B, const float* pold, float* pnew, float dt, int first,
                       uint32_t smem, cudaStream_t stream)
 {
     cudaError_t e = cudaSuccess;
 #define RXM_MCF_MV(BTV)                                                                                              \
     do {                                                                                                             \
-        e = mcf_set_smem(k_mcf_matvec<U, BTV, PC>, smem);                                                            \
-        if (e == cudaSuccess) k_mcf_matvec<U, BTV, PC><<<mv.num_patches, BTV, smem, stream>>>(mv, B, pold, pnew, dt, first); \
+        e = mcf_set_smem(k_mcf_matvec<U, BTV, PC, WS>, smem);                                                        \
+        if (e == cudaSuccess) k_mcf_matvec<U, BTV, PC, WS><<<mv.num_patches, BTV, smem, stream>>>(mv, B, pold, pnew, dt, first); \
     } while (0)
     if (bt == 128) RXM_MCF_MV(128);
     else if (bt == 192) RXM_MCF_MV(192);
@@ -577,7 +587,11 @@ cudaError_t launch_mcf_iteration(const MeshView& mv, const KernelLimits& lim, co
                                  const char** err)
 {
     const uint32_t capv = lim.max_owned[ELEM_V] + 4u;
-    const uint32_t smem = staged_smem(lim) + (uniform ? 16u : a16(4u * (lim.max_fan_total + 8u))) + a16(4u * (capv + 4u)) +
+    // cotangent weights: read where they are used (default) or staged in shared memory (RXM_MCF_WSTAGE=1).  10 M-face torus,
+    // mat-vec alone under ncu: staged 95.1 us (32.6 KB per block, 6 resident), global 82.5 us (19.1 KB, 8 resident)
+    static const bool w_staged = [] { const char* f = getenv("RXM_MCF_WSTAGE"); return f ? atoi(f) != 0 : false; }();
+    const bool        ws       = uniform || w_staged;
+    const uint32_t smem = staged_smem(lim) + (uniform || !ws ? 16u : a16(4u * (lim.max_fan_total + 8u))) + a16(4u * (capv + 4u)) +
                           a16(12u * std::max(lim.max_n[ELEM_V], capv) + 16u) + 64u;
     // block size: the fewest idle threads in the last round over a full patch's owned vertices (ties: the larger block)
     int      bt   = 256;
@@ -593,8 +607,10 @@ cudaError_t launch_mcf_iteration(const MeshView& mv, const KernelLimits& lim, co
     cudaError_t  e;
     if (uniform && precond) e = launch_mv<true, true>(bt, mv, B, pold, pnew, dt, first, smem, stream);
     else if (uniform) e = launch_mv<true, false>(bt, mv, B, pold, pnew, dt, first, smem, stream);
-    else if (precond) e = launch_mv<false, true>(bt, mv, B, pold, pnew, dt, first, smem, stream);
-    else e = launch_mv<false, false>(bt, mv, B, pold, pnew, dt, first, smem, stream);
+    else if (precond && ws) e = launch_mv<false, true>(bt, mv, B, pold, pnew, dt, first, smem, stream);
+    else if (precond) e = launch_mv<false, true, false>(bt, mv, B, pold, pnew, dt, first, smem, stream);
+    else if (ws) e = launch_mv<false, false>(bt, mv, B, pold, pnew, dt, first, smem, stream);
+    else e = launch_mv<false, false, false>(bt, mv, B, pold, pnew, dt, first, smem, stream);
     if (e != cudaSuccess) RXM_MCF_FAIL("patch needs more shared memory than 227 KB");
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
