@@ -531,7 +531,8 @@ static int app_mcf_matvec(const uint32_t* fv, uint32_t nf, const float* x, const
 // The MCF app's solve (apps/MCF/mcf_cg_mat_free.h:13-178) as user code: init_B, then CGMatFreeAttrSolver (the drop-in
 // header include/rxmesh/matrix/cg_mat_free_attr_solver.h) driving the matrix-free mat-vec kernel through run_kernel.  With
 // RXM_REFSRC == 1 both kernels are the reference's own (apps/MCF/mcf_kernels.cuh, unmodified, either Laplacian); otherwise the
-// restated cotangent mat-vec above, with B = M X0 taken from a mat-vec at time step 0.  info: iterations, start, final residual.
+// restated cotangent mat-vec above, with B = M X0 taken from a mat-vec at time step 0.  info[4]: iterations, start residual,
+// final residual, milliseconds of pre_solve + solve.
 static int app_mcf_cg(const uint32_t* fv, uint32_t nf, const float* x, uint32_t nv, uint32_t patch_size, float time_step,
                       int uniform, int pcg, int max_iter, float tol_abs, float tol_rel, float* out, float* info)
 {
@@ -581,10 +582,16 @@ static int app_mcf_cg(const uint32_t* fv, uint32_t nf, const float* x, uint32_t 
     else
         sp.reset(new CGMatFreeAttrSolver<float, VertexHandle>(rx, mat_vec, 3, max_iter, tol_abs, tol_rel));
     IterativeSolver<float, VertexAttribute<float>>& solver = *sp;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    cudaEventRecord(e0, NULL);
     solver.pre_solve(*B, *X, NULL);
     solver.solve(*B, *X, NULL);
+    cudaEventRecord(e1, NULL);
     if (cudaDeviceSynchronize() != cudaSuccess) return 1;
     info[0] = (float)solver.iter_taken(), info[1] = solver.start_residual(), info[2] = solver.final_residual();
+    cudaEventElapsedTime(&info[3], e0, e1);  // pre_solve + solve, ms (what the app reports as pre-solve + solve)
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
     X->move(DEVICE, HOST);
     rx.for_each_vertex(HOST, [&](const VertexHandle& vh) {
         for (uint32_t i = 0; i < 3; ++i)

@@ -184,7 +184,7 @@ def test_user_mcf_cg(shim, name, uniform, pcg, kernels_have_uniform=False):
     V, F = make_mesh(name)
     V = np.ascontiguousarray(V, np.float32)
     dt, ta, tr, mi = (10.0, 1e-6, 0.0, 200) if uniform else (1e-2, 0.0, 1e-9, 500)
-    out, info = np.zeros_like(V), np.zeros(3, np.float32)
+    out, info = np.zeros_like(V), np.zeros(4, np.float32)
     if pcg:
         ta, tr = 0.0, 1e-9  # its residual is <R, M^-1 R>: compare solutions at a relative tolerance
     assert shim.shim_mcf_cg(_p(F), F.shape[0], _p(V), V.shape[0], 512, C.c_float(dt), uniform, pcg, mi, C.c_float(ta), C.c_float(tr),
