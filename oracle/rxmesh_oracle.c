@@ -793,8 +793,9 @@ void rxo_mcf_matvec_scaled(const uint32_t* off, const uint32_t* val, uint32_t nv
  * delta' < tol_abs or delta' / delta0 < tol_rel (iterative_solver.h:57-63) -- the converging iteration is not counted --
  * else beta = delta' / delta, P = R + beta P).  float64 from fp32 coordinates; the three coordinates share one alpha / beta
  * (the reference's dot / norm2 run over all attributes).  info: [0] iterations, [1] converged, [2] <R0,R0>, [3] final <R,R>.
- * PARITY: the reference app has no correctness check for the solve; its mat-vec is pinned (tests/test_gpu_shim.py runs the
- * reference's unmodified mcf_kernels.cuh against rxo_mcf_matvec), the solve is pinned by the property A X = B. */
+ * PARITY: the reference app has no correctness check for the solve; pinned to tests/golden/ref_mcf.npz, the solves of the
+ * reference's own init_B / matvec / precond_matvec kernels (compiled unmodified) run on a B200 under the drop-in CG / PCG solver
+ * headers (tests/golden/make_golden_mcf.py), and by the property A X = B. */
 static void rxo_mcf_weights(const uint32_t* off, const uint32_t* val, uint32_t nv, const float* X, double time_step, int uniform,
                             double* W, double* diag, double* mass)
 {

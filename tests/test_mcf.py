@@ -1,7 +1,9 @@
 """Mean-curvature flow by matrix-free CG (apps/MCF/mcf_cg_mat_free.h, matrix/cg_mat_free_attr_solver.h:45-125):
 the oracle's solver on the CPU, and rxm_mcf_solve against it on the GPU.
 
-The reference app has no correctness check for the solve (apps/MCF/mcf.cu), so the solve is pinned by what it must satisfy:
+The reference app has no correctness check for the solve (apps/MCF/mcf.cu), so the solve is pinned by
+  * golden vectors from the reference's own kernels (init_B / matvec / precond_matvec, unmodified) run on a B200 under the
+    drop-in solvers (tests/golden/ref_mcf.npz, test_oracle_vs_reference_kernels_golden), and by what it must satisfy:
   * the mat-vec it iterates is the one the reference's unmodified mcf_kernels.cuh computes (tests/test_gpu_shim.py,
     tests/test_oracle.py::test_mcf_matvec_constant_vector),
   * the result solves (M + dt L) X = M X0: the residual B - A X, evaluated by the float64 oracle, is at the tolerance,
@@ -76,6 +78,33 @@ def test_oracle_jacobi_pcg_solves_the_same_system(name, uniform):
     assert ia["converged"] and ib["converged"] and ib["iterations"] <= ia["iterations"]
     assert np.abs(a - b).max() < 1e-7 * np.abs(V).max()
     assert (res ** 2).sum() < 1e-10 * ia["start_residual"]
+
+
+def test_oracle_vs_reference_kernels_golden():
+    """The pin of the oracle's solve: tests/golden/ref_mcf.npz holds what THE REFERENCE'S OWN kernels (init_B, matvec,
+    precond_matvec of apps/MCF/mcf_kernels.cuh, compiled unmodified) produced on a B200 under the drop-in CG / PCG solvers
+    (tests/golden/make_golden_mcf.py): 3 meshes x 2 Laplacians x 2 solvers.  The float64 oracle reaches the same solution in
+    the same number of iterations (fp32 residual recursion: +-2, +-10 % beyond 20) from the same start residual."""
+    import os
+    from conftest import GOLDEN
+    sys_path = os.path.join(GOLDEN, "make_golden_mcf.py")
+    assert os.path.exists(sys_path)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_mcf", sys_path)
+    G = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(G)
+    gold = np.load(os.path.join(GOLDEN, "ref_mcf.npz"))
+    for name, uni, pcg in G.CASES:
+        V, F = _mesh(name)
+        rings = O.oriented_rings(F, V.shape[0])
+        dt, ta, tr, mi = G.params(uni, pcg)
+        ref, oinfo = O.mcf_solve(rings, V, dt, bool(uni), mi, ta, tr, precond=bool(pcg))
+        key = "%s_%s_%s" % (name, "uniform" if uni else "cotangent", "pcg" if pcg else "cg")
+        X, info = gold[key + "_X"], gold[key + "_info"]
+        assert oinfo["converged"], key
+        assert abs(int(info[0]) - oinfo["iterations"]) <= 2 + oinfo["iterations"] // 10, (key, info, oinfo)
+        assert abs(info[1] - oinfo["start_residual"]) < 2e-3 * oinfo["start_residual"], (key, info, oinfo)
+        assert np.abs(X - ref).max() < (1e-5 if uni else 5e-5) * np.abs(V).max(), (key, np.abs(X - ref).max())
 
 
 def test_oracle_zero_iterations_and_max_iter():
