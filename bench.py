@@ -750,6 +750,10 @@ def run_sub_records(args, rank, world, local_rank, line, subs):
             cfg["2_eight_queries_10m_sphere"] = guarded(lambda: BC.config_queries(torch, rx, stream))
         if want("bilateral"):
             cfg["3_bilateral_10m_torus"] = guarded(lambda: BC.config_bilateral(torch, rx, stream))
+            # the MCF solve on the same mesh (SURVEY.md 8(f)1 taken to its caller) as a record of its own
+            c3 = cfg["3_bilateral_10m_torus"]
+            if isinstance(c3, dict) and isinstance(c3.get("mcf_cg_same_mesh"), dict):
+                cfg["f1_mcf_solve_10m_torus"] = c3.pop("mcf_cg_same_mesh")
         if cfg and line is not None:
             line["configs"] = cfg
         if want("hardwired") and line is not None and isinstance(line.get("reference_gpu"), dict):
